@@ -1,0 +1,304 @@
+"""Python view of the `lgrngn` particle-system API (ctypes over bindings/lgrngn_capi.h).
+
+Mirrors what the reference's Boost.Python module offers (reference bindings/python/lib.cpp:217-434):
+`opts_init_t`, `opts_t`, the enums, `factory(backend, opts_init)` and a particles object with `init`,
+`step_sync`, `step_async`, `diag_*`, `outbuf`.  numpy arrays stand in for `arrinfo_t` (C order, dimension
+order x[,y],z).  The class is parametrised by the shared library it drives, so the parity tests can point
+the very same calls at the reference build (oracle/_ref) - the product never does.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+MAX_MODES, MAX_DISTROS, MAX_KPARAMS = 4, 4, 4
+
+
+class backend_t:
+    undefined, serial, OpenMP, CUDA, multi_CUDA = range(5)
+
+
+class kernel_t:
+    (undefined, geometric, golovin, hall, hall_davis_no_waals, Long, onishi_hall, onishi_hall_davis_no_waals,
+     hall_pinsky_1000mb_grav, hall_pinsky_cumulonimbus, hall_pinsky_stratocumulus, vohl_davis_no_waals) = range(12)
+
+
+class vt_t:
+    undefined, beard76, beard77, beard77fast, khvorostyanov_spherical, khvorostyanov_nonspherical = range(6)
+
+
+class as_t:
+    undefined, implicit, euler, pred_corr = range(4)
+
+
+class RH_formula_t:
+    pv_cc, rv_cc, pv_tet, rv_tet = range(4)
+
+
+class _Distro(C.Structure):
+    _fields_ = [("kind", C.c_int), ("kappa", C.c_double), ("rd_insol", C.c_double), ("n_modes", C.c_int),
+                ("mean_r", C.c_double * MAX_MODES), ("stdev", C.c_double * MAX_MODES), ("n_tot", C.c_double * MAX_MODES),
+                ("r0", C.c_double), ("n0", C.c_double)]
+
+
+class _OptsInit(C.Structure):
+    _fields_ = [("backend", C.c_int), ("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int),
+                ("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double), ("dt", C.c_double),
+                ("sstp_cond", C.c_int), ("sstp_coal", C.c_int),
+                ("x0", C.c_double), ("y0", C.c_double), ("z0", C.c_double),
+                ("x1", C.c_double), ("y1", C.c_double), ("z1", C.c_double),
+                ("sd_conc", C.c_ulonglong), ("sd_const_multi", C.c_ulonglong), ("n_sd_max", C.c_ulonglong),
+                ("kernel", C.c_int), ("terminal_velocity", C.c_int), ("adve_scheme", C.c_int), ("RH_formula", C.c_int),
+                ("n_kernel_parameters", C.c_int), ("kernel_parameters", C.c_double * MAX_KPARAMS),
+                ("coal_switch", C.c_int), ("sedi_switch", C.c_int), ("subs_switch", C.c_int), ("exact_sstp_cond", C.c_int),
+                ("turb_adve_switch", C.c_int), ("turb_cond_switch", C.c_int), ("turb_coal_switch", C.c_int),
+                ("ice_switch", C.c_int), ("chem_switch", C.c_int),
+                ("RH_max", C.c_double),
+                ("rng_seed", C.c_int), ("rng_seed_init", C.c_int), ("rng_seed_init_switch", C.c_int),
+                ("dev_count", C.c_int), ("dev_id", C.c_int),
+                ("rd_min", C.c_double), ("rd_max", C.c_double),
+                ("open_side_walls", C.c_int), ("periodic_topbot_walls", C.c_int), ("variable_dt_switch", C.c_int),
+                ("th_dry", C.c_int), ("const_p", C.c_int), ("aerosol_independent_of_rhod", C.c_int),
+                ("n_distros", C.c_int), ("distros", _Distro * MAX_DISTROS),
+                ("n_w_LS", C.c_int), ("w_LS", C.POINTER(C.c_double))]
+
+
+class _Opts(C.Structure):
+    _fields_ = [("adve", C.c_int), ("sedi", C.c_int), ("subs", C.c_int), ("cond", C.c_int), ("coal", C.c_int),
+                ("rcyc", C.c_int), ("RH_max", C.c_double), ("dt", C.c_double)]
+
+
+class _Arr(C.Structure):
+    _fields_ = [("data", C.POINTER(C.c_double)), ("strides", C.c_long * 3)]
+
+
+DIAG = {name: i for i, name in enumerate([
+    "all", "rw_ge_rc", "RH_ge_Sc", "dry_rng", "wet_rng", "kappa_rng", "dry_rng_cons", "wet_rng_cons",
+    "kappa_rng_cons", "water", "water_cons", "sd_conc", "pressure", "temperature", "RH", "dry_mom", "wet_mom",
+    "kappa_mom", "precip_rate", "max_rw", "vel_div", "wet_mass_dens"])}
+
+PUDDLE_KEYS = ["HNO3", "NH3", "CO2", "SO2", "H2O2", "O3", "S_VI", "H", "liquid_volume", "dry_volume",
+               "particle_number", "ice_mass", "liquid_number", "ice_number"]
+
+
+def lognormal(kappa, modes, rd_insol=0.0):
+    """dry spectrum: sum of lognormal modes [(mean_r [m], geometric stdev, n_tot [m^-3]), ...]"""
+    return {"kind": 0, "kappa": kappa, "rd_insol": rd_insol, "modes": list(modes)}
+
+
+def expvolume(kappa, r0, n0, rd_insol=0.0):
+    """dry spectrum exponential in volume (Shima et al. 2009): n0 * 3 (r/r0)^3 exp(-(r/r0)^3)"""
+    return {"kind": 1, "kappa": kappa, "rd_insol": rd_insol, "r0": r0, "n0": n0}
+
+
+class Library:
+    """One loaded implementation of the flat binding (the B200 back-end or, in tests, the reference)."""
+
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise OSError("shared library not found: %s (run `python -c 'import __graft_entry__ as g; g.build()'`)" % path)
+        self.path = path
+        self.lib = lib = C.CDLL(path, mode=C.RTLD_LOCAL)
+        P = C.POINTER
+        lib.lgc_last_error.restype = C.c_char_p
+        lib.lgc_impl_name.restype = C.c_char_p
+        lib.lgc_opts_init_defaults.argtypes = [P(_OptsInit)]
+        lib.lgc_opts_defaults.argtypes = [P(_Opts)]
+        lib.lgc_create.argtypes = [P(_OptsInit), P(C.c_void_p)]
+        lib.lgc_destroy.argtypes = [C.c_void_p]
+        lib.lgc_init.argtypes = [C.c_void_p] + [P(_Arr)] * 7
+        lib.lgc_step_sync.argtypes = [C.c_void_p, P(_Opts)] + [P(_Arr)] * 6
+        lib.lgc_sync_in.argtypes = [C.c_void_p] + [P(_Arr)] * 6
+        lib.lgc_step_cond.argtypes = [C.c_void_p, P(_Opts)] + [P(_Arr)] * 2
+        lib.lgc_step_async.argtypes = [C.c_void_p, P(_Opts)]
+        lib.lgc_diag.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
+        lib.lgc_n_cell.argtypes = [C.c_void_p]
+        lib.lgc_n_cell.restype = C.c_long
+        lib.lgc_outbuf.argtypes = [C.c_void_p, P(C.c_double), C.c_long]
+        lib.lgc_get_attr.argtypes = [C.c_void_p, C.c_char_p, P(C.c_double), C.c_long, P(C.c_long)]
+        lib.lgc_get_n.argtypes = [C.c_void_p, P(C.c_ulonglong), C.c_long, P(C.c_long)]
+        lib.lgc_puddle.argtypes = [C.c_void_p, P(C.c_double)]
+        self.name = lib.lgc_impl_name().decode()
+
+    def check(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.lib.lgc_last_error().decode())
+
+    # ---- API objects -------------------------------------------------------------------------------
+    def opts_init_t(self):
+        return OptsInit(self)
+
+    def opts_t(self):
+        return Opts(self)
+
+    def factory(self, backend, opts_init):
+        return Particles(self, backend, opts_init)
+
+
+class OptsInit:
+    """attribute bag with the defaults of opts_init_t (reference lgrngn/opts_init.hpp:194-249)"""
+
+    def __init__(self, library):
+        c = _OptsInit()
+        library.lib.lgc_opts_init_defaults(C.byref(c))
+        for name, _ in _OptsInit._fields_:
+            if name in ("distros", "n_distros", "w_LS", "n_w_LS", "kernel_parameters", "n_kernel_parameters", "backend"):
+                continue
+            setattr(self, name, getattr(c, name))
+        self.kernel_parameters = []
+        self.dry_distros = []      # list of lognormal(...) / expvolume(...)
+        self.w_LS = []
+
+    def _pack(self, backend):
+        c = _OptsInit()
+        c.backend = int(backend)
+        for name, _ in _OptsInit._fields_:
+            if name in ("distros", "n_distros", "w_LS", "n_w_LS", "kernel_parameters", "n_kernel_parameters", "backend"):
+                continue
+            setattr(c, name, getattr(self, name))
+        kp = list(self.kernel_parameters)
+        c.n_kernel_parameters = len(kp)
+        for i, v in enumerate(kp):
+            c.kernel_parameters[i] = float(v)
+        c.n_distros = len(self.dry_distros)
+        for i, d in enumerate(self.dry_distros):
+            cd = c.distros[i]
+            cd.kind, cd.kappa, cd.rd_insol = d["kind"], d["kappa"], d.get("rd_insol", 0.0)
+            if d["kind"] == 0:
+                cd.n_modes = len(d["modes"])
+                for m, (mean_r, stdev, n_tot) in enumerate(d["modes"]):
+                    cd.mean_r[m], cd.stdev[m], cd.n_tot[m] = mean_r, stdev, n_tot
+            else:
+                cd.r0, cd.n0 = d["r0"], d["n0"]
+        keep = None
+        if len(self.w_LS):
+            keep = np.ascontiguousarray(self.w_LS, dtype=np.float64)
+            c.n_w_LS = keep.size
+            c.w_LS = keep.ctypes.data_as(C.POINTER(C.c_double))
+        return c, keep
+
+
+class Opts:
+    def __init__(self, library):
+        c = _Opts()
+        library.lib.lgc_opts_defaults(C.byref(c))
+        for name, _ in _Opts._fields_:
+            setattr(self, name, getattr(c, name))
+
+    def _pack(self):
+        c = _Opts()
+        for name, _ in _Opts._fields_:
+            setattr(c, name, getattr(self, name))
+        return c
+
+
+def _arr(a):
+    """numpy array (float64, any strides that are multiples of 8 B) -> lgc_arr; None -> NULL"""
+    if a is None:
+        return None
+    assert a.dtype == np.float64, "Eulerian fields must be float64"
+    c = _Arr()
+    c.data = a.ctypes.data_as(C.POINTER(C.c_double))
+    st = [s // a.itemsize for s in a.strides] if a.ndim else []
+    while len(st) < 3:
+        st.append(1)
+    for i in range(3):
+        c.strides[i] = st[i]
+    return C.byref(c)
+
+
+class Particles:
+    def __init__(self, library, backend, opts_init):
+        self._L = library
+        self._lib = library.lib
+        c, keep = opts_init._pack(backend)
+        h = C.c_void_p()
+        library.check(self._lib.lgc_create(C.byref(c), C.byref(h)))
+        self._h = h
+        self.n_cell = self._lib.lgc_n_cell(h)
+        self._cap = int(opts_init.n_sd_max) + 16
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.lgc_destroy(h)
+            self._h = None
+
+    def init(self, th, rv, rhod, p=None, Cx=None, Cy=None, Cz=None):
+        self._L.check(self._lib.lgc_init(self._h, _arr(th), _arr(rv), _arr(rhod), _arr(p), _arr(Cx), _arr(Cy), _arr(Cz)))
+
+    def step_sync(self, opts, th, rv, rhod=None, Cx=None, Cy=None, Cz=None):
+        o = opts._pack()
+        self._L.check(self._lib.lgc_step_sync(self._h, C.byref(o), _arr(th), _arr(rv), _arr(rhod), _arr(Cx), _arr(Cy), _arr(Cz)))
+
+    def sync_in(self, th, rv, rhod=None, Cx=None, Cy=None, Cz=None):
+        self._L.check(self._lib.lgc_sync_in(self._h, _arr(th), _arr(rv), _arr(rhod), _arr(Cx), _arr(Cy), _arr(Cz)))
+
+    def step_cond(self, opts, th, rv):
+        o = opts._pack()
+        self._L.check(self._lib.lgc_step_cond(self._h, C.byref(o), _arr(th), _arr(rv)))
+
+    def step_async(self, opts):
+        o = opts._pack()
+        self._L.check(self._lib.lgc_step_async(self._h, C.byref(o)))
+
+    def _diag(self, what, a=0.0, b=0.0):
+        self._L.check(self._lib.lgc_diag(self._h, DIAG[what], float(a), float(b)))
+
+    def outbuf(self):
+        out = np.empty(self.n_cell, dtype=np.float64)
+        self._L.check(self._lib.lgc_outbuf(self._h, out.ctypes.data_as(C.POINTER(C.c_double)), out.size))
+        return out
+
+    def get_attr(self, name):
+        buf = np.empty(self._cap, dtype=np.float64)
+        n = C.c_long()
+        self._L.check(self._lib.lgc_get_attr(self._h, name.encode(), buf.ctypes.data_as(C.POINTER(C.c_double)), buf.size, C.byref(n)))
+        return buf[:n.value].copy()
+
+    def get_n(self):
+        buf = np.empty(self._cap, dtype=np.uint64)
+        n = C.c_long()
+        self._L.check(self._lib.lgc_get_n(self._h, buf.ctypes.data_as(C.POINTER(C.c_ulonglong)), buf.size, C.byref(n)))
+        return buf[:n.value].copy()
+
+    def diag_puddle(self):
+        out = (C.c_double * 14)()
+        self._L.check(self._lib.lgc_puddle(self._h, out))
+        return dict(zip(PUDDLE_KEYS, list(out)))
+
+
+def _add_diag(name, nargs):
+    if nargs == 0:
+        def f(self):
+            self._diag(name)
+    elif nargs == 1:
+        def f(self, k):
+            self._diag(name, k)
+    else:
+        def f(self, a, b):
+            self._diag(name, a, b)
+    f.__name__ = "diag_" + name
+    setattr(Particles, "diag_" + name, f)
+
+
+for _n in ("all", "rw_ge_rc", "RH_ge_Sc", "water", "water_cons", "sd_conc", "pressure", "temperature", "RH",
+           "precip_rate", "max_rw", "vel_div"):
+    _add_diag(_n, 0)
+for _n in ("dry_mom", "wet_mom", "kappa_mom"):
+    _add_diag(_n, 1)
+for _n in ("dry_rng", "wet_rng", "kappa_rng", "dry_rng_cons", "wet_rng_cons", "kappa_rng_cons", "wet_mass_dens"):
+    _add_diag(_n, 2)
+
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+B200_LIB_PATH = os.path.join(_HERE, "lib", "liblgrngn_b200.so")
+_b200 = None
+
+
+def b200():
+    """the B200-native back-end (hand-written CUDA behind the lgrngn API); fails loudly if it is not built"""
+    global _b200
+    if _b200 is None:
+        _b200 = Library(B200_LIB_PATH)
+    return _b200

@@ -1,0 +1,2 @@
+// empty stand-in (oracle build only)
+#pragma once
