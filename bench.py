@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""Headline benchmark: super-droplet updates per second of the full cond + coal + sedi + adve step.
+
+Workload (BASELINE.json configs[3], one x-slab of it per GPU = weak scaling): 3-D LES-like box, 64 x 256 x 128 cells
+per GPU (512 x 256 x 128 on 8 GPUs), 40 super-droplets per cell (8.4e7 per GPU), Hall/Davis coalescence kernel,
+beard77fast fall speeds, implicit advection with Cx = 0.1, Cy = 0.05, two-mode lognormal aerosol, supersaturated
+upper half.  Double precision.  A "step" is one step_sync + step_async of every live super-droplet.
+
+  value  - device-timed (CUDA events on the engine's stream, max over ranks) throughput with the Eulerian fields resident
+           in HBM (lgrngn_b200_step_resident);
+  e2e    - the same step through the reference-facing API (step_sync / step_async with HOST arrays: per step th, rv, rhod
+           and three Courant fields go host->device from pinned memory, th and rv come back), wall clock incl. copies;
+  roofline - dominant kernel from the live per-kernel CUDA-event profile; achieved = algorithmic bytes / mean duration;
+  cpu_baseline - the reference's own OpenMP back-end (oracle/_ref, built from the unmodified reference sources) on a
+           scaled-down box of the same shape, on this machine's host cores.
+
+`--impl reference` times only that CPU reference arm and prints it in the same format.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+A_FULL_BYTES = 192.0          # algorithmic bytes per SD-update, full step, double
+KERNEL_BYTES = {              # algorithmic bytes per SD per launch of the individual kernels
+    "k_cond": 52.0, "k_coal_small": 76.0, "k_coal_big": 76.0, "k_transport": 64.0, "k_gather": 136.0,
+    "k_radix_scatter": 16.0, "k_radix_hist": 4.0, "(k_cell_reduce_small<Term, IS_MAX>)": 20.0,
+    "k_vterm": 24.0, "k_make_keys": 40.0,
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def result(self):
+        self.stop_flag = True
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def pinned(shape):
+    import torch
+    return torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
+
+
+def make_case(lib, nx, ny, nz, sd_conc, n_sd_max_factor=1.25, pin=False, rank=0, size=1):
+    from libcloudphxx_b200 import lgrngn as L
+    from tests import support as S
+    alloc = pinned if pin else (lambda s: np.empty(s, dtype=np.float64))
+    oi = lib.opts_init_t()
+    oi.nx, oi.ny, oi.nz = nx, ny, nz
+    oi.dx = oi.dy = oi.dz = 20.0
+    oi.x1, oi.y1, oi.z1 = nx * 20.0, ny * 20.0, nz * 20.0
+    oi.dt = 1.0
+    oi.sd_conc = sd_conc
+    oi.n_sd_max = int(nx * ny * nz * sd_conc * n_sd_max_factor)
+    oi.kernel = L.kernel_t.hall_davis_no_waals
+    oi.terminal_velocity = L.vt_t.beard77fast
+    oi.adve_scheme = L.as_t.implicit
+    oi.rng_seed = 44 + rank
+    oi.dry_distros = [L.lognormal(0.61, S.AEROSOL_ICICLE)]
+    th_dry, rhod_col, _ = S.hydrostatic_column(nz, 20.0)
+    f = {"th": alloc((nx, ny, nz)), "rv": alloc((nx, ny, nz)), "rhod": alloc((nx, ny, nz)),
+         "Cx": alloc((nx + 1, ny, nz)), "Cy": alloc((nx, ny + 1, nz)), "Cz": alloc((nx, ny, nz + 1))}
+    f["th"][:] = th_dry
+    f["rv"][:] = 6e-3
+    f["rv"][:, :, nz // 2:] = 8.2e-3
+    f["rhod"][:] = rhod_col
+    f["Cx"][:] = 0.1
+    f["Cy"][:] = 0.05
+    f["Cz"][:] = 0.0
+    return oi, lib.opts_t(), f
+
+
+def api_step(p, o, f):
+    p.step_sync(o, f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"])
+    p.step_async(o)
+
+
+def run_reference(args):
+    """CPU reference arm: the reference's OpenMP back-end (unmodified sources, oracle/_ref) on the host cores"""
+    from libcloudphxx_b200 import lgrngn as L
+    from tests import support as S
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    ref = S.oracle_library()
+    nx, ny, nz = args.ref_nx, args.ref_ny, args.ref_nz
+    oi, o, f = make_case(ref, nx, ny, nz, args.sd_conc)
+    p = ref.factory(L.backend_t.OpenMP, oi)
+    p.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
+    n_sd = nx * ny * nz * args.sd_conc
+    for _ in range(args.warmup):
+        api_step(p, o, f)
+    t0 = time.time()
+    for _ in range(args.steps):
+        api_step(p, o, f)
+    dt = time.time() - t0
+    v = n_sd * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "super-droplet updates/s (cond+coal+sedi+adve step)", "value": v, "unit": "SD-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg4-shaped 3-D box %dx%dx%d cells x %d SD/cell (bounded sample of the 64x256x128 slab), hall_davis_no_waals, beard77fast, implicit adve" % (nx, ny, nz, args.sd_conc)},
+        "cpu_baseline": {"value": v, "unit": "SD-updates/s", "cores": cores, "kind": "reference",
+                         "sample": "%dx%dx%d cells x %d SD/cell = %.3g SDs, %d steps, reference OpenMP back-end (-O2)" % (nx, ny, nz, args.sd_conc, n_sd, args.steps)},
+        "e2e": {"value": v, "unit": "SD-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    from libcloudphxx_b200 import lgrngn as L, distributed as D
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = L.b200()
+    lib.lib.lgrngn_b200_set_rng_mode.argtypes = [C.c_int]
+    lib.lib.lgrngn_b200_set_rng_mode(0)            # Philox in the kernels (the parity tests use the mt19937 replay)
+    nx, ny, nz = args.nx, args.ny, args.nz
+    if world > 1:
+        D.configure(lib, rank, world, lft_x1=nx * 20.0, rgt_x0=0.0, n_x_tot=nx * world)
+    oi, o, f = make_case(lib, nx, ny, nz, args.sd_conc, pin=True, rank=rank, size=world)
+    oi.dev_id = local
+    t0 = time.time()
+    p = lib.factory(L.backend_t.CUDA, oi)
+    p.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
+    t_init = time.time() - t0
+    eng = D.engine_of(lib, p)
+    xch = D.SlabExchange(lib, p, rank, world) if world > 1 else None
+    lib.lib.lgc_proto.restype = C.c_void_p
+    lib.lib.lgc_proto.argtypes = [C.c_void_p]
+    lib.lib.lgrngn_b200_step_resident.argtypes = [C.c_void_p, C.c_int]
+    proto = lib.lib.lgc_proto(p._h)
+
+    def resident_step():
+        if lib.lib.lgrngn_b200_step_resident(proto, 0b1111) != 0:
+            raise RuntimeError("resident step failed")
+        if xch:
+            xch.finish_step()
+
+    def host_step():
+        api_step(p, o, f)
+        if xch:
+            xch.finish_step()
+
+    def barrier():
+        eng.sync()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+
+    def reduce_max(x):
+        if not dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(x):
+        if not dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # the first API step uploads the fields; afterwards they are resident
+    host_step()
+    for _ in range(max(args.warmup - 1, 0)):
+        resident_step()
+
+    # ---- device-resident throughput --------------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    l0 = eng.launches()
+    updates = 0
+    eng.timer_start()
+    tw = time.time()
+    for _ in range(args.steps):
+        updates += eng.n_part()
+        resident_step()
+    ms = eng.timer_stop()
+    barrier()
+    wall_ms = 1e3 * (time.time() - tw)
+    launches = eng.launches() - l0
+    clocks = sampler.result()
+    ms = reduce_max(ms)
+    total_updates = reduce_sum(float(updates))
+    value = total_updates / (ms * 1e-3)
+
+    # ---- end to end through the API with host arrays ----------------------------------------------------------------
+    barrier()
+    upd2 = 0
+    t0 = time.time()
+    for _ in range(args.steps):
+        upd2 += eng.n_part()
+        host_step()
+    barrier()
+    e2e_s = reduce_max(time.time() - t0)
+    e2e_value = reduce_sum(float(upd2)) / e2e_s
+    h2d = sum(f[k].nbytes for k in ("th", "rv", "rhod", "Cx", "Cy", "Cz"))
+    d2h = f["th"].nbytes + f["rv"].nbytes
+
+    # ---- per-kernel profile (events around every launch) ----------------------------------------------------------
+    roofline = None
+    prof_table = None
+    if rank == 0:
+        n_live = eng.n_part()
+        eng.profile(True)
+        for _ in range(args.profile_steps):
+            resident_step() if not xch else None
+        rep = eng.profile_report() if not xch else {}
+        eng.profile(False)
+        if rep:
+            tot = sum(ms_ for _, ms_ in rep.values())
+            prof_table = {k: {"launches": n, "ms": round(ms_, 3), "share": round(ms_ / tot, 4)} for k, (n, ms_) in sorted(rep.items(), key=lambda kv: -kv[1][1])}
+            top = max(rep.items(), key=lambda kv: kv[1][1])
+            name, (n_l, t_ms) = top
+            per_sd = KERNEL_BYTES.get(name, 0.0)
+            peak, src = peaks()
+            achieved = per_sd * n_live / (t_ms / n_l * 1e-3) / 1e9 if per_sd else None
+            roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "peak_source": src, "unit": "GB/s",
+                        "frac": (achieved / peak) if achieved else None, "traffic": None,
+                        "algorithmic_bytes_per_sd": per_sd, "sd_per_launch": n_live, "mean_launch_ms": t_ms / n_l,
+                        "step_frac_of_hbm_roofline": value * A_FULL_BYTES / (world * peak * 1e9)}
+
+    # ---- CPU baseline beside it (rank 0, N = 1) -----------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1"],
+                                 capture_output=True, text=True, timeout=900)
+            cpu = json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+        except Exception as ex:      # the baseline is informative; its absence must not hide the GPU number
+            cpu = {"value": None, "unit": "SD-updates/s", "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %r" % (ex,)}
+
+    if rank == 0:
+        n_cell, max_count = eng.cell_stats()
+        line = {
+            "metric": "super-droplet updates/s (cond+coal+sedi+adve step)", "value": value, "unit": "SD-updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg4 x-slab per GPU: %dx%dx%d cells x %d SD/cell, hall_davis_no_waals, beard77fast, implicit adve, sstp 1/1" % (nx, ny, nz, args.sd_conc),
+                       "sd_per_gpu": nx * ny * nz * args.sd_conc, "global_cells": [nx * world, ny, nz], "rng": "philox4x32-10",
+                       "l2": "inputs_exceed_l2 (%.1f GB of SD state per GPU)" % (nx * ny * nz * args.sd_conc * 76 / 1e9),
+                       "init_s": round(t_init, 2), "max_sd_per_cell": max_count, "wall_ms_per_step": wall_ms / args.steps},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "SD-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "kernels": prof_table,
+        }
+        print(json.dumps(line), flush=True)
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nx", type=int, default=64)
+    ap.add_argument("--ny", type=int, default=256)
+    ap.add_argument("--nz", type=int, default=128)
+    ap.add_argument("--sd-conc", type=int, default=40)
+    ap.add_argument("--ref-nx", type=int, default=32)
+    ap.add_argument("--ref-ny", type=int, default=32)
+    ap.add_argument("--ref-nz", type=int, default=32)
+    ap.add_argument("--profile-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,192 @@
+/* lcx_b200.h - C ABI of the B200-native super-droplet engine (liblcx_b200.so).
+ *
+ * One `lcx_engine` owns the super-droplets (SDs) and Eulerian cell fields of ONE x-slab on ONE GPU and
+ * exposes the passes of libcloudph++'s Lagrangian hot path as plain C calls: POD arguments, raw
+ * pointers and sizes, `int` status (0 = ok, message via lcx_last_error()).  No C++ types, exceptions,
+ * Thrust or torch types cross this boundary.  The C++ host layer (libcloudphxx_b200/host) implements
+ * the reference's `lgrngn::particles_t<real_t, CUDA | multi_CUDA>` state machine on top of it; any other
+ * host language can bind the same symbols.
+ *
+ * Every entry point names the reference routine whose effect it reproduces (paths relative to the
+ * reference repository root).  All work is enqueued on the engine's own CUDA stream; calls that return
+ * data to the host synchronise that stream.  There is no CPU fallback: every pass is a hand-written
+ * sm_100a kernel and creation fails if no CUDA device is usable.
+ *
+ * Layout in HBM: structure-of-arrays, physically grouped by grid cell after every lcx_post_copy
+ * (so per-cell segments are contiguous); the reference's storage index of each SD is carried as `sid`
+ * and is what orders ties, random-stream look-ups and lcx_get_attr output.
+ */
+#ifndef LCX_B200_H
+#define LCX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lcx_engine lcx_engine;
+
+/* x-boundary handling of this slab (reference src/detail/bcond.hpp:9-15) */
+enum lcx_bcond_t { LCX_BCOND_SHAREDMEM = 0, LCX_BCOND_DISTMEM = 1, LCX_BCOND_OPEN = 3 };
+
+/* per-cell fields addressable through lcx_cells_set / lcx_cells_get */
+enum lcx_field_t
+{
+  LCX_F_TH = 0, LCX_F_RV, LCX_F_RHOD, LCX_F_P, LCX_F_COURANT_X, LCX_F_COURANT_Y, LCX_F_COURANT_Z,
+  LCX_F_T, LCX_F_RH, LCX_F_ETA, LCX_F_DV, LCX_F_W_LS, LCX_F_MOM, LCX_F_COUNT
+};
+
+/* per-SD attributes */
+enum lcx_attr_t
+{
+  LCX_A_RD3 = 0, LCX_A_RW2, LCX_A_KPA, LCX_A_VT, LCX_A_X, LCX_A_Y, LCX_A_Z, LCX_A_N, LCX_A_SID, LCX_A_IJK, LCX_A_COUNT
+};
+
+/* selectors (reference src/impl/diagnose_SD_attributes/particles_impl_moms.ipp:50-234) */
+enum lcx_select_t
+{
+  LCX_SEL_ALL = 0,      /* moms_all                                  */
+  LCX_SEL_RANGE,        /* moms_rng: lo <= attr < hi                 */
+  LCX_SEL_GT0,          /* moms_gt0: attr > 0                        */
+  LCX_SEL_RW_GE_RC,     /* moms_cmp(rw2, rc2): activated droplets    */
+  LCX_SEL_RH_GE_SC      /* moms_ge0(RH - S_crit)                     */
+};
+
+/* source of the uniform random numbers consumed by coalescence */
+enum lcx_rng_mode_t
+{
+  LCX_RNG_INJECT = 0,   /* caller supplies un[n_part] (by storage index) and u01[n_part] (by sorted position) */
+  LCX_RNG_PHILOX = 1    /* counter-based Philox4x32-10 evaluated in the kernels                               */
+};
+
+typedef struct
+{
+  int device;                 /* CUDA device ordinal (-1: current)                                            */
+  int real_bytes;             /* 8 = double (4 = float reserved)                                              */
+  int nx, ny, nz;             /* cells of THIS slab (0 = dimension absent)                                    */
+  double dx, dy, dz;
+  double x0, y0, z0, x1, y1, z1;      /* Lagrangian domain of this slab, slab-local coordinates                */
+  uint64_t n_sd_max;          /* capacity                                                                     */
+  int kernel;                 /* kernel_t ordinal                                                             */
+  int terminal_velocity;      /* vt_t ordinal                                                                 */
+  int adve_scheme;            /* as_t ordinal                                                                 */
+  int RH_formula;             /* RH_formula_t ordinal                                                         */
+  int th_dry, const_p;
+  int n_kernel_user_params;
+  double kernel_user_params[4];
+  double kernel_r_max;        /* largest tabulated radius [um] of an efficiency table                         */
+  int open_side_walls, periodic_topbot_walls;
+  int bcond_lft, bcond_rgt;   /* lcx_bcond_t                                                                  */
+  double lft_x1, rgt_x0;      /* x1 of the left neighbour / x0 of the right neighbour (distmem)               */
+  int multi_kappa;            /* more than one (kappa) species: kappa is mixed on coalescence                 */
+  int pure_const_multi;       /* constant-multiplicity run: report probabilities >= 1                         */
+  int allow_sstp_cond;        /* keep old rv/th/rhod for per-cell condensation sub-stepping                   */
+} lcx_config;
+
+typedef struct
+{
+  int mode;                   /* lcx_rng_mode_t                                                               */
+  const uint32_t *un;         /* INJECT: host array, n_part entries, indexed by storage index (sid)           */
+  const void *u01;            /* INJECT: host array of real, n_part entries, indexed by sorted position       */
+  uint64_t seed, call;        /* PHILOX: key and per-call counter                                             */
+} lcx_rng;
+
+typedef struct
+{
+  int adve, sedi, subs;       /* processes to apply in lcx_transport                                          */
+  int adve_scheme;            /* as_t actually used this step (pred_corr may fall back to euler)              */
+  double dt;
+} lcx_transport_opts;
+
+/* ---- life cycle ---------------------------------------------------------------------------------- */
+const char *lcx_last_error(void);
+const char *lcx_version(void);
+int  lcx_device_count(void);
+int  lcx_create(const lcx_config *cfg, lcx_engine **out);       /* src/impl/particles_impl.ipp:327-544       */
+int  lcx_destroy(lcx_engine *e);
+int  lcx_sync(lcx_engine *e);                                   /* wait for the engine's stream              */
+void *lcx_stream(lcx_engine *e);                                /* cudaStream_t of the engine                 */
+
+/* ---- Eulerian cell fields (consecutive, z fastest; Courant fields staggered + x-halo) -------------- */
+int  lcx_field_size(lcx_engine *e, int field, int64_t *count);  /* init_sync.ipp:13-52                       */
+int  lcx_cells_set(lcx_engine *e, int field, const void *src, int64_t count, int src_on_device);  /* impl_sync.ipp:15-40 */
+int  lcx_cells_get(lcx_engine *e, int field, void *dst, int64_t count);                            /* impl_sync.ipp:42-68 */
+int  lcx_set_vt0_table(lcx_engine *e, const void *table, int n);            /* init_vterm.ipp:36-59          */
+int  lcx_set_efficiencies(lcx_engine *e, const void *table, int64_t n);     /* init_kernel.ipp:60-145        */
+
+/* ---- super-droplets -------------------------------------------------------------------------------- */
+/* append `count` SDs (host arrays; absent dimensions may be NULL); vt := invalid; sid continues      */
+int  lcx_sd_append(lcx_engine *e, int64_t count, const uint64_t *n, const void *rd3, const void *rw2,
+                   const void *kpa, const void *x, const void *y, const void *z, const uint32_t *ijk);
+int  lcx_n_part(lcx_engine *e, int64_t *n_part);
+/* copy one attribute to the host in reference storage order (sid); n is converted to real           */
+int  lcx_get_attr(lcx_engine *e, int attr, void *dst, int64_t cap, int64_t *n_out);   /* fill_outbuf.ipp:40-79 */
+int  lcx_get_attr_u64(lcx_engine *e, int attr, uint64_t *dst, int64_t cap, int64_t *n_out);
+
+/* ---- housekeeping passes ------------------------------------------------------------------------------ */
+int  lcx_hskpng_Tpr(lcx_engine *e);                             /* hskpng_Tpr.ipp:219-305                    */
+int  lcx_hskpng_mfp(lcx_engine *e);                             /* hskpng_mfp.ipp:42-52                      */
+int  lcx_hskpng_vterm(lcx_engine *e, int only_invalid);         /* hskpng_vterm.ipp:185-342                  */
+int  lcx_sstp_percell_step(lcx_engine *e, int step, int sstp_cond, int var_rho);   /* sstp_percell_step.ipp:7-47 */
+int  lcx_sstp_save(lcx_engine *e);                              /* sstp_save.ipp:7-29                        */
+
+/* ---- condensation (per-cell sub-stepping path) ---------------------------------------------------------- */
+/* one sub-step: [step 0: 3rd wet moment before], implicit-Euler growth of every liquid SD, 3rd wet   */
+/* moment after; leaves the per-cell moment change for lcx_update_th_rv                              */
+int  lcx_cond(lcx_engine *e, double dt_sub, double RH_max, int step, int sstp_cond);   /* percell/particles_impl_cond.ipp:13-139 */
+int  lcx_update_th_rv(lcx_engine *e);                           /* common/particles_impl_update_th_rv.ipp:74-191 */
+
+/* ---- coalescence --------------------------------------------------------------------------------------- */
+/* per-cell random pairing + SDM Monte-Carlo collisions for one sub-step                              */
+int  lcx_coal(lcx_engine *e, double dt_sub, const lcx_rng *rng);          /* coalescence/particles_impl_coal.ipp:273-546 */
+int  lcx_coal_flag(lcx_engine *e, int *increase_sstp_coal);               /* particles_step.ipp:396-400      */
+int  lcx_coal_stats(lcx_engine *e, uint64_t *n_collisions, uint64_t *n_pairs_collided);  /* since creation   */
+
+/* ---- transport: advection + sedimentation + subsidence + boundary conditions ---------------------------- */
+int  lcx_transport(lcx_engine *e, const lcx_transport_opts *o);           /* adve.ipp:98-304, sedi.ipp:13-24, subs.ipp:13-25, bcnd.ipp:114-368 */
+int  lcx_puddle(lcx_engine *e, double out[14]);                           /* accumulated precipitation       */
+
+/* ---- x-slab migration (distributed memory) ------------------------------------------------------------- */
+/* compacts the SDs that left through the left / right face (ascending storage index), shifts x into   */
+/* the neighbour's coordinates and marks the local copies for removal.                                 */
+int  lcx_migr_pack(lcx_engine *e, int64_t *n_lft, int64_t *n_rgt);       /* bcnd.ipp:160-172, pack.ipp:30-121, unpack.ipp:122-145 */
+/* device pointers of the outgoing / incoming buffers: n (uint64[count]) and reals (attribute-major)   */
+int  lcx_migr_buffers(lcx_engine *e, int side, int incoming, void **n_buf, void **real_buf, int64_t *capacity);
+/* copy `count` packed migrants from the outgoing buffer `side` (0: left-movers, 1: right-movers) of `src` into the */
+/* matching incoming buffer of `dst` (device-to-device, peer copy over NVLink when the engines sit on different GPUs) */
+int  lcx_migr_send(lcx_engine *src, int side, lcx_engine *dst, int64_t count);   /* step_async_and_copy.ipp:76-84,110-118 */
+int  lcx_migr_real_attrs(lcx_engine *e, int *count);                      /* number of real attributes sent  */
+/* append `count` arrivals found in the incoming buffer of `side` (0: sent by the right neighbour,   */
+/* 1: by the left neighbour); call for side 0 first                                                   */
+int  lcx_migr_unpack(lcx_engine *e, int side, int64_t count);            /* unpack.ipp:50-120               */
+
+/* ---- end of step: removal / recycling, cell index, per-cell grouping ------------------------------------ */
+/* keep_all != 0: initial grouping - nothing is removed and the cell indices given to lcx_sd_append are used */
+int  lcx_post_copy(lcx_engine *e, int rcyc, int keep_all);                              /* post_copy.ipp:18-35, hskpng_remove.ipp:20-75, rcyc.ipp:44-139, hskpng_ijk.ipp:159-200, hskpng_sort.ipp:15-70, hskpng_count.ipp:16-48 */
+
+/* ---- diagnostics ----------------------------------------------------------------------------------------- */
+int  lcx_moms_select(lcx_engine *e, int kind, int attr, double lo, double hi, int cons);
+int  lcx_moms_calc(lcx_engine *e, int attr, double power, int specific);  /* moms.ipp:277-387                */
+int  lcx_diag_sd_conc(lcx_engine *e);                                     /* particles_diag.ipp:193-211      */
+int  lcx_diag_cell_field(lcx_engine *e, int field);                       /* particles_diag.ipp:148-190      */
+int  lcx_diag_precip_rate(lcx_engine *e);                                 /* particles_diag.ipp:561-586      */
+int  lcx_diag_max_rw(lcx_engine *e);                                      /* particles_diag.ipp:606-634      */
+int  lcx_outbuf(lcx_engine *e, void *dst, int64_t count);                 /* fill_outbuf.ipp:13-37           */
+
+/* ---- timing / introspection (used by bench.py) ----------------------------------------------------------- */
+/* device timer on the engine's stream (CUDA events): start, then stop returns the elapsed milliseconds           */
+int  lcx_timer_start(lcx_engine *e);
+int  lcx_timer_stop(lcx_engine *e, float *ms);
+/* per-kernel profile: while enabled every launch is bracketed by CUDA events; the report is a text table        */
+/* "kernel launches total_ms" (one line per kernel), written into buf (truncated to size)                        */
+int  lcx_profile_enable(lcx_engine *e, int on);
+int  lcx_profile_report(lcx_engine *e, char *buf, int64_t size);
+int  lcx_launch_count(lcx_engine *e, uint64_t *launches);                 /* kernels launched since creation */
+int  lcx_cell_stats(lcx_engine *e, int64_t *n_cell, int64_t *max_count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -277,6 +277,8 @@ int lgc_get_n(lgc_handle *h, unsigned long long *dst, long cap, long *n_out)
   });
 }
 
+void *lgc_proto(lgc_handle *h) { return h->p.get(); }
+
 int lgc_puddle(lgc_handle *h, double *out14)
 {
   return guarded([&] {

@@ -94,6 +94,7 @@ int  lgc_outbuf(lgc_handle *, double *dst, long n);
 int  lgc_get_attr(lgc_handle *, const char *name, double *dst, long cap, long *n_out);
 int  lgc_get_n(lgc_handle *, unsigned long long *dst, long cap, long *n_out);
 int  lgc_puddle(lgc_handle *, double *out14);
+void *lgc_proto(lgc_handle *);            /* the underlying particles_proto_t<double>* (for back-end specific extras) */
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,104 @@
+"""In-tree build of the B200 back-end (no JIT cache: the .so files travel with the repository snapshot).
+
+  lib/liblcx_b200.so     CUDA engine, hand-written sm_100a kernels behind the C ABI of include/lcx_b200.h
+  lib/liblgrngn_b200.so  C++ host layer (lgrngn::factory / particles_proto_t) + flat C binding for Python
+
+nvcc cross-compiles without a GPU.  Flags: -gencode arch=compute_100a,code=sm_100a -lineinfo; -fmad=false keeps
+the reference's order of floating-point operations (bit-exact positions / collision decisions).
+"""
+import os
+import subprocess
+import sys
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+HOST = os.path.join(HERE, "host")
+BIND = os.path.join(HERE, "bindings")
+LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(HERE, "build")
+
+NVCC = os.environ.get("LCX_NVCC", "/usr/local/cuda/bin/nvcc")
+CXX = os.environ.get("LCX_CXX", "/usr/bin/g++")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
+              "-Xcompiler", "-fPIC", "-ccbin", CXX,
+              "-I", os.path.join(REPO, "include")]
+CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-fopenmp", "-Wall", "-Wno-unused-function",
+             "-I", os.path.join(REPO, "include"), "-I", os.path.join(HOST, "include"), "-I", CSRC, "-I", BIND,
+             "-I", "/usr/local/cuda/include"]
+
+CU_SOURCES = ["lcx_api.cu", "lcx_sort.cu", "lcx_cells.cu", "lcx_diag.cu", "lcx_cond.cu", "lcx_coal.cu",
+              "lcx_transport.cu", "lcx_layout.cu"]
+CU_HEADERS = ["lcx_engine.cuh", "lcx_physics.h"]
+
+
+def _mtime(p):
+    return os.path.getmtime(p) if os.path.exists(p) else 0.0
+
+
+def _run(cmd):
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("command failed: %s\n%s" % (" ".join(cmd), r.stdout))
+    return r.stdout
+
+
+def build_engine(force=False, verbose=True, extra=()):
+    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+    hdr_t = max([_mtime(os.path.join(CSRC, h)) for h in CU_HEADERS] + [_mtime(os.path.join(REPO, "include", "lcx_b200.h"))])
+    lib = os.path.join(LIBDIR, "liblcx_b200.so")
+
+    def one(src):
+        s = os.path.join(CSRC, src)
+        o = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+        if not force and _mtime(o) >= max(_mtime(s), hdr_t):
+            return src, 0.0, ""
+        t0 = time.time()
+        out = _run([NVCC] + NVCC_FLAGS + list(extra) + ["-c", s, "-o", o])
+        return src, time.time() - t0, out
+
+    objs = []
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        for src, dt, out in ex.map(one, CU_SOURCES):
+            objs.append(os.path.join(OBJDIR, src.replace(".cu", ".o")))
+            if verbose and dt:
+                print("[build] nvcc %-18s %5.1f s" % (src, dt), flush=True)
+            if verbose and out.strip():
+                print(out)
+    if force or _mtime(lib) < max(_mtime(o) for o in objs):
+        _run([NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"])
+    return lib
+
+
+def build_host(force=False, verbose=True):
+    os.makedirs(LIBDIR, exist_ok=True)
+    os.makedirs(OBJDIR, exist_ok=True)
+    lib = os.path.join(LIBDIR, "liblgrngn_b200.so")
+    srcs = [os.path.join(HOST, "particles_b200.cpp"), os.path.join(BIND, "lgrngn_capi.cpp")]
+    deps = srcs + [os.path.join(REPO, "include", "lcx_b200.h"), os.path.join(CSRC, "lcx_physics.h"),
+                   os.path.join(HOST, "include", "libcloudph++", "lgrngn", "lgrngn_b200_api.hpp"),
+                   os.path.join(BIND, "lgrngn_capi.h")]
+    if not force and _mtime(lib) >= max(_mtime(d) for d in deps) and _mtime(lib) >= _mtime(os.path.join(LIBDIR, "liblcx_b200.so")):
+        return lib
+    objs = []
+    for s in srcs:
+        o = os.path.join(OBJDIR, os.path.basename(s).replace(".cpp", ".o"))
+        t0 = time.time()
+        _run([CXX] + CXX_FLAGS + ["-c", s, "-o", o])
+        if verbose:
+            print("[build] g++  %-18s %5.1f s" % (os.path.basename(s), time.time() - t0), flush=True)
+        objs.append(o)
+    _run([CXX, "-shared", "-fopenmp", "-o", lib] + objs + ["-L", LIBDIR, "-llcx_b200", "-Wl,-rpath,$ORIGIN", "-Wl,-Bsymbolic"])
+    return lib
+
+
+def build_all(force=False, verbose=True):
+    return build_engine(force, verbose), build_host(force, verbose)
+
+
+if __name__ == "__main__":
+    print(build_all(force="--force" in sys.argv))

@@ -1,0 +1,467 @@
+// C-ABI entry points of liblcx_b200.so (declared in include/lcx_b200.h): engine life cycle, buffer management,
+// host<->device transfers, and thin exception-to-status wrappers around the passes implemented in the other
+// translation units.
+#include "lcx_engine.cuh"
+
+#include <map>
+#include <memory>
+#include <sstream>
+
+namespace
+{
+  thread_local std::string g_last_error;
+
+  template <class F>
+  int guarded(F f)
+  {
+    try { f(); return 0; }
+    catch (const std::exception &ex) { g_last_error = ex.what(); return 1; }
+    catch (...) { g_last_error = "unknown error"; return 2; }
+  }
+
+  void use_device(lcx_engine *e) { LCX_CUDA(cudaSetDevice(e->device)); }
+
+  struct field_ref { lcx::real_t *p; size_t n; };
+
+  field_ref field_of(lcx_engine *e, int field)
+  {
+    switch (field)
+    {
+      case LCX_F_TH:        return {e->th.p, e->th.n};
+      case LCX_F_RV:        return {e->rv.p, e->rv.n};
+      case LCX_F_RHOD:      return {e->rhod.p, e->rhod.n};
+      case LCX_F_P:         return {e->p.p, e->p.n};
+      case LCX_F_COURANT_X: return {e->courant_x.p, e->courant_x.n};
+      case LCX_F_COURANT_Y: return {e->courant_y.p, e->courant_y.n};
+      case LCX_F_COURANT_Z: return {e->courant_z.p, e->courant_z.n};
+      case LCX_F_T:         return {e->T.p, e->T.n};
+      case LCX_F_RH:        return {e->RH.p, e->RH.n};
+      case LCX_F_ETA:       return {e->eta.p, e->eta.n};
+      case LCX_F_DV:        return {e->dv.p, e->dv.n};
+      case LCX_F_W_LS:      return {e->w_LS.p, e->w_LS.n};
+      case LCX_F_MOM:       return {e->count_mom.p, e->count_mom.n};
+      default: throw lcx::error("unknown field id " + std::to_string(field));
+    }
+  }
+
+  // cell volumes, clipped by the Lagrangian domain: reference src/impl/initialization/particles_impl_init_grid.ipp:13-55
+  __global__ void k_init_dv(lcx::grid_t g, lcx::real_t *dv)
+  {
+    using lcx::real_t;
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= g.n_cell) return;
+    const int nz1 = max(1, g.nz), ny1 = max(1, g.ny);
+    const int ic = int(c);
+    const int i = (ic / nz1) / ny1, j = (ic / nz1) % ny1, k = ic % nz1;
+    dv[c] = lcx::tmax(real_t(0),
+      (lcx::tmin((i + 1) * g.dx, g.x1) - lcx::tmax(i * g.dx, g.x0)) *
+      (lcx::tmin((j + 1) * g.dy, g.y1) - lcx::tmax(j * g.dy, g.y0)) *
+      (lcx::tmin((k + 1) * g.dz, g.z1) - lcx::tmax(k * g.dz, g.z0)));
+  }
+
+  __global__ void k_fill_tail(size_t first, size_t count, lcx::real_t *vt, uint32_t *sid, uint32_t *ijk, const uint32_t *ijk_src)
+  {
+    const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    vt[first + t] = lcx::real_t(-1);          // "invalid": resize value of vt (particles_impl.ipp:446, hskpng_resize.ipp:14-20)
+    sid[first + t] = uint32_t(first + t);
+    ijk[first + t] = ijk_src ? ijk_src[t] : 0u;
+  }
+}
+
+lcx_engine::~lcx_engine()
+{
+  cudaSetDevice(device);
+  if (stream) cudaStreamSynchronize(stream);
+  sd[0].release(); sd[1].release();
+  key[0].release(); key[1].release(); val[0].release(); val[1].release(); un.release(); flag.release();
+  u01.release(); n_filtered.release(); tmp_real.release(); perm.release();
+  th.release(); rv.release(); rhod.release(); p.release(); T.release(); RH.release(); eta.release(); dv.release();
+  lambda_D.release(); lambda_K.release(); sstp_tmp_rv.release(); sstp_tmp_th.release(); sstp_tmp_rh.release();
+  drw_mom3.release(); rw_mom3.release(); count_mom.release(); mom_partial.release();
+  courant_x.release(); courant_y.release(); courant_z.release(); w_LS.release(); cell_off.release();
+  vt0.release(); eff.release(); hist.release(); scan_tmp.release();
+  for (int s = 0; s < 2; ++s) { for (int d = 0; d < 2; ++d) { mig_n[s][d].release(); mig_real[s][d].release(); } mig_ids[s].release(); }
+  scalars.release(); red_partial.release();
+  for (auto &r : prof) { cudaEventDestroy(r.t0); cudaEventDestroy(r.t1); }
+  if (timer0) { cudaEventDestroy(timer0); cudaEventDestroy(timer1); }
+  if (h_scalars) cudaFreeHost(h_scalars);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+extern "C" {
+
+const char *lcx_last_error(void) { return g_last_error.c_str(); }
+const char *lcx_version(void) { return "lcx_b200 0.1 (sm_100a)"; }
+
+int lcx_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int lcx_create(const lcx_config *cfg, lcx_engine **out)
+{
+  *out = nullptr;
+  return guarded([&] {
+    using namespace lcx;
+    if (cfg->real_bytes != 8) throw error("lcx_create: only real_bytes = 8 (double) is available in this build");
+    if (lcx_device_count() == 0) throw error("lcx_create: no CUDA device is available - the B200 back-end has no CPU fallback");
+    if (cfg->n_sd_max == 0) throw error("lcx_create: n_sd_max must be positive");
+    if (cfg->n_sd_max >= 0xfffffff0ull) throw error("lcx_create: n_sd_max per slab must be below 2^32");
+    std::unique_ptr<lcx_engine> e(new lcx_engine);
+    e->cfg = *cfg;
+    int dev = cfg->device;
+    if (dev < 0) LCX_CUDA(cudaGetDevice(&dev));
+    e->device = dev;
+    LCX_CUDA(cudaSetDevice(dev));
+    LCX_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+
+    grid_t &g = e->grid;
+    g.nx = cfg->nx; g.ny = cfg->ny; g.nz = cfg->nz;
+    g.n_dims = (g.nx ? 1 : 0) + (g.ny ? 1 : 0) + (g.nz ? 1 : 0);
+    if (g.ny && !(g.nx && g.nz)) throw error("lcx_create: a y dimension requires x and z (3-D is xyz, 2-D is xz, 1-D is x)");
+    if (g.nz && !g.nx) throw error("lcx_create: a z dimension requires x");
+    g.dx = cfg->dx; g.dy = cfg->dy; g.dz = cfg->dz;
+    g.x0 = cfg->x0; g.y0 = cfg->y0; g.z0 = cfg->z0; g.x1 = cfg->x1; g.y1 = cfg->y1; g.z1 = cfg->z1;
+    const size_t nx1 = g.nx ? g.nx : 1, ny1 = g.ny ? g.ny : 1, nz1 = g.nz ? g.nz : 1;
+    const size_t n_cell = nx1 * ny1 * nz1;
+    if (n_cell >= 0x7ffffff0ull) throw error("lcx_create: too many cells for one slab");
+    g.n_cell = idx_t(n_cell);
+    g.halo_size = (cfg->adve_scheme == AS_PRED_CORR) ? 2 : 0;
+    g.halo_x = idx_t(g.n_dims == 1 ? g.halo_size : g.n_dims == 2 ? g.halo_size * g.nz : g.halo_size * g.nz * g.ny);
+
+    const size_t cap = e->cap = size_t(cfg->n_sd_max);
+    e->sd[0].alloc(cap, g.nx, g.ny, g.nz);
+    e->sd[1].alloc(cap, g.nx, g.ny, g.nz);
+    for (int b = 0; b < 2; ++b) { e->key[b].alloc(cap); e->val[b].alloc(cap); }
+    e->un.alloc(cap); e->flag.alloc(cap); e->u01.alloc(cap); e->n_filtered.alloc(cap); e->tmp_real.alloc(cap);
+
+    e->th.alloc(n_cell); e->rv.alloc(n_cell); e->rhod.alloc(n_cell); e->p.alloc(n_cell); e->T.alloc(n_cell);
+    e->RH.alloc(n_cell); e->eta.alloc(n_cell); e->dv.alloc(n_cell); e->lambda_D.alloc(n_cell); e->lambda_K.alloc(n_cell);
+    e->drw_mom3.alloc(n_cell); e->rw_mom3.alloc(n_cell); e->count_mom.alloc(n_cell);
+    if (cfg->allow_sstp_cond) { e->sstp_tmp_rv.alloc(n_cell); e->sstp_tmp_th.alloc(n_cell); e->sstp_tmp_rh.alloc(n_cell); }
+    e->cell_off.alloc(n_cell + 2);
+    const size_t h = size_t(g.halo_size);
+    switch (g.n_dims)   // staggered Courant fields with x-halo: init_sync.ipp:29-44
+    {
+      case 3:
+        e->courant_x.alloc((g.nx + 2 * h + 1) * g.ny * g.nz);
+        e->courant_y.alloc((g.nx + 2 * h) * (g.ny + 1) * g.nz);
+        e->courant_z.alloc((g.nx + 2 * h) * g.ny * (g.nz + 1));
+        break;
+      case 2:
+        e->courant_x.alloc((g.nx + 2 * h + 1) * g.nz);
+        e->courant_z.alloc((g.nx + 2 * h) * (g.nz + 1));
+        break;
+      case 1:
+        e->courant_x.alloc(g.nx + 2 * h + 1);
+        break;
+      default: break;
+    }
+    for (dbuf<real_t> *c : {&e->courant_x, &e->courant_y, &e->courant_z})
+      if (c->n) LCX_CUDA(cudaMemsetAsync(c->p, 0, c->bytes(), e->stream));
+
+    const size_t tiles = cap / 2048 + 2;
+    e->hist.alloc(tiles * 256);
+    e->scan_tmp.alloc((tiles * 256) / 1024 * 2 + cap / 1024 * 2 + 8192);   // per-level tile sums of the recursive scan
+
+    if (cfg->bcond_lft == LCX_BCOND_DISTMEM || cfg->bcond_rgt == LCX_BCOND_DISTMEM)
+    {
+      e->mig_cap = cap / nx1 + 4096;
+      if (e->mig_cap > cap) e->mig_cap = cap;
+      const int n_real = 4 + (g.nx ? 1 : 0) + (g.ny ? 1 : 0) + (g.nz ? 1 : 0);
+      for (int s = 0; s < 2; ++s)
+        for (int d = 0; d < 2; ++d) { e->mig_n[s][d].alloc(e->mig_cap); e->mig_real[s][d].alloc(e->mig_cap * n_real); }
+    }
+
+    e->scalars.alloc(1);
+    LCX_CUDA(cudaMemsetAsync(e->scalars.p, 0, sizeof(dev_scalars), e->stream));
+    LCX_CUDA(cudaMallocHost(reinterpret_cast<void **>(&e->h_scalars), sizeof(dev_scalars)));
+    std::memset(e->h_scalars, 0, sizeof(dev_scalars));
+    e->red_partial.alloc(cap / 256 * 4 + 4096);
+
+    if (g.n_dims > 0) { k_init_dv<<<div_up(n_cell, 256), 256, 0, e->stream>>>(g, e->dv.p); LCX_CUDA(cudaGetLastError()); ++e->launches; }
+    LCX_CUDA(cudaMemsetAsync(e->cell_off.p, 0, e->cell_off.bytes(), e->stream));
+    LCX_CUDA(cudaStreamSynchronize(e->stream));
+    *out = e.release();
+  });
+}
+
+int lcx_destroy(lcx_engine *e) { return guarded([&] { delete e; }); }
+
+int lcx_sync(lcx_engine *e) { return guarded([&] { use_device(e); LCX_CUDA(cudaStreamSynchronize(e->stream)); }); }
+
+void *lcx_stream(lcx_engine *e) { return e->stream; }
+
+int lcx_field_size(lcx_engine *e, int field, int64_t *count) { return guarded([&] { *count = int64_t(field_of(e, field).n); }); }
+
+int lcx_cells_set(lcx_engine *e, int field, const void *src, int64_t count, int src_on_device)
+{
+  return guarded([&] {
+    use_device(e);
+    if (field == LCX_F_W_LS && e->w_LS.n != size_t(count)) e->w_LS.alloc(size_t(count));
+    const field_ref f = field_of(e, field);
+    if (size_t(count) != f.n) throw lcx::error("lcx_cells_set: field " + std::to_string(field) + " holds " + std::to_string(f.n) + " values, got " + std::to_string(count));
+    LCX_CUDA(cudaMemcpyAsync(f.p, src, f.n * sizeof(lcx::real_t), src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
+    if (!src_on_device) LCX_CUDA(cudaStreamSynchronize(e->stream));   // the caller may reuse its staging buffer
+  });
+}
+
+int lcx_cells_get(lcx_engine *e, int field, void *dst, int64_t count)
+{
+  return guarded([&] {
+    use_device(e);
+    const field_ref f = field_of(e, field);
+    if (size_t(count) > f.n) throw lcx::error("lcx_cells_get: requested more values than the field holds");
+    LCX_CUDA(cudaMemcpyAsync(dst, f.p, size_t(count) * sizeof(lcx::real_t), cudaMemcpyDeviceToHost, e->stream));
+    LCX_CUDA(cudaStreamSynchronize(e->stream));
+  });
+}
+
+int lcx_set_vt0_table(lcx_engine *e, const void *table, int n)
+{
+  return guarded([&] {
+    use_device(e);
+    if (n != lcx::VT0_N_BIN) throw lcx::error("lcx_set_vt0_table: expected " + std::to_string(int(lcx::VT0_N_BIN)) + " bins");
+    e->vt0.alloc(size_t(n));
+    LCX_CUDA(cudaMemcpy(e->vt0.p, table, size_t(n) * sizeof(lcx::real_t), cudaMemcpyHostToDevice));
+  });
+}
+
+int lcx_set_efficiencies(lcx_engine *e, const void *table, int64_t n)
+{
+  return guarded([&] {
+    use_device(e);
+    e->eff.alloc(size_t(n));
+    LCX_CUDA(cudaMemcpy(e->eff.p, table, size_t(n) * sizeof(lcx::real_t), cudaMemcpyHostToDevice));
+  });
+}
+
+int lcx_sd_append(lcx_engine *e, int64_t count, const uint64_t *n, const void *rd3, const void *rw2, const void *kpa,
+                  const void *x, const void *y, const void *z, const uint32_t *ijk)
+{
+  return guarded([&] {
+    using namespace lcx;
+    use_device(e);
+    if (count <= 0) return;
+    const size_t first = e->n_part, cnt = size_t(count);
+    if (first + cnt > e->cap) throw error("n_sd_max (" + std::to_string(e->cap) + ") < n_part (" + std::to_string(first + cnt) + ")");
+    sd_arrays &s = e->S();
+    auto up = [&](void *dst, const void *src, size_t bytes) { if (dst && src) LCX_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, e->stream)); };
+    up(s.n.p + first, n, cnt * sizeof(n_t));
+    up(s.rd3.p + first, rd3, cnt * sizeof(real_t));
+    up(s.rw2.p + first, rw2, cnt * sizeof(real_t));
+    up(s.kpa.p + first, kpa, cnt * sizeof(real_t));
+    if (e->grid.nx) up(s.x.p + first, x, cnt * sizeof(real_t));
+    if (e->grid.ny) up(s.y.p + first, y, cnt * sizeof(real_t));
+    if (e->grid.nz) up(s.z.p + first, z, cnt * sizeof(real_t));
+    uint32_t *ijk_dev = nullptr;
+    if (ijk) { ijk_dev = e->key[0].p; up(ijk_dev, ijk, cnt * sizeof(uint32_t)); }
+    k_fill_tail<<<div_up(cnt, 256), 256, 0, e->stream>>>(first, cnt, s.vt.p, s.sid.p, s.ijk.p, ijk_dev);
+    LCX_CUDA(cudaGetLastError()); ++e->launches;
+    LCX_CUDA(cudaStreamSynchronize(e->stream));
+    e->n_part = first + cnt;
+    e->grouped = false;
+  });
+}
+
+int lcx_n_part(lcx_engine *e, int64_t *n_part) { *n_part = int64_t(e->n_part); return 0; }
+
+int lcx_get_attr(lcx_engine *e, int attr, void *dst, int64_t cap, int64_t *n_out)
+{
+  return guarded([&] {
+    use_device(e);
+    *n_out = int64_t(e->n_part);
+    if (e->n_part == 0) return;
+    lcx::scatter_attr_by_sid(e, attr, e->tmp_real.p);
+    const size_t cnt = size_t(cap) < e->n_part ? size_t(cap) : e->n_part;
+    LCX_CUDA(cudaMemcpyAsync(dst, e->tmp_real.p, cnt * sizeof(lcx::real_t), cudaMemcpyDeviceToHost, e->stream));
+    LCX_CUDA(cudaStreamSynchronize(e->stream));
+  });
+}
+
+int lcx_get_attr_u64(lcx_engine *e, int attr, uint64_t *dst, int64_t cap, int64_t *n_out)
+{
+  return guarded([&] {
+    std::vector<double> tmp(e->n_part);
+    int64_t n = 0;
+    if (lcx_get_attr(e, attr, tmp.data(), int64_t(tmp.size()), &n) != 0) throw lcx::error(g_last_error);
+    *n_out = n;
+    for (int64_t i = 0; i < n && i < cap; ++i) dst[i] = uint64_t(tmp[size_t(i)]);
+  });
+}
+
+int lcx_hskpng_Tpr(lcx_engine *e) { return guarded([&] { use_device(e); lcx::hskpng_Tpr(e); }); }
+int lcx_hskpng_mfp(lcx_engine *e) { return guarded([&] { use_device(e); lcx::hskpng_mfp(e); }); }
+int lcx_hskpng_vterm(lcx_engine *e, int only_invalid) { return guarded([&] { use_device(e); lcx::hskpng_vterm(e, only_invalid != 0); }); }
+int lcx_sstp_percell_step(lcx_engine *e, int step, int sstp_cond, int var_rho)
+{ return guarded([&] { use_device(e); lcx::sstp_percell_step(e, step, sstp_cond, var_rho != 0); }); }
+int lcx_sstp_save(lcx_engine *e) { return guarded([&] { use_device(e); lcx::sstp_save(e); }); }
+
+int lcx_cond(lcx_engine *e, double dt_sub, double RH_max, int step, int sstp_cond)
+{ return guarded([&] { use_device(e); lcx::cond(e, dt_sub, RH_max, step, sstp_cond); }); }
+int lcx_update_th_rv(lcx_engine *e) { return guarded([&] { use_device(e); lcx::update_th_rv(e); }); }
+
+int lcx_coal(lcx_engine *e, double dt_sub, const lcx_rng *rng) { return guarded([&] { use_device(e); lcx::coal(e, dt_sub, rng); }); }
+
+int lcx_coal_flag(lcx_engine *e, int *increase_sstp_coal)
+{
+  return guarded([&] {
+    use_device(e);
+    LCX_CUDA(cudaMemcpyAsync(e->h_scalars, e->scalars.p, sizeof(lcx::dev_scalars), cudaMemcpyDeviceToHost, e->stream));
+    LCX_CUDA(cudaStreamSynchronize(e->stream));
+    *increase_sstp_coal = int(e->h_scalars->increase_sstp_coal);
+    if (*increase_sstp_coal) LCX_CUDA(cudaMemsetAsync(&e->scalars.p->increase_sstp_coal, 0, sizeof(unsigned int), e->stream));
+  });
+}
+
+int lcx_coal_stats(lcx_engine *e, uint64_t *n_collisions, uint64_t *n_pairs_collided)
+{
+  return guarded([&] {
+    use_device(e);
+    LCX_CUDA(cudaMemcpyAsync(e->h_scalars, e->scalars.p, sizeof(lcx::dev_scalars), cudaMemcpyDeviceToHost, e->stream));
+    LCX_CUDA(cudaStreamSynchronize(e->stream));
+    *n_collisions = e->h_scalars->n_collisions;
+    *n_pairs_collided = e->h_scalars->n_pairs_collided;
+  });
+}
+
+int lcx_transport(lcx_engine *e, const lcx_transport_opts *o) { return guarded([&] { use_device(e); lcx::transport(e, o); }); }
+
+int lcx_puddle(lcx_engine *e, double out[14])
+{
+  return guarded([&] {
+    use_device(e);
+    LCX_CUDA(cudaMemcpyAsync(e->h_scalars, e->scalars.p, sizeof(lcx::dev_scalars), cudaMemcpyDeviceToHost, e->stream));
+    LCX_CUDA(cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < 14; ++i) out[i] = 0;
+    out[8] = e->h_scalars->puddle[0];    // outliq_vol
+    out[9] = e->h_scalars->puddle[1];    // outdry_vol
+    out[10] = e->h_scalars->puddle[3];   // outprtcl_num
+    out[12] = e->h_scalars->puddle[2];   // outliq_num
+  });
+}
+
+int lcx_migr_pack(lcx_engine *e, int64_t *n_lft, int64_t *n_rgt) { return guarded([&] { use_device(e); lcx::migr_pack(e, n_lft, n_rgt); }); }
+
+int lcx_migr_buffers(lcx_engine *e, int side, int incoming, void **n_buf, void **real_buf, int64_t *capacity)
+{
+  return guarded([&] {
+    if (side < 0 || side > 1 || incoming < 0 || incoming > 1) throw lcx::error("lcx_migr_buffers: bad side / direction");
+    *n_buf = e->mig_n[side][incoming].p;
+    *real_buf = e->mig_real[side][incoming].p;
+    *capacity = int64_t(e->mig_cap);
+  });
+}
+
+int lcx_migr_send(lcx_engine *src, int side, lcx_engine *dst, int64_t count)
+{
+  return guarded([&] {
+    if (count <= 0) return;
+    if (side < 0 || side > 1) throw lcx::error("lcx_migr_send: bad side");
+    if (size_t(count) > dst->mig_cap || size_t(count) > src->mig_cap) throw lcx::error("lcx_migr_send: migration buffer overflow");
+    int n_real = 0;
+    lcx_migr_real_attrs(src, &n_real);
+    use_device(src);
+    // on the sender's stream, after its pack kernel; the receiver waits for it before unpacking
+    LCX_CUDA(cudaMemcpyPeerAsync(dst->mig_n[side][1].p, dst->device, src->mig_n[side][0].p, src->device, size_t(count) * sizeof(lcx::n_t), src->stream));
+    LCX_CUDA(cudaMemcpyPeerAsync(dst->mig_real[side][1].p, dst->device, src->mig_real[side][0].p, src->device,
+                                 size_t(count) * size_t(n_real) * sizeof(lcx::real_t), src->stream));
+    LCX_CUDA(cudaStreamSynchronize(src->stream));
+  });
+}
+
+int lcx_migr_real_attrs(lcx_engine *e, int *count)
+{ *count = 4 + (e->grid.nx ? 1 : 0) + (e->grid.ny ? 1 : 0) + (e->grid.nz ? 1 : 0); return 0; }
+
+int lcx_migr_unpack(lcx_engine *e, int side, int64_t count) { return guarded([&] { use_device(e); lcx::migr_unpack(e, side, count); }); }
+
+int lcx_post_copy(lcx_engine *e, int rcyc, int keep_all) { return guarded([&] { use_device(e); lcx::post_copy(e, rcyc != 0, keep_all != 0); }); }
+
+int lcx_moms_select(lcx_engine *e, int kind, int attr, double lo, double hi, int cons)
+{ return guarded([&] { use_device(e); lcx::moms_select(e, kind, attr, lo, hi, cons != 0); }); }
+
+int lcx_moms_calc(lcx_engine *e, int attr, double power, int specific)
+{
+  return guarded([&] {
+    use_device(e);
+    if (!e->selected) throw lcx::error("moment requested before a selector (diag_all, diag_*_rng, ...)");
+    lcx::cell_moment(e, e->n_filtered.p, lcx::attr_ptr(e, attr), power, specific != 0, e->count_mom.p);
+  });
+}
+
+int lcx_diag_sd_conc(lcx_engine *e) { return guarded([&] { use_device(e); lcx::diag_sd_conc(e); }); }
+
+int lcx_diag_cell_field(lcx_engine *e, int field)
+{
+  return guarded([&] {
+    use_device(e);
+    const field_ref f = field_of(e, field);
+    LCX_CUDA(cudaMemcpyAsync(e->count_mom.p, f.p, size_t(e->grid.n_cell) * sizeof(lcx::real_t), cudaMemcpyDeviceToDevice, e->stream));
+  });
+}
+
+int lcx_diag_precip_rate(lcx_engine *e) { return guarded([&] { use_device(e); lcx::diag_precip_rate(e); }); }
+int lcx_diag_max_rw(lcx_engine *e) { return guarded([&] { use_device(e); lcx::diag_max_rw(e); }); }
+
+int lcx_outbuf(lcx_engine *e, void *dst, int64_t count) { return lcx_cells_get(e, LCX_F_MOM, dst, count); }
+
+int lcx_timer_start(lcx_engine *e)
+{
+  return guarded([&] {
+    use_device(e);
+    if (!e->timer0) { LCX_CUDA(cudaEventCreate(&e->timer0)); LCX_CUDA(cudaEventCreate(&e->timer1)); }
+    LCX_CUDA(cudaEventRecord(e->timer0, e->stream));
+  });
+}
+
+int lcx_timer_stop(lcx_engine *e, float *ms)
+{
+  return guarded([&] {
+    use_device(e);
+    if (!e->timer0) throw lcx::error("lcx_timer_stop without lcx_timer_start");
+    LCX_CUDA(cudaEventRecord(e->timer1, e->stream));
+    LCX_CUDA(cudaEventSynchronize(e->timer1));
+    LCX_CUDA(cudaEventElapsedTime(ms, e->timer0, e->timer1));
+  });
+}
+
+int lcx_profile_enable(lcx_engine *e, int on)
+{
+  return guarded([&] {
+    use_device(e);
+    LCX_CUDA(cudaStreamSynchronize(e->stream));
+    for (auto &r : e->prof) { cudaEventDestroy(r.t0); cudaEventDestroy(r.t1); }
+    e->prof.clear();
+    e->profiling = on != 0;
+  });
+}
+
+int lcx_profile_report(lcx_engine *e, char *buf, int64_t size)
+{
+  return guarded([&] {
+    use_device(e);
+    LCX_CUDA(cudaStreamSynchronize(e->stream));
+    std::map<std::string, std::pair<uint64_t, double>> acc;
+    for (auto &r : e->prof)
+    {
+      float ms = 0;
+      LCX_CUDA(cudaEventElapsedTime(&ms, r.t0, r.t1));
+      auto &a = acc[r.name];
+      a.first += 1; a.second += ms;
+    }
+    std::ostringstream os;
+    for (auto &kv : acc) os << kv.first << " " << kv.second.first << " " << kv.second.second << "\n";
+    const std::string s = os.str();
+    if (size > 0) { std::strncpy(buf, s.c_str(), size_t(size) - 1); buf[size - 1] = 0; }
+  });
+}
+
+int lcx_launch_count(lcx_engine *e, uint64_t *launches) { *launches = e->launches; return 0; }
+
+int lcx_cell_stats(lcx_engine *e, int64_t *n_cell, int64_t *max_count)
+{ *n_cell = int64_t(e->grid.n_cell); *max_count = int64_t(e->max_count); return 0; }
+
+}  // extern "C"

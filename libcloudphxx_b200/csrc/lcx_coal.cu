@@ -1,0 +1,244 @@
+// SDM Monte-Carlo coalescence (Shima et al. 2009) for one sub-step.
+// Reference: src/impl/coalescence/particles_impl_coal.ipp:273-546 (driver), :146-269 (collider), :118-143 (collide),
+//            :59-96 (kappa mixing), :99-107 (scale factor); pairing order from
+//            src/impl/housekeeping/particles_impl_hskpng_sort.ipp:31-53 (shuffle = stable sort by a fresh random key,
+//            then stable sort by cell).
+//
+// The reference's candidate pairs are (2k, 2k+1) of each cell's SDs ordered by (random key un, storage index).
+// SDs are physically grouped by cell here, so that order is a per-cell sort of the composite key
+// (un[sid] << 32 | sid), which is unique - no dependence on the physical order inside the cell:
+//   * small cells (max population <= 256): one warp per cell; keys staged in shared memory, rank of each SD by
+//     counting smaller keys (O(m^2/32) per lane, m ~ 40), pairs processed by the lanes;
+//   * big cells (0-D boxes, coarse grids): global LSD radix sort by sid, un, cell (lcx_sort.cu), then one thread
+//     per candidate pair.
+// Random numbers come from an injected stream (parity with the reference's mt19937 draw order: un by storage
+// index, u01 by sorted position of the first SD of the pair) or from Philox4x32-10 evaluated at the same indices.
+#include "lcx_engine.cuh"
+
+namespace lcx
+{
+  namespace
+  {
+    constexpr int TPB = 256;
+    constexpr int WARPS = TPB / 32;
+    constexpr unsigned SMALL_MAX = 256;      // largest cell population handled by the warp-per-cell kernel
+
+    // ---- Philox4x32-10 (Salmon, Moraes, Dror & Shaw, SC'11) --------------------------------------------
+    struct philox_key { uint32_t k0, k1; };
+    __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1)
+    {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+      const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+      c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    }
+    __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], philox_key k)
+    {
+#pragma unroll
+      for (int r = 0; r < 10; ++r)
+      {
+        philox_round(c, k.k0, k.k1);
+        k.k0 += 0x9E3779B9u; k.k1 += 0xBB67AE85u;
+      }
+    }
+
+    struct rng_src
+    {
+      int mode;
+      const uint32_t *un;     // device copy of the injected integer stream (by storage index)
+      const real_t *u01;      // device copy of the injected [0,1) stream (by sorted position)
+      uint64_t seed, call;
+
+      __device__ __forceinline__ uint32_t get_un(uint32_t sid) const
+      {
+        if (mode == LCX_RNG_INJECT) return un[sid];
+        uint32_t c[4] = {sid, 0u, uint32_t(call), uint32_t(call >> 32)};
+        philox4x32_10(c, philox_key{uint32_t(seed), uint32_t(seed >> 32)});
+        return c[0];
+      }
+      __device__ __forceinline__ real_t get_u01(uint32_t pos) const
+      {
+        if (mode == LCX_RNG_INJECT) return u01[pos];
+        uint32_t c[4] = {pos, 1u, uint32_t(call), uint32_t(call >> 32)};
+        philox4x32_10(c, philox_key{uint32_t(seed), uint32_t(seed >> 32)});
+        // 53-bit mantissa from two words, [0,1)
+        const uint64_t bits = (uint64_t(c[0]) << 21) ^ (uint64_t(c[1]) >> 11);
+        return real_t(bits & ((1ull << 53) - 1)) * real_t(1.0 / 9007199254740992.0);
+      }
+    };
+
+    struct coal_ctx
+    {
+      n_t *n; real_t *rw2, *rd3, *vt, *kpa;
+      const real_t *dv;
+      coal_kernel_params<real_t> kp;
+      real_t dt;
+      int multi_kappa, pure_const_multi;
+      dev_scalars *sc;
+    };
+
+    // multiplicity / radius update of one collision event; `hi` keeps the larger multiplicity: coal.ipp:118-143
+    __device__ __forceinline__ void collide(const coal_ctx &cx, uint32_t hi, uint32_t lo, n_t n_hi, n_t n_lo,
+                                           real_t rw2_hi, real_t rw2_lo, real_t rd3_hi, real_t rd3_lo, n_t col_no)
+    {
+      cx.n[hi] = n_hi - col_no * n_lo;
+      const real_t rw_lo = cbrt(col_no * rw2_hi * sqrt(rw2_hi) + rw2_lo * sqrt(rw2_lo));
+      cx.rw2[lo] = rw_lo * rw_lo;
+      const real_t rd3_new = col_no * rd3_hi + rd3_lo;
+      cx.rd3[lo] = rd3_new;
+      cx.vt[lo] = real_t(-1);
+      if (cx.multi_kappa)
+      {
+        // rd3-weighted mean of kappa, applied once per collision: weighted_summator, coal.ipp:59-96
+        const real_t kpa_hi = cx.kpa[hi];
+        real_t kpa_lo = cx.kpa[lo];
+        real_t rd3_old = rd3_new - col_no * rd3_hi;
+        for (int ci = 0; ci < real_t(col_no); ++ci)
+        {
+          kpa_lo = (kpa_hi * rd3_hi + kpa_lo * rd3_old) / (rd3_hi + rd3_old);
+          rd3_old += rd3_hi;
+        }
+        cx.kpa[lo] = kpa_lo;
+      }
+    }
+
+    // one candidate pair: a = physical index of the SD at even in-cell position, b = the next one: coal.ipp:181-268
+    __device__ __forceinline__ void try_pair(const coal_ctx &cx, uint32_t a, uint32_t b, real_t u01, real_t scl, real_t dv_c)
+    {
+      const n_t n_a = cx.n[a], n_b = cx.n[b];
+      const real_t rw2_a = cx.rw2[a], rw2_b = cx.rw2[b];
+      const real_t vt_a = cx.vt[a], vt_b = cx.vt[b];
+      const real_t prob = cx.dt / dv_c * scl * coal_kernel(cx.kp, n_a, n_b, rw2_a, rw2_b, vt_a, vt_b);
+      n_t col_no = n_t(prob);
+      if (cx.pure_const_multi && col_no >= 1) cx.sc->increase_sstp_coal = 1u;
+      if (u01 < prob - col_no) ++col_no;
+      if (col_no == 0) return;
+      const real_t rd3_a = cx.rd3[a], rd3_b = cx.rd3[b];
+      if (n_a >= n_b)
+      {
+        if (n_b > 0) col_no = tmin(col_no, n_t(n_a / n_b));
+        collide(cx, a, b, n_a, n_b, rw2_a, rw2_b, rd3_a, rd3_b, col_no);
+      }
+      else
+      {
+        if (n_a > 0) col_no = tmin(col_no, n_t(n_b / n_a));
+        collide(cx, b, a, n_b, n_a, rw2_b, rw2_a, rd3_b, rd3_a, col_no);
+      }
+      atomicAdd(&cx.sc->n_collisions, (unsigned long long)col_no);
+      atomicAdd(&cx.sc->n_pairs_collided, 1ull);
+    }
+
+    // ---- small cells: warp per cell ---------------------------------------------------------------------
+    __global__ void __launch_bounds__(TPB) k_coal_small(idx_t n_cell, const uint32_t *__restrict__ off, const idx_t *__restrict__ sid,
+                                                       rng_src rng, coal_ctx cx)
+    {
+      __shared__ unsigned long long skey[WARPS][SMALL_MAX];
+      __shared__ unsigned short sperm[WARPS][SMALL_MAX];
+      const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      const idx_t c = blockIdx.x * WARPS + w;
+      if (c >= n_cell) return;
+      const uint32_t b = off[c];
+      const uint32_t m = off[c + 1] - b;
+      if (m < 2) return;
+      for (uint32_t e = lane; e < m; e += 32)
+      {
+        const uint32_t s = sid[b + e];
+        skey[w][e] = ((unsigned long long)rng.get_un(s) << 32) | s;
+      }
+      __syncwarp();
+      for (uint32_t e = lane; e < m; e += 32)
+      {
+        const unsigned long long mine = skey[w][e];
+        uint32_t r = 0;
+        for (uint32_t j = 0; j < m; ++j) r += (skey[w][j] < mine);
+        sperm[w][r] = (unsigned short)e;
+      }
+      __syncwarp();
+      const real_t scl = coal_scale_factor<real_t>(n_t(m));
+      const real_t dv_c = cx.dv[c];
+      for (uint32_t k = lane; 2 * k + 1 < m; k += 32)
+        try_pair(cx, b + sperm[w][2 * k], b + sperm[w][2 * k + 1], rng.get_u01(b + 2 * k), scl, dv_c);
+    }
+
+    // ---- big cells: global sort, then thread per pair ----------------------------------------------------
+    __global__ void __launch_bounds__(TPB) k_fill_sid_keys(size_t n, const idx_t *__restrict__ sid, uint32_t *__restrict__ key, uint32_t *__restrict__ val)
+    {
+      const size_t i = size_t(blockIdx.x) * TPB + threadIdx.x;
+      if (i < n) { key[i] = sid[i]; val[i] = uint32_t(i); }
+    }
+    __global__ void __launch_bounds__(TPB) k_keys_from_un(size_t n, const idx_t *__restrict__ sid, const uint32_t *__restrict__ val, rng_src rng, uint32_t *__restrict__ key)
+    {
+      const size_t i = size_t(blockIdx.x) * TPB + threadIdx.x;
+      if (i < n) key[i] = rng.get_un(sid[val[i]]);
+    }
+    __global__ void __launch_bounds__(TPB) k_keys_from_ijk(size_t n, const idx_t *__restrict__ ijk, const uint32_t *__restrict__ val, uint32_t *__restrict__ key)
+    {
+      const size_t i = size_t(blockIdx.x) * TPB + threadIdx.x;
+      if (i < n) key[i] = ijk[val[i]];
+    }
+    __global__ void __launch_bounds__(TPB) k_coal_big(size_t n_part, const uint32_t *__restrict__ off, const idx_t *__restrict__ ijk,
+                                                     const uint32_t *__restrict__ perm, rng_src rng, coal_ctx cx)
+    {
+      const size_t pos = size_t(blockIdx.x) * TPB + threadIdx.x;
+      if (pos + 1 >= n_part) return;
+      const idx_t c = ijk[pos];               // sorted position and physical position share the cell segments
+      const uint32_t b = off[c], en = off[c + 1];
+      if (((pos - b) & 1u) != 0u) return;     // only every second SD of a cell starts a pair
+      if (pos + 1 >= en) return;              // the last SD of an odd-sized cell stays unpaired
+      try_pair(cx, perm[pos], perm[pos + 1], rng.get_u01(uint32_t(pos)), coal_scale_factor<real_t>(n_t(en - b)), cx.dv[c]);
+    }
+
+    int bit_length(uint64_t v) { int b = 0; while (v) { ++b; v >>= 1; } return b; }
+  }
+
+  void coal(lcx_engine *e, real_t dt_sub, const lcx_rng *r)
+  {
+    if (!e->grouped) throw error("coalescence requested while super-droplets are not grouped by cell");
+    const size_t n = e->n_part;
+    if (n < 2) return;
+    const grid_t &g = e->grid;
+    sd_arrays &s = e->S();
+
+    rng_src rng;
+    rng.mode = r->mode; rng.un = nullptr; rng.u01 = nullptr; rng.seed = r->seed; rng.call = r->call;
+    if (r->mode == LCX_RNG_INJECT)
+    {
+      if (!r->un || !r->u01) throw error("lcx_coal: injected random streams are missing");
+      LCX_CUDA(cudaMemcpyAsync(e->un.p, r->un, n * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+      LCX_CUDA(cudaMemcpyAsync(e->u01.p, r->u01, n * sizeof(real_t), cudaMemcpyHostToDevice, e->stream));
+      rng.un = e->un.p; rng.u01 = e->u01.p;
+    }
+
+    coal_ctx cx;
+    cx.n = s.n.p; cx.rw2 = s.rw2.p; cx.rd3 = s.rd3.p; cx.vt = s.vt.p; cx.kpa = s.kpa.p;
+    cx.dv = e->dv.p;
+    cx.kp.kind = e->cfg.kernel;
+    cx.kp.has_multiplier = (e->cfg.kernel == KERNEL_GEOMETRIC && e->cfg.n_kernel_user_params == 1);
+    cx.kp.user0 = e->cfg.n_kernel_user_params > 0 ? real_t(e->cfg.kernel_user_params[0]) : real_t(0);
+    cx.kp.r_max = real_t(e->cfg.kernel_r_max);
+    cx.kp.eff = e->eff.p;
+    cx.dt = dt_sub;
+    cx.multi_kappa = e->cfg.multi_kappa;
+    cx.pure_const_multi = e->cfg.pure_const_multi;
+    cx.sc = e->scalars.p;
+
+    if (e->max_count <= SMALL_MAX)
+    {
+      LCX_LAUNCH(e, k_coal_small, div_up(g.n_cell, WARPS), TPB, 0, g.n_cell, e->cell_off.p, s.sid.p, rng, cx);
+      return;
+    }
+
+    // global path: stable LSD sort by storage index, then random key, then cell
+    int in = 0;
+    LCX_LAUNCH(e, k_fill_sid_keys, div_up(n, TPB), TPB, 0, n, s.sid.p, e->key[in].p, e->val[in].p);
+    in = radix_sort_pairs(e, n, 0, bit_length(e->sid_dense ? n - 1 : 0xffffffffull), in);
+    LCX_LAUNCH(e, k_keys_from_un, div_up(n, TPB), TPB, 0, n, s.sid.p, e->val[in].p, rng, e->key[in].p);
+    in = radix_sort_pairs(e, n, 0, 32, in);
+    if (g.n_cell > 1)
+    {
+      LCX_LAUNCH(e, k_keys_from_ijk, div_up(n, TPB), TPB, 0, n, s.ijk.p, e->val[in].p, e->key[in].p);
+      in = radix_sort_pairs(e, n, 0, bit_length(g.n_cell - 1), in);
+    }
+    LCX_LAUNCH(e, k_coal_big, div_up(n, TPB), TPB, 0, n, e->cell_off.p, s.ijk.p, e->val[in].p, rng, cx);
+  }
+}

@@ -1,0 +1,210 @@
+// Internal definition of the engine behind include/lcx_b200.h: device buffers, launch helpers and the
+// declarations shared by the translation units (lcx_api.cu, lcx_sort.cu, lcx_cells.cu, lcx_cond.cu,
+// lcx_coal.cu, lcx_transport.cu, lcx_layout.cu, lcx_diag.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/lcx_b200.h"
+#include "lcx_physics.h"
+
+namespace lcx
+{
+  typedef double real_t;          // v1 instantiates the double-precision engine only
+  typedef uint32_t idx_t;         // SD indices / cell indices / storage indices (n_sd_max < 2^32 per slab)
+
+  struct error : std::runtime_error { explicit error(const std::string &s) : std::runtime_error(s) {} };
+
+  inline void cuda_check(cudaError_t st, const char *what, const char *file, int line)
+  {
+    if (st != cudaSuccess)
+      throw error(std::string(what) + ": " + cudaGetErrorString(st) + " (" + file + ":" + std::to_string(line) + ")");
+  }
+#define LCX_CUDA(call) ::lcx::cuda_check((call), #call, __FILE__, __LINE__)
+
+  // raw device allocation with a size, freed by the engine
+  template <class T>
+  struct dbuf
+  {
+    T *p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count)
+    {
+      release();
+      n = count;
+      if (count) LCX_CUDA(cudaMalloc(reinterpret_cast<void **>(&p), count * sizeof(T)));
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    size_t bytes() const { return n * sizeof(T); }
+  };
+
+  // one set of per-SD arrays (structure of arrays)
+  struct sd_arrays
+  {
+    dbuf<n_t> n;
+    dbuf<real_t> rd3, rw2, kpa, vt, x, y, z;
+    dbuf<idx_t> sid, ijk;
+    void alloc(size_t cap, bool has_x, bool has_y, bool has_z)
+    {
+      n.alloc(cap); rd3.alloc(cap); rw2.alloc(cap); kpa.alloc(cap); vt.alloc(cap);
+      if (has_x) x.alloc(cap);
+      if (has_y) y.alloc(cap);
+      if (has_z) z.alloc(cap);
+      sid.alloc(cap); ijk.alloc(cap);
+    }
+    void release()
+    { n.release(); rd3.release(); rw2.release(); kpa.release(); vt.release(); x.release(); y.release(); z.release(); sid.release(); ijk.release(); }
+  };
+
+  // grid description handed to kernels by value
+  struct grid_t
+  {
+    int n_dims, nx, ny, nz;
+    real_t dx, dy, dz, x0, y0, z0, x1, y1, z1;
+    idx_t n_cell;
+    int halo_size;          // cells of x-halo on each side of the Courant fields (2 for pred_corr, else 0)
+    idx_t halo_x;           // halo_size * (cells per x-column): offset of the first real cell in halo-extended numbering
+  };
+
+  // device-side scalars that kernels produce and the host occasionally reads back
+  struct dev_scalars
+  {
+    unsigned int n_part;            // live SDs after the last lcx_post_copy
+    unsigned int max_count;         // largest per-cell SD count
+    unsigned int n_lft, n_rgt;      // migrants found by the last lcx_migr_pack
+    unsigned int increase_sstp_coal;
+    unsigned int pad;
+    unsigned long long n_collisions, n_pairs_collided;
+    double puddle[8];               // liq_vol, dry_vol, liq_num, prtcl_num (+spare), accumulated
+  };
+}
+
+struct lcx_engine
+{
+  lcx_config cfg;
+  lcx::grid_t grid;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint64_t launches = 0;
+
+  size_t cap = 0;                // n_sd_max
+  size_t n_part = 0;             // live SDs (host copy)
+  size_t n_tail = 0;             // SDs appended (migration) since the last post_copy, already counted in n_part
+  unsigned max_count = 0;        // host copy of the largest cell population
+  bool grouped = false;          // SD arrays physically grouped by cell, cell_off valid
+  bool sid_dense = true;
+
+  lcx::sd_arrays sd[2];          // current / alternate (re-layout target)
+  int cur = 0;
+  lcx::sd_arrays &S() { return sd[cur]; }
+  lcx::sd_arrays &A() { return sd[cur ^ 1]; }
+
+  // per-SD scratch
+  lcx::dbuf<uint32_t> key[2], val[2], un, flag;
+  lcx::dbuf<lcx::real_t> u01, n_filtered, tmp_real;
+  lcx::dbuf<uint32_t> perm;      // sorted position -> physical index (big-cell coalescence)
+
+  // per-cell
+  lcx::dbuf<lcx::real_t> th, rv, rhod, p, T, RH, eta, dv, lambda_D, lambda_K;
+  lcx::dbuf<lcx::real_t> sstp_tmp_rv, sstp_tmp_th, sstp_tmp_rh;
+  lcx::dbuf<lcx::real_t> drw_mom3, rw_mom3, count_mom, mom_partial;
+  lcx::dbuf<lcx::real_t> courant_x, courant_y, courant_z, w_LS;
+  lcx::dbuf<uint32_t> cell_off;  // n_cell + 2 entries: start of each cell's segment; [n_cell] = n_part, [n_cell+1] = total incl. dead
+
+  // tables
+  lcx::dbuf<lcx::real_t> vt0, eff;
+
+  // radix-sort / scan scratch
+  lcx::dbuf<uint32_t> hist, scan_tmp;
+
+  // migration buffers: [side][incoming]
+  lcx::dbuf<lcx::n_t> mig_n[2][2];
+  lcx::dbuf<lcx::real_t> mig_real[2][2];
+  lcx::dbuf<uint32_t> mig_ids[2];
+  size_t mig_cap = 0;
+
+  lcx::dbuf<lcx::dev_scalars> scalars;
+  lcx::dev_scalars *h_scalars = nullptr;   // pinned host mirror
+
+  lcx::dbuf<double> red_partial;           // deterministic two-pass reductions
+
+  bool selected = false;                   // a selector filled n_filtered
+
+  // optional per-kernel timing (CUDA events around every launch on the engine's stream), used by bench.py
+  struct prof_rec { const char *name; cudaEvent_t t0, t1; };
+  bool profiling = false;
+  std::vector<prof_rec> prof;
+  cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+
+  ~lcx_engine();
+};
+
+namespace lcx
+{
+  inline unsigned div_up(size_t a, size_t b) { return unsigned((a + b - 1) / b); }
+
+  // ---- lcx_sort.cu -----------------------------------------------------------------------------------
+  // exclusive prefix sum of n uint32 values, in place
+  void exclusive_scan_u32(lcx_engine *e, uint32_t *data, size_t n);
+  // stable LSD radix sort of (key, value) pairs on bits [bit_lo, bit_hi); result ends in key[*out]/val[*out]
+  // (ping-pong between the two buffers of e->key / e->val; `in` is the buffer that holds the input)
+  int radix_sort_pairs(lcx_engine *e, size_t n, int bit_lo, int bit_hi, int in);
+
+  // ---- lcx_layout.cu ---------------------------------------------------------------------------------
+  void compute_cell_offsets(lcx_engine *e, const uint32_t *sorted_keys, size_t n_total);
+  void post_copy(lcx_engine *e, bool rcyc, bool keep_all);
+  void scatter_attr_by_sid(lcx_engine *e, int attr, real_t *dst);
+
+  // ---- lcx_cells.cu ----------------------------------------------------------------------------------
+  void hskpng_Tpr(lcx_engine *e);
+  void hskpng_mfp(lcx_engine *e);
+  void hskpng_vterm(lcx_engine *e, bool only_invalid);
+  void sstp_percell_step(lcx_engine *e, int step, int sstp, bool var_rho);
+  void sstp_save(lcx_engine *e);
+  void update_th_rv(lcx_engine *e);
+
+  // ---- lcx_diag.cu -----------------------------------------------------------------------------------
+  // per-cell sum over the cell's SDs of weight(i) * pow(attr(i), power); weight = n (as real) or n_filtered
+  void cell_moment(lcx_engine *e, const real_t *weight_or_null, const real_t *attr, real_t power, bool specific, real_t *out);
+  void moms_select(lcx_engine *e, int kind, int attr, real_t lo, real_t hi, bool cons);
+  void diag_sd_conc(lcx_engine *e);
+  void diag_precip_rate(lcx_engine *e);
+  void diag_max_rw(lcx_engine *e);
+
+  // ---- lcx_cond.cu -----------------------------------------------------------------------------------
+  void cond(lcx_engine *e, real_t dt_sub, real_t RH_max, int step, int sstp);
+
+  // ---- lcx_coal.cu -----------------------------------------------------------------------------------
+  void coal(lcx_engine *e, real_t dt_sub, const lcx_rng *rng);
+
+  // ---- lcx_transport.cu ------------------------------------------------------------------------------
+  void transport(lcx_engine *e, const lcx_transport_opts *o);
+  void migr_pack(lcx_engine *e, int64_t *n_lft, int64_t *n_rgt);
+  void migr_unpack(lcx_engine *e, int side, int64_t count);
+
+  real_t *attr_ptr(lcx_engine *e, int attr);
+}
+
+#define LCX_LAUNCH(e, kernel, grid, block, smem, ...)                          \
+  do {                                                                         \
+    lcx_engine::prof_rec lcx_pr_ = {#kernel, nullptr, nullptr};                \
+    if ((e)->profiling) {                                                      \
+      LCX_CUDA(cudaEventCreate(&lcx_pr_.t0));                                  \
+      LCX_CUDA(cudaEventCreate(&lcx_pr_.t1));                                  \
+      LCX_CUDA(cudaEventRecord(lcx_pr_.t0, (e)->stream));                      \
+    }                                                                          \
+    kernel<<<(grid), (block), (smem), (e)->stream>>>(__VA_ARGS__);             \
+    LCX_CUDA(cudaGetLastError());                                              \
+    if ((e)->profiling) {                                                      \
+      LCX_CUDA(cudaEventRecord(lcx_pr_.t1, (e)->stream));                      \
+      (e)->prof.push_back(lcx_pr_);                                            \
+    }                                                                          \
+    ++(e)->launches;                                                           \
+  } while (0)

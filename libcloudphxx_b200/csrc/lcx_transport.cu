@@ -1,0 +1,372 @@
+// Super-droplet transport in one sweep: advection on the Arakawa-C Courant fields (implicit / explicit Euler /
+// predictor-corrector), sedimentation, large-scale subsidence, boundary conditions with precipitation
+// accounting, and detection of SDs that left the x-slab.  Plus the x-slab migration pack / unpack kernels.
+//
+// Reference: src/impl/advection/particles_impl_adve.ipp:27-304, src/impl/sedimentation/particles_impl_sedi.ipp:13-24,
+//            src/impl/subsidence/particles_impl_subs.ipp:13-25, src/impl/boundary_conditions/particles_impl_bcnd.ipp:99-368,
+//            src/impl/initialization/particles_impl_init_grid.ipp:93-155 (face-index tables, evaluated arithmetically here),
+//            src/impl/distributed_memory/particles_impl_pack.ipp:15-121, particles_impl_unpack.ipp:15-145,
+//            src/impl_multi_gpu/particles_multi_gpu_impl_step_async_and_copy.ipp:100-140.
+//
+// The reference spends ~20 Thrust passes (plus 4 device-wide reductions for the puddle) on this; here every SD is
+// read once (x, y, z, vt, ijk, n: 48 B) and written once (x, y, z, n: 32 B).  Arithmetic order follows the reference
+// so positions agree bit for bit (compile with -fmad=false).
+#include "lcx_engine.cuh"
+
+namespace lcx
+{
+  namespace
+  {
+    constexpr int TPB = 256;
+
+    struct tr_params
+    {
+      grid_t g;
+      int adve, sedi, subs, scheme;
+      real_t dt;
+      int open_side_walls, periodic_topbot, bcond_lft, bcond_rgt;
+    };
+
+    __device__ __forceinline__ real_t periodic_wrap(real_t x, real_t a, real_t b)   // bcnd.ipp:99-110
+    { return a + fmod((x - a) + 10 * (b - a), b - a); }
+
+    __device__ __forceinline__ real_t step_impl(real_t x, idx_t i, real_t C_l, real_t C_r, real_t dx)   // adve.ipp:27-60
+    { return (x + dx * (C_l - i * (C_r - C_l))) / (1 - (C_r - C_l)); }
+
+    __device__ __forceinline__ real_t step_expl(real_t x, idx_t i, real_t C_l, real_t C_r, real_t dx, bool apply)   // adve.ipp:62-93
+    { return apply * x + (C_r - C_l) * (x - dx * i) + dx * C_l; }
+
+    // staggered-field indices of the two faces of (halo-extended) cell cp in each direction: init_grid.ipp:93-155
+    struct faces { idx_t xl, xr, yl, yr, zl, zr; };
+    __device__ __forceinline__ faces faces_of(const grid_t &g, idx_t cp)
+    {
+      faces f;
+      f.xl = cp;
+      f.xr = cp + (g.n_dims == 3 ? idx_t(g.nz) * g.ny : idx_t(g.nz));
+      f.yl = f.yr = f.zl = f.zr = 0;
+      if (g.n_dims == 3)
+      {
+        const idx_t col = idx_t(g.nz) * g.ny;
+        f.yl = cp + (cp / col) * g.nz;
+        f.yr = f.yl + g.nz;
+        f.zl = cp + g.ny * (cp / col) + (cp - (cp / col) * col) / g.nz;
+        f.zr = f.zl + 1;
+      }
+      else if (g.n_dims == 2)
+      {
+        f.zl = cp + cp / g.nz;
+        f.zr = f.zl + 1;
+      }
+      return f;
+    }
+
+    __device__ __forceinline__ idx_t cell_of(const grid_t &g, real_t x, real_t y, real_t z, idx_t &i, idx_t &j, idx_t &k)   // hskpng_ijk.ipp:159-200
+    {
+      i = g.nx ? idx_t(size_t(double(x) / double(g.dx))) : 0;
+      j = g.ny ? idx_t(size_t(double(y) / double(g.dy))) : 0;
+      k = g.nz ? idx_t(size_t(double(z) / double(g.dz))) : 0;
+      switch (g.n_dims)
+      {
+        case 1: return i;
+        case 2: return i * g.nz + k;
+        case 3: return i * (idx_t(g.nz) * g.ny) + j * g.nz + k;
+        default: return 0;
+      }
+    }
+
+    __global__ void __launch_bounds__(TPB) k_transport(size_t n_part, tr_params P,
+                                                      real_t *__restrict__ xs, real_t *__restrict__ ys, real_t *__restrict__ zs,
+                                                      const real_t *__restrict__ vt, const idx_t *__restrict__ ijk, n_t *__restrict__ ns,
+                                                      const real_t *__restrict__ rw2, const real_t *__restrict__ rd3,
+                                                      const real_t *__restrict__ Cx, const real_t *__restrict__ Cy, const real_t *__restrict__ Cz,
+                                                      const real_t *__restrict__ w_LS, uint32_t *__restrict__ flag, double *__restrict__ partial)
+    {
+      __shared__ double red[4][TPB / 32];
+      const grid_t &g = P.g;
+      const size_t t = size_t(blockIdx.x) * TPB + threadIdx.x;
+      double pud[4] = {0, 0, 0, 0};   // liquid volume, dry volume, liquid number, particle number leaving through z0
+
+      if (t < n_part)
+      {
+        const idx_t c = ijk[t];
+        idx_t i = 0, j = 0, k = 0;
+        switch (g.n_dims)
+        {
+          case 1: i = c; break;
+          case 2: i = c / g.nz; k = c % g.nz; break;
+          case 3: i = c / (idx_t(g.nz) * g.ny); j = (c / g.nz) % g.ny; k = c % g.nz; break;
+        }
+        real_t x = g.nx ? xs[t] : 0, y = g.ny ? ys[t] : 0, z = g.nz ? zs[t] : 0;
+        n_t n = ns[t];
+
+        if (P.adve && g.n_dims > 0)
+        {
+          if (P.scheme == AS_IMPLICIT || P.scheme == AS_EULER)
+          {
+            const faces f = faces_of(g, c + g.halo_x);
+            if (P.scheme == AS_IMPLICIT)
+            {
+              x = step_impl(x, i, Cx[f.xl], Cx[f.xr], g.dx);
+              if (g.n_dims > 2) y = step_impl(y, j, Cy[f.yl], Cy[f.yr], g.dy);
+              if (g.n_dims > 1) z = step_impl(z, k, Cz[f.zl], Cz[f.zr], g.dz);
+            }
+            else
+            {
+              x = step_expl(x, i, Cx[f.xl], Cx[f.xr], g.dx, true);
+              if (g.n_dims > 2) y = step_expl(y, j, Cy[f.yl], Cy[f.yr], g.dy, true);
+              if (g.n_dims > 1) z = step_expl(z, k, Cz[f.zl], Cz[f.zr], g.dz, true);
+            }
+          }
+          else   // predictor-corrector in halo-shifted coordinates: adve.ipp:183-303
+          {
+            x = x + real_t(g.halo_size) * g.dx;
+            idx_t ih, jh, kh;
+            idx_t ch = cell_of(g, x, y, z, ih, jh, kh);
+            real_t x_old = x, y_old = y, z_old = z;
+            faces f = faces_of(g, ch);
+            x = step_expl(x, ih, Cx[f.xl], Cx[f.xr], g.dx, true);
+            if (g.n_dims > 2) y = step_expl(y, jh, Cy[f.yl], Cy[f.yr], g.dy, true);
+            if (g.n_dims > 1) z = step_expl(z, kh, Cz[f.zl], Cz[f.zr], g.dz, true);
+            if (g.n_dims > 1)
+            {
+              if (z >= g.z1) z = g.z1 - 1e-8 * g.dz;
+              if (z <= g.z0) z = g.z0 + 1e-8 * g.dz;
+            }
+            if (g.n_dims == 3)
+            {
+              if (y >= g.y1) y_old = y_old + (g.y1 - g.y0);
+              if (y < g.y0)  y_old = y_old - (g.y1 - g.y0);
+              y = periodic_wrap(y, g.y0, g.y1);
+            }
+            ch = cell_of(g, x, y, z, ih, jh, kh);
+            x_old = x + x_old;
+            if (g.n_dims > 2) y_old = y + y_old;
+            if (g.n_dims > 1) z_old = z + z_old;
+            f = faces_of(g, ch);
+            x = step_expl(x, ih, Cx[f.xl], Cx[f.xr], g.dx, false);
+            if (g.n_dims > 2) y = step_expl(y, jh, Cy[f.yl], Cy[f.yr], g.dy, false);
+            if (g.n_dims > 1) z = step_expl(z, kh, Cz[f.zl], Cz[f.zr], g.dz, false);
+            x = (x + x_old) / real_t(2.);
+            if (g.n_dims > 2) y = (y + y_old) / real_t(2.);
+            if (g.n_dims > 1) z = (z + z_old) / real_t(2.);
+            x = x - real_t(g.halo_size) * g.dx;
+          }
+        }
+
+        if (P.sedi) z = z - P.dt * vt[t];            // sedi.ipp:18-23 (vt may be the -1 "invalid" marker, as in the reference)
+        if (P.subs) z = z - P.dt * w_LS[k];          // subs.ipp:18-23 (k from before the move)
+
+        uint32_t fl = 0;
+        if (g.n_dims > 0)
+        {
+          // x walls: bcnd.ipp:124-195
+          if (P.bcond_lft == LCX_BCOND_SHAREDMEM && P.bcond_rgt == LCX_BCOND_SHAREDMEM)
+          {
+            if (!P.open_side_walls) x = periodic_wrap(x, g.x0, g.x1);
+            else if (x >= g.x1 || x < g.x0) n = 0;
+          }
+          else
+          {
+            if (x < g.x0)       { if (P.bcond_lft == LCX_BCOND_OPEN) n = 0; else fl = 1; }
+            else if (x >= g.x1) { if (P.bcond_rgt == LCX_BCOND_OPEN) n = 0; else fl = 2; }
+          }
+          // y walls: bcnd.ipp:197-219
+          if (g.n_dims == 3)
+          {
+            if (!P.open_side_walls) y = periodic_wrap(y, g.y0, g.y1);
+            else if (y >= g.y1 || y < g.y0) n = 0;
+          }
+          // z walls: bcnd.ipp:221-364
+          if (g.n_dims > 1)
+          {
+            if (!P.periodic_topbot)
+            {
+              if (z >= g.z1) n = 0;
+              if (z < g.z0)
+              {
+                const real_t nf = real_t(n);
+                const real_t r2 = rw2[t];
+                pud[0] = count_vol(nf, r2, real_t(3. / 2.));
+                pud[1] = count_vol(nf, rd3[t], real_t(1.));
+                pud[2] = (r2 == real_t(0)) ? 0. : nf;
+                pud[3] = nf;
+                n = 0;
+              }
+            }
+            else z = periodic_wrap(z, g.z0, g.z1);
+          }
+        }
+
+        if (g.nx) xs[t] = x;
+        if (g.ny) ys[t] = y;
+        if (g.nz) zs[t] = z;
+        ns[t] = n;
+        flag[t] = fl;
+      }
+
+      // deterministic block sums of the precipitation terms (second pass: k_puddle_final)
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+      {
+        double v = pud[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v;
+      }
+      __syncthreads();
+      if (threadIdx.x < 4)
+      {
+        double s = 0;
+        for (int w = 0; w < TPB / 32; ++w) s += red[threadIdx.x][w];
+        partial[size_t(threadIdx.x) * gridDim.x + blockIdx.x] = s;
+      }
+    }
+
+    __global__ void __launch_bounds__(TPB) k_puddle_final(unsigned n_blocks, const double *__restrict__ partial, dev_scalars *sc)
+    {
+      __shared__ double red[TPB];
+      for (int q = 0; q < 4; ++q)
+      {
+        double s = 0;
+        for (unsigned b = threadIdx.x; b < n_blocks; b += TPB) s += partial[size_t(q) * n_blocks + b];
+        red[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = TPB / 2; o > 0; o >>= 1) { if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o]; __syncthreads(); }
+        if (threadIdx.x == 0) sc->puddle[q] += red[0];
+        __syncthreads();
+      }
+    }
+
+    // ---- migration ---------------------------------------------------------------------------------------
+    __global__ void __launch_bounds__(TPB) k_mig_collect(size_t n_part, uint32_t which, const uint32_t *__restrict__ flag, const idx_t *__restrict__ sid,
+                                                        uint32_t *__restrict__ key, uint32_t *__restrict__ val, unsigned int *counter)
+    {
+      const size_t t = size_t(blockIdx.x) * TPB + threadIdx.x;
+      if (t >= n_part || flag[t] != which) return;
+      const unsigned slot = atomicAdd(counter, 1u);
+      key[slot] = sid[t];          // order is fixed afterwards by sorting on the storage index
+      val[slot] = uint32_t(t);
+    }
+
+    struct mig_attrs { const real_t *src[7]; int n; int x_slot; };
+
+    __global__ void __launch_bounds__(TPB) k_mig_pack(unsigned count, const uint32_t *__restrict__ val, mig_attrs A, n_t *__restrict__ ns,
+                                                     real_t lcl, real_t rmt, n_t *__restrict__ out_n, real_t *__restrict__ out_real)
+    {
+      const unsigned jx = blockIdx.x * TPB + threadIdx.x;
+      if (jx >= count) return;
+      const uint32_t ph = val[jx];
+      out_n[jx] = ns[ph];
+      for (int a = 0; a < A.n; ++a)
+      {
+        real_t v = A.src[a][ph];
+        if (a == A.x_slot) v = rmt + v - lcl;                 // remote coordinate: pack.ipp:15-26
+        out_real[size_t(a) * count + jx] = v;
+      }
+      ns[ph] = 0;                                             // flag_lft / flag_rgt: unpack.ipp:122-145
+    }
+
+    struct mig_dst { real_t *dst[7]; int n; int x_slot; };
+
+    __global__ void __launch_bounds__(TPB) k_mig_unpack(unsigned count, size_t n_part_old, mig_dst A, n_t *__restrict__ ns, idx_t *__restrict__ sid,
+                                                       const n_t *__restrict__ in_n, const real_t *__restrict__ in_real,
+                                                       real_t x0, real_t x1, real_t tol, int from_right)
+    {
+      const unsigned jx = blockIdx.x * TPB + threadIdx.x;
+      if (jx >= count) return;
+      const size_t d = n_part_old + jx;
+      ns[d] = in_n[jx];
+      sid[d] = idx_t(d);
+      for (int a = 0; a < A.n; ++a)
+      {
+        real_t v = in_real[size_t(a) * count + jx];
+        if (a == A.x_slot)
+        {
+          v = v >= x1 ? v - tol : v < x0 ? v + tol : v;       // tolerance_away_from_bcond: unpack.ipp:15-31,101
+          if (from_right && v == x1) v = nextafter(v, real_t(0.));   // step_async_and_copy.ipp:137
+        }
+        A.dst[a][d] = v;
+      }
+    }
+
+    int fill_attr_list(lcx_engine *e, real_t **list, int *x_slot)
+    {
+      sd_arrays &s = e->S();
+      int n = 0;
+      list[n++] = s.rd3.p; list[n++] = s.rw2.p; list[n++] = s.kpa.p; list[n++] = s.vt.p;
+      *x_slot = -1;
+      if (e->grid.nx) { *x_slot = n; list[n++] = s.x.p; }
+      if (e->grid.ny) list[n++] = s.y.p;
+      if (e->grid.nz) list[n++] = s.z.p;
+      return n;
+    }
+  }
+
+  void transport(lcx_engine *e, const lcx_transport_opts *o)
+  {
+    const size_t n = e->n_part;
+    if (n == 0 || e->grid.n_dims == 0) return;
+    sd_arrays &s = e->S();
+    tr_params P;
+    P.g = e->grid;
+    P.adve = o->adve; P.sedi = o->sedi && e->grid.nz; P.subs = o->subs && e->grid.nz; P.scheme = o->adve_scheme;
+    P.dt = real_t(o->dt);
+    P.open_side_walls = e->cfg.open_side_walls; P.periodic_topbot = e->cfg.periodic_topbot_walls;
+    P.bcond_lft = e->cfg.bcond_lft; P.bcond_rgt = e->cfg.bcond_rgt;
+    if (P.subs && e->w_LS.n < size_t(e->grid.nz)) throw error("subsidence requested but no w_LS profile was set");
+    if (P.scheme == AS_PRED_CORR && e->grid.halo_size != 2) throw error("predictor-corrector advection needs a 2-cell Courant halo");
+    const unsigned blocks = div_up(n, TPB);
+    if (e->red_partial.n < size_t(blocks) * 4) { LCX_CUDA(cudaStreamSynchronize(e->stream)); e->red_partial.alloc(size_t(blocks) * 4 + 1024); }
+    LCX_LAUNCH(e, k_transport, blocks, TPB, 0, n, P, s.x.p, s.y.p, s.z.p, s.vt.p, s.ijk.p, s.n.p, s.rw2.p, s.rd3.p,
+               e->courant_x.p, e->courant_y.p, e->courant_z.p, e->w_LS.p, e->flag.p, e->red_partial.p);
+    if (e->grid.n_dims > 1 && !e->cfg.periodic_topbot_walls)
+      LCX_LAUNCH(e, k_puddle_final, 1, TPB, 0, blocks, e->red_partial.p, e->scalars.p);
+    e->grouped = false;   // positions changed: cell segments are stale until lcx_post_copy
+  }
+
+  void migr_pack(lcx_engine *e, int64_t *n_lft, int64_t *n_rgt)
+  {
+    const size_t n = e->n_part;
+    sd_arrays &s = e->S();
+    *n_lft = *n_rgt = 0;
+    if (n == 0) return;
+    for (int side = 0; side < 2; ++side)
+    {
+      const int bc = side == 0 ? e->cfg.bcond_lft : e->cfg.bcond_rgt;
+      if (bc != LCX_BCOND_DISTMEM) continue;
+      unsigned int *counter = side == 0 ? &e->scalars.p->n_lft : &e->scalars.p->n_rgt;
+      LCX_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), e->stream));
+      LCX_LAUNCH(e, k_mig_collect, div_up(n, TPB), TPB, 0, n, uint32_t(side + 1), e->flag.p, s.sid.p, e->key[0].p, e->val[0].p, counter);
+      LCX_CUDA(cudaMemcpyAsync(e->h_scalars, e->scalars.p, sizeof(dev_scalars), cudaMemcpyDeviceToHost, e->stream));
+      LCX_CUDA(cudaStreamSynchronize(e->stream));
+      const unsigned count = side == 0 ? e->h_scalars->n_lft : e->h_scalars->n_rgt;
+      (side == 0 ? *n_lft : *n_rgt) = count;
+      if (count == 0) continue;
+      if (count > e->mig_cap) throw error("migration buffer overflow: " + std::to_string(count) + " super-droplets cross one slab face, capacity " + std::to_string(e->mig_cap));
+      int bits = 0; { uint64_t v = e->n_part ? e->n_part - 1 : 0; while (v) { ++bits; v >>= 1; } if (bits == 0) bits = 1; }
+      const int res = radix_sort_pairs(e, count, 0, bits, 0);
+      mig_attrs A; real_t *list[7];
+      A.n = fill_attr_list(e, list, &A.x_slot);
+      for (int a = 0; a < A.n; ++a) A.src[a] = list[a];
+      const real_t lcl = side == 0 ? e->grid.x0 : e->grid.x1;
+      const real_t rmt = side == 0 ? real_t(e->cfg.lft_x1) : real_t(e->cfg.rgt_x0);
+      LCX_LAUNCH(e, k_mig_pack, div_up(count, TPB), TPB, 0, count, e->val[res].p, A, s.n.p, lcl, rmt, e->mig_n[side][0].p, e->mig_real[side][0].p);
+    }
+  }
+
+  void migr_unpack(lcx_engine *e, int side, int64_t count)
+  {
+    if (count <= 0) return;
+    if (size_t(count) > e->mig_cap) throw error("migration buffer overflow on receive");
+    if (e->n_part + size_t(count) > e->cap)
+      throw error("n_sd_max (" + std::to_string(e->cap) + ") < n_part (" + std::to_string(e->n_part + size_t(count)) + ")");
+    sd_arrays &s = e->S();
+    mig_dst A; real_t *list[7];
+    A.n = fill_attr_list(e, list, &A.x_slot);
+    for (int a = 0; a < A.n; ++a) A.dst[a] = list[a];
+    LCX_LAUNCH(e, k_mig_unpack, div_up(size_t(count), TPB), TPB, 0, unsigned(count), e->n_part, A, s.n.p, s.sid.p,
+               e->mig_n[side][1].p, e->mig_real[side][1].p, e->grid.x0, e->grid.x1, real_t(5e-4), int(side == 0));
+    e->n_part += size_t(count);
+    e->grouped = false;
+  }
+}

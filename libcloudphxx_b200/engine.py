@@ -1,0 +1,112 @@
+"""ctypes view of the parts of the engine C ABI (include/lcx_b200.h) that Python-side plumbing needs:
+device timers, the per-kernel profile, launch counters and the x-slab migration hooks used when one process
+drives one GPU (torchrun) and torch.distributed moves the migrant buffers over NCCL/NVLink.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LCX_LIB_PATH = os.path.join(_HERE, "lib", "liblcx_b200.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LCX_LIB_PATH):
+            raise OSError("CUDA engine not built: %s is missing (there is no CPU fallback)" % LCX_LIB_PATH)
+        l = C.CDLL(LCX_LIB_PATH, mode=C.RTLD_GLOBAL)
+        l.lcx_last_error.restype = C.c_char_p
+        l.lcx_version.restype = C.c_char_p
+        l.lcx_timer_start.argtypes = [C.c_void_p]
+        l.lcx_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        l.lcx_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        l.lcx_profile_report.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+        l.lcx_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        l.lcx_n_part.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        l.lcx_sync.argtypes = [C.c_void_p]
+        l.lcx_cell_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        l.lcx_migr_pack.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        l.lcx_migr_buffers.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+        l.lcx_migr_real_attrs.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
+        l.lcx_migr_unpack.argtypes = [C.c_void_p, C.c_int, C.c_int64]
+        l.lcx_coal_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError(lib().lcx_last_error().decode())
+
+
+class Engine:
+    """non-owning handle of the lcx_engine behind a single-slab particle system"""
+
+    def __init__(self, handle):
+        if not handle:
+            raise RuntimeError("no engine behind this particle system")
+        self.h = C.c_void_p(handle)
+        self.l = lib()
+
+    def sync(self):
+        check(self.l.lcx_sync(self.h))
+
+    def timer_start(self):
+        check(self.l.lcx_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(self.l.lcx_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def launches(self):
+        v = C.c_uint64()
+        check(self.l.lcx_launch_count(self.h, C.byref(v)))
+        return v.value
+
+    def n_part(self):
+        v = C.c_int64()
+        check(self.l.lcx_n_part(self.h, C.byref(v)))
+        return v.value
+
+    def cell_stats(self):
+        a, b = C.c_int64(), C.c_int64()
+        check(self.l.lcx_cell_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def coal_stats(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        check(self.l.lcx_coal_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def profile(self, on):
+        check(self.l.lcx_profile_enable(self.h, int(on)))
+
+    def profile_report(self):
+        buf = C.create_string_buffer(1 << 16)
+        check(self.l.lcx_profile_report(self.h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, launches, ms = line.rsplit(" ", 2)
+            out[name] = (int(launches), float(ms))
+        return out
+
+    # ---- migration -------------------------------------------------------------------------------------------
+    def migr_pack(self):
+        a, b = C.c_int64(), C.c_int64()
+        check(self.l.lcx_migr_pack(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def migr_buffers(self, side, incoming):
+        n_buf, r_buf, cap = C.c_void_p(), C.c_void_p(), C.c_int64()
+        check(self.l.lcx_migr_buffers(self.h, side, int(incoming), C.byref(n_buf), C.byref(r_buf), C.byref(cap)))
+        return n_buf.value, r_buf.value, cap.value
+
+    def migr_real_attrs(self):
+        v = C.c_int()
+        check(self.l.lcx_migr_real_attrs(self.h, C.byref(v)))
+        return v.value
+
+    def migr_unpack(self, side, count):
+        check(self.l.lcx_migr_unpack(self.h, side, count))

@@ -1,0 +1,1035 @@
+// C++ host layer of the B200-native Lagrangian microphysics: the `lgrngn::factory` / `particles_proto_t`
+// implementation for the CUDA and multi_CUDA back-ends.  All device work goes through the C ABI of
+// include/lcx_b200.h (liblcx_b200.so); nothing here touches CUDA directly.
+//
+// What lives here (and which reference code it stands in for):
+//   * option checks, call-order state machine, error texts   src/particles_step.ipp:32-494, src/particles_init.ipp:16-131,
+//                                                            src/impl/initialization/particles_impl_init_sanity_check.ipp:14-176
+//   * Eulerian <-> Lagrangian index maps and field syncing    src/impl/initialization/particles_impl_init_e2l.ipp:34-114,
+//                                                            src/impl/particles_impl_sync.ipp:15-68
+//   * super-droplet initialisation from dry spectra            src/impl/initialization/particles_impl_init_{dist_analysis,
+//     (host side, same libm and the same mt19937 draw order     SD_with_distros_sd_conc,count_num,ijk,dry_sd_conc,n,wet,xyz}.ipp
+//     as the reference's CPU back-ends => bit-identical state)
+//   * random streams for coalescence                           src/detail/urand.hpp:19-88 (replay) or Philox in the kernels
+//   * x-slab decomposition and migration between devices        src/detail/distmem_opts.hpp:10-52,
+//                                                            src/impl_multi_gpu/particles_multi_gpu_impl.ipp:15-207,
+//                                                            src/impl_multi_gpu/particles_multi_gpu_impl_step_async_and_copy.ipp:28-206
+#include <libcloudph++/lgrngn/factory.hpp>
+
+#include "lcx_b200.h"
+#include "lcx_physics.h"
+#include "particles_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <fstream>
+#include <iostream>
+#include <limits>
+#include <random>
+#include <sstream>
+
+namespace libcloudphxx
+{
+  namespace lgrngn
+  {
+    namespace b200
+    {
+      // ---- process-wide settings (see particles_b200.h) ---------------------------------------------------
+      namespace
+      {
+        int initial_rng_mode()
+        {
+          const char *s = std::getenv("LCX_RNG");
+          if (s && (std::string(s) == "mt19937" || std::string(s) == "replay")) return LGRNGN_B200_RNG_MT19937;
+          return LGRNGN_B200_RNG_PHILOX;
+        }
+        int g_rng_mode = initial_rng_mode();
+        lgrngn_b200_distmem g_distmem = {0, 1, -1., -1., 0};
+
+        void chk(int rc) { if (rc != 0) throw std::runtime_error(std::string("libcloudph++ (B200 engine): ") + lcx_last_error()); }
+
+        std::string data_dir()
+        {
+          if (const char *s = std::getenv("LCX_DATA_DIR")) return s;
+          Dl_info info;
+          if (dladdr(reinterpret_cast<void *>(&initial_rng_mode), &info) && info.dli_fname)
+          {
+            std::string p(info.dli_fname);
+            const size_t slash = p.find_last_of('/');
+            p = (slash == std::string::npos) ? std::string(".") : p.substr(0, slash);
+            return p + "/../data";
+          }
+          return "data";
+        }
+
+        template <class real_t>
+        std::vector<real_t> load_efficiencies(const std::string &name)
+        {
+          const std::string path = data_dir() + "/" + name + ".f64";
+          std::ifstream f(path, std::ios::binary);
+          if (!f) throw std::runtime_error("libcloudph++: cannot open collision-efficiency table " + path);
+          f.seekg(0, std::ios::end);
+          const size_t bytes = size_t(f.tellg());
+          f.seekg(0);
+          std::vector<double> raw(bytes / sizeof(double));
+          f.read(reinterpret_cast<char *>(raw.data()), std::streamsize(raw.size() * sizeof(double)));
+          return std::vector<real_t>(raw.begin(), raw.end());
+        }
+
+        inline int m1(int n) { return n == 0 ? 1 : n; }
+      }
+
+      enum bcond_t { sharedmem = LCX_BCOND_SHAREDMEM, distmem = LCX_BCOND_DISTMEM, open = LCX_BCOND_OPEN };
+
+      // x-slab decomposition: src/detail/distmem_opts.hpp:10-52
+      template <class real_t>
+      int get_dev_nx(const opts_init_t<real_t> &o, int rank, int size)
+      {
+        if (rank < size - 1) return int(o.nx / size + .5);
+        return o.nx - rank * int(o.nx / size + .5);
+      }
+      template <class real_t>
+      int distmem_opts(opts_init_t<real_t> &o, int rank, int size)
+      {
+        const int n_x_bfr = rank * get_dev_nx(o, 0, size);
+        o.nx = get_dev_nx(o, rank, size);
+        if (rank != 0) o.x0 = 0.;
+        if (rank != size - 1) o.x1 = o.nx * o.dx;
+        else o.x1 = o.x1 - n_x_bfr * o.dx;
+        o.n_sd_max = o.n_sd_max / size + 1;
+        return n_x_bfr;
+      }
+
+      // ======================================================================================================
+      // one x-slab on one device: the reference's particles_t<real_t, CUDA>
+      // ======================================================================================================
+      template <class real_t>
+      struct slab
+      {
+        typedef unsigned long long n_t;
+
+        opts_init_t<real_t> oi;            // this slab's options
+        lcx_engine *e = nullptr;
+        int n_dims;
+        size_t n_cell;
+        int n_x_bfr = 0, n_x_tot = 0;
+        size_t n_cell_bfr = 0;
+        int halo_size, halo_x, halo_y, halo_z;
+        std::pair<int, int> bcond;
+        real_t lft_x1 = -1, rgt_x0 = -1;
+        bool spawned = false;              // part of a multi-slab run: migration and post_copy are driven from outside
+
+        bool init_called = false, should_now_run_async = false, should_now_run_cond = false, var_rho = false;
+        real_t dt;
+        int sstp_cond, sstp_coal;
+        as_t adve_scheme;
+        bool allow_sstp_cond, pure_const_multi;
+
+        int rng_mode;
+        std::mt19937 engine;               // one generator per object, as src/detail/urand.hpp:24,57
+        uint64_t philox_call = 0;
+        std::vector<uint32_t> un_host;
+        std::vector<real_t> u01_host;
+
+        struct map_t { std::vector<long> l2e; };
+        map_t m_th, m_rv, m_rhod, m_p, m_cx, m_cy, m_cz;
+        std::vector<real_t> stage, outbuf_host;
+        std::map<common::output_t, real_t> puddle0;
+
+        slab(const opts_init_t<real_t> &o, std::pair<int, int> bc, int n_x_tot_) : oi(o), bcond(bc)
+        {
+          oi.dev_count = 0;
+          n_dims = oi.nx / m1(oi.nx) + oi.ny / m1(oi.ny) + oi.nz / m1(oi.nz);
+          n_cell = size_t(m1(oi.nx)) * m1(oi.ny) * m1(oi.nz);
+          n_x_tot = n_x_tot_;
+          halo_size = oi.adve_scheme == as_t::pred_corr ? 2 : 0;
+          halo_x = n_dims == 1 ? halo_size : n_dims == 2 ? halo_size * oi.nz : halo_size * oi.nz * oi.ny;
+          halo_y = halo_size * (oi.ny + 1) * oi.nz;
+          halo_z = n_dims == 2 ? halo_size * (oi.nz + 1) : halo_size * (oi.nz + 1) * oi.ny;
+          adve_scheme = oi.adve_scheme;
+          sstp_cond = oi.sstp_cond; sstp_coal = oi.sstp_coal; dt = oi.dt;
+          allow_sstp_cond = oi.sstp_cond > 1 || oi.sstp_cond_act > 1;
+          pure_const_multi = (oi.sd_conc == 0) && (oi.sd_const_multi > 0 || oi.dry_sizes.size() > 0);
+          rng_mode = g_rng_mode;
+          engine.seed(oi.rng_seed);
+          unsupported_options();
+        }
+
+        ~slab() { if (e) lcx_destroy(e); }
+
+        void unsupported_options() const
+        {
+          // everything SURVEY.md section 8 marks out of scope is refused loudly instead of being ignored
+          if (oi.chem_switch) throw std::runtime_error("libcloudph++: aqueous chemistry (chem_switch) is not part of the B200 back-end");
+          if (oi.ice_switch) throw std::runtime_error("libcloudph++: ice microphysics (ice_switch) is not part of the B200 back-end");
+          if (oi.turb_adve_switch || oi.turb_cond_switch || oi.turb_coal_switch)
+            throw std::runtime_error("libcloudph++: SGS turbulence for super-droplets (turb_*_switch) is not part of the B200 back-end");
+          if (oi.src_type != src_t::off) throw std::runtime_error("libcloudph++: aerosol sources (src_type) are not part of the B200 back-end");
+          if (oi.rlx_switch) throw std::runtime_error("libcloudph++: aerosol relaxation (rlx_switch) is not part of the B200 back-end");
+          if (oi.exact_sstp_cond && (oi.sstp_cond > 1 || oi.sstp_cond_act > 1))
+            throw std::runtime_error("libcloudph++: per-particle condensation sub-stepping (exact_sstp_cond with sstp_cond > 1) is not available yet in the B200 back-end");
+          if (oi.diag_incloud_time) throw std::runtime_error("libcloudph++: diag_incloud_time is not part of the B200 back-end");
+          if (oi.kernel == kernel_t::onishi_hall || oi.kernel == kernel_t::onishi_hall_davis_no_waals)
+            throw std::runtime_error("libcloudph++: To use the turbulent Onishis kernel, set turb_coal_switch=True");
+          if (oi.sd_conc_large_tail || oi.sd_const_multi > 0 || oi.dry_sizes.size() > 0)
+            throw std::runtime_error("libcloudph++: only opts_init.sd_conc initialisation from dry_distros is available yet in the B200 back-end");
+          if (!oi.aerosol_conc_factor.empty())
+            throw std::runtime_error("libcloudph++: aerosol_conc_factor is not available yet in the B200 back-end");
+        }
+
+        bool is_distmem() const { return bcond.first == distmem || bcond.second == distmem; }
+
+        // ---- sanity checks of init(): init_sanity_check.ipp:14-176 (the applicable subset, same texts) --------
+        void init_sanity_check(const arrinfo_t<real_t> &th, const arrinfo_t<real_t> &rv, const arrinfo_t<real_t> &rhod,
+                               const arrinfo_t<real_t> &p, const arrinfo_t<real_t> &cx, const arrinfo_t<real_t> &cy,
+                               const arrinfo_t<real_t> &cz, size_t n_ambient_chem)
+        {
+          if (init_called) throw std::runtime_error("libcloudph++: init() may be called just once");
+          init_called = true;
+          if (th.is_null() || rv.is_null() || rhod.is_null())
+            throw std::runtime_error("libcloudph++: passing th, rv and rhod is mandatory");
+          check_courants(cx, cy, cz);
+          if (n_ambient_chem != 0) throw std::runtime_error("libcloudph++: chemistry was switched off and ambient_chem is not empty");
+          if (oi.dry_distros.size() == 0 && oi.dry_sizes.size() == 0)
+            throw std::runtime_error("libcloudph++: Both dry_distros and dry_sizes are undefined");
+          if (n_dims > 0)
+          {
+            if (!(oi.x0 >= 0 && oi.x0 < m1(oi.nx) * oi.dx)) throw std::runtime_error("libcloudph++: !(x0 >= 0 & x0 < min(1,nx)*dz)");
+            if (!(oi.y0 >= 0 && oi.y0 < m1(oi.ny) * oi.dy)) throw std::runtime_error("libcloudph++: !(y0 >= 0 & y0 < min(1,ny)*dy)");
+            if (!(oi.z0 >= 0 && oi.z0 < m1(oi.nz) * oi.dz)) throw std::runtime_error("libcloudph++: !(z0 >= 0 & z0 < min(1,nz)*dz)");
+            if (!(oi.y1 > oi.y0 && oi.y1 <= m1(oi.ny) * oi.dy)) throw std::runtime_error("libcloudph++: !(y1 > y0 & y1 <= min(1,ny)*dy)");
+            if (!(oi.z1 > oi.z0 && oi.z1 <= m1(oi.nz) * oi.dz)) throw std::runtime_error("libcloudph++: !(z1 > z0 & z1 <= min(1,nz)*dz)");
+          }
+          if (oi.dt == 0) throw std::runtime_error("libcloudph++: please specify opts_init.dt");
+          if (oi.sd_conc * oi.sd_const_multi != 0)
+            throw std::runtime_error("libcloudph++: specify either opts_init.sd_conc or opts_init.sd_const_multi, not both");
+          if (oi.sd_conc == 0 && oi.sd_const_multi == 0 && oi.dry_sizes.size() == 0)
+            throw std::runtime_error("libcloudph++: please specify opts_init.sd_conc, opts_init.sd_const_multi or opts_init.dry_sizes");
+          if (oi.coal_switch)
+          {
+            if (oi.terminal_velocity == vt_t::undefined)
+              throw std::runtime_error("libcloudph++: please specify opts_init.terminal_velocity or turn off opts_init.coal_switch");
+            if (oi.kernel == kernel_t::undefined) throw std::runtime_error("libcloudph++: please specify opts_init.kernel");
+          }
+          if (oi.sedi_switch && oi.terminal_velocity == vt_t::undefined)
+            throw std::runtime_error("libcloudph++: please specify opts_init.terminal_velocity or turn off opts_init.sedi_switch");
+          if (oi.sedi_switch && oi.nz == 0) throw std::runtime_error("libcloudph++: opts_init.sedi_switch can be True only if n_dims > 1");
+          if (oi.subs_switch && oi.nz == 0) throw std::runtime_error("libcloudph++: opts_init.subs_switch can be True only if n_dims > 1");
+          if (oi.subs_switch && size_t(oi.nz) != oi.w_LS.size())
+            throw std::runtime_error("libcloudph++: opts_init.subs_switch == True, but subsidence velocity profile size != nz");
+          if (oi.const_p && p.is_null())
+            throw std::runtime_error("libcloudph++: In const_p option, pressure profile must be passed (p in init())");
+          if (!oi.const_p && !p.is_null())
+            throw std::runtime_error("libcloudph++: pressure profile was passed in init(), but the constant pressure option was not used");
+          if (oi.sstp_cond < 1) throw std::runtime_error("libcloudph++: opts_init.sstp_cond needs to be greater than 0");
+          if (oi.adaptive_sstp_cond && !oi.exact_sstp_cond)
+            throw std::runtime_error("libcloudph++: Adaptive condensation substepping (opts_init.adaptive_sstp_cond) works oly for per-particle substepping (opts_init.exact_sstp_cond)");
+          if (!oi.sstp_cond_mix && !oi.exact_sstp_cond)
+            throw std::runtime_error("libcloudph++: Mixing of rv and th (opts_init.sstp_cond_mix) can only be disable for per-particle substepping (opts_init.exact_sstp_cond)");
+        }
+
+        void check_courants(const arrinfo_t<real_t> &cx, const arrinfo_t<real_t> &cy, const arrinfo_t<real_t> &cz) const
+        {
+          if (!cx.is_null() || !cy.is_null() || !cz.is_null())
+          {
+            if (n_dims == 0) throw std::runtime_error("libcloudph++: Courant numbers passed in 0D setup");
+            if (n_dims == 1 && (cx.is_null() || !cy.is_null() || !cz.is_null()))
+              throw std::runtime_error("libcloudph++: Only X Courant number allowed in 1D setup");
+            if (n_dims == 2 && (cx.is_null() || !cy.is_null() || cz.is_null()))
+              throw std::runtime_error("libcloudph++: Only X and Z Courant numbers allowed in 2D setup");
+            if (n_dims == 3 && (cx.is_null() || cy.is_null() || cz.is_null()))
+              throw std::runtime_error("libcloudph++: All XYZ Courant number components required in 3D setup");
+          }
+        }
+
+        // ---- Eulerian <-> Lagrangian index map: init_e2l.ipp:34-114 ---------------------------------------------
+        void init_e2l(const arrinfo_t<real_t> &arr, map_t &m, int field, int ext_x = 0, int ext_y = 0, int ext_z = 0, long offset = 0)
+        {
+          int64_t count = 0;
+          chk(lcx_field_size(e, field, &count));
+          m.l2e.resize(size_t(count));
+          const long shift = long(n_cell_bfr) + offset;
+          long max_stride = 0, max_stride_n_cell = 0;
+          switch (n_dims)
+          {
+            case 0: m.l2e[0] = 0; break;
+            case 1:
+              for (long q = 0; q < long(count); ++q) m.l2e[size_t(q)] = int(shift + q);
+              max_stride = 1; max_stride_n_cell = n_x_tot + ext_x;
+              break;
+            case 2:
+              for (long q = 0; q < long(count); ++q)
+              {
+                const int v = int(shift + q);
+                m.l2e[size_t(q)] = arr.strides[0] * (v / (oi.nz + ext_z)) + arr.strides[1] * (v % (oi.nz + ext_z));
+              }
+              max_stride = arr.strides[0]; max_stride_n_cell = n_x_tot + ext_x;
+              break;
+            case 3:
+              for (long q = 0; q < long(count); ++q)
+              {
+                const int v = int(shift + q);
+                m.l2e[size_t(q)] = arr.strides[0] * (v / ((oi.nz + ext_z) * (oi.ny + ext_y)))
+                                 + arr.strides[1] * ((v / (oi.nz + ext_z)) % (oi.ny + ext_y))
+                                 + arr.strides[2] * (v % (oi.nz + ext_z));
+              }
+              max_stride = std::max(arr.strides[0], arr.strides[1]);
+              max_stride_n_cell = max_stride == arr.strides[0] ? n_x_tot + ext_x : oi.ny + ext_y;
+              break;
+          }
+          const long n_tot = max_stride_n_cell * max_stride;
+          if (n_dims > 0)
+            for (long &l : m.l2e) { if (l >= n_tot) l -= n_tot; else if (l < 0) l += n_tot; }
+        }
+
+        void sync_in_field(const arrinfo_t<real_t> &from, const map_t &m, int field)   // impl_sync.ipp:15-40
+        {
+          if (from.is_null()) return;
+          stage.resize(m.l2e.size());
+          const real_t *src = from.data;
+          for (size_t q = 0; q < m.l2e.size(); ++q) stage[q] = src[m.l2e[q]];
+          chk(lcx_cells_set(e, field, stage.data(), int64_t(stage.size()), 0));
+        }
+        void sync_out_field(int field, const map_t &m, arrinfo_t<real_t> &to)           // impl_sync.ipp:42-68
+        {
+          if (to.is_null()) return;
+          stage.resize(m.l2e.size());
+          chk(lcx_cells_get(e, field, stage.data(), int64_t(stage.size())));
+          real_t *dst = to.data;
+          for (size_t q = 0; q < m.l2e.size(); ++q) dst[m.l2e[q]] = stage[q];
+        }
+
+        // ---- engine creation ------------------------------------------------------------------------------------
+        void create_engine()
+        {
+          lcx_config c;
+          std::memset(&c, 0, sizeof(c));
+          c.device = oi.dev_id;
+          c.real_bytes = sizeof(real_t);
+          c.nx = oi.nx; c.ny = oi.ny; c.nz = oi.nz;
+          c.dx = oi.dx; c.dy = oi.dy; c.dz = oi.dz;
+          c.x0 = oi.x0; c.y0 = oi.y0; c.z0 = oi.z0; c.x1 = oi.x1; c.y1 = oi.y1; c.z1 = oi.z1;
+          c.n_sd_max = oi.n_sd_max;
+          c.kernel = int(oi.kernel); c.terminal_velocity = int(oi.terminal_velocity);
+          c.adve_scheme = int(oi.adve_scheme); c.RH_formula = int(oi.RH_formula);
+          c.th_dry = oi.th_dry; c.const_p = oi.const_p;
+          c.n_kernel_user_params = int(std::min<size_t>(oi.kernel_parameters.size(), 4));
+          for (int q = 0; q < c.n_kernel_user_params; ++q) c.kernel_user_params[q] = oi.kernel_parameters[size_t(q)];
+          c.open_side_walls = oi.open_side_walls; c.periodic_topbot_walls = oi.periodic_topbot_walls;
+          c.bcond_lft = bcond.first; c.bcond_rgt = bcond.second;
+          c.lft_x1 = lft_x1; c.rgt_x0 = rgt_x0;
+          c.multi_kappa = (oi.dry_distros.size() + oi.dry_sizes.size() > 1);
+          c.pure_const_multi = pure_const_multi;
+          c.allow_sstp_cond = allow_sstp_cond;
+          std::vector<real_t> eff;
+          if (oi.coal_switch) eff = init_kernel(c);
+          chk(lcx_create(&c, &e));
+          if (!eff.empty()) chk(lcx_set_efficiencies(e, eff.data(), int64_t(eff.size())));
+        }
+
+        // kernel parameter checks and efficiency tables: init_kernel.ipp:6-235
+        std::vector<real_t> init_kernel(lcx_config &c) const
+        {
+          const size_t n_user = oi.kernel_parameters.size();
+          std::vector<real_t> eff;
+          auto table = [&](const char *name, const char *what, double r_max) {
+            if (n_user != 0) throw std::runtime_error(std::string("libcloudph++: ") + what + " kernel doesn't accept parameters.");
+            eff = load_efficiencies<real_t>(name);
+            c.kernel_r_max = r_max;
+          };
+          switch (oi.kernel)
+          {
+            case kernel_t::golovin:
+              if (n_user != 1) throw std::runtime_error("libcloudph++: Golovin kernel accepts exactly one parameter.");
+              break;
+            case kernel_t::geometric:
+              if (n_user > 1) throw std::runtime_error("libcloudph++: Geometric kernel accepts up to one parameter.");
+              break;
+            case kernel_t::Long:
+              if (n_user > 0) throw std::runtime_error("libcloudph++: Long kernel doesn't take parameters.");
+              break;
+            case kernel_t::hall:                      table("hall", "Hall", 300.); break;
+            case kernel_t::hall_davis_no_waals:       table("hall_davis_no_waals", "Hall + Davis", 1100.); break;
+            case kernel_t::vohl_davis_no_waals:       table("vohl_davis_no_waals", "Vohl + Davis", 0.); break;
+            case kernel_t::hall_pinsky_stratocumulus: table("hall_pinsky_stratocumulus", "Hall + Pinsky (stratocumulus)", 0.); break;
+            case kernel_t::hall_pinsky_1000mb_grav:   table("hall_pinsky_1000mb_grav", "Hall + Pinsky (gravitational 1000mb)", 0.); break;
+            case kernel_t::hall_pinsky_cumulonimbus:  table("hall_pinsky_cumulonimbus", "Hall + Pinsky (cumulonimbus)", 0.); break;
+            default: break;
+          }
+          if (!eff.empty())
+          {
+            // the first value of each data file is r_max [um] of that table (written by tools/extract_efficiencies.py)
+            c.kernel_r_max = double(eff.front());
+            eff.erase(eff.begin());
+          }
+          return eff;
+        }
+
+        // ---- init(): particles_init.ipp:16-131 -------------------------------------------------------------------
+        void init(const arrinfo_t<real_t> &th, const arrinfo_t<real_t> &rv, const arrinfo_t<real_t> &rhod, const arrinfo_t<real_t> &p,
+                  const arrinfo_t<real_t> &cx, const arrinfo_t<real_t> &cy, const arrinfo_t<real_t> &cz, size_t n_ambient_chem)
+        {
+          init_sanity_check(th, rv, rhod, p, cx, cy, cz, n_ambient_chem);
+          if (oi.rng_seed_init_switch) engine.seed(oi.rng_seed_init);
+          create_engine();
+
+          init_e2l(th, m_th, LCX_F_TH);
+          init_e2l(rv, m_rv, LCX_F_RV);
+          init_e2l(rhod, m_rhod, LCX_F_RHOD);
+          if (oi.const_p) init_e2l(p, m_p, LCX_F_P);
+          init_courant_maps(cx, cy, cz);
+
+          sync_in_field(th, m_th, LCX_F_TH);
+          sync_in_field(rv, m_rv, LCX_F_RV);
+          sync_in_field(rhod, m_rhod, LCX_F_RHOD);
+          if (oi.const_p) sync_in_field(p, m_p, LCX_F_P);
+          sync_in_field(cx, m_cx, LCX_F_COURANT_X);
+          sync_in_field(cy, m_cy, LCX_F_COURANT_Y);
+          sync_in_field(cz, m_cz, LCX_F_COURANT_Z);
+          if (oi.subs_switch) chk(lcx_cells_set(e, LCX_F_W_LS, oi.w_LS.data(), int64_t(oi.w_LS.size()), 0));
+
+          chk(lcx_hskpng_Tpr(e));
+
+          if (!oi.no_ccn_at_init && oi.dry_distros.size() > 0) init_SD_with_distros(th, rv, rhod, p);
+
+          if (oi.terminal_velocity == vt_t::beard77fast)
+          {
+            // cached sea-level fall speeds, evaluated on the host like the reference's CPU back-ends: init_vterm.ipp:36-59
+            const lcx::vt0_bins<real_t> bins;
+            std::vector<real_t> vt0(lcx::VT0_N_BIN);
+            for (int it = 0; it < lcx::VT0_N_BIN; ++it) vt0[size_t(it)] = lcx::vt_beard77_v0(bins.mid(it));
+            chk(lcx_set_vt0_table(e, vt0.data(), int(vt0.size())));
+          }
+          chk(lcx_hskpng_vterm(e, 1));
+          chk(lcx_sstp_save(e));
+          chk(lcx_post_copy(e, 0, /*keep_all=*/1));      // hskpng_count(): group by the cells assigned at creation
+          engine.seed(oi.rng_seed);
+          philox_call = 0;
+        }
+
+        void init_courant_maps(const arrinfo_t<real_t> &cx, const arrinfo_t<real_t> &cy, const arrinfo_t<real_t> &cz)
+        {
+          if (!cx.is_null()) init_e2l(cx, m_cx, LCX_F_COURANT_X, 1, 0, 0, -halo_x);
+          if (!cy.is_null()) init_e2l(cy, m_cy, LCX_F_COURANT_Y, 0, 1, 0, long(n_x_bfr) * oi.nz - halo_y);
+          if (!cz.is_null()) init_e2l(cz, m_cz, LCX_F_COURANT_Z, 0, 0, 1, long(n_x_bfr) * std::max(1, oi.ny) - halo_z);
+        }
+
+        // host copies of the per-cell state the initialisation needs, computed with the host libm
+        struct cell_state { std::vector<real_t> rhod, T, RH, dv; };
+
+        cell_state host_cells(const arrinfo_t<real_t> &th, const arrinfo_t<real_t> &rv, const arrinfo_t<real_t> &rhod, const arrinfo_t<real_t> &p) const
+        {
+          cell_state cs;
+          cs.rhod.resize(n_cell); cs.T.resize(n_cell); cs.RH.resize(n_cell); cs.dv.resize(n_cell);
+          for (size_t c = 0; c < n_cell; ++c)
+          {
+            const real_t th_c = th.data[m_th.l2e[c]], rv_c = rv.data[m_rv.l2e[c]], rhod_c = rhod.data[m_rhod.l2e[c]];
+            real_t T_c, p_c;
+            if (oi.th_dry) T_c = lcx::T_of_th_dry(th_c, rhod_c);
+            else           T_c = th_c * lcx::exner(p.data[m_p.l2e[c]]);
+            p_c = oi.const_p ? p.data[m_p.l2e[c]] : lcx::p_of_rhod_rv_T(rhod_c, rv_c, T_c);
+            cs.rhod[c] = rhod_c; cs.T[c] = T_c;
+            cs.RH[c] = lcx::RH_of(int(oi.RH_formula), p_c, rv_c, T_c);
+            if (n_dims == 0) cs.dv[c] = real_t(1) / rhod_c;
+            else
+            {
+              const int ic = int(c), nz1 = std::max(1, oi.nz), ny1 = std::max(1, oi.ny);
+              const int i = (ic / nz1) / ny1, j = (ic / nz1) % ny1, k = ic % nz1;
+              cs.dv[c] = std::max(real_t(0),
+                (std::min((i + 1) * oi.dx, oi.x1) - std::max(i * oi.dx, oi.x0)) *
+                (std::min((j + 1) * oi.dy, oi.y1) - std::max(j * oi.dy, oi.y0)) *
+                (std::min((k + 1) * oi.dz, oi.z1) - std::max(k * oi.dz, oi.z0)));
+            }
+          }
+          return cs;
+        }
+
+        // range of ln(rd) that the super-droplets of one spectrum must cover: init_dist_analysis.ipp:17-75
+        void dist_analysis_sd_conc(const common::unary_function<real_t> &fun, const cell_state &cs,
+                                   real_t &log_rd_min, real_t &log_rd_max, real_t &multiplier) const
+        {
+          const n_t sd_conc = oi.sd_conc;
+          const real_t dt_ = 1;
+          const real_t vol = n_dims == 0 ? cs.dv[0] : (oi.dx * oi.dy * oi.dz);
+          if (oi.rd_min >= 0 && oi.rd_max >= 0)
+          {
+            const real_t rd_min = oi.rd_min, rd_max = oi.rd_max;
+            multiplier = std::log(rd_max / rd_min) / sd_conc * dt_ * vol;
+            log_rd_min = std::log(rd_min);
+            log_rd_max = std::log(rd_max);
+            return;
+          }
+          if (!(oi.rd_min < 0 && oi.rd_max < 0)) throw std::runtime_error("libcloudph++: opts_init.rd_min * opts_init.rd_max < 0");
+          const real_t rd_min_init = 1e-14, rd_max_init = 1e-3;      // src/detail/config.hpp:23-24
+          real_t rd_min = rd_min_init, rd_max = rd_max_init;
+          bool found = false;
+          while (!found)
+          {
+            multiplier = std::log(rd_max / rd_min) / sd_conc * dt_ * vol;
+            log_rd_min = std::log(rd_min);
+            log_rd_max = std::log(rd_max);
+            const n_t n_min = n_t(fun(log_rd_min) * multiplier), n_max = n_t(fun(log_rd_max) * multiplier);
+            if (rd_min == rd_min_init && n_min != 0)
+            { std::ostringstream s; s << "Initial dry radii distribution is non-zero (" << n_min << ") for rd_min_init (" << rd_min_init << ")"; throw std::runtime_error(s.str()); }
+            if (rd_max == rd_max_init && n_max != 0)
+            { std::ostringstream s; s << "Initial dry radii distribution is non-zero (" << n_max << ") for rd_max_init (" << rd_max_init << ")"; throw std::runtime_error(s.str()); }
+            if (n_min == 0) rd_min *= 1.01;
+            else if (n_max == 0) rd_max /= 1.01;
+            else found = true;
+          }
+        }
+
+        real_t draw_u01() { return std::uniform_real_distribution<real_t>(0, 1)(engine); }
+
+        void init_SD_with_distros(const arrinfo_t<real_t> &th, const arrinfo_t<real_t> &rv, const arrinfo_t<real_t> &rhod, const arrinfo_t<real_t> &p)
+        {
+          const cell_state cs = host_cells(th, rv, rhod, p);
+          real_t log_rd_min = 0, log_rd_max = 0, multiplier = 0;
+
+          real_t tot_lnrd_rng = 0.;                                   // init_SD_with_distros.ipp:18-29
+          for (const auto &dd : oi.dry_distros)
+          {
+            dist_analysis_sd_conc(*dd.second, cs, log_rd_min, log_rd_max, multiplier);
+            tot_lnrd_rng += log_rd_max - log_rd_min;
+          }
+
+          const real_t rho_stp = lcx::cst<real_t>::rho_stp();
+          for (const auto &dd : oi.dry_distros)
+          {
+            const common::unary_function<real_t> &fun = *dd.second;
+            dist_analysis_sd_conc(fun, cs, log_rd_min, log_rd_max, multiplier);
+            if (log_rd_min >= log_rd_max)
+            { std::ostringstream s; s << "Distribution analysis error: rd_min(" << std::exp(log_rd_min) << ") >= rd_max(" << std::exp(log_rd_max) << ")"; throw std::runtime_error(s.str()); }
+
+            // init_SD_with_distros_sd_conc.ipp:26-33, init_count_num.ipp:32-35
+            const real_t fraction = (log_rd_max - log_rd_min) / tot_lnrd_rng;
+            multiplier *= oi.sd_conc / int(fraction * oi.sd_conc + 0.5);
+            const n_t per_cell = n_t(fraction * oi.sd_conc);
+            const size_t n_new = size_t(per_cell) * n_cell;
+
+            std::vector<n_t> n(n_new);
+            std::vector<real_t> rd3(n_new), rw2(n_new), kpa(n_new, dd.first.kappa), xs, ys, zs;
+            std::vector<uint32_t> ijk(n_new);
+            for (size_t s = 0; s < n_new; ++s) ijk[s] = uint32_t(s / per_cell);      // init_ijk.ipp:36-52 (cell-major)
+
+            // dry radii, stratified in ln(rd) within each cell: init_dry_sd_conc.ipp:25-66
+            std::vector<real_t> u01(n_new);
+            for (size_t s = 0; s < n_new; ++s) u01[s] = draw_u01();
+#pragma omp parallel for schedule(static)
+            for (long sl = 0; sl < long(n_new); ++sl)
+            {
+              const size_t s = size_t(sl);
+              const size_t ptr = size_t(ijk[s]) * per_cell;
+              const real_t lnrd = log_rd_min + real_t(s - ptr + u01[s]) * (log_rd_max - log_rd_min) / real_t(per_cell);
+              rd3[s] = std::exp(3 * lnrd);
+              // multiplicities: init_n.ipp:48-137
+              const real_t lnrd2 = std::log(rd3[s]) / 3.;
+              real_t v = multiplier * fun(lnrd2);
+              if (!oi.aerosol_independent_of_rhod) v = v * cs.rhod[ijk[s]] / rho_stp;
+              if (n_dims > 0) v = v * cs.dv[ijk[s]] / real_t(oi.dx * oi.dy * oi.dz);
+              n[s] = n_t(v + real_t(0.5));
+              // equilibrium wet radius: init_wet.ipp:18-74
+              const real_t RH = std::min(cs.RH[ijk[s]], oi.RH_max);
+              rw2[s] = std::pow(lcx::rw3_eq(rd3[s], kpa[s], RH, cs.T[ijk[s]]), real_t(2. / 3));
+            }
+
+            // positions, uniform within the part of the cell inside the Lagrangian domain: init_xyz.ipp:16-73
+            const int nn[3] = {oi.nx, oi.ny, oi.nz};
+            const real_t a[3] = {oi.x0, oi.y0, oi.z0}, b[3] = {oi.x1, oi.y1, oi.z1}, d[3] = {oi.dx, oi.dy, oi.dz};
+            std::vector<real_t> *v[3] = {&xs, &ys, &zs};
+            for (int ix = 0; ix < 3; ++ix)
+            {
+              if (nn[ix] == 0) continue;
+              v[ix]->resize(n_new);
+              for (size_t s = 0; s < n_new; ++s) u01[s] = draw_u01();
+              const size_t nz1 = size_t(m1(oi.nz)), ny1 = size_t(m1(oi.ny));
+              for (size_t s = 0; s < n_new; ++s)
+              {
+                const size_t c = ijk[s];
+                size_t ii;
+                if (n_dims == 1) ii = c;
+                else if (n_dims == 2) ii = ix == 0 ? c / nz1 : c % nz1;
+                else ii = ix == 0 ? c / (nz1 * ny1) : ix == 1 ? (c / nz1) % ny1 : c % nz1;
+                (*v[ix])[s] = u01[s] * std::min(b[ix], (ii + 1) * d[ix]) + (1. - u01[s]) * std::max(a[ix], ii * d[ix]);
+              }
+            }
+            chk(lcx_sd_append(e, int64_t(n_new), reinterpret_cast<const uint64_t *>(n.data()), rd3.data(), rw2.data(), kpa.data(),
+                              xs.empty() ? nullptr : xs.data(), ys.empty() ? nullptr : ys.data(), zs.empty() ? nullptr : zs.data(), ijk.data()));
+          }
+        }
+
+        // ---- time stepping ---------------------------------------------------------------------------------------
+        void adjust_timesteps(real_t dt_)   // impl_adjust_timesteps.ipp:13-22
+        {
+          if (dt_ > 0 && !oi.variable_dt_switch) throw std::runtime_error("libcloudph++: opts.dt specified, but opts_init.variable_dt_switch is false.");
+          sstp_cond = dt_ > 0 && oi.sstp_cond > 1 ? int(std::ceil(oi.sstp_cond * dt_ / oi.dt)) : oi.sstp_cond;
+          sstp_coal = dt_ > 0 && oi.sstp_coal > 1 ? int(std::ceil(oi.sstp_coal * dt_ / oi.dt)) : oi.sstp_coal;
+          dt = dt_ > 0 ? dt_ : oi.dt;
+        }
+
+        void sync_in(arrinfo_t<real_t> &th, arrinfo_t<real_t> &rv, const arrinfo_t<real_t> &rhod, const arrinfo_t<real_t> &cx,
+                     const arrinfo_t<real_t> &cy, const arrinfo_t<real_t> &cz, const arrinfo_t<real_t> &diss_rate, size_t n_ambient_chem)
+        {
+          if (!init_called) throw std::runtime_error("libcloudph++: please call init() before calling step_sync()");
+          if (should_now_run_async) throw std::runtime_error("libcloudph++: please call step_async() before calling step_sync() again");
+          if (th.is_null() || rv.is_null()) throw std::runtime_error("libcloudph++: passing th and rv is mandatory");
+          check_courants(cx, cy, cz);
+          if (n_ambient_chem != 0) throw std::runtime_error("libcloudph++: chemistry was switched off and ambient_chem is not empty");
+          if (!diss_rate.is_null())
+            throw std::runtime_error("libcloudph++: turbulent advection, coalescence and condesation are switched off and diss_rate is not empty");
+          if (m_cx.l2e.empty()) init_courant_maps(cx, cy, cz);
+          var_rho = !rhod.is_null();
+          sync_in_field(th, m_th, LCX_F_TH);
+          sync_in_field(rv, m_rv, LCX_F_RV);
+          sync_in_field(rhod, m_rhod, LCX_F_RHOD);
+          sync_in_field(cx, m_cx, LCX_F_COURANT_X);
+          sync_in_field(cy, m_cy, LCX_F_COURANT_Y);
+          sync_in_field(cz, m_cz, LCX_F_COURANT_Z);
+          // |C_x| > 2 would leave the 2-cell halo of the predictor-corrector scheme: fall back to Euler for this step
+          if (oi.adve_scheme == as_t::pred_corr && !cx.is_null())
+          {
+            real_t mn = std::numeric_limits<real_t>::max(), mx = -mn;
+            for (const real_t v : stage) { mn = std::min(mn, v); mx = std::max(mx, v); }
+            (void)mn; (void)mx;
+            real_t cmin = std::numeric_limits<real_t>::max(), cmax = -cmin;
+            for (const long l : m_cx.l2e) { cmin = std::min(cmin, cx.data[l]); cmax = std::max(cmax, cx.data[l]); }
+            if (!(cmin >= real_t(-2.)) || !(cmax <= real_t(2.))) adve_scheme = as_t::euler;
+          }
+          should_now_run_cond = true;
+        }
+
+        // device-resident variant of sync_in + step_cond: the fields of the previous step stay where they are
+        void step_resident(const opts_t<real_t> &opts)
+        {
+          if (!init_called) throw std::runtime_error("libcloudph++: please call init() before calling step_sync()");
+          arrinfo_t<real_t> none_th, none_rv;
+          var_rho = false;
+          should_now_run_cond = true;
+          step_cond(opts, none_th, none_rv);
+          step_async(opts);
+        }
+
+        void step_cond(const opts_t<real_t> &opts, arrinfo_t<real_t> &th, arrinfo_t<real_t> &rv)
+        {
+          if (!should_now_run_cond) throw std::runtime_error("libcloudph++: please call sync_in() before calling step_cond()");
+          if (opts.turb_cond) throw std::runtime_error("libcloudph++: turb_cond_swtich=False, but turb_cond==True");
+          should_now_run_cond = false;
+          adjust_timesteps(opts.dt);
+          if (opts.cond)
+          {
+            chk(lcx_hskpng_mfp(e));          // from the T, p left by the previous Tpr, as the reference does (particles_step.ipp:189-194)
+            for (int step = 0; step < sstp_cond; ++step)
+            {
+              chk(lcx_sstp_percell_step(e, step, sstp_cond, var_rho));
+              chk(lcx_hskpng_Tpr(e));
+              chk(lcx_cond(e, dt / sstp_cond, opts.RH_max, step, sstp_cond));
+              chk(lcx_update_th_rv(e));
+            }
+            chk(lcx_sstp_save(e));
+            sync_out_field(LCX_F_TH, m_th, th);
+            sync_out_field(LCX_F_RV, m_rv, rv);
+          }
+          if (opts.chem_dsl || opts.chem_dsc || opts.chem_rct)
+            throw std::runtime_error("libcloudph++: all chemistry was switched off in opts_init");
+          should_now_run_async = true;
+        }
+
+        // everything of step_async up to (not including) migration / post_copy: particles_step.ipp:339-482
+        void step_async_local(const opts_t<real_t> &opts)
+        {
+          if (!should_now_run_async) throw std::runtime_error("libcloudph++: please call step_sync() before calling step_async() again");
+          should_now_run_async = false;
+          if (opts.chem_dsl || opts.chem_dsc || opts.chem_rct) throw std::runtime_error("libcloudph++: all chemistry was switched off in opts_init");
+          if (opts.coal && !oi.coal_switch) throw std::runtime_error("libcloudph++: coalescence was switched off in opts_init");
+          if (opts.sedi && !oi.sedi_switch) throw std::runtime_error("libcloudph++: sedimentation was switched off in opts_init");
+          if (opts.subs && !oi.subs_switch) throw std::runtime_error("libcloudph++: subsidence was switched off in opts_init");
+          if (opts.turb_adve) throw std::runtime_error("libcloudph++: turb_adve_switch=False, but turb_adve==True");
+          if (opts.src) throw std::runtime_error("libcloudph++: aerosol source was switched off in opts_init");
+          if (opts.rlx) throw std::runtime_error("libcloudph++: aerosol relaxation was switched off in opts_init");
+          adjust_timesteps(opts.dt);
+
+          chk(lcx_hskpng_Tpr(e));
+          if (opts.sedi || opts.coal || opts.cond) chk(lcx_hskpng_vterm(e, 0));
+
+          if (opts.coal)
+          {
+            for (int step = 0; step < sstp_coal; ++step)
+            {
+              lcx_rng r;
+              std::memset(&r, 0, sizeof(r));
+              if (rng_mode == LGRNGN_B200_RNG_MT19937)
+              {
+                // same draw order as the reference: un[n_part] for the shuffle, then u01[n_part] (hskpng_sort.ipp:33, coal.ipp:373)
+                int64_t n_part = 0;
+                chk(lcx_n_part(e, &n_part));
+                un_host.resize(size_t(n_part)); u01_host.resize(size_t(n_part));
+                std::uniform_int_distribution<unsigned int> dist_un(0, std::numeric_limits<unsigned int>::max());
+                for (auto &v : un_host) v = uint32_t(real_t(dist_un(engine)));
+                for (auto &v : u01_host) v = draw_u01();
+                r.mode = LCX_RNG_INJECT; r.un = un_host.data(); r.u01 = u01_host.data();
+              }
+              else { r.mode = LCX_RNG_PHILOX; r.seed = uint64_t(uint32_t(oi.rng_seed)); r.call = philox_call++; }
+              chk(lcx_coal(e, dt / sstp_coal, &r));
+              if (step + 1 != sstp_coal) chk(lcx_hskpng_vterm(e, 1));
+            }
+            if (pure_const_multi)
+            {
+              int flag = 0;
+              chk(lcx_coal_flag(e, &flag));
+              if (flag) ++sstp_coal;
+            }
+          }
+
+          if (n_dims > 0)
+          {
+            lcx_transport_opts t;
+            t.adve = opts.adve; t.sedi = opts.sedi; t.subs = opts.subs; t.adve_scheme = int(adve_scheme); t.dt = dt;
+            chk(lcx_transport(e, &t));
+          }
+          adve_scheme = oi.adve_scheme;
+        }
+
+        void post_copy(const opts_t<real_t> &opts) { chk(lcx_post_copy(e, opts.rcyc, 0)); }
+
+        void step_async(const opts_t<real_t> &opts)
+        {
+          step_async_local(opts);
+          if (!spawned) post_copy(opts);
+        }
+
+        // ---- diagnostics -----------------------------------------------------------------------------------------
+        void diag_field(int field) { chk(lcx_hskpng_Tpr(e)); chk(lcx_diag_cell_field(e, field)); }
+
+        real_t *outbuf()
+        {
+          outbuf_host.resize(n_cell);
+          chk(lcx_outbuf(e, outbuf_host.data(), int64_t(n_cell)));
+          return outbuf_host.data();
+        }
+
+        std::vector<real_t> get_attr(const std::string &name)
+        {
+          int a;
+          if (name == "rw2") a = LCX_A_RW2; else if (name == "rd3") a = LCX_A_RD3; else if (name == "kappa") a = LCX_A_KPA;
+          else if (name == "x") a = LCX_A_X; else if (name == "y") a = LCX_A_Y; else if (name == "z") a = LCX_A_Z;
+          else if (name == "n") a = LCX_A_N; else if (name == "vt") a = LCX_A_VT; else if (name == "ijk") a = LCX_A_IJK;
+          else if (name == "rd2_insol" || name == "T_freeze" || name == "ice_a" || name == "ice_c" || name == "ice_rho")
+            throw std::runtime_error("Requested ice attribute '" + name + "' but ice_switch is off.");
+          else throw std::runtime_error("Unknown attribute name passed to get_attr.");
+          if ((a == LCX_A_X && !oi.nx) || (a == LCX_A_Y && !oi.ny) || (a == LCX_A_Z && !oi.nz)) return std::vector<real_t>();
+          int64_t n_part = 0;
+          chk(lcx_n_part(e, &n_part));
+          std::vector<real_t> out(size_t(n_part), real_t(0));
+          int64_t got = 0;
+          chk(lcx_get_attr(e, a, out.data(), n_part, &got));
+          return out;
+        }
+
+        std::map<common::output_t, real_t> diag_puddle()
+        {
+          double raw[14];
+          chk(lcx_puddle(e, raw));
+          std::map<common::output_t, real_t> res;
+          for (int q = 0; q < 14; ++q) res[static_cast<common::output_t>(q)] = real_t(raw[q]);
+          return res;
+        }
+      };
+
+      // ======================================================================================================
+      // particles_proto_t over one or several slabs
+      // ======================================================================================================
+      template <class real_t>
+      struct particles_impl : particles_proto_t<real_t>
+      {
+        typedef particles_proto_t<real_t> parent_t;
+        typedef typename parent_t::chem_map_t chem_map_t;
+        typedef typename parent_t::chem_cmap_t chem_cmap_t;
+
+        std::vector<std::unique_ptr<slab<real_t>>> slabs;
+        opts_init_t<real_t> glob;
+        bool multi;
+        std::vector<real_t> gathered;
+
+        // single device (optionally one rank of a process-distributed run, see particles_b200.h)
+        explicit particles_impl(const opts_init_t<real_t> &o) : glob(o), multi(false)
+        {
+          std::pair<int, int> bc;
+          const lgrngn_b200_distmem dm = g_distmem;
+          if (dm.size > 1)
+          {
+            if (o.nx == 0) throw std::runtime_error("libcloudph++: distributed memory doesn't work for 0D setup.");
+            if (!o.open_side_walls) bc = std::make_pair(int(distmem), int(distmem));
+            else bc = std::make_pair(dm.rank == 0 ? int(open) : int(distmem), dm.rank == dm.size - 1 ? int(open) : int(distmem));
+          }
+          else bc = o.open_side_walls ? std::make_pair(int(open), int(open)) : std::make_pair(int(sharedmem), int(sharedmem));
+          slabs.emplace_back(new slab<real_t>(o, bc, o.nx));   // Eulerian arrays are rank-local
+          if (dm.size > 1)
+          {
+            slabs[0]->spawned = true;
+            slabs[0]->lft_x1 = real_t(dm.lft_x1);
+            slabs[0]->rgt_x0 = real_t(dm.rgt_x0);
+          }
+          this->opts_init = &slabs[0]->oi;
+        }
+
+        // several devices in this process: particles_multi_gpu_impl.ipp:35-207
+        particles_impl(const opts_init_t<real_t> &o, int) : glob(o), multi(true)
+        {
+          if (glob.nx == 0) throw std::runtime_error("libcloudph++: multi_CUDA doesn't work for 0D setup.");
+          if (!(glob.x1 > glob.x0 && glob.x1 <= glob.nx * glob.dx)) throw std::runtime_error("libcloudph++: !(x1 > x0 & x1 <= min(1,nx)*dx)");
+          int dev_count = lcx_device_count();
+          if (glob.dev_count > 0)
+          {
+            if (dev_count < glob.dev_count)
+            { std::ostringstream s; s << "number of available GPUs (" << dev_count << ") smaller than number of GPUs defined in opts_init (" << glob.dev_count << ")"; throw std::runtime_error(s.str()); }
+            dev_count = glob.dev_count;
+          }
+          if (dev_count == 0) throw std::runtime_error("libcloudph++: no CUDA device is available");
+          if (dev_count > glob.nx)
+          { std::ostringstream s; s << "Number of CUDA devices (" << dev_count << ") used is greater than nx (" << glob.nx << ")"; throw std::runtime_error(s.str()); }
+          glob.dev_count = dev_count;
+          if (glob.dev_id >= 0)
+          {
+            std::cout << "Libcloudph++ warning: opts_init.dev_id is not compatible with the multi_CUDA backend, ignoring it's value." << std::endl;
+            glob.dev_id = -1;
+          }
+          // LCX_SLABS_ON_ONE_DEVICE=1 places every slab on device 0: lets the decomposition be tested on a single GPU
+          const char *fold = std::getenv("LCX_SLABS_ON_ONE_DEVICE");
+          const bool one_device = fold && std::string(fold) == "1";
+          for (int d = 0; d < dev_count; ++d)
+          {
+            opts_init_t<real_t> o_d(glob);
+            int n_x_bfr = 0;
+            if (dev_count > 1) n_x_bfr = distmem_opts(o_d, d, dev_count);
+            o_d.dev_id = one_device ? 0 : d;
+            std::pair<int, int> bc = o_d.open_side_walls ? std::make_pair(int(open), int(open)) : std::make_pair(int(sharedmem), int(sharedmem));
+            if (dev_count > 1)
+            {
+              if (d == 0) bc.second = distmem;
+              else if (d == dev_count - 1) bc.first = distmem;
+              else bc = std::make_pair(int(distmem), int(distmem));
+              if (!o_d.open_side_walls) { if (d == 0) bc.first = distmem; else if (d == dev_count - 1) bc.second = distmem; }
+            }
+            slabs.emplace_back(new slab<real_t>(o_d, bc, glob.nx));
+            slab<real_t> &s = *slabs.back();
+            s.n_x_bfr = n_x_bfr;
+            s.n_cell_bfr = size_t(n_x_bfr) * m1(o_d.ny) * m1(o_d.nz);
+            s.spawned = dev_count > 1;
+            s.oi.dev_count = dev_count;
+          }
+          for (int d = 0; d < dev_count && dev_count > 1; ++d)
+          {
+            const int lft = d > 0 ? d - 1 : dev_count - 1, rgt = d < dev_count - 1 ? d + 1 : 0;
+            slabs[size_t(d)]->lft_x1 = slabs[size_t(lft)]->oi.x1;
+            slabs[size_t(d)]->rgt_x0 = slabs[size_t(rgt)]->oi.x0;
+          }
+          this->opts_init = &glob;
+        }
+
+        slab<real_t> &one() { return *slabs[0]; }
+
+        // ---- API ---------------------------------------------------------------------------------------------------
+        void init(const arrinfo_t<real_t> th, const arrinfo_t<real_t> rv, const arrinfo_t<real_t> rhod, const arrinfo_t<real_t> p,
+                  const arrinfo_t<real_t> cx, const arrinfo_t<real_t> cy, const arrinfo_t<real_t> cz, const chem_cmap_t ambient_chem) override
+        {
+          for (auto &s : slabs) s->init(th, rv, rhod, p, cx, cy, cz, ambient_chem.size());
+        }
+
+        void step_sync(const opts_t<real_t> &opts, arrinfo_t<real_t> th, arrinfo_t<real_t> rv, const arrinfo_t<real_t> rhod,
+                       const arrinfo_t<real_t> cx, const arrinfo_t<real_t> cy, const arrinfo_t<real_t> cz,
+                       const arrinfo_t<real_t> diss_rate, chem_map_t ambient_chem) override
+        {
+          sync_in(th, rv, rhod, cx, cy, cz, diss_rate, ambient_chem);
+          step_cond(opts, th, rv, ambient_chem);
+        }
+
+        void sync_in(arrinfo_t<real_t> th, arrinfo_t<real_t> rv, const arrinfo_t<real_t> rhod, const arrinfo_t<real_t> cx,
+                     const arrinfo_t<real_t> cy, const arrinfo_t<real_t> cz, const arrinfo_t<real_t> diss_rate, chem_map_t ambient_chem) override
+        {
+          for (auto &s : slabs) s->sync_in(th, rv, rhod, cx, cy, cz, diss_rate, ambient_chem.size());
+        }
+
+        void step_cond(const opts_t<real_t> &opts, arrinfo_t<real_t> th, arrinfo_t<real_t> rv, chem_map_t) override
+        {
+          for (auto &s : slabs) s->step_cond(opts, th, rv);
+        }
+
+        void step_async(const opts_t<real_t> &opts) override
+        {
+          if (multi && opts.rcyc)
+            throw std::runtime_error("libcloudph++: Particle recycling can't be used in the multi_CUDA backend (it would consume whole memory quickly");
+          for (auto &s : slabs) s->step_async_local(opts);
+          const int G = int(slabs.size());
+          if (multi && G > 1)
+          {
+            if (opts.adve)
+            {
+              // neighbour exchange in the reference's order: every slab first receives its right neighbour's left-movers,
+              // then its left neighbour's right-movers (step_async_and_copy.ipp:76-190)
+              std::vector<int64_t> n_lft(size_t(G), 0), n_rgt(size_t(G), 0);
+              for (int d = 0; d < G; ++d) chk(lcx_migr_pack(slabs[size_t(d)]->e, &n_lft[size_t(d)], &n_rgt[size_t(d)]));
+              for (int d = 0; d < G; ++d)
+              {
+                const int rgt = d < G - 1 ? d + 1 : 0;
+                if (slabs[size_t(d)]->bcond.second == distmem && n_lft[size_t(rgt)] > 0)
+                  chk(lcx_migr_send(slabs[size_t(rgt)]->e, 0, slabs[size_t(d)]->e, n_lft[size_t(rgt)]));
+              }
+              for (int d = 0; d < G; ++d)
+              {
+                const int rgt = d < G - 1 ? d + 1 : 0;
+                if (slabs[size_t(d)]->bcond.second == distmem) chk(lcx_migr_unpack(slabs[size_t(d)]->e, 0, n_lft[size_t(rgt)]));
+              }
+              for (int d = 0; d < G; ++d)
+              {
+                const int lft = d > 0 ? d - 1 : G - 1;
+                if (slabs[size_t(d)]->bcond.first == distmem && n_rgt[size_t(lft)] > 0)
+                  chk(lcx_migr_send(slabs[size_t(lft)]->e, 1, slabs[size_t(d)]->e, n_rgt[size_t(lft)]));
+              }
+              for (int d = 0; d < G; ++d)
+              {
+                const int lft = d > 0 ? d - 1 : G - 1;
+                if (slabs[size_t(d)]->bcond.first == distmem) chk(lcx_migr_unpack(slabs[size_t(d)]->e, 1, n_rgt[size_t(lft)]));
+              }
+            }
+            for (auto &s : slabs) s->post_copy(opts);
+          }
+          else
+            for (auto &s : slabs) if (!s->spawned) s->post_copy(opts);   // a spawned single slab is finished by its driver (particles_b200.h)
+        }
+
+        // selectors
+        void sel(int kind, int attr, real_t lo, real_t hi, bool cons) { for (auto &s : slabs) chk(lcx_moms_select(s->e, kind, attr, lo, hi, cons)); }
+        void diag_all() override { sel(LCX_SEL_ALL, 0, 0, 0, false); }
+        void diag_rw_ge_rc() override { sel(LCX_SEL_RW_GE_RC, 0, 0, 0, false); }
+        void diag_RH_ge_Sc() override { sel(LCX_SEL_RH_GE_SC, 0, 0, 0, false); }
+        void diag_dry_rng(const real_t &r0, const real_t &r1) override { sel(LCX_SEL_RANGE, LCX_A_RD3, std::pow(r0, 3), std::pow(r1, 3), false); }
+        void diag_wet_rng(const real_t &r0, const real_t &r1) override { sel(LCX_SEL_RANGE, LCX_A_RW2, std::pow(r0, 2), std::pow(r1, 2), false); }
+        void diag_kappa_rng(const real_t &k0, const real_t &k1) override { sel(LCX_SEL_RANGE, LCX_A_KPA, k0, k1, false); }
+        void diag_water() override { sel(LCX_SEL_GT0, LCX_A_RW2, 0, 0, false); }
+        void diag_dry_rng_cons(const real_t &r0, const real_t &r1) override { sel(LCX_SEL_RANGE, LCX_A_RD3, std::pow(r0, 3), std::pow(r1, 3), true); }
+        void diag_wet_rng_cons(const real_t &r0, const real_t &r1) override { sel(LCX_SEL_RANGE, LCX_A_RW2, std::pow(r0, 2), std::pow(r1, 2), true); }
+        void diag_kappa_rng_cons(const real_t &k0, const real_t &k1) override { sel(LCX_SEL_RANGE, LCX_A_KPA, k0, k1, true); }
+        void diag_water_cons() override { sel(LCX_SEL_GT0, LCX_A_RW2, 0, 0, true); }
+        void diag_ice() override { no_ice(); }
+        void diag_ice_cons() override { no_ice(); }
+        void diag_ice_a_rng(const real_t &, const real_t &) override { no_ice(); }
+        void diag_ice_c_rng(const real_t &, const real_t &) override { no_ice(); }
+        void diag_ice_a_rng_cons(const real_t &, const real_t &) override { no_ice(); }
+        void diag_ice_c_rng_cons(const real_t &, const real_t &) override { no_ice(); }
+        void diag_ice_a_mom(const int &) override { no_ice(); }
+        void diag_ice_c_mom(const int &) override { no_ice(); }
+        void diag_ice_mix_ratio() override { no_ice(); }
+        void diag_precip_rate_ice_mass() override { no_ice(); }
+        static void no_ice() { throw std::runtime_error("libcloudph++: ice is switched off in opts_init, but diag_ice was called"); }
+        void diag_chem(const enum common::chem::chem_species_t &) override
+        { throw std::runtime_error("libcloudph++: chemistry is switched off in opts_init, but diag_chem was called"); }
+
+        // moments and fields
+        void mom(int attr, real_t power) { for (auto &s : slabs) chk(lcx_moms_calc(s->e, attr, power, 1)); }
+        void diag_dry_mom(const int &k) override { mom(LCX_A_RD3, k / 3.); }
+        void diag_wet_mom(const int &k) override { mom(LCX_A_RW2, k / 2.); }
+        void diag_kappa_mom(const int &k) override { mom(LCX_A_KPA, k); }
+        void diag_sd_conc() override { for (auto &s : slabs) chk(lcx_diag_sd_conc(s->e)); }
+        void diag_pressure() override { for (auto &s : slabs) s->diag_field(LCX_F_P); }
+        void diag_temperature() override { for (auto &s : slabs) s->diag_field(LCX_F_T); }
+        void diag_RH() override { for (auto &s : slabs) s->diag_field(LCX_F_RH); }
+        void diag_precip_rate() override { for (auto &s : slabs) chk(lcx_diag_precip_rate(s->e)); }
+        void diag_max_rw() override { for (auto &s : slabs) chk(lcx_diag_max_rw(s->e)); }
+
+        real_t *outbuf() override
+        {
+          if (!multi) return one().outbuf();
+          gathered.resize(size_t(m1(glob.nx)) * m1(glob.ny) * m1(glob.nz));
+          for (auto &s : slabs)
+          {
+            const real_t *part = s->outbuf();
+            std::copy(part, part + s->n_cell, gathered.begin() + long(s->n_cell_bfr));
+          }
+          return gathered.data();
+        }
+
+        std::vector<real_t> get_attr(const std::string &name) override
+        {
+          if (multi) throw std::runtime_error("get_attr doesnt work in multi_CUDA backend.");
+          return one().get_attr(name);
+        }
+
+        std::map<common::output_t, real_t> diag_puddle() override
+        {
+          std::map<common::output_t, real_t> res;
+          for (int q = 0; q < 14; ++q) res[static_cast<common::output_t>(q)] = 0;
+          for (auto &s : slabs) for (const auto &kv : s->diag_puddle()) res[kv.first] += kv.second;
+          return res;
+        }
+      };
+    }
+
+    // ---- factory: src/lib.cpp:13-44 -----------------------------------------------------------------------------
+    template <typename real_t>
+    particles_proto_t<real_t> *factory(const backend_t backend, opts_init_t<real_t> opts_init)
+    {
+      switch (backend)
+      {
+        case multi_CUDA:
+        case CUDA:
+          if constexpr (std::is_same<real_t, double>::value)
+          {
+            if (backend == multi_CUDA) return new b200::particles_impl<double>(opts_init, 0);
+            return new b200::particles_impl<double>(opts_init);
+          }
+          else
+            throw std::runtime_error("libcloudph++: the B200 back-end is built for double precision only (float is not instantiated yet)");
+        case OpenMP:     throw std::runtime_error("libcloudph++: OpenMP backend was not compiled");
+        case serial:     throw std::runtime_error("libcloudph++: serial backend was not compiled");
+        default:         throw std::runtime_error("libcloudph++: unknown backend");
+      }
+    }
+
+    template particles_proto_t<float> *factory(const backend_t, opts_init_t<float>);
+    template particles_proto_t<double> *factory(const backend_t, opts_init_t<double>);
+  }
+}
+
+// ---- C entry points for process-distributed runs and test control (particles_b200.h) ---------------------------------
+namespace lg = libcloudphxx::lgrngn;
+
+extern "C" {
+
+void lgrngn_b200_set_rng_mode(int mode) { lg::b200::g_rng_mode = mode; }
+int lgrngn_b200_get_rng_mode(void) { return lg::b200::g_rng_mode; }
+void lgrngn_b200_set_distmem(const lgrngn_b200_distmem *d) { lg::b200::g_distmem = *d; }
+
+static lg::b200::slab<double> &slab_of(void *proto)
+{
+  auto *p = dynamic_cast<lg::b200::particles_impl<double> *>(static_cast<lg::particles_proto_t<double> *>(proto));
+  if (!p) throw std::runtime_error("not a B200 particle system");
+  return p->one();
+}
+
+void *lgrngn_b200_engine(void *proto)
+{
+  try { return slab_of(proto).e; } catch (...) { return nullptr; }
+}
+
+int lgrngn_b200_step_resident(void *proto, int flags)
+{
+  try
+  {
+    lg::opts_t<double> o;
+    o.adve = flags & 1; o.sedi = flags & 2; o.cond = flags & 4; o.coal = flags & 8;
+    slab_of(proto).step_resident(o);
+    return 0;
+  }
+  catch (const std::exception &ex) { std::cerr << ex.what() << std::endl; return 1; }
+}
+
+int lgrngn_b200_post_copy(void *proto, int rcyc)
+{
+  try { lg::opts_t<double> o; o.rcyc = rcyc != 0; slab_of(proto).post_copy(o); return 0; }
+  catch (const std::exception &ex) { std::cerr << ex.what() << std::endl; return 1; }
+}
+
+}

@@ -1,0 +1,37 @@
+/* Extra C entry points of liblgrngn_b200.so that have no counterpart in the reference's public API:
+ *   - choice of the random stream feeding coalescence (replay of the reference's mt19937 draw order for parity
+ *     runs, or Philox evaluated inside the kernels);
+ *   - process-distributed runs (one process per GPU, e.g. under torchrun): rank / size / neighbour geometry are
+ *     set before `factory(CUDA, opts_init)` is called with the rank-LOCAL opts_init, the way the reference's
+ *     MPI mode works (reference src/particles_ctor.ipp:22-75, tests/mpi/mpi_adve_test.cpp:88-141); step_async then
+ *     stops before migration and the caller drives pack -> exchange -> unpack -> post_copy through the engine ABI.
+ */
+#ifndef LGRNGN_B200_EXTRAS_H
+#define LGRNGN_B200_EXTRAS_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { LGRNGN_B200_RNG_PHILOX = 0, LGRNGN_B200_RNG_MT19937 = 1 };
+
+typedef struct
+{
+  int rank, size;          /* size <= 1: single process                                     */
+  double lft_x1, rgt_x0;   /* x1 of the left neighbour's slab, x0 of the right neighbour's   */
+  int n_x_tot;             /* total number of x cells over all ranks (0: unknown)            */
+} lgrngn_b200_distmem;
+
+void  lgrngn_b200_set_rng_mode(int mode);       /* applies to particle systems created afterwards (default: $LCX_RNG or Philox) */
+int   lgrngn_b200_get_rng_mode(void);
+void  lgrngn_b200_set_distmem(const lgrngn_b200_distmem *d);
+void *lgrngn_b200_engine(void *particles_proto); /* lcx_engine* of a single-slab particle system */
+int   lgrngn_b200_post_copy(void *particles_proto, int rcyc);
+/* one full model step (condensation + th/rv feedback, then coalescence / transport / housekeeping) on the Eulerian  */
+/* fields ALREADY RESIDENT in device memory: no host<->device field traffic.  flags: bit0 adve, bit1 sedi, bit2 cond, */
+/* bit3 coal.  Used by bench.py for the device-resident throughput figure.                                            */
+int   lgrngn_b200_step_resident(void *particles_proto, int flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

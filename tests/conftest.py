@@ -1,0 +1,26 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `pytest -m gpu`)")
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """the reference's own serial/OpenMP back-ends, built from /root/reference by oracle/build_ref.py (the oracle)"""
+    from tests.support import oracle_library
+    return oracle_library()
+
+
+@pytest.fixture(scope="session")
+def b200():
+    """the product: B200 back-end through the flat binding; parity runs replay the reference's mt19937 stream"""
+    from tests.support import b200_library
+    return b200_library()

@@ -1,0 +1,220 @@
+"""Shared helpers of the test-suite: library loading, case set-ups mirroring BASELINE.json's configs, comparisons.
+
+Only tests (and bench.py's cpu_baseline / smoke()) may touch oracle/ - the product package never does.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from libcloudphxx_b200 import lgrngn as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_LIB = os.path.join(ROOT, "oracle", "_ref", "liblgrngn_ref.so")
+
+_cache = {}
+
+
+def oracle_library():
+    if "ref" not in _cache:
+        if not os.path.exists(ORACLE_LIB):
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("build_ref", os.path.join(ROOT, "oracle", "build_ref.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build(verbose=False)
+        lib = L.Library(ORACLE_LIB)
+        assert lib.name == "reference"
+        lib.lib.lgc_ref_dump_u64.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_ulonglong), C.c_long]
+        lib.lib.lgc_ref_dump_u64.restype = C.c_long
+        lib.lib.lgc_ref_dump_f64.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_double), C.c_long]
+        lib.lib.lgc_ref_dump_f64.restype = C.c_long
+        _cache["ref"] = lib
+    return _cache["ref"]
+
+
+def b200_library():
+    if "b200" not in _cache:
+        lib = L.b200()
+        assert lib.name == "b200"
+        lib.lib.lgrngn_b200_set_rng_mode.argtypes = [C.c_int]
+        lib.lib.lgrngn_b200_set_rng_mode(1)      # replay the reference's mt19937 draw order
+        _cache["b200"] = lib
+    return _cache["b200"]
+
+
+def ref_dump_u64(ref, prt, name, cap):
+    buf = np.empty(cap, dtype=np.uint64)
+    n = ref.lib.lgc_ref_dump_u64(prt._h, name.encode(), buf.ctypes.data_as(C.POINTER(C.c_ulonglong)), cap)
+    assert n >= 0, name
+    return buf[:n].copy()
+
+
+def ref_dump_f64(ref, prt, name, cap):
+    buf = np.empty(cap, dtype=np.float64)
+    n = ref.lib.lgc_ref_dump_f64(prt._h, name.encode(), buf.ctypes.data_as(C.POINTER(C.c_double)), cap)
+    assert n >= 0, name
+    return buf[:n].copy()
+
+
+# ---- case set-ups -------------------------------------------------------------------------------------------------
+AEROSOL_ICICLE = [(0.02e-6, 1.4, 60e6), (0.075e-6, 1.6, 40e6)]     # models/kinematic_2D/src/opts_common.hpp:48-62
+
+
+def box_golovin(lib, n_sd=2 ** 14, dt=1.0, sstp_coal=1):
+    """cfg1: 0-D box, Golovin kernel (tests/python/physics/coalescence_golovin.py:33-84)"""
+    oi = lib.opts_init_t()
+    oi.dt = dt
+    oi.sstp_coal = sstp_coal
+    oi.sedi_switch = 0
+    oi.sd_conc = n_sd
+    oi.n_sd_max = n_sd
+    oi.kernel = L.kernel_t.golovin
+    oi.kernel_parameters = [1500.0]
+    oi.terminal_velocity = L.vt_t.beard77fast
+    oi.dry_distros = [L.expvolume(1e-10, 30.084e-6, 2.0 ** 23)]
+    fields = dict(th=np.array([300.0]), rv=np.array([0.01]), rhod=np.array([1.0]))
+    o = lib.opts_t()
+    o.adve = o.sedi = o.cond = 0
+    o.coal = 1
+    return oi, o, fields
+
+
+def parcel(lib, n_sd=10000, dt=0.1, sstp_cond=1, RH_formula=L.RH_formula_t.pv_cc):
+    """cfg2: 0-D adiabatic parcel, condensation only (tests/python/unit/parcel/test.py:15-39)"""
+    oi = lib.opts_init_t()
+    oi.dt = dt
+    oi.sstp_cond = sstp_cond
+    oi.coal_switch = 0
+    oi.sedi_switch = 0
+    oi.sd_conc = n_sd
+    oi.n_sd_max = n_sd
+    oi.RH_formula = RH_formula
+    oi.dry_distros = [L.lognormal(0.61, [(0.04e-6, 2.0, 566e6)])]
+    T0, p0, RH0 = 282.2, 95000.0, 0.95
+    # invert for th_dry, rv, rhod at the parcel's starting point
+    R_d, R_v, c_pd, eps = 8.3144621 / 0.02897, 8.3144621 / 0.018, 1005.0, 0.018 / 0.02897
+    pvs = 611.73 * np.exp((2.5e6 + (4218 - 1850) * 273.16) / R_v * (1 / 273.16 - 1 / T0) - (4218 - 1850) / R_v * np.log(T0 / 273.16))
+    pv = RH0 * pvs
+    rv = eps * pv / (p0 - pv)
+    rhod = (p0 - pv) / R_d / T0
+    th = T0 * (1e5 / (p0 - pv)) ** (R_d / c_pd)
+    fields = dict(th=np.array([th]), rv=np.array([rv]), rhod=np.array([rhod]))
+    o = lib.opts_t()
+    o.adve = o.sedi = o.coal = 0
+    o.cond = 1
+    return oi, o, fields
+
+
+def hydrostatic_column(nz, dz, th0=289.0, rv0=7.5e-3, p0=101500.0):
+    """dry-air density / dry potential temperature of a hydrostatic column with constant th_std and rv
+    (the set-up of models/kinematic_2D/src/cases/icmw8_case1.hpp:119-136, in closed form)"""
+    R_d, R_v, c_pd, g = 8.3144621 / 0.02897, 8.3144621 / 0.018, 1005.0, 9.81
+    z = (np.arange(nz) + 0.5) * dz
+    p = p0 * (1.0 - g * z / (c_pd * th0)) ** (c_pd / R_d)
+    T = th0 * (p / 1e5) ** (R_d / c_pd)
+    rhod = p / (R_d * T * (1 + rv0 * R_v / R_d))
+    th_dry = th0 * (1 + rv0 * R_v / R_d) ** (R_d / c_pd)
+    return th_dry, rhod, z
+
+
+def box_3d(lib, nx=8, ny=8, nz=8, sd_conc=32, dt=1.0, kernel=L.kernel_t.hall_davis_no_waals, vt=L.vt_t.beard77fast,
+           adve=L.as_t.implicit, sstp_cond=1, sstp_coal=1, cx=0.1, cy=0.05, n_sd_max=None, rain_mode=False):
+    """cfg4-shaped 3-D box, full microphysics, scaled down"""
+    oi = lib.opts_init_t()
+    oi.nx, oi.ny, oi.nz = nx, ny, nz
+    oi.dx = oi.dy = oi.dz = 20.0
+    oi.x1, oi.y1, oi.z1 = nx * 20.0, ny * 20.0, nz * 20.0
+    oi.dt = dt
+    oi.sstp_cond, oi.sstp_coal = sstp_cond, sstp_coal
+    oi.sd_conc = sd_conc
+    oi.n_sd_max = n_sd_max or int(nx * ny * nz * sd_conc * 1.5)
+    oi.kernel = kernel
+    oi.terminal_velocity = vt
+    oi.adve_scheme = adve
+    distros = [L.lognormal(0.61, AEROSOL_ICICLE)]
+    if rain_mode:
+        distros.append(L.lognormal(1.28, [(30e-6, 1.2, 1e5)]))       # tests/mpi/mpi_adve_test.cpp:23-31 style large mode
+    oi.dry_distros = distros
+    th_dry, rhod_col, _ = hydrostatic_column(nz, 20.0)
+    th = np.full((nx, ny, nz), th_dry)
+    rv = np.full((nx, ny, nz), 6e-3)
+    rv[:, :, nz // 2:] = 8.2e-3
+    rhod = np.broadcast_to(rhod_col, (nx, ny, nz)).copy()
+    Cx = np.full((nx + 1, ny, nz), cx)
+    Cy = np.full((nx, ny + 1, nz), cy)
+    Cz = np.zeros((nx, ny, nz + 1))
+    fields = dict(th=th, rv=rv, rhod=rhod, Cx=Cx, Cy=Cy, Cz=Cz)
+    return oi, lib.opts_t(), fields
+
+
+def kinematic_2d(lib, nx=16, nz=16, sd_conc=32, dt=1.0, kernel=L.kernel_t.geometric, kparams=(0.5,), vt=L.vt_t.khvorostyanov_spherical,
+                 adve=L.as_t.implicit, sstp_cond=2, sstp_coal=2, w_max=0.6):
+    """cfg3: ICMW-8 case-1 style single-eddy flow on a 2-D (x,z) grid (kin_cloud_2d_lgrngn.hpp:167-196, icmw8_case1.hpp:84-88,199-218)"""
+    oi = lib.opts_init_t()
+    dx = dz = 1500.0 / (nx - 1)
+    oi.nx, oi.nz = nx, nz
+    oi.dx, oi.dz = dx, dz
+    oi.x0, oi.z0 = dx / 2, dz / 2
+    oi.x1, oi.z1 = (nx - 0.5) * dx, (nz - 0.5) * dz
+    oi.dt = dt
+    oi.sstp_cond, oi.sstp_coal = sstp_cond, sstp_coal
+    oi.sd_conc = sd_conc
+    oi.n_sd_max = nx * nz * sd_conc
+    oi.kernel = kernel
+    oi.kernel_parameters = list(kparams)
+    oi.terminal_velocity = vt
+    oi.adve_scheme = adve
+    oi.dry_distros = [L.lognormal(0.61, AEROSOL_ICICLE)]
+    th_dry, rhod_col, _ = hydrostatic_column(nz, dz)
+    th = np.full((nx, nz), th_dry)
+    rv = np.full((nx, nz), 7.5e-3)
+    rhod = np.broadcast_to(rhod_col, (nx, nz)).copy()
+    # non-divergent single eddy from the stream function psi = -sin(pi z/Z) cos(2 pi x/X), scaled to w_max
+    X, Z = (nx - 1) * dx, (nz - 1) * dz
+    A = w_max * X / (2 * np.pi)
+    xe = (np.arange(nx + 1) - 0.5) * dx
+    zc = (np.arange(nz)) * dz
+    xc = (np.arange(nx)) * dx
+    ze = (np.arange(nz + 1) - 0.5) * dz
+    psi = lambda x, z: -A * np.sin(np.pi * z / Z) * np.cos(2 * np.pi * x / X)
+    u = -(psi(xe[:, None], zc[None, :] + dz / 2) - psi(xe[:, None], zc[None, :] - dz / 2)) / dz
+    w = (psi(xc[None, :].T + dx / 2, ze[None, :]) - psi(xc[None, :].T - dx / 2, ze[None, :])) / dx
+    Cx = np.ascontiguousarray(u * dt / dx)
+    Cz = np.ascontiguousarray(w * dt / dz)
+    fields = dict(th=th, rv=rv, rhod=rhod, Cx=Cx, Cz=Cz)
+    return oi, lib.opts_t(), fields
+
+
+def make(lib, backend, oi):
+    return lib.factory(backend, oi)
+
+
+def run_pair(ref, b200, setup, n_steps, backend_ref=L.backend_t.serial, on_step=None, **kw):
+    """runs the same case on the oracle and on the B200 back-end, step by step; on_step(step, p_ref, p_new, f_ref, f_new)"""
+    oi_r, o_r, f_r = setup(ref, **kw)
+    oi_n, o_n, f_n = setup(b200, **kw)
+    p_r = ref.factory(backend_ref, oi_r)
+    p_n = b200.factory(L.backend_t.CUDA, oi_n)
+    init_args = lambda f: (f["th"], f["rv"], f["rhod"], None, f.get("Cx"), f.get("Cy"), f.get("Cz"))
+    p_r.init(*init_args(f_r))
+    p_n.init(*init_args(f_n))
+    if on_step:
+        on_step(-1, p_r, p_n, f_r, f_n)
+    for step in range(n_steps):
+        for p, o, f in ((p_r, o_r, f_r), (p_n, o_n, f_n)):
+            p.step_sync(o, f["th"], f["rv"], f["rhod"], f.get("Cx"), f.get("Cy"), f.get("Cz"))
+            p.step_async(o)
+        if on_step:
+            on_step(step, p_r, p_n, f_r, f_n)
+    return p_r, p_n, f_r, f_n
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    d = np.abs(a - b)
+    s = np.maximum(np.abs(a), np.abs(b))
+    with np.errstate(invalid="ignore", divide="ignore"):
+        r = np.where(s > 0, d / s, 0.0)
+    return float(r.max()) if r.size else 0.0

@@ -1,0 +1,217 @@
+"""Parity of the B200 back-end with the reference's own CPU back-end (oracle/_ref), through the C ABI.
+
+Classes of agreement:
+  exact      - cell indices, per-cell counts, multiplicities, collision outcomes under the replayed mt19937 stream,
+               dry radii, positions when only + - * / are involved;
+  tolerance  - anything that went through exp/log/pow/cbrt on the device (CUDA libm vs glibc: a few ulp),
+               per-cell sums (order of summation), the condensation root (hard bound 2*2^-15 on rw2, typically 1e-12).
+"""
+import numpy as np
+import pytest
+
+from libcloudphxx_b200 import lgrngn as L
+from tests import support as S
+
+pytestmark = pytest.mark.gpu
+
+
+def attrs(p, names=("rd3", "rw2", "kappa")):
+    return {k: p.get_attr(k) for k in names}
+
+
+def test_init_is_bit_identical_3d(ref, b200):
+    """SD initialisation replays the reference's host maths and draw order: every attribute equal to the last bit"""
+    def check(step, p_r, p_n, f_r, f_n):
+        for k in ("rd3", "rw2", "kappa", "x", "y", "z"):
+            a, b = p_r.get_attr(k), p_n.get_attr(k)
+            assert a.shape == b.shape and a.size > 0
+            assert np.array_equal(a, b), (k, S.rel_err(a, b))
+        assert np.array_equal(p_r.get_n(), p_n.get_n())
+    S.run_pair(ref, b200, S.box_3d, 0, on_step=check, nx=4, ny=3, nz=5, sd_conc=16)
+
+
+@pytest.mark.parametrize("n_sd", [2 ** 10, 2 ** 14])
+def test_golovin_box_exact(ref, b200, n_sd):
+    """cfg1: multiplicities, wet and dry radii bit-identical after every step (Golovin kernel: only * + sqrt cbrt)"""
+    hist = []
+
+    def check(step, p_r, p_n, f_r, f_n):
+        n_r, n_n = p_r.get_n(), p_n.get_n()
+        assert np.array_equal(n_r, n_n), "multiplicities differ at step %d" % step
+        assert np.array_equal(p_r.get_attr("rd3"), p_n.get_attr("rd3")), step
+        # cbrt differs by <= 1 ulp between glibc and CUDA -> <= 3 ulp on rw2 per collision, accumulating over
+        # successive collisions of the same SD
+        assert S.rel_err(p_r.get_attr("rw2"), p_n.get_attr("rw2")) < 1e-14, step
+        hist.append(int(n_r.sum()))
+    S.run_pair(ref, b200, S.box_golovin, 30, on_step=check, n_sd=n_sd)
+    assert hist[-1] < hist[0], "no collisions happened - the test would be vacuous"
+
+
+def test_golovin_substeps_and_removal(ref, b200):
+    """sstp_coal > 1 and SDs that vanish (equal multiplicities) are removed identically"""
+    def check(step, p_r, p_n, f_r, f_n):
+        assert np.array_equal(p_r.get_n(), p_n.get_n()), step
+    p_r, p_n, _, _ = S.run_pair(ref, b200, S.box_golovin, 10, on_step=check, n_sd=2 ** 12, dt=40.0, sstp_coal=4)
+    assert p_n.get_n().size == p_r.get_n().size
+
+
+@pytest.mark.parametrize("sstp_cond", [1, 3])
+@pytest.mark.parametrize("rhf", [L.RH_formula_t.pv_cc, L.RH_formula_t.rv_cc, L.RH_formula_t.pv_tet, L.RH_formula_t.rv_tet])
+def test_parcel_condensation(ref, b200, sstp_cond, rhf):
+    """cfg2: per-SD implicit-Euler growth + th/rv feedback; rw2 within 1e-9 (hard bound 6e-5), th/rv within 1e-12 per step"""
+    def drive(lib):
+        oi, o, f = S.parcel(lib, n_sd=4096, dt=1.0, sstp_cond=sstp_cond, RH_formula=rhf)
+        p = lib.factory(L.backend_t.serial if lib.name == "reference" else L.backend_t.CUDA, oi)
+        p.init(f["th"], f["rv"], f["rhod"])
+        out = []
+        for step in range(40):
+            f["rhod"] *= 0.9995          # adiabatic expansion drives supersaturation and activation
+            f["th"] *= 1.0
+            p.step_sync(o, f["th"], f["rv"], f["rhod"])
+            p.step_async(o)
+            out.append((f["th"][0], f["rv"][0], p.get_attr("rw2")))
+        return out
+    a, b = drive(ref), drive(b200)
+    worst, stats = 0.0, []
+    for step, ((th_r, rv_r, rw_r), (th_n, rv_n, rw_n)) in enumerate(zip(a, b)):
+        err = np.abs(rw_r - rw_n) / rw_r
+        worst = max(worst, err.max())
+        # hard bound for one step from identical state: both root solves stop on a bracket of relative width 2^-15 and
+        # return its midpoint; when the last trial point hits the root to rounding accuracy, the sign of the residual
+        # (libm ulps) picks the side.  Later steps compound it, and a droplet sitting at its activation threshold can
+        # activate one step apart in the two runs, so the bulk is bounded through quantiles.
+        if step == 0:
+            assert err.max() < 2.0 ** -15, (step, err.max())
+        assert np.quantile(err, 0.99) < (step + 1) * 2.0 ** -15, (step, np.quantile(err, 0.99))
+        assert np.median(err) < 1e-7, (step, np.median(err))
+        assert abs(th_r - th_n) / th_r < 1e-9, (step, abs(th_r - th_n) / th_r)
+        assert abs(rv_r - rv_n) / rv_r < 1e-7, (step, abs(rv_r - rv_n) / rv_r)
+        stats.append((err.max(), np.median(err), abs(th_r - th_n) / th_r, abs(rv_r - rv_n) / rv_r))
+    st = np.array(stats)
+    print("parcel sstp=%d RH_formula=%d: max over steps of [rw2 max, rw2 median, th, rv] rel. diff = %s" % (sstp_cond, rhf, st.max(axis=0)))
+    assert a[-1][2].max() > 1e-11, "nothing activated - the test would be vacuous"
+
+
+@pytest.mark.parametrize("scheme", [L.as_t.implicit, L.as_t.euler])
+def test_advection_positions_exact_2d(ref, b200, scheme):
+    """advection only uses + - * / : positions and cell indices agree to the last bit
+    (pred_corr is left out in 2-D: the reference itself runs out of temporary vectors there, tmp_drp_no = 2)"""
+    def setup(lib):
+        oi, o, f = S.kinematic_2d(lib, nx=12, nz=10, sd_conc=8, adve=scheme, sstp_cond=1, sstp_coal=1, w_max=12.0)
+        o.cond = o.coal = o.sedi = 0
+        return oi, o, f
+
+    def check(step, p_r, p_n, f_r, f_n):
+        for k in ("x", "z"):
+            a, b = p_r.get_attr(k), p_n.get_attr(k)
+            assert a.size == b.size, (k, step, a.size, b.size)
+            assert np.array_equal(a, b), (k, step, S.rel_err(a, b))
+        cap = p_r._cap
+        assert np.array_equal(S.ref_dump_u64(ref, p_r, "ijk", cap), p_n.get_attr("ijk").astype(np.uint64)), step
+    S.run_pair(ref, b200, setup, 12, on_step=check)
+
+
+@pytest.mark.parametrize("scheme", [L.as_t.implicit, L.as_t.euler, L.as_t.pred_corr])
+def test_advection_positions_exact_3d(ref, b200, scheme):
+    """3-D advection with all three schemes (pred_corr uses the 2-cell Courant halo), sheared non-uniform Courant field"""
+    def setup(lib):
+        oi, o, f = S.box_3d(lib, nx=6, ny=5, nz=7, sd_conc=8, adve=scheme)
+        rng = np.random.default_rng(7)
+        f["Cx"] = 0.3 + 0.4 * rng.random(f["Cx"].shape)
+        f["Cy"] = -0.2 + 0.4 * rng.random(f["Cy"].shape)
+        f["Cz"] = -0.1 + 0.2 * rng.random(f["Cz"].shape)
+        f["Cz"][:, :, 0] = 0.0
+        f["Cz"][:, :, -1] = 0.0
+        o.cond = o.coal = o.sedi = 0
+        return oi, o, f
+
+    def check(step, p_r, p_n, f_r, f_n):
+        for k in ("x", "y", "z"):
+            a, b = p_r.get_attr(k), p_n.get_attr(k)
+            assert a.size == b.size, (k, step, a.size, b.size)
+            assert np.array_equal(a, b), (k, step, S.rel_err(a, b))
+        assert np.array_equal(S.ref_dump_u64(ref, p_r, "ijk", p_r._cap), p_n.get_attr("ijk").astype(np.uint64)), step
+    S.run_pair(ref, b200, setup, 8, on_step=check)
+
+
+@pytest.mark.parametrize("kernel,vt", [(L.kernel_t.hall_davis_no_waals, L.vt_t.beard77fast), (L.kernel_t.geometric, L.vt_t.beard76),
+                                       (L.kernel_t.Long, L.vt_t.khvorostyanov_spherical), (L.kernel_t.hall, L.vt_t.beard77)])
+def test_coal_sedi_adve_3d_without_condensation(ref, b200, kernel, vt):
+    """coalescence + sedimentation + advection + removal in 3-D (no condensation, whose root solve carries its own
+    2^-15 tolerance): multiplicities, dry radii and the set of surviving SDs identical; radii / positions to a few ulp"""
+    seen = {"collided": False, "removed": False}
+
+    def setup(lib):
+        oi, o, f = S.box_3d(lib, nx=6, ny=5, nz=8, sd_conc=32, rain_mode=True, kernel=kernel, vt=vt, dt=2.0, sstp_coal=2)
+        o.cond = 0
+        return oi, o, f
+
+    def check(step, p_r, p_n, f_r, f_n):
+        n_r, n_n = p_r.get_n(), p_n.get_n()
+        assert n_r.size == n_n.size, (step, n_r.size, n_n.size)
+        assert np.array_equal(n_r, n_n), "multiplicities differ at step %d" % step
+        assert np.array_equal(p_r.get_attr("rd3"), p_n.get_attr("rd3")), step
+        assert S.rel_err(p_r.get_attr("rw2"), p_n.get_attr("rw2")) < 1e-14, (step, S.rel_err(p_r.get_attr("rw2"), p_n.get_attr("rw2")))
+        for k in ("x", "y"):
+            assert np.array_equal(p_r.get_attr(k), p_n.get_attr(k)), (k, step)
+        assert S.rel_err(p_r.get_attr("z"), p_n.get_attr("z")) < 1e-11, step      # z -= dt * vt, vt through log/exp/pow
+        if step == -1:
+            seen["n0"], seen["size0"] = int(n_r.sum()), n_r.size
+        else:
+            seen["collided"] |= int(n_r.sum()) < seen["n0"]
+            seen["removed"] |= n_r.size < seen["size0"]
+    S.run_pair(ref, b200, setup, 6, on_step=check)
+    assert seen["collided"] and seen["removed"], seen
+
+
+def test_full_step_3d(ref, b200):
+    """cfg4-shaped box: cond + coal + sedi + adve; integer state exact, floating-point state within the stated tolerance"""
+    log = []
+
+    def check(step, p_r, p_n, f_r, f_n):
+        n_r, n_n = p_r.get_n(), p_n.get_n()
+        assert n_r.size == n_n.size, step
+        assert np.array_equal(n_r, n_n), "multiplicities differ at step %d" % step
+        assert np.array_equal(p_r.get_attr("rd3"), p_n.get_attr("rd3")), step
+        e_rw = S.rel_err(p_r.get_attr("rw2"), p_n.get_attr("rw2"))
+        e_z = S.rel_err(p_r.get_attr("z"), p_n.get_attr("z"))
+        e_th, e_rv = S.rel_err(f_r["th"], f_n["th"]), S.rel_err(f_r["rv"], f_n["rv"])
+        log.append((e_rw, e_z, e_th, e_rv))
+        assert e_rw < (step + 2) * 2.0 ** -15, (step, e_rw)        # condensation root: bracket of relative width 2^-15 per step
+        for k in ("x", "y"):
+            assert np.array_equal(p_r.get_attr(k), p_n.get_attr(k)), (k, step)
+        assert e_z < 1e-8, (step, e_z)
+        assert e_th < 1e-9, (step, e_th)
+        assert e_rv < 1e-7, (step, e_rv)
+    S.run_pair(ref, b200, S.box_3d, 6, on_step=check, nx=6, ny=5, nz=8, sd_conc=32, rain_mode=True)
+    print("full step: max rel. diff [rw2, z, th, rv] =", np.array(log).max(axis=0))
+
+
+def test_diagnostics_match(ref, b200):
+    """diag_* + outbuf: selectors are exact, moments agree to summation-order tolerance"""
+    p_r, p_n, _, _ = S.run_pair(ref, b200, S.box_3d, 3, nx=5, ny=4, nz=6, sd_conc=24, rain_mode=True)
+    def both(f):
+        return f(p_r), f(p_n)
+    for sel in (lambda p: p.diag_all(), lambda p: p.diag_wet_rng(0.5e-6, 25e-6), lambda p: p.diag_dry_rng(0.0, 0.05e-6),
+                lambda p: p.diag_rw_ge_rc(), lambda p: p.diag_RH_ge_Sc(), lambda p: (p.diag_wet_rng(1e-7, 1.0), p.diag_kappa_rng_cons(0.5, 1.0))):
+        for k in range(4):
+            def f(p):
+                sel(p); p.diag_wet_mom(k); return p.outbuf()
+            a, b = both(f)
+            assert S.rel_err(a, b) < (1e-12 if k == 0 else 1e-4), (k, S.rel_err(a, b))   # k > 0 inherits the condensation tolerance on rw2
+        def g(p):
+            sel(p); p.diag_sd_conc(); return p.outbuf()
+        a, b = both(g)
+        assert np.array_equal(a, b)
+    for name in ("pressure", "temperature", "RH", "max_rw"):
+        def h(p):
+            getattr(p, "diag_" + name)(); return p.outbuf()
+        a, b = both(h)
+        assert S.rel_err(a, b) < (1e-4 if name == "max_rw" else 1e-8), (name, S.rel_err(a, b))
+    def pr(p):
+        p.diag_all(); p.diag_precip_rate(); return p.outbuf()
+    a, b = both(pr)
+    assert S.rel_err(a, b) < 1e-4
+    pa, pb = p_r.diag_puddle(), p_n.diag_puddle()
+    for k in ("liquid_volume", "dry_volume", "particle_number", "liquid_number"):
+        assert abs(pa[k] - pb[k]) <= 1e-4 * max(abs(pa[k]), 1e-300), k
