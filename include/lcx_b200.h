@@ -133,10 +133,9 @@ int  lcx_sstp_percell_step(lcx_engine *e, int step, int sstp_cond, int var_rho);
 int  lcx_sstp_save(lcx_engine *e);                              /* sstp_save.ipp:7-29                        */
 
 /* ---- condensation (per-cell sub-stepping path) ---------------------------------------------------------- */
-/* one sub-step: [step 0: 3rd wet moment before], implicit-Euler growth of every liquid SD, 3rd wet   */
-/* moment after; leaves the per-cell moment change for lcx_update_th_rv                              */
-int  lcx_cond(lcx_engine *e, double dt_sub, double RH_max, int step, int sstp_cond);   /* percell/particles_impl_cond.ipp:13-139 */
-int  lcx_update_th_rv(lcx_engine *e);                           /* common/particles_impl_update_th_rv.ipp:74-191 */
+/* one sub-step: 3rd wet moment before (step 0; later sub-steps reuse the previous "after"), implicit-Euler growth */
+/* of every liquid SD, 3rd wet moment after, and the vapour / heat feedback rv -= drv, th -= drv dth/drv              */
+int  lcx_cond(lcx_engine *e, double dt_sub, double RH_max, int step, int sstp_cond);   /* percell/particles_impl_cond.ipp:13-139, common/particles_impl_update_th_rv.ipp:74-191 */
 
 /* ---- coalescence --------------------------------------------------------------------------------------- */
 /* per-cell random pairing + SDM Monte-Carlo collisions for one sub-step                              */

@@ -33,6 +33,8 @@ CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-fopenmp", "-Wa
 CU_SOURCES = ["lcx_api.cu", "lcx_sort.cu", "lcx_cells.cu", "lcx_diag.cu", "lcx_cond.cu", "lcx_coal.cu",
               "lcx_transport.cu", "lcx_layout.cu"]
 CU_HEADERS = ["lcx_engine.cuh", "lcx_physics.h"]
+# translation units whose results are tolerance-class anyway (condensation root solve): FMA contraction allowed
+FMAD_OK = {"lcx_cond.cu"}
 
 
 def _mtime(p):
@@ -58,7 +60,10 @@ def build_engine(force=False, verbose=True, extra=()):
         if not force and _mtime(o) >= max(_mtime(s), hdr_t):
             return src, 0.0, ""
         t0 = time.time()
-        out = _run([NVCC] + NVCC_FLAGS + list(extra) + ["-c", s, "-o", o])
+        flags = list(NVCC_FLAGS)
+        if src in FMAD_OK and os.environ.get("LCX_COND_FMAD", "0") == "1":
+            flags[flags.index("-fmad=false")] = "-fmad=true"
+        out = _run([NVCC] + flags + list(extra) + ["-c", s, "-o", o])
         return src, time.time() - t0, out
 
     objs = []

@@ -302,7 +302,6 @@ int lcx_sstp_save(lcx_engine *e) { return guarded([&] { use_device(e); lcx::sstp
 
 int lcx_cond(lcx_engine *e, double dt_sub, double RH_max, int step, int sstp_cond)
 { return guarded([&] { use_device(e); lcx::cond(e, dt_sub, RH_max, step, sstp_cond); }); }
-int lcx_update_th_rv(lcx_engine *e) { return guarded([&] { use_device(e); lcx::update_th_rv(e); }); }
 
 int lcx_coal(lcx_engine *e, double dt_sub, const lcx_rng *rng) { return guarded([&] { use_device(e); lcx::coal(e, dt_sub, rng); }); }
 

@@ -1,59 +1,158 @@
 // Condensation / evaporation, per-cell sub-stepping path.
 // Reference: src/impl/condensation/percell/particles_impl_cond.ipp:13-139 (driver),
 //            src/impl/condensation/common/particles_impl_cond_common.ipp:79-338 (advance_rw2 + minfun),
-//            src/impl/common/save_liq_ice_content_before_change.ipp:13-58 (3rd moment before).
+//            src/impl/common/save_liq_ice_content_before_change.ipp:13-58 (3rd moment before),
+//            src/impl/common/particles_impl_update_th_rv.ipp:74-191 (vapour / heat feedback).
 //
-// Kernel: one thread per super-droplet; the eight cell scalars are fetched through the SD's cell index -
-// SDs are grouped by cell, so a warp touches one or two cells and the loads are L1 broadcasts.  The
-// implicit-Euler root solve is FP64-compute bound (about 4.6 growth-rate evaluations per SD); algorithmic
-// HBM traffic is 44 B read (rw2, rd3, kpa, vt, ijk) + 8 B written per SD.
+// The reference runs per sub-step: 2 reduce_by_key (3rd wet moment before / after), 1 transform with 9 gathered cell
+// fields, and 8 small per-cell transforms.  Here, for grids with small cells, ONE kernel does all of it:
+//   k_cond_cells  - a group of 8 lanes owns one cell; its SDs are a contiguous segment, walked 8 at a time;
+//                   per SD: n r^3 before, implicit-Euler root solve (TOMS 748), n r^3 after;
+//                   per cell: deterministic 8-lane shuffle reduction, then rv -= drv, th -= drv dth/drv.
+//                   HBM traffic: 40 B read (n, rw2, rd3, kpa, vt) + 8 B written per SD, cell constants once per cell.
+// Cells too populous for that (0-D boxes: one cell with 1e5..1e6 SDs) use a thread-per-SD kernel between two
+// chunked per-cell moment reductions (lcx_diag.cu).
+// The root solve is FP64-compute bound (~4.6 growth-rate evaluations per SD); the growth law is therefore evaluated
+// in the single-quotient form of lcx_physics.h (growth_fast) by default; LCX_COND_EXACT=1 selects the operation-by-
+// operation transcription of the reference's formula (growth_fn) for cross-checking.
 #include "lcx_engine.cuh"
+
+#include <cstdlib>
 
 namespace lcx
 {
   namespace
   {
     constexpr int TPB = 128;
+    constexpr int GROUP = 8;                 // lanes per cell in k_cond_cells
+    constexpr unsigned FUSED_MAX = 2048;     // largest cell population for the fused kernel
 
-    __global__ void __launch_bounds__(TPB) k_cond(size_t n_part, real_t dt, real_t RH_max,
-                                                 real_t *__restrict__ rw2, const real_t *__restrict__ rd3, const real_t *__restrict__ kpa,
-                                                 const real_t *__restrict__ vt, const idx_t *__restrict__ ijk,
-                                                 const real_t *__restrict__ rhod, const real_t *__restrict__ rv, const real_t *__restrict__ T,
-                                                 const real_t *__restrict__ p, const real_t *__restrict__ RH, const real_t *__restrict__ eta,
-                                                 const real_t *__restrict__ lam_D, const real_t *__restrict__ lam_K)
+    struct cond_args
+    {
+      real_t *rw2; const real_t *rd3, *kpa, *vt; const n_t *n; const idx_t *ijk;
+      const real_t *rhod, *rv_c, *T, *p, *RH, *eta, *lam_D, *lam_K;
+    };
+
+    __device__ __forceinline__ cond_cell<real_t> load_cell(const cond_args &a, idx_t c)
+    {
+      cond_cell<real_t> cl;
+      cl.rhod = a.rhod[c]; cl.rv = a.rv_c[c]; cl.T = a.T[c]; cl.p = a.p[c]; cl.RH = a.RH[c]; cl.eta = a.eta[c];
+      cl.lambda_D = a.lam_D[c]; cl.lambda_K = a.lam_K[c];
+      return cl;
+    }
+
+    // thread per SD (big cells)
+    template <bool EXACT>
+    __global__ void __launch_bounds__(TPB) k_cond(size_t n_part, real_t dt, real_t RH_max, cond_args a)
     {
       const size_t i = size_t(blockIdx.x) * TPB + threadIdx.x;
       if (i >= n_part) return;
-      const real_t r2 = rw2[i];
+      const real_t r2 = a.rw2[i];
       if (r2 <= 0) return;
-      const idx_t c = ijk[i];
-      cond_cell<real_t> cl;
-      cl.rhod = rhod[c]; cl.rv = rv[c]; cl.T = T[c]; cl.p = p[c]; cl.RH = RH[c]; cl.eta = eta[c];
-      cl.lambda_D = lam_D[c]; cl.lambda_K = lam_K[c];
-      rw2[i] = advance_rw2(r2, rd3[i], kpa[i], vt[i], cl, dt, RH_max);
+      const cond_cell<real_t> cl = load_cell(a, a.ijk[i]);
+      if (EXACT) a.rw2[i] = advance_rw2(r2, a.rd3[i], a.kpa[i], a.vt[i], cl, dt, RH_max);
+      else       a.rw2[i] = advance_rw2_fast(r2, a.rd3[i], a.kpa[i], a.vt[i], make_cond_consts(cl, RH_max), dt);
     }
 
-    // out[c] = a[c] - b[c]  (drw_mom3 = -before + after), optionally keeping `a` for the next sub-step
+    // group of 8 lanes per cell: growth + 3rd-moment change + th/rv update
+    template <bool EXACT>
+    __global__ void __launch_bounds__(TPB) k_cond_cells(idx_t n_cell, const uint32_t *__restrict__ off, real_t dt, real_t RH_max, cond_args a,
+                                                       int n_dims, const real_t *__restrict__ dv, int first_step, int keep_after,
+                                                       real_t *__restrict__ rw_mom3, real_t *__restrict__ drw_mom3,
+                                                       real_t *__restrict__ th, real_t *__restrict__ rv)
+    {
+      const idx_t c = (blockIdx.x * TPB + threadIdx.x) / GROUP;
+      const int l = threadIdx.x % GROUP;
+      const bool live = c < n_cell;
+      real_t m3_before = 0, m3_after = 0;
+      cond_cell<real_t> cl;
+      if (live)
+      {
+        cl = load_cell(a, c);
+        const cond_cell_consts<real_t> k = make_cond_consts(cl, RH_max);
+        const uint32_t b = off[c], en = off[c + 1];
+        for (uint32_t i = b + l; i < en; i += GROUP)
+        {
+          const real_t r2 = a.rw2[i];
+          const real_t nn = real_t(a.n[i]);
+          m3_before += nn * (r2 * sqrt(r2));
+          real_t r2n = r2;
+          if (r2 > 0)
+          {
+            r2n = EXACT ? advance_rw2(r2, a.rd3[i], a.kpa[i], a.vt[i], cl, dt, RH_max)
+                        : advance_rw2_fast(r2, a.rd3[i], a.kpa[i], a.vt[i], k, dt);
+            a.rw2[i] = r2n;
+          }
+          m3_after += nn * (r2n * sqrt(r2n));
+        }
+      }
+#pragma unroll
+      for (int o = GROUP / 2; o > 0; o >>= 1)
+      {
+        m3_before += __shfl_xor_sync(0xffffffffu, m3_before, o, GROUP);
+        m3_after += __shfl_xor_sync(0xffffffffu, m3_after, o, GROUP);
+      }
+      if (live && l == 0)
+      {
+        // specific moments: divided by the cell volume, then by the dry-air density (moms.ipp:322-350)
+        if (n_dims > 0) { m3_before = m3_before / dv[c] / cl.rhod; m3_after = m3_after / dv[c] / cl.rhod; }
+        if (!first_step) m3_before = rw_mom3[c];           // value left by the previous sub-step (cond.ipp:38-49)
+        if (keep_after) rw_mom3[c] = m3_after;
+        const real_t drv = (-m3_before + m3_after) * (cst<real_t>::rho_w() * real_t(4. / 3) * cst<real_t>::pi());
+        drw_mom3[c] = drv;
+        rv[c] = cl.rv - drv;
+        const real_t th_c = th[c];
+        th[c] = th_c - drv * d_th_d_rv(cl.T, th_c);
+      }
+    }
+
+    // out[c] = -before[c] + after[c]
     __global__ void k_mom_diff(idx_t n_cell, const real_t *__restrict__ after, const real_t *__restrict__ before, real_t *__restrict__ out)
     {
       const idx_t c = blockIdx.x * blockDim.x + threadIdx.x;
       if (c < n_cell) out[c] = -before[c] + after[c];
     }
+
+    bool exact_requested()
+    {
+      static const bool v = [] { const char *s = std::getenv("LCX_COND_EXACT"); return s && s[0] == '1'; }();
+      return v;
+    }
   }
 
+  // one condensation sub-step INCLUDING the th/rv feedback (the host layer no longer calls update_th_rv separately)
   void cond(lcx_engine *e, real_t dt_sub, real_t RH_max, int step, int sstp)
   {
     const grid_t &g = e->grid;
     sd_arrays &s = e->S();
-    // 3rd specific wet moment before the change: computed at the first sub-step, afterwards the value left
-    // by the previous sub-step is reused as is (it was normalised with that sub-step's rhod - cond.ipp:38-49)
+    if (!e->grouped) throw error("condensation requested while super-droplets are not grouped by cell");
+    cond_args a = {s.rw2.p, s.rd3.p, s.kpa.p, s.vt.p, s.n.p, s.ijk.p, e->rhod.p, e->rv.p, e->T.p, e->p.p, e->RH.p, e->eta.p, e->lambda_D.p, e->lambda_K.p};
+    const bool exact = exact_requested();
+    const int keep_after = step < sstp - 1;
+
+    if (e->max_count <= FUSED_MAX)
+    {
+      const unsigned blocks = div_up(size_t(g.n_cell) * GROUP, TPB);
+      if (exact)
+        LCX_LAUNCH(e, (k_cond_cells<true>), blocks, TPB, 0, g.n_cell, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p, int(step == 0), keep_after,
+                   e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p);
+      else
+        LCX_LAUNCH(e, (k_cond_cells<false>), blocks, TPB, 0, g.n_cell, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p, int(step == 0), keep_after,
+                   e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p);
+      return;
+    }
+
+    // big cells: moment before, growth, moment after, feedback
     if (step == 0) cell_moment(e, nullptr, s.rw2.p, real_t(3. / 2.), true, e->rw_mom3.p);
     if (e->n_part)
-      LCX_LAUNCH(e, k_cond, div_up(e->n_part, TPB), TPB, 0, e->n_part, dt_sub, RH_max, s.rw2.p, s.rd3.p, s.kpa.p, s.vt.p, s.ijk.p,
-                 e->rhod.p, e->rv.p, e->T.p, e->p.p, e->RH.p, e->eta.p, e->lambda_D.p, e->lambda_K.p);
+    {
+      if (exact) LCX_LAUNCH(e, (k_cond<true>), div_up(e->n_part, TPB), TPB, 0, e->n_part, dt_sub, RH_max, a);
+      else       LCX_LAUNCH(e, (k_cond<false>), div_up(e->n_part, TPB), TPB, 0, e->n_part, dt_sub, RH_max, a);
+    }
     cell_moment(e, nullptr, s.rw2.p, real_t(3. / 2.), true, e->count_mom.p);
     LCX_LAUNCH(e, k_mom_diff, div_up(g.n_cell, 256), 256, 0, g.n_cell, e->count_mom.p, e->rw_mom3.p, e->drw_mom3.p);
-    if (step < sstp - 1)
+    if (keep_after)
       LCX_CUDA(cudaMemcpyAsync(e->rw_mom3.p, e->count_mom.p, size_t(g.n_cell) * sizeof(real_t), cudaMemcpyDeviceToDevice, e->stream));
+    update_th_rv(e);
   }
 }

@@ -418,39 +418,262 @@ namespace lcx
     LCX_HD real_t operator()(const real_t &x) const { return (rw2_old + dt * drw2_dt(x) - x); }
   };
 
-  // one implicit-Euler step of rw^2 (advance_rw2::operator(), cond_common.ipp:187-337)
+  // One implicit-Euler step of rw^2: control flow of advance_rw2::operator() (cond_common.ipp:187-337) with its
+  // TOMS 748 root solve (toms748 above) unrolled into a state machine that has ONE evaluation site of the growth
+  // law.  Same abscissae, same arithmetic, same result as calling toms748(f, a, b, fa, fb, tol, n_iter) - but on the
+  // GPU every lane of a warp evaluates f at its own trial point in lock-step whatever phase of the algorithm it is
+  // in, and the kernel stays small enough for the instruction cache (the straightforward inlining of toms748 puts
+  // ~6 copies of f into 100 KB of SASS and stalls on instruction fetch).
+  template <class F, class real_t>
+  LCX_HD real_t implicit_euler_rw2(const F &f, real_t rw2_old, real_t rd3, real_t dt, uintmax_t n_iter = 100, real_t cond_mlt = 2)
+  {
+    using namespace root748;
+    enum { INIT0, INIT1, FIRST, SECOND, LOOP1, LOOP2, LOOP3, LOOP4 };
+    const width_tol<real_t> tol(sizeof(real_t) * 8 / 4);
+    const real_t mu = 0.5f;
+    state<real_t> s;
+    s.a = s.b = s.fa = s.fb = s.d = s.fd = s.e = s.fe = 0;
+    real_t drw2 = 0, rd2 = 0, a0 = 0, b0 = 0, result = rw2_old;
+    uintmax_t left = n_iter;
+    int phase = INIT0;
+    real_t c = rw2_old;
+    bool bracketing = false;      // the pending evaluation is a rebracket() step: guard c first, update [a,b] afterwards
+
+    for (;;)
+    {
+      if (bracketing)
+      {
+        const real_t t2 = fpl<real_t>::eps() * 2;
+        if ((s.b - s.a) < 2 * t2 * s.a)          c = s.a + (s.b - s.a) / 2;
+        else if (c <= s.a + fabs(s.a) * t2)      c = s.a + fabs(s.a) * t2;
+        else if (c >= s.b - fabs(s.b) * t2)      c = s.b - fabs(s.a) * t2;
+      }
+      const real_t g = f.drw2_dt(c);                         // the only evaluation site
+      const real_t fc = (rw2_old + dt * g - c);
+      if (bracketing)
+      {
+        if (fc == 0) { s.a = c; s.fa = 0; s.d = 0; s.fd = 0; }
+        else if (copysign(real_t(1), s.fa * fc) < 0) { s.d = s.b; s.fd = s.fb; s.b = c; s.fb = fc; }
+        else                                         { s.d = s.a; s.fd = s.fa; s.a = c; s.fa = fc; }
+      }
+
+      // what to do next: finish, or pick the next trial point by interpolation (one shared site for the quadratic /
+      // cubic formulae), or by the double-length secant / bisection rules
+      bool finish = false, loop_head = false;
+      int newton_steps = 0;          // > 0: interpolate (cubic when the four function values are distinct, else quadratic)
+      bool quadratic_only = false;
+      switch (phase)
+      {
+        case INIT0:
+        {
+          drw2 = dt * g;
+          if (drw2 == 0) return rw2_old;
+          const real_t rd = cbrt(rd3);
+          rd2 = rd * rd;
+          s.a = tmax(rd2, rw2_old + tmin(real_t(0), cond_mlt * drw2));
+          s.b = rw2_old + tmax(real_t(0), cond_mlt * drw2);
+          if (s.a == s.b) return rw2_old;
+          c = (drw2 > 0) ? s.b : s.a;
+          phase = INIT1;
+          continue;
+        }
+        case INIT1:
+        {
+          if (drw2 > 0) { s.fa = drw2; s.fb = fc; } else { s.fa = fc; s.fb = drw2; }
+          if (s.fa * s.fb > 0) { result = rw2_old + drw2; return result < rd2 ? rd2 : result; }   // not bracketed: explicit Euler
+          if (tol(s.a, s.b) || (s.fa == 0) || (s.fb == 0)) { finish = true; break; }
+          s.fe = s.e = s.fd = 1e5F;
+          c = secant(s.a, s.b, s.fa, s.fb);
+          bracketing = true;
+          phase = FIRST;
+          continue;
+        }
+        case FIRST:
+          --left;
+          if (left && (s.fa != 0) && !tol(s.a, s.b)) { newton_steps = 2; quadratic_only = true; phase = SECOND; }
+          else loop_head = true;
+          break;
+        case SECOND:
+          --left;
+          loop_head = true;
+          break;
+        case LOOP1:
+          if ((0 == --left) || (s.fa == 0) || tol(s.a, s.b)) { finish = true; break; }
+          newton_steps = 3; phase = LOOP2;
+          break;
+        case LOOP2:
+        {
+          if ((0 == --left) || (s.fa == 0) || tol(s.a, s.b)) { finish = true; break; }
+          real_t u, fu;
+          if (fabs(s.fa) < fabs(s.fb)) { u = s.a; fu = s.fa; } else { u = s.b; fu = s.fb; }
+          c = u - 2 * (fu / (s.fb - s.fa)) * (s.b - s.a);
+          if (fabs(c - u) > (s.b - s.a) / 2) c = s.a + (s.b - s.a) / 2;
+          s.e = s.d; s.fe = s.fd;
+          phase = LOOP3;
+          continue;
+        }
+        case LOOP3:
+          if ((0 == --left) || (s.fa == 0) || tol(s.a, s.b)) { finish = true; break; }
+          if ((s.b - s.a) < mu * (b0 - a0)) { loop_head = true; break; }
+          s.e = s.d; s.fe = s.fd;
+          c = real_t(s.a + (s.b - s.a) / 2);
+          phase = LOOP4;
+          continue;
+        case LOOP4:
+          --left;
+          loop_head = true;
+          break;
+      }
+
+      if (loop_head)
+      {
+        if (left && (s.fa != 0) && !tol(s.a, s.b)) { a0 = s.a; b0 = s.b; newton_steps = 2; phase = LOOP1; }
+        else finish = true;
+      }
+      if (newton_steps)
+      {
+        bool have = false;
+        if (!quadratic_only && !values_coincide(s))
+        {
+          // inverse cubic interpolation; out-of-bracket results fall back to three Newton steps on the parabola
+          const real_t q11 = (s.d - s.e) * s.fd / (s.fe - s.fd);
+          const real_t q21 = (s.b - s.d) * s.fb / (s.fd - s.fb);
+          const real_t q31 = (s.a - s.b) * s.fa / (s.fb - s.fa);
+          const real_t d21 = (s.b - s.d) * s.fd / (s.fd - s.fb);
+          const real_t d31 = (s.a - s.b) * s.fb / (s.fb - s.fa);
+          const real_t q22 = (d21 - q11) * s.fb / (s.fe - s.fb);
+          const real_t q32 = (d31 - q21) * s.fa / (s.fd - s.fa);
+          const real_t d32 = (d31 - q21) * s.fd / (s.fd - s.fa);
+          const real_t q33 = (d32 - q22) * s.fa / (s.fe - s.fa);
+          c = q31 + q32 + q33 + s.a;
+          have = !((c <= s.a) || (c >= s.b));
+          if (!have) newton_steps = 3;
+        }
+        if (!have) c = quadratic(s.a, s.b, s.d, s.fa, s.fb, s.fd, unsigned(newton_steps));
+        // the point removed by the coming rebracket becomes (e,fe) - except after the second step of the loop body,
+        // where the reference does not refresh it (toms748.hpp:381-392)
+        if (phase != LOOP2) { s.e = s.d; s.fe = s.fd; }
+        continue;
+      }
+      if (finish)
+      {
+        if (s.fa == 0) s.b = s.a; else if (s.fb == 0) s.a = s.b;
+        result = (s.a + s.b) / 2;
+        return result < rd2 ? rd2 : result;
+      }
+    }
+  }
+
   template <class real_t>
   LCX_HD real_t advance_rw2(real_t rw2_old, real_t rd3, real_t kpa, real_t vt, const cond_cell<real_t> &cl,
-                            real_t dt, real_t RH_max, uintmax_t n_iter = 100, real_t cond_mlt = 2)
+                            real_t dt, real_t RH_max)
   {
     if (rw2_old <= 0) return rw2_old;
     growth_fn<real_t> f;
     f.rw2_old = rw2_old; f.dt = dt; f.rhod = cl.rhod; f.rv = cl.rv; f.T = cl.T; f.p = cl.p;
     f.RH_eff = cl.RH > RH_max ? RH_max : cl.RH;
     f.eta = cl.eta; f.rd3 = rd3; f.kpa = kpa; f.vt = vt; f.lam_D = cl.lambda_D; f.lam_K = cl.lambda_K;
+    return implicit_euler_rw2(f, rw2_old, rd3, dt);
+  }
 
-    const real_t drw2 = dt * f.drw2_dt(rw2_old);
-    if (drw2 == 0) return rw2_old;
+  // ---- the same growth law, arranged for throughput ---------------------------------------------------
+  // drw2/dt written as ONE quotient: every per-cell factor is precomputed once per cell (cond_cell_consts), the two
+  // transition-regime factors, the water activity and the Maxwell-Mason denominator share a single division, 1/rw
+  // comes from rsqrt, and cbrt(1 + x) uses its series for x < 1e-4 (cloud droplets: Re Sc ~ 1e-6).  Algebraically
+  // identical to growth_fn::drw2_dt; numerically within a few ulp of it (the same size as the libm differences between
+  // host and device), so results stay inside the root solver's own 2^-15 bracket tolerance.
+  template <class real_t>
+  struct cond_cell_consts
+  {
+    real_t c_Re;      // 2 rhod / eta              -> Re = vt * rw * c_Re
+    real_t Sc, Pr;
+    real_t lam_D, lam_K;
+    real_t A;         // Kelvin length 2 sigma / (R_v T rho_w)
+    real_t inv_RH;    // 1 / min(RH, RH_max)
+    real_t X;         // 1 / (D_0 rho_v)
+    real_t Y;         // l_v (l_v / (R_v T) - 1) / (K_0 RH T)
+  };
 
-    const real_t rd = cbrt(rd3);
-    const real_t rd2 = rd * rd;
-    const real_t a = tmax(rd2, rw2_old + tmin(real_t(0), cond_mlt * drw2)),
-                 b = rw2_old + tmax(real_t(0), cond_mlt * drw2);
-    if (a == b) return rw2_old;
+  template <class real_t>
+  LCX_HD cond_cell_consts<real_t> make_cond_consts(const cond_cell<real_t> &cl, real_t RH_max)
+  {
+    typedef cst<real_t> c;
+    cond_cell_consts<real_t> k;
+    const real_t RH_eff = cl.RH > RH_max ? RH_max : cl.RH;
+    const real_t lv = l_v(cl.T);
+    k.c_Re = real_t(2) * cl.rhod / cl.eta;
+    k.Sc = cl.eta / cl.rhod / c::D_0();
+    k.Pr = c::c_pd() * cl.eta / c::K_0();
+    k.lam_D = cl.lambda_D; k.lam_K = cl.lambda_K;
+    k.A = kelvin_A(cl.T);
+    k.inv_RH = real_t(1) / RH_eff;
+    k.X = real_t(1) / (c::D_0() * (cl.rhod * cl.rv));
+    k.Y = lv * (lv / c::R_v() / cl.T - real_t(1)) / (c::K_0() * RH_eff * cl.T);
+    return k;
+  }
 
-    real_t fa, fb;
-    if (drw2 > 0) { fa = drw2; fb = f(b); }
-    else          { fa = f(a); fb = drw2; }
+  template <class real_t>
+  LCX_HD real_t nusselt_fast(real_t P, real_t Re)
+  {
+    const real_t x = Re * P;
+    const real_t cb = (fabs(x) < real_t(1e-4))
+      ? real_t(1) + x * (real_t(1. / 3) - x * (real_t(1. / 9) - x * real_t(5. / 81)))
+      : real_t(cbrt(real_t(1) + x));
+    const real_t boost = (Re > real_t(1)) ? tmax(real_t(1), real_t(pow(Re, real_t(.077)))) : real_t(1);
+    return real_t(1) + cb * boost;
+  }
 
-    real_t rw2_new;
-    if (fa * fb > 0) rw2_new = rw2_old + drw2;                       // not bracketed: explicit Euler
-    else
+  template <class real_t>
+  struct growth_fast
+  {
+    real_t rw2_old, dt, rd3, rd3_dry, vt_cRe;   // rd3_dry = rd3 (1 - kappa), vt_cRe = vt * c_Re
+    cond_cell_consts<real_t> k;
+
+    LCX_HD real_t drw2_dt(real_t rw2) const
     {
-      uintmax_t it = n_iter;
-      rw2_new = toms748(f, a, b, fa, fb, width_tol<real_t>(sizeof(real_t) * 8 / 4), it);
+#if defined(__CUDA_ARCH__)
+      const real_t inv_rw = rsqrt(rw2);
+#else
+      const real_t inv_rw = real_t(1) / sqrt(rw2);
+#endif
+      const real_t rw = rw2 * inv_rw;
+      const real_t rw3 = rw2 * rw;
+      const real_t Re = vt_cRe * rw;
+      // Sh = Nu(Sc, Re), Nu = Nu(Pr, Re): the Re^0.077 factor is shared, the two cube roots go through one code site
+      const real_t boost = (Re > real_t(1)) ? tmax(real_t(1), real_t(pow(Re, real_t(.077)))) : real_t(1);
+      real_t nu[2] = {k.Sc, k.Pr};
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+      for (int q = 0; q < 2; ++q)
+      {
+        const real_t x = Re * nu[q];
+        const real_t cb = (fabs(x) < real_t(1e-4))
+          ? real_t(1) + x * (real_t(1. / 3) - x * (real_t(1. / 9) - x * real_t(5. / 81)))
+          : real_t(cbrt(real_t(1) + x));
+        nu[q] = real_t(1) + cb * boost;
+      }
+      const real_t Sh = nu[0], Nu = nu[1];
+      const real_t KnD = k.lam_D * inv_rw, KnK = k.lam_K * inv_rw;
+      const real_t bDn = real_t(1) + KnD, bDd = real_t(1) + KnD * (real_t(1.71) + real_t(1.33) * KnD);
+      const real_t bKn = real_t(1) + KnK, bKd = real_t(1) + KnK * (real_t(1.71) + real_t(1.33) * KnK);
+      const real_t awn = rw3 - rd3, awd = rw3 - rd3_dry;
+      const real_t klv = exp(k.A * inv_rw);
+      const real_t tD = bDn * Sh, tK = bKn * Nu;
+      const real_t num = (awd - awn * klv * k.inv_RH) * (tD * tK);
+      const real_t den = awd * (k.X * bDd * tK + k.Y * bKd * tD);
+      return num / (cst<real_t>::rho_w() * den);
     }
-    if (rw2_new < rd2) rw2_new = rd2;
-    return rw2_new;
+    LCX_HD real_t operator()(const real_t &x) const { return (rw2_old + dt * drw2_dt(x) - x); }
+  };
+
+  template <class real_t>
+  LCX_HD real_t advance_rw2_fast(real_t rw2_old, real_t rd3, real_t kpa, real_t vt, const cond_cell_consts<real_t> &k, real_t dt)
+  {
+    if (rw2_old <= 0) return rw2_old;
+    growth_fast<real_t> f;
+    f.rw2_old = rw2_old; f.dt = dt; f.rd3 = rd3; f.rd3_dry = rd3 * (real_t(1) - kpa); f.vt_cRe = vt * k.c_Re; f.k = k;
+    return implicit_euler_rw2(f, rw2_old, rd3, dt);
   }
 
   // ------------------------------------------------------------------------------------------------

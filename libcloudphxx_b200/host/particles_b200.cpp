@@ -625,8 +625,7 @@ namespace libcloudphxx
             {
               chk(lcx_sstp_percell_step(e, step, sstp_cond, var_rho));
               chk(lcx_hskpng_Tpr(e));
-              chk(lcx_cond(e, dt / sstp_cond, opts.RH_max, step, sstp_cond));
-              chk(lcx_update_th_rv(e));
+              chk(lcx_cond(e, dt / sstp_cond, opts.RH_max, step, sstp_cond));   // includes update_th_rv
             }
             chk(lcx_sstp_save(e));
             sync_out_field(LCX_F_TH, m_th, th);
