@@ -169,7 +169,7 @@ def run_b200(args):
     p.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
     t_init = time.time() - t0
     eng = D.engine_of(lib, p)
-    xch = D.SlabExchange(lib, p, rank, world) if world > 1 else None
+    xch = D.SlabExchange(D.EngineSlab(lib, p), rank, world) if world > 1 else None
     lib.lib.lgc_proto.restype = C.c_void_p
     lib.lib.lgc_proto.argtypes = [C.c_void_p]
     lib.lib.lgrngn_b200_step_resident.argtypes = [C.c_void_p, C.c_int]

@@ -42,37 +42,63 @@ def engine_of(lib, prt):
     return E.Engine(lib.lib.lgrngn_b200_engine(lib.lib.lgc_proto(prt._h)))
 
 
-class SlabExchange:
-    """finishes step_async of a process-distributed slab: pack -> neighbour exchange -> unpack -> post_copy"""
+class EngineSlab:
+    """adapter between SlabExchange and a real particle system: packed migrants live in the engine's device memory"""
 
-    def __init__(self, lib, prt, rank, size, backend="nccl"):
+    device = "cuda"
+
+    def __init__(self, lib, prt):
         import torch
-        import torch.distributed as dist
-        self.torch, self.dist = torch, dist
-        self.lib, self.prt, self.rank, self.size = lib, prt, rank, size
+        self.torch, self.lib, self.prt = torch, lib, prt
         self.eng = engine_of(lib, prt)
-        self.lft = (rank - 1) % size
-        self.rgt = (rank + 1) % size
         self.n_real = self.eng.migr_real_attrs()
-        self.on_gpu = backend == "nccl"
         lib.lib.lgrngn_b200_post_copy.argtypes = [C.c_void_p, C.c_int]
-        self.counts_dev = torch.zeros(4, dtype=torch.int64, device="cuda" if self.on_gpu else "cpu")
+        lib.lib.lgc_proto.restype = C.c_void_p
 
-    def _view(self, side, incoming, count):
+    def pack(self):
+        return self.eng.migr_pack()          # synchronises the engine's stream: the outgoing buffers are complete
+
+    def tensors(self, side, incoming, count):
         torch = self.torch
         n_ptr, r_ptr, cap = self.eng.migr_buffers(side, incoming)
+        if count > cap:
+            raise RuntimeError("migration buffer overflow: %d > %d" % (count, cap))
         n = torch.as_tensor(_CudaView(n_ptr, max(count, 1), "<i8"), device="cuda")[:count]
         r = torch.as_tensor(_CudaView(r_ptr, max(count * self.n_real, 1), "<f8"), device="cuda")[:count * self.n_real]
         return n, r
 
+    def received(self):
+        self.torch.cuda.current_stream().synchronize()
+
+    def unpack(self, side, count):
+        self.eng.migr_unpack(side, count)
+
+    def post_copy(self, rcyc):
+        lib = self.lib.lib
+        if lib.lgrngn_b200_post_copy(lib.lgc_proto(self.prt._h), int(rcyc)) != 0:
+            raise RuntimeError("post_copy failed")
+
+
+class SlabExchange:
+    """finishes step_async of a process-distributed slab: pack -> neighbour exchange -> unpack -> post_copy.
+    `slab` is an EngineSlab (GPU, NCCL) or any object with the same five methods (the CPU/gloo tests use a stand-in)."""
+
+    def __init__(self, slab, rank, size):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.slab, self.rank, self.size = slab, rank, size
+        self.lft = (rank - 1) % size
+        self.rgt = (rank + 1) % size
+
     def finish_step(self, adve=True, rcyc=False):
-        torch, dist = self.torch, self.dist
+        torch, dist, slab = self.torch, self.dist, self.slab
         if adve and self.size > 1:
-            n_lft, n_rgt = self.eng.migr_pack()          # synchronises the engine stream: buffers are ready
+            n_lft, n_rgt = slab.pack()
             # how many arrive: my right neighbour's left-movers and my left neighbour's right-movers
-            send = torch.tensor([n_lft, n_rgt], dtype=torch.int64, device=self.counts_dev.device)
-            from_rgt = torch.zeros(1, dtype=torch.int64, device=send.device)
-            from_lft = torch.zeros(1, dtype=torch.int64, device=send.device)
+            send = torch.tensor([n_lft, n_rgt], dtype=torch.int64, device=slab.device)
+            from_rgt = torch.zeros(1, dtype=torch.int64, device=slab.device)
+            from_lft = torch.zeros(1, dtype=torch.int64, device=slab.device)
             ops = [dist.P2POp(dist.isend, send[0:1], self.lft), dist.P2POp(dist.isend, send[1:2], self.rgt),
                    dist.P2POp(dist.irecv, from_rgt, self.rgt), dist.P2POp(dist.irecv, from_lft, self.lft)]
             for w in dist.batch_isend_irecv(ops):
@@ -80,24 +106,21 @@ class SlabExchange:
             n_from_rgt, n_from_lft = int(from_rgt.item()), int(from_lft.item())
             ops = []
             if n_lft:
-                n, r = self._view(0, False, n_lft)
+                n, r = slab.tensors(0, False, n_lft)
                 ops += [dist.P2POp(dist.isend, n, self.lft), dist.P2POp(dist.isend, r, self.lft)]
             if n_rgt:
-                n, r = self._view(1, False, n_rgt)
+                n, r = slab.tensors(1, False, n_rgt)
                 ops += [dist.P2POp(dist.isend, n, self.rgt), dist.P2POp(dist.isend, r, self.rgt)]
             if n_from_rgt:
-                n, r = self._view(0, True, n_from_rgt)
+                n, r = slab.tensors(0, True, n_from_rgt)
                 ops += [dist.P2POp(dist.irecv, n, self.rgt), dist.P2POp(dist.irecv, r, self.rgt)]
             if n_from_lft:
-                n, r = self._view(1, True, n_from_lft)
+                n, r = slab.tensors(1, True, n_from_lft)
                 ops += [dist.P2POp(dist.irecv, n, self.lft), dist.P2POp(dist.irecv, r, self.lft)]
             if ops:
                 for w in dist.batch_isend_irecv(ops):
                     w.wait()
-                torch.cuda.current_stream().synchronize()
-            self.eng.migr_unpack(0, n_from_rgt)
-            self.eng.migr_unpack(1, n_from_lft)
-        lib = self.lib.lib
-        lib.lgc_proto.restype = C.c_void_p
-        if lib.lgrngn_b200_post_copy(lib.lgc_proto(self.prt._h), int(rcyc)) != 0:
-            raise RuntimeError("post_copy failed")
+                slab.received()
+            slab.unpack(0, n_from_rgt)      # arrivals from the right neighbour first, as the reference appends them
+            slab.unpack(1, n_from_lft)
+        slab.post_copy(rcyc)

@@ -779,10 +779,13 @@ namespace libcloudphxx
         {
           if (glob.nx == 0) throw std::runtime_error("libcloudph++: multi_CUDA doesn't work for 0D setup.");
           if (!(glob.x1 > glob.x0 && glob.x1 <= glob.nx * glob.dx)) throw std::runtime_error("libcloudph++: !(x1 > x0 & x1 <= min(1,nx)*dx)");
+          // LCX_SLABS_ON_ONE_DEVICE=1 places every slab on device 0: lets the decomposition be tested on a single GPU
+          const char *fold = std::getenv("LCX_SLABS_ON_ONE_DEVICE");
+          const bool one_device = fold && std::string(fold) == "1";
           int dev_count = lcx_device_count();
           if (glob.dev_count > 0)
           {
-            if (dev_count < glob.dev_count)
+            if (dev_count < glob.dev_count && !(one_device && dev_count > 0))
             { std::ostringstream s; s << "number of available GPUs (" << dev_count << ") smaller than number of GPUs defined in opts_init (" << glob.dev_count << ")"; throw std::runtime_error(s.str()); }
             dev_count = glob.dev_count;
           }
@@ -795,9 +798,6 @@ namespace libcloudphxx
             std::cout << "Libcloudph++ warning: opts_init.dev_id is not compatible with the multi_CUDA backend, ignoring it's value." << std::endl;
             glob.dev_id = -1;
           }
-          // LCX_SLABS_ON_ONE_DEVICE=1 places every slab on device 0: lets the decomposition be tested on a single GPU
-          const char *fold = std::getenv("LCX_SLABS_ON_ONE_DEVICE");
-          const bool one_device = fold && std::string(fold) == "1";
           for (int d = 0; d < dev_count; ++d)
           {
             opts_init_t<real_t> o_d(glob);

@@ -1,0 +1,129 @@
+"""x-slab decomposition: the in-process multi_CUDA back-end and the one-process-per-GPU (torchrun + NCCL) mode.
+
+No CPU oracle exists for partitioned runs (the reference needs MPI for that, absent here), so the checks are the ones the
+reference's own distributed test makes (tests/mpi/mpi_adve_test.cpp:143-256) plus transport independence:
+  * advecting once round the periodic domain with C = +1 rolls every per-cell statistic exactly and returns it unchanged,
+    with unequal slabs; nothing is lost or duplicated;
+  * the same slabs on one device and on several devices give bit-identical results;
+  * one slab of multi_CUDA (dev_count = 1) is the CUDA back-end.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from libcloudphxx_b200 import lgrngn as L
+from tests import support as S
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def n_devices():
+    import torch
+    return torch.cuda.device_count()
+
+
+def per_cell(p, shape):
+    out = []
+    for mom in (p.diag_sd_conc, lambda: p.diag_dry_mom(1), lambda: p.diag_wet_mom(1), lambda: p.diag_kappa_mom(1), lambda: p.diag_dry_mom(0)):
+        p.diag_all(); mom(); out.append(p.outbuf().reshape(shape).copy())
+    return out
+
+
+def roundtrip_case(b200, dev_count, nx=5, scheme=L.as_t.implicit):
+    oi, o, f = S.box_3d(b200, nx=nx, ny=3, nz=4, sd_conc=16, rain_mode=True, adve=scheme)
+    oi.dev_count = dev_count
+    oi.n_sd_max = int(oi.n_sd_max * 2)       # the per-slab capacity n_sd_max / G + 1 must cover the widest slab
+    f["Cx"][:] = 1.0
+    f["Cy"][:] = 0.0
+    o.cond = o.coal = o.sedi = 0
+    return oi, o, f
+
+
+@pytest.mark.parametrize("slabs", [2, 3])
+def test_multi_cuda_roundtrip_on_one_device(b200, monkeypatch, slabs):
+    """unequal x-slabs folded onto one GPU: migration rolls the per-cell statistics exactly, once round = identity"""
+    monkeypatch.setenv("LCX_SLABS_ON_ONE_DEVICE", "1")
+    nx = 5 if slabs == 2 else 7
+    oi, o, f = roundtrip_case(b200, slabs, nx=nx)
+    p = b200.factory(L.backend_t.multi_CUDA, oi)
+    p.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
+    shape = (nx, 3, 4)
+    before = per_cell(p, shape)
+    assert before[0].sum() > 0
+    for step in range(nx):
+        p.step_sync(o, f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"])
+        p.step_async(o)
+        now = per_cell(p, shape)
+        for a, b in zip(before, now):
+            assert np.array_equal(np.roll(a, step + 1, axis=0), b), step
+    for a, b in zip(before, per_cell(p, shape)):
+        assert np.array_equal(a, b)
+
+
+def test_multi_cuda_single_slab_is_cuda(b200):
+    """dev_count = 1: the multi_CUDA object must reproduce the CUDA back-end bit for bit (full microphysics)"""
+    res = []
+    for backend in (L.backend_t.CUDA, L.backend_t.multi_CUDA):
+        oi, o, f = S.box_3d(b200, nx=4, ny=3, nz=6, sd_conc=24, rain_mode=True)
+        oi.dev_count = 1
+        p = b200.factory(backend, oi)
+        p.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
+        for _ in range(4):
+            p.step_sync(o, f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"])
+            p.step_async(o)
+        res.append(per_cell(p, (4, 3, 6)) + [f["th"].copy(), f["rv"].copy()])
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
+
+
+def test_multi_cuda_full_microphysics_runs_and_conserves(b200, monkeypatch):
+    """cond + coal + sedi + adve over 3 slabs: dry aerosol volume is conserved up to what rains out"""
+    monkeypatch.setenv("LCX_SLABS_ON_ONE_DEVICE", "1")
+    oi, o, f = S.box_3d(b200, nx=6, ny=4, nz=6, sd_conc=24, rain_mode=True, cx=0.5)
+    oi.dev_count = 3
+    p = b200.factory(L.backend_t.multi_CUDA, oi)
+    p.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
+    dv_rhod = 20.0 ** 3 * f["rhod"]
+
+    def dry_volume():
+        p.diag_all(); p.diag_dry_mom(3)
+        return float((p.outbuf().reshape(6, 4, 6) * dv_rhod).sum()) * 4. / 3 * np.pi
+    v0 = dry_volume()
+    for _ in range(5):
+        p.step_sync(o, f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"])
+        p.step_async(o)
+    v1 = dry_volume()
+    fallen = p.diag_puddle()["dry_volume"]
+    assert abs(v1 + fallen - v0) <= 1e-10 * v0, (v0, v1, fallen)
+
+
+@pytest.mark.skipif("n_devices() < 2")
+def test_multi_cuda_devices_match_fold(b200, monkeypatch):
+    """transport independence: 2 slabs on 2 GPUs (peer copies) == the same 2 slabs on one GPU, bit for bit"""
+    res = []
+    for fold in ("1", "0"):
+        monkeypatch.setenv("LCX_SLABS_ON_ONE_DEVICE", fold)
+        oi, o, f = S.box_3d(b200, nx=6, ny=4, nz=6, sd_conc=24, rain_mode=True, cx=0.5)
+        oi.dev_count = 2
+        p = b200.factory(L.backend_t.multi_CUDA, oi)
+        p.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
+        for _ in range(5):
+            p.step_sync(o, f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"])
+            p.step_async(o)
+        res.append(per_cell(p, (6, 4, 6)) + [f["th"].copy(), f["rv"].copy()])
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.skipif("n_devices() < 2")
+def test_torchrun_ranks_roundtrip():
+    """one process per GPU, migrants exchanged over NCCL on the engine's own device buffers"""
+    n = min(n_devices(), 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+           "--master-port", "29517", os.path.join(ROOT, "tests", "dist_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0 and "DIST_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
