@@ -171,6 +171,8 @@ int  lcx_moms_calc(lcx_engine *e, int attr, double power, int specific);  /* mom
 int  lcx_diag_sd_conc(lcx_engine *e);                                     /* particles_diag.ipp:193-211      */
 int  lcx_diag_cell_field(lcx_engine *e, int field);                       /* particles_diag.ipp:148-190      */
 int  lcx_diag_precip_rate(lcx_engine *e);                                 /* particles_diag.ipp:561-586      */
+int  lcx_diag_mass_dens(lcx_engine *e, int attr, double rad, double sig0, double xp);   /* particles_impl_mass_dens.ipp:13-98 */
+int  lcx_diag_vel_div(lcx_engine *e, double dt);                          /* particles_diag.ipp:497-558      */
 int  lcx_diag_max_rw(lcx_engine *e);                                      /* particles_diag.ipp:606-634      */
 int  lcx_outbuf(lcx_engine *e, void *dst, int64_t count);                 /* fill_outbuf.ipp:13-37           */
 

@@ -403,6 +403,9 @@ int lcx_diag_cell_field(lcx_engine *e, int field)
 }
 
 int lcx_diag_precip_rate(lcx_engine *e) { return guarded([&] { use_device(e); lcx::diag_precip_rate(e); }); }
+int lcx_diag_mass_dens(lcx_engine *e, int attr, double rad, double sig0, double xp)
+{ return guarded([&] { use_device(e); lcx::diag_mass_dens(e, attr, rad, sig0, xp); }); }
+int lcx_diag_vel_div(lcx_engine *e, double dt) { return guarded([&] { use_device(e); lcx::diag_vel_div(e, dt); }); }
 int lcx_diag_max_rw(lcx_engine *e) { return guarded([&] { use_device(e); lcx::diag_max_rw(e); }); }
 
 int lcx_outbuf(lcx_engine *e, void *dst, int64_t count) { return lcx_cells_get(e, LCX_F_MOM, dst, count); }

@@ -38,6 +38,17 @@ namespace lcx
       const real_t *w, *rw2, *vt;
       __device__ __forceinline__ real_t operator()(size_t i) const { return w[i] * (pow(rw2[i], real_t(3. / 2)) * vt[i]); }
     };
+    struct term_mass_dens   // Gaussian-kernel estimator of the mass density function (particles_impl_mass_dens.ipp:13-35)
+    {
+      const real_t *w, *x; const idx_t *ijk; const uint32_t *off; real_t rad, sig0, xp;
+      __device__ __forceinline__ real_t operator()(size_t i) const
+      {
+        const idx_t c = ijk[i];
+        const real_t sig = sig0 / pow(real_t(off[c + 1] - off[c]), real_t(0.2));
+        const real_t xi = x[i];
+        return w[i] / sig * pow(xi, 3 * xp) * exp(-pow((log(pow(xi, xp)) - log(rad)) / sig, 2) / 2.);
+      }
+    };
     struct term_radius   // rw, reduced with max (particles_diag.ipp:606-634)
     {
       const real_t *rw2;
@@ -52,14 +63,17 @@ namespace lcx
       return v;
     }
 
-    __device__ __forceinline__ real_t normalise(real_t s, bool specific, idx_t c, const real_t *dv, const real_t *rhod)
+    enum { NORM_NONE = 0, NORM_SPECIFIC = 1, NORM_MASS_DENS = 2 };
+    __device__ __forceinline__ real_t normalise(real_t s, int mode, idx_t c, const real_t *dv, const real_t *rhod)
     {
-      if (specific) { s = s / dv[c]; s = s / rhod[c]; }   // two successive divisions, as moms.ipp:322-350
+      if (mode == NORM_SPECIFIC) { s = s / dv[c]; s = s / rhod[c]; }   // two successive divisions, as moms.ipp:322-350
+      else if (mode == NORM_MASS_DENS)                                  // particles_impl_mass_dens.ipp:75-96
+        s = (4. / 3. * cst<real_t>::rho_w() * sqrt(cst<real_t>::pi() / 2.)) * s / dv[c];
       return s;
     }
 
     template <class Term, bool IS_MAX>
-    __global__ void __launch_bounds__(TPB) k_cell_reduce_small(idx_t n_cell, const uint32_t *__restrict__ off, Term term, bool specific,
+    __global__ void __launch_bounds__(TPB) k_cell_reduce_small(idx_t n_cell, const uint32_t *__restrict__ off, Term term, int specific,
                                                               const real_t *__restrict__ dv, const real_t *__restrict__ rhod, real_t *__restrict__ out)
     {
       const idx_t c = blockIdx.x * WARPS + (threadIdx.x >> 5);
@@ -94,7 +108,7 @@ namespace lcx
 
     template <bool IS_MAX>
     __global__ void __launch_bounds__(TPB) k_cell_reduce_final(idx_t n_cell, const uint32_t *__restrict__ off, unsigned n_chunks, const real_t *__restrict__ partial,
-                                                              bool specific, const real_t *__restrict__ dv, const real_t *__restrict__ rhod, real_t *__restrict__ out)
+                                                              int specific, const real_t *__restrict__ dv, const real_t *__restrict__ rhod, real_t *__restrict__ out)
     {
       const idx_t c = blockIdx.x * TPB + threadIdx.x;
       if (c >= n_cell) return;
@@ -105,11 +119,11 @@ namespace lcx
     }
 
     template <class Term, bool IS_MAX>
-    void cell_reduce(lcx_engine *e, Term term, bool specific, real_t *out)
+    void cell_reduce(lcx_engine *e, Term term, int norm, real_t *out)
     {
       const grid_t &g = e->grid;
       if (!e->grouped) throw error("per-cell reduction requested while super-droplets are not grouped by cell");
-      const bool spec = specific && g.n_dims > 0;
+      const int spec = (norm == NORM_SPECIFIC && g.n_dims == 0) ? int(NORM_NONE) : norm;   // a parcel is 1 kg of dry air
       if (e->max_count <= BIG_THRESHOLD)
       {
         LCX_LAUNCH(e, (k_cell_reduce_small<Term, IS_MAX>), div_up(g.n_cell, WARPS), TPB, 0, g.n_cell, e->cell_off.p, term, spec, e->dv.p, e->rhod.p, out);
@@ -176,7 +190,7 @@ namespace lcx
   void cell_moment(lcx_engine *e, const real_t *weight_or_null, const real_t *attr, real_t power, bool specific, real_t *out)
   {
     term_moment t = {weight_or_null, e->S().n.p, attr, power};
-    cell_reduce<term_moment, false>(e, t, specific, out);
+    cell_reduce<term_moment, false>(e, t, specific ? NORM_SPECIFIC : NORM_NONE, out);
   }
 
   void moms_select(lcx_engine *e, int kind, int attr, real_t lo, real_t hi, bool cons)
@@ -194,7 +208,7 @@ namespace lcx
   {
     if (!e->selected) throw error("diag_sd_conc called before a selector");
     term_positive t = {e->n_filtered.p};
-    cell_reduce<term_positive, false>(e, t, false, e->count_mom.p);
+    cell_reduce<term_positive, false>(e, t, NORM_NONE, e->count_mom.p);
   }
 
   void diag_precip_rate(lcx_engine *e)
@@ -202,12 +216,52 @@ namespace lcx
     if (!e->selected) throw error("diag_precip_rate called before a selector");
     hskpng_vterm(e, false);   // side effect kept: the reference refreshes every vt here (particles_diag.ipp:565)
     term_precip t = {e->n_filtered.p, e->S().rw2.p, e->S().vt.p};
-    cell_reduce<term_precip, false>(e, t, false, e->count_mom.p);
+    cell_reduce<term_precip, false>(e, t, NORM_NONE, e->count_mom.p);
   }
 
   void diag_max_rw(lcx_engine *e)
   {
     term_radius t = {e->S().rw2.p};
-    cell_reduce<term_radius, true>(e, t, false, e->count_mom.p);
+    cell_reduce<term_radius, true>(e, t, NORM_NONE, e->count_mom.p);
+  }
+
+  void diag_mass_dens(lcx_engine *e, int attr, real_t rad, real_t sig0, real_t xp)
+  {
+    if (!e->selected) throw error("diag_*_mass_dens called before a selector");
+    term_mass_dens t = {e->n_filtered.p, attr_ptr(e, attr), e->S().ijk.p, e->cell_off.p, rad, sig0, xp};
+    cell_reduce<term_mass_dens, false>(e, t, NORM_MASS_DENS, e->count_mom.p);
+  }
+
+  namespace
+  {
+    // divergence of the Courant field, divided by dt (particles_diag.ipp:497-558; the reference's argument is named dx)
+    __global__ void k_vel_div(grid_t g, real_t dt, const real_t *__restrict__ Cx, const real_t *__restrict__ Cy, const real_t *__restrict__ Cz, real_t *__restrict__ out)
+    {
+      const idx_t c = blockIdx.x * blockDim.x + threadIdx.x;
+      if (c >= g.n_cell) return;
+      const idx_t cp = c + g.halo_x;
+      real_t div = 0;
+      if (g.n_dims == 3)
+      {
+        const idx_t col = idx_t(g.nz) * g.ny;
+        const idx_t yl = cp + (cp / col) * g.nz;
+        div = div + (Cy[yl + g.nz] - Cy[yl]) / dt;
+      }
+      if (g.n_dims >= 2)
+      {
+        const idx_t zl = g.n_dims == 3 ? cp + g.ny * (cp / (idx_t(g.nz) * g.ny)) + (cp - (cp / (idx_t(g.nz) * g.ny)) * (idx_t(g.nz) * g.ny)) / g.nz : cp + cp / g.nz;
+        div = div + (Cz[zl + 1] - Cz[zl]) / dt;
+      }
+      const idx_t xr = cp + (g.n_dims == 3 ? idx_t(g.nz) * g.ny : idx_t(g.nz));
+      div = div + (Cx[xr] - Cx[cp]) / dt;
+      out[c] = div;
+    }
+  }
+
+  void diag_vel_div(lcx_engine *e, real_t dt)
+  {
+    const grid_t &g = e->grid;
+    if (g.n_dims == 0) return;
+    LCX_LAUNCH(e, k_vel_div, div_up(g.n_cell, TPB), TPB, 0, g, dt, e->courant_x.p, e->courant_y.p, e->courant_z.p, e->count_mom.p);
   }
 }

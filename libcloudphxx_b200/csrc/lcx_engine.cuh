@@ -177,6 +177,8 @@ namespace lcx
   void diag_sd_conc(lcx_engine *e);
   void diag_precip_rate(lcx_engine *e);
   void diag_max_rw(lcx_engine *e);
+  void diag_mass_dens(lcx_engine *e, int attr, real_t rad, real_t sig0, real_t xp);
+  void diag_vel_div(lcx_engine *e, real_t dt);
 
   // ---- lcx_cond.cu -----------------------------------------------------------------------------------
   void cond(lcx_engine *e, real_t dt_sub, real_t RH_max, int step, int sstp);

@@ -937,6 +937,8 @@ namespace libcloudphxx
         void diag_RH() override { for (auto &s : slabs) s->diag_field(LCX_F_RH); }
         void diag_precip_rate() override { for (auto &s : slabs) chk(lcx_diag_precip_rate(s->e)); }
         void diag_max_rw() override { for (auto &s : slabs) chk(lcx_diag_max_rw(s->e)); }
+        void diag_wet_mass_dens(const real_t &rad, const real_t &sig0) override { for (auto &s : slabs) chk(lcx_diag_mass_dens(s->e, LCX_A_RW2, rad, sig0, 1. / 2.)); }
+        void diag_vel_div() override { for (auto &s : slabs) chk(lcx_diag_vel_div(s->e, s->oi.dt)); }
 
         real_t *outbuf() override
         {

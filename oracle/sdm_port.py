@@ -1,0 +1,649 @@
+"""CPU restatement of libcloudph++'s Lagrangian super-droplet step (serial back-end), in numpy / plain Python.
+
+TEST INFRASTRUCTURE - not part of the product.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may
+import this module; libcloudphxx_b200/ never does.
+
+Parity status: PINNED.  tests/test_cpu_oracle.py runs this port beside the reference's own serial back-end built from the
+unmodified sources (oracle/_ref, see oracle/build_ref.py) on the same seeded inputs and requires bit-identical super-droplet
+state (multiplicities, radii, positions) and per-cell fields; tests/golden/ holds vectors generated from that reference
+build (tools/make_golden.py) so the pin also holds where /root/reference is absent.  Scalar libm calls go through
+Python's math module (the same glibc the reference's CPU back-end uses), numpy is used only for + - * / sqrt and for
+integer work, so that agreement can be exact.
+
+Every function cites the reference code it restates (paths relative to the reference repository root).
+"""
+import math
+
+import numpy as np
+
+# ---- constants: include/libcloudph++/common/{moist_air.hpp:26-45,104,110; const_cp.hpp:27-31; earth.hpp:17-22} ---------
+c_pd, c_pv, c_pw = 1005.0, 1850.0, 4218.0
+M_d = 0.02897
+M_v = 1 * 1e-3 + 17 * 1e-3
+eps = M_v / M_d
+kaBoNA = 8.3144621
+R_d, R_v = kaBoNA / M_d, kaBoNA / M_v
+rho_w = 1e3
+D_0, K_0 = 2.26e-5, 2.4e-2
+p_1000 = 100000.0
+p_tri, T_tri, l_tri = 611.73, 273.16, 2.5e6
+g_acc = 9.81
+p_stp, T_stp = 101325.0, 273.15 + 15
+rho_stp = p_stp / T_stp / R_d
+PI = math.pi
+
+N_ITER = 100                     # src/detail/config.hpp:17
+EPS_TOL = max(math.ldexp(1.0, 1 - 16), 4 * np.finfo(np.float64).eps)   # eps_tolerance(sizeof(double)*8/4): toms748.hpp:262-286
+VT0_N_BIN, VT0_LN_R_MIN, VT0_LN_R_MAX = 10000, math.log(5e-7), math.log(3e-3)   # config.hpp:27-44
+
+
+# ---- random stream: src/detail/urand.hpp:19-88 (one std::mt19937 per object; libstdc++ distributions) -------------------
+class HostRNG:
+    def __init__(self, seed):
+        self.rs = np.random.RandomState(seed)          # init_genrand(seed) == std::mt19937(seed)
+
+    def reseed(self, seed):
+        self.rs = np.random.RandomState(seed)
+
+    def raw(self, n):
+        return self.rs.randint(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.uint64)
+
+    def u01(self, n):
+        # std::uniform_real_distribution<double> = generate_canonical<double,53>: two 32-bit draws, low word first
+        r = self.raw(2 * n)
+        v = (r[0::2].astype(np.float64) + r[1::2].astype(np.float64) * 4294967296.0) / 18446744073709551616.0
+        return np.where(v >= 1.0, np.nextafter(1.0, 0.0), v)
+
+    def un(self, n):
+        return self.raw(n).astype(np.uint32)           # std::uniform_int_distribution<unsigned>(0, UINT_MAX)
+
+
+# ---- per-cell thermodynamics: src/impl/housekeeping/particles_impl_hskpng_Tpr.ipp:219-305 ------------------------------
+def T_of_th_dry(th, rhod):                              # common/theta_dry.hpp:24-35
+    return math.pow(th * math.pow(rhod * R_d / p_1000, R_d / c_pd), c_pd / (c_pd - R_d))
+
+
+def p_vs_cc(T):                                         # common/const_cp.hpp:34-43
+    return p_tri * math.exp((l_tri + (c_pw - c_pv) * T_tri) / R_v * (1.0 / T_tri - 1.0 / T) - (c_pw - c_pv) / R_v * math.log(T / T_tri))
+
+
+def RH_pv_cc(p, rv, T):                                 # hskpng_Tpr.ipp:71-78, common/moist_air.hpp:88-95
+    return (p * rv / (rv + eps)) / p_vs_cc(T)
+
+
+def visc(T):                                            # common/vterm.hpp:22-31
+    q = T / T_tri
+    return (1.72 * 1e-5) * (393.0 / (T + 120.0)) * (q * math.sqrt(q))
+
+
+def l_v(T):                                             # common/const_cp.hpp:82-87
+    return l_tri + (c_pv - c_pw) * (T - T_tri)
+
+
+def kelvin_A(T):                                        # common/kelvin_term.hpp:23-41
+    return 2.0 * (0.07275 * (1.0 - 0.002 * (T - 291.0))) / R_v / T / rho_w
+
+
+def a_w(rw3, rd3, kappa):                               # common/kappa_koehler.hpp:46-54
+    return (rw3 - rd3) / (rw3 - rd3 * (1.0 - kappa))
+
+
+# ---- TOMS 748: include/libcloudph++/common/detail/toms748.hpp:291-454 ----------------------------------------------------
+DBL_EPS, DBL_MIN, DBL_MAX = np.finfo(np.float64).eps, np.finfo(np.float64).tiny, np.finfo(np.float64).max
+
+
+def _tol(a, b):
+    return abs(a - b) <= EPS_TOL * min(abs(a), abs(b))
+
+
+def _safe_div(num, den, r):
+    if abs(den) < 1 and abs(den * DBL_MAX) <= abs(num):
+        return r
+    return num / den
+
+
+def _secant(a, b, fa, fb):
+    tol = DBL_EPS * 5
+    c = a - (fa / (fb - fa)) * (b - a)
+    if c <= a + abs(a) * tol or c >= b - abs(b) * tol:
+        return (a + b) / 2
+    return c
+
+
+def _quadratic(a, b, d, fa, fb, fd, count):
+    B = _safe_div(fb - fa, b - a, DBL_MAX)
+    A = _safe_div(fd - fb, d - b, DBL_MAX)
+    A = _safe_div(A - B, d - a, 0.0)
+    if A == 0:
+        return _secant(a, b, fa, fb)
+    c = a if math.copysign(1.0, A * fa) > 0 else b
+    for _ in range(count):
+        c -= _safe_div(fa + (B + A * (c - b)) * (c - a), B + A * (2 * c - a - b), 1 + c - a)
+    if c <= a or c >= b:
+        c = _secant(a, b, fa, fb)
+    return c
+
+
+def _cubic(a, b, d, e, fa, fb, fd, fe):
+    with np.errstate(all="ignore"):
+        q11 = np.float64(d - e) * fd / np.float64(fe - fd)
+        q21 = np.float64(b - d) * fb / np.float64(fd - fb)
+        q31 = np.float64(a - b) * fa / np.float64(fb - fa)
+        d21 = np.float64(b - d) * fd / np.float64(fd - fb)
+        d31 = np.float64(a - b) * fb / np.float64(fb - fa)
+        q22 = (d21 - q11) * fb / np.float64(fe - fb)
+        q32 = (d31 - q21) * fa / np.float64(fd - fa)
+        d32 = (d31 - q21) * fd / np.float64(fd - fa)
+        q33 = (d32 - q22) * fa / np.float64(fe - fa)
+        c = float(q31 + q32 + q33 + a)
+    if not (c > a and c < b):
+        c = _quadratic(a, b, d, fa, fb, fd, 3)
+    return c
+
+
+def _prof(fa, fb, fd, fe):
+    m = DBL_MIN * 32
+    return (abs(fa - fb) < m or abs(fa - fd) < m or abs(fa - fe) < m or abs(fb - fd) < m or abs(fb - fe) < m or abs(fd - fe) < m)
+
+
+def toms748(f, a, b, fa, fb, max_iter=N_ITER):
+    count = max_iter
+    st = dict(a=a, b=b, fa=fa, fb=fb, d=0.0, fd=0.0)
+
+    def bracket(c):
+        a, b = st["a"], st["b"]
+        tol = DBL_EPS * 2
+        if (b - a) < 2 * tol * a:
+            c = a + (b - a) / 2
+        elif c <= a + abs(a) * tol:
+            c = a + abs(a) * tol
+        elif c >= b - abs(b) * tol:
+            c = b - abs(a) * tol
+        fc = f(c)
+        if fc == 0:
+            st.update(a=c, fa=0.0, d=0.0, fd=0.0)
+            return
+        if math.copysign(1.0, st["fa"] * fc) < 0:
+            st.update(d=st["b"], fd=st["fb"], b=c, fb=fc)
+        else:
+            st.update(d=st["a"], fd=st["fa"], a=c, fa=fc)
+
+    def done():
+        if st["fa"] == 0:
+            st["b"] = st["a"]
+        elif st["fb"] == 0:
+            st["a"] = st["b"]
+        return (st["a"] + st["b"]) / 2
+
+    if _tol(a, b) or fa == 0 or fb == 0:
+        return done()
+    e = fe = 1e5
+    st["fd"] = 1e5
+    if st["fa"] != 0:
+        bracket(_secant(st["a"], st["b"], st["fa"], st["fb"]))
+        count -= 1
+        if count and st["fa"] != 0 and not _tol(st["a"], st["b"]):
+            c = _quadratic(st["a"], st["b"], st["d"], st["fa"], st["fb"], st["fd"], 2)
+            e, fe = st["d"], st["fd"]
+            bracket(c)
+            count -= 1
+    while count and st["fa"] != 0 and not _tol(st["a"], st["b"]):
+        a0, b0 = st["a"], st["b"]
+        if _prof(st["fa"], st["fb"], st["fd"], fe):
+            c = _quadratic(st["a"], st["b"], st["d"], st["fa"], st["fb"], st["fd"], 2)
+        else:
+            c = _cubic(st["a"], st["b"], st["d"], e, st["fa"], st["fb"], st["fd"], fe)
+        e, fe = st["d"], st["fd"]
+        bracket(c)
+        count -= 1
+        if count == 0 or st["fa"] == 0 or _tol(st["a"], st["b"]):
+            break
+        if _prof(st["fa"], st["fb"], st["fd"], fe):
+            c = _quadratic(st["a"], st["b"], st["d"], st["fa"], st["fb"], st["fd"], 3)
+        else:
+            c = _cubic(st["a"], st["b"], st["d"], e, st["fa"], st["fb"], st["fd"], fe)
+        bracket(c)
+        count -= 1
+        if count == 0 or st["fa"] == 0 or _tol(st["a"], st["b"]):
+            break
+        if abs(st["fa"]) < abs(st["fb"]):
+            u, fu = st["a"], st["fa"]
+        else:
+            u, fu = st["b"], st["fb"]
+        c = u - 2 * (fu / (st["fb"] - st["fa"])) * (st["b"] - st["a"])
+        if abs(c - u) > (st["b"] - st["a"]) / 2:
+            c = st["a"] + (st["b"] - st["a"]) / 2
+        e, fe = st["d"], st["fd"]
+        bracket(c)
+        count -= 1
+        if count == 0 or st["fa"] == 0 or _tol(st["a"], st["b"]):
+            break
+        if (st["b"] - st["a"]) < 0.5 * (b0 - a0):
+            continue
+        e, fe = st["d"], st["fd"]
+        bracket(st["a"] + (st["b"] - st["a"]) / 2)
+        count -= 1
+    return done()
+
+
+# ---- equilibrium wet radius: common/kappa_koehler.hpp:58-146, src/impl/initialization/particles_impl_init_wet.ipp:18-74 --
+def rw3_eq(rd3, kappa, RH, T):
+    if kappa == 0:
+        return rd3
+    A = kelvin_A(T)
+    f = lambda rw3: RH - a_w(rw3, rd3, kappa) * math.exp(A / math.cbrt(rw3))
+    lo, hi = rd3, rd3 * (1 - RH * (1 - kappa)) / (1 - RH)
+    return toms748(f, lo, hi, f(lo), f(hi))
+
+
+# ---- condensational growth: src/impl/condensation/common/particles_impl_cond_common.ipp:79-338 --------------------------
+def drw2_dt(rw2, rhod, rv, T, p, RH_eff, eta, rd3, kpa, vt, lam_D, lam_K):
+    rw = math.sqrt(rw2)
+    rw3 = rw * rw * rw
+    Re = vt * (2.0 * rw) * rhod / eta
+    Sc = eta / rhod / D_0
+    Pr = c_pd * eta / K_0
+
+    def beta(Kn):                                       # common/transition_regime.hpp:15-19
+        return (1 + Kn) / (1 + 1.71 * Kn + 1.33 * Kn * Kn)
+
+    def Nu(P):                                          # common/ventil.hpp:29-45
+        pw = math.pow(Re, .077) if Re >= 0 else float("nan")
+        return 1.0 + math.cbrt(1.0 + Re * P) * (pw if 1.0 < pw else 1.0)
+    D = D_0 * beta(lam_D / rw) * (Nu(Sc) / 2)
+    K = K_0 * beta(lam_K / rw) * (Nu(Pr) / 2)
+    lv = l_v(T)
+    rho_v = rhod * rv
+    klv = math.exp(kelvin_A(T) / rw)
+    rdrdt = (1.0 - a_w(rw3, rd3, kpa) * klv / RH_eff) / rho_w / (1.0 / D / rho_v + lv / K / RH_eff / T * (lv / R_v / T - 1.0))   # common/maxwell-mason.hpp:33-45
+    return 2.0 * rdrdt
+
+
+def advance_rw2(rw2_old, dt, RH_max, rhod, rv, T, p, RH, eta, rd3, kpa, vt, lam_D, lam_K, cond_mlt=2.0):
+    if rw2_old <= 0:
+        return rw2_old
+    RH_eff = RH_max if RH > RH_max else RH
+    g = lambda x: drw2_dt(x, rhod, rv, T, p, RH_eff, eta, rd3, kpa, vt, lam_D, lam_K)
+    f = lambda x: (rw2_old + dt * g(x) - x)
+    drw2 = dt * g(rw2_old)
+    if drw2 == 0:
+        return rw2_old
+    rd = math.cbrt(rd3)
+    rd2 = rd * rd
+    a = max(rd2, rw2_old + min(0.0, cond_mlt * drw2))
+    b = rw2_old + max(0.0, cond_mlt * drw2)
+    if a == b:
+        return rw2_old
+    if drw2 > 0:
+        fa, fb = drw2, f(b)
+    else:
+        fa, fb = f(a), drw2
+    if fa * fb > 0:
+        new = rw2_old + drw2
+    else:
+        new = toms748(f, a, b, fa, fb)
+    return rd2 if new < rd2 else new
+
+
+# ---- terminal velocity (beard77fast): common/vterm.hpp:112-164, hskpng_vterm.ipp:14-36,185-342, init_vterm.ipp:36-59 --------
+def vt_beard77_v0(r):
+    m_s = [0.105035e2, 0.108750e1, -0.133245, -0.659969e-2]
+    m_l = [0.65639e1, -0.10391e1, -0.14001e1, -0.82736e0, -0.34277e0, -0.83072e-1, -0.10583e-1, -0.54208e-3]
+    x = math.log(2 * 100 * r)
+    y = 0.0
+    for i, m in enumerate(m_s if r <= 20e-6 else m_l):
+        y += m * math.pow(x, float(i))
+    return math.exp(y) / 100.
+
+
+def vt0_table():
+    dlnr = (VT0_LN_R_MAX - VT0_LN_R_MIN) / VT0_N_BIN
+    return np.array([vt_beard77_v0(math.exp(VT0_LN_R_MIN + (it + 0.5) * dlnr)) for it in range(VT0_N_BIN)])
+
+
+def vt_beard77_fact(r, p, rhoa, eta):
+    eta_0 = 1.818e-5
+    if r <= 20e-6:
+        l_0 = 6.62e-8
+        l = l_0 * (eta / eta_0) * math.sqrt(p_stp / p * rho_stp / rhoa)
+        return (eta_0 / eta) * (1 + 1.255 * (l / r)) / (1 + 1.255 * (l_0 / r))
+    eps_s = (eta_0 / eta) - 1
+    eps_c = math.sqrt(rho_stp / rhoa) - 1
+    return 1.104 * eps_s + ((1.058 * eps_c - 1.104 * eps_s) * (5.52 + math.log(2 * 100 * r)) / 5.01) + 1
+
+
+def vt_beard77fast(rw2, p, rhod, eta, table):
+    dlnr = (VT0_LN_R_MAX - VT0_LN_R_MIN) / VT0_N_BIN
+    lnr = .5 * math.log(rw2)
+    b = 0 if lnr <= VT0_LN_R_MIN else (VT0_N_BIN - 1 if lnr >= VT0_LN_R_MAX else int((lnr - VT0_LN_R_MIN) / dlnr))
+    return vt_beard77_fact(math.sqrt(rw2), p, rhod, eta) * table[b]
+
+
+# ---- collision kernels: src/detail/kernels.hpp:40-176, kernel_interpolation.hpp:9-64, kernel_utils.hpp:12-29 ---------------
+def kernel_index(R):
+    return int(R) if R <= 100. else int(100 + (R - 100.) / 10.)
+
+
+def kernel_vector_index(i, j):
+    return int(0.5 * i * (i + 1) + j) if i >= j else int(0.5 * j * (j + 1) + i)
+
+
+def interpolated_efficiency(eff, r_max, r1, r2):
+    r1 *= 1e6
+    r2 *= 1e6
+    if r1 >= r_max:
+        r1 = r_max - 1e-6
+    if r2 >= r_max:
+        r2 = r_max - 1e-6
+    if r1 >= 100.:
+        x0, dx = int(math.floor(r1 / 10.) * 10), 10
+    else:
+        x0, dx = int(math.floor(r1)), 1
+    if r2 >= 100.:
+        x2, dy = int(math.floor(r2 / 10.) * 10), 10
+    else:
+        x2, dy = int(math.floor(r2)), 1
+    x1, x3 = x0 + dx, x2 + dy
+    iv = [kernel_vector_index(kernel_index(a), kernel_index(b)) for a, b in ((x0, x2), (x1, x2), (x0, x3), (x1, x3))]
+    w = [r1 - x0, x1 - r1, r2 - x2, x3 - r2]
+    return (eff[iv[0]] * w[1] * w[3] + eff[iv[1]] * w[0] * w[3] + eff[iv[2]] * w[1] * w[2] + eff[iv[3]] * w[0] * w[2]) / dx / dy
+
+
+def coal_kernel(kind, params, n_a, n_b, rw2_a, rw2_b, vt_a, vt_b):
+    nmax = float(max(n_a, n_b))
+    if kind == "golovin":
+        return PI * 4. / 3. * params["b"] * nmax * (rw2_a * math.sqrt(rw2_a) + rw2_b * math.sqrt(rw2_b))
+    geo = PI * nmax * abs(vt_a - vt_b) * (rw2_a + rw2_b + 2. * math.sqrt(rw2_a * rw2_b))
+    if kind == "geometric":
+        return geo * params["mult"] if "mult" in params else geo
+    if kind == "efficiencies":
+        return interpolated_efficiency(params["eff"], params["r_max"], math.sqrt(rw2_a), math.sqrt(rw2_b)) * geo
+    raise ValueError(kind)
+
+
+# ---- the particle system ----------------------------------------------------------------------------------------------------
+class Particles:
+    """0-D / 2-D / 3-D box, sd_conc initialisation, per-cell condensation sub-stepping, SDM coalescence, implicit / Euler
+    advection, sedimentation, periodic side walls, open top / bottom.  Call order as the reference (src/particles_step.ipp)."""
+
+    def __init__(self, nx=0, ny=0, nz=0, dx=1., dy=1., dz=1., dt=1., x0=0., y0=0., z0=0., x1=1., y1=1., z1=1., sd_conc=0, n_sd_max=0,
+                 sstp_cond=1, sstp_coal=1, kernel=None, kernel_params=None, vt="beard77fast", adve_scheme="implicit",
+                 dry_distros=(), RH_max_init=.95, rng_seed=44, sedi_switch=True, coal_switch=True):
+        self.nx, self.ny, self.nz = nx, ny, nz
+        self.dx, self.dy, self.dz, self.dt = dx, dy, dz, dt
+        self.x0, self.y0, self.z0, self.x1, self.y1, self.z1 = x0, y0, z0, x1, y1, z1
+        self.n_dims = (nx > 0) + (ny > 0) + (nz > 0)
+        self.n_cell = max(1, nx) * max(1, ny) * max(1, nz)
+        self.sd_conc, self.n_sd_max = sd_conc, n_sd_max
+        self.sstp_cond, self.sstp_coal = sstp_cond, sstp_coal
+        self.kernel, self.kernel_params = kernel, kernel_params or {}
+        self.vt_kind, self.adve_scheme = vt, adve_scheme
+        self.dry_distros = list(dry_distros)          # [(kappa, callable n(ln r))], iterated in ascending kappa like std::map
+        self.RH_max_init = RH_max_init
+        self.rng_seed = rng_seed
+        self.rng = HostRNG(rng_seed)
+        self.puddle = dict(liquid_volume=0., dry_volume=0., liquid_number=0., particle_number=0.)
+        self.table = vt0_table() if vt == "beard77fast" else None
+
+    # -- grid helpers: src/impl/initialization/particles_impl_init_grid.ipp:13-155 ------------------------------------------
+    def unravel(self, c):
+        nz1, ny1 = max(1, self.nz), max(1, self.ny)
+        return (c // nz1) // ny1, (c // nz1) % ny1, c % nz1
+
+    def cell_volumes(self):
+        i, j, k = self.unravel(np.arange(self.n_cell))
+        ext = lambda idx, d, a, b: np.minimum((idx + 1) * d, b) - np.maximum(idx * d, a)
+        return np.maximum(0., ext(i, self.dx, self.x0, self.x1) * ext(j, self.dy, self.y0, self.y1) * ext(k, self.dz, self.z0, self.z1))
+
+    def hskpng_Tpr(self):                               # hskpng_Tpr.ipp:219-305 (th_dry, variable pressure, pv_cc)
+        for c in range(self.n_cell):
+            T = T_of_th_dry(self.th[c], self.rhod[c])
+            p = self.rhod[c] * (R_d + self.rv[c] * R_v) * T
+            self.T[c], self.p[c] = T, p
+            self.RH[c] = RH_pv_cc(p, self.rv[c], T)
+            self.eta[c] = visc(T)
+        if self.n_dims == 0:
+            self.dv = 1.0 / self.rhod
+
+    def hskpng_mfp(self):                               # hskpng_mfp.ipp:42-52, common/mean_free_path.hpp:16-51
+        self.lam_D = np.array([2.0 * D_0 / math.sqrt(2.0 * (R_v * T)) for T in self.T])
+        self.lam_K = np.array([.8 * (K_0 * T / p) / math.sqrt(2.0 * (R_d * T)) for T, p in zip(self.T, self.p)])
+
+    def hskpng_vterm(self, only_invalid):               # hskpng_vterm.ipp:185-342
+        for s in range(self.n_part):
+            if self.rw2[s] > 0 and (not only_invalid or self.vt[s] == -1.0):
+                c = self.ijk[s]
+                self.vt[s] = vt_beard77fast(self.rw2[s], self.p[c], self.rhod[c], self.eta[c], self.table) if self.vt_kind == "beard77fast" else 0.0
+
+    # -- init: src/particles_init.ipp:16-131 and src/impl/initialization/* ----------------------------------------------------
+    def init(self, th, rv, rhod, Cx=None, Cy=None, Cz=None):
+        C = self.n_cell
+        self.th, self.rv, self.rhod = (np.array(a, dtype=np.float64).reshape(C).copy() for a in (th, rv, rhod))
+        self.Cx, self.Cy, self.Cz = Cx, Cy, Cz
+        self.T, self.p, self.RH, self.eta = (np.zeros(C) for _ in range(4))
+        self.dv = self.cell_volumes() if self.n_dims else np.zeros(C)
+        self.hskpng_Tpr()
+        parts = {k: [] for k in ("n", "rd3", "rw2", "kpa", "x", "y", "z", "ijk")}
+        ranges = [self.dist_analysis(fun) for _, fun in self.dry_distros]
+        tot = sum(r[1] - r[0] for r in ranges)
+        for (kappa, fun), (lmin, lmax, mult) in zip(self.dry_distros, ranges):
+            fraction = (lmax - lmin) / tot
+            mult *= self.sd_conc // int(fraction * self.sd_conc + 0.5)          # integer division: init_SD_with_distros_sd_conc.ipp:28
+            per_cell = int(fraction * self.sd_conc)
+            n_new = per_cell * C
+            ijk = np.repeat(np.arange(C), per_cell)                               # init_ijk.ipp:36-52
+            u01 = self.rng.u01(n_new)                                             # init_dry_sd_conc.ipp:48
+            s = np.arange(n_new)
+            lnrd = lmin + ((s - ijk * per_cell) + u01) * (lmax - lmin) / float(per_cell)
+            rd3 = np.array([math.exp(3 * v) for v in lnrd])
+            n = np.empty(n_new, dtype=np.uint64)
+            rw2 = np.empty(n_new)
+            for q in range(n_new):
+                v = mult * fun(math.log(rd3[q]) / 3.)                             # init_n.ipp:48-137
+                v = v * self.rhod[ijk[q]] / rho_stp
+                if self.n_dims > 0:
+                    v = v * self.dv[ijk[q]] / (self.dx * self.dy * self.dz)
+                n[q] = int(v + 0.5)
+                RH = min(self.RH[ijk[q]], self.RH_max_init)
+                rw2[q] = math.pow(rw3_eq(rd3[q], kappa, RH, self.T[ijk[q]]), 2. / 3)     # init_wet.ipp:18-40
+            ii, jj, kk = self.unravel(ijk)
+            pos = {}
+            for name, nn, idx, a, b, d in (("x", self.nx, ii, self.x0, self.x1, self.dx), ("y", self.ny, jj, self.y0, self.y1, self.dy),
+                                           ("z", self.nz, kk, self.z0, self.z1, self.dz)):
+                if nn == 0:
+                    pos[name] = np.zeros(0)
+                    continue
+                u = self.rng.u01(n_new)                                           # init_xyz.ipp:49-73
+                pos[name] = u * np.minimum(b, (idx + 1) * d) + (1. - u) * np.maximum(a, idx * d)
+            for k, v in (("n", n), ("rd3", rd3), ("rw2", rw2), ("kpa", np.full(n_new, kappa)), ("x", pos["x"]), ("y", pos["y"]), ("z", pos["z"]), ("ijk", ijk)):
+                parts[k].append(v)
+        for k, v in parts.items():
+            setattr(self, k, np.concatenate(v) if v else np.zeros(0))
+        self.ijk = self.ijk.astype(np.int64)
+        self.n_part = self.n.size
+        self.vt = np.full(self.n_part, -1.0)
+        self.hskpng_vterm(True)
+        self.old = dict(rv=self.rv.copy(), th=self.th.copy(), rhod=self.rhod.copy())   # sstp_save
+        self.sort(False)
+        self.rng.reseed(self.rng_seed)
+
+    def dist_analysis(self, fun):                       # init_dist_analysis.ipp:17-75 (automatic range detection)
+        vol = self.dv[0] if self.n_dims == 0 else self.dx * self.dy * self.dz
+        rd_min, rd_max = 1e-14, 1e-3
+        while True:
+            mult = math.log(rd_max / rd_min) / self.sd_conc * 1.0 * vol
+            lmin, lmax = math.log(rd_min), math.log(rd_max)
+            n_min, n_max = int(fun(lmin) * mult), int(fun(lmax) * mult)
+            if n_min == 0:
+                rd_min *= 1.01
+            elif n_max == 0:
+                rd_max /= 1.01
+            else:
+                return lmin, lmax, mult
+
+    # -- sort / shuffle / count: hskpng_sort.ipp:15-70, hskpng_count.ipp:16-48 --------------------------------------------------
+    def sort(self, shuffle):
+        ids = np.arange(self.n_part)
+        if shuffle:
+            un = self.rng.un(self.n_part)
+            ids = ids[np.argsort(un, kind="stable")]
+        self.sorted_id = ids[np.argsort(self.ijk[ids], kind="stable")]
+        self.sorted_ijk = self.ijk[self.sorted_id]
+        self.count_ijk, self.count_num = np.unique(self.sorted_ijk, return_counts=True)
+
+    # -- moments: particles_impl_moms.ipp:240-387 ---------------------------------------------------------------------------------
+    def moment(self, attr, power, n_filtered=None, specific=True):
+        w = self.n.astype(np.float64) if n_filtered is None else n_filtered
+        out = np.zeros(self.n_cell)
+        for pos in range(self.n_part):                   # sequential sum in sorted order, like the serial reduce_by_key
+            s = self.sorted_id[pos]
+            out[self.ijk[s]] += w[s] * math.pow(attr[s], power)
+        if specific and self.n_dims > 0:
+            out = out / self.dv / self.rhod
+        return out
+
+    # -- condensation: src/particles_step.ipp:161-336, percell/particles_impl_cond.ipp:13-139, update_th_rv.ipp:74-191 ----------
+    def step_sync(self, th, rv, rhod=None, RH_max=44., cond=True):
+        C = self.n_cell
+        self.th, self.rv = (np.array(a, dtype=np.float64).reshape(C).copy() for a in (th, rv))
+        var_rho = rhod is not None
+        if var_rho:
+            self.rhod = np.array(rhod, dtype=np.float64).reshape(C).copy()
+        if not cond:
+            return self.th, self.rv
+        self.hskpng_mfp()
+        sstp = self.sstp_cond
+        for step in range(sstp):
+            if sstp > 1:                                 # sstp_percell_step.ipp:7-47
+                for name in (("rv", "th", "rhod") if var_rho else ("rv", "th")):
+                    scl = getattr(self, name)
+                    if step == 0:
+                        self.old[name] = scl - self.old[name]
+                        scl = scl - (sstp - 1) * self.old[name] / sstp
+                    else:
+                        scl = scl + self.old[name] / sstp
+                    setattr(self, name, scl)
+            self.hskpng_Tpr()
+            if step == 0:
+                m3_before = self.moment(self.rw2, 1.5)
+            dt = self.dt / sstp
+            for s in range(self.n_part):
+                c = self.ijk[s]
+                self.rw2[s] = advance_rw2(self.rw2[s], dt, RH_max, self.rhod[c], self.rv[c], self.T[c], self.p[c], self.RH[c], self.eta[c],
+                                          self.rd3[s], self.kpa[s], self.vt[s], self.lam_D[c], self.lam_K[c])
+            m3_after = self.moment(self.rw2, 1.5)
+            drv = (-m3_before + m3_after) * (rho_w * (4. / 3) * PI)
+            self.rv = self.rv - drv
+            self.th = self.th - drv * (-self.th / self.T * np.array([l_v(T) for T in self.T]) / c_pd)
+            m3_before = m3_after
+        self.old = dict(rv=self.rv.copy(), th=self.th.copy(), rhod=self.rhod.copy())
+        return self.th, self.rv
+
+    # -- coalescence: coalescence/particles_impl_coal.ipp:99-546 --------------------------------------------------------------------
+    def coal(self, dt):
+        self.sort(True)
+        u01 = self.rng.u01(self.n_part)
+        off = np.zeros(self.n_cell + 1, dtype=np.int64)
+        off[self.count_ijk + 1] = self.count_num
+        off = np.cumsum(off)
+        n_coll = 0
+        for pos in range(self.n_part - 1):
+            c = self.sorted_ijk[pos]
+            if (pos - off[c]) % 2 != 0 or self.sorted_ijk[pos + 1] != c:
+                continue
+            a, b = self.sorted_id[pos], self.sorted_id[pos + 1]
+            m = int(off[c + 1] - off[c])
+            scl = (float(m * (m - 1)) / 2) / (m // 2) if m > 1 else 0.
+            prob = dt / self.dv[c] * scl * coal_kernel(self.kernel, self.kernel_params, int(self.n[a]), int(self.n[b]),
+                                                         self.rw2[a], self.rw2[b], self.vt[a], self.vt[b])
+            col_no = int(prob)
+            if u01[pos] < prob - col_no:
+                col_no += 1
+            if col_no == 0:
+                continue
+            hi, lo = (a, b) if self.n[a] >= self.n[b] else (b, a)
+            if self.n[lo] > 0:
+                col_no = min(col_no, int(self.n[hi]) // int(self.n[lo]))
+            n_coll += col_no
+            self.n[hi] = int(self.n[hi]) - col_no * int(self.n[lo])
+            rw = math.cbrt(col_no * self.rw2[hi] * math.sqrt(self.rw2[hi]) + self.rw2[lo] * math.sqrt(self.rw2[lo]))
+            self.rw2[lo] = rw * rw
+            rd3_new = col_no * self.rd3[hi] + self.rd3[lo]
+            if len(self.dry_distros) > 1:                # kappa mixing: coal.ipp:59-96
+                rd3_old = rd3_new - col_no * self.rd3[hi]
+                for _ in range(col_no):
+                    self.kpa[lo] = (self.kpa[hi] * self.rd3[hi] + self.kpa[lo] * rd3_old) / (self.rd3[hi] + rd3_old)
+                    rd3_old += self.rd3[hi]
+            self.rd3[lo] = rd3_new
+            self.vt[lo] = -1.0
+        return n_coll
+
+    # -- transport: advection/particles_impl_adve.ipp:27-165, sedi.ipp:13-24, bcnd.ipp:99-368 -----------------------------------------
+    def adve(self):
+        if self.n_dims == 0:
+            return
+        i, j, k = self.unravel(self.ijk)
+        dims = [("x", i, self.Cx, self.dx, 0)]
+        if self.n_dims == 3:
+            dims.append(("y", j, self.Cy, self.dy, 1))
+        if self.n_dims >= 2:
+            dims.append(("z", k, self.Cz, self.dz, self.n_dims - 1))
+        for name, idx, Cf, d, axis in dims:
+            x = getattr(self, name)
+            grid = (i, j, k) if self.n_dims == 3 else ((i, k) if self.n_dims == 2 else (i,))
+            lo = list(grid)
+            hi = list(grid)
+            hi[axis] = hi[axis] + 1
+            C_l, C_r = Cf[tuple(lo)], Cf[tuple(hi)]
+            if self.n_dims == 1:
+                C_r = C_l                                # rgt = lft + nz with nz = 0: init_grid.ipp:110-119
+            if self.adve_scheme == "implicit":
+                x = (x + d * (C_l - idx * (C_r - C_l))) / (1 - (C_r - C_l))
+            else:
+                x = 1 * x + (C_r - C_l) * (x - d * idx) + d * C_l
+            setattr(self, name, x)
+
+    def bcnd(self):
+        if self.n_dims == 0:
+            return
+        wrap = lambda x, a, b: a + np.fmod((x - a) + 10 * (b - a), b - a)
+        self.x = wrap(self.x, self.x0, self.x1)
+        if self.n_dims == 3:
+            self.y = wrap(self.y, self.y0, self.y1)
+        if self.n_dims > 1:
+            self.n[self.z >= self.z1] = 0
+            out = self.z < self.z0
+            nf = np.where(out, self.n.astype(np.float64), 0.)
+            self.puddle["liquid_volume"] += sum(4. / 3. * PI * nf[s] * math.pow(self.rw2[s], 1.5) for s in range(self.n_part))
+            self.puddle["dry_volume"] += sum(4. / 3. * PI * nf[s] * math.pow(self.rd3[s], 1.) for s in range(self.n_part))
+            self.puddle["liquid_number"] += float(np.where(self.rw2 == 0, 0., nf).sum())
+            self.puddle["particle_number"] += float(nf.sum())
+            self.n[out] = 0
+
+    def step_async(self, adve=True, sedi=True, coal=True, cond=True):
+        self.hskpng_Tpr()
+        if sedi or coal or cond:
+            self.hskpng_vterm(False)
+        n_coll = 0
+        if coal:
+            for step in range(self.sstp_coal):
+                n_coll += self.coal(self.dt / self.sstp_coal)
+                if step + 1 != self.sstp_coal:
+                    self.hskpng_vterm(True)
+        if adve:
+            self.adve()
+        if sedi and self.nz:
+            self.z = self.z - self.dt * self.vt
+        self.bcnd()
+        keep = self.n != 0                               # hskpng_remove_n0: hskpng_remove.ipp:20-75
+        for name in ("n", "rd3", "rw2", "kpa", "vt", "x", "y", "z"):
+            a = getattr(self, name)
+            if a.size:
+                setattr(self, name, a[keep])
+        self.n_part = int(keep.sum())
+        ii = (self.x / self.dx).astype(np.int64) if self.nx else 0      # hskpng_ijk.ipp:159-200
+        jj = (self.y / self.dy).astype(np.int64) if self.ny else 0
+        kk = (self.z / self.dz).astype(np.int64) if self.nz else 0
+        self.ijk = ((ii * max(1, self.ny) + jj) * max(1, self.nz) + kk) * np.ones(self.n_part, dtype=np.int64)
+        self.sort(False)
+        return n_coll

@@ -1,0 +1,126 @@
+"""CPU-only checks of the drop-in boundary: the shared libraries load without a GPU, export every symbol the headers
+declare, refuse to run without a device (no CPU fallback), and reproduce the reference's error behaviour for API misuse."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from libcloudphxx_b200 import engine as E
+from libcloudphxx_b200 import lgrngn as L
+from tests import support as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions(header):
+    text = open(header).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:lcx|lgc|lgrngn_b200)_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_engine_abi_exports_every_declared_symbol():
+    lib = E.lib()
+    names = declared_functions(os.path.join(ROOT, "include", "lcx_b200.h"))
+    assert len(names) > 40
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert b"sm_100a" in lib.lcx_version()
+
+
+def test_host_library_exports_binding_and_extras():
+    lib = L.b200().lib
+    for header in ("libcloudphxx_b200/bindings/lgrngn_capi.h", "libcloudphxx_b200/host/particles_b200.h"):
+        names = declared_functions(os.path.join(ROOT, header))
+        assert names
+        missing = [n for n in names if not hasattr(lib, n)]
+        assert not missing, (header, missing)
+
+
+def gpu_present():
+    return E.lib().lcx_device_count() > 0
+
+
+@pytest.mark.skipif("gpu_present()")
+def test_no_cpu_fallback():
+    """without a CUDA device the product refuses to run instead of silently computing on the host"""
+    lib = L.b200()
+    oi, o, f = S.box_golovin(lib, n_sd=64)
+    p = lib.factory(L.backend_t.CUDA, oi)
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        p.init(f["th"], f["rv"], f["rhod"])
+
+
+def test_cpu_backends_are_not_part_of_the_product():
+    lib = L.b200()
+    oi, _, _ = S.box_golovin(lib, n_sd=64)
+    for backend, name in ((L.backend_t.serial, "serial"), (L.backend_t.OpenMP, "OpenMP")):
+        with pytest.raises(RuntimeError, match="%s backend was not compiled" % name):
+            lib.factory(backend, oi)
+    with pytest.raises(RuntimeError, match="unknown backend"):
+        lib.factory(L.backend_t.undefined, oi)
+
+
+@pytest.mark.parametrize("field,value,message", [
+    ("chem_switch", 1, "chemistry"), ("ice_switch", 1, "ice"), ("turb_coal_switch", 1, "turbulence"),
+    ("sd_const_multi", 10, "sd_conc initialisation"), ("exact_sstp_cond", 1, None)])
+def test_out_of_scope_options_are_refused_loudly(field, value, message):
+    lib = L.b200()
+    oi, _, _ = S.box_golovin(lib, n_sd=64)
+    setattr(oi, field, value)
+    if field == "exact_sstp_cond":
+        oi.sstp_cond = 4
+        message = "per-particle condensation sub-stepping"
+    if field == "sd_const_multi":
+        oi.sd_conc = 0
+    with pytest.raises(RuntimeError, match=message):
+        lib.factory(L.backend_t.CUDA, oi)
+
+
+def test_call_order_and_argument_errors_match_the_reference(ref):
+    """same std::runtime_error texts as the reference (src/particles_step.ipp:44-47,169-170,343-344; init_sanity_check.ipp)"""
+    new = L.b200()
+
+    def messages(lib, backend):
+        out = []
+        oi, o, f = S.box_golovin(lib, n_sd=64)
+        p = lib.factory(backend, oi)
+        for call in (lambda: p.step_sync(o, f["th"], f["rv"], f["rhod"]),        # before init
+                     lambda: p.init(None, f["rv"], f["rhod"]),                    # th missing
+                     ):
+            try:
+                call()
+                out.append(None)
+            except RuntimeError as ex:
+                out.append(str(ex))
+        return out
+    a = messages(ref, L.backend_t.serial)
+    b = messages(new, L.backend_t.CUDA)
+    assert a == b and all(a), (a, b)
+
+    # kernel parameter validation happens before any device work
+    oi, o, f = S.box_golovin(new, n_sd=64)
+    oi.kernel_parameters = []
+    p = new.factory(L.backend_t.CUDA, oi)
+    with pytest.raises(RuntimeError, match="Golovin kernel accepts exactly one parameter"):
+        p.init(f["th"], f["rv"], f["rhod"])
+    oi, o, f = S.box_golovin(new, n_sd=64)
+    oi.dt = 0
+    p = new.factory(L.backend_t.CUDA, oi)
+    with pytest.raises(RuntimeError, match="please specify opts_init.dt"):
+        p.init(f["th"], f["rv"], f["rhod"])
+
+
+def test_multi_cuda_constructor_checks():
+    lib = L.b200()
+    oi, _, _ = S.box_golovin(lib, n_sd=64)
+    with pytest.raises(RuntimeError, match="multi_CUDA doesn't work for 0D setup"):
+        lib.factory(L.backend_t.multi_CUDA, oi)
+
+
+def test_efficiency_tables_are_shipped():
+    for name in ("hall", "hall_davis_no_waals", "vohl_davis_no_waals", "hall_pinsky_stratocumulus", "hall_pinsky_cumulonimbus", "hall_pinsky_1000mb_grav"):
+        t = np.fromfile(os.path.join(ROOT, "libcloudphxx_b200", "data", name + ".f64"))
+        assert t.size == 1 + 201 * 202 // 2 and t[0] == 1100.0
+        assert 0.0 <= t[1:].min() and t[1:].max() < 1e2

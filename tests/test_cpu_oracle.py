@@ -1,0 +1,157 @@
+"""Pins the oracle (no GPU needed).
+
+  1. oracle/_ref - the reference's own serial/OpenMP back-ends built from the unmodified sources - reproduces the fixtures the
+     reference's tests hold for this path: refdata/lgrngn_cond_substepping_refdata.csv (per-cell rows, tolerances of
+     lgrngn_cond_substepping_test.py:79-91), the Bott array of coalescence_hall_davis_no_waals.py:82 (RMSD < 6e-2),
+     the known-answer p_vs(273.16 K) = 611.73 Pa (tests/common/test_common_pvs.cpp:7), mass conservation of test_coal.py.
+  2. oracle/sdm_port.py - the numpy restatement - agrees with oracle/_ref bit for bit on the same seeded inputs, and with
+     the committed golden vectors made from it (tools/make_golden.py), so it stays pinned where the reference is absent.
+"""
+import importlib.util
+import math
+import os
+
+import numpy as np
+import pytest
+
+from libcloudphxx_b200 import lgrngn as L
+from tests import support as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def load_port():
+    spec = importlib.util.spec_from_file_location("sdm_port", os.path.join(ROOT, "oracle", "sdm_port.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+port = load_port()
+
+
+def test_known_answer_saturation_pressure():
+    assert port.p_vs_cc(273.16) == 611.73
+
+
+def test_host_random_stream_is_libstdcxx_mt19937():
+    """10000th draw of std::mt19937 (default seed 5489) is 4123659995 by the C++ standard [rand.predef]"""
+    rng = port.HostRNG(5489)
+    assert int(rng.raw(10000)[-1]) == 4123659995
+
+
+@pytest.mark.parametrize("sstp_cond", [1, 2, 3, 4, 6, 8, 32])
+@pytest.mark.parametrize("rhf", [L.RH_formula_t.pv_cc, L.RH_formula_t.rv_tet])
+def test_reference_build_reproduces_cond_fixture(ref, sstp_cond, rhf):
+    names = {0: "pv_cc", 1: "rv_cc", 2: "pv_tet", 3: "rv_tet"}
+    rows = [r for r in S.load_cond_substepping_rows() if r["constp"] == "False" and r["RH_formula"] == names[rhf] and int(r["sstp_cond"]) == sstp_cond]
+    assert len(rows) == 1
+    res = S.cond_substepping_scenario(ref, L.backend_t.OpenMP, rhf, sstp_cond, False)
+    assert not S.check_cond_substepping(res, rows[0]), S.check_cond_substepping(res, rows[0])
+
+
+def test_reference_build_reproduces_cond_fixture_const_p(ref):
+    rows = [r for r in S.load_cond_substepping_rows() if r["constp"] == "True" and r["RH_formula"] == "pv_cc" and int(r["sstp_cond"]) == 4]
+    res = S.cond_substepping_scenario(ref, L.backend_t.OpenMP, L.RH_formula_t.pv_cc, 4, True)
+    assert not S.check_cond_substepping(res, rows[0]), S.check_cond_substepping(res, rows[0])
+
+
+def test_reference_build_reproduces_bott_spectrum(ref):
+    bott = np.load(os.path.join(ROOT, "tests", "golden", "bott1800.npy"))
+    oi, o, f = S.hall_davis_box(ref, L.vt_t.beard77fast)
+    p = ref.factory(L.backend_t.OpenMP, oi)
+    p.init(f["th"], f["rv"], f["rhod"])
+    p.step_sync(o, f["th"], f["rv"], f["rhod"])
+    p.step_async(o)
+    assert S.rmsd(S.mass_density_spectrum(p) * 1000, bott) < 6e-2
+
+
+def make_port(case, **kw):
+    if case == "golovin":
+        n_sd = kw["n_sd"]
+        r0, n0 = 30.084e-6, 2.0 ** 23
+        fun = lambda lnr: n0 * 3. * (math.exp(lnr) / r0) ** 3 * math.exp(-(math.exp(lnr) / r0) ** 3)
+        return port.Particles(dt=1., sd_conc=n_sd, n_sd_max=n_sd, kernel="golovin", kernel_params={"b": 1500.}, dry_distros=[(1e-10, fun)])
+    raise ValueError(case)
+
+
+def expvol_as_capi(lnr, r0=30.084e-6, n0=2.0 ** 23):
+    # same arithmetic as the binding's functor (bindings/lgrngn_capi.cpp: expvolume::funval)
+    r = math.exp(lnr)
+    q = r / r0
+    q3 = q * q * q
+    return n0 * 3. * q3 * math.exp(-q3)
+
+
+def lognormal_as_capi(modes):
+    def f(lnr):
+        res = 0.0
+        for mean_r, stdev, n_tot in modes:
+            lns, d = math.log(stdev), lnr - math.log(mean_r)
+            res += n_tot * math.exp(-(d * d) / 2. / (lns * lns)) / lns / math.sqrt(2 * math.pi)
+        return res
+    return f
+
+
+def test_port_matches_reference_golovin_box_exactly(ref):
+    n_sd = 512
+    oi, o, f = S.box_golovin(ref, n_sd=n_sd)
+    p_r = ref.factory(L.backend_t.serial, oi)
+    p_r.init(f["th"], f["rv"], f["rhod"])
+    p_p = port.Particles(dt=1., sd_conc=n_sd, n_sd_max=n_sd, kernel="golovin", kernel_params={"b": 1500.}, dry_distros=[(1e-10, expvol_as_capi)],
+                         sedi_switch=False)
+    p_p.init(f["th"], f["rv"], f["rhod"])
+    assert np.array_equal(p_r.get_n(), p_p.n) and np.array_equal(p_r.get_attr("rd3"), p_p.rd3) and np.array_equal(p_r.get_attr("rw2"), p_p.rw2)
+    collided = 0
+    for step in range(25):
+        p_r.step_sync(o, f["th"], f["rv"], f["rhod"]); p_r.step_async(o)
+        p_p.step_sync(f["th"], f["rv"], f["rhod"], cond=False)
+        collided += p_p.step_async(adve=False, sedi=False, coal=True, cond=False)
+        assert np.array_equal(p_r.get_n(), p_p.n), step
+        assert np.array_equal(p_r.get_attr("rd3"), p_p.rd3), step
+        assert np.array_equal(p_r.get_attr("rw2"), p_p.rw2), step
+    assert collided > 0
+
+
+def test_port_matches_golden_golovin_box():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_golovin_box.npz"))
+    n_sd = 2 ** 10
+    p = port.Particles(dt=1., sd_conc=n_sd, n_sd_max=n_sd, kernel="golovin", kernel_params={"b": 1500.}, dry_distros=[(1e-10, expvol_as_capi)])
+    th, rv, rhod = np.array([300.]), np.array([0.01]), np.array([1.])
+    p.init(th, rv, rhod)
+    assert np.array_equal(g["g_n_0"], p.n) and np.array_equal(g["g_rw2_0"], p.rw2)
+    for step in range(1, 13):
+        p.step_sync(th, rv, rhod, cond=False)
+        p.step_async(adve=False, sedi=False, coal=True, cond=False)
+        assert np.array_equal(g["g_n_%d" % step], p.n), step
+        assert np.array_equal(g["g_rd3_%d" % step], p.rd3) and np.array_equal(g["g_rw2_%d" % step], p.rw2), step
+
+
+def port_box3d(f, nx, ny, nz, sd_conc, eff):
+    return port.Particles(nx=nx, ny=ny, nz=nz, dx=20., dy=20., dz=20., dt=1., x1=nx * 20., y1=ny * 20., z1=nz * 20., sd_conc=sd_conc,
+                          n_sd_max=int(nx * ny * nz * sd_conc * 1.5), kernel="efficiencies", kernel_params={"eff": eff[1:], "r_max": eff[0]},
+                          dry_distros=[(0.61, lognormal_as_capi(S.AEROSOL_ICICLE)), (1.28, lognormal_as_capi([(30e-6, 1.2, 1e5)]))])
+
+
+def test_port_matches_reference_full_step_3d(ref):
+    """cond + coal + sedi + adve in a 3-D box: the restatement follows the reference to the last bit"""
+    nx, ny, nz, sd_conc = 3, 2, 4, 8
+    eff = np.fromfile(os.path.join(ROOT, "libcloudphxx_b200", "data", "hall_davis_no_waals.f64"))
+    oi, o, f = S.box_3d(ref, nx=nx, ny=ny, nz=nz, sd_conc=sd_conc, rain_mode=True)
+    p_r = ref.factory(L.backend_t.serial, oi)
+    p_r.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
+    fp = {k: v.copy() for k, v in f.items()}
+    p_p = port_box3d(fp, nx, ny, nz, sd_conc, eff)
+    p_p.init(fp["th"], fp["rv"], fp["rhod"], fp["Cx"], fp["Cy"], fp["Cz"])
+    for k, a in (("rd3", p_p.rd3), ("rw2", p_p.rw2), ("x", p_p.x), ("y", p_p.y), ("z", p_p.z)):
+        assert np.array_equal(p_r.get_attr(k), a), k
+    assert np.array_equal(p_r.get_n(), p_p.n)
+    for step in range(3):
+        p_r.step_sync(o, f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"]); p_r.step_async(o)
+        th, rv = p_p.step_sync(fp["th"], fp["rv"], fp["rhod"])
+        fp["th"][:], fp["rv"][:] = th.reshape(fp["th"].shape), rv.reshape(fp["rv"].shape)
+        p_p.step_async()
+        assert np.array_equal(p_r.get_n(), p_p.n), step
+        for k, a in (("rd3", p_p.rd3), ("rw2", p_p.rw2), ("x", p_p.x), ("y", p_p.y), ("z", p_p.z)):
+            assert np.array_equal(p_r.get_attr(k), a), (k, step, S.rel_err(p_r.get_attr(k), a))
+        assert np.array_equal(f["th"], fp["th"]) and np.array_equal(f["rv"], fp["rv"]), step
