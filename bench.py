@@ -32,10 +32,17 @@ sys.path.insert(0, ROOT)
 
 A_FULL_BYTES = 192.0          # algorithmic bytes per SD-update, full step, double
 KERNEL_BYTES = {              # algorithmic bytes per SD per launch of the individual kernels
+    "k_cond_cells": 48.0,      # rw2 r+w, rd3, kpa, vt, n (8 B each); the cell fields are 1/40 of that
     "k_cond": 52.0, "k_coal_small": 76.0, "k_coal_big": 76.0, "k_transport": 64.0, "k_gather": 136.0,
     "k_radix_scatter": 16.0, "k_radix_hist": 4.0, "(k_cell_reduce_small<Term, IS_MAX>)": 20.0,
     "k_vterm": 24.0, "k_make_keys": 40.0,
 }
+
+
+def kernel_bytes(name):
+    """profile names carry template arguments and parentheses (e.g. "(k_cond_cells<false>)"): longest key contained in the name"""
+    hits = [k for k in KERNEL_BYTES if k.strip("()").split("<")[0] in name]
+    return KERNEL_BYTES[max(hits, key=len)] if hits else 0.0
 
 
 def peaks():
@@ -259,7 +266,7 @@ def run_b200(args):
             prof_table = {k: {"launches": n, "ms": round(ms_, 3), "share": round(ms_ / tot, 4)} for k, (n, ms_) in sorted(rep.items(), key=lambda kv: -kv[1][1])}
             top = max(rep.items(), key=lambda kv: kv[1][1])
             name, (n_l, t_ms) = top
-            per_sd = KERNEL_BYTES.get(name, 0.0)
+            per_sd = kernel_bytes(name)
             peak, src = peaks()
             achieved = per_sd * n_live / (t_ms / n_l * 1e-3) / 1e9 if per_sd else None
             roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "peak_source": src, "unit": "GB/s",

@@ -121,6 +121,9 @@ int  lcx_set_efficiencies(lcx_engine *e, const void *table, int64_t n);     /* i
 int  lcx_sd_append(lcx_engine *e, int64_t count, const uint64_t *n, const void *rd3, const void *rw2,
                    const void *kpa, const void *x, const void *y, const void *z, const uint32_t *ijk);
 int  lcx_n_part(lcx_engine *e, int64_t *n_part);
+/* always != 0 (default): storage indices are re-numbered after every removal, as injected random streams and          */
+/* lcx_get_attr need; 0: the re-numbering is postponed until something needs it (enough for the Philox stream)         */
+int  lcx_set_dense_storage_index(lcx_engine *e, int always);
 /* copy one attribute to the host in reference storage order (sid); n is converted to real           */
 int  lcx_get_attr(lcx_engine *e, int attr, void *dst, int64_t cap, int64_t *n_out);   /* fill_outbuf.ipp:40-79 */
 int  lcx_get_attr_u64(lcx_engine *e, int attr, uint64_t *dst, int64_t cap, int64_t *n_out);

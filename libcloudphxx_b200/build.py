@@ -63,6 +63,8 @@ def build_engine(force=False, verbose=True, extra=()):
         flags = list(NVCC_FLAGS)
         if src in FMAD_OK and os.environ.get("LCX_COND_FMAD", "0") == "1":
             flags[flags.index("-fmad=false")] = "-fmad=true"
+        if src == "lcx_cond.cu":
+            flags += [f for f in os.environ.get("LCX_COND_DEFS", "").split() if f]
         out = _run([NVCC] + flags + list(extra) + ["-c", s, "-o", o])
         return src, time.time() - t0, out
 

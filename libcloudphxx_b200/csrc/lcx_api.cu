@@ -81,7 +81,7 @@ lcx_engine::~lcx_engine()
   drw_mom3.release(); rw_mom3.release(); count_mom.release(); mom_partial.release();
   courant_x.release(); courant_y.release(); courant_z.release(); w_LS.release(); cell_off.release();
   vt0.release(); eff.release(); hist.release(); scan_tmp.release();
-  for (int s = 0; s < 2; ++s) { for (int d = 0; d < 2; ++d) { mig_n[s][d].release(); mig_real[s][d].release(); } mig_ids[s].release(); }
+  for (int s = 0; s < 2; ++s) { for (int d = 0; d < 2; ++d) { mig_n[s][d].release(); mig_real[s][d].release(); } mig_key[s].release(); mig_val[s].release(); }
   scalars.release(); red_partial.release();
   for (auto &r : prof) { cudaEventDestroy(r.t0); cudaEventDestroy(r.t1); }
   if (timer0) { cudaEventDestroy(timer0); cudaEventDestroy(timer1); }
@@ -174,6 +174,7 @@ int lcx_create(const lcx_config *cfg, lcx_engine **out)
       const int n_real = 4 + (g.nx ? 1 : 0) + (g.ny ? 1 : 0) + (g.nz ? 1 : 0);
       for (int s = 0; s < 2; ++s)
         for (int d = 0; d < 2; ++d) { e->mig_n[s][d].alloc(e->mig_cap); e->mig_real[s][d].alloc(e->mig_cap * n_real); }
+      for (int s = 0; s < 2; ++s) { e->mig_key[s].alloc(e->mig_cap); e->mig_val[s].alloc(e->mig_cap); }
     }
 
     e->scalars.alloc(1);
@@ -246,6 +247,7 @@ int lcx_sd_append(lcx_engine *e, int64_t count, const uint64_t *n, const void *r
     using namespace lcx;
     use_device(e);
     if (count <= 0) return;
+    lcx::densify_sid(e);
     const size_t first = e->n_part, cnt = size_t(count);
     if (first + cnt > e->cap) throw error("n_sd_max (" + std::to_string(e->cap) + ") < n_part (" + std::to_string(first + cnt) + ")");
     sd_arrays &s = e->S();
@@ -263,9 +265,14 @@ int lcx_sd_append(lcx_engine *e, int64_t count, const uint64_t *n, const void *r
     LCX_CUDA(cudaGetLastError()); ++e->launches;
     LCX_CUDA(cudaStreamSynchronize(e->stream));
     e->n_part = first + cnt;
+    e->sid_hi = e->n_part;
     e->grouped = false;
+    e->keys_ready = 0;
   });
 }
+
+int lcx_set_dense_storage_index(lcx_engine *e, int always)
+{ return guarded([&] { use_device(e); e->dense_always = always != 0; if (e->dense_always) lcx::densify_sid(e); }); }
 
 int lcx_n_part(lcx_engine *e, int64_t *n_part) { *n_part = int64_t(e->n_part); return 0; }
 

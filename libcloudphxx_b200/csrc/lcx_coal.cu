@@ -7,8 +7,8 @@
 // The reference's candidate pairs are (2k, 2k+1) of each cell's SDs ordered by (random key un, storage index).
 // SDs are physically grouped by cell here, so that order is a per-cell sort of the composite key
 // (un[sid] << 32 | sid), which is unique - no dependence on the physical order inside the cell:
-//   * small cells (max population <= 256): one warp per cell; keys staged in shared memory, rank of each SD by
-//     counting smaller keys (O(m^2/32) per lane, m ~ 40), pairs processed by the lanes;
+//   * small cells (max population <= 256): 16 lanes per cell (two cells per warp); keys staged in shared memory, rank
+//     of each SD by counting smaller keys (O(m^2/16) per lane, m ~ 40), pairs processed by the lanes;
 //   * big cells (0-D boxes, coarse grids): global LSD radix sort by sid, un, cell (lcx_sort.cu), then one thread
 //     per candidate pair.
 // Random numbers come from an injected stream (parity with the reference's mt19937 draw order: un by storage
@@ -20,8 +20,9 @@ namespace lcx
   namespace
   {
     constexpr int TPB = 256;
-    constexpr int WARPS = TPB / 32;
-    constexpr unsigned SMALL_MAX = 256;      // largest cell population handled by the warp-per-cell kernel
+    constexpr int CELL_LANES = 16;           // lanes that share one cell in k_coal_small (two cells per warp)
+    constexpr int GROUPS = TPB / CELL_LANES;
+    constexpr unsigned SMALL_MAX = 256;      // largest cell population handled by k_coal_small
 
     // ---- Philox4x32-10 (Salmon, Moraes, Dror & Shaw, SC'11) --------------------------------------------
     struct philox_key { uint32_t k0, k1; };
@@ -103,7 +104,8 @@ namespace lcx
     }
 
     // one candidate pair: a = physical index of the SD at even in-cell position, b = the next one: coal.ipp:181-268
-    __device__ __forceinline__ void try_pair(const coal_ctx &cx, uint32_t a, uint32_t b, real_t u01, real_t scl, real_t dv_c)
+    __device__ __forceinline__ void try_pair(const coal_ctx &cx, uint32_t a, uint32_t b, real_t u01, real_t scl, real_t dv_c,
+                                            unsigned long long &n_coll, unsigned long long &n_pairs)
     {
       const n_t n_a = cx.n[a], n_b = cx.n[b];
       const real_t rw2_a = cx.rw2[a], rw2_b = cx.rw2[b];
@@ -124,40 +126,60 @@ namespace lcx
         if (n_a > 0) col_no = tmin(col_no, n_t(n_b / n_a));
         collide(cx, b, a, n_b, n_a, rw2_b, rw2_a, rd3_b, rd3_a, col_no);
       }
-      atomicAdd(&cx.sc->n_collisions, (unsigned long long)col_no);
-      atomicAdd(&cx.sc->n_pairs_collided, 1ull);
+      n_coll += col_no;
+      n_pairs += 1;
     }
 
-    // ---- small cells: warp per cell ---------------------------------------------------------------------
+    // collision statistics: one pair of atomics per warp that saw a collision
+    __device__ __forceinline__ void flush_stats(const coal_ctx &cx, unsigned long long n_coll, unsigned long long n_pairs)
+    {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+      {
+        n_coll += __shfl_xor_sync(0xffffffffu, n_coll, o);
+        n_pairs += __shfl_xor_sync(0xffffffffu, n_pairs, o);
+      }
+      if ((threadIdx.x & 31) == 0 && n_pairs)
+      {
+        atomicAdd(&cx.sc->n_collisions, n_coll);
+        atomicAdd(&cx.sc->n_pairs_collided, n_pairs);
+      }
+    }
+
+    // ---- small cells: 16 lanes per cell -------------------------------------------------------------------
     __global__ void __launch_bounds__(TPB) k_coal_small(idx_t n_cell, const uint32_t *__restrict__ off, const idx_t *__restrict__ sid,
                                                        rng_src rng, coal_ctx cx)
     {
-      __shared__ unsigned long long skey[WARPS][SMALL_MAX];
-      __shared__ unsigned short sperm[WARPS][SMALL_MAX];
-      const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-      const idx_t c = blockIdx.x * WARPS + w;
-      if (c >= n_cell) return;
-      const uint32_t b = off[c];
-      const uint32_t m = off[c + 1] - b;
-      if (m < 2) return;
-      for (uint32_t e = lane; e < m; e += 32)
+      __shared__ unsigned long long skey[GROUPS][SMALL_MAX];
+      __shared__ unsigned short sperm[GROUPS][SMALL_MAX];
+      const int grp = threadIdx.x / CELL_LANES, l = threadIdx.x % CELL_LANES;
+      const idx_t c = blockIdx.x * GROUPS + grp;
+      uint32_t b = 0, m = 0;
+      if (c < n_cell) { b = off[c]; m = off[c + 1] - b; }
+      if (m < 2) m = 0;                                    // nothing to pair; keep the lanes for the warp-wide syncs
+      for (uint32_t e = l; e < m; e += CELL_LANES)
       {
         const uint32_t s = sid[b + e];
-        skey[w][e] = ((unsigned long long)rng.get_un(s) << 32) | s;
+        skey[grp][e] = ((unsigned long long)rng.get_un(s) << 32) | s;
       }
       __syncwarp();
-      for (uint32_t e = lane; e < m; e += 32)
+      for (uint32_t e = l; e < m; e += CELL_LANES)
       {
-        const unsigned long long mine = skey[w][e];
+        const unsigned long long mine = skey[grp][e];
         uint32_t r = 0;
-        for (uint32_t j = 0; j < m; ++j) r += (skey[w][j] < mine);
-        sperm[w][r] = (unsigned short)e;
+        for (uint32_t j = 0; j < m; ++j) r += (skey[grp][j] < mine);
+        sperm[grp][r] = (unsigned short)e;
       }
       __syncwarp();
-      const real_t scl = coal_scale_factor<real_t>(n_t(m));
-      const real_t dv_c = cx.dv[c];
-      for (uint32_t k = lane; 2 * k + 1 < m; k += 32)
-        try_pair(cx, b + sperm[w][2 * k], b + sperm[w][2 * k + 1], rng.get_u01(b + 2 * k), scl, dv_c);
+      unsigned long long n_coll = 0, n_pairs = 0;
+      if (m)
+      {
+        const real_t scl = coal_scale_factor<real_t>(n_t(m));
+        const real_t dv_c = cx.dv[c];
+        for (uint32_t k = l; 2 * k + 1 < m; k += CELL_LANES)
+          try_pair(cx, b + sperm[grp][2 * k], b + sperm[grp][2 * k + 1], rng.get_u01(b + 2 * k), scl, dv_c, n_coll, n_pairs);
+      }
+      flush_stats(cx, n_coll, n_pairs);
     }
 
     // ---- big cells: global sort, then thread per pair ----------------------------------------------------
@@ -185,7 +207,13 @@ namespace lcx
       const uint32_t b = off[c], en = off[c + 1];
       if (((pos - b) & 1u) != 0u) return;     // only every second SD of a cell starts a pair
       if (pos + 1 >= en) return;              // the last SD of an odd-sized cell stays unpaired
-      try_pair(cx, perm[pos], perm[pos + 1], rng.get_u01(uint32_t(pos)), coal_scale_factor<real_t>(n_t(en - b)), cx.dv[c]);
+      unsigned long long n_coll = 0, n_pairs = 0;
+      try_pair(cx, perm[pos], perm[pos + 1], rng.get_u01(uint32_t(pos)), coal_scale_factor<real_t>(n_t(en - b)), cx.dv[c], n_coll, n_pairs);
+      if (n_pairs)
+      {
+        atomicAdd(&cx.sc->n_collisions, n_coll);
+        atomicAdd(&cx.sc->n_pairs_collided, n_pairs);
+      }
     }
 
     int bit_length(uint64_t v) { int b = 0; while (v) { ++b; v >>= 1; } return b; }
@@ -204,6 +232,7 @@ namespace lcx
     if (r->mode == LCX_RNG_INJECT)
     {
       if (!r->un || !r->u01) throw error("lcx_coal: injected random streams are missing");
+      densify_sid(e);      // un[] is indexed by the dense storage index
       LCX_CUDA(cudaMemcpyAsync(e->un.p, r->un, n * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
       LCX_CUDA(cudaMemcpyAsync(e->u01.p, r->u01, n * sizeof(real_t), cudaMemcpyHostToDevice, e->stream));
       rng.un = e->un.p; rng.u01 = e->u01.p;
@@ -224,14 +253,14 @@ namespace lcx
 
     if (e->max_count <= SMALL_MAX)
     {
-      LCX_LAUNCH(e, k_coal_small, div_up(g.n_cell, WARPS), TPB, 0, g.n_cell, e->cell_off.p, s.sid.p, rng, cx);
+      LCX_LAUNCH(e, k_coal_small, div_up(g.n_cell, GROUPS), TPB, 0, g.n_cell, e->cell_off.p, s.sid.p, rng, cx);
       return;
     }
 
     // global path: stable LSD sort by storage index, then random key, then cell
     int in = 0;
     LCX_LAUNCH(e, k_fill_sid_keys, div_up(n, TPB), TPB, 0, n, s.sid.p, e->key[in].p, e->val[in].p);
-    in = radix_sort_pairs(e, n, 0, bit_length(e->sid_dense ? n - 1 : 0xffffffffull), in);
+    in = radix_sort_pairs(e, n, 0, bit_length(e->sid_hi ? e->sid_hi - 1 : 0), in);
     LCX_LAUNCH(e, k_keys_from_un, div_up(n, TPB), TPB, 0, n, s.sid.p, e->val[in].p, rng, e->key[in].p);
     in = radix_sort_pairs(e, n, 0, 32, in);
     if (g.n_cell > 1)

@@ -15,6 +15,9 @@
 // The root solve is FP64-compute bound (~4.6 growth-rate evaluations per SD); the growth law is therefore evaluated
 // in the single-quotient form of lcx_physics.h (growth_fast) by default; LCX_COND_EXACT=1 selects the operation-by-
 // operation transcription of the reference's formula (growth_fn) for cross-checking.
+#ifndef LCX_NO_FAST_DIV
+#define LCX_FAST_DIV 1      // see lcx_physics.h: quotients inside the root solve need not be correctly rounded
+#endif
 #include "lcx_engine.cuh"
 
 #include <cstdlib>
@@ -24,7 +27,10 @@ namespace lcx
   namespace
   {
     constexpr int TPB = 128;
-    constexpr int GROUP = 8;                 // lanes per cell in k_cond_cells
+#ifndef LCX_COND_MINB
+#define LCX_COND_MINB 8                      // 8 CTAs of 4 warps per SM (64 registers): measured best of {4,5,6,8}
+#endif
+    constexpr int GROUP = 8;                 // lanes per cell in k_cond_cells (4 and 16 measured slower)
     constexpr unsigned FUSED_MAX = 2048;     // largest cell population for the fused kernel
 
     struct cond_args
@@ -55,8 +61,13 @@ namespace lcx
     }
 
     // group of 8 lanes per cell: growth + 3rd-moment change + th/rv update
+    // Not fused here although it looks tempting: the hskpng_Tpr + hskpng_vterm_all that open step_async.  Measured as an
+    // epilogue of the last sub-step it cost 0.86 ms against 0.27 ms for the separate full-occupancy k_vterm (16 M SDs).
+    // Lanes of a group stay in lock-step droplet by droplet on purpose: all root solves of a warp are then in the same
+    // phase of TOMS 748 and share its (division-heavy) interpolation code; letting early finishers start their next
+    // droplet at once (persistent-lane variant, measured) desynchronises the phases and is 35 % slower.
     template <bool EXACT>
-    __global__ void __launch_bounds__(TPB) k_cond_cells(idx_t n_cell, const uint32_t *__restrict__ off, real_t dt, real_t RH_max, cond_args a,
+    __global__ void __launch_bounds__(TPB, LCX_COND_MINB) k_cond_cells(idx_t n_cell, const uint32_t *__restrict__ off, real_t dt, real_t RH_max, cond_args a,
                                                        int n_dims, const real_t *__restrict__ dv, int first_step, int keep_after,
                                                        real_t *__restrict__ rw_mom3, real_t *__restrict__ drw_mom3,
                                                        real_t *__restrict__ th, real_t *__restrict__ rv)

@@ -99,7 +99,12 @@ struct lcx_engine
   size_t n_tail = 0;             // SDs appended (migration) since the last post_copy, already counted in n_part
   unsigned max_count = 0;        // host copy of the largest cell population
   bool grouped = false;          // SD arrays physically grouped by cell, cell_off valid
+  // storage indices: every sid is < sid_hi; dense means {sid} = [0, n_part).  With injected random streams (and for
+  // get_attr) they must be dense, so removals are followed by a re-numbering; with Philox any unique, order-preserving
+  // index will do and the re-numbering is postponed until something needs it (dense_always = false)
+  size_t sid_hi = 0;
   bool sid_dense = true;
+  bool dense_always = true;
 
   lcx::sd_arrays sd[2];          // current / alternate (re-layout target)
   int cur = 0;
@@ -127,8 +132,9 @@ struct lcx_engine
   // migration buffers: [side][incoming]
   lcx::dbuf<lcx::n_t> mig_n[2][2];
   lcx::dbuf<lcx::real_t> mig_real[2][2];
-  lcx::dbuf<uint32_t> mig_ids[2];
+  lcx::dbuf<uint32_t> mig_key[2], mig_val[2];
   size_t mig_cap = 0;
+  size_t keys_ready = 0;         // key[0] / val[0] already hold the re-layout sort keys of SDs [0, keys_ready) (written by k_transport)
 
   lcx::dbuf<lcx::dev_scalars> scalars;
   lcx::dev_scalars *h_scalars = nullptr;   // pinned host mirror
@@ -156,11 +162,14 @@ namespace lcx
   // stable LSD radix sort of (key, value) pairs on bits [bit_lo, bit_hi); result ends in key[*out]/val[*out]
   // (ping-pong between the two buffers of e->key / e->val; `in` is the buffer that holds the input)
   int radix_sort_pairs(lcx_engine *e, size_t n, int bit_lo, int bit_hi, int in);
+  // the same on caller-supplied ping-pong buffers (migration lists keep the engine's key/val buffers untouched)
+  int radix_sort_pairs(lcx_engine *e, size_t n, int bit_lo, int bit_hi, uint32_t *const key[2], uint32_t *const val[2], int in);
 
   // ---- lcx_layout.cu ---------------------------------------------------------------------------------
   void compute_cell_offsets(lcx_engine *e, const uint32_t *sorted_keys, size_t n_total);
   void post_copy(lcx_engine *e, bool rcyc, bool keep_all);
   void scatter_attr_by_sid(lcx_engine *e, int attr, real_t *dst);
+  void densify_sid(lcx_engine *e);
 
   // ---- lcx_cells.cu ----------------------------------------------------------------------------------
   void hskpng_Tpr(lcx_engine *e);

@@ -19,11 +19,11 @@ namespace lcx
   {
     constexpr int TPB = 256;
 
-    __global__ void __launch_bounds__(TPB) k_make_keys(size_t n, grid_t g, const n_t *__restrict__ ns,
+    __global__ void __launch_bounds__(TPB) k_make_keys(size_t first, size_t n, grid_t g, const n_t *__restrict__ ns,
                                                       const real_t *__restrict__ xs, const real_t *__restrict__ ys, const real_t *__restrict__ zs,
                                                       uint32_t *__restrict__ key, uint32_t *__restrict__ val)
     {
-      const size_t t = size_t(blockIdx.x) * TPB + threadIdx.x;
+      const size_t t = first + size_t(blockIdx.x) * TPB + threadIdx.x;
       if (t >= n) return;
       uint32_t k = g.n_cell;   // dead
       if (ns[t] != 0)
@@ -140,7 +140,13 @@ namespace lcx
     if (keep_all)   // initial grouping: every SD stays, cells are the ones assigned at creation (init_ijk.ipp:36-52)
       LCX_LAUNCH(e, k_keys_from_ijk, div_up(n_old, TPB), TPB, 0, n_old, s.ijk.p, e->key[0].p, e->val[0].p);
     else
-      LCX_LAUNCH(e, k_make_keys, div_up(n_old, TPB), TPB, 0, n_old, g, s.n.p, s.x.p, s.y.p, s.z.p, e->key[0].p, e->val[0].p);
+    {
+      // k_transport already wrote the keys of the SDs it moved; only later arrivals (migration) are keyed here
+      const size_t first = e->keys_ready <= n_old ? e->keys_ready : 0;
+      if (first < n_old)
+        LCX_LAUNCH(e, k_make_keys, div_up(n_old - first, TPB), TPB, 0, first, n_old, g, s.n.p, s.x.p, s.y.p, s.z.p, e->key[0].p, e->val[0].p);
+    }
+    e->keys_ready = 0;
     const int res = radix_sort_pairs(e, n_old, 0, bit_length(g.n_cell), 0);
     compute_cell_offsets(e, e->key[res].p, n_old);
 
@@ -163,21 +169,37 @@ namespace lcx
     e->grouped = true;
     e->selected = false;
 
-    if (n_new < n_old && n_new)
+    if (n_new < n_old)
     {
-      // re-densify the storage index: new sid = rank of the old sid among survivors (stable compaction order)
-      sd_arrays &c = e->S();
-      LCX_CUDA(cudaMemsetAsync(e->flag.p, 0, n_old * sizeof(uint32_t), e->stream));
-      LCX_LAUNCH(e, k_mark_sid, div_up(n_new, TPB), TPB, 0, n_new, c.sid.p, e->flag.p);
-      exclusive_scan_u32(e, e->flag.p, n_old);
-      LCX_LAUNCH(e, k_remap_sid, div_up(n_new, TPB), TPB, 0, n_new, c.sid.p, e->flag.p);
+      e->sid_dense = false;
+      if (e->dense_always) densify_sid(e);
     }
+    if (n_new == 0) { e->sid_hi = 0; e->sid_dense = true; }
+  }
+
+  // new sid = rank of the old sid among the survivors (the order a stable compaction of the reference's storage gives)
+  void densify_sid(lcx_engine *e)
+  {
+    if (e->sid_dense) return;
+    const size_t n = e->n_part, space = e->sid_hi;
+    if (n)
+    {
+      if (space > e->flag.n) throw error("internal error: storage-index space exceeds the scratch buffer");
+      sd_arrays &c = e->S();
+      LCX_CUDA(cudaMemsetAsync(e->flag.p, 0, space * sizeof(uint32_t), e->stream));
+      LCX_LAUNCH(e, k_mark_sid, div_up(n, TPB), TPB, 0, n, c.sid.p, e->flag.p);
+      exclusive_scan_u32(e, e->flag.p, space);
+      LCX_LAUNCH(e, k_remap_sid, div_up(n, TPB), TPB, 0, n, c.sid.p, e->flag.p);
+    }
+    e->sid_hi = n;
+    e->sid_dense = true;
   }
 
   void scatter_attr_by_sid(lcx_engine *e, int attr, real_t *dst)
   {
     const size_t n = e->n_part;
     if (n == 0) return;
+    densify_sid(e);
     sd_arrays &s = e->S();
     if (attr == LCX_A_N)
       LCX_LAUNCH(e, (k_scatter_by_sid<n_t>), div_up(n, TPB), TPB, 0, n, s.sid.p, s.n.p, dst);

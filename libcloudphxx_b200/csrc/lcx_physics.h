@@ -31,6 +31,25 @@ namespace lcx
   enum { AS_UNDEFINED = 0, AS_IMPLICIT, AS_EULER, AS_PRED_CORR };
   enum { RH_PV_CC = 0, RH_RV_CC, RH_PV_TET, RH_RV_TET };
 
+  // Division inside the condensation root solve.  There every quotient is either the next trial abscissa or part of the
+  // residual whose root is wanted to 2^-15 only, so a correctly rounded result buys nothing: a translation unit may define
+  // LCX_FAST_DIV to get reciprocal-approximation + two Newton steps + one residual correction on the device (error <= 1 ulp,
+  // no special-case branch), about 1/3 of the instructions of the IEEE division sequence.  Everywhere else "/" is IEEE.
+#if defined(LCX_FAST_DIV) && defined(__CUDA_ARCH__)
+  __device__ __forceinline__ double lcx_div(double a, double b)
+  {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
+    r = fma(fma(-b, r, 1.0), r, r);
+    r = fma(fma(-b, r, 1.0), r, r);
+    const double q = a * r;
+    return fma(fma(-b, q, a), r, q);
+  }
+  __device__ __forceinline__ float lcx_div(float a, float b) { return a / b; }
+#else
+  template <class T> LCX_HD T lcx_div(T a, T b) { return a / b; }
+#endif
+
   template <class T> LCX_HD T tmin(T a, T b) { return (b < a) ? b : a; }   // std::min semantics
   template <class T> LCX_HD T tmax(T a, T b) { return (a < b) ? b : a; }   // std::max semantics (NaN in b is dropped)
 
@@ -188,7 +207,7 @@ namespace lcx
     LCX_HD T guarded_div(T num, T den, T fallback)
     {
       if (fabs(den) < 1 && fabs(den * fpl<T>::huge_()) <= fabs(num)) return fallback;
-      return num / den;
+      return lcx_div(num, den);
     }
 
     // shrink [a,b] around the sign change using the trial point c; the discarded end goes to (d,fd)
@@ -209,7 +228,7 @@ namespace lcx
     LCX_HD T secant(const T &a, const T &b, const T &fa, const T &fb)
     {
       const T tol = fpl<T>::eps() * 5;
-      const T c = a - (fa / (fb - fa)) * (b - a);
+      const T c = a - lcx_div(fa, fb - fa) * (b - a);
       if ((c <= a + fabs(a) * tol) || (c >= b - fabs(b) * tol)) return (a + b) / 2;
       return c;
     }
@@ -419,27 +438,30 @@ namespace lcx
   };
 
   // One implicit-Euler step of rw^2: control flow of advance_rw2::operator() (cond_common.ipp:187-337) with its
-  // TOMS 748 root solve (toms748 above) unrolled into a state machine that has ONE evaluation site of the growth
-  // law.  Same abscissae, same arithmetic, same result as calling toms748(f, a, b, fa, fb, tol, n_iter) - but on the
-  // GPU every lane of a warp evaluates f at its own trial point in lock-step whatever phase of the algorithm it is
-  // in, and the kernel stays small enough for the instruction cache (the straightforward inlining of toms748 puts
-  // ~6 copies of f into 100 KB of SASS and stalls on instruction fetch).
-  template <class F, class real_t>
-  LCX_HD real_t implicit_euler_rw2(const F &f, real_t rw2_old, real_t rd3, real_t dt, uintmax_t n_iter = 100, real_t cond_mlt = 2)
+  // TOMS 748 root solve (toms748 above) turned inside out into a resumable state machine: the caller evaluates the
+  // growth law at point() and hands the value to feed().  Same abscissae, same arithmetic, same result as calling
+  // toms748(f, a, b, fa, fb, tol, n_iter).  Why: on the GPU the growth law then has ONE evaluation site, so (i) the
+  // kernel fits the instruction cache (straightforward inlining of toms748 puts ~6 copies of f into 100 KB of SASS and
+  // stalls on instruction fetch) and (ii) a lane that finishes its droplet early can start the next one while its
+  // neighbours keep iterating - all lanes stay in the same loop body whatever phase or droplet they are at.
+  template <class real_t>
+  struct euler_rw2_solver
   {
-    using namespace root748;
     enum { INIT0, INIT1, FIRST, SECOND, LOOP1, LOOP2, LOOP3, LOOP4 };
-    const width_tol<real_t> tol(sizeof(real_t) * 8 / 4);
-    const real_t mu = 0.5f;
-    state<real_t> s;
-    s.a = s.b = s.fa = s.fb = s.d = s.fd = s.e = s.fe = 0;
-    real_t drw2 = 0, rd2 = 0, a0 = 0, b0 = 0, result = rw2_old;
-    uintmax_t left = n_iter;
-    int phase = INIT0;
-    real_t c = rw2_old;
-    bool bracketing = false;      // the pending evaluation is a rebracket() step: guard c first, update [a,b] afterwards
+    root748::state<real_t> s;
+    real_t rw2_old, dt, drw2, rd2, a0, b0, c;
+    unsigned left;
+    int phase;
+    bool bracketing;      // the pending evaluation is a rebracket() step: c was guarded, [a,b] is updated afterwards
 
-    for (;;)
+    LCX_HD void start(real_t rw2_old_, real_t dt_, unsigned n_iter = 100)
+    {
+      rw2_old = rw2_old_; dt = dt_; c = rw2_old_; left = n_iter; phase = INIT0; bracketing = false;
+      s.a = s.b = s.fa = s.fb = s.d = s.fd = s.e = s.fe = 0; drw2 = rd2 = a0 = b0 = 0;
+    }
+
+    // abscissa at which drw2/dt is wanted next
+    LCX_HD real_t point()
     {
       if (bracketing)
       {
@@ -448,7 +470,17 @@ namespace lcx
         else if (c <= s.a + fabs(s.a) * t2)      c = s.a + fabs(s.a) * t2;
         else if (c >= s.b - fabs(s.b) * t2)      c = s.b - fabs(s.a) * t2;
       }
-      const real_t g = f.drw2_dt(c);                         // the only evaluation site
+      return c;
+    }
+
+    LCX_HD real_t clamp(real_t r) const { return r < rd2 ? rd2 : r; }
+
+    // consumes g = drw2_dt(point()); returns true when the step is complete (result = new rw2)
+    LCX_HD bool feed(real_t g, real_t rd3, real_t &result, real_t cond_mlt = 2)
+    {
+      using namespace root748;
+      const width_tol<real_t> tol(sizeof(real_t) * 8 / 4);
+      const real_t mu = 0.5f;
       const real_t fc = (rw2_old + dt * g - c);
       if (bracketing)
       {
@@ -457,8 +489,6 @@ namespace lcx
         else                                         { s.d = s.a; s.fd = s.fa; s.a = c; s.fa = fc; }
       }
 
-      // what to do next: finish, or pick the next trial point by interpolation (one shared site for the quadratic /
-      // cubic formulae), or by the double-length secant / bisection rules
       bool finish = false, loop_head = false;
       int newton_steps = 0;          // > 0: interpolate (cubic when the four function values are distinct, else quadratic)
       bool quadratic_only = false;
@@ -467,26 +497,26 @@ namespace lcx
         case INIT0:
         {
           drw2 = dt * g;
-          if (drw2 == 0) return rw2_old;
+          if (drw2 == 0) { result = rw2_old; return true; }
           const real_t rd = cbrt(rd3);
           rd2 = rd * rd;
           s.a = tmax(rd2, rw2_old + tmin(real_t(0), cond_mlt * drw2));
           s.b = rw2_old + tmax(real_t(0), cond_mlt * drw2);
-          if (s.a == s.b) return rw2_old;
+          if (s.a == s.b) { result = rw2_old; return true; }
           c = (drw2 > 0) ? s.b : s.a;
           phase = INIT1;
-          continue;
+          return false;
         }
         case INIT1:
         {
           if (drw2 > 0) { s.fa = drw2; s.fb = fc; } else { s.fa = fc; s.fb = drw2; }
-          if (s.fa * s.fb > 0) { result = rw2_old + drw2; return result < rd2 ? rd2 : result; }   // not bracketed: explicit Euler
+          if (s.fa * s.fb > 0) { result = clamp(rw2_old + drw2); return true; }      // not bracketed: explicit Euler
           if (tol(s.a, s.b) || (s.fa == 0) || (s.fb == 0)) { finish = true; break; }
           s.fe = s.e = s.fd = 1e5F;
           c = secant(s.a, s.b, s.fa, s.fb);
           bracketing = true;
           phase = FIRST;
-          continue;
+          return false;
         }
         case FIRST:
           --left;
@@ -506,11 +536,11 @@ namespace lcx
           if ((0 == --left) || (s.fa == 0) || tol(s.a, s.b)) { finish = true; break; }
           real_t u, fu;
           if (fabs(s.fa) < fabs(s.fb)) { u = s.a; fu = s.fa; } else { u = s.b; fu = s.fb; }
-          c = u - 2 * (fu / (s.fb - s.fa)) * (s.b - s.a);
+          c = u - 2 * lcx_div(fu, s.fb - s.fa) * (s.b - s.a);
           if (fabs(c - u) > (s.b - s.a) / 2) c = s.a + (s.b - s.a) / 2;
           s.e = s.d; s.fe = s.fd;
           phase = LOOP3;
-          continue;
+          return false;
         }
         case LOOP3:
           if ((0 == --left) || (s.fa == 0) || tol(s.a, s.b)) { finish = true; break; }
@@ -518,7 +548,7 @@ namespace lcx
           s.e = s.d; s.fe = s.fd;
           c = real_t(s.a + (s.b - s.a) / 2);
           phase = LOOP4;
-          continue;
+          return false;
         case LOOP4:
           --left;
           loop_head = true;
@@ -530,38 +560,46 @@ namespace lcx
         if (left && (s.fa != 0) && !tol(s.a, s.b)) { a0 = s.a; b0 = s.b; newton_steps = 2; phase = LOOP1; }
         else finish = true;
       }
-      if (newton_steps)
-      {
-        bool have = false;
-        if (!quadratic_only && !values_coincide(s))
-        {
-          // inverse cubic interpolation; out-of-bracket results fall back to three Newton steps on the parabola
-          const real_t q11 = (s.d - s.e) * s.fd / (s.fe - s.fd);
-          const real_t q21 = (s.b - s.d) * s.fb / (s.fd - s.fb);
-          const real_t q31 = (s.a - s.b) * s.fa / (s.fb - s.fa);
-          const real_t d21 = (s.b - s.d) * s.fd / (s.fd - s.fb);
-          const real_t d31 = (s.a - s.b) * s.fb / (s.fb - s.fa);
-          const real_t q22 = (d21 - q11) * s.fb / (s.fe - s.fb);
-          const real_t q32 = (d31 - q21) * s.fa / (s.fd - s.fa);
-          const real_t d32 = (d31 - q21) * s.fd / (s.fd - s.fa);
-          const real_t q33 = (d32 - q22) * s.fa / (s.fe - s.fa);
-          c = q31 + q32 + q33 + s.a;
-          have = !((c <= s.a) || (c >= s.b));
-          if (!have) newton_steps = 3;
-        }
-        if (!have) c = quadratic(s.a, s.b, s.d, s.fa, s.fb, s.fd, unsigned(newton_steps));
-        // the point removed by the coming rebracket becomes (e,fe) - except after the second step of the loop body,
-        // where the reference does not refresh it (toms748.hpp:381-392)
-        if (phase != LOOP2) { s.e = s.d; s.fe = s.fd; }
-        continue;
-      }
       if (finish)
       {
         if (s.fa == 0) s.b = s.a; else if (s.fb == 0) s.a = s.b;
-        result = (s.a + s.b) / 2;
-        return result < rd2 ? rd2 : result;
+        result = clamp((s.a + s.b) / 2);
+        return true;
       }
+      // newton_steps > 0 here: next trial point by interpolation (one shared site for the cubic / quadratic formulae)
+      bool have = false;
+      if (!quadratic_only && !values_coincide(s))
+      {
+        // inverse cubic interpolation; out-of-bracket results fall back to three Newton steps on the parabola
+        const real_t q11 = lcx_div((s.d - s.e) * s.fd, s.fe - s.fd);
+        const real_t q21 = lcx_div((s.b - s.d) * s.fb, s.fd - s.fb);
+        const real_t q31 = lcx_div((s.a - s.b) * s.fa, s.fb - s.fa);
+        const real_t d21 = lcx_div((s.b - s.d) * s.fd, s.fd - s.fb);
+        const real_t d31 = lcx_div((s.a - s.b) * s.fb, s.fb - s.fa);
+        const real_t q22 = lcx_div((d21 - q11) * s.fb, s.fe - s.fb);
+        const real_t q32 = lcx_div((d31 - q21) * s.fa, s.fd - s.fa);
+        const real_t d32 = lcx_div((d31 - q21) * s.fd, s.fd - s.fa);
+        const real_t q33 = lcx_div((d32 - q22) * s.fa, s.fe - s.fa);
+        c = q31 + q32 + q33 + s.a;
+        have = !((c <= s.a) || (c >= s.b));
+        if (!have) newton_steps = 3;
+      }
+      if (!have) c = quadratic(s.a, s.b, s.d, s.fa, s.fb, s.fd, unsigned(newton_steps));
+      // the point removed by the coming rebracket becomes (e,fe) - except after the second step of the loop body,
+      // where the reference does not refresh it (toms748.hpp:381-392)
+      if (phase != LOOP2) { s.e = s.d; s.fe = s.fd; }
+      return false;
     }
+  };
+
+  template <class F, class real_t>
+  LCX_HD real_t implicit_euler_rw2(const F &f, real_t rw2_old, real_t rd3, real_t dt)
+  {
+    euler_rw2_solver<real_t> sv;
+    sv.start(rw2_old, dt);
+    real_t result = rw2_old;
+    for (;;)
+      if (sv.feed(f.drw2_dt(sv.point()), rd3, result)) return result;
   }
 
   template <class real_t>
@@ -662,7 +700,7 @@ namespace lcx
       const real_t tD = bDn * Sh, tK = bKn * Nu;
       const real_t num = (awd - awn * klv * k.inv_RH) * (tD * tK);
       const real_t den = awd * (k.X * bDd * tK + k.Y * bKd * tD);
-      return num / (cst<real_t>::rho_w() * den);
+      return lcx_div(num, cst<real_t>::rho_w() * den);
     }
     LCX_HD real_t operator()(const real_t &x) const { return (rw2_old + dt * drw2_dt(x) - x); }
   };

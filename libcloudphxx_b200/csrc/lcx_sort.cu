@@ -188,6 +188,12 @@ namespace lcx
 
   int radix_sort_pairs(lcx_engine *e, size_t n, int bit_lo, int bit_hi, int in)
   {
+    uint32_t *k[2] = {e->key[0].p, e->key[1].p}, *v[2] = {e->val[0].p, e->val[1].p};
+    return radix_sort_pairs(e, n, bit_lo, bit_hi, k, v, in);
+  }
+
+  int radix_sort_pairs(lcx_engine *e, size_t n, int bit_lo, int bit_hi, uint32_t *const key[2], uint32_t *const val[2], int in)
+  {
     if (n == 0) return in;
     const unsigned tiles = div_up(n, SORT_TILE);
     if (size_t(tiles) * RADIX > e->hist.n) throw error("radix_sort_pairs: histogram scratch too small");
@@ -196,9 +202,9 @@ namespace lcx
       const int bits = (bit_hi - shift) < 8 ? (bit_hi - shift) : 8;
       const uint32_t mask = (1u << bits) - 1u;
       const int out = in ^ 1;
-      LCX_LAUNCH(e, k_radix_hist, tiles, SORT_THREADS, 0, e->key[in].p, n, shift, mask, e->hist.p, tiles);
+      LCX_LAUNCH(e, k_radix_hist, tiles, SORT_THREADS, 0, key[in], n, shift, mask, e->hist.p, tiles);
       exclusive_scan_u32(e, e->hist.p, size_t(tiles) * RADIX);
-      LCX_LAUNCH(e, k_radix_scatter, tiles, SORT_THREADS, 0, e->key[in].p, e->val[in].p, e->key[out].p, e->val[out].p,
+      LCX_LAUNCH(e, k_radix_scatter, tiles, SORT_THREADS, 0, key[in], val[in], key[out], val[out],
                  n, shift, mask, e->hist.p, tiles);
       in = out;
     }

@@ -27,8 +27,25 @@ namespace lcx
       int open_side_walls, periodic_topbot, bcond_lft, bcond_rgt;
     };
 
+    // fmod(t, L) for t >= 0, L > 0 and a small quotient, without the library's iterative reduction.  fmod is exact in IEEE
+    // arithmetic (the remainder is always representable), and t - q L evaluated by ONE fma is exact whenever it is
+    // representable, i.e. as soon as q is the true integer quotient; a quotient off by one (rounding of t / L) is
+    // detected by the sign / size of the remainder and the fma is redone.  Bit-identical to fmod().
+    __device__ __forceinline__ real_t fmod_small_quotient(real_t t, real_t L)
+    {
+      real_t q = floor(t / L);
+      real_t r = fma(-q, L, t);
+      if (r < 0)       { q -= 1; r = fma(-q, L, t); }
+      else if (r >= L) { q += 1; r = fma(-q, L, t); }
+      return r;
+    }
     __device__ __forceinline__ real_t periodic_wrap(real_t x, real_t a, real_t b)   // bcnd.ipp:99-110
-    { return a + fmod((x - a) + 10 * (b - a), b - a); }
+    {
+      const real_t L = b - a, t = (x - a) + 10 * L;
+      // the reference assumes |displacement| < 10 domain lengths; outside that (or for NaN) fall back to the library
+      const real_t r = (t >= 0 && t < 64 * L) ? fmod_small_quotient(t, L) : fmod(t, L);
+      return a + r;
+    }
 
     __device__ __forceinline__ real_t step_impl(real_t x, idx_t i, real_t C_l, real_t C_r, real_t dx)   // adve.ipp:27-60
     { return (x + dx * (C_l - i * (C_r - C_l))) / (1 - (C_r - C_l)); }
@@ -60,11 +77,22 @@ namespace lcx
       return f;
     }
 
+    // size_t(double(x) / dx) of hskpng_ijk.ipp:171 without the division: x * (1/dx) differs from the correctly rounded quotient
+    // by a few ulp (< 1e-12 for any grid index < 2^20), so its integer part is the same unless the quotient sits within 1e-9
+    // of an integer - only then (an SD numerically on a cell face) is the IEEE division evaluated.  Bit-identical result.
+    __device__ __forceinline__ idx_t index_of(real_t x, real_t dx, real_t inv_dx)
+    {
+      const double q = double(x) * double(inv_dx);
+      const double fl = floor(q), fr = q - fl;
+      if (fr > 1e-9 && fr < 1 - 1e-9 && q < 1048576.) return idx_t(size_t(fl));
+      return idx_t(size_t(double(x) / double(dx)));
+    }
+
     __device__ __forceinline__ idx_t cell_of(const grid_t &g, real_t x, real_t y, real_t z, idx_t &i, idx_t &j, idx_t &k)   // hskpng_ijk.ipp:159-200
     {
-      i = g.nx ? idx_t(size_t(double(x) / double(g.dx))) : 0;
-      j = g.ny ? idx_t(size_t(double(y) / double(g.dy))) : 0;
-      k = g.nz ? idx_t(size_t(double(z) / double(g.dz))) : 0;
+      i = g.nx ? index_of(x, g.dx, real_t(1) / g.dx) : 0;
+      j = g.ny ? index_of(y, g.dy, real_t(1) / g.dy) : 0;
+      k = g.nz ? index_of(z, g.dz, real_t(1) / g.dz) : 0;
       switch (g.n_dims)
       {
         case 1: return i;
@@ -79,14 +107,15 @@ namespace lcx
                                                       const real_t *__restrict__ vt, const idx_t *__restrict__ ijk, n_t *__restrict__ ns,
                                                       const real_t *__restrict__ rw2, const real_t *__restrict__ rd3,
                                                       const real_t *__restrict__ Cx, const real_t *__restrict__ Cy, const real_t *__restrict__ Cz,
-                                                      const real_t *__restrict__ w_LS, uint32_t *__restrict__ flag, double *__restrict__ partial)
+                                                      const real_t *__restrict__ w_LS, uint32_t *__restrict__ flag, double *__restrict__ partial,
+                                                      uint32_t *__restrict__ key, uint32_t *__restrict__ val)
     {
       __shared__ double red[4][TPB / 32];
       const grid_t &g = P.g;
-      const size_t t = size_t(blockIdx.x) * TPB + threadIdx.x;
       double pud[4] = {0, 0, 0, 0};   // liquid volume, dry volume, liquid number, particle number leaving through z0
 
-      if (t < n_part)
+      // grid-stride over tiles of TPB super-droplets: the precipitation sums are reduced once per CTA
+      for (size_t t = size_t(blockIdx.x) * TPB + threadIdx.x; t < n_part; t += size_t(gridDim.x) * TPB)
       {
         const idx_t c = ijk[t];
         idx_t i = 0, j = 0, k = 0;
@@ -186,10 +215,10 @@ namespace lcx
               {
                 const real_t nf = real_t(n);
                 const real_t r2 = rw2[t];
-                pud[0] = count_vol(nf, r2, real_t(3. / 2.));
-                pud[1] = count_vol(nf, rd3[t], real_t(1.));
-                pud[2] = (r2 == real_t(0)) ? 0. : nf;
-                pud[3] = nf;
+                pud[0] += count_vol(nf, r2, real_t(3. / 2.));
+                pud[1] += count_vol(nf, rd3[t], real_t(1.));
+                pud[2] += (r2 == real_t(0)) ? 0. : nf;
+                pud[3] += nf;
                 n = 0;
               }
             }
@@ -202,6 +231,17 @@ namespace lcx
         if (g.nz) zs[t] = z;
         ns[t] = n;
         flag[t] = fl;
+        // sort key of the coming re-layout (hskpng_ijk of post_copy): new cell, or n_cell for SDs that are gone;
+        // migrants leave through lcx_migr_pack, which zeroes their multiplicity and re-keys them
+        uint32_t kx = g.n_cell;
+        if (n != 0 && fl == 0)
+        {
+          idx_t i2, j2, k2;
+          kx = cell_of(g, x, y, z, i2, j2, k2);
+          if (kx >= g.n_cell) kx = g.n_cell - 1;
+        }
+        key[t] = kx;
+        val[t] = uint32_t(t);
       }
 
       // deterministic block sums of the precipitation terms (second pass: k_puddle_final)
@@ -239,11 +279,12 @@ namespace lcx
 
     // ---- migration ---------------------------------------------------------------------------------------
     __global__ void __launch_bounds__(TPB) k_mig_collect(size_t n_part, uint32_t which, const uint32_t *__restrict__ flag, const idx_t *__restrict__ sid,
-                                                        uint32_t *__restrict__ key, uint32_t *__restrict__ val, unsigned int *counter)
+                                                        uint32_t *__restrict__ key, uint32_t *__restrict__ val, unsigned int *counter, unsigned cap)
     {
       const size_t t = size_t(blockIdx.x) * TPB + threadIdx.x;
       if (t >= n_part || flag[t] != which) return;
       const unsigned slot = atomicAdd(counter, 1u);
+      if (slot >= cap) return;     // overflow is reported by the host from the counter
       key[slot] = sid[t];          // order is fixed afterwards by sorting on the storage index
       val[slot] = uint32_t(t);
     }
@@ -263,12 +304,12 @@ namespace lcx
         if (a == A.x_slot) v = rmt + v - lcl;                 // remote coordinate: pack.ipp:15-26
         out_real[size_t(a) * count + jx] = v;
       }
-      ns[ph] = 0;                                             // flag_lft / flag_rgt: unpack.ipp:122-145
+      ns[ph] = 0;                                             // flag_lft / flag_rgt: unpack.ipp:122-145 (its sort key already says "gone")
     }
 
     struct mig_dst { real_t *dst[7]; int n; int x_slot; };
 
-    __global__ void __launch_bounds__(TPB) k_mig_unpack(unsigned count, size_t n_part_old, mig_dst A, n_t *__restrict__ ns, idx_t *__restrict__ sid,
+    __global__ void __launch_bounds__(TPB) k_mig_unpack(unsigned count, size_t n_part_old, size_t sid_first, mig_dst A, n_t *__restrict__ ns, idx_t *__restrict__ sid,
                                                        const n_t *__restrict__ in_n, const real_t *__restrict__ in_real,
                                                        real_t x0, real_t x1, real_t tol, int from_right)
     {
@@ -276,7 +317,7 @@ namespace lcx
       if (jx >= count) return;
       const size_t d = n_part_old + jx;
       ns[d] = in_n[jx];
-      sid[d] = idx_t(d);
+      sid[d] = idx_t(sid_first + jx);
       for (int a = 0; a < A.n; ++a)
       {
         real_t v = in_real[size_t(a) * count + jx];
@@ -315,10 +356,11 @@ namespace lcx
     P.bcond_lft = e->cfg.bcond_lft; P.bcond_rgt = e->cfg.bcond_rgt;
     if (P.subs && e->w_LS.n < size_t(e->grid.nz)) throw error("subsidence requested but no w_LS profile was set");
     if (P.scheme == AS_PRED_CORR && e->grid.halo_size != 2) throw error("predictor-corrector advection needs a 2-cell Courant halo");
-    const unsigned blocks = div_up(n, TPB);
+    const unsigned blocks = unsigned(std::min<size_t>(div_up(n, TPB), size_t(148) * 16));   // 148 SMs x 16 resident CTAs
     if (e->red_partial.n < size_t(blocks) * 4) { LCX_CUDA(cudaStreamSynchronize(e->stream)); e->red_partial.alloc(size_t(blocks) * 4 + 1024); }
     LCX_LAUNCH(e, k_transport, blocks, TPB, 0, n, P, s.x.p, s.y.p, s.z.p, s.vt.p, s.ijk.p, s.n.p, s.rw2.p, s.rd3.p,
-               e->courant_x.p, e->courant_y.p, e->courant_z.p, e->w_LS.p, e->flag.p, e->red_partial.p);
+               e->courant_x.p, e->courant_y.p, e->courant_z.p, e->w_LS.p, e->flag.p, e->red_partial.p, e->key[0].p, e->val[0].p);
+    e->keys_ready = n;      // key[0] / val[0] hold the sort keys of SDs [0, n)
     if (e->grid.n_dims > 1 && !e->cfg.periodic_topbot_walls)
       LCX_LAUNCH(e, k_puddle_final, 1, TPB, 0, blocks, e->red_partial.p, e->scalars.p);
     e->grouped = false;   // positions changed: cell segments are stale until lcx_post_copy
@@ -336,21 +378,22 @@ namespace lcx
       if (bc != LCX_BCOND_DISTMEM) continue;
       unsigned int *counter = side == 0 ? &e->scalars.p->n_lft : &e->scalars.p->n_rgt;
       LCX_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), e->stream));
-      LCX_LAUNCH(e, k_mig_collect, div_up(n, TPB), TPB, 0, n, uint32_t(side + 1), e->flag.p, s.sid.p, e->key[0].p, e->val[0].p, counter);
+      uint32_t *mk[2] = {e->mig_key[0].p, e->mig_key[1].p}, *mv[2] = {e->mig_val[0].p, e->mig_val[1].p};
+      LCX_LAUNCH(e, k_mig_collect, div_up(n, TPB), TPB, 0, n, uint32_t(side + 1), e->flag.p, s.sid.p, mk[0], mv[0], counter, unsigned(e->mig_cap));
       LCX_CUDA(cudaMemcpyAsync(e->h_scalars, e->scalars.p, sizeof(dev_scalars), cudaMemcpyDeviceToHost, e->stream));
       LCX_CUDA(cudaStreamSynchronize(e->stream));
       const unsigned count = side == 0 ? e->h_scalars->n_lft : e->h_scalars->n_rgt;
       (side == 0 ? *n_lft : *n_rgt) = count;
       if (count == 0) continue;
       if (count > e->mig_cap) throw error("migration buffer overflow: " + std::to_string(count) + " super-droplets cross one slab face, capacity " + std::to_string(e->mig_cap));
-      int bits = 0; { uint64_t v = e->n_part ? e->n_part - 1 : 0; while (v) { ++bits; v >>= 1; } if (bits == 0) bits = 1; }
-      const int res = radix_sort_pairs(e, count, 0, bits, 0);
+      int bits = 0; { uint64_t v = e->sid_hi ? e->sid_hi - 1 : 0; while (v) { ++bits; v >>= 1; } if (bits == 0) bits = 1; }
+      const int res = radix_sort_pairs(e, count, 0, bits, mk, mv, 0);
       mig_attrs A; real_t *list[7];
       A.n = fill_attr_list(e, list, &A.x_slot);
       for (int a = 0; a < A.n; ++a) A.src[a] = list[a];
       const real_t lcl = side == 0 ? e->grid.x0 : e->grid.x1;
       const real_t rmt = side == 0 ? real_t(e->cfg.lft_x1) : real_t(e->cfg.rgt_x0);
-      LCX_LAUNCH(e, k_mig_pack, div_up(count, TPB), TPB, 0, count, e->val[res].p, A, s.n.p, lcl, rmt, e->mig_n[side][0].p, e->mig_real[side][0].p);
+      LCX_LAUNCH(e, k_mig_pack, div_up(count, TPB), TPB, 0, count, mv[res], A, s.n.p, lcl, rmt, e->mig_n[side][0].p, e->mig_real[side][0].p);
     }
   }
 
@@ -364,9 +407,11 @@ namespace lcx
     mig_dst A; real_t *list[7];
     A.n = fill_attr_list(e, list, &A.x_slot);
     for (int a = 0; a < A.n; ++a) A.dst[a] = list[a];
-    LCX_LAUNCH(e, k_mig_unpack, div_up(size_t(count), TPB), TPB, 0, unsigned(count), e->n_part, A, s.n.p, s.sid.p,
+    if (e->sid_hi + size_t(count) > e->cap) densify_sid(e);
+    LCX_LAUNCH(e, k_mig_unpack, div_up(size_t(count), TPB), TPB, 0, unsigned(count), e->n_part, e->sid_hi, A, s.n.p, s.sid.p,
                e->mig_n[side][1].p, e->mig_real[side][1].p, e->grid.x0, e->grid.x1, real_t(5e-4), int(side == 0));
     e->n_part += size_t(count);
+    e->sid_hi += size_t(count);
     e->grouped = false;
   }
 }

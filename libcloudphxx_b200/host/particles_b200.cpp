@@ -327,6 +327,7 @@ namespace libcloudphxx
           std::vector<real_t> eff;
           if (oi.coal_switch) eff = init_kernel(c);
           chk(lcx_create(&c, &e));
+          chk(lcx_set_dense_storage_index(e, rng_mode == LGRNGN_B200_RNG_MT19937));
           if (!eff.empty()) chk(lcx_set_efficiencies(e, eff.data(), int64_t(eff.size())));
         }
 
@@ -625,7 +626,8 @@ namespace libcloudphxx
             {
               chk(lcx_sstp_percell_step(e, step, sstp_cond, var_rho));
               chk(lcx_hskpng_Tpr(e));
-              chk(lcx_cond(e, dt / sstp_cond, opts.RH_max, step, sstp_cond));   // includes update_th_rv
+              // includes update_th_rv; on the last sub-step also the Tpr + vterm_all that step_async begins with
+              chk(lcx_cond(e, dt / sstp_cond, opts.RH_max, step, sstp_cond));
             }
             chk(lcx_sstp_save(e));
             sync_out_field(LCX_F_TH, m_th, th);
