@@ -83,6 +83,7 @@ namespace lcx
     unsigned int pad;
     unsigned long long n_collisions, n_pairs_collided;
     double puddle[8];               // liq_vol, dry_vol, liq_num, prtcl_num (+spare), accumulated
+    unsigned long long rcyc_zero, rcyc_one, rcyc_max;   // SDs with n == 0, with n == 1, largest n (recycling)
   };
 }
 

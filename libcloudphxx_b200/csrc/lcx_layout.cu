@@ -105,6 +105,51 @@ namespace lcx
       if (t < n) dst[sid[t]] = real_t(src[t]);
     }
 
+    // ---- recycling (rcyc.ipp:44-139) --------------------------------------------------------------------------------
+    __global__ void __launch_bounds__(TPB) k_rcyc_stats(size_t n, const n_t *__restrict__ ns, dev_scalars *sc)
+    {
+      const size_t t = size_t(blockIdx.x) * TPB + threadIdx.x;
+      const n_t v = (t < n) ? ns[t] : n_t(2);
+      const unsigned zeros = __ballot_sync(0xffffffffu, v == 0), ones = __ballot_sync(0xffffffffu, v == 1);
+      unsigned long long m = v;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { const unsigned long long w = __shfl_xor_sync(0xffffffffu, m, o); m = w > m ? w : m; }
+      if ((threadIdx.x & 31) == 0)
+      {
+        if (zeros) atomicAdd(&sc->rcyc_zero, (unsigned long long)__popc(zeros));
+        if (ones) atomicAdd(&sc->rcyc_one, (unsigned long long)__popc(ones));
+        atomicMax(&sc->rcyc_max, m);
+      }
+    }
+
+    // order[sid] = physical index: the identity permutation of the reference's storage (thrust::sequence, rcyc.ipp:69)
+    __global__ void __launch_bounds__(TPB) k_rcyc_order(size_t n, const idx_t *__restrict__ sid, uint32_t *__restrict__ order)
+    {
+      const size_t t = size_t(blockIdx.x) * TPB + threadIdx.x;
+      if (t < n) order[sid[t]] = uint32_t(t);
+    }
+
+    __global__ void __launch_bounds__(TPB) k_rcyc_keys(size_t n, const n_t *__restrict__ ns, const uint32_t *__restrict__ order, int shift, uint32_t *__restrict__ key)
+    {
+      const size_t t = size_t(blockIdx.x) * TPB + threadIdx.x;
+      if (t < n) key[t] = uint32_t(ns[order[t]] >> shift);
+    }
+
+    // q-th dead SD (ascending storage index) takes the attributes of the q-th largest multiplicity; the pair shares n
+    __global__ void __launch_bounds__(TPB) k_rcyc_copy(size_t n_flagged, size_t n, const uint32_t *__restrict__ order, n_t *__restrict__ ns,
+                                                      real_t *__restrict__ rd3, real_t *__restrict__ rw2, real_t *__restrict__ kpa, real_t *__restrict__ vt,
+                                                      real_t *__restrict__ x, real_t *__restrict__ y, real_t *__restrict__ z)
+    {
+      const size_t q = size_t(blockIdx.x) * TPB + threadIdx.x;
+      if (q >= n_flagged) return;
+      const uint32_t dst = order[q], src = order[n - 1 - q];
+      rd3[dst] = rd3[src]; rw2[dst] = rw2[src]; kpa[dst] = kpa[src]; vt[dst] = vt[src];
+      x[dst] = x[src]; y[dst] = y[src]; z[dst] = z[src];
+      const n_t m = ns[src];
+      ns[dst] = m - m / 2;
+      ns[src] = m / 2;
+    }
+
     int bit_length(uint64_t v) { int b = 0; while (v) { ++b; v >>= 1; } return b; }
 
     void add(gather_set &G, const void *src, void *dst, int width)
@@ -122,9 +167,45 @@ namespace lcx
     LCX_LAUNCH(e, k_max_count, div_up(g.n_cell, TPB), TPB, 0, g.n_cell, e->cell_off.p, e->scalars.p);
   }
 
+  // rcyc.ipp:44-139.  The reference sorts (stably) the whole storage by multiplicity; ties therefore resolve by storage
+  // index, which is what the hidden sid carries here.  Afterwards every key is stale (hskpng_ijk follows in post_copy).
+  static void recycle(lcx_engine *e)
+  {
+    const size_t n = e->n_part;
+    if (n == 0) return;
+    sd_arrays &s = e->S();
+    dev_scalars *sc = e->scalars.p;
+    LCX_CUDA(cudaMemsetAsync(&sc->rcyc_zero, 0, 3 * sizeof(unsigned long long), e->stream));
+    LCX_LAUNCH(e, k_rcyc_stats, div_up(n, TPB), TPB, 0, n, s.n.p, sc);
+    LCX_CUDA(cudaMemcpyAsync(e->h_scalars, sc, sizeof(dev_scalars), cudaMemcpyDeviceToHost, e->stream));
+    LCX_CUDA(cudaStreamSynchronize(e->stream));
+    const size_t n_zero = e->h_scalars->rcyc_zero, n_one = e->h_scalars->rcyc_one;
+    const uint64_t n_max = e->h_scalars->rcyc_max;
+    if (n_zero == 0) return;
+    if (e->cfg.pure_const_multi) return;                     // plain removal (rcyc.ipp:58-62)
+    // SDs counted from the large end of the sorted multiplicities up to the first n == 1; when nobody has n == 1 the
+    // reference's find() runs off the end and returns the whole length (rcyc.ipp:87-90)
+    const size_t n_splittable = n_one ? n - n_zero - n_one : n;
+    if (n_splittable == 0) return;
+    const size_t n_flagged = n_zero < n_splittable ? n_zero : n_splittable;
+
+    densify_sid(e);
+    uint32_t *key[2] = {e->key[0].p, e->key[1].p}, *val[2] = {e->val[0].p, e->val[1].p};
+    LCX_LAUNCH(e, k_rcyc_order, div_up(n, TPB), TPB, 0, n, s.sid.p, val[0]);
+    int cur = 0;
+    const int bits = bit_length(n_max);
+    for (int shift = 0; shift < bits; shift += 32)
+    {
+      LCX_LAUNCH(e, k_rcyc_keys, div_up(n, TPB), TPB, 0, n, s.n.p, val[cur], shift, key[cur]);
+      cur = radix_sort_pairs(e, n, 0, bits - shift < 32 ? bits - shift : 32, key, val, cur);
+    }
+    LCX_LAUNCH(e, k_rcyc_copy, div_up(n_flagged, TPB), TPB, 0, n_flagged, n, val[cur], s.n.p, s.rd3.p, s.rw2.p, s.kpa.p, s.vt.p, s.x.p, s.y.p, s.z.p);
+    e->keys_ready = 0;
+  }
+
   void post_copy(lcx_engine *e, bool rcyc, bool keep_all)
   {
-    if (rcyc) throw error("opts.rcyc (recycling of super-droplets) is not implemented yet in the B200 back-end");
+    if (rcyc && !keep_all) recycle(e);
     const grid_t &g = e->grid;
     const size_t n_old = e->n_part;
     sd_arrays &s = e->S();

@@ -164,6 +164,36 @@ def test_coal_sedi_adve_3d_without_condensation(ref, b200, kernel, vt):
     assert seen["collided"] and seen["removed"], seen
 
 
+def test_recycling_3d(ref, b200):
+    """opts.rcyc: SDs that left through the bottom / were used up by coalescence are re-created from the SDs with the
+    largest multiplicities (rcyc.ipp:44-139); who is split, who is re-created and the resulting storage order are exact"""
+    seen = {"recycled": 0}
+
+    def setup(lib):
+        oi, o, f = S.box_3d(lib, nx=6, ny=5, nz=8, sd_conc=32, rain_mode=True, dt=2.0, sstp_coal=2)
+        o.cond = 0
+        o.rcyc = 1
+        return oi, o, f
+
+    def check(step, p_r, p_n, f_r, f_n):
+        n_r, n_n = p_r.get_n(), p_n.get_n()
+        assert n_r.size == n_n.size, (step, n_r.size, n_n.size)
+        assert np.array_equal(n_r, n_n), "multiplicities differ at step %d" % step
+        assert np.array_equal(p_r.get_attr("rd3"), p_n.get_attr("rd3")), step
+        assert S.rel_err(p_r.get_attr("rw2"), p_n.get_attr("rw2")) < 1e-14, step
+        for k in ("x", "y"):
+            assert np.array_equal(p_r.get_attr(k), p_n.get_attr(k)), (k, step)
+        assert S.rel_err(p_r.get_attr("z"), p_n.get_attr("z")) < 1e-11, step
+        if step == -1:
+            seen["size0"], seen["n0"] = n_r.size, n_r.copy()
+        else:
+            assert n_r.size == seen["size0"], "recycling keeps the number of SDs"       # enough splittable SDs in this case
+            seen["recycled"] += int((n_r != seen["n0"]).sum())
+            seen["n0"] = n_r.copy()
+    S.run_pair(ref, b200, setup, 6, on_step=check)
+    assert seen["recycled"] > 0, seen
+
+
 def test_full_step_3d(ref, b200):
     """cfg4-shaped box: cond + coal + sedi + adve; integer state exact, floating-point state within the stated tolerance"""
     log = []
