@@ -15,7 +15,7 @@ extern "C" {
 
 typedef struct lgc_handle lgc_handle;
 
-enum { LGC_MAX_MODES = 4, LGC_MAX_DISTROS = 4, LGC_MAX_KPARAMS = 4 };
+enum { LGC_MAX_MODES = 4, LGC_MAX_DISTROS = 4, LGC_MAX_KPARAMS = 4, LGC_MAX_SIZES = 16 };
 
 /* dry spectrum n(ln r) [m^-3 per unit ln r, at STP] */
 typedef struct
@@ -26,6 +26,9 @@ typedef struct
   double mean_r[LGC_MAX_MODES], stdev[LGC_MAX_MODES], n_tot[LGC_MAX_MODES];
   double r0, n0;                   /* kind 1: n0 * 3 (r/r0)^3 exp(-(r/r0)^3)                       */
 } lgc_distro;
+
+/* one entry of opts_init_t::dry_sizes: (kappa, rd_insol) -> radius -> (STP concentration, SDs per cell) */
+typedef struct { double kappa, rd_insol, radius, conc; int count; } lgc_dry_size;
 
 typedef struct
 {
@@ -50,6 +53,11 @@ typedef struct
   lgc_distro distros[LGC_MAX_DISTROS];
   int n_w_LS;
   const double *w_LS;
+  int sd_conc_large_tail, no_ccn_at_init;
+  int n_dry_sizes;
+  lgc_dry_size dry_sizes[LGC_MAX_SIZES];
+  int n_aerosol_conc_factor;
+  const double *aerosol_conc_factor;
 } lgc_opts_init;
 
 typedef struct

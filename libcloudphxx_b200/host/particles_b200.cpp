@@ -174,10 +174,6 @@ namespace libcloudphxx
           if (oi.diag_incloud_time) throw std::runtime_error("libcloudph++: diag_incloud_time is not part of the B200 back-end");
           if (oi.kernel == kernel_t::onishi_hall || oi.kernel == kernel_t::onishi_hall_davis_no_waals)
             throw std::runtime_error("libcloudph++: To use the turbulent Onishis kernel, set turb_coal_switch=True");
-          if (oi.sd_conc_large_tail || oi.sd_const_multi > 0 || oi.dry_sizes.size() > 0)
-            throw std::runtime_error("libcloudph++: only opts_init.sd_conc initialisation from dry_distros is available yet in the B200 back-end");
-          if (!oi.aerosol_conc_factor.empty())
-            throw std::runtime_error("libcloudph++: aerosol_conc_factor is not available yet in the B200 back-end");
         }
 
         bool is_distmem() const { return bcond.first == distmem || bcond.second == distmem; }
@@ -203,6 +199,12 @@ namespace libcloudphxx
             if (!(oi.y1 > oi.y0 && oi.y1 <= m1(oi.ny) * oi.dy)) throw std::runtime_error("libcloudph++: !(y1 > y0 & y1 <= min(1,ny)*dy)");
             if (!(oi.z1 > oi.z0 && oi.z1 <= m1(oi.nz) * oi.dz)) throw std::runtime_error("libcloudph++: !(z1 > z0 & z1 <= min(1,nz)*dz)");
           }
+          if (!oi.aerosol_conc_factor.empty() && n_dims < 2)
+            throw std::runtime_error("libcloudph++: aerosol_conc_factor can only be used in 2D and 3D");
+          if (!oi.aerosol_conc_factor.empty() && size_t(oi.nz) != oi.aerosol_conc_factor.size())
+            throw std::runtime_error("libcloudph++: aerosol_conc_factor size needs to be either 0 or nz");
+          if (!oi.aerosol_conc_factor.empty() && !oi.aerosol_independent_of_rhod)
+            throw std::runtime_error("libcloudph++: aerosol_conc_factor can only be used if aerosol_independent_of_rhod==true");
           if (oi.dt == 0) throw std::runtime_error("libcloudph++: please specify opts_init.dt");
           if (oi.sd_conc * oi.sd_const_multi != 0)
             throw std::runtime_error("libcloudph++: specify either opts_init.sd_conc or opts_init.sd_const_multi, not both");
@@ -394,7 +396,12 @@ namespace libcloudphxx
 
           chk(lcx_hskpng_Tpr(e));
 
-          if (!oi.no_ccn_at_init && oi.dry_distros.size() > 0) init_SD_with_distros(th, rv, rhod, p);
+          if (!oi.no_ccn_at_init)
+          {
+            const cell_state cs = host_cells(th, rv, rhod, p);
+            if (oi.dry_distros.size() > 0) init_SD_with_distros(cs);
+            if (oi.dry_sizes.size() > 0) init_SD_with_sizes(cs);
+          }
 
           if (oi.terminal_velocity == vt_t::beard77fast)
           {
@@ -485,81 +492,254 @@ namespace libcloudphxx
 
         real_t draw_u01() { return std::uniform_real_distribution<real_t>(0, 1)(engine); }
 
-        void init_SD_with_distros(const arrinfo_t<real_t> &th, const arrinfo_t<real_t> &rv, const arrinfo_t<real_t> &rhod, const arrinfo_t<real_t> &p)
+        // Brent's minimiser (Brent 1973, ch. 5) with the stopping rule and step choices of the Boost.Math routine the
+        // reference calls in init_dist_analysis.ipp:95 (brent_find_minima with bits capped at half the mantissa)
+        template <class F>
+        static std::pair<real_t, real_t> brent_minimum(const F &f, real_t lo, real_t hi, int max_iter)
         {
-          const cell_state cs = host_cells(th, rv, rhod, p);
-          real_t log_rd_min = 0, log_rd_max = 0, multiplier = 0;
-
-          real_t tot_lnrd_rng = 0.;                                   // init_SD_with_distros.ipp:18-29
-          for (const auto &dd : oi.dry_distros)
+          const real_t tol = std::ldexp(real_t(1), 1 - std::numeric_limits<real_t>::digits / 2);
+          const real_t golden = real_t(0.3819660f);
+          real_t x = hi, w = hi, v = hi, fx = f(x), fw = fx, fv = fx, d = 0, d_prev = 0;
+          for (int it = 0; it < max_iter; ++it)
           {
-            dist_analysis_sd_conc(*dd.second, cs, log_rd_min, log_rd_max, multiplier);
-            tot_lnrd_rng += log_rd_max - log_rd_min;
-          }
-
-          const real_t rho_stp = lcx::cst<real_t>::rho_stp();
-          for (const auto &dd : oi.dry_distros)
-          {
-            const common::unary_function<real_t> &fun = *dd.second;
-            dist_analysis_sd_conc(fun, cs, log_rd_min, log_rd_max, multiplier);
-            if (log_rd_min >= log_rd_max)
-            { std::ostringstream s; s << "Distribution analysis error: rd_min(" << std::exp(log_rd_min) << ") >= rd_max(" << std::exp(log_rd_max) << ")"; throw std::runtime_error(s.str()); }
-
-            // init_SD_with_distros_sd_conc.ipp:26-33, init_count_num.ipp:32-35
-            const real_t fraction = (log_rd_max - log_rd_min) / tot_lnrd_rng;
-            multiplier *= oi.sd_conc / int(fraction * oi.sd_conc + 0.5);
-            const n_t per_cell = n_t(fraction * oi.sd_conc);
-            const size_t n_new = size_t(per_cell) * n_cell;
-
-            std::vector<n_t> n(n_new);
-            std::vector<real_t> rd3(n_new), rw2(n_new), kpa(n_new, dd.first.kappa), xs, ys, zs;
-            std::vector<uint32_t> ijk(n_new);
-            for (size_t s = 0; s < n_new; ++s) ijk[s] = uint32_t(s / per_cell);      // init_ijk.ipp:36-52 (cell-major)
-
-            // dry radii, stratified in ln(rd) within each cell: init_dry_sd_conc.ipp:25-66
-            std::vector<real_t> u01(n_new);
-            for (size_t s = 0; s < n_new; ++s) u01[s] = draw_u01();
-#pragma omp parallel for schedule(static)
-            for (long sl = 0; sl < long(n_new); ++sl)
+            const real_t mid = (lo + hi) / 2, t1 = tol * std::fabs(x) + tol / 4, t2 = 2 * t1;
+            if (std::fabs(x - mid) <= t2 - (hi - lo) / 2) break;
+            bool parabolic = false;
+            if (std::fabs(d_prev) > t1)
             {
-              const size_t s = size_t(sl);
-              const size_t ptr = size_t(ijk[s]) * per_cell;
-              const real_t lnrd = log_rd_min + real_t(s - ptr + u01[s]) * (log_rd_max - log_rd_min) / real_t(per_cell);
-              rd3[s] = std::exp(3 * lnrd);
-              // multiplicities: init_n.ipp:48-137
-              const real_t lnrd2 = std::log(rd3[s]) / 3.;
-              real_t v = multiplier * fun(lnrd2);
-              if (!oi.aerosol_independent_of_rhod) v = v * cs.rhod[ijk[s]] / rho_stp;
-              if (n_dims > 0) v = v * cs.dv[ijk[s]] / real_t(oi.dx * oi.dy * oi.dz);
-              n[s] = n_t(v + real_t(0.5));
-              // equilibrium wet radius: init_wet.ipp:18-74
-              const real_t RH = std::min(cs.RH[ijk[s]], oi.RH_max);
-              rw2[s] = std::pow(lcx::rw3_eq(rd3[s], kpa[s], RH, cs.T[ijk[s]]), real_t(2. / 3));
-            }
-
-            // positions, uniform within the part of the cell inside the Lagrangian domain: init_xyz.ipp:16-73
-            const int nn[3] = {oi.nx, oi.ny, oi.nz};
-            const real_t a[3] = {oi.x0, oi.y0, oi.z0}, b[3] = {oi.x1, oi.y1, oi.z1}, d[3] = {oi.dx, oi.dy, oi.dz};
-            std::vector<real_t> *v[3] = {&xs, &ys, &zs};
-            for (int ix = 0; ix < 3; ++ix)
-            {
-              if (nn[ix] == 0) continue;
-              v[ix]->resize(n_new);
-              for (size_t s = 0; s < n_new; ++s) u01[s] = draw_u01();
-              const size_t nz1 = size_t(m1(oi.nz)), ny1 = size_t(m1(oi.ny));
-              for (size_t s = 0; s < n_new; ++s)
+              real_t r = (x - w) * (fx - fv), q = (x - v) * (fx - fw), pnum = (x - v) * q - (x - w) * r;
+              q = 2 * (q - r);
+              if (q > 0) pnum = -pnum;
+              q = std::fabs(q);
+              const real_t d_before = d_prev;
+              d_prev = d;
+              parabolic = !(std::fabs(pnum) >= std::fabs(q * d_before / 2) || pnum <= q * (lo - x) || pnum >= q * (hi - x));
+              if (parabolic)
               {
-                const size_t c = ijk[s];
-                size_t ii;
-                if (n_dims == 1) ii = c;
-                else if (n_dims == 2) ii = ix == 0 ? c / nz1 : c % nz1;
-                else ii = ix == 0 ? c / (nz1 * ny1) : ix == 1 ? (c / nz1) % ny1 : c % nz1;
-                (*v[ix])[s] = u01[s] * std::min(b[ix], (ii + 1) * d[ix]) + (1. - u01[s]) * std::max(a[ix], ii * d[ix]);
+                d = pnum / q;
+                const real_t u = x + d;
+                if ((u - lo) < t2 || (hi - u) < t2) d = (mid - x) < 0 ? -std::fabs(t1) : std::fabs(t1);
               }
             }
-            chk(lcx_sd_append(e, int64_t(n_new), reinterpret_cast<const uint64_t *>(n.data()), rd3.data(), rw2.data(), kpa.data(),
-                              xs.empty() ? nullptr : xs.data(), ys.empty() ? nullptr : ys.data(), zs.empty() ? nullptr : zs.data(), ijk.data()));
+            if (!parabolic)
+            {
+              d_prev = (x >= mid) ? lo - x : hi - x;
+              d = golden * d_prev;
+            }
+            const real_t u = std::fabs(d) >= t1 ? x + d : (d > 0 ? x + std::fabs(t1) : x - std::fabs(t1));
+            const real_t fu = f(u);
+            if (fu <= fx)
+            {
+              (u >= x ? lo : hi) = x;
+              v = w; fv = fw; w = x; fw = fx; x = u; fx = fu;
+            }
+            else
+            {
+              (u < x ? lo : hi) = u;
+              if (fu <= fw || w == x) { v = w; fv = fw; w = u; fw = fu; }
+              else if (fu <= fv || v == x || v == w) { v = u; fv = fu; }
+            }
           }
+          return std::make_pair(x, fx);
+        }
+
+        // ln(rd) range of a spectrum for constant-multiplicity sampling: where it drops to 1e-20 of its maximum
+        // (init_dist_analysis.ipp:78-123, config.hpp:17-24)
+        void dist_analysis_const_multi(const common::unary_function<real_t> &fun, real_t &log_rd_min, real_t &log_rd_max) const
+        {
+          if (oi.rd_min >= 0 && oi.rd_max >= 0)
+          {
+            log_rd_min = std::log(oi.rd_min);
+            log_rd_max = std::log(oi.rd_max);
+            return;
+          }
+          if (!(oi.rd_min < 0 && oi.rd_max < 0)) throw std::runtime_error("libcloudph++: opts_init.rd_min * opts_init.rd_max < 0");
+          const real_t lo = std::log(real_t(1e-14)), hi = std::log(real_t(1e-3)), threshold = 1e20;
+          const auto top = brent_minimum([&](real_t x) { return real_t(-1) * fun(x); }, lo, hi, 100);
+          const real_t bound = -top.second / threshold;
+          const real_t minus_bound = -bound;
+          auto g = [&](real_t x) { return minus_bound + fun(x); };
+          const lcx::width_tol<real_t> tol(sizeof(real_t) * 8 / 4);
+          uintmax_t it = 100;
+          log_rd_min = lcx::toms748(g, lo, top.first, g(lo), g(top.first), tol, it);
+          it = 100;
+          log_rd_max = lcx::toms748(g, top.first, hi, g(top.first), g(hi), tol, it);
+        }
+
+        // concentration at STP -> number of particles in each cell: init_count_num.ipp:35-64
+        std::vector<real_t> conc_to_number(const cell_state &cs, real_t conc) const
+        {
+          std::vector<real_t> arr(n_cell, conc);
+          const real_t rho_stp = lcx::cst<real_t>::rho_stp();
+          for (size_t c = 0; c < n_cell; ++c)
+          {
+            arr[c] = arr[c] * cs.dv[c];
+            if (!oi.aerosol_independent_of_rhod) arr[c] = cs.rhod[c] / rho_stp * arr[c];
+            if (!oi.aerosol_conc_factor.empty()) arr[c] = arr[c] * oi.aerosol_conc_factor[c % size_t(oi.nz)];
+          }
+          return arr;
+        }
+
+        // cell of every new SD: count_num[0] times cell 0, count_num[1] times cell 1, ... (init_ijk.ipp:36-52)
+        std::vector<uint32_t> cells_of_new(const std::vector<size_t> &count_num) const
+        {
+          size_t tot = 0;
+          for (const size_t c : count_num) tot += c;
+          std::vector<uint32_t> ijk;
+          ijk.reserve(tot);
+          for (size_t c = 0; c < n_cell; ++c) ijk.insert(ijk.end(), count_num[c], uint32_t(c));
+          return ijk;
+        }
+
+        // common tail of every initialisation flavour: kappa, equilibrium wet radius (init_wet.ipp:18-74), positions
+        // uniform within the part of the cell inside the Lagrangian domain (init_xyz.ipp:16-73), upload
+        void finalize_new(const cell_state &cs, const std::vector<uint32_t> &ijk, const std::vector<n_t> &n, const std::vector<real_t> &rd3, real_t kappa)
+        {
+          const size_t n_new = ijk.size();
+          if (n_new == 0) return;
+          std::vector<real_t> rw2(n_new), kpa(n_new, kappa), xs, ys, zs, u01(n_new);
+#pragma omp parallel for schedule(static)
+          for (long sl = 0; sl < long(n_new); ++sl)
+          {
+            const size_t s = size_t(sl);
+            const real_t RH = std::min(cs.RH[ijk[s]], oi.RH_max);
+            rw2[s] = std::pow(lcx::rw3_eq(rd3[s], kpa[s], RH, cs.T[ijk[s]]), real_t(2. / 3));
+          }
+          const int nn[3] = {oi.nx, oi.ny, oi.nz};
+          const real_t a[3] = {oi.x0, oi.y0, oi.z0}, b[3] = {oi.x1, oi.y1, oi.z1}, d[3] = {oi.dx, oi.dy, oi.dz};
+          std::vector<real_t> *v[3] = {&xs, &ys, &zs};
+          for (int ix = 0; ix < 3; ++ix)
+          {
+            if (nn[ix] == 0) continue;
+            v[ix]->resize(n_new);
+            for (size_t s = 0; s < n_new; ++s) u01[s] = draw_u01();
+            const size_t nz1 = size_t(m1(oi.nz)), ny1 = size_t(m1(oi.ny));
+            for (size_t s = 0; s < n_new; ++s)
+            {
+              const size_t c = ijk[s];
+              size_t ii;
+              if (n_dims == 1) ii = c;
+              else if (n_dims == 2) ii = ix == 0 ? c / nz1 : c % nz1;
+              else ii = ix == 0 ? c / (nz1 * ny1) : ix == 1 ? (c / nz1) % ny1 : c % nz1;
+              (*v[ix])[s] = u01[s] * std::min(b[ix], (ii + 1) * d[ix]) + (1. - u01[s]) * std::max(a[ix], ii * d[ix]);
+            }
+          }
+          chk(lcx_sd_append(e, int64_t(n_new), reinterpret_cast<const uint64_t *>(n.data()), rd3.data(), rw2.data(), kpa.data(),
+                            xs.empty() ? nullptr : xs.data(), ys.empty() ? nullptr : ys.data(), zs.empty() ? nullptr : zs.data(), ijk.data()));
+        }
+
+        // sd_conc SDs per cell, stratified in ln(rd): init_SD_with_distros_sd_conc.ipp:16-52, init_dry_sd_conc.ipp:25-66, init_n.ipp:48-137
+        void init_sd_conc(const cell_state &cs, const kappa_rd_insol_t<real_t> &kr, const common::unary_function<real_t> &fun,
+                          real_t tot_lnrd_rng, real_t &log_rd_max_out)
+        {
+          real_t log_rd_min = 0, log_rd_max = 0, multiplier = 0;
+          dist_analysis_sd_conc(fun, cs, log_rd_min, log_rd_max, multiplier);
+          log_rd_max_out = log_rd_max;
+          if (log_rd_min >= log_rd_max)
+          { std::ostringstream s; s << "Distribution analysis error: rd_min(" << std::exp(log_rd_min) << ") >= rd_max(" << std::exp(log_rd_max) << ")"; throw std::runtime_error(s.str()); }
+
+          const real_t rho_stp = lcx::cst<real_t>::rho_stp();
+          const real_t fraction = (log_rd_max - log_rd_min) / tot_lnrd_rng;
+          multiplier *= oi.sd_conc / int(fraction * oi.sd_conc + 0.5);
+          const size_t per_cell = size_t(fraction * oi.sd_conc);                      // init_count_num.ipp:32-35
+          const std::vector<uint32_t> ijk = cells_of_new(std::vector<size_t>(n_cell, per_cell));
+          const size_t n_new = ijk.size();
+
+          std::vector<n_t> n(n_new);
+          std::vector<real_t> rd3(n_new), u01(n_new);
+          for (size_t s = 0; s < n_new; ++s) u01[s] = draw_u01();
+#pragma omp parallel for schedule(static)
+          for (long sl = 0; sl < long(n_new); ++sl)
+          {
+            const size_t s = size_t(sl);
+            const size_t ptr = size_t(ijk[s]) * per_cell;
+            const real_t lnrd = log_rd_min + real_t(s - ptr + u01[s]) * (log_rd_max - log_rd_min) / real_t(per_cell);
+            rd3[s] = std::exp(3 * lnrd);
+            const real_t lnrd2 = std::log(rd3[s]) / 3.;
+            real_t v = multiplier * fun(lnrd2);
+            if (!oi.aerosol_independent_of_rhod) v = v * cs.rhod[ijk[s]] / rho_stp;
+            if (!oi.aerosol_conc_factor.empty()) v = v * oi.aerosol_conc_factor[ijk[s] % size_t(oi.nz)];
+            if (n_dims > 0) v = v * cs.dv[ijk[s]] / real_t(oi.dx * oi.dy * oi.dz);
+            n[s] = n_t(v + real_t(0.5));
+          }
+          finalize_new(cs, ijk, n, rd3, kr.kappa);
+        }
+
+        // SDs of one fixed multiplicity, dry radii drawn from the spectrum's CDF tabulated with bin_precision = 1e-4 in ln(rd):
+        // init_SD_with_distros_const_multi.ipp:16-39 / _tail.ipp:16-40, init_count_num.ipp:67-104, init_dry_const_multi.ipp:25-83
+        void init_const_multi(const cell_state &cs, const kappa_rd_insol_t<real_t> &kr, const common::unary_function<real_t> &fun,
+                              n_t multi, const real_t *log_rd_min_forced)
+        {
+          const real_t bin = 1e-4;
+          real_t log_rd_min = 0, log_rd_max = 0;
+          dist_analysis_const_multi(fun, log_rd_min, log_rd_max);
+          if (log_rd_min_forced) log_rd_min = *log_rd_min_forced;
+          if (log_rd_min >= log_rd_max)
+          { std::ostringstream s; s << "Distribution analysis error: rd_min(" << std::exp(log_rd_min) << ") >= rd_max(" << std::exp(log_rd_max) << ")"; throw std::runtime_error(s.str()); }
+
+          // trapezoid integral of the spectrum -> concentration -> SDs per cell
+          const int n_bin = int((log_rd_max - log_rd_min) / bin);
+          real_t integral = (fun(log_rd_min) + fun(log_rd_max)) / 2.;
+          for (int i = 1; i < n_bin; ++i) integral += fun(log_rd_min + i * bin);
+          integral = integral * bin;
+          const std::vector<real_t> number = conc_to_number(cs, integral);
+          std::vector<size_t> count_num(n_cell);
+          for (size_t c = 0; c < n_cell; ++c) count_num[c] = size_t(number[c] / multi + real_t(0.5));
+          const std::vector<uint32_t> ijk = cells_of_new(count_num);
+          const size_t n_new = ijk.size();
+
+          const size_t n_pt = size_t((log_rd_max - log_rd_min) / bin + 1);
+          std::vector<real_t> cdf(n_pt);
+          for (size_t i = 0; i < n_pt; ++i) cdf[i] = real_t(1) * fun(log_rd_min + bin * i);
+          for (size_t i = 1; i < n_pt; ++i) cdf[i] = cdf[i - 1] + cdf[i];
+          const real_t total = cdf.back();
+          for (size_t i = 0; i < n_pt; ++i) cdf[i] = cdf[i] / total;
+
+          std::vector<real_t> rd3(n_new);
+          for (size_t s = 0; s < n_new; ++s)
+          {
+            const real_t pos = real_t(std::upper_bound(cdf.begin(), cdf.end(), draw_u01()) - cdf.begin());
+            rd3[s] = std::exp(3 * (log_rd_min + pos * bin));
+          }
+          finalize_new(cs, ijk, std::vector<n_t>(n_new, multi), rd3, kr.kappa);
+        }
+
+        void init_SD_with_distros(const cell_state &cs)                      // init_SD_with_distros.ipp:15-60
+        {
+          real_t tot_lnrd_rng = 0.;
+          if (oi.sd_conc > 0)
+            for (const auto &dd : oi.dry_distros)
+            {
+              real_t lo = 0, hi = 0, mult = 0;
+              dist_analysis_sd_conc(*dd.second, cs, lo, hi, mult);
+              tot_lnrd_rng += hi - lo;
+            }
+          for (const auto &dd : oi.dry_distros)
+          {
+            if (oi.sd_conc > 0)
+            {
+              real_t log_rd_max = 0;
+              init_sd_conc(cs, dd.first, *dd.second, tot_lnrd_rng, log_rd_max);
+              if (oi.sd_conc_large_tail) init_const_multi(cs, dd.first, *dd.second, 1, &log_rd_max);
+            }
+            if (oi.sd_const_multi > 0) init_const_multi(cs, dd.first, *dd.second, oi.sd_const_multi, nullptr);
+          }
+        }
+
+        // monodisperse batches: kappa -> { radius -> (STP concentration, SDs per cell) }: init_SD_with_sizes.ipp:16-76
+        void init_SD_with_sizes(const cell_state &cs)
+        {
+          for (const auto &species : oi.dry_sizes)
+            for (const auto &size : species.second)
+            {
+              const real_t radius = size.first, conc = size.second.first;
+              const int sd_count = size.second.second;
+              const std::vector<uint32_t> ijk = cells_of_new(std::vector<size_t>(n_cell, size_t(sd_count)));
+              const std::vector<real_t> number = conc_to_number(cs, conc);
+              std::vector<n_t> n(ijk.size());
+              for (size_t s = 0; s < ijk.size(); ++s) n[s] = n_t(number[ijk[s]] / sd_count + real_t(.5));   // init_n.ipp:147-162
+              finalize_new(cs, ijk, n, std::vector<real_t>(ijk.size(), radius * radius * radius), species.first.kappa);
+            }
         }
 
         // ---- time stepping ---------------------------------------------------------------------------------------

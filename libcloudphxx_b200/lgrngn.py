@@ -11,7 +11,7 @@ import os
 
 import numpy as np
 
-MAX_MODES, MAX_DISTROS, MAX_KPARAMS = 4, 4, 4
+MAX_MODES, MAX_DISTROS, MAX_KPARAMS, MAX_SIZES = 4, 4, 4, 16
 
 
 class backend_t:
@@ -41,6 +41,10 @@ class _Distro(C.Structure):
                 ("r0", C.c_double), ("n0", C.c_double)]
 
 
+class _DrySize(C.Structure):
+    _fields_ = [("kappa", C.c_double), ("rd_insol", C.c_double), ("radius", C.c_double), ("conc", C.c_double), ("count", C.c_int)]
+
+
 class _OptsInit(C.Structure):
     _fields_ = [("backend", C.c_int), ("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int),
                 ("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double), ("dt", C.c_double),
@@ -60,7 +64,10 @@ class _OptsInit(C.Structure):
                 ("open_side_walls", C.c_int), ("periodic_topbot_walls", C.c_int), ("variable_dt_switch", C.c_int),
                 ("th_dry", C.c_int), ("const_p", C.c_int), ("aerosol_independent_of_rhod", C.c_int),
                 ("n_distros", C.c_int), ("distros", _Distro * MAX_DISTROS),
-                ("n_w_LS", C.c_int), ("w_LS", C.POINTER(C.c_double))]
+                ("n_w_LS", C.c_int), ("w_LS", C.POINTER(C.c_double)),
+                ("sd_conc_large_tail", C.c_int), ("no_ccn_at_init", C.c_int),
+                ("n_dry_sizes", C.c_int), ("dry_sizes", _DrySize * MAX_SIZES),
+                ("n_aerosol_conc_factor", C.c_int), ("aerosol_conc_factor", C.POINTER(C.c_double))]
 
 
 class _Opts(C.Structure):
@@ -135,6 +142,10 @@ class Library:
         return Particles(self, backend, opts_init)
 
 
+_NOT_SCALAR = ("distros", "n_distros", "w_LS", "n_w_LS", "kernel_parameters", "n_kernel_parameters", "backend",
+               "dry_sizes", "n_dry_sizes", "aerosol_conc_factor", "n_aerosol_conc_factor")
+
+
 class OptsInit:
     """attribute bag with the defaults of opts_init_t (reference lgrngn/opts_init.hpp:194-249)"""
 
@@ -142,18 +153,20 @@ class OptsInit:
         c = _OptsInit()
         library.lib.lgc_opts_init_defaults(C.byref(c))
         for name, _ in _OptsInit._fields_:
-            if name in ("distros", "n_distros", "w_LS", "n_w_LS", "kernel_parameters", "n_kernel_parameters", "backend"):
+            if name in _NOT_SCALAR:
                 continue
             setattr(self, name, getattr(c, name))
         self.kernel_parameters = []
         self.dry_distros = []      # list of lognormal(...) / expvolume(...)
         self.w_LS = []
+        self.dry_sizes = {}        # {(kappa, rd_insol) or kappa: {radius: (STP concentration, SDs per cell)}}
+        self.aerosol_conc_factor = []
 
     def _pack(self, backend):
         c = _OptsInit()
         c.backend = int(backend)
         for name, _ in _OptsInit._fields_:
-            if name in ("distros", "n_distros", "w_LS", "n_w_LS", "kernel_parameters", "n_kernel_parameters", "backend"):
+            if name in _NOT_SCALAR:
                 continue
             setattr(c, name, getattr(self, name))
         kp = list(self.kernel_parameters)
@@ -170,11 +183,23 @@ class OptsInit:
                     cd.mean_r[m], cd.stdev[m], cd.n_tot[m] = mean_r, stdev, n_tot
             else:
                 cd.r0, cd.n0 = d["r0"], d["n0"]
-        keep = None
+        i = 0
+        for key, sizes in self.dry_sizes.items():
+            kappa, rd_insol = key if isinstance(key, tuple) else (key, 0.0)
+            for radius, (conc, count) in sizes.items():
+                ds = c.dry_sizes[i]
+                ds.kappa, ds.rd_insol, ds.radius, ds.conc, ds.count = kappa, rd_insol, radius, conc, int(count)
+                i += 1
+        c.n_dry_sizes = i
+        keep = []
         if len(self.w_LS):
-            keep = np.ascontiguousarray(self.w_LS, dtype=np.float64)
-            c.n_w_LS = keep.size
-            c.w_LS = keep.ctypes.data_as(C.POINTER(C.c_double))
+            keep.append(np.ascontiguousarray(self.w_LS, dtype=np.float64))
+            c.n_w_LS = keep[-1].size
+            c.w_LS = keep[-1].ctypes.data_as(C.POINTER(C.c_double))
+        if len(self.aerosol_conc_factor):
+            keep.append(np.ascontiguousarray(self.aerosol_conc_factor, dtype=np.float64))
+            c.n_aerosol_conc_factor = keep[-1].size
+            c.aerosol_conc_factor = keep[-1].ctypes.data_as(C.POINTER(C.c_double))
         return c, keep
 
 

@@ -13,7 +13,7 @@ namespace boost { namespace math { namespace tools {
     const int digits = std::numeric_limits<T>::digits;
     if (bits > digits / 2) bits = digits / 2;
     const T tol = std::ldexp(T(1), 1 - bits);
-    const T golden = T(0.3819660);
+    const T golden = T(0.3819660f);   // single-precision literal, as in Boost
     T x = hi, w = hi, v = hi, fx = f(x), fw = fx, fv = fx, step = 0, prev_step = 0;
     std::uintmax_t left = max_iter;
     while (left)

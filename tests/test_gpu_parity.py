@@ -30,6 +30,52 @@ def test_init_is_bit_identical_3d(ref, b200):
     S.run_pair(ref, b200, S.box_3d, 0, on_step=check, nx=4, ny=3, nz=5, sd_conc=16)
 
 
+def _variant(lib, kind):
+    oi, o, f = S.box_3d(lib, nx=4, ny=3, nz=5, sd_conc=16, n_sd_max=200000)
+    if kind == "const_multi":                       # init_SD_with_distros_const_multi.ipp, automatic ln(rd) range
+        oi.sd_conc, oi.sd_const_multi = 0, int(2e9)
+    elif kind == "const_multi_user_range":
+        oi.sd_conc, oi.sd_const_multi = 0, int(1e9)
+        oi.rd_min, oi.rd_max = 5e-9, 2e-6
+    elif kind == "large_tail":                      # init_SD_with_distros_tail.ipp
+        oi.sd_conc_large_tail = 1
+        oi.sd_conc = 256                            # the tail holds ~ 0.1 * sd_conc / ln(rd_max / rd_min) SDs per cell
+        oi.dry_distros = [L.lognormal(0.61, S.AEROSOL_ICICLE), L.lognormal(1.28, [(0.5e-6, 1.6, 2e3)])]
+    elif kind == "dry_sizes":                       # init_SD_with_sizes.ipp, next to a spectrum
+        oi.dry_sizes = {0.3: {0.1e-6: (30e6, 5), 0.5e-6: (1e6, 2)}, (0.9, 0.0): {1e-6: (2e5, 3)}}
+    elif kind == "dry_sizes_only":
+        oi.sd_conc = 0
+        oi.dry_distros = []
+        oi.dry_sizes = {0.61: {0.05e-6: (60e6, 8), 0.8e-6: (3e6, 4)}}
+    elif kind == "conc_factor":                     # init_n.ipp:96-107
+        oi.aerosol_independent_of_rhod = 1
+        oi.aerosol_conc_factor = [1.0, 0.5, 2.0, 0.25, 1.5]
+    elif kind == "sd_conc_user_range":
+        oi.rd_min, oi.rd_max = 1e-9, 5e-6
+    o.cond = 0
+    return oi, o, f
+
+
+@pytest.mark.parametrize("kind", ["const_multi", "const_multi_user_range", "large_tail", "dry_sizes", "dry_sizes_only", "conc_factor",
+                                  "sd_conc_user_range"])
+def test_init_variants(ref, b200, kind):
+    """every way the reference creates SDs at t=0 (sd_conc, sd_const_multi, large tail, dry_sizes, concentration profile):
+    identical attributes; then two steps of coalescence + transport stay exact (pure const-multi runs remove used-up SDs)"""
+    def check(step, p_r, p_n, f_r, f_n):
+        n_r, n_n = p_r.get_n(), p_n.get_n()
+        assert n_r.size == n_n.size and n_r.size > 0, (step, n_r.size, n_n.size)
+        assert np.array_equal(n_r, n_n), step
+        for k in ("rd3", "kappa", "x", "y"):
+            assert np.array_equal(p_r.get_attr(k), p_n.get_attr(k)), (k, step)
+        if step == -1:
+            assert np.array_equal(p_r.get_attr("rw2"), p_n.get_attr("rw2"))
+            assert np.array_equal(p_r.get_attr("z"), p_n.get_attr("z"))
+        else:
+            assert S.rel_err(p_r.get_attr("rw2"), p_n.get_attr("rw2")) < 1e-14, step
+            assert S.rel_err(p_r.get_attr("z"), p_n.get_attr("z")) < 1e-11, step
+    S.run_pair(ref, b200, lambda lib: _variant(lib, kind), 2, on_step=check)
+
+
 @pytest.mark.parametrize("n_sd", [2 ** 10, 2 ** 14])
 def test_golovin_box_exact(ref, b200, n_sd):
     """cfg1: multiplicities, wet and dry radii bit-identical after every step (Golovin kernel: only * + sqrt cbrt)"""
