@@ -65,6 +65,7 @@ def build_engine(force=False, verbose=True, extra=()):
             flags[flags.index("-fmad=false")] = "-fmad=true"
         if src == "lcx_cond.cu":
             flags += [f for f in os.environ.get("LCX_COND_DEFS", "").split() if f]
+        flags += [f for f in os.environ.get("LCX_DEFS_" + src.split(".")[0].upper(), "").split() if f]   # tuning experiments
         out = _run([NVCC] + flags + list(extra) + ["-c", s, "-o", o])
         return src, time.time() - t0, out
 

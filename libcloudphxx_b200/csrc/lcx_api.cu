@@ -82,7 +82,7 @@ lcx_engine::~lcx_engine()
   courant_x.release(); courant_y.release(); courant_z.release(); w_LS.release(); cell_off.release();
   vt0.release(); eff.release(); hist.release(); scan_tmp.release();
   for (int s = 0; s < 2; ++s) { for (int d = 0; d < 2; ++d) { mig_n[s][d].release(); mig_real[s][d].release(); } mig_key[s].release(); mig_val[s].release(); }
-  scalars.release(); red_partial.release();
+  scalars.release(); red_partial.release(); cell_tmp4.release();
   for (auto &r : prof) { cudaEventDestroy(r.t0); cudaEventDestroy(r.t1); }
   if (timer0) { cudaEventDestroy(timer0); cudaEventDestroy(timer1); }
   if (h_scalars) cudaFreeHost(h_scalars);
@@ -141,6 +141,7 @@ int lcx_create(const lcx_config *cfg, lcx_engine **out)
     e->th.alloc(n_cell); e->rv.alloc(n_cell); e->rhod.alloc(n_cell); e->p.alloc(n_cell); e->T.alloc(n_cell);
     e->RH.alloc(n_cell); e->eta.alloc(n_cell); e->dv.alloc(n_cell); e->lambda_D.alloc(n_cell); e->lambda_K.alloc(n_cell);
     e->drw_mom3.alloc(n_cell); e->rw_mom3.alloc(n_cell); e->count_mom.alloc(n_cell);
+    if (cfg->terminal_velocity == lcx::VT_BEARD77 || cfg->terminal_velocity == lcx::VT_BEARD77FAST) e->cell_tmp4.alloc(size_t(n_cell) * 4);
     if (cfg->allow_sstp_cond) { e->sstp_tmp_rv.alloc(n_cell); e->sstp_tmp_th.alloc(n_cell); e->sstp_tmp_rh.alloc(n_cell); }
     e->cell_off.alloc(n_cell + 2);
     const size_t h = size_t(g.halo_size);

@@ -56,6 +56,30 @@ namespace lcx
       vt[i] = vt_of(formula, r2, T[c], p[c], rhod[c], eta[c], vt0);
     }
 
+    // Beard (1977) variants: the altitude correction needs four per-cell numbers (two divisions, two square roots);
+    // they are evaluated once per cell here instead of once per SD, then k_vterm_beard77 does the per-droplet rest
+    __global__ void __launch_bounds__(TPB) k_beard77_cells(idx_t n_cell, const real_t *__restrict__ p, const real_t *__restrict__ rhod,
+                                                          const real_t *__restrict__ eta, beard77_cell<real_t> *__restrict__ out)
+    {
+      const idx_t c = blockIdx.x * TPB + threadIdx.x;
+      if (c < n_cell) out[c] = vt_beard77_cell_consts(p[c], rhod[c], eta[c]);
+    }
+
+    template <bool FAST>
+    __global__ void __launch_bounds__(TPB) k_vterm_beard77(size_t n_part, int only_invalid, const real_t *__restrict__ rw2, const idx_t *__restrict__ ijk,
+                                                          const beard77_cell<real_t> *__restrict__ cells, const real_t *__restrict__ vt0, real_t *__restrict__ vt)
+    {
+      const size_t i = size_t(blockIdx.x) * TPB + threadIdx.x;
+      if (i >= n_part) return;
+      const real_t r2 = rw2[i];
+      if (!(r2 > real_t(0))) return;
+      if (only_invalid && !(vt[i] == real_t(-1))) return;
+      const beard77_cell<real_t> k = cells[ijk[i]];
+      const real_t r = sqrt(r2);
+      const vt0_bins<real_t> bins;
+      vt[i] = vt_beard77_fact(r, k) * (FAST ? vt0[bins.bin_of(r2)] : vt_beard77_v0(r));
+    }
+
     // linear interpolation of the Eulerian state over condensation sub-steps: sstp_percell_step.ipp:7-47
     __global__ void __launch_bounds__(TPB) k_sstp_percell(idx_t n_cell, int step, real_t sstp, real_t *__restrict__ scl, real_t *__restrict__ tmp)
     {
@@ -101,6 +125,18 @@ namespace lcx
   {
     if (e->n_part == 0) return;
     sd_arrays &s = e->S();
+    const int formula = e->cfg.terminal_velocity;
+    if (formula == VT_BEARD77 || formula == VT_BEARD77FAST)
+    {
+      const grid_t &g = e->grid;
+      beard77_cell<real_t> *cells = reinterpret_cast<beard77_cell<real_t> *>(e->cell_tmp4.p);
+      LCX_LAUNCH(e, k_beard77_cells, div_up(g.n_cell, TPB), TPB, 0, g.n_cell, e->p.p, e->rhod.p, e->eta.p, cells);
+      if (formula == VT_BEARD77FAST)
+        LCX_LAUNCH(e, (k_vterm_beard77<true>), div_up(e->n_part, TPB), TPB, 0, e->n_part, int(only_invalid), s.rw2.p, s.ijk.p, cells, e->vt0.p, s.vt.p);
+      else
+        LCX_LAUNCH(e, (k_vterm_beard77<false>), div_up(e->n_part, TPB), TPB, 0, e->n_part, int(only_invalid), s.rw2.p, s.ijk.p, cells, e->vt0.p, s.vt.p);
+      return;
+    }
     LCX_LAUNCH(e, k_vterm, div_up(e->n_part, TPB), TPB, 0, e->n_part, e->cfg.terminal_velocity, int(only_invalid),
                s.rw2.p, s.ijk.p, e->T.p, e->p.p, e->rhod.p, e->eta.p, e->vt0.p, s.vt.p);
   }

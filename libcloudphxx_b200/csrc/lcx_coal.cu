@@ -7,8 +7,9 @@
 // The reference's candidate pairs are (2k, 2k+1) of each cell's SDs ordered by (random key un, storage index).
 // SDs are physically grouped by cell here, so that order is a per-cell sort of the composite key
 // (un[sid] << 32 | sid), which is unique - no dependence on the physical order inside the cell:
-//   * small cells (max population <= 256): 16 lanes per cell (two cells per warp); keys staged in shared memory, rank
-//     of each SD by counting smaller keys (O(m^2/16) per lane, m ~ 40), pairs processed by the lanes;
+//   * small cells (max population <= 256): 16 lanes per cell (two cells per warp); random keys staged in shared memory,
+//     rank of each SD by counting smaller keys (four per load), ties re-ranked with the storage index, pairs processed
+//     by the lanes;
 //   * big cells (0-D boxes, coarse grids): global LSD radix sort by sid, un, cell (lcx_sort.cu), then one thread
 //     per candidate pair.
 // Random numbers come from an injected stream (parity with the reference's mt19937 draw order: un by storage
@@ -62,8 +63,7 @@ namespace lcx
         if (mode == LCX_RNG_INJECT) return u01[pos];
         uint32_t c[4] = {pos, 1u, uint32_t(call), uint32_t(call >> 32)};
         philox4x32_10(c, philox_key{uint32_t(seed), uint32_t(seed >> 32)});
-        // 53-bit mantissa from two words, [0,1)
-        const uint64_t bits = (uint64_t(c[0]) << 21) ^ (uint64_t(c[1]) >> 11);
+        const uint64_t bits = (uint64_t(c[0]) << 21) ^ (uint64_t(c[1]) >> 11);      // 53-bit mantissa from two words, [0,1)
         return real_t(bits & ((1ull << 53) - 1)) * real_t(1.0 / 9007199254740992.0);
       }
     };
@@ -147,37 +147,107 @@ namespace lcx
     }
 
     // ---- small cells: 16 lanes per cell -------------------------------------------------------------------
+    // Pair order = rank of (un, sid) inside the cell.  Ranks are counted on the 32-bit random key alone, four keys per
+    // shared-memory load; two SDs of a cell drawing the same key (about once per 10^7 cells) leave a slot of the
+    // permutation unfilled, which is detected and that cell re-ranked with the storage index as tie-break.
+    // Philox mode draws per cell: block q of cell c gives four keys (q < 2^31) or the u01 of two pairs (q >= 2^31).
+    constexpr int KEY_PAD = 4;               // shifts the two cells of a warp to different banks for the 16-byte loads
+
+    __device__ __forceinline__ void philox_cell_block(const rng_src &rng, uint32_t c, uint32_t q, uint32_t (&w)[4])
+    {
+      w[0] = c; w[1] = q; w[2] = uint32_t(rng.call); w[3] = uint32_t(rng.call >> 32);
+      philox4x32_10(w, philox_key{uint32_t(rng.seed), uint32_t(rng.seed >> 32)});
+    }
+
+    __device__ __forceinline__ real_t u01_from_words(uint32_t w0, uint32_t w1)      // 53-bit mantissa from two words, [0,1)
+    {
+      const uint64_t bits = (uint64_t(w0) << 21) ^ (uint64_t(w1) >> 11);
+      return real_t(bits & ((1ull << 53) - 1)) * real_t(1.0 / 9007199254740992.0);
+    }
+
     __global__ void __launch_bounds__(TPB) k_coal_small(idx_t n_cell, const uint32_t *__restrict__ off, const idx_t *__restrict__ sid,
                                                        rng_src rng, coal_ctx cx)
     {
-      __shared__ unsigned long long skey[GROUPS][SMALL_MAX];
+      __shared__ __align__(16) uint32_t skey[GROUPS][SMALL_MAX + KEY_PAD];
       __shared__ unsigned short sperm[GROUPS][SMALL_MAX];
       const int grp = threadIdx.x / CELL_LANES, l = threadIdx.x % CELL_LANES;
       const idx_t c = blockIdx.x * GROUPS + grp;
       uint32_t b = 0, m = 0;
       if (c < n_cell) { b = off[c]; m = off[c + 1] - b; }
       if (m < 2) m = 0;                                    // nothing to pair; keep the lanes for the warp-wide syncs
-      for (uint32_t e = l; e < m; e += CELL_LANES)
+      const uint32_t m4 = (m + 3u) & ~3u;
+      uint32_t *const key = skey[grp];
+      unsigned short *const perm = sperm[grp];
+      const bool philox = rng.mode != LCX_RNG_INJECT;
+
+      // random sort keys, padded to a multiple of four with the largest value (never "smaller than" anything)
+      if (philox)
+        for (uint32_t q = l; 4 * q < m; q += CELL_LANES)
+        {
+          uint32_t w[4];
+          philox_cell_block(rng, c, q, w);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) if (4 * q + i >= m) w[i] = 0xffffffffu;
+          *reinterpret_cast<uint4 *>(key + 4 * q) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      else
+        for (uint32_t e = l; e < m4; e += CELL_LANES) key[e] = e < m ? rng.un[sid[b + e]] : 0xffffffffu;
+      for (uint32_t e = l; e < m; e += CELL_LANES) perm[e] = 0xffffu;
+      __syncwarp();
+
+      // rank = number of smaller keys; a lane ranks up to four of its SDs per sweep over the keys
+      for (uint32_t e0 = l; e0 < m; e0 += 4 * CELL_LANES)
       {
-        const uint32_t s = sid[b + e];
-        skey[grp][e] = ((unsigned long long)rng.get_un(s) << 32) | s;
+        uint32_t mine[4], r[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const uint32_t e = e0 + i * CELL_LANES; mine[i] = e < m ? key[e] : 0u; }
+        for (uint32_t j = 0; j < m4; j += 4)
+        {
+          const uint4 k = *reinterpret_cast<const uint4 *>(key + j);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) r[i] += (k.x < mine[i]) + (k.y < mine[i]) + (k.z < mine[i]) + (k.w < mine[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const uint32_t e = e0 + i * CELL_LANES; if (e < m) perm[r[i]] = (unsigned short)e; }
       }
       __syncwarp();
-      for (uint32_t e = l; e < m; e += CELL_LANES)
+
+      // equal keys inside the cell collide on one slot and leave another empty
+      bool hole = false;
+      for (uint32_t e = l; e < m; e += CELL_LANES) hole |= perm[e] == 0xffffu;
+      const unsigned group_lanes = 0xffffu << (threadIdx.x & 16);
+      if (__ballot_sync(0xffffffffu, hole) & group_lanes)
       {
-        const unsigned long long mine = skey[grp][e];
-        uint32_t r = 0;
-        for (uint32_t j = 0; j < m; ++j) r += (skey[grp][j] < mine);
-        sperm[grp][r] = (unsigned short)e;
+        for (uint32_t e = l; e < m; e += CELL_LANES)
+        {
+          const uint32_t mine = key[e], ms = sid[b + e];
+          uint32_t r = 0;
+          for (uint32_t j = 0; j < m; ++j) r += (key[j] < mine) || (key[j] == mine && sid[b + j] < ms);
+          perm[r] = (unsigned short)e;
+        }
       }
       __syncwarp();
+
+      // u01 of the candidate pairs: two words each, written over the keys
+      if (philox)
+        for (uint32_t q = l; 4 * q < m; q += CELL_LANES)     // m/2 pairs x 2 words = m words
+        {
+          uint32_t w[4];
+          philox_cell_block(rng, c, q | 0x80000000u, w);
+          *reinterpret_cast<uint4 *>(key + 4 * q) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      __syncwarp();
+
       unsigned long long n_coll = 0, n_pairs = 0;
       if (m)
       {
         const real_t scl = coal_scale_factor<real_t>(n_t(m));
         const real_t dv_c = cx.dv[c];
         for (uint32_t k = l; 2 * k + 1 < m; k += CELL_LANES)
-          try_pair(cx, b + sperm[grp][2 * k], b + sperm[grp][2 * k + 1], rng.get_u01(b + 2 * k), scl, dv_c, n_coll, n_pairs);
+        {
+          const real_t u01 = philox ? u01_from_words(key[2 * k], key[2 * k + 1]) : rng.u01[b + 2 * k];
+          try_pair(cx, b + perm[2 * k], b + perm[2 * k + 1], u01, scl, dv_c, n_coll, n_pairs);
+        }
       }
       flush_stats(cx, n_coll, n_pairs);
     }

@@ -15,8 +15,8 @@
 // The root solve is FP64-compute bound (~4.6 growth-rate evaluations per SD); the growth law is therefore evaluated
 // in the single-quotient form of lcx_physics.h (growth_fast) by default; LCX_COND_EXACT=1 selects the operation-by-
 // operation transcription of the reference's formula (growth_fn) for cross-checking.
-#ifndef LCX_NO_FAST_DIV
-#define LCX_FAST_DIV 1      // see lcx_physics.h: quotients inside the root solve need not be correctly rounded
+#ifndef LCX_NO_FAST_MATH
+#define LCX_FAST_MATH 1      // see lcx_physics.h: quotients inside the root solve need not be correctly rounded
 #endif
 #include "lcx_engine.cuh"
 

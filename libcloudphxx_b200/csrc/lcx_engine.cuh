@@ -121,6 +121,7 @@ struct lcx_engine
   lcx::dbuf<lcx::real_t> th, rv, rhod, p, T, RH, eta, dv, lambda_D, lambda_K;
   lcx::dbuf<lcx::real_t> sstp_tmp_rv, sstp_tmp_th, sstp_tmp_rh;
   lcx::dbuf<lcx::real_t> drw_mom3, rw_mom3, count_mom, mom_partial;
+  lcx::dbuf<lcx::real_t> cell_tmp4;        // 4 reals per cell: per-cell parts of the Beard (1977) fall-speed correction
   lcx::dbuf<lcx::real_t> courant_x, courant_y, courant_z, w_LS;
   lcx::dbuf<uint32_t> cell_off;  // n_cell + 2 entries: start of each cell's segment; [n_cell] = n_part, [n_cell+1] = total incl. dead
 

@@ -31,11 +31,11 @@ namespace lcx
   enum { AS_UNDEFINED = 0, AS_IMPLICIT, AS_EULER, AS_PRED_CORR };
   enum { RH_PV_CC = 0, RH_RV_CC, RH_PV_TET, RH_RV_TET };
 
-  // Division inside the condensation root solve.  There every quotient is either the next trial abscissa or part of the
+  // Arithmetic inside the condensation root solve.  There every quotient is either the next trial abscissa or part of the
   // residual whose root is wanted to 2^-15 only, so a correctly rounded result buys nothing: a translation unit may define
-  // LCX_FAST_DIV to get reciprocal-approximation + two Newton steps + one residual correction on the device (error <= 1 ulp,
+  // LCX_FAST_MATH to get reciprocal-approximation + two Newton steps + one residual correction on the device (error <= 1 ulp,
   // no special-case branch), about 1/3 of the instructions of the IEEE division sequence.  Everywhere else "/" is IEEE.
-#if defined(LCX_FAST_DIV) && defined(__CUDA_ARCH__)
+#if defined(LCX_FAST_MATH) && defined(__CUDA_ARCH__)
   __device__ __forceinline__ double lcx_div(double a, double b)
   {
     double r;
@@ -46,8 +46,45 @@ namespace lcx
     return fma(fma(-b, q, a), r, q);
   }
   __device__ __forceinline__ float lcx_div(float a, float b) { return a / b; }
+  // 1/sqrt(x), x normal and positive: hardware seed + two Newton steps (<= 1 ulp; the library routine spends ~50
+  // instructions on the same thing because it also serves subnormals, zeros and infinities)
+  __device__ __forceinline__ double lcx_rsqrt(double x)
+  {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double hx = 0.5 * x;
+    r = fma(r, fma(-hx * r, r, 0.5), r);
+    r = fma(r, fma(-hx * r, r, 0.5), r);
+    return r;
+  }
+  __device__ __forceinline__ float lcx_rsqrt(float x) { return rsqrtf(x); }
+  // exp(x) for the Kelvin term, 0 <= x < 1/8 (x = A / rw, A ~ 1e-9 m): Taylor polynomial of degree 11, remainder < 3e-20
+  __device__ __forceinline__ double lcx_exp_small(double x)
+  {
+    if (!(x >= 0 && x < 0.125)) return exp(x);
+    double p = 1.0 / 39916800.0;
+    p = fma(p, x, 1.0 / 3628800.0); p = fma(p, x, 1.0 / 362880.0); p = fma(p, x, 1.0 / 40320.0); p = fma(p, x, 1.0 / 5040.0);
+    p = fma(p, x, 1.0 / 720.0); p = fma(p, x, 1.0 / 120.0); p = fma(p, x, 1.0 / 24.0); p = fma(p, x, 1.0 / 6.0);
+    p = fma(p, x, 0.5); p = fma(p, x, 1.0); p = fma(p, x, 1.0);
+    return p;
+  }
+  __device__ __forceinline__ float lcx_exp_small(float x) { return exp(x); }
+  // cbrt(y), 1 <= y < 1e30: single-precision seed, two Newton steps with the seed's slope (error 1e-7 -> 1e-14 -> 1e-21)
+  __device__ __forceinline__ double lcx_cbrt_ge1(double y)
+  {
+    const float c0 = cbrtf(float(y));
+    const double s = double(1.0f / (3.0f * c0 * c0));
+    double c = double(c0);
+    c = fma(-fma(c * c, c, -y), s, c);
+    c = fma(-fma(c * c, c, -y), s, c);
+    return c;
+  }
+  __device__ __forceinline__ float lcx_cbrt_ge1(float y) { return cbrtf(y); }
 #else
   template <class T> LCX_HD T lcx_div(T a, T b) { return a / b; }
+  template <class T> LCX_HD T lcx_rsqrt(T x) { return T(1) / sqrt(x); }
+  template <class T> LCX_HD T lcx_exp_small(T x) { return exp(x); }
+  template <class T> LCX_HD T lcx_cbrt_ge1(T y) { return cbrt(y); }
 #endif
 
   template <class T> LCX_HD T tmin(T a, T b) { return (b < a) ? b : a; }   // std::min semantics
@@ -669,11 +706,7 @@ namespace lcx
 
     LCX_HD real_t drw2_dt(real_t rw2) const
     {
-#if defined(__CUDA_ARCH__)
-      const real_t inv_rw = rsqrt(rw2);
-#else
-      const real_t inv_rw = real_t(1) / sqrt(rw2);
-#endif
+      const real_t inv_rw = lcx_rsqrt(rw2);
       const real_t rw = rw2 * inv_rw;
       const real_t rw3 = rw2 * rw;
       const real_t Re = vt_cRe * rw;
@@ -688,7 +721,7 @@ namespace lcx
         const real_t x = Re * nu[q];
         const real_t cb = (fabs(x) < real_t(1e-4))
           ? real_t(1) + x * (real_t(1. / 3) - x * (real_t(1. / 9) - x * real_t(5. / 81)))
-          : real_t(cbrt(real_t(1) + x));
+          : real_t(lcx_cbrt_ge1(real_t(1) + x));
         nu[q] = real_t(1) + cb * boost;
       }
       const real_t Sh = nu[0], Nu = nu[1];
@@ -696,7 +729,7 @@ namespace lcx
       const real_t bDn = real_t(1) + KnD, bDd = real_t(1) + KnD * (real_t(1.71) + real_t(1.33) * KnD);
       const real_t bKn = real_t(1) + KnK, bKd = real_t(1) + KnK * (real_t(1.71) + real_t(1.33) * KnK);
       const real_t awn = rw3 - rd3, awd = rw3 - rd3_dry;
-      const real_t klv = exp(k.A * inv_rw);
+      const real_t klv = lcx_exp_small(k.A * inv_rw);
       const real_t tD = bDn * Sh, tK = bKn * Nu;
       const real_t num = (awd - awn * klv * k.inv_RH) * (tD * tK);
       const real_t den = awd * (k.X * bDd * tK + k.Y * bKd * tD);
@@ -774,6 +807,30 @@ namespace lcx
     const real_t eps_c = sqrt(c::rho_stp() / rhoa) - 1;
     return real_t(1.104) * eps_s
       + ((real_t(1.058) * eps_c - real_t(1.104) * eps_s) * (real_t(5.52) + log(2 * 100 * r)) / real_t(5.01)) + 1;
+  }
+  // The same factor with its per-cell sub-expressions evaluated once per cell (identical operations in identical
+  // order, so identical results): what depends on the droplet is l / r, l_0 / r and log(r) only.
+  template <class real_t>
+  struct beard77_cell { real_t l, eta_ratio, eps_s, eps_c; };
+  template <class real_t>
+  LCX_HD beard77_cell<real_t> vt_beard77_cell_consts(real_t p, real_t rhoa, real_t eta)
+  {
+    typedef cst<real_t> c;
+    const real_t eta_0(1.818e-5), l_0(6.62e-8);
+    beard77_cell<real_t> k;
+    k.l = l_0 * (eta / eta_0) * sqrt(c::p_stp() / p * c::rho_stp() / rhoa);
+    k.eta_ratio = eta_0 / eta;
+    k.eps_s = (eta_0 / eta) - 1;
+    k.eps_c = sqrt(c::rho_stp() / rhoa) - 1;
+    return k;
+  }
+  template <class real_t>
+  LCX_HD real_t vt_beard77_fact(real_t r, const beard77_cell<real_t> &k)
+  {
+    if (r <= real_t(20e-6))
+      return k.eta_ratio * (1 + real_t(1.255) * (k.l / r)) / (1 + real_t(1.255) * (real_t(6.62e-8) / r));
+    return real_t(1.104) * k.eps_s
+      + ((real_t(1.058) * k.eps_c - real_t(1.104) * k.eps_s) * (real_t(5.52) + log(2 * 100 * r)) / real_t(5.01)) + 1;
   }
   // Beard (1976): vterm.hpp:168-221
   template <class real_t>

@@ -13,6 +13,8 @@
 // so positions agree bit for bit (compile with -fmad=false).
 #include "lcx_engine.cuh"
 
+#include <cstdlib>
+
 namespace lcx
 {
   namespace
@@ -102,7 +104,10 @@ namespace lcx
       }
     }
 
-    __global__ void __launch_bounds__(TPB) k_transport(size_t n_part, tr_params P,
+#ifndef LCX_TR_MINB
+#define LCX_TR_MINB 6      // latency-bound kernel: 40 registers, 48 resident warps; measured best of {3,4,5,6}
+#endif
+    __global__ void __launch_bounds__(TPB, LCX_TR_MINB) k_transport(size_t n_part, tr_params P,
                                                       real_t *__restrict__ xs, real_t *__restrict__ ys, real_t *__restrict__ zs,
                                                       const real_t *__restrict__ vt, const idx_t *__restrict__ ijk, n_t *__restrict__ ns,
                                                       const real_t *__restrict__ rw2, const real_t *__restrict__ rd3,
@@ -356,7 +361,8 @@ namespace lcx
     P.bcond_lft = e->cfg.bcond_lft; P.bcond_rgt = e->cfg.bcond_rgt;
     if (P.subs && e->w_LS.n < size_t(e->grid.nz)) throw error("subsidence requested but no w_LS profile was set");
     if (P.scheme == AS_PRED_CORR && e->grid.halo_size != 2) throw error("predictor-corrector advection needs a 2-cell Courant halo");
-    const unsigned blocks = unsigned(std::min<size_t>(div_up(n, TPB), size_t(148) * 16));   // 148 SMs x 16 resident CTAs
+    static const int ctas_per_sm = [] { const char *v = std::getenv("LCX_TR_CTAS"); return v ? std::atoi(v) : 48; }();
+    const unsigned blocks = unsigned(ctas_per_sm > 0 ? std::min<size_t>(div_up(n, TPB), size_t(148) * ctas_per_sm) : div_up(n, TPB));
     if (e->red_partial.n < size_t(blocks) * 4) { LCX_CUDA(cudaStreamSynchronize(e->stream)); e->red_partial.alloc(size_t(blocks) * 4 + 1024); }
     LCX_LAUNCH(e, k_transport, blocks, TPB, 0, n, P, s.x.p, s.y.p, s.z.p, s.vt.p, s.ijk.p, s.n.p, s.rw2.p, s.rd3.p,
                e->courant_x.p, e->courant_y.p, e->courant_z.p, e->w_LS.p, e->flag.p, e->red_partial.p, e->key[0].p, e->val[0].p);
