@@ -113,6 +113,12 @@ void *lcx_stream(lcx_engine *e);                                /* cudaStream_t 
 int  lcx_field_size(lcx_engine *e, int field, int64_t *count);  /* init_sync.ipp:13-52                       */
 int  lcx_cells_set(lcx_engine *e, int field, const void *src, int64_t count, int src_on_device);  /* impl_sync.ipp:15-40 */
 int  lcx_cells_get(lcx_engine *e, int field, void *dst, int64_t count);                            /* impl_sync.ipp:42-68 */
+/* contiguous pieces of a field, queued on the engine's stream without waiting (the caller ends a batch with lcx_sync);  */
+/* host memory may be pageable or pinned - pinned memory (lcx_host_alloc or the caller's own) moves at full PCIe rate      */
+int  lcx_cells_set_part(lcx_engine *e, int field, int64_t offset, const void *src, int64_t count);
+int  lcx_cells_get_part(lcx_engine *e, int field, int64_t offset, void *dst, int64_t count);
+int  lcx_host_alloc(size_t bytes, void **out);                  /* page-locked staging memory for the host layer          */
+int  lcx_host_free(void *p);
 int  lcx_set_vt0_table(lcx_engine *e, const void *table, int n);            /* init_vterm.ipp:36-59          */
 int  lcx_set_efficiencies(lcx_engine *e, const void *table, int64_t n);     /* init_kernel.ipp:60-145        */
 

@@ -222,6 +222,34 @@ int lcx_cells_get(lcx_engine *e, int field, void *dst, int64_t count)
   });
 }
 
+int lcx_cells_set_part(lcx_engine *e, int field, int64_t offset, const void *src, int64_t count)
+{
+  return guarded([&] {
+    use_device(e);
+    const field_ref f = field_of(e, field);
+    if (offset < 0 || count < 0 || size_t(offset + count) > f.n) throw lcx::error("lcx_cells_set_part: range outside field " + std::to_string(field));
+    LCX_CUDA(cudaMemcpyAsync(static_cast<lcx::real_t *>(f.p) + offset, src, size_t(count) * sizeof(lcx::real_t), cudaMemcpyHostToDevice, e->stream));
+  });
+}
+
+int lcx_cells_get_part(lcx_engine *e, int field, int64_t offset, void *dst, int64_t count)
+{
+  return guarded([&] {
+    use_device(e);
+    const field_ref f = field_of(e, field);
+    if (offset < 0 || count < 0 || size_t(offset + count) > f.n) throw lcx::error("lcx_cells_get_part: range outside field " + std::to_string(field));
+    LCX_CUDA(cudaMemcpyAsync(dst, static_cast<const lcx::real_t *>(f.p) + offset, size_t(count) * sizeof(lcx::real_t), cudaMemcpyDeviceToHost, e->stream));
+  });
+}
+
+int lcx_host_alloc(size_t bytes, void **out)
+{
+  *out = nullptr;
+  return guarded([&] { LCX_CUDA(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault)); });
+}
+
+int lcx_host_free(void *p) { return guarded([&] { if (p) LCX_CUDA(cudaFreeHost(p)); }); }
+
 int lcx_set_vt0_table(lcx_engine *e, const void *table, int n)
 {
   return guarded([&] {

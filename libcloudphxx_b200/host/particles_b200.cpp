@@ -134,9 +134,30 @@ namespace libcloudphxx
         std::vector<uint32_t> un_host;
         std::vector<real_t> u01_host;
 
-        struct map_t { std::vector<long> l2e; };
+        // l2e[q] = element of the caller's array that feeds cell q; runs = the same map as maximal contiguous pieces.
+        // Few runs (contiguous arrays: 1 for scalars, 3 for a Courant field with its periodic halo) are copied straight
+        // between the caller's memory and the device; anything else goes through a page-locked staging buffer.
+        struct run_t { long dst, src, len; };
+        struct map_t
+        {
+          std::vector<long> l2e;
+          std::vector<run_t> runs;
+          real_t *pinned = nullptr;
+          bool direct() const { return runs.size() <= 16; }
+          void find_runs()
+          {
+            runs.clear();
+            for (size_t q = 0; q < l2e.size(); ++q)
+            {
+              if (!runs.empty() && l2e[q] == runs.back().src + runs.back().len) ++runs.back().len;
+              else runs.push_back(run_t{long(q), l2e[q], 1});
+            }
+          }
+          ~map_t() { if (pinned) lcx_host_free(pinned); }
+        };
         map_t m_th, m_rv, m_rhod, m_p, m_cx, m_cy, m_cz;
-        std::vector<real_t> stage, outbuf_host;
+        std::vector<real_t> outbuf_host;
+        std::vector<std::pair<const map_t *, real_t *>> pending_out;
         std::map<common::output_t, real_t> puddle0;
 
         slab(const opts_init_t<real_t> &o, std::pair<int, int> bc, int n_x_tot_) : oi(o), bcond(bc)
@@ -285,23 +306,53 @@ namespace libcloudphxx
           const long n_tot = max_stride_n_cell * max_stride;
           if (n_dims > 0)
             for (long &l : m.l2e) { if (l >= n_tot) l -= n_tot; else if (l < 0) l += n_tot; }
+          m.find_runs();
+          if (!m.direct() && !m.pinned)
+          {
+            void *ptr = nullptr;
+            chk(lcx_host_alloc(m.l2e.size() * sizeof(real_t), &ptr));
+            m.pinned = static_cast<real_t *>(ptr);
+          }
         }
 
+        // both directions only queue the copies; the caller ends the batch with finish_transfers()
         void sync_in_field(const arrinfo_t<real_t> &from, const map_t &m, int field)   // impl_sync.ipp:15-40
         {
           if (from.is_null()) return;
-          stage.resize(m.l2e.size());
           const real_t *src = from.data;
-          for (size_t q = 0; q < m.l2e.size(); ++q) stage[q] = src[m.l2e[q]];
-          chk(lcx_cells_set(e, field, stage.data(), int64_t(stage.size()), 0));
+          if (m.direct())
+          {
+            for (const run_t &r : m.runs) chk(lcx_cells_set_part(e, field, r.dst, src + r.src, r.len));
+            return;
+          }
+          const long n = long(m.l2e.size());
+#pragma omp parallel for schedule(static)
+          for (long q = 0; q < n; ++q) m.pinned[q] = src[m.l2e[size_t(q)]];
+          chk(lcx_cells_set_part(e, field, 0, m.pinned, n));
         }
         void sync_out_field(int field, const map_t &m, arrinfo_t<real_t> &to)           // impl_sync.ipp:42-68
         {
           if (to.is_null()) return;
-          stage.resize(m.l2e.size());
-          chk(lcx_cells_get(e, field, stage.data(), int64_t(stage.size())));
-          real_t *dst = to.data;
-          for (size_t q = 0; q < m.l2e.size(); ++q) dst[m.l2e[q]] = stage[q];
+          if (m.direct())
+          {
+            for (const run_t &r : m.runs) chk(lcx_cells_get_part(e, field, r.dst, to.data + r.src, r.len));
+            return;
+          }
+          chk(lcx_cells_get_part(e, field, 0, m.pinned, int64_t(m.l2e.size())));
+          pending_out.push_back(std::make_pair(&m, to.data));
+        }
+        void finish_transfers()
+        {
+          chk(lcx_sync(e));
+          for (const auto &po : pending_out)
+          {
+            const map_t &m = *po.first;
+            real_t *dst = po.second;
+            const long n = long(m.l2e.size());
+#pragma omp parallel for schedule(static)
+            for (long q = 0; q < n; ++q) dst[m.l2e[size_t(q)]] = m.pinned[q];
+          }
+          pending_out.clear();
         }
 
         // ---- engine creation ------------------------------------------------------------------------------------
@@ -392,6 +443,7 @@ namespace libcloudphxx
           sync_in_field(cx, m_cx, LCX_F_COURANT_X);
           sync_in_field(cy, m_cy, LCX_F_COURANT_Y);
           sync_in_field(cz, m_cz, LCX_F_COURANT_Z);
+          finish_transfers();
           if (oi.subs_switch) chk(lcx_cells_set(e, LCX_F_W_LS, oi.w_LS.data(), int64_t(oi.w_LS.size()), 0));
 
           chk(lcx_hskpng_Tpr(e));
@@ -769,12 +821,10 @@ namespace libcloudphxx
           sync_in_field(cx, m_cx, LCX_F_COURANT_X);
           sync_in_field(cy, m_cy, LCX_F_COURANT_Y);
           sync_in_field(cz, m_cz, LCX_F_COURANT_Z);
+          finish_transfers();          // the caller may overwrite its arrays as soon as this returns
           // |C_x| > 2 would leave the 2-cell halo of the predictor-corrector scheme: fall back to Euler for this step
           if (oi.adve_scheme == as_t::pred_corr && !cx.is_null())
           {
-            real_t mn = std::numeric_limits<real_t>::max(), mx = -mn;
-            for (const real_t v : stage) { mn = std::min(mn, v); mx = std::max(mx, v); }
-            (void)mn; (void)mx;
             real_t cmin = std::numeric_limits<real_t>::max(), cmax = -cmin;
             for (const long l : m_cx.l2e) { cmin = std::min(cmin, cx.data[l]); cmax = std::max(cmax, cx.data[l]); }
             if (!(cmin >= real_t(-2.)) || !(cmax <= real_t(2.))) adve_scheme = as_t::euler;
@@ -812,6 +862,7 @@ namespace libcloudphxx
             chk(lcx_sstp_save(e));
             sync_out_field(LCX_F_TH, m_th, th);
             sync_out_field(LCX_F_RV, m_rv, rv);
+            finish_transfers();
           }
           if (opts.chem_dsl || opts.chem_dsc || opts.chem_rct)
             throw std::runtime_error("libcloudph++: all chemistry was switched off in opts_init");

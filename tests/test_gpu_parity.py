@@ -291,3 +291,26 @@ def test_diagnostics_match(ref, b200):
     pa, pb = p_r.diag_puddle(), p_n.diag_puddle()
     for k in ("liquid_volume", "dry_volume", "particle_number", "liquid_number"):
         assert abs(pa[k] - pb[k]) <= 1e-4 * max(abs(pa[k]), 1e-300), k
+
+
+def test_strided_eulerian_arrays(b200):
+    """fields living inside larger arrays (halo-padded model arrays: thousands of contiguous pieces) take the page-locked
+    staging path; contiguous arrays are copied in place - both must give the same run, including th/rv written back"""
+    def run(padded):
+        oi, o, f = S.box_3d(b200, nx=6, ny=20, nz=8, sd_conc=8, rain_mode=True)
+        if padded:
+            for k in list(f):
+                big = np.full(tuple(np.array(f[k].shape) + (4, 2, 0)), np.nan)
+                view = big[2:2 + f[k].shape[0], 1:1 + f[k].shape[1], :]
+                view[...] = f[k]
+                f[k] = view
+                assert not view.flags["C_CONTIGUOUS"]
+        p = b200.factory(L.backend_t.CUDA, oi)
+        p.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
+        for _ in range(3):
+            p.step_sync(o, f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"])
+            p.step_async(o)
+        return p.get_n(), p.get_attr("rw2"), p.get_attr("x"), np.array(f["th"]), np.array(f["rv"])
+    a, b = run(False), run(True)
+    for u, v in zip(a, b):
+        assert np.array_equal(u, v)
