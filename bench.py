@@ -35,7 +35,7 @@ KERNEL_BYTES = {              # algorithmic bytes per SD per launch of the indiv
     "k_cond_cells": 48.0,      # rw2 r+w, rd3, kpa, vt, n (8 B each); the cell fields are 1/40 of that
     "k_cond": 52.0, "k_coal_small": 76.0, "k_coal_big": 76.0, "k_transport": 64.0, "k_gather": 136.0,
     "k_radix_scatter": 16.0, "k_radix_hist": 4.0, "(k_cell_reduce_small<Term, IS_MAX>)": 20.0,
-    "k_vterm": 24.0, "k_make_keys": 40.0,
+    "k_vterm": 24.0, "k_make_keys": 40.0, "k_cell_offsets": 4.0,
 }
 
 
@@ -43,6 +43,17 @@ def kernel_bytes(name):
     """profile names carry template arguments and parentheses (e.g. "(k_cond_cells<false>)"): longest key contained in the name"""
     hits = [k for k in KERNEL_BYTES if k.strip("()").split("<")[0] in name]
     return KERNEL_BYTES[max(hits, key=len)] if hits else 0.0
+
+
+def traffic_of(name, n_sd):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture (profiles/):
+    recorded per SD there because the capture ran on a smaller box; scaled to this launch's SD count"""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    table = json.load(open(p))["dram_bytes_per_sd"]
+    hits = [k for k in table if k in name]
+    return table[max(hits, key=len)] * n_sd if hits else None
 
 
 def peaks():
@@ -164,6 +175,11 @@ def run_b200(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = L.b200()
+    if world > 1:       # torchrun exports OMP_NUM_THREADS=1; the host-side initialisation wants its share of the cores
+        try:
+            C.CDLL("libgomp.so.1").omp_set_num_threads(max(1, (os.cpu_count() or 1) // world))
+        except OSError:
+            pass
     lib.lib.lgrngn_b200_set_rng_mode.argtypes = [C.c_int]
     lib.lib.lgrngn_b200_set_rng_mode(0)            # Philox in the kernels (the parity tests use the mt19937 replay)
     nx, ny, nz = args.nx, args.ny, args.nz
@@ -270,9 +286,13 @@ def run_b200(args):
             peak, src = peaks()
             achieved = per_sd * n_live / (t_ms / n_l * 1e-3) / 1e9 if per_sd else None
             roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "peak_source": src, "unit": "GB/s",
-                        "frac": (achieved / peak) if achieved else None, "traffic": None,
+                        "frac": (achieved / peak) if achieved else None, "traffic": traffic_of(name, n_live),
                         "algorithmic_bytes_per_sd": per_sd, "sd_per_launch": n_live, "mean_launch_ms": t_ms / n_l,
-                        "step_frac_of_hbm_roofline": value * A_FULL_BYTES / (world * peak * 1e9)}
+                        "step_frac_of_hbm_roofline": value * A_FULL_BYTES / (world * peak * 1e9),
+                        "note": "k_cond_cells is FP64-pipe/latency bound, not HBM bound (ncu: fp64 pipe ~57 % busy, ~20 of 32 lanes active): profiles/",
+                        "per_kernel": {k: {"GB/s": round(kernel_bytes(k) * n_live / (ms_ / n * 1e-3) / 1e9, 1),
+                                           "frac": round(kernel_bytes(k) * n_live / (ms_ / n * 1e-3) / 1e9 / peak, 4)}
+                                       for k, (n, ms_) in rep.items() if kernel_bytes(k) and ms_ > 0}}
 
     # ---- CPU baseline beside it (rank 0, N = 1) -----------------------------------------------------------------------
     cpu = None
@@ -315,9 +335,9 @@ def main():
     ap.add_argument("--ny", type=int, default=256)
     ap.add_argument("--nz", type=int, default=128)
     ap.add_argument("--sd-conc", type=int, default=40)
-    ap.add_argument("--ref-nx", type=int, default=32)
-    ap.add_argument("--ref-ny", type=int, default=32)
-    ap.add_argument("--ref-nz", type=int, default=32)
+    ap.add_argument("--ref-nx", type=int, default=64)      # CPU arm: 64^3 cells x 40 SD = 1.05e7 SDs, about 1.5 s per step on 16 cores
+    ap.add_argument("--ref-ny", type=int, default=64)
+    ap.add_argument("--ref-nz", type=int, default=64)
     ap.add_argument("--profile-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
