@@ -3,6 +3,8 @@
 // translation units.
 #include "lcx_engine.cuh"
 
+#include <cstdlib>
+
 #include <map>
 #include <memory>
 #include <sstream>
@@ -130,6 +132,16 @@ int lcx_create(const lcx_config *cfg, lcx_engine **out)
     if (n_cell >= 0x7ffffff0ull) throw error("lcx_create: too many cells for one slab");
     g.n_cell = idx_t(n_cell);
     g.halo_size = (cfg->adve_scheme == AS_PRED_CORR) ? 2 : 0;
+    {
+      // spare bits of the last radix digit (lcx_post_copy sorts on 8-bit digits); LCX_SIZE_CLASS_BITS=0 switches the sub-key off
+      int bits = 0; for (uint64_t v = n_cell; v; v >>= 1) ++bits;
+      const int spare = (8 - bits % 8) % 8;
+      const char *env = std::getenv("LCX_SIZE_CLASS_BITS");
+      const int want = env ? std::atoi(env) : 3;
+      g.class_bits = spare < want ? spare : want;
+      if (g.class_bits < 0) g.class_bits = 0;
+      if (g.class_bits > 3) g.class_bits = 3;
+    }
     g.halo_x = idx_t(g.n_dims == 1 ? g.halo_size : g.n_dims == 2 ? g.halo_size * g.nz : g.halo_size * g.nz * g.ny);
 
     const size_t cap = e->cap = size_t(cfg->n_sd_max);

@@ -71,7 +71,26 @@ namespace lcx
     idx_t n_cell;
     int halo_size;          // cells of x-halo on each side of the Courant fields (2 for pred_corr, else 0)
     idx_t halo_x;           // halo_size * (cells per x-column): offset of the first real cell in halo-extended numbering
+    int class_bits;         // low bits of the re-layout sort key that order the SDs of a cell by size class (0..3)
   };
+
+  // Re-layout sort key: cell index in the high bits, a coarse size class (factor 4 in radius per class) in the bits that
+  // the last 8-bit radix digit leaves unused anyway.  Inside a cell the SDs then lie ordered by size, so the lanes that
+  // run the condensation root solve in lock-step work on similar droplets (similar iteration counts).  Any order inside
+  // a cell is valid: pairing for coalescence is by random key, sums over a cell carry a tolerance.
+  __host__ __device__ inline uint32_t relayout_key(const grid_t &g, idx_t cell, real_t rw2)
+  {
+    if (g.class_bits == 0) return cell;
+#if defined(__CUDA_ARCH__)
+    const int e = int((__double_as_longlong(double(rw2)) >> 52) & 0x7ff) - 1023;
+#else
+    int e = 0; if (rw2 > 0) { (void)frexp(double(rw2), &e); e -= 1; } else e = -1023;
+#endif
+    int cls = (e + 50) >> 2;            // r < 0.1 um -> 0, 0.1-0.4 -> 1, 0.4-1.6 -> 2, 1.6-6.4 -> 3, 6.4-25 -> 4, 25-100 -> 5, ...
+    cls = cls < 0 ? 0 : cls > 7 ? 7 : cls;
+    return (cell << g.class_bits) | uint32_t(cls >> (3 - g.class_bits));
+  }
+  __host__ __device__ inline uint32_t relayout_dead_key(const grid_t &g) { return g.n_cell << g.class_bits; }
 
   // device-side scalars that kernels produce and the host occasionally reads back
   struct dev_scalars

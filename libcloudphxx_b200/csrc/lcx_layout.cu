@@ -19,14 +19,15 @@ namespace lcx
   {
     constexpr int TPB = 256;
 
-    __global__ void __launch_bounds__(TPB) k_make_keys(size_t first, size_t n, grid_t g, const n_t *__restrict__ ns,
+    __global__ void __launch_bounds__(TPB) k_make_keys(size_t first, size_t n, grid_t g, const n_t *__restrict__ ns, const real_t *__restrict__ rw2,
                                                       const real_t *__restrict__ xs, const real_t *__restrict__ ys, const real_t *__restrict__ zs,
                                                       uint32_t *__restrict__ key, uint32_t *__restrict__ val)
     {
       const size_t t = first + size_t(blockIdx.x) * TPB + threadIdx.x;
       if (t >= n) return;
       uint32_t k = g.n_cell;   // dead
-      if (ns[t] != 0)
+      const bool live = ns[t] != 0;
+      if (live)
       {
         // i = size_t(double(x) / dx): the division is done in double whatever real_t is (hskpng_ijk.ipp:171)
         const idx_t i = g.nx ? idx_t(size_t(double(xs[t]) / double(g.dx))) : 0;
@@ -41,17 +42,17 @@ namespace lcx
         }
         if (k >= g.n_cell) k = g.n_cell - 1;   // never index outside the grid (the reference leaves this undefined)
       }
-      key[t] = k;
+      key[t] = live ? relayout_key(g, k, rw2[t]) : relayout_dead_key(g);
       val[t] = uint32_t(t);
     }
 
     // off[c] = first sorted position whose key is >= c, for c in [0, n_cell+1]; off[n_cell+1] = n
-    __global__ void __launch_bounds__(TPB) k_cell_offsets(size_t n, uint32_t n_cell, const uint32_t *__restrict__ key, uint32_t *__restrict__ off)
+    __global__ void __launch_bounds__(TPB) k_cell_offsets(size_t n, uint32_t n_cell, int class_bits, const uint32_t *__restrict__ key, uint32_t *__restrict__ off)
     {
       const size_t t = size_t(blockIdx.x) * TPB + threadIdx.x;
       if (t > n) return;
-      const uint32_t hi = (t == n) ? n_cell + 1 : key[t];
-      const uint32_t lo = (t == 0) ? 0u : key[t - 1] + 1;
+      const uint32_t hi = (t == n) ? n_cell + 1 : key[t] >> class_bits;
+      const uint32_t lo = (t == 0) ? 0u : (key[t - 1] >> class_bits) + 1;
       for (uint32_t c = lo; c <= hi && c <= n_cell; ++c) off[c] = uint32_t(t);
       if (t == n) off[n_cell + 1] = uint32_t(n);
     }
@@ -66,19 +67,23 @@ namespace lcx
       if (c == 0) sc->n_part = off[n_cell];
     }
 
-    __global__ void __launch_bounds__(TPB) k_keys_from_ijk(size_t n, const idx_t *__restrict__ ijk, uint32_t *__restrict__ key, uint32_t *__restrict__ val)
+    __global__ void __launch_bounds__(TPB) k_keys_from_ijk(size_t n, grid_t g, const idx_t *__restrict__ ijk, const real_t *__restrict__ rw2,
+                                                          uint32_t *__restrict__ key, uint32_t *__restrict__ val)
     {
       const size_t t = size_t(blockIdx.x) * TPB + threadIdx.x;
-      if (t < n) { key[t] = ijk[t]; val[t] = uint32_t(t); }
+      if (t < n) { key[t] = relayout_key(g, ijk[t], rw2[t]); val[t] = uint32_t(t); }
     }
 
     struct gather_set { const void *src[10]; void *dst[10]; int width[10]; int n; };
 
-    __global__ void __launch_bounds__(TPB) k_gather(size_t n, const uint32_t *__restrict__ perm, gather_set G)
+    // every attribute of the survivors moves to its sorted position; the cell index comes from the sorted key
+    __global__ void __launch_bounds__(TPB) k_gather(size_t n, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ key, int class_bits,
+                                                   idx_t *__restrict__ ijk, gather_set G)
     {
       const size_t t = size_t(blockIdx.x) * TPB + threadIdx.x;
       if (t >= n) return;
       const uint32_t s = perm[t];
+      ijk[t] = key[t] >> class_bits;
 #pragma unroll 1
       for (int a = 0; a < G.n; ++a)
       {
@@ -163,7 +168,7 @@ namespace lcx
   {
     const grid_t &g = e->grid;
     LCX_CUDA(cudaMemsetAsync(&e->scalars.p->max_count, 0, sizeof(unsigned int), e->stream));
-    LCX_LAUNCH(e, k_cell_offsets, div_up(n_total + 1, TPB), TPB, 0, n_total, g.n_cell, sorted_keys, e->cell_off.p);
+    LCX_LAUNCH(e, k_cell_offsets, div_up(n_total + 1, TPB), TPB, 0, n_total, g.n_cell, g.class_bits, sorted_keys, e->cell_off.p);
     LCX_LAUNCH(e, k_max_count, div_up(g.n_cell, TPB), TPB, 0, g.n_cell, e->cell_off.p, e->scalars.p);
   }
 
@@ -219,16 +224,16 @@ namespace lcx
     }
 
     if (keep_all)   // initial grouping: every SD stays, cells are the ones assigned at creation (init_ijk.ipp:36-52)
-      LCX_LAUNCH(e, k_keys_from_ijk, div_up(n_old, TPB), TPB, 0, n_old, s.ijk.p, e->key[0].p, e->val[0].p);
+      LCX_LAUNCH(e, k_keys_from_ijk, div_up(n_old, TPB), TPB, 0, n_old, g, s.ijk.p, s.rw2.p, e->key[0].p, e->val[0].p);
     else
     {
       // k_transport already wrote the keys of the SDs it moved; only later arrivals (migration) are keyed here
       const size_t first = e->keys_ready <= n_old ? e->keys_ready : 0;
       if (first < n_old)
-        LCX_LAUNCH(e, k_make_keys, div_up(n_old - first, TPB), TPB, 0, first, n_old, g, s.n.p, s.x.p, s.y.p, s.z.p, e->key[0].p, e->val[0].p);
+        LCX_LAUNCH(e, k_make_keys, div_up(n_old - first, TPB), TPB, 0, first, n_old, g, s.n.p, s.rw2.p, s.x.p, s.y.p, s.z.p, e->key[0].p, e->val[0].p);
     }
     e->keys_ready = 0;
-    const int res = radix_sort_pairs(e, n_old, 0, bit_length(g.n_cell), 0);
+    const int res = radix_sort_pairs(e, n_old, 0, bit_length(g.n_cell) + g.class_bits, 0);
     compute_cell_offsets(e, e->key[res].p, n_old);
 
     LCX_CUDA(cudaMemcpyAsync(e->h_scalars, e->scalars.p, sizeof(dev_scalars), cudaMemcpyDeviceToHost, e->stream));
@@ -242,8 +247,7 @@ namespace lcx
       add(G, s.n.p, a.n.p, 8); add(G, s.rd3.p, a.rd3.p, 8); add(G, s.rw2.p, a.rw2.p, 8); add(G, s.kpa.p, a.kpa.p, 8);
       add(G, s.vt.p, a.vt.p, 8); add(G, s.x.p, a.x.p, 8); add(G, s.y.p, a.y.p, 8); add(G, s.z.p, a.z.p, 8);
       add(G, s.sid.p, a.sid.p, 4);
-      LCX_LAUNCH(e, k_gather, div_up(n_new, TPB), TPB, 0, n_new, e->val[res].p, G);
-      LCX_CUDA(cudaMemcpyAsync(a.ijk.p, e->key[res].p, n_new * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
+      LCX_LAUNCH(e, k_gather, div_up(n_new, TPB), TPB, 0, n_new, e->val[res].p, e->key[res].p, g.class_bits, a.ijk.p, G);
     }
     e->cur ^= 1;
     e->n_part = n_new;

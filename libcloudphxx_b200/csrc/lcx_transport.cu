@@ -238,12 +238,13 @@ namespace lcx
         flag[t] = fl;
         // sort key of the coming re-layout (hskpng_ijk of post_copy): new cell, or n_cell for SDs that are gone;
         // migrants leave through lcx_migr_pack, which zeroes their multiplicity and re-keys them
-        uint32_t kx = g.n_cell;
+        uint32_t kx = relayout_dead_key(g);
         if (n != 0 && fl == 0)
         {
           idx_t i2, j2, k2;
-          kx = cell_of(g, x, y, z, i2, j2, k2);
-          if (kx >= g.n_cell) kx = g.n_cell - 1;
+          idx_t cell = cell_of(g, x, y, z, i2, j2, k2);
+          if (cell >= g.n_cell) cell = g.n_cell - 1;
+          kx = relayout_key(g, cell, g.class_bits ? rw2[t] : real_t(0));
         }
         key[t] = kx;
         val[t] = uint32_t(t);
