@@ -57,6 +57,14 @@ namespace
     }
   };
 
+  // the caller's own n(ln r)
+  struct callback_distro : lc::unary_function<double>
+  {
+    double (*fn)(double, void *);
+    void *ctx;
+    double funval(const double lnr) const { return fn(lnr, ctx); }
+  };
+
   lg::arrinfo_t<double> mk(const lgc_arr *a)
   {
     if (a == nullptr || a->data == nullptr) return lg::arrinfo_t<double>();
@@ -172,6 +180,13 @@ int lgc_create(const lgc_opts_init *c, lgc_handle **out)
       {
         auto s = std::make_shared<expvolume>();
         s->r0 = d.r0; s->n0 = d.n0;
+        f = s;
+      }
+      else if (d.kind == 2)
+      {
+        if (!d.fn) throw std::runtime_error("lgc_create: distro kind 2 without a function");
+        auto s = std::make_shared<callback_distro>();
+        s->fn = d.fn; s->ctx = d.ctx;
         f = s;
       }
       else throw std::runtime_error("lgc_create: unknown distro kind");

@@ -20,11 +20,13 @@ enum { LGC_MAX_MODES = 4, LGC_MAX_DISTROS = 4, LGC_MAX_KPARAMS = 4, LGC_MAX_SIZE
 /* dry spectrum n(ln r) [m^-3 per unit ln r, at STP] */
 typedef struct
 {
-  int    kind;                     /* 0: sum of lognormal modes; 1: exponential in volume          */
+  int    kind;                     /* 0: sum of lognormal modes; 1: exponential in volume; 2: caller's function */
   double kappa, rd_insol;
   int    n_modes;
   double mean_r[LGC_MAX_MODES], stdev[LGC_MAX_MODES], n_tot[LGC_MAX_MODES];
   double r0, n0;                   /* kind 1: n0 * 3 (r/r0)^3 exp(-(r/r0)^3)                       */
+  double (*fn)(double lnr, void *ctx);   /* kind 2: n(ln r), called from the host-side initialisation (what the  */
+  void  *ctx;                            /*         reference's Python binding does with a Python callable)      */
 } lgc_distro;
 
 /* one entry of opts_init_t::dry_sizes: (kappa, rd_insol) -> radius -> (STP concentration, SDs per cell) */

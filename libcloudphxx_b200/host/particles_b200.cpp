@@ -1266,4 +1266,47 @@ int lgrngn_b200_post_copy(void *proto, int rcyc)
   catch (const std::exception &ex) { std::cerr << ex.what() << std::endl; return 1; }
 }
 
+
+double lgrngn_b200_common(const char *name, double a, double b, double c, double d, double e)
+{
+  typedef lcx::cst<double> k;
+  const std::string n(name);
+  // constants (lib.cpp:40-66)
+  if (n == "R_d") return k::R_d();
+  if (n == "R_v") return k::R_v();
+  if (n == "c_pd") return k::c_pd();
+  if (n == "c_pv") return k::c_pv();
+  if (n == "c_pw") return k::c_pw();
+  if (n == "g") return k::g();
+  if (n == "p_1000") return k::p_1000();
+  if (n == "eps") return k::eps();
+  if (n == "rho_stp") return k::rho_stp();
+  if (n == "rho_w") return k::rho_w();
+  if (n == "T_tri") return k::T_tri();
+  if (n == "p_tri") return k::p_tri();
+  if (n == "l_tri") return k::l_tri();
+  // functions (common.hpp:20-170)
+  if (n == "th_dry2std") return a / std::pow(1 + b * k::R_v() / k::R_d(), k::R_d() / k::c_pd());      // theta_dry.hpp:97-108
+  if (n == "th_std2dry") return a * std::pow(1 + b * k::R_v() / k::R_d(), k::R_d() / k::c_pd());      // theta_dry.hpp:83-94
+  if (n == "exner") return lcx::exner(a);
+  if (n == "p_v") return lcx::p_v(a, b);
+  if (n == "p_vs") return lcx::p_vs_cc(a);
+  if (n == "p_vs_tet") return lcx::p_vs_tet(a);
+  if (n == "r_vs") return lcx::r_vs_cc(a, b);
+  if (n == "l_v") return lcx::l_v(a);
+  if (n == "T") return lcx::T_of_th_dry(a, b);
+  if (n == "p") return lcx::p_of_rhod_rv_T(a, b, c);
+  if (n == "visc") return lcx::visc(a);
+  if (n == "rw3_cr") return lcx::rw3_cr(a, b, c);
+  if (n == "S_cr") return lcx::S_cr(a, b, c);
+  if (n == "p_hydro")                                                                                   // hydrostatic.hpp:26-39
+  {
+    const double R_moist = (k::R_d() + c * k::R_v()) / (1 + c);                                        // moist_air::R(r): moist_air.hpp:55-70
+    return k::p_1000() * std::pow(std::pow(e / k::p_1000(), k::R_d() / k::c_pd()) - k::R_d() / k::c_pd() * k::g() / b / R_moist * (a - d),
+                                  k::c_pd() / k::R_d());
+  }
+  if (n == "rhod") return (a - lcx::p_v(a, c)) / (std::pow(a / k::p_1000(), k::R_d() / k::c_pd()) * k::R_d() * b);   // theta_std.hpp:25-32
+  return std::numeric_limits<double>::quiet_NaN();
+}
+
 }

@@ -30,6 +30,9 @@ int   lgrngn_b200_post_copy(void *particles_proto, int rcyc);
 /* fields ALREADY RESIDENT in device memory: no host<->device field traffic.  flags: bit0 adve, bit1 sedi, bit2 cond, */
 /* bit3 coal.  Used by bench.py for the device-resident throughput figure.                                            */
 int   lgrngn_b200_step_resident(void *particles_proto, int flags);
+/* scalar thermodynamic helpers and constants of libcloudphxx::common as the reference's Python module exposes them  */
+/* (bindings/python/common.hpp:20-170, lib.cpp:40-120); unknown names give NaN                                       */
+double lgrngn_b200_common(const char *name, double a, double b, double c, double d, double e);
 
 #ifdef __cplusplus
 }

@@ -38,7 +38,11 @@ class RH_formula_t:
 class _Distro(C.Structure):
     _fields_ = [("kind", C.c_int), ("kappa", C.c_double), ("rd_insol", C.c_double), ("n_modes", C.c_int),
                 ("mean_r", C.c_double * MAX_MODES), ("stdev", C.c_double * MAX_MODES), ("n_tot", C.c_double * MAX_MODES),
-                ("r0", C.c_double), ("n0", C.c_double)]
+                ("r0", C.c_double), ("n0", C.c_double),
+                ("fn", C.c_void_p), ("ctx", C.c_void_p)]
+
+
+DISTRO_FN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)
 
 
 class _DrySize(C.Structure):
@@ -91,6 +95,11 @@ PUDDLE_KEYS = ["HNO3", "NH3", "CO2", "SO2", "H2O2", "O3", "S_VI", "H", "liquid_v
 def lognormal(kappa, modes, rd_insol=0.0):
     """dry spectrum: sum of lognormal modes [(mean_r [m], geometric stdev, n_tot [m^-3]), ...]"""
     return {"kind": 0, "kappa": kappa, "rd_insol": rd_insol, "modes": list(modes)}
+
+
+def callable_distro(kappa, fn, rd_insol=0.0):
+    """dry spectrum given as a Python callable n(ln r) [m^-3 per unit ln r at STP], like the reference's Python binding"""
+    return {"kind": 2, "kappa": kappa, "rd_insol": rd_insol, "fn": fn}
 
 
 def expvolume(kappa, r0, n0, rd_insol=0.0):
@@ -173,6 +182,7 @@ class OptsInit:
         c.n_kernel_parameters = len(kp)
         for i, v in enumerate(kp):
             c.kernel_parameters[i] = float(v)
+        keep = []
         c.n_distros = len(self.dry_distros)
         for i, d in enumerate(self.dry_distros):
             cd = c.distros[i]
@@ -181,8 +191,13 @@ class OptsInit:
                 cd.n_modes = len(d["modes"])
                 for m, (mean_r, stdev, n_tot) in enumerate(d["modes"]):
                     cd.mean_r[m], cd.stdev[m], cd.n_tot[m] = mean_r, stdev, n_tot
-            else:
+            elif d["kind"] == 1:
                 cd.r0, cd.n0 = d["r0"], d["n0"]
+            else:
+                fn = d["fn"]
+                cb = DISTRO_FN(lambda lnr, _ctx, fn=fn: float(fn(lnr)))
+                keep.append(cb)                      # must outlive the particles object
+                cd.fn = C.cast(cb, C.c_void_p)
         i = 0
         for key, sizes in self.dry_sizes.items():
             kappa, rd_insol = key if isinstance(key, tuple) else (key, 0.0)
@@ -191,7 +206,6 @@ class OptsInit:
                 ds.kappa, ds.rd_insol, ds.radius, ds.conc, ds.count = kappa, rd_insol, radius, conc, int(count)
                 i += 1
         c.n_dry_sizes = i
-        keep = []
         if len(self.w_LS):
             keep.append(np.ascontiguousarray(self.w_LS, dtype=np.float64))
             c.n_w_LS = keep[-1].size
@@ -237,6 +251,7 @@ class Particles:
         self._L = library
         self._lib = library.lib
         c, keep = opts_init._pack(backend)
+        self._keep = keep          # arrays and callbacks the C side still points to (dry spectra are evaluated in init())
         h = C.c_void_p()
         library.check(self._lib.lgc_create(C.byref(c), C.byref(h)))
         self._h = h
