@@ -88,7 +88,20 @@ lcx_engine::~lcx_engine()
   for (auto &r : prof) { cudaEventDestroy(r.t0); cudaEventDestroy(r.t1); }
   if (timer0) { cudaEventDestroy(timer0); cudaEventDestroy(timer1); }
   if (h_scalars) cudaFreeHost(h_scalars);
+  if (courant_ready) cudaEventDestroy(courant_ready);
+  if (main_mark) cudaEventDestroy(main_mark);
+  if (copy_stream) cudaStreamDestroy(copy_stream);
   if (stream) cudaStreamDestroy(stream);
+}
+
+namespace lcx
+{
+  void wait_courant(lcx_engine *e)
+  {
+    if (!e->courant_pending) return;
+    LCX_CUDA(cudaStreamWaitEvent(e->stream, e->courant_ready, 0));
+    e->courant_pending = false;
+  }
 }
 
 extern "C" {
@@ -119,6 +132,9 @@ int lcx_create(const lcx_config *cfg, lcx_engine **out)
     e->device = dev;
     LCX_CUDA(cudaSetDevice(dev));
     LCX_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    LCX_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    LCX_CUDA(cudaEventCreateWithFlags(&e->courant_ready, cudaEventDisableTiming));
+    LCX_CUDA(cudaEventCreateWithFlags(&e->main_mark, cudaEventDisableTiming));
 
     grid_t &g = e->grid;
     g.nx = cfg->nx; g.ny = cfg->ny; g.nz = cfg->nz;
@@ -205,7 +221,14 @@ int lcx_create(const lcx_config *cfg, lcx_engine **out)
 
 int lcx_destroy(lcx_engine *e) { return guarded([&] { delete e; }); }
 
-int lcx_sync(lcx_engine *e) { return guarded([&] { use_device(e); LCX_CUDA(cudaStreamSynchronize(e->stream)); }); }
+int lcx_sync(lcx_engine *e)
+{
+  return guarded([&] {
+    use_device(e);
+    LCX_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->courant_pending) LCX_CUDA(cudaStreamSynchronize(e->copy_stream));   // the data stay "pending" for the engine's stream
+  });
+}
 
 void *lcx_stream(lcx_engine *e) { return e->stream; }
 
@@ -217,6 +240,7 @@ int lcx_cells_set(lcx_engine *e, int field, const void *src, int64_t count, int 
     use_device(e);
     if (field == LCX_F_W_LS && e->w_LS.n != size_t(count)) e->w_LS.alloc(size_t(count));
     const field_ref f = field_of(e, field);
+    lcx::wait_courant(e);
     if (size_t(count) != f.n) throw lcx::error("lcx_cells_set: field " + std::to_string(field) + " holds " + std::to_string(f.n) + " values, got " + std::to_string(count));
     LCX_CUDA(cudaMemcpyAsync(f.p, src, f.n * sizeof(lcx::real_t), src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->stream));
     if (!src_on_device) LCX_CUDA(cudaStreamSynchronize(e->stream));   // the caller may reuse its staging buffer
@@ -228,6 +252,7 @@ int lcx_cells_get(lcx_engine *e, int field, void *dst, int64_t count)
   return guarded([&] {
     use_device(e);
     const field_ref f = field_of(e, field);
+    lcx::wait_courant(e);
     if (size_t(count) > f.n) throw lcx::error("lcx_cells_get: requested more values than the field holds");
     LCX_CUDA(cudaMemcpyAsync(dst, f.p, size_t(count) * sizeof(lcx::real_t), cudaMemcpyDeviceToHost, e->stream));
     LCX_CUDA(cudaStreamSynchronize(e->stream));
@@ -240,7 +265,23 @@ int lcx_cells_set_part(lcx_engine *e, int field, int64_t offset, const void *src
     use_device(e);
     const field_ref f = field_of(e, field);
     if (offset < 0 || count < 0 || size_t(offset + count) > f.n) throw lcx::error("lcx_cells_set_part: range outside field " + std::to_string(field));
-    LCX_CUDA(cudaMemcpyAsync(static_cast<lcx::real_t *>(f.p) + offset, src, size_t(count) * sizeof(lcx::real_t), cudaMemcpyHostToDevice, e->stream));
+    cudaStream_t st = e->stream;
+    const bool courant = field == LCX_F_COURANT_X || field == LCX_F_COURANT_Y || field == LCX_F_COURANT_Z;
+    if (courant)
+    {
+      st = e->copy_stream;
+      if (!e->courant_pending)      // first piece of a batch: everything queued so far may still read the old fields
+      {
+        LCX_CUDA(cudaEventRecord(e->main_mark, e->stream));
+        LCX_CUDA(cudaStreamWaitEvent(e->copy_stream, e->main_mark, 0));
+      }
+    }
+    LCX_CUDA(cudaMemcpyAsync(static_cast<lcx::real_t *>(f.p) + offset, src, size_t(count) * sizeof(lcx::real_t), cudaMemcpyHostToDevice, st));
+    if (courant)
+    {
+      LCX_CUDA(cudaEventRecord(e->courant_ready, e->copy_stream));
+      e->courant_pending = true;
+    }
   });
 }
 

@@ -262,6 +262,7 @@ namespace lcx
   {
     const grid_t &g = e->grid;
     if (g.n_dims == 0) return;
+    wait_courant(e);
     LCX_LAUNCH(e, k_vel_div, div_up(g.n_cell, TPB), TPB, 0, g, dt, e->courant_x.p, e->courant_y.p, e->courant_z.p, e->count_mom.p);
   }
 }

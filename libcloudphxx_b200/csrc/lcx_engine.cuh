@@ -112,6 +112,11 @@ struct lcx_engine
   lcx::grid_t grid;
   int device = 0;
   cudaStream_t stream = nullptr;
+  // Courant fields are needed late in the step (transport): their host->device copies run on a second stream, so that
+  // they overlap the condensation kernel; consumers call lcx::wait_courant first
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t courant_ready = nullptr, main_mark = nullptr;
+  bool courant_pending = false;
   uint64_t launches = 0;
 
   size_t cap = 0;                // n_sd_max
@@ -212,6 +217,7 @@ namespace lcx
 
   // ---- lcx_cond.cu -----------------------------------------------------------------------------------
   void cond(lcx_engine *e, real_t dt_sub, real_t RH_max, int step, int sstp);
+  void wait_courant(lcx_engine *e);      // orders the engine's stream after pending Courant-field uploads
 
   // ---- lcx_coal.cu -----------------------------------------------------------------------------------
   void coal(lcx_engine *e, real_t dt_sub, const lcx_rng *rng);

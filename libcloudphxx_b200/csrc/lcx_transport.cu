@@ -353,6 +353,7 @@ namespace lcx
   {
     const size_t n = e->n_part;
     if (n == 0 || e->grid.n_dims == 0) return;
+    wait_courant(e);
     sd_arrays &s = e->S();
     tr_params P;
     P.g = e->grid;

@@ -158,6 +158,7 @@ namespace libcloudphxx
         map_t m_th, m_rv, m_rhod, m_p, m_cx, m_cy, m_cz;
         std::vector<real_t> outbuf_host;
         std::vector<std::pair<const map_t *, real_t *>> pending_out;
+        bool transfers_open = false;       // uploads of a deferred sync_in not yet waited for
         std::map<common::output_t, real_t> puddle0;
 
         slab(const opts_init_t<real_t> &o, std::pair<int, int> bc, int n_x_tot_) : oi(o), bcond(bc)
@@ -803,8 +804,11 @@ namespace libcloudphxx
           dt = dt_ > 0 ? dt_ : oi.dt;
         }
 
+        // defer_wait: the caller (step_sync) runs step_cond right away and waits for the uploads at its end, so the Courant
+        // fields - needed only by step_async - travel while the condensation kernel runs
         void sync_in(arrinfo_t<real_t> &th, arrinfo_t<real_t> &rv, const arrinfo_t<real_t> &rhod, const arrinfo_t<real_t> &cx,
-                     const arrinfo_t<real_t> &cy, const arrinfo_t<real_t> &cz, const arrinfo_t<real_t> &diss_rate, size_t n_ambient_chem)
+                     const arrinfo_t<real_t> &cy, const arrinfo_t<real_t> &cz, const arrinfo_t<real_t> &diss_rate, size_t n_ambient_chem,
+                     bool defer_wait = false)
         {
           if (!init_called) throw std::runtime_error("libcloudph++: please call init() before calling step_sync()");
           if (should_now_run_async) throw std::runtime_error("libcloudph++: please call step_async() before calling step_sync() again");
@@ -821,7 +825,8 @@ namespace libcloudphxx
           sync_in_field(cx, m_cx, LCX_F_COURANT_X);
           sync_in_field(cy, m_cy, LCX_F_COURANT_Y);
           sync_in_field(cz, m_cz, LCX_F_COURANT_Z);
-          finish_transfers();          // the caller may overwrite its arrays as soon as this returns
+          transfers_open = defer_wait;
+          if (!defer_wait) finish_transfers();          // the caller may overwrite its arrays as soon as this returns
           // |C_x| > 2 would leave the 2-cell halo of the predictor-corrector scheme: fall back to Euler for this step
           if (oi.adve_scheme == as_t::pred_corr && !cx.is_null())
           {
@@ -856,14 +861,15 @@ namespace libcloudphxx
             {
               chk(lcx_sstp_percell_step(e, step, sstp_cond, var_rho));
               chk(lcx_hskpng_Tpr(e));
-              // includes update_th_rv; on the last sub-step also the Tpr + vterm_all that step_async begins with
-              chk(lcx_cond(e, dt / sstp_cond, opts.RH_max, step, sstp_cond));
+              chk(lcx_cond(e, dt / sstp_cond, opts.RH_max, step, sstp_cond));      // includes update_th_rv
             }
             chk(lcx_sstp_save(e));
             sync_out_field(LCX_F_TH, m_th, th);
             sync_out_field(LCX_F_RV, m_rv, rv);
             finish_transfers();
+            transfers_open = false;
           }
+          if (transfers_open) { finish_transfers(); transfers_open = false; }     // deferred uploads of step_sync
           if (opts.chem_dsl || opts.chem_dsc || opts.chem_rct)
             throw std::runtime_error("libcloudph++: all chemistry was switched off in opts_init");
           should_now_run_async = true;
@@ -1074,7 +1080,7 @@ namespace libcloudphxx
                        const arrinfo_t<real_t> cx, const arrinfo_t<real_t> cy, const arrinfo_t<real_t> cz,
                        const arrinfo_t<real_t> diss_rate, chem_map_t ambient_chem) override
         {
-          sync_in(th, rv, rhod, cx, cy, cz, diss_rate, ambient_chem);
+          for (auto &s : slabs) s->sync_in(th, rv, rhod, cx, cy, cz, diss_rate, ambient_chem.size(), /*defer_wait=*/true);
           step_cond(opts, th, rv, ambient_chem);
         }
 
