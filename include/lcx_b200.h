@@ -83,6 +83,7 @@ typedef struct
   int multi_kappa;            /* more than one (kappa) species: kappa is mixed on coalescence                 */
   int pure_const_multi;       /* constant-multiplicity run: report probabilities >= 1                         */
   int allow_sstp_cond;        /* keep old rv/th/rhod for per-cell condensation sub-stepping                   */
+  int exact_sstp_cond;        /* per-particle sub-stepping: every SD carries its own rv, th, rhod (, p) history */
 } lcx_config;
 
 typedef struct
@@ -144,6 +145,9 @@ int  lcx_sstp_save(lcx_engine *e);                              /* sstp_save.ipp
 /* ---- condensation (per-cell sub-stepping path) ---------------------------------------------------------- */
 /* one sub-step: 3rd wet moment before (step 0; later sub-steps reuse the previous "after"), implicit-Euler growth */
 /* of every liquid SD, 3rd wet moment after, and the vapour / heat feedback rv -= drv, th -= drv dth/drv              */
+/* per-particle condensation sub-stepping, all sub-steps of one time step (particles_step.ipp:199-236,                 */
+/* condensation/perparticle/*.ipp); mix != 0: the vapour / heat exchanged by the SDs of a cell is shared after each sub-step */
+int  lcx_cond_perparticle(lcx_engine *e, double dt, double RH_max, int sstp_cond, int mix);
 int  lcx_cond(lcx_engine *e, double dt_sub, double RH_max, int step, int sstp_cond);   /* percell/particles_impl_cond.ipp:13-139, common/particles_impl_update_th_rv.ipp:74-191 */
 
 /* ---- coalescence --------------------------------------------------------------------------------------- */

@@ -123,6 +123,7 @@ void lgc_opts_init_defaults(lgc_opts_init *o)
   o->variable_dt_switch = d.variable_dt_switch; o->th_dry = d.th_dry; o->const_p = d.const_p;
   o->aerosol_independent_of_rhod = d.aerosol_independent_of_rhod;
   o->sd_conc_large_tail = d.sd_conc_large_tail; o->no_ccn_at_init = d.no_ccn_at_init;
+  o->sstp_cond_mix = d.sstp_cond_mix;
 }
 
 void lgc_opts_defaults(lgc_opts *o)
@@ -158,6 +159,7 @@ int lgc_create(const lgc_opts_init *c, lgc_handle **out)
     o.aerosol_independent_of_rhod = c->aerosol_independent_of_rhod;
     if (c->n_w_LS > 0) o.w_LS.assign(c->w_LS, c->w_LS + c->n_w_LS);
     o.sd_conc_large_tail = c->sd_conc_large_tail; o.no_ccn_at_init = c->no_ccn_at_init;
+    o.sstp_cond_mix = c->sstp_cond_mix;
     if (c->n_aerosol_conc_factor > 0) o.aerosol_conc_factor.assign(c->aerosol_conc_factor, c->aerosol_conc_factor + c->n_aerosol_conc_factor);
     for (int i = 0; i < c->n_dry_sizes; ++i)
     {

@@ -60,6 +60,7 @@ typedef struct
   lgc_dry_size dry_sizes[LGC_MAX_SIZES];
   int n_aerosol_conc_factor;
   const double *aerosol_conc_factor;
+  int sstp_cond_mix;               /* per-particle sub-stepping: share vapour / heat inside a cell after each sub-step */
 } lgc_opts_init;
 
 typedef struct

@@ -163,6 +163,8 @@ int lcx_create(const lcx_config *cfg, lcx_engine **out)
     const size_t cap = e->cap = size_t(cfg->n_sd_max);
     e->sd[0].alloc(cap, g.nx, g.ny, g.nz);
     e->sd[1].alloc(cap, g.nx, g.ny, g.nz);
+    if (cfg->exact_sstp_cond && cfg->allow_sstp_cond)
+      for (int b = 0; b < 2; ++b) e->sd[b].alloc_pp(cap, cfg->const_p != 0);
     for (int b = 0; b < 2; ++b) { e->key[b].alloc(cap); e->val[b].alloc(cap); }
     e->un.alloc(cap); e->flag.alloc(cap); e->u01.alloc(cap); e->n_filtered.alloc(cap); e->tmp_real.alloc(cap);
 
@@ -200,7 +202,8 @@ int lcx_create(const lcx_config *cfg, lcx_engine **out)
     {
       e->mig_cap = cap / nx1 + 4096;
       if (e->mig_cap > cap) e->mig_cap = cap;
-      const int n_real = 4 + (g.nx ? 1 : 0) + (g.ny ? 1 : 0) + (g.nz ? 1 : 0);
+      int n_real = 0;
+      lcx_migr_real_attrs(e.get(), &n_real);
       for (int s = 0; s < 2; ++s)
         for (int d = 0; d < 2; ++d) { e->mig_n[s][d].alloc(e->mig_cap); e->mig_real[s][d].alloc(e->mig_cap * n_real); }
       for (int s = 0; s < 2; ++s) { e->mig_key[s].alloc(e->mig_cap); e->mig_val[s].alloc(e->mig_cap); }
@@ -389,6 +392,9 @@ int lcx_sstp_percell_step(lcx_engine *e, int step, int sstp_cond, int var_rho)
 { return guarded([&] { use_device(e); lcx::sstp_percell_step(e, step, sstp_cond, var_rho != 0); }); }
 int lcx_sstp_save(lcx_engine *e) { return guarded([&] { use_device(e); lcx::sstp_save(e); }); }
 
+int lcx_cond_perparticle(lcx_engine *e, double dt, double RH_max, int sstp_cond, int mix)
+{ return guarded([&] { use_device(e); lcx::cond_perparticle(e, dt, RH_max, sstp_cond, mix != 0); }); }
+
 int lcx_cond(lcx_engine *e, double dt_sub, double RH_max, int step, int sstp_cond)
 { return guarded([&] { use_device(e); lcx::cond(e, dt_sub, RH_max, step, sstp_cond); }); }
 
@@ -462,7 +468,11 @@ int lcx_migr_send(lcx_engine *src, int side, lcx_engine *dst, int64_t count)
 }
 
 int lcx_migr_real_attrs(lcx_engine *e, int *count)
-{ *count = 4 + (e->grid.nx ? 1 : 0) + (e->grid.ny ? 1 : 0) + (e->grid.nz ? 1 : 0); return 0; }
+{
+  *count = 4 + (e->grid.nx ? 1 : 0) + (e->grid.ny ? 1 : 0) + (e->grid.nz ? 1 : 0);
+  if (e->cfg.exact_sstp_cond && e->cfg.allow_sstp_cond) *count += e->cfg.const_p ? 4 : 3;
+  return 0;
+}
 
 int lcx_migr_unpack(lcx_engine *e, int side, int64_t count) { return guarded([&] { use_device(e); lcx::migr_unpack(e, side, count); }); }
 

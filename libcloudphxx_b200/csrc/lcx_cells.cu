@@ -155,6 +155,7 @@ namespace lcx
   void sstp_save(lcx_engine *e)
   {
     if (!e->cfg.allow_sstp_cond) return;
+    if (e->cfg.exact_sstp_cond) { pp_save(e, 0); return; }        // per-particle version: sstp_save.ipp:19-24
     const size_t b = size_t(e->grid.n_cell) * sizeof(real_t);
     LCX_CUDA(cudaMemcpyAsync(e->sstp_tmp_rv.p, e->rv.p, b, cudaMemcpyDeviceToDevice, e->stream));
     LCX_CUDA(cudaMemcpyAsync(e->sstp_tmp_th.p, e->th.p, b, cudaMemcpyDeviceToDevice, e->stream));

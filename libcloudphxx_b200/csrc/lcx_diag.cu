@@ -49,6 +49,16 @@ namespace lcx
         return w[i] / sig * pow(xi, 3 * xp) * exp(-pow((log(pow(xi, xp)) - log(rad)) / sig, 2) / 2.);
       }
     };
+    struct term_plain    // a per-SD array as it is
+    {
+      const real_t *v;
+      __device__ __forceinline__ real_t operator()(size_t i) const { return v[i]; }
+    };
+    struct term_sid      // storage index, reduced with max
+    {
+      const idx_t *sid;
+      __device__ __forceinline__ real_t operator()(size_t i) const { return real_t(sid[i]); }
+    };
     struct term_radius   // rw, reduced with max (particles_diag.ipp:606-634)
     {
       const real_t *rw2;
@@ -191,6 +201,18 @@ namespace lcx
   {
     term_moment t = {weight_or_null, e->S().n.p, attr, power};
     cell_reduce<term_moment, false>(e, t, specific ? NORM_SPECIFIC : NORM_NONE, out);
+  }
+
+  void cell_sum(lcx_engine *e, const real_t *per_sd, real_t *out)
+  {
+    term_plain t = {per_sd};
+    cell_reduce<term_plain, false>(e, t, NORM_NONE, out);
+  }
+
+  void cell_max_sid(lcx_engine *e, real_t *out)
+  {
+    term_sid t = {e->S().sid.p};
+    cell_reduce<term_sid, true>(e, t, NORM_NONE, out);
   }
 
   void moms_select(lcx_engine *e, int kind, int attr, real_t lo, real_t hi, bool cons)

@@ -51,6 +51,8 @@ namespace lcx
     dbuf<n_t> n;
     dbuf<real_t> rd3, rw2, kpa, vt, x, y, z;
     dbuf<idx_t> sid, ijk;
+    dbuf<real_t> pp_rv, pp_th, pp_rh, pp_p;      // per-particle sub-stepping: the SD's own record of rv, th, rhod, p (sstp_tmp_*)
+    void alloc_pp(size_t cap, bool with_p) { pp_rv.alloc(cap); pp_th.alloc(cap); pp_rh.alloc(cap); if (with_p) pp_p.alloc(cap); }
     void alloc(size_t cap, bool has_x, bool has_y, bool has_z)
     {
       n.alloc(cap); rd3.alloc(cap); rw2.alloc(cap); kpa.alloc(cap); vt.alloc(cap);
@@ -60,7 +62,8 @@ namespace lcx
       sid.alloc(cap); ijk.alloc(cap);
     }
     void release()
-    { n.release(); rd3.release(); rw2.release(); kpa.release(); vt.release(); x.release(); y.release(); z.release(); sid.release(); ijk.release(); }
+    { n.release(); rd3.release(); rw2.release(); kpa.release(); vt.release(); x.release(); y.release(); z.release(); sid.release(); ijk.release();
+      pp_rv.release(); pp_th.release(); pp_rh.release(); pp_p.release(); }
   };
 
   // grid description handed to kernels by value
@@ -217,6 +220,10 @@ namespace lcx
 
   // ---- lcx_cond.cu -----------------------------------------------------------------------------------
   void cond(lcx_engine *e, real_t dt_sub, real_t RH_max, int step, int sstp);
+  void cond_perparticle(lcx_engine *e, real_t dt, real_t RH_max, int sstp, bool mix);
+  void pp_save(lcx_engine *e, size_t first);                 // sstp_tmp_x[i] = x[ijk[i]] for i >= first (sstp_save.ipp, init_perparticle_sstp.ipp)
+  void cell_sum(lcx_engine *e, const real_t *per_sd, real_t *out);       // plain per-cell sums of a per-SD array
+  void cell_max_sid(lcx_engine *e, real_t *out);             // largest storage index in every cell (as real)
   void wait_courant(lcx_engine *e);      // orders the engine's stream after pending Courant-field uploads
 
   // ---- lcx_coal.cu -----------------------------------------------------------------------------------

@@ -191,8 +191,8 @@ namespace libcloudphxx
             throw std::runtime_error("libcloudph++: SGS turbulence for super-droplets (turb_*_switch) is not part of the B200 back-end");
           if (oi.src_type != src_t::off) throw std::runtime_error("libcloudph++: aerosol sources (src_type) are not part of the B200 back-end");
           if (oi.rlx_switch) throw std::runtime_error("libcloudph++: aerosol relaxation (rlx_switch) is not part of the B200 back-end");
-          if (oi.exact_sstp_cond && (oi.sstp_cond > 1 || oi.sstp_cond_act > 1))
-            throw std::runtime_error("libcloudph++: per-particle condensation sub-stepping (exact_sstp_cond with sstp_cond > 1) is not available yet in the B200 back-end");
+          if (oi.adaptive_sstp_cond || oi.sstp_cond_act > 1)
+            throw std::runtime_error("libcloudph++: adaptive per-particle condensation sub-stepping (adaptive_sstp_cond, sstp_cond_act) is not available yet in the B200 back-end");
           if (oi.diag_incloud_time) throw std::runtime_error("libcloudph++: diag_incloud_time is not part of the B200 back-end");
           if (oi.kernel == kernel_t::onishi_hall || oi.kernel == kernel_t::onishi_hall_davis_no_waals)
             throw std::runtime_error("libcloudph++: To use the turbulent Onishis kernel, set turb_coal_switch=True");
@@ -378,6 +378,7 @@ namespace libcloudphxx
           c.multi_kappa = (oi.dry_distros.size() + oi.dry_sizes.size() > 1);
           c.pure_const_multi = pure_const_multi;
           c.allow_sstp_cond = allow_sstp_cond;
+          c.exact_sstp_cond = oi.exact_sstp_cond;
           std::vector<real_t> eff;
           if (oi.coal_switch) eff = init_kernel(c);
           chk(lcx_create(&c, &e));
@@ -857,12 +858,15 @@ namespace libcloudphxx
           if (opts.cond)
           {
             chk(lcx_hskpng_mfp(e));          // from the T, p left by the previous Tpr, as the reference does (particles_step.ipp:189-194)
-            for (int step = 0; step < sstp_cond; ++step)
-            {
-              chk(lcx_sstp_percell_step(e, step, sstp_cond, var_rho));
-              chk(lcx_hskpng_Tpr(e));
-              chk(lcx_cond(e, dt / sstp_cond, opts.RH_max, step, sstp_cond));      // includes update_th_rv
-            }
+            if (oi.exact_sstp_cond && sstp_cond > 1)           // per-particle sub-stepping: particles_step.ipp:199-236
+              chk(lcx_cond_perparticle(e, dt, opts.RH_max, sstp_cond, oi.sstp_cond_mix));
+            else
+              for (int step = 0; step < sstp_cond; ++step)
+              {
+                chk(lcx_sstp_percell_step(e, step, sstp_cond, var_rho));
+                chk(lcx_hskpng_Tpr(e));
+                chk(lcx_cond(e, dt / sstp_cond, opts.RH_max, step, sstp_cond));      // includes update_th_rv
+              }
             chk(lcx_sstp_save(e));
             sync_out_field(LCX_F_TH, m_th, th);
             sync_out_field(LCX_F_RV, m_rv, rv);

@@ -71,7 +71,8 @@ class _OptsInit(C.Structure):
                 ("n_w_LS", C.c_int), ("w_LS", C.POINTER(C.c_double)),
                 ("sd_conc_large_tail", C.c_int), ("no_ccn_at_init", C.c_int),
                 ("n_dry_sizes", C.c_int), ("dry_sizes", _DrySize * MAX_SIZES),
-                ("n_aerosol_conc_factor", C.c_int), ("aerosol_conc_factor", C.POINTER(C.c_double))]
+                ("n_aerosol_conc_factor", C.c_int), ("aerosol_conc_factor", C.POINTER(C.c_double)),
+                ("sstp_cond_mix", C.c_int)]
 
 
 class _Opts(C.Structure):

@@ -226,7 +226,7 @@ def th_dry2std(th_dry, rv):
     return th_dry / (1 + rv * R_v / R_d) ** (R_d / c_pd)
 
 
-def cond_substepping_scenario(lib, backend, RH_formula, sstp_cond, constp, step_count=100):
+def cond_substepping_scenario(lib, backend, RH_formula, sstp_cond, constp, step_count=100, exact_sstp=False, mixing=True):
     """the per-cell rows of tests/python/physics/lgrngn_cond_substepping.py:152-250: 0-D parcel with a CCN and a GCCN mode,
     100 steps in supersaturated air after an abrupt change of density (exercises rhod sub-stepping), then 100 steps of
     evaporation; returns the quantities the reference pins in refdata/lgrngn_cond_substepping_refdata.csv"""
@@ -239,6 +239,8 @@ def cond_substepping_scenario(lib, backend, RH_formula, sstp_cond, constp, step_
     oi.n_sd_max = 1000
     oi.sstp_cond = sstp_cond
     oi.RH_formula = RH_formula
+    oi.exact_sstp_cond = int(exact_sstp)          # per-particle sub-stepping (lgrngn_cond_substepping.py:158-160)
+    oi.sstp_cond_mix = int(mixing)
     o = lib.opts_t()
     o.adve = o.sedi = o.coal = 0
     o.RH_max = 1.005
@@ -306,9 +308,9 @@ COND_SUBSTEPPING_TOL = {     # tests/python/physics/lgrngn_cond_substepping_test
     "th_post_cond": ("rtol", 1e-4), "rv_post_cond": ("rtol", 1e-3)}
 
 
-def load_cond_substepping_rows():
+def load_cond_substepping_rows(which="percell"):
     import csv
-    path = os.path.join(ROOT, "tests", "golden", "lgrngn_cond_substepping_percell.csv")
+    path = os.path.join(ROOT, "tests", "golden", "lgrngn_cond_substepping_%s.csv" % which)
     with open(path) as fh:
         return list(csv.DictReader(fh))
 

@@ -64,14 +64,11 @@ def test_cpu_backends_are_not_part_of_the_product():
 
 @pytest.mark.parametrize("field,value,message", [
     ("chem_switch", 1, "chemistry"), ("ice_switch", 1, "ice"), ("turb_coal_switch", 1, "turbulence"),
-    ("turb_cond_switch", 1, "turbulence"), ("exact_sstp_cond", 1, None)])
+    ("turb_cond_switch", 1, "turbulence")])
 def test_out_of_scope_options_are_refused_loudly(field, value, message):
     lib = L.b200()
     oi, _, _ = S.box_golovin(lib, n_sd=64)
     setattr(oi, field, value)
-    if field == "exact_sstp_cond":
-        oi.sstp_cond = 4
-        message = "per-particle condensation sub-stepping"
     with pytest.raises(RuntimeError, match=message):
         lib.factory(L.backend_t.CUDA, oi)
 

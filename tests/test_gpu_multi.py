@@ -80,10 +80,13 @@ def test_multi_cuda_single_slab_is_cuda(b200):
         assert np.array_equal(a, b)
 
 
-def test_multi_cuda_full_microphysics_runs_and_conserves(b200, monkeypatch):
-    """cond + coal + sedi + adve over 3 slabs: dry aerosol volume is conserved up to what rains out"""
+@pytest.mark.parametrize("exact_sstp", [0, 1])
+def test_multi_cuda_full_microphysics_runs_and_conserves(b200, monkeypatch, exact_sstp):
+    """cond + coal + sedi + adve over 3 slabs: dry aerosol volume is conserved up to what rains out; with per-particle
+    sub-stepping the migrants also carry their rv / th / rhod records (particles_impl.ipp:452-459)"""
     monkeypatch.setenv("LCX_SLABS_ON_ONE_DEVICE", "1")
-    oi, o, f = S.box_3d(b200, nx=6, ny=4, nz=6, sd_conc=24, rain_mode=True, cx=0.5)
+    oi, o, f = S.box_3d(b200, nx=6, ny=4, nz=6, sd_conc=24, rain_mode=True, cx=0.5, sstp_cond=2 if exact_sstp else 1)
+    oi.exact_sstp_cond = exact_sstp
     oi.dev_count = 3
     p = b200.factory(L.backend_t.multi_CUDA, oi)
     p.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
@@ -99,6 +102,7 @@ def test_multi_cuda_full_microphysics_runs_and_conserves(b200, monkeypatch):
     v1 = dry_volume()
     fallen = p.diag_puddle()["dry_volume"]
     assert abs(v1 + fallen - v0) <= 1e-10 * v0, (v0, v1, fallen)
+    assert np.isfinite(f["th"]).all() and np.isfinite(f["rv"]).all() and (f["rv"] > 0).all()
 
 
 @pytest.mark.skipif("n_devices() < 2")

@@ -314,3 +314,53 @@ def test_strided_eulerian_arrays(b200):
     a, b = run(False), run(True)
     for u, v in zip(a, b):
         assert np.array_equal(u, v)
+
+
+@pytest.mark.parametrize("mixing", [1, 0])
+@pytest.mark.parametrize("sstp_cond", [2, 5])
+def test_parcel_perparticle_substepping(ref, b200, sstp_cond, mixing):
+    """exact_sstp_cond: every SD sub-steps in its own thermodynamic state; same tolerance
+    class as the per-cell path (the root solve), th / rv follow"""
+    def drive(lib):
+        oi, o, f = S.parcel(lib, n_sd=4096, dt=1.0, sstp_cond=sstp_cond)
+        oi.exact_sstp_cond, oi.sstp_cond_mix = 1, mixing
+        p = lib.factory(L.backend_t.serial if lib.name == "reference" else L.backend_t.CUDA, oi)
+        p.init(f["th"], f["rv"], f["rhod"])
+        out = []
+        for step in range(30):
+            f["rhod"] *= 0.9995
+            p.step_sync(o, f["th"], f["rv"], f["rhod"])
+            p.step_async(o)
+            out.append((f["th"][0], f["rv"][0], p.get_attr("rw2")))
+        return out
+    a, b = drive(ref), drive(b200)
+    for step, ((th_r, rv_r, rw_r), (th_n, rv_n, rw_n)) in enumerate(zip(a, b)):
+        err = np.abs(rw_r - rw_n) / rw_r
+        if step == 0:
+            assert err.max() < sstp_cond * 2.0 ** -15, (step, err.max())
+        assert np.quantile(err, 0.99) < (step + 1) * sstp_cond * 2.0 ** -15, (step, np.quantile(err, 0.99))
+        assert np.median(err) < 1e-7, (step, np.median(err))
+        assert abs(th_r - th_n) / th_r < 1e-9, (step, abs(th_r - th_n) / th_r)
+        assert abs(rv_r - rv_n) / rv_r < 1e-7, (step, abs(rv_r - rv_n) / rv_r)
+    assert a[-1][2].max() > 1e-11, "nothing activated - the test would be vacuous"
+
+
+@pytest.mark.parametrize("mixing", [1, 0])
+def test_perparticle_substepping_3d_with_transport(ref, b200, mixing):
+    """the per-SD records of rv, th, rhod travel with the SDs through advection, coalescence, removal and re-layout"""
+    def setup(lib):
+        oi, o, f = S.box_3d(lib, nx=6, ny=5, nz=8, sd_conc=32, rain_mode=True, sstp_cond=3)
+        oi.exact_sstp_cond, oi.sstp_cond_mix = 1, mixing
+        return oi, o, f
+
+    def check(step, p_r, p_n, f_r, f_n):
+        n_r, n_n = p_r.get_n(), p_n.get_n()
+        assert n_r.size == n_n.size, step
+        assert np.array_equal(n_r, n_n), "multiplicities differ at step %d" % step
+        assert np.array_equal(p_r.get_attr("rd3"), p_n.get_attr("rd3")), step
+        for k in ("x", "y"):
+            assert np.array_equal(p_r.get_attr(k), p_n.get_attr(k)), (k, step)
+        assert S.rel_err(p_r.get_attr("rw2"), p_n.get_attr("rw2")) < (step + 2) * 3 * 2.0 ** -15, step
+        assert S.rel_err(f_r["th"], f_n["th"]) < 1e-9, (step, S.rel_err(f_r["th"], f_n["th"]))
+        assert S.rel_err(f_r["rv"], f_n["rv"]) < 1e-7, (step, S.rel_err(f_r["rv"], f_n["rv"]))
+    S.run_pair(ref, b200, setup, 5, on_step=check)

@@ -2,6 +2,7 @@
 """Generates the committed fixtures under tests/golden/ (run in the build container, where /root/reference exists).
 
   lgrngn_cond_substepping_percell.csv   the 56 per-cell-substepping rows (exact_sstp = False) of the reference's own fixture
+  lgrngn_cond_substepping_perparticle.csv   its 112 per-particle rows without adaptation (exact_sstp = True, mixing on / off)
                                         tests/python/physics/refdata/lgrngn_cond_substepping_refdata.csv
   bott1800.npy                          the 149-value Bott bin-model mass-density array embedded in the reference's
                                         tests/python/physics/coalescence_hall_davis_no_waals.py:82
@@ -35,6 +36,13 @@ def main():
         w.writeheader()
         w.writerows(rows)
     print("cond substepping rows:", len(rows))
+    with open(src) as fh:
+        rows = [r for r in csv.DictReader(fh) if r["exact_sstp"] == "True" and r["adaptive"] == "False"]
+    with open(os.path.join(OUT, "lgrngn_cond_substepping_perparticle.csv"), "w", newline="") as fh:
+        w = csv.DictWriter(fh, fieldnames=list(rows[0].keys()))
+        w.writeheader()
+        w.writerows(rows)
+    print("per-particle (non-adaptive) cond substepping rows:", len(rows))
 
     text = open(os.path.join(REF, "tests", "python", "physics", "coalescence_hall_davis_no_waals.py")).read()
     arr = re.search(r"bott1800 = np.array\(\[(.*?)\]\)", text, re.S).group(1)
