@@ -84,6 +84,8 @@ typedef struct
   int pure_const_multi;       /* constant-multiplicity run: report probabilities >= 1                         */
   int allow_sstp_cond;        /* keep old rv/th/rhod for per-cell condensation sub-stepping                   */
   int exact_sstp_cond;        /* per-particle sub-stepping: every SD carries its own rv, th, rhod (, p) history */
+  int sstp_cond_act;          /* > 1: SDs crossing their critical radius sub-step this many times; keeps rc2 per SD */
+  double rc2_T;               /* temperature [deg C] at which that critical radius is evaluated (opts_init.rc2_T) */
 } lcx_config;
 
 typedef struct
@@ -148,6 +150,10 @@ int  lcx_sstp_save(lcx_engine *e);                              /* sstp_save.ipp
 /* per-particle condensation sub-stepping, all sub-steps of one time step (particles_step.ipp:199-236,                 */
 /* condensation/perparticle/*.ipp); mix != 0: the vapour / heat exchanged by the SDs of a cell is shared after each sub-step */
 int  lcx_cond_perparticle(lcx_engine *e, double dt, double RH_max, int sstp_cond, int mix);
+/* the same with the number of sub-steps chosen per SD (perparticle_nomixing_adaptive_sstp_cond.ipp:8-335); no mixing      */
+int  lcx_cond_perparticle_adaptive(lcx_engine *e, double dt, double RH_max, int sstp_cond_max, int sstp_cond_act,
+                                   double drw2_eps, double drw2_max);
+int  lcx_hskpng_rc2(lcx_engine *e);                             /* hskpng_rc2.ipp:13-32: critical radii flagged invalid */
 int  lcx_cond(lcx_engine *e, double dt_sub, double RH_max, int step, int sstp_cond);   /* percell/particles_impl_cond.ipp:13-139, common/particles_impl_update_th_rv.ipp:74-191 */
 
 /* ---- coalescence --------------------------------------------------------------------------------------- */

@@ -124,6 +124,8 @@ void lgc_opts_init_defaults(lgc_opts_init *o)
   o->aerosol_independent_of_rhod = d.aerosol_independent_of_rhod;
   o->sd_conc_large_tail = d.sd_conc_large_tail; o->no_ccn_at_init = d.no_ccn_at_init;
   o->sstp_cond_mix = d.sstp_cond_mix;
+  o->adaptive_sstp_cond = d.adaptive_sstp_cond; o->sstp_cond_act = d.sstp_cond_act;
+  o->sstp_cond_adapt_drw2_eps = d.sstp_cond_adapt_drw2_eps; o->sstp_cond_adapt_drw2_max = d.sstp_cond_adapt_drw2_max; o->rc2_T = d.rc2_T;
 }
 
 void lgc_opts_defaults(lgc_opts *o)
@@ -160,6 +162,8 @@ int lgc_create(const lgc_opts_init *c, lgc_handle **out)
     if (c->n_w_LS > 0) o.w_LS.assign(c->w_LS, c->w_LS + c->n_w_LS);
     o.sd_conc_large_tail = c->sd_conc_large_tail; o.no_ccn_at_init = c->no_ccn_at_init;
     o.sstp_cond_mix = c->sstp_cond_mix;
+    o.adaptive_sstp_cond = c->adaptive_sstp_cond; o.sstp_cond_act = c->sstp_cond_act;
+    o.sstp_cond_adapt_drw2_eps = c->sstp_cond_adapt_drw2_eps; o.sstp_cond_adapt_drw2_max = c->sstp_cond_adapt_drw2_max; o.rc2_T = c->rc2_T;
     if (c->n_aerosol_conc_factor > 0) o.aerosol_conc_factor.assign(c->aerosol_conc_factor, c->aerosol_conc_factor + c->n_aerosol_conc_factor);
     for (int i = 0; i < c->n_dry_sizes; ++i)
     {

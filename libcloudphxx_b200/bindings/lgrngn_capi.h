@@ -61,6 +61,8 @@ typedef struct
   int n_aerosol_conc_factor;
   const double *aerosol_conc_factor;
   int sstp_cond_mix;               /* per-particle sub-stepping: share vapour / heat inside a cell after each sub-step */
+  int adaptive_sstp_cond, sstp_cond_act;
+  double sstp_cond_adapt_drw2_eps, sstp_cond_adapt_drw2_max, rc2_T;
 } lgc_opts_init;
 
 typedef struct

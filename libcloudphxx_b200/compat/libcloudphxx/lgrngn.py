@@ -90,9 +90,8 @@ class opts_t:
 class opts_init_t:
     """lgrngn::opts_init_t (opts_init.hpp:29-253): the defaults come from the library itself"""
     _EXTRA = dict(src_x0=0., src_x1=0., src_y0=0., src_y1=0., src_z0=0., src_z1=0., rlx_switch=False,
-                  sstp_cond_act=1, rc2_T=10., sstp_chem=1, supstp_rlx=1, rlx_bins=0, rlx_sd_per_bin=0, rlx_timescale=1.,
-                  src_type=src_t.off, chem_rho=0., diag_incloud_time=False, time_dep_ice_nucl=False, adaptive_sstp_cond=False,
-                  sstp_cond_adapt_drw2_eps=1e-3, sstp_cond_adapt_drw2_max=2, y0=0., y1=1.)
+                  sstp_chem=1, supstp_rlx=1, rlx_bins=0, rlx_sd_per_bin=0, rlx_timescale=1.,
+                  src_type=src_t.off, chem_rho=0., diag_incloud_time=False, time_dep_ice_nucl=False, y0=0., y1=1.)
 
     def __init__(self):
         object.__setattr__(self, "_flat", _library().opts_init_t())
@@ -138,8 +137,7 @@ class opts_init_t:
         flat = object.__getattribute__(self, "_flat")
         # std::map iteration order of the reference: ascending (kappa, rd_insol)
         flat.dry_distros = [_L.callable_distro(k[0], fn, k[1]) for k, fn in sorted(self._dry_distros.items())]
-        refused = {"rlx_switch": "aerosol relaxation (rlx_switch)", "diag_incloud_time": "diag_incloud_time",
-                   "adaptive_sstp_cond": "adaptive per-particle condensation sub-stepping (adaptive_sstp_cond)"}
+        refused = {"rlx_switch": "aerosol relaxation (rlx_switch)", "diag_incloud_time": "diag_incloud_time"}
         for k, what in refused.items():
             if getattr(self, k, False):
                 raise RuntimeError("libcloudph++: %s is not part of the B200 back-end" % what)

@@ -61,11 +61,12 @@ namespace
       (lcx::tmin((k + 1) * g.dz, g.z1) - lcx::tmax(k * g.dz, g.z0)));
   }
 
-  __global__ void k_fill_tail(size_t first, size_t count, lcx::real_t *vt, uint32_t *sid, uint32_t *ijk, const uint32_t *ijk_src)
+  __global__ void k_fill_tail(size_t first, size_t count, lcx::real_t *vt, lcx::real_t *rc2, uint32_t *sid, uint32_t *ijk, const uint32_t *ijk_src)
   {
     const size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (t >= count) return;
     vt[first + t] = lcx::real_t(-1);          // "invalid": resize value of vt (particles_impl.ipp:446, hskpng_resize.ipp:14-20)
+    if (rc2) rc2[first + t] = lcx::real_t(-1);   // the same for rc2 (particles_impl.ipp:490)
     sid[first + t] = uint32_t(first + t);
     ijk[first + t] = ijk_src ? ijk_src[t] : 0u;
   }
@@ -164,7 +165,11 @@ int lcx_create(const lcx_config *cfg, lcx_engine **out)
     e->sd[0].alloc(cap, g.nx, g.ny, g.nz);
     e->sd[1].alloc(cap, g.nx, g.ny, g.nz);
     if (cfg->exact_sstp_cond && cfg->allow_sstp_cond)
-      for (int b = 0; b < 2; ++b) e->sd[b].alloc_pp(cap, cfg->const_p != 0);
+      for (int b = 0; b < 2; ++b)
+      {
+        e->sd[b].alloc_pp(cap, cfg->const_p != 0);
+        if (cfg->sstp_cond_act > 1) e->sd[b].rc2.alloc(cap);
+      }
     for (int b = 0; b < 2; ++b) { e->key[b].alloc(cap); e->val[b].alloc(cap); }
     e->un.alloc(cap); e->flag.alloc(cap); e->u01.alloc(cap); e->n_filtered.alloc(cap); e->tmp_real.alloc(cap);
 
@@ -346,7 +351,7 @@ int lcx_sd_append(lcx_engine *e, int64_t count, const uint64_t *n, const void *r
     if (e->grid.nz) up(s.z.p + first, z, cnt * sizeof(real_t));
     uint32_t *ijk_dev = nullptr;
     if (ijk) { ijk_dev = e->key[0].p; up(ijk_dev, ijk, cnt * sizeof(uint32_t)); }
-    k_fill_tail<<<div_up(cnt, 256), 256, 0, e->stream>>>(first, cnt, s.vt.p, s.sid.p, s.ijk.p, ijk_dev);
+    k_fill_tail<<<div_up(cnt, 256), 256, 0, e->stream>>>(first, cnt, s.vt.p, s.rc2.p, s.sid.p, s.ijk.p, ijk_dev);
     LCX_CUDA(cudaGetLastError()); ++e->launches;
     LCX_CUDA(cudaStreamSynchronize(e->stream));
     e->n_part = first + cnt;
@@ -394,6 +399,11 @@ int lcx_sstp_save(lcx_engine *e) { return guarded([&] { use_device(e); lcx::sstp
 
 int lcx_cond_perparticle(lcx_engine *e, double dt, double RH_max, int sstp_cond, int mix)
 { return guarded([&] { use_device(e); lcx::cond_perparticle(e, dt, RH_max, sstp_cond, mix != 0); }); }
+
+int lcx_cond_perparticle_adaptive(lcx_engine *e, double dt, double RH_max, int sstp_cond_max, int sstp_cond_act, double drw2_eps, double drw2_max)
+{ return guarded([&] { use_device(e); lcx::cond_perparticle_adaptive(e, dt, RH_max, sstp_cond_max, sstp_cond_act, drw2_eps, drw2_max); }); }
+
+int lcx_hskpng_rc2(lcx_engine *e) { return guarded([&] { use_device(e); lcx::hskpng_rc2(e); }); }
 
 int lcx_cond(lcx_engine *e, double dt_sub, double RH_max, int step, int sstp_cond)
 { return guarded([&] { use_device(e); lcx::cond(e, dt_sub, RH_max, step, sstp_cond); }); }
@@ -470,7 +480,7 @@ int lcx_migr_send(lcx_engine *src, int side, lcx_engine *dst, int64_t count)
 int lcx_migr_real_attrs(lcx_engine *e, int *count)
 {
   *count = 4 + (e->grid.nx ? 1 : 0) + (e->grid.ny ? 1 : 0) + (e->grid.nz ? 1 : 0);
-  if (e->cfg.exact_sstp_cond && e->cfg.allow_sstp_cond) *count += e->cfg.const_p ? 4 : 3;
+  if (e->cfg.exact_sstp_cond && e->cfg.allow_sstp_cond) *count += (e->cfg.const_p ? 4 : 3) + (e->cfg.sstp_cond_act > 1 ? 1 : 0);
   return 0;
 }
 

@@ -71,6 +71,7 @@ namespace lcx
     struct coal_ctx
     {
       n_t *n; real_t *rw2, *rd3, *vt, *kpa;
+      real_t *rc2;            // nullptr unless activation sub-stepping keeps critical radii (coal.ipp:527-541)
       const real_t *dv;
       coal_kernel_params<real_t> kp;
       real_t dt;
@@ -88,6 +89,7 @@ namespace lcx
       const real_t rd3_new = col_no * rd3_hi + rd3_lo;
       cx.rd3[lo] = rd3_new;
       cx.vt[lo] = real_t(-1);
+      if (cx.rc2) cx.rc2[lo] = real_t(-1);
       if (cx.multi_kappa)
       {
         // rd3-weighted mean of kappa, applied once per collision: weighted_summator, coal.ipp:59-96
@@ -309,7 +311,7 @@ namespace lcx
     }
 
     coal_ctx cx;
-    cx.n = s.n.p; cx.rw2 = s.rw2.p; cx.rd3 = s.rd3.p; cx.vt = s.vt.p; cx.kpa = s.kpa.p;
+    cx.n = s.n.p; cx.rw2 = s.rw2.p; cx.rd3 = s.rd3.p; cx.vt = s.vt.p; cx.kpa = s.kpa.p; cx.rc2 = s.rc2.p;
     cx.dv = e->dv.p;
     cx.kp.kind = e->cfg.kernel;
     cx.kp.has_multiplier = (e->cfg.kernel == KERNEL_GEOMETRIC && e->cfg.n_kernel_user_params == 1);

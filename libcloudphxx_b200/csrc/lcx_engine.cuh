@@ -52,6 +52,7 @@ namespace lcx
     dbuf<real_t> rd3, rw2, kpa, vt, x, y, z;
     dbuf<idx_t> sid, ijk;
     dbuf<real_t> pp_rv, pp_th, pp_rh, pp_p;      // per-particle sub-stepping: the SD's own record of rv, th, rhod, p (sstp_tmp_*)
+    dbuf<real_t> rc2;                            // critical radius squared at rc2_T (only with sstp_cond_act > 1)
     void alloc_pp(size_t cap, bool with_p) { pp_rv.alloc(cap); pp_th.alloc(cap); pp_rh.alloc(cap); if (with_p) pp_p.alloc(cap); }
     void alloc(size_t cap, bool has_x, bool has_y, bool has_z)
     {
@@ -63,7 +64,7 @@ namespace lcx
     }
     void release()
     { n.release(); rd3.release(); rw2.release(); kpa.release(); vt.release(); x.release(); y.release(); z.release(); sid.release(); ijk.release();
-      pp_rv.release(); pp_th.release(); pp_rh.release(); pp_p.release(); }
+      pp_rv.release(); pp_th.release(); pp_rh.release(); pp_p.release(); rc2.release(); }
   };
 
   // grid description handed to kernels by value
@@ -221,6 +222,8 @@ namespace lcx
   // ---- lcx_cond.cu -----------------------------------------------------------------------------------
   void cond(lcx_engine *e, real_t dt_sub, real_t RH_max, int step, int sstp);
   void cond_perparticle(lcx_engine *e, real_t dt, real_t RH_max, int sstp, bool mix);
+  void cond_perparticle_adaptive(lcx_engine *e, real_t dt, real_t RH_max, int sstp_max, int sstp_act, real_t drw2_eps, real_t drw2_max);
+  void hskpng_rc2(lcx_engine *e);
   void pp_save(lcx_engine *e, size_t first);                 // sstp_tmp_x[i] = x[ijk[i]] for i >= first (sstp_save.ipp, init_perparticle_sstp.ipp)
   void cell_sum(lcx_engine *e, const real_t *per_sd, real_t *out);       // plain per-cell sums of a per-SD array
   void cell_max_sid(lcx_engine *e, real_t *out);             // largest storage index in every cell (as real)

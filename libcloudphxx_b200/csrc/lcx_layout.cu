@@ -74,7 +74,7 @@ namespace lcx
       if (t < n) { key[t] = relayout_key(g, ijk[t], rw2[t]); val[t] = uint32_t(t); }
     }
 
-    struct gather_set { const void *src[14]; void *dst[14]; int width[14]; int n; };
+    struct gather_set { const void *src[15]; void *dst[15]; int width[15]; int n; };
 
     // every attribute of the survivors moves to its sorted position; the cell index comes from the sorted key
     __global__ void __launch_bounds__(TPB) k_gather(size_t n, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ key, int class_bits,
@@ -144,7 +144,7 @@ namespace lcx
     __global__ void __launch_bounds__(TPB) k_rcyc_copy(size_t n_flagged, size_t n, const uint32_t *__restrict__ order, n_t *__restrict__ ns,
                                                       real_t *__restrict__ rd3, real_t *__restrict__ rw2, real_t *__restrict__ kpa, real_t *__restrict__ vt,
                                                       real_t *__restrict__ x, real_t *__restrict__ y, real_t *__restrict__ z,
-                                                      real_t *__restrict__ p0, real_t *__restrict__ p1, real_t *__restrict__ p2, real_t *__restrict__ p3)
+                                                      real_t *__restrict__ p0, real_t *__restrict__ p1, real_t *__restrict__ p2, real_t *__restrict__ p3, real_t *__restrict__ rc2)
     {
       const size_t q = size_t(blockIdx.x) * TPB + threadIdx.x;
       if (q >= n_flagged) return;
@@ -154,6 +154,7 @@ namespace lcx
       if (y) y[dst] = y[src];
       if (z) z[dst] = z[src];
       if (p0) { p0[dst] = p0[src]; p1[dst] = p1[src]; p2[dst] = p2[src]; if (p3) p3[dst] = p3[src]; }      // sstp_tmp_* travel too (distmem_real_vctrs)
+      if (rc2) rc2[dst] = rc2[src];
       const n_t m = ns[src];
       ns[dst] = m - m / 2;
       ns[src] = m / 2;
@@ -209,7 +210,7 @@ namespace lcx
       cur = radix_sort_pairs(e, n, 0, bits - shift < 32 ? bits - shift : 32, key, val, cur);
     }
     LCX_LAUNCH(e, k_rcyc_copy, div_up(n_flagged, TPB), TPB, 0, n_flagged, n, val[cur], s.n.p, s.rd3.p, s.rw2.p, s.kpa.p, s.vt.p, s.x.p, s.y.p, s.z.p,
-               s.pp_rv.p, s.pp_th.p, s.pp_rh.p, s.pp_p.p);
+               s.pp_rv.p, s.pp_th.p, s.pp_rh.p, s.pp_p.p, s.rc2.p);
     e->keys_ready = 0;
   }
 
@@ -253,6 +254,7 @@ namespace lcx
       add(G, s.vt.p, a.vt.p, 8); add(G, s.x.p, a.x.p, 8); add(G, s.y.p, a.y.p, 8); add(G, s.z.p, a.z.p, 8);
       add(G, s.sid.p, a.sid.p, 4);
       add(G, s.pp_rv.p, a.pp_rv.p, 8); add(G, s.pp_th.p, a.pp_th.p, 8); add(G, s.pp_rh.p, a.pp_rh.p, 8); add(G, s.pp_p.p, a.pp_p.p, 8);
+      add(G, s.rc2.p, a.rc2.p, 8);
       LCX_LAUNCH(e, k_gather, div_up(n_new, TPB), TPB, 0, n_new, e->val[res].p, e->key[res].p, g.class_bits, a.ijk.p, G);
     }
     e->cur ^= 1;

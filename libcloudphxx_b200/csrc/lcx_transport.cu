@@ -295,7 +295,7 @@ namespace lcx
       val[slot] = uint32_t(t);
     }
 
-    struct mig_attrs { const real_t *src[11]; int n; int x_slot; };
+    struct mig_attrs { const real_t *src[12]; int n; int x_slot; };
 
     __global__ void __launch_bounds__(TPB) k_mig_pack(unsigned count, const uint32_t *__restrict__ val, mig_attrs A, n_t *__restrict__ ns,
                                                      real_t lcl, real_t rmt, n_t *__restrict__ out_n, real_t *__restrict__ out_real)
@@ -313,7 +313,7 @@ namespace lcx
       ns[ph] = 0;                                             // flag_lft / flag_rgt: unpack.ipp:122-145 (its sort key already says "gone")
     }
 
-    struct mig_dst { real_t *dst[11]; int n; int x_slot; };
+    struct mig_dst { real_t *dst[12]; int n; int x_slot; };
 
     __global__ void __launch_bounds__(TPB) k_mig_unpack(unsigned count, size_t n_part_old, size_t sid_first, mig_dst A, n_t *__restrict__ ns, idx_t *__restrict__ sid,
                                                        const n_t *__restrict__ in_n, const real_t *__restrict__ in_real,
@@ -346,6 +346,7 @@ namespace lcx
       if (e->grid.ny) list[n++] = s.y.p;
       if (e->grid.nz) list[n++] = s.z.p;
       if (s.pp_rv.p) { list[n++] = s.pp_rv.p; list[n++] = s.pp_th.p; list[n++] = s.pp_rh.p; if (s.pp_p.p) list[n++] = s.pp_p.p; }   // particles_impl.ipp:452-459
+      if (s.rc2.p) list[n++] = s.rc2.p;                                                                                           // particles_impl.ipp:488-491
       return n;
     }
   }
@@ -397,7 +398,7 @@ namespace lcx
       if (count > e->mig_cap) throw error("migration buffer overflow: " + std::to_string(count) + " super-droplets cross one slab face, capacity " + std::to_string(e->mig_cap));
       int bits = 0; { uint64_t v = e->sid_hi ? e->sid_hi - 1 : 0; while (v) { ++bits; v >>= 1; } if (bits == 0) bits = 1; }
       const int res = radix_sort_pairs(e, count, 0, bits, mk, mv, 0);
-      mig_attrs A; real_t *list[11];
+      mig_attrs A; real_t *list[12];
       A.n = fill_attr_list(e, list, &A.x_slot);
       for (int a = 0; a < A.n; ++a) A.src[a] = list[a];
       const real_t lcl = side == 0 ? e->grid.x0 : e->grid.x1;
@@ -413,7 +414,7 @@ namespace lcx
     if (e->n_part + size_t(count) > e->cap)
       throw error("n_sd_max (" + std::to_string(e->cap) + ") < n_part (" + std::to_string(e->n_part + size_t(count)) + ")");
     sd_arrays &s = e->S();
-    mig_dst A; real_t *list[11];
+    mig_dst A; real_t *list[12];
     A.n = fill_attr_list(e, list, &A.x_slot);
     for (int a = 0; a < A.n; ++a) A.dst[a] = list[a];
     if (e->sid_hi + size_t(count) > e->cap) densify_sid(e);

@@ -191,8 +191,6 @@ namespace libcloudphxx
             throw std::runtime_error("libcloudph++: SGS turbulence for super-droplets (turb_*_switch) is not part of the B200 back-end");
           if (oi.src_type != src_t::off) throw std::runtime_error("libcloudph++: aerosol sources (src_type) are not part of the B200 back-end");
           if (oi.rlx_switch) throw std::runtime_error("libcloudph++: aerosol relaxation (rlx_switch) is not part of the B200 back-end");
-          if (oi.adaptive_sstp_cond || oi.sstp_cond_act > 1)
-            throw std::runtime_error("libcloudph++: adaptive per-particle condensation sub-stepping (adaptive_sstp_cond, sstp_cond_act) is not available yet in the B200 back-end");
           if (oi.diag_incloud_time) throw std::runtime_error("libcloudph++: diag_incloud_time is not part of the B200 back-end");
           if (oi.kernel == kernel_t::onishi_hall || oi.kernel == kernel_t::onishi_hall_davis_no_waals)
             throw std::runtime_error("libcloudph++: To use the turbulent Onishis kernel, set turb_coal_switch=True");
@@ -253,6 +251,10 @@ namespace libcloudphxx
             throw std::runtime_error("libcloudph++: Adaptive condensation substepping (opts_init.adaptive_sstp_cond) works oly for per-particle substepping (opts_init.exact_sstp_cond)");
           if (!oi.sstp_cond_mix && !oi.exact_sstp_cond)
             throw std::runtime_error("libcloudph++: Mixing of rv and th (opts_init.sstp_cond_mix) can only be disable for per-particle substepping (opts_init.exact_sstp_cond)");
+          if (oi.sstp_cond_mix && oi.adaptive_sstp_cond && oi.exact_sstp_cond)
+            throw std::runtime_error("libcloudph++: Adaptive cond substepping (opts_init.adaptive_sstp_cond) with per-particle substepping (opts_init.exact_sstp_cond) requires mixing of th and rv between subteps (opts_init.sstp_cond_mix) to be disabled");
+          if (oi.sstp_cond_act > 1 && (oi.sstp_cond_mix || !oi.exact_sstp_cond || !oi.adaptive_sstp_cond))
+            throw std::runtime_error("libcloudph++: number of substeps for activation (opts_init.sstp_cond_act) can be greater than 1 only if mixing of rv and th (opts_init.sstp_cond_mix) is disabled and if per-particle condensation substepping is used (opts_init.exact_sstp_cond) and if adaptive substepping is used (opts_init.adaptive_sstp_cond)");
         }
 
         void check_courants(const arrinfo_t<real_t> &cx, const arrinfo_t<real_t> &cy, const arrinfo_t<real_t> &cz) const
@@ -379,6 +381,8 @@ namespace libcloudphxx
           c.pure_const_multi = pure_const_multi;
           c.allow_sstp_cond = allow_sstp_cond;
           c.exact_sstp_cond = oi.exact_sstp_cond;
+          c.sstp_cond_act = oi.sstp_cond_act;
+          c.rc2_T = oi.rc2_T;
           std::vector<real_t> eff;
           if (oi.coal_switch) eff = init_kernel(c);
           chk(lcx_create(&c, &e));
@@ -466,6 +470,7 @@ namespace libcloudphxx
             chk(lcx_set_vt0_table(e, vt0.data(), int(vt0.size())));
           }
           chk(lcx_hskpng_vterm(e, 1));
+          chk(lcx_hskpng_rc2(e));                        // critical radii for activation sub-stepping (particles_init.ipp:116-117)
           chk(lcx_sstp_save(e));
           chk(lcx_post_copy(e, 0, /*keep_all=*/1));      // hskpng_count(): group by the cells assigned at creation
           engine.seed(oi.rng_seed);
@@ -858,8 +863,13 @@ namespace libcloudphxx
           if (opts.cond)
           {
             chk(lcx_hskpng_mfp(e));          // from the T, p left by the previous Tpr, as the reference does (particles_step.ipp:189-194)
-            if (oi.exact_sstp_cond && sstp_cond > 1)           // per-particle sub-stepping: particles_step.ipp:199-236
-              chk(lcx_cond_perparticle(e, dt, opts.RH_max, sstp_cond, oi.sstp_cond_mix));
+            if (oi.exact_sstp_cond && (sstp_cond > 1 || oi.sstp_cond_act > 1))     // per-particle sub-stepping: particles_step.ipp:199-236
+            {
+              if (oi.adaptive_sstp_cond)
+                chk(lcx_cond_perparticle_adaptive(e, dt, opts.RH_max, sstp_cond, oi.sstp_cond_act, oi.sstp_cond_adapt_drw2_eps, oi.sstp_cond_adapt_drw2_max));
+              else
+                chk(lcx_cond_perparticle(e, dt, opts.RH_max, sstp_cond, oi.sstp_cond_mix));
+            }
             else
               for (int step = 0; step < sstp_cond; ++step)
               {
@@ -923,6 +933,7 @@ namespace libcloudphxx
               chk(lcx_coal_flag(e, &flag));
               if (flag) ++sstp_coal;
             }
+            chk(lcx_hskpng_rc2(e));                       // collisions changed rd3 / kappa (particles_step.ipp:402-403)
           }
 
           if (n_dims > 0)

@@ -72,7 +72,8 @@ class _OptsInit(C.Structure):
                 ("sd_conc_large_tail", C.c_int), ("no_ccn_at_init", C.c_int),
                 ("n_dry_sizes", C.c_int), ("dry_sizes", _DrySize * MAX_SIZES),
                 ("n_aerosol_conc_factor", C.c_int), ("aerosol_conc_factor", C.POINTER(C.c_double)),
-                ("sstp_cond_mix", C.c_int)]
+                ("sstp_cond_mix", C.c_int), ("adaptive_sstp_cond", C.c_int), ("sstp_cond_act", C.c_int),
+                ("sstp_cond_adapt_drw2_eps", C.c_double), ("sstp_cond_adapt_drw2_max", C.c_double), ("rc2_T", C.c_double)]
 
 
 class _Opts(C.Structure):

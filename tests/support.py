@@ -226,7 +226,8 @@ def th_dry2std(th_dry, rv):
     return th_dry / (1 + rv * R_v / R_d) ** (R_d / c_pd)
 
 
-def cond_substepping_scenario(lib, backend, RH_formula, sstp_cond, constp, step_count=100, exact_sstp=False, mixing=True):
+def cond_substepping_scenario(lib, backend, RH_formula, sstp_cond, constp, step_count=100, exact_sstp=False, mixing=True,
+                              adaptive=False, sstp_cond_act=1, drw2_eps=None, drw2_max=None):
     """the per-cell rows of tests/python/physics/lgrngn_cond_substepping.py:152-250: 0-D parcel with a CCN and a GCCN mode,
     100 steps in supersaturated air after an abrupt change of density (exercises rhod sub-stepping), then 100 steps of
     evaporation; returns the quantities the reference pins in refdata/lgrngn_cond_substepping_refdata.csv"""
@@ -241,6 +242,9 @@ def cond_substepping_scenario(lib, backend, RH_formula, sstp_cond, constp, step_
     oi.RH_formula = RH_formula
     oi.exact_sstp_cond = int(exact_sstp)          # per-particle sub-stepping (lgrngn_cond_substepping.py:158-160)
     oi.sstp_cond_mix = int(mixing)
+    oi.adaptive_sstp_cond, oi.sstp_cond_act = int(adaptive), int(sstp_cond_act)          # lgrngn_cond_substepping.py:161-165
+    if drw2_eps is not None:
+        oi.sstp_cond_adapt_drw2_eps, oi.sstp_cond_adapt_drw2_max = drw2_eps, drw2_max
     o = lib.opts_t()
     o.adve = o.sedi = o.coal = 0
     o.RH_max = 1.005

@@ -32,6 +32,17 @@ def test_cond_perparticle_substepping_fixture(b200, row):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("row", S.load_cond_substepping_rows("adaptive"),
+                         ids=lambda r: "%s-sstp%s-constp%s-act%s" % (r["RH_formula"], r["sstp_cond"], r["constp"], r["sstp_cond_act"]))
+def test_cond_adaptive_substepping_fixture(b200, row):
+    """the 112 adaptive per-particle rows (sstp_cond_act 1 and 8) of the same reference file"""
+    res = S.cond_substepping_scenario(b200, L.backend_t.CUDA, RH_NAMES[row["RH_formula"]], int(row["sstp_cond"]), row["constp"] == "True",
+                                      exact_sstp=True, mixing=False, adaptive=True, sstp_cond_act=int(row["sstp_cond_act"]),
+                                      drw2_eps=float(row["sstp_cond_adapt_drw2_eps"]), drw2_max=float(row["sstp_cond_adapt_drw2_max"]))
+    bad = S.check_cond_substepping(res, row)
+    assert not bad, bad
+
+
 @pytest.mark.parametrize("vt", [L.vt_t.beard76, L.vt_t.beard77, L.vt_t.beard77fast])
 def test_hall_davis_coalescence_vs_bott(b200, vt):
     """tests/python/physics/coalescence_hall_davis_no_waals.py:82-105: mass-density spectrum after 1800 s vs Bott's bin model"""

@@ -364,3 +364,50 @@ def test_perparticle_substepping_3d_with_transport(ref, b200, mixing):
         assert S.rel_err(f_r["th"], f_n["th"]) < 1e-9, (step, S.rel_err(f_r["th"], f_n["th"]))
         assert S.rel_err(f_r["rv"], f_n["rv"]) < 1e-7, (step, S.rel_err(f_r["rv"], f_n["rv"]))
     S.run_pair(ref, b200, setup, 5, on_step=check)
+
+
+@pytest.mark.parametrize("sstp_cond,act", [(8, 1), (8, 4), (1, 4), (6, 1)])
+def test_parcel_adaptive_substepping(ref, b200, sstp_cond, act):
+    """adaptive_sstp_cond: the number of sub-steps is chosen per SD (and forced to sstp_cond_act when the SD crosses its
+    critical radius); decisions compare growth increments against thresholds, so besides the root-solve tolerance a
+    droplet may now and then take a different number of sub-steps in the two runs - bounded through quantiles"""
+    def drive(lib):
+        oi, o, f = S.parcel(lib, n_sd=4096, dt=1.0, sstp_cond=sstp_cond)
+        oi.exact_sstp_cond, oi.sstp_cond_mix, oi.adaptive_sstp_cond, oi.sstp_cond_act = 1, 0, 1, act
+        oi.sstp_cond_adapt_drw2_eps, oi.sstp_cond_adapt_drw2_max = 1e-3, 2.0
+        p = lib.factory(L.backend_t.serial if lib.name == "reference" else L.backend_t.CUDA, oi)
+        p.init(f["th"], f["rv"], f["rhod"])
+        out = []
+        for step in range(30):
+            f["rhod"] *= 0.9995
+            p.step_sync(o, f["th"], f["rv"], f["rhod"])
+            p.step_async(o)
+            out.append((f["th"][0], f["rv"][0], p.get_attr("rw2")))
+        return out
+    a, b = drive(ref), drive(b200)
+    for step, ((th_r, rv_r, rw_r), (th_n, rv_n, rw_n)) in enumerate(zip(a, b)):
+        err = np.abs(rw_r - rw_n) / rw_r
+        assert np.quantile(err, 0.99) < (step + 1) * 8 * 2.0 ** -15, (step, np.quantile(err, 0.99))
+        assert np.median(err) < 1e-7, (step, np.median(err))
+        assert abs(th_r - th_n) / th_r < 1e-8, (step, abs(th_r - th_n) / th_r)
+        assert abs(rv_r - rv_n) / rv_r < 1e-6, (step, abs(rv_r - rv_n) / rv_r)
+    assert a[-1][2].max() > 1e-11, "nothing activated - the test would be vacuous"
+
+
+def test_adaptive_substepping_3d_with_coalescence(ref, b200):
+    """critical radii (rc2) are invalidated by collisions, refreshed, and travel with the SDs"""
+    def setup(lib):
+        oi, o, f = S.box_3d(lib, nx=6, ny=5, nz=8, sd_conc=32, rain_mode=True, sstp_cond=4)
+        oi.exact_sstp_cond, oi.sstp_cond_mix, oi.adaptive_sstp_cond, oi.sstp_cond_act = 1, 0, 1, 8
+        return oi, o, f
+
+    def check(step, p_r, p_n, f_r, f_n):
+        n_r, n_n = p_r.get_n(), p_n.get_n()
+        assert n_r.size == n_n.size, step
+        assert np.array_equal(n_r, n_n), "multiplicities differ at step %d" % step
+        assert np.array_equal(p_r.get_attr("rd3"), p_n.get_attr("rd3")), step
+        err = np.abs(p_r.get_attr("rw2") - p_n.get_attr("rw2")) / p_r.get_attr("rw2")
+        assert np.quantile(err, 0.999) < (step + 2) * 8 * 2.0 ** -15, (step, np.quantile(err, 0.999))
+        assert S.rel_err(f_r["th"], f_n["th"]) < 1e-8, (step, S.rel_err(f_r["th"], f_n["th"]))
+        assert S.rel_err(f_r["rv"], f_n["rv"]) < 1e-6, (step, S.rel_err(f_r["rv"], f_n["rv"]))
+    S.run_pair(ref, b200, setup, 5, on_step=check)

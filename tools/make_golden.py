@@ -3,6 +3,7 @@
 
   lgrngn_cond_substepping_percell.csv   the 56 per-cell-substepping rows (exact_sstp = False) of the reference's own fixture
   lgrngn_cond_substepping_perparticle.csv   its 112 per-particle rows without adaptation (exact_sstp = True, mixing on / off)
+  lgrngn_cond_substepping_adaptive.csv      its 112 adaptive per-particle rows (sstp_cond_act 1 and 8)
                                         tests/python/physics/refdata/lgrngn_cond_substepping_refdata.csv
   bott1800.npy                          the 149-value Bott bin-model mass-density array embedded in the reference's
                                         tests/python/physics/coalescence_hall_davis_no_waals.py:82
@@ -43,6 +44,13 @@ def main():
         w.writeheader()
         w.writerows(rows)
     print("per-particle (non-adaptive) cond substepping rows:", len(rows))
+    with open(src) as fh:
+        rows = [r for r in csv.DictReader(fh) if r["adaptive"] == "True"]
+    with open(os.path.join(OUT, "lgrngn_cond_substepping_adaptive.csv"), "w", newline="") as fh:
+        w = csv.DictWriter(fh, fieldnames=list(rows[0].keys()))
+        w.writeheader()
+        w.writerows(rows)
+    print("adaptive per-particle cond substepping rows:", len(rows))
 
     text = open(os.path.join(REF, "tests", "python", "physics", "coalescence_hall_davis_no_waals.py")).read()
     arr = re.search(r"bott1800 = np.array\(\[(.*?)\]\)", text, re.S).group(1)
