@@ -82,7 +82,7 @@ lcx_engine::~lcx_engine()
   th.release(); rv.release(); rhod.release(); p.release(); T.release(); RH.release(); eta.release(); dv.release();
   lambda_D.release(); lambda_K.release(); sstp_tmp_rv.release(); sstp_tmp_th.release(); sstp_tmp_rh.release();
   drw_mom3.release(); rw_mom3.release(); count_mom.release(); mom_partial.release();
-  courant_x.release(); courant_y.release(); courant_z.release(); w_LS.release(); cell_off.release();
+  courant_x.release(); courant_y.release(); courant_z.release(); w_LS.release(); cell_off.release(); cell_off_new.release(); arr_off.release(); mv_scan.release();
   vt0.release(); eff.release(); hist.release(); scan_tmp.release();
   for (int s = 0; s < 2; ++s) { for (int d = 0; d < 2; ++d) { mig_n[s][d].release(); mig_real[s][d].release(); } mig_key[s].release(); mig_val[s].release(); }
   scalars.release(); red_partial.release(); cell_tmp4.release();
@@ -154,7 +154,7 @@ int lcx_create(const lcx_config *cfg, lcx_engine **out)
       int bits = 0; for (uint64_t v = n_cell; v; v >>= 1) ++bits;
       const int spare = (8 - bits % 8) % 8;
       const char *env = std::getenv("LCX_SIZE_CLASS_BITS");
-      const int want = env ? std::atoi(env) : 3;
+      const int want = env ? std::atoi(env) : 0;      // off by default: the movers-only re-layout keeps arrival order inside a cell
       g.class_bits = spare < want ? spare : want;
       if (g.class_bits < 0) g.class_bits = 0;
       if (g.class_bits > 3) g.class_bits = 3;
@@ -178,7 +178,7 @@ int lcx_create(const lcx_config *cfg, lcx_engine **out)
     e->drw_mom3.alloc(n_cell); e->rw_mom3.alloc(n_cell); e->count_mom.alloc(n_cell);
     if (cfg->terminal_velocity == lcx::VT_BEARD77 || cfg->terminal_velocity == lcx::VT_BEARD77FAST) e->cell_tmp4.alloc(size_t(n_cell) * 4);
     if (cfg->allow_sstp_cond) { e->sstp_tmp_rv.alloc(n_cell); e->sstp_tmp_th.alloc(n_cell); e->sstp_tmp_rh.alloc(n_cell); }
-    e->cell_off.alloc(n_cell + 2);
+    e->cell_off.alloc(n_cell + 2); e->cell_off_new.alloc(n_cell + 2); e->arr_off.alloc(n_cell + 2); e->mv_scan.alloc(n_cell + 2);
     const size_t h = size_t(g.halo_size);
     switch (g.n_dims)   // staggered Courant fields with x-halo: init_sync.ipp:29-44
     {

@@ -167,7 +167,10 @@ namespace lcx
       return real_t(bits & ((1ull << 53) - 1)) * real_t(1.0 / 9007199254740992.0);
     }
 
-    __global__ void __launch_bounds__(TPB) k_coal_small(idx_t n_cell, const uint32_t *__restrict__ off, const idx_t *__restrict__ sid,
+#ifndef LCX_COAL_MINB
+#define LCX_COAL_MINB 4      // 64 registers, 4 CTAs per SM: measured best of {1,3,4,5}
+#endif
+    __global__ void __launch_bounds__(TPB, LCX_COAL_MINB) k_coal_small(idx_t n_cell, const uint32_t *__restrict__ off, const idx_t *__restrict__ sid,
                                                        rng_src rng, coal_ctx cx)
     {
       __shared__ __align__(16) uint32_t skey[GROUPS][SMALL_MAX + KEY_PAD];

@@ -151,6 +151,9 @@ struct lcx_engine
   lcx::dbuf<lcx::real_t> drw_mom3, rw_mom3, count_mom, mom_partial;
   lcx::dbuf<lcx::real_t> cell_tmp4;        // 4 reals per cell: per-cell parts of the Beard (1977) fall-speed correction
   lcx::dbuf<lcx::real_t> courant_x, courant_y, courant_z, w_LS;
+  size_t n_grouped = 0;          // SDs [0, n_grouped) still lie in the segments described by cell_off / ijk of the last re-layout
+  lcx::dbuf<uint32_t> mv_scan;   // n_cell + 2: movers per old cell, then their exclusive scan (movers-only re-layout)
+  lcx::dbuf<uint32_t> arr_off, cell_off_new;   // n_cell + 2 each: arrivals per cell, segment starts being built
   lcx::dbuf<uint32_t> cell_off;  // n_cell + 2 entries: start of each cell's segment; [n_cell] = n_part, [n_cell+1] = total incl. dead
 
   // tables

@@ -13,6 +13,9 @@
 // travels with each SD and is re-densified (rank among survivors) so that it keeps indexing the injected random streams.
 #include "lcx_engine.cuh"
 
+#include <cstdlib>
+#include <string>
+
 namespace lcx
 {
   namespace
@@ -83,7 +86,7 @@ namespace lcx
       const size_t t = size_t(blockIdx.x) * TPB + threadIdx.x;
       if (t >= n) return;
       const uint32_t s = perm[t];
-      ijk[t] = key[t] >> class_bits;
+      if (key) ijk[t] = key[t] >> class_bits;
 #pragma unroll 1
       for (int a = 0; a < G.n; ++a)
       {
@@ -160,6 +163,106 @@ namespace lcx
       ns[src] = m / 2;
     }
 
+    // ---- movers-only re-layout ------------------------------------------------------------------------------------------
+    // Between two re-layouts most SDs stay in their cell (Courant numbers well below one): the stayers of a cell keep their
+    // relative order, so only the SDs that changed cell (or arrived, or died) need sorting.  mv[t] = 1 for movers; after an
+    // exclusive scan mv[t] = number of movers before t.
+    // Everything below walks the OLD cell segments with 8 lanes per cell (four cells per warp): a lane knows its SD's old cell
+    // from the segment it is in, movers are ranked inside the cell with a ballot, and only per-cell counts are scanned.
+    constexpr int MVG = 8;
+    __device__ __forceinline__ unsigned group_ballot(bool pred)
+    { return (__ballot_sync(0xffffffffu, pred) >> ((threadIdx.x & 31) / MVG * MVG)) & ((1u << MVG) - 1u); }
+
+    // movers (SDs whose new key names another cell, incl. the dead) per old cell; entry n_cell = arrivals appended since
+    __global__ void __launch_bounds__(TPB) k_mv_count(uint32_t n_cell, size_t n_old, size_t n_grouped, int class_bits, const uint32_t *__restrict__ off,
+                                                     const uint32_t *__restrict__ key, uint32_t *__restrict__ mvcnt)
+    {
+      const uint32_t c = (blockIdx.x * TPB + threadIdx.x) / MVG;
+      const int l = threadIdx.x % MVG;
+      const bool live = c < n_cell;
+      const uint32_t b = live ? off[c] : 0u, en = live ? off[c + 1] : 0u;
+      uint32_t cnt = 0;
+      const uint32_t rounds = __reduce_max_sync(0xffffffffu, (en - b + MVG - 1) / MVG);
+      for (uint32_t r = 0; r < rounds; ++r)
+      {
+        const uint32_t t = b + r * MVG + l;
+        cnt += __popc(group_ballot(t < en && (key[t] >> class_bits) != c));
+      }
+      if (live && l == 0) mvcnt[c] = cnt;
+      if (c == n_cell && l == 0) { mvcnt[n_cell] = uint32_t(n_old - n_grouped); mvcnt[n_cell + 1] = 0u; }
+    }
+    // compact list of the movers (new cell, old position), cell by cell in storage order; mvoff = exclusive scan of mvcnt
+    __global__ void __launch_bounds__(TPB) k_mv_list(uint32_t n_cell, int class_bits, const uint32_t *__restrict__ off, const uint32_t *__restrict__ key,
+                                                    const uint32_t *__restrict__ mvoff, uint32_t *__restrict__ mkey, uint32_t *__restrict__ mval)
+    {
+      const uint32_t c = (blockIdx.x * TPB + threadIdx.x) / MVG;
+      const int l = threadIdx.x % MVG;
+      const bool live = c < n_cell;
+      const uint32_t b = live ? off[c] : 0u, en = live ? off[c + 1] : 0u;
+      uint32_t base = live ? mvoff[c] : 0u;
+      const uint32_t rounds = __reduce_max_sync(0xffffffffu, (en - b + MVG - 1) / MVG);
+      for (uint32_t r = 0; r < rounds; ++r)
+      {
+        const uint32_t t = b + r * MVG + l;
+        const uint32_t k = t < en ? key[t] >> class_bits : c;
+        const bool mover = t < en && k != c;
+        const unsigned m = group_ballot(mover);
+        if (mover) { const uint32_t j = base + __popc(m & ((1u << l) - 1u)); mkey[j] = k; mval[j] = t; }
+        base += __popc(m);
+      }
+    }
+    __global__ void __launch_bounds__(TPB) k_mv_list_tail(size_t n_old, size_t n_grouped, int class_bits, const uint32_t *__restrict__ key, uint32_t first,
+                                                         uint32_t *__restrict__ mkey, uint32_t *__restrict__ mval)
+    {
+      const size_t t = n_grouped + size_t(blockIdx.x) * TPB + threadIdx.x;
+      if (t >= n_old) return;
+      const size_t j = size_t(first) + (t - n_grouped);
+      mkey[j] = key[t] >> class_bits; mval[j] = uint32_t(t);
+    }
+    // stayers move to the front of their cell's new segment in their old order
+    __global__ void __launch_bounds__(TPB) k_mv_place_stayers(uint32_t n_cell, int class_bits, const uint32_t *__restrict__ off, const uint32_t *__restrict__ key,
+                                                             const uint32_t *__restrict__ new_off, uint32_t *__restrict__ perm, idx_t *__restrict__ ijk_new)
+    {
+      const uint32_t c = (blockIdx.x * TPB + threadIdx.x) / MVG;
+      const int l = threadIdx.x % MVG;
+      const bool live = c < n_cell;
+      const uint32_t b = live ? off[c] : 0u, en = live ? off[c + 1] : 0u;
+      uint32_t base = live ? new_off[c] : 0u;
+      const uint32_t rounds = __reduce_max_sync(0xffffffffu, (en - b + MVG - 1) / MVG);
+      for (uint32_t r = 0; r < rounds; ++r)
+      {
+        const uint32_t t = b + r * MVG + l;
+        const bool stays = t < en && (key[t] >> class_bits) == c;
+        const unsigned m = group_ballot(stays);
+        if (stays) { const uint32_t d = base + __popc(m & ((1u << l) - 1u)); perm[d] = t; ijk_new[d] = c; }
+        base += __popc(m);
+      }
+    }
+    // population of every cell after the move: stayers (old segment minus its movers) + arrivals
+    __global__ void __launch_bounds__(TPB) k_mv_counts(uint32_t n_cell, const uint32_t *__restrict__ old_off, const uint32_t *__restrict__ mvoff,
+                                                      const uint32_t *__restrict__ arr_off, uint32_t *__restrict__ cnt)
+    {
+      const uint32_t c = blockIdx.x * TPB + threadIdx.x;
+      if (c > n_cell + 1) return;
+      uint32_t v = 0;
+      if (c < n_cell) v = (old_off[c + 1] - old_off[c]) - (mvoff[c + 1] - mvoff[c]) + (arr_off[c + 1] - arr_off[c]);
+      cnt[c] = v;      // [n_cell], [n_cell + 1] = 0: after the scan both hold the number of survivors
+    }
+    __global__ void __launch_bounds__(TPB) k_mv_place_arrivals(uint32_t n_m, uint32_t n_cell, const uint32_t *__restrict__ mkey, const uint32_t *__restrict__ mval,
+                                                              const uint32_t *__restrict__ new_off, const uint32_t *__restrict__ arr_off,
+                                                              uint32_t *__restrict__ perm, idx_t *__restrict__ ijk_new)
+    {
+      const uint32_t j = blockIdx.x * TPB + threadIdx.x;
+      if (j >= n_m) return;
+      const uint32_t c = mkey[j];
+      if (c >= n_cell) return;                               // dead
+      const uint32_t a0 = arr_off[c];
+      const uint32_t stay = (new_off[c + 1] - new_off[c]) - (arr_off[c + 1] - a0);
+      const uint32_t d = new_off[c] + stay + (j - a0);
+      perm[d] = mval[j];
+      ijk_new[d] = c;
+    }
+
     int bit_length(uint64_t v) { int b = 0; while (v) { ++b; v >>= 1; } return b; }
 
     void add(gather_set &G, const void *src, void *dst, int width)
@@ -214,6 +317,50 @@ namespace lcx
     e->keys_ready = 0;
   }
 
+  // Re-layout that sorts only the SDs which changed cell.  Returns false (nothing done) when too many SDs moved for it to pay
+  // off or when there is no previous grouping to start from; the caller then takes the full radix sort.
+  // Result: perm in val[0], new cell indices in A().ijk, segment starts in cell_off, n_part / max_count in the device scalars.
+  static bool relayout_movers(lcx_engine *e, size_t n_old)
+  {
+    static const bool enabled = [] { const char *v = std::getenv("LCX_RELAYOUT"); return !(v && std::string(v) == "sort"); }();
+    const grid_t &g = e->grid;
+    if (!enabled || e->n_grouped == 0 || e->n_grouped > n_old || e->max_count > 2048) return false;   // huge cells (0-D boxes): 8 lanes per cell would crawl
+    // movers per old cell -> exclusive scan -> total (one readback)
+    uint32_t *mvoff = e->mv_scan.p;
+    const unsigned cell_blocks = div_up((size_t(g.n_cell) + 1) * MVG, TPB);
+    LCX_LAUNCH(e, k_mv_count, cell_blocks, TPB, 0, g.n_cell, n_old, e->n_grouped, g.class_bits, e->cell_off.p, e->key[0].p, mvoff);
+    exclusive_scan_u32(e, mvoff, size_t(g.n_cell) + 2);
+    uint32_t n_m = 0;
+    LCX_CUDA(cudaMemcpyAsync(&n_m, mvoff + g.n_cell + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    LCX_CUDA(cudaStreamSynchronize(e->stream));
+    if (size_t(n_m) * 5 > n_old * 2 || size_t(n_m) * 2 > e->cap) return false;        // > 40 % movers: sort everything
+
+    uint32_t *mk[2] = {e->key[1].p, e->key[1].p + n_m}, *mv[2] = {e->val[1].p, e->val[1].p + n_m};
+    int res = 0;
+    if (n_m)
+    {
+      LCX_LAUNCH(e, k_mv_list, cell_blocks, TPB, 0, g.n_cell, g.class_bits, e->cell_off.p, e->key[0].p, mvoff, mk[0], mv[0]);
+      if (n_old > e->n_grouped)
+      {
+        const uint32_t first = n_m - uint32_t(n_old - e->n_grouped);
+        LCX_LAUNCH(e, k_mv_list_tail, div_up(n_old - e->n_grouped, TPB), TPB, 0, n_old, e->n_grouped, g.class_bits, e->key[0].p, first, mk[0], mv[0]);
+      }
+      res = radix_sort_pairs(e, n_m, 0, bit_length(g.n_cell), mk, mv, 0);
+    }
+    LCX_LAUNCH(e, k_cell_offsets, div_up(size_t(n_m) + 1, TPB), TPB, 0, size_t(n_m), g.n_cell, 0, mk[res], e->arr_off.p);
+    LCX_LAUNCH(e, k_mv_counts, div_up(g.n_cell + 2, TPB), TPB, 0, g.n_cell, e->cell_off.p, mvoff, e->arr_off.p, e->cell_off_new.p);
+    exclusive_scan_u32(e, e->cell_off_new.p, size_t(g.n_cell) + 2);
+    LCX_LAUNCH(e, k_mv_place_stayers, cell_blocks, TPB, 0, g.n_cell, g.class_bits, e->cell_off.p, e->key[0].p, e->cell_off_new.p,
+               e->val[0].p, e->A().ijk.p);
+    if (n_m)
+      LCX_LAUNCH(e, k_mv_place_arrivals, div_up(n_m, TPB), TPB, 0, n_m, g.n_cell, mk[res], mv[res], e->cell_off_new.p, e->arr_off.p,
+                 e->val[0].p, e->A().ijk.p);
+    LCX_CUDA(cudaMemcpyAsync(e->cell_off.p, e->cell_off_new.p, (size_t(g.n_cell) + 2) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
+    LCX_CUDA(cudaMemsetAsync(&e->scalars.p->max_count, 0, sizeof(unsigned int), e->stream));
+    LCX_LAUNCH(e, k_max_count, div_up(g.n_cell, TPB), TPB, 0, g.n_cell, e->cell_off.p, e->scalars.p);
+    return true;
+  }
+
   void post_copy(lcx_engine *e, bool rcyc, bool keep_all)
   {
     if (rcyc && !keep_all) recycle(e);
@@ -221,11 +368,12 @@ namespace lcx
     const size_t n_old = e->n_part;
     sd_arrays &s = e->S();
     sd_arrays &a = e->A();
+    const uint32_t *sorted_keys = nullptr;     // full-sort path only: the gather takes the cell index from them
 
     if (n_old == 0)
     {
       LCX_CUDA(cudaMemsetAsync(e->cell_off.p, 0, e->cell_off.bytes(), e->stream));
-      e->max_count = 0; e->grouped = true;
+      e->max_count = 0; e->grouped = true; e->n_grouped = 0;
       return;
     }
 
@@ -239,8 +387,17 @@ namespace lcx
         LCX_LAUNCH(e, k_make_keys, div_up(n_old - first, TPB), TPB, 0, first, n_old, g, s.n.p, s.rw2.p, s.x.p, s.y.p, s.z.p, e->key[0].p, e->val[0].p);
     }
     e->keys_ready = 0;
-    const int res = radix_sort_pairs(e, n_old, 0, bit_length(g.n_cell) + g.class_bits, 0);
-    compute_cell_offsets(e, e->key[res].p, n_old);
+
+    // where every survivor goes: perm[new position] = old position, segment starts in cell_off, new cell index in a.ijk
+    const uint32_t *perm = nullptr;
+    if (!keep_all && relayout_movers(e, n_old)) perm = e->val[0].p;
+    else
+    {
+      const int res = radix_sort_pairs(e, n_old, 0, bit_length(g.n_cell) + g.class_bits, 0);
+      compute_cell_offsets(e, e->key[res].p, n_old);
+      perm = e->val[res].p;
+      sorted_keys = e->key[res].p;
+    }
 
     LCX_CUDA(cudaMemcpyAsync(e->h_scalars, e->scalars.p, sizeof(dev_scalars), cudaMemcpyDeviceToHost, e->stream));
     LCX_CUDA(cudaStreamSynchronize(e->stream));
@@ -255,10 +412,11 @@ namespace lcx
       add(G, s.sid.p, a.sid.p, 4);
       add(G, s.pp_rv.p, a.pp_rv.p, 8); add(G, s.pp_th.p, a.pp_th.p, 8); add(G, s.pp_rh.p, a.pp_rh.p, 8); add(G, s.pp_p.p, a.pp_p.p, 8);
       add(G, s.rc2.p, a.rc2.p, 8);
-      LCX_LAUNCH(e, k_gather, div_up(n_new, TPB), TPB, 0, n_new, e->val[res].p, e->key[res].p, g.class_bits, a.ijk.p, G);
+      LCX_LAUNCH(e, k_gather, div_up(n_new, TPB), TPB, 0, n_new, perm, sorted_keys, g.class_bits, a.ijk.p, G);
     }
     e->cur ^= 1;
     e->n_part = n_new;
+    e->n_grouped = n_new;
     e->grouped = true;
     e->selected = false;
 
