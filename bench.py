@@ -31,11 +31,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 A_FULL_BYTES = 192.0          # algorithmic bytes per SD-update, full step, double
-KERNEL_BYTES = {              # algorithmic bytes per SD per launch of the individual kernels
+KERNEL_BYTES = {              # algorithmic bytes per SD per launch of the kernels that sweep all SDs
     "k_cond_cells": 48.0,      # rw2 r+w, rd3, kpa, vt, n (8 B each); the cell fields are 1/40 of that
-    "k_cond": 52.0, "k_coal_small": 76.0, "k_coal_big": 76.0, "k_transport": 64.0, "k_gather": 136.0,
-    "k_radix_scatter": 16.0, "k_radix_hist": 4.0, "(k_cell_reduce_small<Term, IS_MAX>)": 20.0,
-    "k_vterm": 24.0, "k_make_keys": 40.0, "k_cell_offsets": 4.0,
+    "k_cond": 52.0, "k_coal_small": 76.0, "k_coal_big": 76.0, "k_transport": 80.0, "k_gather": 136.0,
+    "(k_cell_reduce_small<Term, IS_MAX>)": 20.0, "k_vterm": 24.0, "k_make_keys": 40.0,
+    "k_mv_count": 4.0, "k_mv_list": 4.0, "k_mv_place_stayers": 12.0,
+    # the radix sort and k_mv_place_arrivals / k_cell_offsets only see the SDs that changed cell: no per-SD figure
 }
 
 
