@@ -124,7 +124,7 @@ namespace libcloudphxx
 
         bool init_called = false, should_now_run_async = false, should_now_run_cond = false, var_rho = false;
         real_t dt;
-        int sstp_cond, sstp_coal;
+        int sstp_cond, sstp_coal, sstp_cond_act;
         as_t adve_scheme;
         bool allow_sstp_cond, pure_const_multi;
 
@@ -172,7 +172,7 @@ namespace libcloudphxx
           halo_y = halo_size * (oi.ny + 1) * oi.nz;
           halo_z = n_dims == 2 ? halo_size * (oi.nz + 1) : halo_size * (oi.nz + 1) * oi.ny;
           adve_scheme = oi.adve_scheme;
-          sstp_cond = oi.sstp_cond; sstp_coal = oi.sstp_coal; dt = oi.dt;
+          sstp_cond = oi.sstp_cond; sstp_coal = oi.sstp_coal; sstp_cond_act = oi.sstp_cond_act; dt = oi.dt;
           allow_sstp_cond = oi.sstp_cond > 1 || oi.sstp_cond_act > 1;
           pure_const_multi = (oi.sd_conc == 0) && (oi.sd_const_multi > 0 || oi.dry_sizes.size() > 0);
           rng_mode = g_rng_mode;
@@ -807,6 +807,7 @@ namespace libcloudphxx
           if (dt_ > 0 && !oi.variable_dt_switch) throw std::runtime_error("libcloudph++: opts.dt specified, but opts_init.variable_dt_switch is false.");
           sstp_cond = dt_ > 0 && oi.sstp_cond > 1 ? int(std::ceil(oi.sstp_cond * dt_ / oi.dt)) : oi.sstp_cond;
           sstp_coal = dt_ > 0 && oi.sstp_coal > 1 ? int(std::ceil(oi.sstp_coal * dt_ / oi.dt)) : oi.sstp_coal;
+          sstp_cond_act = dt_ > 0 && oi.sstp_cond_act > 1 ? int(std::ceil(oi.sstp_cond_act * dt_ / oi.dt)) : oi.sstp_cond_act;
           dt = dt_ > 0 ? dt_ : oi.dt;
         }
 
@@ -863,10 +864,10 @@ namespace libcloudphxx
           if (opts.cond)
           {
             chk(lcx_hskpng_mfp(e));          // from the T, p left by the previous Tpr, as the reference does (particles_step.ipp:189-194)
-            if (oi.exact_sstp_cond && (sstp_cond > 1 || oi.sstp_cond_act > 1))     // per-particle sub-stepping: particles_step.ipp:199-236
+            if (oi.exact_sstp_cond && (sstp_cond > 1 || sstp_cond_act > 1))     // per-particle sub-stepping: particles_step.ipp:199-236
             {
               if (oi.adaptive_sstp_cond)
-                chk(lcx_cond_perparticle_adaptive(e, dt, opts.RH_max, sstp_cond, oi.sstp_cond_act, oi.sstp_cond_adapt_drw2_eps, oi.sstp_cond_adapt_drw2_max));
+                chk(lcx_cond_perparticle_adaptive(e, dt, opts.RH_max, sstp_cond, sstp_cond_act, oi.sstp_cond_adapt_drw2_eps, oi.sstp_cond_adapt_drw2_max));
               else
                 chk(lcx_cond_perparticle(e, dt, opts.RH_max, sstp_cond, oi.sstp_cond_mix));
             }
