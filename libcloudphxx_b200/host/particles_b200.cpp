@@ -1223,6 +1223,205 @@ namespace libcloudphxx
       };
     }
 
+
+    // ---- single-precision callers ----------------------------------------------------------------------------------
+    // factory<float> (src/lib.cpp:43) is served by the double-precision engine: options and fields are widened on the way in,
+    // th / rv, outbuf, get_attr and diag_puddle narrowed on the way out.  Arithmetic is therefore done in double (compute
+    // type >= the caller's); super-droplet attributes are not bit-comparable with a float build of the reference (whose
+    // random draws and roundings differ), fields and moments agree to single-precision accuracy.
+    namespace b200
+    {
+      class particles_float : public particles_proto_t<float>
+      {
+        typedef particles_proto_t<float> base_t;
+        std::unique_ptr<particles_proto_t<double>> dbl;
+        opts_init_t<float> oi_f;
+        std::vector<float> outbuf_f;
+        int n_dims;
+
+        struct widened_fun : common::unary_function<double>
+        {
+          std::shared_ptr<common::unary_function<float>> f;
+          double funval(const double x) const { return double((*f)(float(x))); }
+        };
+
+        struct staged
+        {
+          std::vector<double> buf;
+          std::vector<ptrdiff_t> strides;
+          arrinfo_t<double> info() { return buf.empty() ? arrinfo_t<double>() : arrinfo_t<double>(buf.data(), strides); }
+        };
+
+        // extents of a field: scalars nx x ny x nz, Courant components one more along their own direction
+        void extents(int ext, long (&n)[3], int &nd) const
+        {
+          const int nn[3] = {oi_f.nx, oi_f.ny, oi_f.nz};
+          nd = 0;
+          for (int d = 0; d < 3; ++d) if (nn[d] > 0) n[nd++] = nn[d] + (ext == d ? 1 : 0);
+          for (int d = nd; d < 3; ++d) n[d] = 1;
+        }
+        template <class F>
+        void for_each_element(const arrinfo_t<float> &a, int ext, F f) const
+        {
+          long n[3]; int nd;
+          extents(ext, n, nd);
+          const ptrdiff_t s0 = nd > 0 ? (nd == 1 ? 1 : a.strides[0]) : 0, s1 = nd > 1 ? a.strides[1] : 0, s2 = nd > 2 ? a.strides[2] : 0;
+          long q = 0;
+          for (long i = 0; i < n[0]; ++i)
+            for (long j = 0; j < n[1]; ++j)
+              for (long k = 0; k < n[2]; ++k, ++q)
+                f(q, a.data[i * s0 + j * s1 + k * s2]);
+        }
+        void widen(const arrinfo_t<float> &a, int ext, staged &st) const
+        {
+          st.buf.clear();
+          if (a.is_null()) return;
+          long n[3]; int nd;
+          extents(ext, n, nd);
+          st.buf.resize(size_t(n[0] * n[1] * n[2]));
+          st.strides.assign({ptrdiff_t(n[1] * n[2]), ptrdiff_t(nd > 2 ? n[2] : 1), ptrdiff_t(1)});
+          if (nd == 2) st.strides = {ptrdiff_t(n[1]), ptrdiff_t(1)};
+          if (nd <= 1) st.strides = {ptrdiff_t(1)};
+          for_each_element(a, ext, [&](long q, float &v) { st.buf[size_t(q)] = double(v); });
+        }
+        void narrow(const staged &st, arrinfo_t<float> &a) const
+        {
+          if (a.is_null() || st.buf.empty()) return;
+          for_each_element(a, -1, [&](long q, float &v) { v = float(st.buf[size_t(q)]); });
+        }
+        static opts_t<double> widen(const opts_t<float> &o)
+        {
+          opts_t<double> r;
+          r.adve = o.adve; r.sedi = o.sedi; r.subs = o.subs; r.cond = o.cond; r.coal = o.coal; r.src = o.src; r.rlx = o.rlx; r.rcyc = o.rcyc;
+          r.turb_adve = o.turb_adve; r.turb_cond = o.turb_cond; r.turb_coal = o.turb_coal; r.ice_nucl = o.ice_nucl;
+          r.chem_dsl = o.chem_dsl; r.chem_dsc = o.chem_dsc; r.chem_rct = o.chem_rct;
+          r.RH_max = o.RH_max; r.dt = o.dt;
+          return r;
+        }
+        static opts_init_t<double> widen(const opts_init_t<float> &o)
+        {
+          opts_init_t<double> r;
+          for (const auto &dd : o.dry_distros)
+          {
+            auto w = std::make_shared<widened_fun>();
+            w->f = dd.second;
+            r.dry_distros.emplace(kappa_rd_insol_t<double>(dd.first.kappa, dd.first.rd_insol), w);
+          }
+          for (const auto &ds : o.dry_sizes)
+            for (const auto &sz : ds.second)
+              r.dry_sizes[kappa_rd_insol_t<double>(ds.first.kappa, ds.first.rd_insol)][double(sz.first)] = std::make_pair(double(sz.second.first), sz.second.second);
+          r.nx = o.nx; r.ny = o.ny; r.nz = o.nz; r.dx = o.dx; r.dy = o.dy; r.dz = o.dz; r.dt = o.dt;
+          r.sstp_cond = o.sstp_cond; r.sstp_coal = o.sstp_coal; r.sstp_cond_act = o.sstp_cond_act; r.sstp_chem = o.sstp_chem;
+          r.x0 = o.x0; r.y0 = o.y0; r.z0 = o.z0; r.x1 = o.x1; r.y1 = o.y1; r.z1 = o.z1;
+          r.sd_conc = o.sd_conc; r.sd_conc_large_tail = o.sd_conc_large_tail; r.aerosol_independent_of_rhod = o.aerosol_independent_of_rhod;
+          r.variable_dt_switch = o.variable_dt_switch; r.sd_const_multi = o.sd_const_multi; r.n_sd_max = o.n_sd_max;
+          r.kernel = o.kernel; r.terminal_velocity = o.terminal_velocity; r.adve_scheme = o.adve_scheme; r.RH_formula = o.RH_formula;
+          r.kernel_parameters.assign(o.kernel_parameters.begin(), o.kernel_parameters.end());
+          r.chem_switch = o.chem_switch; r.coal_switch = o.coal_switch; r.sedi_switch = o.sedi_switch; r.subs_switch = o.subs_switch;
+          r.rlx_switch = o.rlx_switch; r.turb_adve_switch = o.turb_adve_switch; r.turb_cond_switch = o.turb_cond_switch;
+          r.turb_coal_switch = o.turb_coal_switch; r.ice_switch = o.ice_switch; r.exact_sstp_cond = o.exact_sstp_cond;
+          r.sstp_cond_mix = o.sstp_cond_mix; r.adaptive_sstp_cond = o.adaptive_sstp_cond; r.time_dep_ice_nucl = o.time_dep_ice_nucl;
+          r.sstp_cond_adapt_drw2_eps = o.sstp_cond_adapt_drw2_eps; r.sstp_cond_adapt_drw2_max = o.sstp_cond_adapt_drw2_max;
+          r.chem_rho = o.chem_rho; r.diag_incloud_time = o.diag_incloud_time;
+          r.RH_max = o.RH_max; r.rng_seed = o.rng_seed; r.rng_seed_init = o.rng_seed_init; r.rng_seed_init_switch = o.rng_seed_init_switch;
+          r.dev_count = o.dev_count; r.dev_id = o.dev_id;
+          r.w_LS.assign(o.w_LS.begin(), o.w_LS.end()); r.SGS_mix_len.assign(o.SGS_mix_len.begin(), o.SGS_mix_len.end());
+          r.aerosol_conc_factor.assign(o.aerosol_conc_factor.begin(), o.aerosol_conc_factor.end());
+          r.rd_min = o.rd_min; r.rd_max = o.rd_max;
+          r.no_ccn_at_init = o.no_ccn_at_init; r.open_side_walls = o.open_side_walls; r.periodic_topbot_walls = o.periodic_topbot_walls;
+          r.rc2_T = o.rc2_T; r.src_type = o.src_type;
+          r.rlx_bins = o.rlx_bins; r.rlx_sd_per_bin = o.rlx_sd_per_bin; r.supstp_rlx = o.supstp_rlx; r.rlx_timescale = o.rlx_timescale;
+          r.th_dry = o.th_dry; r.const_p = o.const_p;
+          return r;
+        }
+
+        staged s_th, s_rv, s_rhod, s_p, s_cx, s_cy, s_cz;
+
+        public:
+        particles_float(const backend_t backend, const opts_init_t<float> &o) : oi_f(o)
+        {
+          n_dims = (o.nx > 0) + (o.ny > 0) + (o.nz > 0);
+          const opts_init_t<double> od = widen(o);
+          dbl.reset(backend == multi_CUDA ? new particles_impl<double>(od, 0) : new particles_impl<double>(od));
+          oi_f.n_sd_max = dbl->opts_init->n_sd_max;
+          this->opts_init = &oi_f;
+        }
+
+        void init(const arrinfo_t<float> th, const arrinfo_t<float> rv, const arrinfo_t<float> rhod, const arrinfo_t<float> p,
+                  const arrinfo_t<float> cx, const arrinfo_t<float> cy, const arrinfo_t<float> cz, const base_t::chem_cmap_t chem) override
+        {
+          if (!chem.empty()) throw std::runtime_error("libcloudph++: chemistry was switched off and ambient_chem is not empty");
+          widen(th, -1, s_th); widen(rv, -1, s_rv); widen(rhod, -1, s_rhod); widen(p, -1, s_p);
+          widen(cx, 0, s_cx); widen(cy, 1, s_cy); widen(cz, 2, s_cz);
+          dbl->init(s_th.info(), s_rv.info(), s_rhod.info(), s_p.info(), s_cx.info(), s_cy.info(), s_cz.info());
+        }
+        void sync_in(arrinfo_t<float> th, arrinfo_t<float> rv, const arrinfo_t<float> rhod, const arrinfo_t<float> cx, const arrinfo_t<float> cy,
+                     const arrinfo_t<float> cz, const arrinfo_t<float> diss_rate, base_t::chem_map_t chem) override
+        {
+          if (!chem.empty()) throw std::runtime_error("libcloudph++: chemistry was switched off and ambient_chem is not empty");
+          if (!diss_rate.is_null())
+            throw std::runtime_error("libcloudph++: turbulent advection, coalescence and condesation are switched off and diss_rate is not empty");
+          widen(th, -1, s_th); widen(rv, -1, s_rv); widen(rhod, -1, s_rhod);
+          widen(cx, 0, s_cx); widen(cy, 1, s_cy); widen(cz, 2, s_cz);
+          dbl->sync_in(s_th.info(), s_rv.info(), s_rhod.info(), s_cx.info(), s_cy.info(), s_cz.info());
+        }
+        void step_cond(const opts_t<float> &o, arrinfo_t<float> th, arrinfo_t<float> rv, base_t::chem_map_t) override
+        {
+          dbl->step_cond(widen(o), s_th.info(), s_rv.info());
+          narrow(s_th, th); narrow(s_rv, rv);
+        }
+        void step_sync(const opts_t<float> &o, arrinfo_t<float> th, arrinfo_t<float> rv, const arrinfo_t<float> rhod, const arrinfo_t<float> cx,
+                       const arrinfo_t<float> cy, const arrinfo_t<float> cz, const arrinfo_t<float> diss_rate, base_t::chem_map_t chem) override
+        {
+          sync_in(th, rv, rhod, cx, cy, cz, diss_rate, chem);
+          step_cond(o, th, rv, chem);
+        }
+        void step_async(const opts_t<float> &o) override { dbl->step_async(widen(o)); }
+
+        void diag_all() override { dbl->diag_all(); }
+        void diag_rw_ge_rc() override { dbl->diag_rw_ge_rc(); }
+        void diag_RH_ge_Sc() override { dbl->diag_RH_ge_Sc(); }
+        void diag_dry_rng(const float &a, const float &b) override { dbl->diag_dry_rng(a, b); }
+        void diag_wet_rng(const float &a, const float &b) override { dbl->diag_wet_rng(a, b); }
+        void diag_kappa_rng(const float &a, const float &b) override { dbl->diag_kappa_rng(a, b); }
+        void diag_water() override { dbl->diag_water(); }
+        void diag_dry_rng_cons(const float &a, const float &b) override { dbl->diag_dry_rng_cons(a, b); }
+        void diag_wet_rng_cons(const float &a, const float &b) override { dbl->diag_wet_rng_cons(a, b); }
+        void diag_kappa_rng_cons(const float &a, const float &b) override { dbl->diag_kappa_rng_cons(a, b); }
+        void diag_water_cons() override { dbl->diag_water_cons(); }
+        void diag_sd_conc() override { dbl->diag_sd_conc(); }
+        void diag_pressure() override { dbl->diag_pressure(); }
+        void diag_temperature() override { dbl->diag_temperature(); }
+        void diag_RH() override { dbl->diag_RH(); }
+        void diag_dry_mom(const int &k) override { dbl->diag_dry_mom(k); }
+        void diag_wet_mom(const int &k) override { dbl->diag_wet_mom(k); }
+        void diag_kappa_mom(const int &k) override { dbl->diag_kappa_mom(k); }
+        void diag_wet_mass_dens(const float &a, const float &b) override { dbl->diag_wet_mass_dens(a, b); }
+        void diag_precip_rate() override { dbl->diag_precip_rate(); }
+        void diag_max_rw() override { dbl->diag_max_rw(); }
+        void diag_vel_div() override { dbl->diag_vel_div(); }
+        std::map<common::output_t, float> diag_puddle() override
+        {
+          std::map<common::output_t, float> r;
+          for (const auto &kv : dbl->diag_puddle()) r[kv.first] = float(kv.second);
+          return r;
+        }
+        std::vector<float> get_attr(const std::string &name) override
+        {
+          const std::vector<double> v = dbl->get_attr(name);
+          return std::vector<float>(v.begin(), v.end());
+        }
+        float *outbuf() override
+        {
+          const double *src = dbl->outbuf();
+          const size_t n = size_t(std::max(1, oi_f.nx)) * size_t(std::max(1, oi_f.ny)) * size_t(std::max(1, oi_f.nz));
+          outbuf_f.resize(n);
+          for (size_t q = 0; q < n; ++q) outbuf_f[q] = float(src[q]);
+          return outbuf_f.data();
+        }
+      };
+    }
+
     // ---- factory: src/lib.cpp:13-44 -----------------------------------------------------------------------------
     template <typename real_t>
     particles_proto_t<real_t> *factory(const backend_t backend, opts_init_t<real_t> opts_init)
@@ -1237,7 +1436,7 @@ namespace libcloudphxx
             return new b200::particles_impl<double>(opts_init);
           }
           else
-            throw std::runtime_error("libcloudph++: the B200 back-end is built for double precision only (float is not instantiated yet)");
+            return new b200::particles_float(backend, opts_init);
         case OpenMP:     throw std::runtime_error("libcloudph++: OpenMP backend was not compiled");
         case serial:     throw std::runtime_error("libcloudph++: serial backend was not compiled");
         default:         throw std::runtime_error("libcloudph++: unknown backend");

@@ -1,0 +1,78 @@
+// factory<float> against factory<double> on the same 3-D case (public C++ API only, as a host model would use it).
+// Build: g++ -std=c++17 -I libcloudphxx_b200/host/include tests/cpp/float_api.cpp -L libcloudphxx_b200/lib -llgrngn_b200 -Wl,-rpath,...
+#include <libcloudph++/lgrngn/factory.hpp>
+
+#include <cmath>
+#include <cstdio>
+#include <memory>
+#include <vector>
+
+using namespace libcloudphxx::lgrngn;
+
+template <class real_t>
+struct lognormal : libcloudphxx::common::unary_function<real_t>
+{
+  real_t funval(const real_t lnr) const
+  {
+    const real_t mean_r = 0.04e-6, sd = 1.4, n_tot = 60e6;
+    const real_t d = lnr - std::log(mean_r), ls = std::log(sd);
+    return n_tot * std::exp(-d * d / 2 / (ls * ls)) / ls / std::sqrt(real_t(2 * M_PI));
+  }
+};
+
+template <class real_t>
+struct result { std::vector<real_t> th, rv; double sd_conc_sum, m3_sum; size_t n_sd; };
+
+template <class real_t>
+result<real_t> run()
+{
+  const int nx = 6, ny = 5, nz = 8;
+  opts_init_t<real_t> oi;
+  oi.nx = nx; oi.ny = ny; oi.nz = nz;
+  oi.dx = oi.dy = oi.dz = 20;
+  oi.x1 = nx * 20; oi.y1 = ny * 20; oi.z1 = nz * 20;
+  oi.dt = 1;
+  oi.sd_conc = 32;
+  oi.n_sd_max = nx * ny * nz * 48;
+  oi.kernel = kernel_t::hall_davis_no_waals;
+  oi.terminal_velocity = vt_t::beard77fast;
+  oi.dry_distros.emplace(kappa_rd_insol_t<real_t>(real_t(0.61), real_t(0)), std::make_shared<lognormal<real_t>>());
+  const size_t n = size_t(nx) * ny * nz;
+  result<real_t> r;
+  r.th.assign(n, real_t(289.99)); r.rv.assign(n, real_t(8.5e-3));
+  std::vector<real_t> rhod(n, real_t(1.1)), cx((nx + 1) * ny * nz, real_t(0.1)), cy(nx * (ny + 1) * nz, real_t(0.05)), cz(nx * ny * (nz + 1), real_t(0));
+  const std::vector<ptrdiff_t> s{ptrdiff_t(ny * nz), ptrdiff_t(nz), 1}, sy{ptrdiff_t((ny + 1) * nz), ptrdiff_t(nz), 1}, sz{ptrdiff_t(ny * (nz + 1)), ptrdiff_t(nz + 1), 1};
+  std::unique_ptr<particles_proto_t<real_t>> p(factory<real_t>(CUDA, oi));
+  p->init(arrinfo_t<real_t>(r.th.data(), s), arrinfo_t<real_t>(r.rv.data(), s), arrinfo_t<real_t>(rhod.data(), s), arrinfo_t<real_t>(),
+          arrinfo_t<real_t>(cx.data(), s), arrinfo_t<real_t>(cy.data(), sy), arrinfo_t<real_t>(cz.data(), sz));
+  opts_t<real_t> o;
+  for (int step = 0; step < 4; ++step)
+  {
+    p->step_sync(o, arrinfo_t<real_t>(r.th.data(), s), arrinfo_t<real_t>(r.rv.data(), s), arrinfo_t<real_t>(rhod.data(), s),
+                 arrinfo_t<real_t>(cx.data(), s), arrinfo_t<real_t>(cy.data(), sy), arrinfo_t<real_t>(cz.data(), sz));
+    p->step_async(o);
+  }
+  p->diag_all(); p->diag_sd_conc();
+  r.sd_conc_sum = 0; for (size_t q = 0; q < n; ++q) r.sd_conc_sum += p->outbuf()[q];
+  p->diag_all(); p->diag_wet_mom(3);
+  r.m3_sum = 0; for (size_t q = 0; q < n; ++q) r.m3_sum += p->outbuf()[q];
+  r.n_sd = p->get_attr("rw2").size();
+  return r;
+}
+
+int main()
+{
+  const auto d = run<double>();
+  const auto f = run<float>();
+  double e_th = 0, e_rv = 0;
+  for (size_t q = 0; q < d.th.size(); ++q)
+  {
+    e_th = std::fmax(e_th, std::fabs(double(f.th[q]) - d.th[q]) / d.th[q]);
+    e_rv = std::fmax(e_rv, std::fabs(double(f.rv[q]) - d.rv[q]) / d.rv[q]);
+  }
+  const double e_m3 = std::fabs(f.m3_sum - d.m3_sum) / d.m3_sum;
+  std::printf("float vs double: th %.3g rv %.3g m3 %.3g, SDs %zu / %zu, sd_conc sums %.0f / %.0f\n", e_th, e_rv, e_m3, f.n_sd, d.n_sd, f.sd_conc_sum, d.sd_conc_sum);
+  // inputs / outputs pass through single precision once per step; the spectrum is evaluated in float
+  const bool ok = e_th < 5e-6 && e_rv < 5e-4 && e_m3 < 5e-3 && f.n_sd > 0 && std::fabs(double(f.n_sd) - double(d.n_sd)) < 0.02 * d.n_sd && f.sd_conc_sum == double(f.n_sd);
+  return ok ? 0 : 1;
+}

@@ -411,3 +411,19 @@ def test_adaptive_substepping_3d_with_coalescence(ref, b200):
         assert S.rel_err(f_r["th"], f_n["th"]) < 1e-8, (step, S.rel_err(f_r["th"], f_n["th"]))
         assert S.rel_err(f_r["rv"], f_n["rv"]) < 1e-6, (step, S.rel_err(f_r["rv"], f_n["rv"]))
     S.run_pair(ref, b200, setup, 5, on_step=check)
+
+
+def test_float_api_is_served_by_the_double_engine(tmp_path):
+    """factory<float> (src/lib.cpp:43): a C++ caller in single precision gets the same physics as one in double, to
+    single-precision accuracy of the fields it exchanges (tests/cpp/float_api.cpp, public C++ API only)"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "float_api")
+    lib = os.path.join(root, "libcloudphxx_b200", "lib")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-I", os.path.join(root, "libcloudphxx_b200", "host", "include"),
+                    os.path.join(root, "tests", "cpp", "float_api.cpp"), "-L", lib, "-llgrngn_b200", "-llcx_b200",
+                    "-Wl,-rpath," + lib, "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
