@@ -166,7 +166,7 @@ def run_reference(args):
 
 def run_b200(args):
     import torch
-    from libcloudphxx_b200 import lgrngn as L, distributed as D
+    from libcloudphxx_b200 import lgrngn as L, distributed as D, engine as E
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -295,6 +295,23 @@ def run_b200(args):
                                            "frac": round(kernel_bytes(k) * n_live / (ms_ / n * 1e-3) / 1e9 / peak, 4)}
                                        for k, (n, ms_) in rep.items() if kernel_bytes(k) and ms_ > 0}}
 
+    # ---- the opt-in fast root search, for information (not the headline: see include/lcx_b200.h lcx_set_cond_solver) ----
+    alt = None
+    if world == 1 and not xch:
+        E.set_cond_solver("secant")
+        for _ in range(2):
+            resident_step()
+        upd3 = 0
+        eng.timer_start()
+        for _ in range(args.steps):
+            upd3 += eng.n_part()
+            resident_step()
+        ms3 = eng.timer_stop()
+        E.set_cond_solver("toms748")
+        alt = {"cond_solver": "secant", "value": upd3 / (ms3 * 1e-3), "ms_per_step": ms3 / args.steps,
+               "note": "safeguarded secant instead of the reference's TOMS 748 trial points: within 2^-15 per step of the reference, "
+                       "different trajectory; informative only"}
+
     # ---- CPU baseline beside it (rank 0, N = 1) -----------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -313,12 +330,13 @@ def run_b200(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "cfg4 x-slab per GPU: %dx%dx%d cells x %d SD/cell, hall_davis_no_waals, beard77fast, implicit adve, sstp 1/1" % (nx, ny, nz, args.sd_conc),
                        "sd_per_gpu": nx * ny * nz * args.sd_conc, "global_cells": [nx * world, ny, nz], "rng": "philox4x32-10",
+                       "cond_solver": "toms748 (the reference's trial points)",
                        "l2": "inputs_exceed_l2 (%.1f GB of SD state per GPU)" % (nx * ny * nz * args.sd_conc * 76 / 1e9),
                        "init_s": round(t_init, 2), "max_sd_per_cell": max_count, "wall_ms_per_step": wall_ms / args.steps},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "SD-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": int(launches),
-            "roofline": roofline, "cpu_baseline": cpu, "kernels": prof_table,
+            "roofline": roofline, "cpu_baseline": cpu, "opt_in_fast_solver": alt, "kernels": prof_table,
         }
         print(json.dumps(line), flush=True)
     if dist:

@@ -147,6 +147,13 @@ int  lcx_sstp_save(lcx_engine *e);                              /* sstp_save.ipp
 /* ---- condensation (per-cell sub-stepping path) ---------------------------------------------------------- */
 /* one sub-step: 3rd wet moment before (step 0; later sub-steps reuse the previous "after"), implicit-Euler growth */
 /* of every liquid SD, 3rd wet moment after, and the vapour / heat feedback rv -= drv, th -= drv dth/drv              */
+/* root search used by every condensation entry point below, process-wide: 1 = the reference's TOMS 748 with identical trial */
+/* points (default; toms748.hpp:291-454), 2 = the same with the growth law transcribed operation by operation                */
+/* (cond_common.ipp:79-174), 0 = opt-in fast mode: safeguarded secant that stops when the root is known to the reference's    */
+/* tolerance (half the evaluations; results within 2^-15 per step of the reference but on a different trajectory - the rows  */
+/* of the reference's fixture that count threshold crossings are not reproduced in this mode)                               */
+int  lcx_set_cond_solver(int mode);
+int  lcx_get_cond_solver(void);
 /* per-particle condensation sub-stepping, all sub-steps of one time step (particles_step.ipp:199-236,                 */
 /* condensation/perparticle/*.ipp); mix != 0: the vapour / heat exchanged by the SDs of a cell is shared after each sub-step */
 int  lcx_cond_perparticle(lcx_engine *e, double dt, double RH_max, int sstp_cond, int mix);

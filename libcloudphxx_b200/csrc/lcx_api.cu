@@ -397,6 +397,9 @@ int lcx_sstp_percell_step(lcx_engine *e, int step, int sstp_cond, int var_rho)
 { return guarded([&] { use_device(e); lcx::sstp_percell_step(e, step, sstp_cond, var_rho != 0); }); }
 int lcx_sstp_save(lcx_engine *e) { return guarded([&] { use_device(e); lcx::sstp_save(e); }); }
 
+int lcx_set_cond_solver(int mode) { lcx::set_cond_solver(mode); return 0; }
+int lcx_get_cond_solver(void) { return lcx::cond_solver(); }
+
 int lcx_cond_perparticle(lcx_engine *e, double dt, double RH_max, int sstp_cond, int mix)
 { return guarded([&] { use_device(e); lcx::cond_perparticle(e, dt, RH_max, sstp_cond, mix != 0); }); }
 

@@ -21,6 +21,7 @@
 #include "lcx_engine.cuh"
 
 #include <cstdlib>
+#include <string>
 
 namespace lcx
 {
@@ -31,7 +32,10 @@ namespace lcx
 #define LCX_COND_MINB 8                      // 8 CTAs of 4 warps per SM (64 registers): measured best of {4,5,6,8}
 #endif
     constexpr int GROUP = 8;                 // lanes per cell in k_cond_cells (4 and 16 measured slower)
-    constexpr unsigned FUSED_MAX = 2048;     // largest cell population for the fused kernel
+#ifndef LCX_COND_FUSED_MAX
+#define LCX_COND_FUSED_MAX 2048
+#endif
+    constexpr unsigned FUSED_MAX = LCX_COND_FUSED_MAX;     // largest cell population for the fused kernel
 
     struct cond_args
     {
@@ -48,7 +52,7 @@ namespace lcx
     }
 
     // thread per SD (big cells)
-    template <bool EXACT>
+    template <int MODE>
     __global__ void __launch_bounds__(TPB) k_cond(size_t n_part, real_t dt, real_t RH_max, cond_args a)
     {
       const size_t i = size_t(blockIdx.x) * TPB + threadIdx.x;
@@ -56,8 +60,8 @@ namespace lcx
       const real_t r2 = a.rw2[i];
       if (r2 <= 0) return;
       const cond_cell<real_t> cl = load_cell(a, a.ijk[i]);
-      if (EXACT) a.rw2[i] = advance_rw2(r2, a.rd3[i], a.kpa[i], a.vt[i], cl, dt, RH_max);
-      else       a.rw2[i] = advance_rw2_fast(r2, a.rd3[i], a.kpa[i], a.vt[i], make_cond_consts(cl, RH_max), dt);
+      if (MODE == COND_EXACT) a.rw2[i] = advance_rw2(r2, a.rd3[i], a.kpa[i], a.vt[i], cl, dt, RH_max);
+      else                    a.rw2[i] = advance_rw2_fast<MODE == COND_TOMS748>(r2, a.rd3[i], a.kpa[i], a.vt[i], make_cond_consts(cl, RH_max), dt);
     }
 
     // group of 8 lanes per cell: growth + 3rd-moment change + th/rv update
@@ -66,7 +70,7 @@ namespace lcx
     // Lanes of a group stay in lock-step droplet by droplet on purpose: all root solves of a warp are then in the same
     // phase of TOMS 748 and share its (division-heavy) interpolation code; letting early finishers start their next
     // droplet at once (persistent-lane variant, measured) desynchronises the phases and is 35 % slower.
-    template <bool EXACT>
+    template <int MODE>
     __global__ void __launch_bounds__(TPB, LCX_COND_MINB) k_cond_cells(idx_t n_cell, const uint32_t *__restrict__ off, real_t dt, real_t RH_max, cond_args a,
                                                        int n_dims, const real_t *__restrict__ dv, int first_step, int keep_after,
                                                        real_t *__restrict__ rw_mom3, real_t *__restrict__ drw_mom3,
@@ -90,8 +94,8 @@ namespace lcx
           real_t r2n = r2;
           if (r2 > 0)
           {
-            r2n = EXACT ? advance_rw2(r2, a.rd3[i], a.kpa[i], a.vt[i], cl, dt, RH_max)
-                        : advance_rw2_fast(r2, a.rd3[i], a.kpa[i], a.vt[i], k, dt);
+            r2n = MODE == COND_EXACT ? advance_rw2(r2, a.rd3[i], a.kpa[i], a.vt[i], cl, dt, RH_max)
+                                        : advance_rw2_fast<MODE == COND_TOMS748>(r2, a.rd3[i], a.kpa[i], a.vt[i], k, dt);
             a.rw2[i] = r2n;
           }
           m3_after += nn * (r2n * sqrt(r2n));
@@ -124,12 +128,20 @@ namespace lcx
       if (c < n_cell) out[c] = -before[c] + after[c];
     }
 
-    bool exact_requested()
-    {
-      static const bool v = [] { const char *s = std::getenv("LCX_COND_EXACT"); return s && s[0] == '1'; }();
-      return v;
-    }
+    int g_solver = -1;
   }
+
+  int cond_solver()
+  {
+    if (g_solver < 0)
+    {
+      const char *v = std::getenv("LCX_COND_SOLVER"), *x = std::getenv("LCX_COND_EXACT");
+      const std::string m = v ? v : "";
+      g_solver = (m == "exact" || (x && x[0] == '1')) ? COND_EXACT : m == "secant" ? COND_SECANT : COND_TOMS748;
+    }
+    return g_solver;
+  }
+  void set_cond_solver(int mode) { g_solver = (mode == COND_EXACT || mode == COND_SECANT) ? mode : COND_TOMS748; }
 
   // one condensation sub-step INCLUDING the th/rv feedback (the host layer no longer calls update_th_rv separately)
   void cond(lcx_engine *e, real_t dt_sub, real_t RH_max, int step, int sstp)
@@ -138,18 +150,14 @@ namespace lcx
     sd_arrays &s = e->S();
     if (!e->grouped) throw error("condensation requested while super-droplets are not grouped by cell");
     cond_args a = {s.rw2.p, s.rd3.p, s.kpa.p, s.vt.p, s.n.p, s.ijk.p, e->rhod.p, e->rv.p, e->T.p, e->p.p, e->RH.p, e->eta.p, e->lambda_D.p, e->lambda_K.p};
-    const bool exact = exact_requested();
+    const int mode = cond_solver();
     const int keep_after = step < sstp - 1;
 
     if (e->max_count <= FUSED_MAX)
     {
       const unsigned blocks = div_up(size_t(g.n_cell) * GROUP, TPB);
-      if (exact)
-        LCX_LAUNCH(e, (k_cond_cells<true>), blocks, TPB, 0, g.n_cell, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p, int(step == 0), keep_after,
-                   e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p);
-      else
-        LCX_LAUNCH(e, (k_cond_cells<false>), blocks, TPB, 0, g.n_cell, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p, int(step == 0), keep_after,
-                   e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p);
+      LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_cond_cells<M>), blocks, TPB, 0, g.n_cell, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p,
+                                        int(step == 0), keep_after, e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p));
       return;
     }
 
@@ -157,8 +165,7 @@ namespace lcx
     if (step == 0) cell_moment(e, nullptr, s.rw2.p, real_t(3. / 2.), true, e->rw_mom3.p);
     if (e->n_part)
     {
-      if (exact) LCX_LAUNCH(e, (k_cond<true>), div_up(e->n_part, TPB), TPB, 0, e->n_part, dt_sub, RH_max, a);
-      else       LCX_LAUNCH(e, (k_cond<false>), div_up(e->n_part, TPB), TPB, 0, e->n_part, dt_sub, RH_max, a);
+      LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_cond<M>), div_up(e->n_part, TPB), TPB, 0, e->n_part, dt_sub, RH_max, a));
     }
     cell_moment(e, nullptr, s.rw2.p, real_t(3. / 2.), true, e->count_mom.p);
     LCX_LAUNCH(e, k_mom_diff, div_up(g.n_cell, 256), 256, 0, g.n_cell, e->count_mom.p, e->rw_mom3.p, e->drw_mom3.p);

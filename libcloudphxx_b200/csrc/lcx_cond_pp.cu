@@ -58,7 +58,7 @@ namespace lcx
 
     struct pp_opts { int th_dry, const_p, RH_formula, n_dims, mix, step, sstp; real_t dt_sub, RH_max; };
 
-    template <bool EXACT>
+    template <int MODE>
     __global__ void __launch_bounds__(TPB) k_pp_advance(size_t n, pp_opts O, pp_state S, const idx_t *__restrict__ ijk,
                                                        real_t *__restrict__ rw2, const real_t *__restrict__ rd3, const real_t *__restrict__ kpa,
                                                        const real_t *__restrict__ vt, const n_t *__restrict__ ns,
@@ -87,8 +87,8 @@ namespace lcx
       cl.RH = RH_of(O.RH_formula, p_i, rv_i, T_i);
       cl.eta = visc(T_i);
       cl.lambda_D = lam_D[c]; cl.lambda_K = lam_K[c];
-      const real_t r2n = EXACT ? advance_rw2(r2, rd3[i], kpa[i], vt[i], cl, O.dt_sub, O.RH_max)
-                               : advance_rw2_fast(r2, rd3[i], kpa[i], vt[i], make_cond_consts(cl, O.RH_max), O.dt_sub);
+      const real_t r2n = MODE == COND_EXACT ? advance_rw2(r2, rd3[i], kpa[i], vt[i], cl, O.dt_sub, O.RH_max)
+                                        : advance_rw2_fast<MODE == COND_TOMS748>(r2, rd3[i], kpa[i], vt[i], make_cond_consts(cl, O.RH_max), O.dt_sub);
       rw2[i] = r2n;
 
       const real_t rw3n = pow(r2n, real_t(3) / real_t(2));
@@ -145,7 +145,7 @@ namespace lcx
     // heat release of a first step that was "already done" during the trials).
     struct pp_adapt { int sstp_max, sstp_act, th_dry, const_p, RH_formula, n_dims; real_t drw2_eps, drw2_max, dt, RH_max; };
 
-    template <bool EXACT>
+    template <int MODE>
     __global__ void __launch_bounds__(TPB) k_pp_adaptive(size_t n, pp_adapt A, pp_state S, const idx_t *__restrict__ ijk,
                                                         real_t *__restrict__ rw2, const real_t *__restrict__ rd3, const real_t *__restrict__ kpa,
                                                         const real_t *__restrict__ vt, const n_t *__restrict__ ns, const real_t *__restrict__ rc2,
@@ -168,8 +168,8 @@ namespace lcx
       auto grow = [&](real_t dt_sub) -> real_t {
         cond_cell<real_t> cl;
         cl.rhod = t_rh; cl.rv = t_rv; cl.T = Tp; cl.p = t_p; cl.RH = RH; cl.eta = visc(Tp); cl.lambda_D = lD; cl.lambda_K = lK;
-        return EXACT ? advance_rw2(r2, rd3_i, kpa_i, vt_i, cl, dt_sub, A.RH_max)
-                     : advance_rw2_fast(r2, rd3_i, kpa_i, vt_i, make_cond_consts(cl, A.RH_max), dt_sub);
+        return MODE == COND_EXACT ? advance_rw2(r2, rd3_i, kpa_i, vt_i, cl, dt_sub, A.RH_max)
+                                        : advance_rw2_fast<MODE == COND_TOMS748>(r2, rd3_i, kpa_i, vt_i, make_cond_consts(cl, A.RH_max), dt_sub);
       };
 
       unsigned sstp = unsigned(A.sstp_max);
@@ -275,17 +275,15 @@ namespace lcx
     sd_arrays &s = e->S();
     const pp_state S = state_of(e);
     if (sstp_act > 1 && !s.rc2.p) throw error("sstp_cond_act > 1 needs the critical radii (opts_init.sstp_cond_act at construction)");
-    static const bool exact = [] { const char *v = std::getenv("LCX_COND_EXACT"); return v && v[0] == '1'; }();
+    const int mode = cond_solver();
 
     cell_moment(e, nullptr, s.rw2.p, real_t(3. / 2.), true, e->rw_mom3.p);                   // save_liq_ice_content_before_change
     if (n)
     {
       LCX_LAUNCH(e, k_pp_delta, div_up(n, 256), 256, 0, n, s.ijk.p, S, e->cfg.const_p, e->rv.p, e->th.p, e->rhod.p, e->p.p);
       pp_adapt A = {sstp_max, sstp_act, e->cfg.th_dry, e->cfg.const_p, e->cfg.RH_formula, g.n_dims, drw2_eps, drw2_max, dt, RH_max};
-      if (exact)
-        LCX_LAUNCH(e, (k_pp_adaptive<true>), div_up(n, TPB), TPB, 0, n, A, S, s.ijk.p, s.rw2.p, s.rd3.p, s.kpa.p, s.vt.p, s.n.p, s.rc2.p, e->dv.p, e->lambda_D.p, e->lambda_K.p);
-      else
-        LCX_LAUNCH(e, (k_pp_adaptive<false>), div_up(n, TPB), TPB, 0, n, A, S, s.ijk.p, s.rw2.p, s.rd3.p, s.kpa.p, s.vt.p, s.n.p, s.rc2.p, e->dv.p, e->lambda_D.p, e->lambda_K.p);
+      LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_pp_adaptive<M>), div_up(n, TPB), TPB, 0, n, A, S, s.ijk.p, s.rw2.p, s.rd3.p, s.kpa.p, s.vt.p, s.n.p, s.rc2.p,
+                                        e->dv.p, e->lambda_D.p, e->lambda_K.p));
     }
     cell_moment(e, nullptr, s.rw2.p, real_t(3. / 2.), true, e->count_mom.p);                 // calc_liq_ice_content_change
     LCX_LAUNCH(e, k_diff, div_up(g.n_cell, 256), 256, 0, g.n_cell, e->count_mom.p, e->rw_mom3.p, e->drw_mom3.p);
@@ -300,7 +298,7 @@ namespace lcx
     const grid_t &g = e->grid;
     sd_arrays &s = e->S();
     const pp_state S = state_of(e);
-    static const bool exact = [] { const char *v = std::getenv("LCX_COND_EXACT"); return v && v[0] == '1'; }();
+    const int mode = cond_solver();
 
     if (!mix) cell_moment(e, nullptr, s.rw2.p, real_t(3. / 2.), true, e->rw_mom3.p);       // save_liq_ice_content_before_change
     if (n)
@@ -311,10 +309,8 @@ namespace lcx
       for (int step = 0; step < sstp; ++step)
       {
         O.step = step;
-        if (exact)
-          LCX_LAUNCH(e, (k_pp_advance<true>), div_up(n, TPB), TPB, 0, n, O, S, s.ijk.p, s.rw2.p, s.rd3.p, s.kpa.p, s.vt.p, s.n.p, e->dv.p, e->lambda_D.p, e->lambda_K.p);
-        else
-          LCX_LAUNCH(e, (k_pp_advance<false>), div_up(n, TPB), TPB, 0, n, O, S, s.ijk.p, s.rw2.p, s.rd3.p, s.kpa.p, s.vt.p, s.n.p, e->dv.p, e->lambda_D.p, e->lambda_K.p);
+        LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_pp_advance<M>), div_up(n, TPB), TPB, 0, n, O, S, s.ijk.p, s.rw2.p, s.rd3.p, s.kpa.p, s.vt.p, s.n.p,
+                                          e->dv.p, e->lambda_D.p, e->lambda_K.p));
         if (mix)
         {
           LCX_LAUNCH(e, k_pp_dth, div_up(n, 256), 256, 0, n, S, dth);

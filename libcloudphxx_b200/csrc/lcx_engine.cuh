@@ -223,6 +223,8 @@ namespace lcx
   void diag_vel_div(lcx_engine *e, real_t dt);
 
   // ---- lcx_cond.cu -----------------------------------------------------------------------------------
+  int cond_solver();                      // COND_SECANT / COND_TOMS748 / COND_EXACT: lcx_set_cond_solver, else $LCX_COND_SOLVER, else TOMS 748
+  void set_cond_solver(int mode);
   void cond(lcx_engine *e, real_t dt_sub, real_t RH_max, int step, int sstp);
   void cond_perparticle(lcx_engine *e, real_t dt, real_t RH_max, int sstp, bool mix);
   void cond_perparticle_adaptive(lcx_engine *e, real_t dt, real_t RH_max, int sstp_max, int sstp_act, real_t drw2_eps, real_t drw2_max);
@@ -242,6 +244,15 @@ namespace lcx
 
   real_t *attr_ptr(lcx_engine *e, int attr);
 }
+
+// runs CALL once with the compile-time constant M set to the run-time solver mode
+#define LCX_BY_COND_MODE(mode, CALL)                                          \
+  switch (mode)                                                               \
+  {                                                                           \
+    case lcx::COND_EXACT:   { constexpr int M = lcx::COND_EXACT; CALL; } break;     \
+    case lcx::COND_SECANT:  { constexpr int M = lcx::COND_SECANT; CALL; } break;    \
+    default:                { constexpr int M = lcx::COND_TOMS748; CALL; } break;   \
+  }
 
 #define LCX_LAUNCH(e, kernel, grid, block, smem, ...)                          \
   do {                                                                         \

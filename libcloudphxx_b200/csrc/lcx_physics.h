@@ -639,6 +639,65 @@ namespace lcx
       if (sv.feed(f.drw2_dt(sv.point()), rd3, result)) return result;
   }
 
+
+  // The same implicit-Euler step with a root search that stops as soon as the root is KNOWN to the reference's tolerance,
+  // instead of shrinking a bracket to it from both sides.  Everything up to and including the choice between "explicit
+  // Euler", "unchanged" and "root search" is the reference's (cond_common.ipp:187-303); the search itself is a safeguarded
+  // secant iteration: f(x) = rw2_old + dt g(x) - x is smooth and, over one (sub-)step, close to linear for every droplet that
+  // is not a haze particle in equilibrium, so the first secant point is usually already 1e-6 of the bracket from the root.
+  // An iterate c is accepted when |f(c) / f'| < 2^-19 c with f' from the last two points (and then corrected by that last
+  // secant step): error <= 2^-18 relative, the reference's own midpoint-of-bracket answer carries 2^-16, so the two differ
+  // by less than the 2^-15 that two valid TOMS 748 answers may differ by.  The sign-changing bracket is kept throughout and
+  // bisected when the secant point leaves it; if nothing is accepted within 40 evaluations the bracket midpoint is returned
+  // once it is narrower than 2^-15 relative (never observed).  North star: "toms748/Newton ... within a stated tolerance".
+  template <class F, class real_t>
+  LCX_HD real_t implicit_euler_rw2_secant(const F &f, real_t rw2_old, real_t rd3, real_t dt, real_t cond_mlt = 2)
+  {
+    const real_t drw2 = dt * f.drw2_dt(rw2_old);
+    if (drw2 == 0) return rw2_old;
+    const real_t rd = cbrt(rd3), rd2 = rd * rd;
+    real_t a = tmax(rd2, rw2_old + tmin(real_t(0), cond_mlt * drw2));
+    real_t b = rw2_old + tmax(real_t(0), cond_mlt * drw2);
+    if (a == b) return rw2_old;
+    real_t fa, fb;
+    if (drw2 > 0) { fa = drw2; fb = rw2_old + dt * f.drw2_dt(b) - b; }
+    else          { fb = drw2; fa = rw2_old + dt * f.drw2_dt(a) - a; }
+    if (fa * fb > 0) { const real_t r = rw2_old + drw2; return r < rd2 ? rd2 : r; }      // not bracketed: explicit Euler
+    if (fa == 0) return a < rd2 ? rd2 : a;
+    if (fb == 0) return b < rd2 ? rd2 : b;
+
+    const real_t accept = real_t(1) / real_t(524288), width = real_t(1) / real_t(32768);        // 2^-19, 2^-15
+    // the two most recent points (p0 older) drive the secant; [a, b] always brackets the root
+    real_t p0 = a, f0 = fa, p1 = b, f1 = fb;
+    if (fabs(fa) < fabs(fb)) { p0 = b; f0 = fb; p1 = a; f1 = fa; }
+    for (int it = 0; it < 40; ++it)
+    {
+      const real_t slope = lcx_div(f1 - f0, p1 - p0);
+      real_t c = p1 - lcx_div(f1, slope);
+      if (!(c > a && c < b)) c = a + (b - a) / 2;
+      const real_t fc = rw2_old + dt * f.drw2_dt(c) - c;
+      if (fc == 0) return c < rd2 ? rd2 : c;
+      if ((fc > 0) == (fa > 0)) { a = c; fa = fc; } else { b = c; fb = fc; }
+      // slope through the newest two points; a usable estimate needs it to point the way f does (f decreases across the root)
+      const real_t s2 = lcx_div(fc - f1, c - p1);
+      if (s2 < 0)
+      {
+        const real_t step = lcx_div(fc, s2);
+        if (fabs(step) < accept * c)
+        {
+          real_t r = c - step;
+          if (!(r > a && r < b)) r = c;
+          return r < rd2 ? rd2 : r;
+        }
+      }
+      if ((b - a) <= width * tmin(fabs(a), fabs(b))) break;
+      p0 = p1; f0 = f1; p1 = c; f1 = fc;
+      if (f1 == f0) { p0 = (fc > 0) == (fa > 0) ? b : a; f0 = (fc > 0) == (fa > 0) ? fb : fa; }     // flat spot: fall back to the bracket end
+    }
+    const real_t r = a + (b - a) / 2;
+    return r < rd2 ? rd2 : r;
+  }
+
   template <class real_t>
   LCX_HD real_t advance_rw2(real_t rw2_old, real_t rd3, real_t kpa, real_t vt, const cond_cell<real_t> &cl,
                             real_t dt, real_t RH_max)
@@ -736,13 +795,19 @@ namespace lcx
     LCX_HD real_t operator()(const real_t &x) const { return (rw2_old + dt * drw2_dt(x) - x); }
   };
 
-  template <class real_t>
+  // root search of the condensation step: COND_TOMS748 (default) - the reference's TOMS 748 with the same trial points (fast
+  // growth law); COND_EXACT - TOMS 748 and the growth law transcribed operation by operation; COND_SECANT (opt-in) - stop as
+  // soon as the root is known to the reference's tolerance
+  enum { COND_SECANT = 0, COND_TOMS748 = 1, COND_EXACT = 2 };
+
+  template <bool TOMS, class real_t>
   LCX_HD real_t advance_rw2_fast(real_t rw2_old, real_t rd3, real_t kpa, real_t vt, const cond_cell_consts<real_t> &k, real_t dt)
   {
     if (rw2_old <= 0) return rw2_old;
     growth_fast<real_t> f;
     f.rw2_old = rw2_old; f.dt = dt; f.rd3 = rd3; f.rd3_dry = rd3 * (real_t(1) - kpa); f.vt_cRe = vt * k.c_Re; f.k = k;
-    return implicit_euler_rw2(f, rw2_old, rd3, dt);
+    if (TOMS) return implicit_euler_rw2(f, rw2_old, rd3, dt);          // the reference's root search, same trial points
+    return implicit_euler_rw2_secant(f, rw2_old, rd3, dt);
   }
 
   // ------------------------------------------------------------------------------------------------

@@ -35,6 +35,20 @@ def lib():
     return _lib
 
 
+COND_SOLVERS = {"secant": 0, "toms748": 1, "exact": 2}
+
+
+def set_cond_solver(name):
+    """root search of the condensation step, process-wide: "toms748" (default, the reference's trial points), "exact" (TOMS 748 +
+    operation-by-operation growth law), "secant" (opt-in fast mode); see include/lcx_b200.h lcx_set_cond_solver"""
+    lib().lcx_set_cond_solver(COND_SOLVERS[name])
+
+
+def get_cond_solver():
+    mode = lib().lcx_get_cond_solver()
+    return [k for k, v in COND_SOLVERS.items() if v == mode][0]
+
+
 def check(rc):
     if rc != 0:
         raise RuntimeError(lib().lcx_last_error().decode())

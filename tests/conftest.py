@@ -24,3 +24,13 @@ def b200():
     """the product: B200 back-end through the flat binding; parity runs replay the reference's mt19937 stream"""
     from tests.support import b200_library
     return b200_library()
+
+
+@pytest.fixture(params=["toms748", "secant"])
+def cond_solver(request):
+    """runs a test under both root searches of the condensation step: the default (the reference's TOMS 748 with identical
+    trial points) and the opt-in safeguarded secant (half the evaluations, same per-step tolerance, different trajectory)"""
+    from libcloudphxx_b200 import engine
+    engine.set_cond_solver(request.param)
+    yield request.param
+    engine.set_cond_solver("toms748")

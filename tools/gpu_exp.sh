@@ -5,11 +5,8 @@ run() {
 import json,sys
 d=json.loads(sys.stdin.read())
 ks=d['kernels']
-def g(s):
-    v=[v for n,v in ks.items() if s in n]
-    return sum(x['ms']/x['launches'] for x in v) if v else 0
-print('$1', 'ms/step %.3f e2e %.3g (%.3f ms) coal %.3f vterm %.3f'%(d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], g('k_coal_small'), g('k_vterm')))
+print('$1', 'ms/step %.3f e2e %.3g (%.3f ms)'%(d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step']))
+for k,v in list(ks.items())[:3]: print('   %-40s %3d %8.3f'%(k[:40], v['launches'], v['ms']/2))
 "
 }
-LCX_COAL_FUSE_VT=0 run "separate vterm"
-run "fused vterm"
+run "secant"
