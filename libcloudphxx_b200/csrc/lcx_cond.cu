@@ -12,9 +12,10 @@
 //                   HBM traffic: 40 B read (n, rw2, rd3, kpa, vt) + 8 B written per SD, cell constants once per cell.
 // Cells too populous for that (0-D boxes: one cell with 1e5..1e6 SDs) use a thread-per-SD kernel between two
 // chunked per-cell moment reductions (lcx_diag.cu).
-// The root solve is FP64-compute bound (~4.6 growth-rate evaluations per SD); the growth law is therefore evaluated
-// in the single-quotient form of lcx_physics.h (growth_fast) by default; LCX_COND_EXACT=1 selects the operation-by-
-// operation transcription of the reference's formula (growth_fn) for cross-checking.
+// The root solve is FP64-compute bound; three variants are compiled (lcx_set_cond_solver / LCX_COND_SOLVER, lcx_physics.h):
+//   toms748 (default) - the reference's TOMS 748, trial point by trial point, growth law in the single-quotient form growth_fast;
+//   exact             - the same with the reference's formula transcribed operation by operation (growth_fn), for cross-checks;
+//   secant            - opt-in: safeguarded secant that stops once the root is known to the reference's tolerance (half the work).
 #ifndef LCX_NO_FAST_MATH
 #define LCX_FAST_MATH 1      // see lcx_physics.h: quotients inside the root solve need not be correctly rounded
 #endif

@@ -7,10 +7,13 @@
 //   hskpng_ijk         src/impl/housekeeping/particles_impl_hskpng_ijk.ipp:159-200
 //   hskpng_sort/count  src/impl/housekeeping/particles_impl_hskpng_sort.ipp:15-70, particles_impl_hskpng_count.ipp:16-48
 //
-// One key per SD (cell index, or n_cell for dead SDs) -> stable LSD radix sort of (key, physical index) on
-// ceil(log2(n_cell+1)) bits -> cell offsets from the sorted keys -> one gather of every attribute into the alternate
-// buffer set.  Dead SDs sort behind the last cell and are simply not copied.  The reference's storage index `sid`
-// travels with each SD and is re-densified (rank among survivors) so that it keeps indexing the injected random streams.
+// One key per SD (cell index, or n_cell for dead SDs).  Usual case (relayout_movers): most SDs stay in their cell, so only
+// the movers are listed and radix-sorted by new cell; stayers keep their order at the front of their cell's new segment,
+// arrivals follow; segment starts come from per-cell counts.  Otherwise (first grouping, > 40 % movers, huge cells): stable
+// LSD radix sort of all (key, physical index) pairs on ceil(log2(n_cell+1)) bits and offsets from the sorted keys.  Either
+// way one gather then moves every attribute into the alternate buffer set; dead SDs are simply not copied.  The reference's
+// storage index `sid` travels with each SD and is re-densified lazily (rank among survivors) when the replayed random
+// stream or get_attr need it dense.
 #include "lcx_engine.cuh"
 
 #include <cstdlib>
