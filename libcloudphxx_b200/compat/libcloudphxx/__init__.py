@@ -6,8 +6,8 @@ Lagrangian scheme and the `common` helpers its scripts use:
 
 Same names, argument order, defaults and error texts as the Boost.Python module (lib.cpp:217-434, lgrngn.hpp:41-330), on
 top of the flat C binding (`bindings/lgrngn_capi.h`).  Environment:
-  LIBCLOUDPHXX_COMPAT_IMPL = b200 (default) | reference   which shared library serves the calls (the second one is the
-                                                          parity oracle, oracle/_ref, and exists for validation only)
+  LIBCLOUDPHXX_COMPAT_LIBRARY = /path/to/lib.so           another shared library exporting the same flat binding
+                                                          (bindings/lgrngn_capi.h) instead of the B200 back-end
   LIBCLOUDPHXX_COMPAT_REDIRECT = 1                        scripts written for backend_t.serial / OpenMP get the CUDA
                                                           back-end instead of "backend was not compiled"
 The bulk schemes (blk_1m, blk_2m) are not part of this package.

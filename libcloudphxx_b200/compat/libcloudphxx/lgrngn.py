@@ -7,14 +7,10 @@ from libcloudphxx_b200 import lgrngn as _L
 
 
 def _library():
-    impl = os.environ.get("LIBCLOUDPHXX_COMPAT_IMPL", "b200")
-    if impl == "b200":
-        return _L.b200()
-    if impl == "reference":
-        here = os.path.dirname(os.path.abspath(__file__))
-        root = os.path.abspath(os.path.join(here, "..", "..", ".."))
-        return _L.Library(os.path.join(root, "oracle", "_ref", "liblgrngn_ref.so"))
-    raise RuntimeError("LIBCLOUDPHXX_COMPAT_IMPL must be 'b200' or 'reference'")
+    """the shared library that serves the calls: the B200 back-end, unless LIBCLOUDPHXX_COMPAT_LIBRARY names another
+    library exporting the same flat binding (bindings/lgrngn_capi.h)"""
+    path = os.environ.get("LIBCLOUDPHXX_COMPAT_LIBRARY")
+    return _L.Library(path) if path else _L.b200()
 
 
 class _Enum(int):

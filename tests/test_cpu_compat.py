@@ -22,7 +22,8 @@ SCRIPTS = ["unit/uniform_init.py", "unit/lgrngn_adve.py", "unit/terminal_velocit
 def env(impl):
     e = dict(os.environ)
     e["PYTHONPATH"] = ROOT + os.pathsep + COMPAT + os.pathsep + e.get("PYTHONPATH", "")
-    e["LIBCLOUDPHXX_COMPAT_IMPL"] = impl
+    if impl == "reference":      # the oracle exports the same flat binding: point the package at it (test infrastructure only)
+        e["LIBCLOUDPHXX_COMPAT_LIBRARY"] = os.path.join(ROOT, "oracle", "_ref", "liblgrngn_ref.so")
     e.setdefault("OMP_NUM_THREADS", "8")
     return e
 
@@ -53,7 +54,7 @@ def test_common_constants_and_known_answers():
 
 
 def test_surface_names_defaults_and_errors():
-    os.environ["LIBCLOUDPHXX_COMPAT_IMPL"] = "b200"
+    os.environ.pop("LIBCLOUDPHXX_COMPAT_LIBRARY", None)
     sys.path.insert(0, COMPAT)
     try:
         from libcloudphxx import lgrngn

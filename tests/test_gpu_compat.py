@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.fixture(scope="module")
 def pkg():
-    os.environ["LIBCLOUDPHXX_COMPAT_IMPL"] = "b200"
+    os.environ.pop("LIBCLOUDPHXX_COMPAT_LIBRARY", None)
     os.environ["LIBCLOUDPHXX_COMPAT_REDIRECT"] = "1"
     sys.path.insert(0, os.path.join(ROOT, "libcloudphxx_b200", "compat"))
     import libcloudphxx
