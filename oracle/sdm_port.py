@@ -236,6 +236,13 @@ def rw3_eq(rd3, kappa, RH, T):
     return toms748(f, lo, hi, f(lo), f(hi))
 
 
+def rw3_cr(rd3, kappa, T):                              # common/kappa_koehler.hpp:90-119,153-169 (maximum of the Koehler curve)
+    A = kelvin_A(T)
+    f = lambda rw3: (A * (rd3 - rw3) * ((kappa - 1) * rd3 + rw3) + 3 * kappa * rd3 * rw3 * math.cbrt(rw3))
+    lo, hi = 1e0 * rd3, 1e8 * rd3
+    return toms748(f, lo, hi, f(lo), f(hi))
+
+
 # ---- condensational growth: src/impl/condensation/common/particles_impl_cond_common.ipp:79-338 --------------------------
 def drw2_dt(rw2, rhod, rv, T, p, RH_eff, eta, rd3, kpa, vt, lam_D, lam_K):
     rw = math.sqrt(rw2)
@@ -363,12 +370,15 @@ def coal_kernel(kind, params, n_a, n_b, rw2_a, rw2_b, vt_a, vt_b):
 
 # ---- the particle system ----------------------------------------------------------------------------------------------------
 class Particles:
-    """0-D / 2-D / 3-D box, sd_conc initialisation, per-cell condensation sub-stepping, SDM coalescence, implicit / Euler
-    advection, sedimentation, periodic side walls, open top / bottom.  Call order as the reference (src/particles_step.ipp)."""
+    """0-D / 2-D / 3-D box, sd_conc initialisation, per-cell and per-particle (mixing / no mixing / adaptive, activation
+    sub-stepping with rc2) condensation sub-stepping, SDM coalescence, implicit / Euler advection, sedimentation, periodic side
+    walls, open top / bottom, removal or recycling of used-up SDs.  Call order as the reference (src/particles_step.ipp)."""
 
     def __init__(self, nx=0, ny=0, nz=0, dx=1., dy=1., dz=1., dt=1., x0=0., y0=0., z0=0., x1=1., y1=1., z1=1., sd_conc=0, n_sd_max=0,
                  sstp_cond=1, sstp_coal=1, kernel=None, kernel_params=None, vt="beard77fast", adve_scheme="implicit",
-                 dry_distros=(), RH_max_init=.95, rng_seed=44, sedi_switch=True, coal_switch=True):
+                 dry_distros=(), RH_max_init=.95, rng_seed=44, sedi_switch=True, coal_switch=True,
+                 exact_sstp_cond=False, sstp_cond_mix=True, adaptive_sstp_cond=False, sstp_cond_act=1,
+                 sstp_cond_adapt_drw2_eps=1e-4, sstp_cond_adapt_drw2_max=4., rc2_T=10.):
         self.nx, self.ny, self.nz = nx, ny, nz
         self.dx, self.dy, self.dz, self.dt = dx, dy, dz, dt
         self.x0, self.y0, self.z0, self.x1, self.y1, self.z1 = x0, y0, z0, x1, y1, z1
@@ -384,6 +394,10 @@ class Particles:
         self.rng = HostRNG(rng_seed)
         self.puddle = dict(liquid_volume=0., dry_volume=0., liquid_number=0., particle_number=0.)
         self.table = vt0_table() if vt == "beard77fast" else None
+        # per-particle condensation sub-stepping (opts_init.hpp:96-106)
+        self.exact_sstp_cond, self.sstp_cond_mix, self.adaptive_sstp_cond = exact_sstp_cond, sstp_cond_mix, adaptive_sstp_cond
+        self.sstp_cond_act, self.drw2_eps, self.drw2_max, self.rc2_T = sstp_cond_act, sstp_cond_adapt_drw2_eps, sstp_cond_adapt_drw2_max, rc2_T
+        self.allow_sstp_cond = sstp_cond > 1 or sstp_cond_act > 1                       # particles_impl.ipp:376
 
     # -- grid helpers: src/impl/initialization/particles_impl_init_grid.ipp:13-155 ------------------------------------------
     def unravel(self, c):
@@ -463,9 +477,23 @@ class Particles:
         self.n_part = self.n.size
         self.vt = np.full(self.n_part, -1.0)
         self.hskpng_vterm(True)
-        self.old = dict(rv=self.rv.copy(), th=self.th.copy(), rhod=self.rhod.copy())   # sstp_save
+        self.rc2 = np.full(self.n_part, -1.0)                                        # particles_impl.ipp:490 (detail::invalid)
+        self.hskpng_rc2()
+        self.sstp_save()
         self.sort(False)
         self.rng.reseed(self.rng_seed)
+
+    def hskpng_rc2(self):                               # hskpng_rc2.ipp:13-32, particles_diag.ipp:41-62
+        if self.sstp_cond_act == 1 or not self.allow_sstp_cond:
+            return
+        for s in range(self.n_part):
+            if self.rc2[s] == -1.0:
+                self.rc2[s] = math.pow(rw3_cr(self.rd3[s], self.kpa[s], self.rc2_T + 273.15), 2. / 3)
+
+    def sstp_save(self):                                # condensation/common/sstp_save.ipp:13-29
+        if self.exact_sstp_cond and self.allow_sstp_cond:
+            self.pp = dict(rv=self.rv[self.ijk].copy(), th=self.th[self.ijk].copy(), rhod=self.rhod[self.ijk].copy())
+        self.old = dict(rv=self.rv.copy(), th=self.th.copy(), rhod=self.rhod.copy())
 
     def dist_analysis(self, fun):                       # init_dist_analysis.ipp:17-75 (automatic range detection)
         vol = self.dv[0] if self.n_dims == 0 else self.dx * self.dy * self.dz
@@ -513,6 +541,10 @@ class Particles:
             return self.th, self.rv
         self.hskpng_mfp()
         sstp = self.sstp_cond
+        if self.exact_sstp_cond and (sstp > 1 or self.sstp_cond_act > 1):      # particles_step.ipp:199-236
+            self.cond_perparticle(RH_max)
+            self.sstp_save()
+            return self.th, self.rv
         for step in range(sstp):
             if sstp > 1:                                 # sstp_percell_step.ipp:7-47
                 for name in (("rv", "th", "rhod") if var_rho else ("rv", "th")):
@@ -536,8 +568,143 @@ class Particles:
             self.rv = self.rv - drv
             self.th = self.th - drv * (-self.th / self.T * np.array([l_v(T) for T in self.T]) / c_pd)
             m3_before = m3_after
-        self.old = dict(rv=self.rv.copy(), th=self.th.copy(), rhod=self.rhod.copy())
+        self.sstp_save()
         return self.th, self.rv
+
+    # -- per-particle sub-stepping: condensation/perparticle/*.ipp ------------------------------------------------------------------
+    def _pp_state(self, th, rv, rhod):                  # cond_perparticle_advance_rw2.ipp:33-78 (th_dry, variable pressure, pv_cc)
+        T = T_of_th_dry(th, rhod)
+        p = rhod * (R_d + rv * R_v) * T
+        return T, p, RH_pv_cc(p, rv, T)
+
+    def _drv(self, drw3, s, rhod_s):                    # rw3diff2drv, cond_common.ipp:24-41
+        mlt = -rho_w * (4. / 3) * PI
+        nn = float(self.n[s])
+        return mlt * drw3 * nn / rhod_s / self.dv[self.ijk[s]] if self.n_dims > 0 else mlt * drw3 * nn
+
+    def cond_perparticle(self, RH_max):
+        N, sstp = self.n_part, self.sstp_cond
+        pp = self.pp
+        dlt = {k: getattr(self, k)[self.ijk] - pp[k] for k in ("rv", "th", "rhod")}     # calculate_noncond_perparticle_sstp_delta.ipp:13-37
+        if not self.sstp_cond_mix:
+            m3_before = self.moment(self.rw2, 1.5)       # save_liq_ice_content_before_change
+        if self.adaptive_sstp_cond:
+            for s in range(N):
+                self._adaptive_one(s, dlt, RH_max)
+        else:
+            rw3 = np.zeros(N)
+            for step in range(sstp):
+                drv, dth, Tp = np.zeros(N), np.zeros(N), np.zeros(N)
+                for s in range(N):
+                    for k in ("rv", "th", "rhod"):       # apply_noncond_perparticle_sstp_delta.ipp:13-33
+                        pp[k][s] = pp[k][s] + dlt[k][s] / sstp
+                    drw3 = -(rw3[s] if step > 0 else math.pow(self.rw2[s], 1.5))     # set_perparticle_drwX_to_minus_rwX.ipp:13-38
+                    T, p, RH = self._pp_state(pp["th"][s], pp["rv"][s], pp["rhod"][s])
+                    c = self.ijk[s]
+                    self.rw2[s] = advance_rw2(self.rw2[s], self.dt / sstp, RH_max, pp["rhod"][s], pp["rv"][s], T, p, RH, visc(T),
+                                              self.rd3[s], self.kpa[s], self.vt[s], self.lam_D[c], self.lam_K[c])
+                    r3 = math.pow(self.rw2[s], 1.5)       # add_perparticle_rwX_to_drwX.ipp:13-44
+                    if step < sstp - 1:
+                        rw3[s] = r3
+                    drw3 = r3 + drw3
+                    drv[s] = self._drv(drw3, s, pp["rhod"][s])
+                    Tp[s] = T
+                # apply_perparticle_drw3_to_perparticle_rv_and_th.ipp:13-62
+                if self.sstp_cond_mix:
+                    add = self._cell_sums(drv)
+                    pp["rv"] = pp["rv"] + add[self.ijk]
+                else:
+                    pp["rv"] = drv + pp["rv"]
+                for s in range(N):
+                    dth[s] = drv[s] * (-pp["th"][s] / Tp[s] * l_v(Tp[s]) / c_pd)
+                if self.sstp_cond_mix:
+                    add = self._cell_sums(dth)
+                    pp["th"] = pp["th"] + add[self.ijk]
+                else:
+                    pp["th"] = dth + pp["th"]
+        # apply_perparticle_cond_change_to_percell_rv_and_th.ipp:13-26
+        if self.sstp_cond_mix:
+            for s in range(N):                           # update_state: every SD writes its cell, the last in storage order stays
+                self.rv[self.ijk[s]] = pp["rv"][s]
+                self.th[self.ijk[s]] = pp["th"][s]
+        else:
+            m3_after = self.moment(self.rw2, 1.5)
+            drv_c = (-m3_before + m3_after) * (rho_w * (4. / 3) * PI)
+            self.rv = self.rv - drv_c
+            self.th = self.th - drv_c * (-self.th / self.T * np.array([l_v(T) for T in self.T]) / c_pd)      # T of the last hskpng_Tpr
+
+    def _cell_sums(self, per_sd):                       # update_pstate, update_th_rv.ipp:243-283 (sum in sorted order)
+        out = np.zeros(self.n_cell)
+        for pos in range(self.n_part):
+            s = self.sorted_id[pos]
+            out[self.ijk[s]] += per_sd[s]
+        return out
+
+    def _adaptive_one(self, s, dlt, RH_max):            # perparticle_nomixing_adaptive_sstp_cond.ipp:49-290
+        pp, c = self.pp, self.ijk[s]
+        t = {k: pp[k][s] for k in ("rv", "th", "rhod")}
+        rw2 = self.rw2[s]
+        st = {}
+
+        def shift(m):
+            for k in ("rv", "th", "rhod"):
+                t[k] += dlt[k][s] * m
+
+        def thermo():
+            st["T"], st["p"], st["RH"] = self._pp_state(t["th"], t["rv"], t["rhod"])
+
+        def grow(r2, dt):
+            return advance_rw2(r2, dt, RH_max, t["rhod"], t["rv"], st["T"], st["p"], st["RH"], visc(st["T"]),
+                               self.rd3[s], self.kpa[s], self.vt[s], self.lam_D[c], self.lam_K[c])
+        sstp_max, sstp = self.sstp_cond, self.sstp_cond
+        first_done = sstp_max == 1
+        drw2 = drw2_new = 0.0
+        tr = 1
+        while tr <= sstp_max:
+            frac = 1.0 if tr == 1 else -1.0 / tr
+            shift(frac)
+            thermo()
+            d = grow(rw2, self.dt / tr) - rw2
+            if tr == 1:
+                drw2 = d
+            else:
+                drw2_new = d
+                if abs(drw2_new * 2 - drw2) <= self.drw2_eps * rw2 and abs(drw2) < self.drw2_max * rw2:
+                    sstp = tr // 2
+                    shift(-frac)
+                    first_done = True
+                    break
+                drw2 = drw2_new
+            tr *= 2
+        if self.sstp_cond_act > 1:
+            rc2 = self.rc2[s]
+            if (rw2 < rc2 and (rw2 + sstp * drw2) > rc2) or (rw2 > rc2 and (rw2 + sstp * drw2) < rc2):
+                sstp = self.sstp_cond_act
+                first_done = False
+        if not first_done:
+            shift(-frac if sstp_max == 1 else frac)
+        frac = 1.0 / sstp
+        rw3 = 0.0
+        for step in range(sstp):
+            drw3 = -rw3 if step > 0 else -math.pow(rw2, 1.5)
+            if first_done and step == 0:
+                rw2 += drw2
+            else:
+                shift(frac)
+                thermo()
+                rw2 = grow(rw2, self.dt / sstp)
+            if step < sstp - 1:
+                rw3 = math.pow(rw2, 1.5)
+                drw3 += rw3
+            else:
+                drw3 += math.pow(rw2, 1.5)
+            drw3 = self._drv(drw3, s, t["rhod"])
+            t["rv"] += drw3
+            drw3 = drw3 * (-t["th"] / st["T"] * l_v(st["T"]) / c_pd)
+            t["th"] += drw3
+        for k in ("rv", "th", "rhod"):
+            pp[k][s] = t[k]
+        self.rw2[s] = rw2
 
     # -- coalescence: coalescence/particles_impl_coal.ipp:99-546 --------------------------------------------------------------------
     def coal(self, dt):
@@ -576,6 +743,8 @@ class Particles:
                     rd3_old += self.rd3[hi]
             self.rd3[lo] = rd3_new
             self.vt[lo] = -1.0
+            if self.sstp_cond_act > 1 and self.allow_sstp_cond:
+                self.rc2[lo] = -1.0                      # coal.ipp:527-541 (invalidator)
         return n_coll
 
     # -- transport: advection/particles_impl_adve.ipp:27-165, sedi.ipp:13-24, bcnd.ipp:99-368 -----------------------------------------
@@ -620,7 +789,36 @@ class Particles:
             self.puddle["particle_number"] += float(nf.sum())
             self.n[out] = 0
 
-    def step_async(self, adve=True, sedi=True, coal=True, cond=True):
+    def rcyc(self):                                     # housekeeping/particles_impl_rcyc.ipp:44-139
+        n_to_rcyc = n_flagged = int((self.n == 0).sum())
+        self.n_recycled = 0
+        if n_flagged == 0:
+            return False
+        order = np.argsort(self.n, kind="stable")       # sort_by_key on (n, storage index): stable in the cpp back-end
+        tmp = self.n[order]
+        ones = np.nonzero(tmp[::-1] == 1)[0]
+        n_splittable = int(ones[0]) if ones.size else self.n_part                      # find() from the large end
+        if n_splittable == 0:
+            return False
+        n_flagged = min(n_flagged, n_splittable)
+        src, dst = order[::-1][:n_flagged], order[:n_flagged]
+        names = ["rd3", "rw2", "kpa", "vt", "x", "y", "z", "rc2"]
+        for q in range(n_flagged):                       # copy_n runs front to back
+            for name in names:
+                a = getattr(self, name)
+                if a.size:
+                    a[dst[q]] = a[src[q]]
+            if hasattr(self, "pp"):
+                for k in self.pp:
+                    self.pp[k][dst[q]] = self.pp[k][src[q]]
+        for q in range(n_flagged):
+            self.n[dst[q]] = self.n[src[q]] - self.n[src[q]] // np.uint64(2)
+        for q in range(n_flagged):
+            self.n[src[q]] = self.n[src[q]] // np.uint64(2)
+        self.n_recycled = n_flagged
+        return n_flagged == n_to_rcyc                    # all recycled: nothing left to remove
+
+    def step_async(self, adve=True, sedi=True, coal=True, cond=True, rcyc=False):
         self.hskpng_Tpr()
         if sedi or coal or cond:
             self.hskpng_vterm(False)
@@ -630,16 +828,22 @@ class Particles:
                 n_coll += self.coal(self.dt / self.sstp_coal)
                 if step + 1 != self.sstp_coal:
                     self.hskpng_vterm(True)
+            self.hskpng_rc2()                            # particles_step.ipp:402-403
         if adve:
             self.adve()
         if sedi and self.nz:
             self.z = self.z - self.dt * self.vt
         self.bcnd()
+        self.n_recycled = 0
+        if rcyc:                                         # post_copy.ipp:24-29
+            self.rcyc()
         keep = self.n != 0                               # hskpng_remove_n0: hskpng_remove.ipp:20-75
-        for name in ("n", "rd3", "rw2", "kpa", "vt", "x", "y", "z"):
+        for name in ("n", "rd3", "rw2", "kpa", "vt", "x", "y", "z", "rc2"):
             a = getattr(self, name)
             if a.size:
                 setattr(self, name, a[keep])
+        if hasattr(self, "pp"):
+            self.pp = {k: v[keep] for k, v in self.pp.items()}
         self.n_part = int(keep.sum())
         ii = (self.x / self.dx).astype(np.int64) if self.nx else 0      # hskpng_ijk.ipp:159-200
         jj = (self.y / self.dy).astype(np.int64) if self.ny else 0
