@@ -236,6 +236,63 @@ def rw3_eq(rd3, kappa, RH, T):
     return toms748(f, lo, hi, f(lo), f(hi))
 
 
+def brent_find_minima(f, lo, hi, max_iter=N_ITER):
+    """Brent's minimiser as Boost.Math implements it (boost/math/tools/minima.hpp, bits capped at half the mantissa; the golden
+    section constant is a single-precision literal there) - called by init_dist_analysis.ipp:95.  The reference build of the
+    oracle uses oracle/boost_shim's restatement of the same routine: parity with real Boost is unpinned (no Boost here)."""
+    tol = math.ldexp(1.0, 1 - 53 // 2)
+    golden = float(np.float32(0.3819660))
+    x = w = v = hi
+    fw = fv = fx = f(x)
+    delta2 = delta = 0.0
+    for _ in range(max_iter):
+        mid = (lo + hi) / 2
+        fract1 = tol * abs(x) + tol / 4
+        fract2 = 2 * fract1
+        if abs(x - mid) <= (fract2 - (hi - lo) / 2):
+            break
+        parabolic = False
+        if abs(delta2) > fract1:
+            r = (x - w) * (fx - fv)
+            q = (x - v) * (fx - fw)
+            pnum = (x - v) * q - (x - w) * r
+            q = 2 * (q - r)
+            if q > 0:
+                pnum = -pnum
+            q = abs(q)
+            td = delta2
+            delta2 = delta
+            if not (abs(pnum) >= abs(q * td / 2) or pnum <= q * (lo - x) or pnum >= q * (hi - x)):
+                delta = pnum / q
+                u = x + delta
+                if (u - lo) < fract2 or (hi - u) < fract2:
+                    delta = -abs(fract1) if (mid - x) < 0 else abs(fract1)
+                parabolic = True
+        if not parabolic:
+            delta2 = (lo - x) if x >= mid else (hi - x)
+            delta = golden * delta2
+        u = (x + delta) if abs(delta) >= fract1 else ((x + abs(fract1)) if delta > 0 else (x - abs(fract1)))
+        fu = f(u)
+        if fu <= fx:
+            if u >= x:
+                lo = x
+            else:
+                hi = x
+            v, w, x = w, x, u
+            fv, fw, fx = fw, fx, fu
+        else:
+            if u < x:
+                lo = u
+            else:
+                hi = u
+            if fu <= fw or w == x:
+                v, w = w, u
+                fv, fw = fw, fu
+            elif fu <= fv or v == x or v == w:
+                v, fv = u, fu
+    return x, fx
+
+
 def rw3_cr(rd3, kappa, T):                              # common/kappa_koehler.hpp:90-119,153-169 (maximum of the Koehler curve)
     A = kelvin_A(T)
     f = lambda rw3: (A * (rd3 - rw3) * ((kappa - 1) * rd3 + rw3) + 3 * kappa * rd3 * rw3 * math.cbrt(rw3))
@@ -378,13 +435,19 @@ class Particles:
                  sstp_cond=1, sstp_coal=1, kernel=None, kernel_params=None, vt="beard77fast", adve_scheme="implicit",
                  dry_distros=(), RH_max_init=.95, rng_seed=44, sedi_switch=True, coal_switch=True,
                  exact_sstp_cond=False, sstp_cond_mix=True, adaptive_sstp_cond=False, sstp_cond_act=1,
-                 sstp_cond_adapt_drw2_eps=1e-4, sstp_cond_adapt_drw2_max=4., rc2_T=10.):
+                 sstp_cond_adapt_drw2_eps=1e-4, sstp_cond_adapt_drw2_max=4., rc2_T=10.,
+                 sd_const_multi=0, sd_conc_large_tail=False, dry_sizes=(), aerosol_independent_of_rhod=False, aerosol_conc_factor=(),
+                 rd_min=-1., rd_max=-1.):
         self.nx, self.ny, self.nz = nx, ny, nz
         self.dx, self.dy, self.dz, self.dt = dx, dy, dz, dt
         self.x0, self.y0, self.z0, self.x1, self.y1, self.z1 = x0, y0, z0, x1, y1, z1
         self.n_dims = (nx > 0) + (ny > 0) + (nz > 0)
         self.n_cell = max(1, nx) * max(1, ny) * max(1, nz)
         self.sd_conc, self.n_sd_max = sd_conc, n_sd_max
+        self.sd_const_multi, self.sd_conc_large_tail = sd_const_multi, sd_conc_large_tail
+        self.dry_sizes = list(dry_sizes)               # [(kappa, {radius: (STP concentration, SDs per cell)})] in ascending kappa
+        self.aerosol_independent_of_rhod, self.aerosol_conc_factor = aerosol_independent_of_rhod, list(aerosol_conc_factor)
+        self.rd_min, self.rd_max = rd_min, rd_max
         self.sstp_cond, self.sstp_coal = sstp_cond, sstp_coal
         self.kernel, self.kernel_params = kernel, kernel_params or {}
         self.vt_kind, self.adve_scheme = vt, adve_scheme
@@ -438,26 +501,11 @@ class Particles:
         self.dv = self.cell_volumes() if self.n_dims else np.zeros(C)
         self.hskpng_Tpr()
         parts = {k: [] for k in ("n", "rd3", "rw2", "kpa", "x", "y", "z", "ijk")}
-        ranges = [self.dist_analysis(fun) for _, fun in self.dry_distros]
-        tot = sum(r[1] - r[0] for r in ranges)
-        for (kappa, fun), (lmin, lmax, mult) in zip(self.dry_distros, ranges):
-            fraction = (lmax - lmin) / tot
-            mult *= self.sd_conc // int(fraction * self.sd_conc + 0.5)          # integer division: init_SD_with_distros_sd_conc.ipp:28
-            per_cell = int(fraction * self.sd_conc)
-            n_new = per_cell * C
-            ijk = np.repeat(np.arange(C), per_cell)                               # init_ijk.ipp:36-52
-            u01 = self.rng.u01(n_new)                                             # init_dry_sd_conc.ipp:48
-            s = np.arange(n_new)
-            lnrd = lmin + ((s - ijk * per_cell) + u01) * (lmax - lmin) / float(per_cell)
-            rd3 = np.array([math.exp(3 * v) for v in lnrd])
-            n = np.empty(n_new, dtype=np.uint64)
+
+        def finalize(ijk, n, rd3, kappa):                # init_SD_with_distros.ipp:62-107: kappa, init_wet, init_xyz
+            n_new = ijk.size
             rw2 = np.empty(n_new)
             for q in range(n_new):
-                v = mult * fun(math.log(rd3[q]) / 3.)                             # init_n.ipp:48-137
-                v = v * self.rhod[ijk[q]] / rho_stp
-                if self.n_dims > 0:
-                    v = v * self.dv[ijk[q]] / (self.dx * self.dy * self.dz)
-                n[q] = int(v + 0.5)
                 RH = min(self.RH[ijk[q]], self.RH_max_init)
                 rw2[q] = math.pow(rw3_eq(rd3[q], kappa, RH, self.T[ijk[q]]), 2. / 3)     # init_wet.ipp:18-40
             ii, jj, kk = self.unravel(ijk)
@@ -471,6 +519,73 @@ class Particles:
                 pos[name] = u * np.minimum(b, (idx + 1) * d) + (1. - u) * np.maximum(a, idx * d)
             for k, v in (("n", n), ("rd3", rd3), ("rw2", rw2), ("kpa", np.full(n_new, kappa)), ("x", pos["x"]), ("y", pos["y"]), ("z", pos["z"]), ("ijk", ijk)):
                 parts[k].append(v)
+
+        def conc_to_number(conc):                        # init_count_num.ipp:35-64
+            arr = np.full(C, conc) * self.dv
+            if not self.aerosol_independent_of_rhod:
+                arr = self.rhod / rho_stp * arr
+            if len(self.aerosol_conc_factor):
+                arr = arr * np.asarray(self.aerosol_conc_factor)[np.arange(C) % self.nz]
+            return arr
+
+        def const_multi(kappa, fun, multi, forced_min=None):      # init_SD_with_distros_const_multi.ipp / _tail.ipp
+            lmin, lmax = self.dist_analysis_const_multi(fun)
+            if forced_min is not None:
+                lmin = forced_min
+            assert lmin < lmax, "Distribution analysis error"
+            bin_ = 1e-4                                           # config.hpp: bin_precision
+            nb = int((lmax - lmin) / bin_)                        # detail::integrate, init_count_num.ipp:17-27
+            integral = (fun(lmin) + fun(lmax)) / 2.
+            for i in range(1, nb):
+                integral += fun(lmin + i * bin_)
+            integral = integral * bin_
+            count = (conc_to_number(integral) / multi + 0.5).astype(np.int64)     # init_count_num_hlpr
+            ijk = np.repeat(np.arange(C), count)
+            n_pt = int((lmax - lmin) / bin_ + 1)                  # calc_CDF, init_dry_const_multi.ipp:25-45
+            cdf = np.array([1 * fun(lmin + bin_ * i) for i in range(n_pt)])
+            for i in range(1, n_pt):
+                cdf[i] = cdf[i - 1] + cdf[i]
+            cdf = cdf / cdf[-1]
+            u01 = self.rng.u01(ijk.size)
+            pos = np.searchsorted(cdf, u01, side="right").astype(np.float64)      # thrust::upper_bound
+            rd3 = np.array([math.exp(3 * (lmin + p_ * bin_)) for p_ in pos])
+            finalize(ijk, np.full(ijk.size, multi, dtype=np.uint64), rd3, kappa)
+
+        ranges = [self.dist_analysis(fun) for _, fun in self.dry_distros] if self.sd_conc > 0 else []
+        tot = sum(r[1] - r[0] for r in ranges)
+        for idx_d, (kappa, fun) in enumerate(self.dry_distros):
+            if self.sd_conc > 0:
+                lmin, lmax, mult = ranges[idx_d]
+                fraction = (lmax - lmin) / tot
+                mult *= self.sd_conc // int(fraction * self.sd_conc + 0.5)          # integer division: init_SD_with_distros_sd_conc.ipp:28
+                per_cell = int(fraction * self.sd_conc)
+                n_new = per_cell * C
+                ijk = np.repeat(np.arange(C), per_cell)                               # init_ijk.ipp:36-52
+                u01 = self.rng.u01(n_new)                                             # init_dry_sd_conc.ipp:48
+                s = np.arange(n_new)
+                lnrd = lmin + ((s - ijk * per_cell) + u01) * (lmax - lmin) / float(per_cell)
+                rd3 = np.array([math.exp(3 * v) for v in lnrd])
+                n = np.empty(n_new, dtype=np.uint64)
+                for q in range(n_new):
+                    v = mult * fun(math.log(rd3[q]) / 3.)                             # init_n.ipp:48-137
+                    if not self.aerosol_independent_of_rhod:
+                        v = v * self.rhod[ijk[q]] / rho_stp
+                    if len(self.aerosol_conc_factor):
+                        v = v * self.aerosol_conc_factor[ijk[q] % self.nz]
+                    if self.n_dims > 0:
+                        v = v * self.dv[ijk[q]] / (self.dx * self.dy * self.dz)
+                    n[q] = int(v + 0.5)
+                finalize(ijk, n, rd3, kappa)
+                if self.sd_conc_large_tail:
+                    const_multi(kappa, fun, 1, forced_min=lmax)
+            if self.sd_const_multi > 0:
+                const_multi(kappa, fun, self.sd_const_multi)
+        for (kappa, sizes) in self.dry_sizes:            # init_SD_with_sizes.ipp:16-76 (std::map order: ascending kappa, then radius)
+            for radius, (conc, count) in sorted(sizes.items()):
+                ijk = np.repeat(np.arange(C), count)
+                number = conc_to_number(conc)
+                n = (number[ijk] / count + .5).astype(np.uint64)                  # init_n.ipp:147-162
+                finalize(ijk, n, np.full(ijk.size, radius * radius * radius), kappa)
         for k, v in parts.items():
             setattr(self, k, np.concatenate(v) if v else np.zeros(0))
         self.ijk = self.ijk.astype(np.int64)
@@ -495,8 +610,19 @@ class Particles:
             self.pp = dict(rv=self.rv[self.ijk].copy(), th=self.th[self.ijk].copy(), rhod=self.rhod[self.ijk].copy())
         self.old = dict(rv=self.rv.copy(), th=self.th.copy(), rhod=self.rhod.copy())
 
+    def dist_analysis_const_multi(self, fun):           # init_dist_analysis.ipp:78-123
+        if self.rd_min >= 0 and self.rd_max >= 0:
+            return math.log(self.rd_min), math.log(self.rd_max)
+        lo, hi = math.log(1e-14), math.log(1e-3)
+        x_max, f_max = brent_find_minima(lambda x: -1 * fun(x), lo, hi)
+        bound = -f_max / 1e20                            # config.hpp: threshold
+        g = lambda x: -bound + fun(x)
+        return toms748(g, lo, x_max, g(lo), g(x_max)), toms748(g, x_max, hi, g(x_max), g(hi))
+
     def dist_analysis(self, fun):                       # init_dist_analysis.ipp:17-75 (automatic range detection)
         vol = self.dv[0] if self.n_dims == 0 else self.dx * self.dy * self.dz
+        if self.rd_min >= 0 and self.rd_max >= 0:       # user-defined range
+            return math.log(self.rd_min), math.log(self.rd_max), math.log(self.rd_max / self.rd_min) / self.sd_conc * 1.0 * vol
         rd_min, rd_max = 1e-14, 1e-3
         while True:
             mult = math.log(rd_max / rd_min) / self.sd_conc * 1.0 * vol

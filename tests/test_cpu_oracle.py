@@ -215,3 +215,39 @@ def test_port_perparticle_substepping_matches_reference(ref, variant):
         for k, a in (("rd3", p_p.rd3), ("rw2", p_p.rw2), ("x", p_p.x), ("y", p_p.y), ("z", p_p.z)):
             assert np.array_equal(p_r.get_attr(k), a), (k, step, S.rel_err(p_r.get_attr(k), a))
         assert np.array_equal(f["th"], fp["th"]) and np.array_equal(f["rv"], fp["rv"]), (step, S.rel_err(f["th"], fp["th"]), S.rel_err(f["rv"], fp["rv"]))
+
+
+@pytest.mark.parametrize("kind", ["const_multi", "const_multi_user_range", "large_tail", "dry_sizes", "conc_factor", "sd_conc_user_range"])
+def test_port_initialisation_flavours_match_reference(ref, kind):
+    """every way of creating SDs at t = 0 (init_SD_with_distros*.ipp, init_SD_with_sizes.ipp): same attributes to the last bit"""
+    nx, ny, nz = 3, 2, 5
+    oi, o, f = S.box_3d(ref, nx=nx, ny=ny, nz=nz, sd_conc=16, n_sd_max=200000)
+    kw = dict(sd_conc=16, dry_distros=[(0.61, lognormal_as_capi(S.AEROSOL_ICICLE))])
+    if kind == "const_multi":
+        oi.sd_conc, oi.sd_const_multi = 0, int(2e9)
+        kw.update(sd_conc=0, sd_const_multi=int(2e9))
+    elif kind == "const_multi_user_range":
+        oi.sd_conc, oi.sd_const_multi, oi.rd_min, oi.rd_max = 0, int(1e9), 5e-9, 2e-6
+        kw.update(sd_conc=0, sd_const_multi=int(1e9), rd_min=5e-9, rd_max=2e-6)
+    elif kind == "large_tail":
+        oi.sd_conc_large_tail, oi.sd_conc = 1, 256
+        oi.dry_distros = [L.lognormal(0.61, S.AEROSOL_ICICLE), L.lognormal(1.28, [(0.5e-6, 1.6, 2e3)])]
+        kw.update(sd_conc=256, sd_conc_large_tail=True,
+                  dry_distros=[(0.61, lognormal_as_capi(S.AEROSOL_ICICLE)), (1.28, lognormal_as_capi([(0.5e-6, 1.6, 2e3)]))])
+    elif kind == "dry_sizes":
+        oi.dry_sizes = {0.3: {0.1e-6: (30e6, 5), 0.5e-6: (1e6, 2)}, (0.9, 0.0): {1e-6: (2e5, 3)}}
+        kw.update(dry_sizes=[(0.3, {0.1e-6: (30e6, 5), 0.5e-6: (1e6, 2)}), (0.9, {1e-6: (2e5, 3)})])
+    elif kind == "conc_factor":
+        oi.aerosol_independent_of_rhod, oi.aerosol_conc_factor = 1, [1.0, 0.5, 2.0, 0.25, 1.5]
+        kw.update(aerosol_independent_of_rhod=True, aerosol_conc_factor=[1.0, 0.5, 2.0, 0.25, 1.5])
+    elif kind == "sd_conc_user_range":
+        oi.rd_min, oi.rd_max = 1e-9, 5e-6
+        kw.update(rd_min=1e-9, rd_max=5e-6)
+    p_r = ref.factory(L.backend_t.serial, oi)
+    p_r.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
+    p_p = port.Particles(nx=nx, ny=ny, nz=nz, dx=20., dy=20., dz=20., dt=1., x1=nx * 20., y1=ny * 20., z1=nz * 20., n_sd_max=200000,
+                         kernel="efficiencies", kernel_params={}, **kw)
+    p_p.init(f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"])
+    assert p_p.n.size > 0 and np.array_equal(p_r.get_n(), p_p.n)
+    for k, a in (("rd3", p_p.rd3), ("rw2", p_p.rw2), ("kappa", p_p.kpa), ("x", p_p.x), ("y", p_p.y), ("z", p_p.z)):
+        assert np.array_equal(p_r.get_attr(k), a), (kind, k)
