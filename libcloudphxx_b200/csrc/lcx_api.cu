@@ -21,7 +21,18 @@ namespace
     catch (...) { g_last_error = "unknown error"; return 2; }
   }
 
-  void use_device(lcx_engine *e) { LCX_CUDA(cudaSetDevice(e->device)); }
+  // consumer = the call may read or write cell fields on the engine's stream: order it after pending uploads
+  void use_device(lcx_engine *e, bool consumer = true)
+  {
+    LCX_CUDA(cudaSetDevice(e->device));
+    if (!consumer) return;
+    if (e->scalars_pending)
+    {
+      LCX_CUDA(cudaStreamWaitEvent(e->stream, e->scalars_ready, 0));
+      e->scalars_pending = false;
+    }
+    e->tail_is_gather = false;
+  }
 
   struct field_ref { lcx::real_t *p; size_t n; };
 
@@ -89,6 +100,8 @@ lcx_engine::~lcx_engine()
   for (auto &r : prof) { cudaEventDestroy(r.t0); cudaEventDestroy(r.t1); }
   if (timer0) { cudaEventDestroy(timer0); cudaEventDestroy(timer1); }
   if (h_scalars) cudaFreeHost(h_scalars);
+  if (scalars_ready) cudaEventDestroy(scalars_ready);
+  if (pre_gather) cudaEventDestroy(pre_gather);
   if (courant_ready) cudaEventDestroy(courant_ready);
   if (main_mark) cudaEventDestroy(main_mark);
   if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -136,6 +149,8 @@ int lcx_create(const lcx_config *cfg, lcx_engine **out)
     LCX_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     LCX_CUDA(cudaEventCreateWithFlags(&e->courant_ready, cudaEventDisableTiming));
     LCX_CUDA(cudaEventCreateWithFlags(&e->main_mark, cudaEventDisableTiming));
+    LCX_CUDA(cudaEventCreateWithFlags(&e->scalars_ready, cudaEventDisableTiming));
+    LCX_CUDA(cudaEventCreateWithFlags(&e->pre_gather, cudaEventDisableTiming));
 
     grid_t &g = e->grid;
     g.nx = cfg->nx; g.ny = cfg->ny; g.nz = cfg->nz;
@@ -234,7 +249,8 @@ int lcx_sync(lcx_engine *e)
   return guarded([&] {
     use_device(e);
     LCX_CUDA(cudaStreamSynchronize(e->stream));
-    if (e->courant_pending) LCX_CUDA(cudaStreamSynchronize(e->copy_stream));   // the data stay "pending" for the engine's stream
+    if (e->upload_batch_open) LCX_CUDA(cudaStreamSynchronize(e->copy_stream));   // the data stay "pending" for the engine's stream
+    e->upload_batch_open = false;
   });
 }
 
@@ -270,26 +286,24 @@ int lcx_cells_get(lcx_engine *e, int field, void *dst, int64_t count)
 int lcx_cells_set_part(lcx_engine *e, int field, int64_t offset, const void *src, int64_t count)
 {
   return guarded([&] {
-    use_device(e);
+    const bool after_relayout = e->tail_is_gather;      // nothing but the gather has been queued since the last re-layout
+    use_device(e, /*consumer=*/false);
     const field_ref f = field_of(e, field);
     if (offset < 0 || count < 0 || size_t(offset + count) > f.n) throw lcx::error("lcx_cells_set_part: range outside field " + std::to_string(field));
-    cudaStream_t st = e->stream;
     const bool courant = field == LCX_F_COURANT_X || field == LCX_F_COURANT_Y || field == LCX_F_COURANT_Z;
-    if (courant)
+    if (!e->upload_batch_open)      // first piece of a batch: what is queued on the engine's stream may still read the old fields
     {
-      st = e->copy_stream;
-      if (!e->courant_pending)      // first piece of a batch: everything queued so far may still read the old fields
+      if (after_relayout) LCX_CUDA(cudaStreamWaitEvent(e->copy_stream, e->pre_gather, 0));     // ... except the gather
+      else
       {
         LCX_CUDA(cudaEventRecord(e->main_mark, e->stream));
         LCX_CUDA(cudaStreamWaitEvent(e->copy_stream, e->main_mark, 0));
       }
+      e->upload_batch_open = true;
     }
-    LCX_CUDA(cudaMemcpyAsync(static_cast<lcx::real_t *>(f.p) + offset, src, size_t(count) * sizeof(lcx::real_t), cudaMemcpyHostToDevice, st));
-    if (courant)
-    {
-      LCX_CUDA(cudaEventRecord(e->courant_ready, e->copy_stream));
-      e->courant_pending = true;
-    }
+    LCX_CUDA(cudaMemcpyAsync(static_cast<lcx::real_t *>(f.p) + offset, src, size_t(count) * sizeof(lcx::real_t), cudaMemcpyHostToDevice, e->copy_stream));
+    if (courant) { LCX_CUDA(cudaEventRecord(e->courant_ready, e->copy_stream)); e->courant_pending = true; }
+    else         { LCX_CUDA(cudaEventRecord(e->scalars_ready, e->copy_stream)); e->scalars_pending = true; }
   });
 }
 

@@ -121,6 +121,11 @@ struct lcx_engine
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t courant_ready = nullptr, main_mark = nullptr;
   bool courant_pending = false;
+  // th, rv, rhod, p uploads use the same copy stream: right after a re-layout the engine's stream is still busy with the
+  // gather (which touches no cell field), and the next step's fields can already travel (pre_gather marks the point the
+  // copy stream has to wait for); every entry point that consumes cell fields first orders itself after scalars_ready
+  cudaEvent_t scalars_ready = nullptr, pre_gather = nullptr;
+  bool scalars_pending = false, upload_batch_open = false, tail_is_gather = false;
   uint64_t launches = 0;
 
   size_t cap = 0;                // n_sd_max

@@ -372,6 +372,7 @@ namespace lcx
     sd_arrays &s = e->S();
     sd_arrays &a = e->A();
     const uint32_t *sorted_keys = nullptr;     // full-sort path only: the gather takes the cell index from them
+    bool gather_queued = false;
 
     if (n_old == 0)
     {
@@ -415,7 +416,9 @@ namespace lcx
       add(G, s.sid.p, a.sid.p, 4);
       add(G, s.pp_rv.p, a.pp_rv.p, 8); add(G, s.pp_th.p, a.pp_th.p, 8); add(G, s.pp_rh.p, a.pp_rh.p, 8); add(G, s.pp_p.p, a.pp_p.p, 8);
       add(G, s.rc2.p, a.rc2.p, 8);
+      LCX_CUDA(cudaEventRecord(e->pre_gather, e->stream));      // uploads of the next step's fields may overtake the gather
       LCX_LAUNCH(e, k_gather, div_up(n_new, TPB), TPB, 0, n_new, perm, sorted_keys, g.class_bits, a.ijk.p, G);
+      gather_queued = true;
     }
     e->cur ^= 1;
     e->n_part = n_new;
@@ -429,6 +432,7 @@ namespace lcx
       if (e->dense_always) densify_sid(e);
     }
     if (n_new == 0) { e->sid_hi = 0; e->sid_dense = true; }
+    e->tail_is_gather = gather_queued;           // cleared by the next entry point that works on cell fields
   }
 
   // new sid = rank of the old sid among the survivors (the order a stable compaction of the reference's storage gives)
