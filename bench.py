@@ -65,29 +65,76 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    def __init__(self, index=0):
-        super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+    """SM clock and throttle reasons of one GPU, sampled WHILE the timed region runs.
 
-    def run(self):
+    The timed region lasts a few hundred milliseconds, one `nvidia-smi` process start takes about as long, so the samples
+    come from NVML in this process (the same counters nvidia-smi prints: clocks.sm, clocks.max.sm,
+    clocks_event_reasons.*), every 2 ms; `nvidia-smi` is only the fallback when NVML cannot be loaded.
+    """
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index=0, pci_bus_id=None):
+        super().__init__(daemon=True)
+        self.index, self.pci, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, pci_bus_id, [], set(), False, None
+        self.source = None
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.handle = None
+            if pci_bus_id:
+                try:
+                    self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(pci_bus_id.encode() if isinstance(pci_bus_id, str) else pci_bus_id)
+                except Exception:
+                    self.handle = None
+            if self.handle is None:
+                vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip().isdigit()]
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(int(vis[index]) if index < len(vis) else index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self.nvml = self.handle = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        for bit, nm in self.REASONS.items():
+            if mask & bit:
+                self.reasons.add(nm)
+
+    def _sample_smi(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+        self.samples.append(float(out[0]))
+        self.max_mhz = float(out[1])
+        self.source = "nvidia-smi"
+        for nm, v in zip(names, out[2:]):
+            if v.strip().lower().startswith("active"):
+                self.reasons.add(nm)
+
+    def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
-                self.max_mhz = float(out[1])
-                for nm, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(nm)
+                if self.nvml:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.002 if self.nvml else 0.05)
 
     def result(self):
         self.stop_flag = True
-        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        self.join(timeout=6)
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "source": self.source}
 
 
 def pinned(shape):
@@ -236,7 +283,12 @@ def run_b200(args):
         resident_step()
 
     # ---- device-resident throughput --------------------------------------------------------------------------
-    sampler = ClockSampler(local)
+    props = torch.cuda.get_device_properties(local)
+    try:
+        pci = "%08x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+    except AttributeError:
+        pci = None
+    sampler = ClockSampler(local, pci)
     sampler.start()
     barrier()
     l0 = eng.launches()
@@ -250,7 +302,6 @@ def run_b200(args):
     barrier()
     wall_ms = 1e3 * (time.time() - tw)
     launches = eng.launches() - l0
-    clocks = sampler.result()
     ms = reduce_max(ms)
     total_updates = reduce_sum(float(updates))
     value = total_updates / (ms * 1e-3)
@@ -264,6 +315,7 @@ def run_b200(args):
         host_step()
     barrier()
     e2e_s = reduce_max(time.time() - t0)
+    clocks = sampler.result()          # sampled over both timed regions (device-resident and end-to-end)
     e2e_value = reduce_sum(float(upd2)) / e2e_s
     h2d = sum(f[k].nbytes for k in ("th", "rv", "rhod", "Cx", "Cy", "Cz"))
     d2h = f["th"].nbytes + f["rv"].nbytes
@@ -347,7 +399,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nx", type=int, default=64)

@@ -154,6 +154,11 @@ int  lcx_sstp_save(lcx_engine *e);                              /* sstp_save.ipp
 /* of the reference's fixture that count threshold crossings are not reproduced in this mode)                               */
 int  lcx_set_cond_solver(int mode);
 int  lcx_get_cond_solver(void);
+/* work distribution of the fused per-cell condensation kernel, process-wide; results are the same up to the order in   */
+/* which the droplets of a cell are summed: 0 = automatic (default), -1 = eight lanes per cell, k in 1..16 = a warp per   */
+/* run of k consecutive cells with its lanes balanced over the run's super-droplets                                       */
+int  lcx_set_cond_layout(int cells_per_warp);
+int  lcx_get_cond_layout(void);
 /* per-particle condensation sub-stepping, all sub-steps of one time step (particles_step.ipp:199-236,                 */
 /* condensation/perparticle/*.ipp); mix != 0: the vapour / heat exchanged by the SDs of a cell is shared after each sub-step */
 int  lcx_cond_perparticle(lcx_engine *e, double dt, double RH_max, int sstp_cond, int mix);

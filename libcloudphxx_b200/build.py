@@ -17,8 +17,11 @@ REPO = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 HOST = os.path.join(HERE, "host")
 BIND = os.path.join(HERE, "bindings")
-LIBDIR = os.path.join(HERE, "lib")
-OBJDIR = os.path.join(HERE, "build")
+# LCX_BUILD_TAG=<tag> builds a tuning variant into lib_<tag>/ (objects in build_<tag>/) next to the product; the loaders pick
+# it up through LCX_B200_LIBDIR.  Experiments only: the product is lib/.
+_TAG = os.environ.get("LCX_BUILD_TAG", "")
+LIBDIR = os.path.join(HERE, "lib" + ("_" + _TAG if _TAG else ""))
+OBJDIR = os.path.join(HERE, "build" + ("_" + _TAG if _TAG else ""))
 
 NVCC = os.environ.get("LCX_NVCC", "/usr/local/cuda/bin/nvcc")
 CXX = os.environ.get("LCX_CXX", "/usr/bin/g++")

@@ -413,6 +413,8 @@ int lcx_sstp_save(lcx_engine *e) { return guarded([&] { use_device(e); lcx::sstp
 
 int lcx_set_cond_solver(int mode) { lcx::set_cond_solver(mode); return 0; }
 int lcx_get_cond_solver(void) { return lcx::cond_solver(); }
+int lcx_set_cond_layout(int cells_per_warp) { lcx::set_cond_layout(cells_per_warp); return 0; }
+int lcx_get_cond_layout(void) { return lcx::cond_layout(); }
 
 int lcx_cond_perparticle(lcx_engine *e, double dt, double RH_max, int sstp_cond, int mix)
 { return guarded([&] { use_device(e); lcx::cond_perparticle(e, dt, RH_max, sstp_cond, mix != 0); }); }

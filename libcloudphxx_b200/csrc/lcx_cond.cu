@@ -10,6 +10,12 @@
 //                   per SD: n r^3 before, implicit-Euler root solve (TOMS 748), n r^3 after;
 //                   per cell: deterministic 8-lane shuffle reduction, then rv -= drv, th -= drv dth/drv.
 //                   HBM traffic: 40 B read (n, rw2, rd3, kpa, vt) + 8 B written per SD, cell constants once per cell.
+//   k_cond_range  - the same work with the lanes balanced over SDs instead of cells: a warp owns a run of up to 16
+//                   consecutive cells, i.e. ONE contiguous range of SDs, and walks it 32 SDs at a time; the per-cell
+//                   constants of the run sit in shared memory, the per-cell sums come from a segmented warp reduction
+//                   (the cell index is non-decreasing along the range).  k_cond_cells leaves lanes idle whenever the
+//                   four cells of a warp differ in population (measured: 24.7 of 32 lanes in the kernel body at
+//                   40 +- 6 SDs per cell); here only the last round of a warp is ragged.  Chosen on large grids.
 // Cells too populous for that (0-D boxes: one cell with 1e5..1e6 SDs) use a thread-per-SD kernel between two
 // chunked per-cell moment reductions (lcx_diag.cu).
 // The root solve is FP64-compute bound; three variants are compiled (lcx_set_cond_solver / LCX_COND_SOLVER, lcx_physics.h):
@@ -122,6 +128,80 @@ namespace lcx
       }
     }
 
+    // a warp per run of `run` consecutive cells (run <= RANGE_MAX): lanes balanced over the SDs of the run
+    constexpr int RANGE_MAX = 16;
+    template <int MODE>
+    __global__ void __launch_bounds__(TPB, LCX_COND_MINB) k_cond_range(idx_t n_cell, int run, const uint32_t *__restrict__ off, real_t dt, real_t RH_max, cond_args a,
+                                                       int n_dims, const real_t *__restrict__ dv, int first_step, int keep_after,
+                                                       real_t *__restrict__ rw_mom3, real_t *__restrict__ drw_mom3,
+                                                       real_t *__restrict__ th, real_t *__restrict__ rv)
+    {
+      constexpr int WARPS = TPB / 32;
+      __shared__ cond_cell_consts<real_t> s_k[WARPS][RANGE_MAX];
+      __shared__ real_t s_m[WARPS][RANGE_MAX][2];
+      const int w = threadIdx.x / 32, l = threadIdx.x % 32;
+      const size_t c0_ = (size_t(blockIdx.x) * WARPS + w) * size_t(run);
+      if (c0_ >= n_cell) return;                      // whole warps leave; nothing below synchronises across warps
+      const idx_t c0 = idx_t(c0_);
+      const int nc = int(n_cell - c0 < idx_t(run) ? n_cell - c0 : idx_t(run));
+      if (l < nc)
+      {
+        if (MODE != COND_EXACT) s_k[w][l] = make_cond_consts(load_cell(a, c0 + l), RH_max);
+        s_m[w][l][0] = 0; s_m[w][l][1] = 0;
+      }
+      __syncwarp();
+      const uint32_t b = off[c0], en = off[c0 + nc];
+      for (uint32_t base = b; base < en; base += 32)
+      {
+        const uint32_t i = base + l;
+        const bool act = i < en;
+        int ci = RANGE_MAX;                           // idle lanes sit behind the last SD: keys stay non-decreasing
+        real_t mb = 0, ma = 0;
+        if (act)
+        {
+          const idx_t cc = a.ijk[i] - c0;
+          ci = cc < idx_t(nc) ? int(cc) : nc - 1;
+          const real_t r2 = a.rw2[i];
+          const real_t nn = real_t(a.n[i]);
+          mb = nn * (r2 * sqrt(r2));
+          real_t r2n = r2;
+          if (r2 > 0)
+          {
+            r2n = MODE == COND_EXACT ? advance_rw2(r2, a.rd3[i], a.kpa[i], a.vt[i], load_cell(a, c0 + ci), dt, RH_max)
+                                        : advance_rw2_fast<MODE == COND_TOMS748>(r2, a.rd3[i], a.kpa[i], a.vt[i], s_k[w][ci], dt);
+            a.rw2[i] = r2n;
+          }
+          ma = nn * (r2n * sqrt(r2n));
+        }
+        // segmented sums over lanes with equal cell index; afterwards the first lane of every segment holds its total
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+          const int ko = __shfl_down_sync(0xffffffffu, ci, o);
+          const real_t vb = __shfl_down_sync(0xffffffffu, mb, o);
+          const real_t va = __shfl_down_sync(0xffffffffu, ma, o);
+          if (l + o < 32 && ko == ci) { mb += vb; ma += va; }
+        }
+        const int prev = __shfl_up_sync(0xffffffffu, ci, 1);
+        if (act && (l == 0 || prev != ci)) { s_m[w][ci][0] += mb; s_m[w][ci][1] += ma; }     // one writer per cell and round
+        __syncwarp();
+      }
+      if (l < nc)
+      {
+        const idx_t c = c0 + l;
+        const cond_cell<real_t> cl = load_cell(a, c);      // read again rather than kept in registers across the solve; nobody wrote rv[c] yet
+        real_t m3_before = s_m[w][l][0], m3_after = s_m[w][l][1];
+        if (n_dims > 0) { m3_before = m3_before / dv[c] / cl.rhod; m3_after = m3_after / dv[c] / cl.rhod; }
+        if (!first_step) m3_before = rw_mom3[c];
+        if (keep_after) rw_mom3[c] = m3_after;
+        const real_t drv = (-m3_before + m3_after) * (cst<real_t>::rho_w() * real_t(4. / 3) * cst<real_t>::pi());
+        drw_mom3[c] = drv;
+        rv[c] = cl.rv - drv;
+        const real_t th_c = th[c];
+        th[c] = th_c - drv * d_th_d_rv(cl.T, th_c);
+      }
+    }
+
     // out[c] = -before[c] + after[c]
     __global__ void k_mom_diff(idx_t n_cell, const real_t *__restrict__ after, const real_t *__restrict__ before, real_t *__restrict__ out)
     {
@@ -130,6 +210,36 @@ namespace lcx
     }
 
     int g_solver = -1;
+    int g_layout = -2;         // -2: not read yet; -1: 8 lanes per cell; 0: automatic; 1..RANGE_MAX: cells per warp of k_cond_range
+  }
+
+  int cond_layout()
+  {
+    if (g_layout == -2)
+    {
+      const char *v = std::getenv("LCX_COND_LAYOUT");
+      g_layout = v ? std::atoi(v) : 0;
+      if (g_layout < -1 || g_layout > RANGE_MAX) g_layout = 0;
+    }
+    return g_layout;
+  }
+  void set_cond_layout(int cells_per_warp) { g_layout = (cells_per_warp < -1 || cells_per_warp > RANGE_MAX) ? 0 : cells_per_warp; }
+
+  // cells per warp of k_cond_range, or 0 for k_cond_cells.  Automatic rule: runs as long as possible (the ragged last round
+  // of a warp costs 16 idle lanes on average, so a run should hold a few hundred SDs) while the grid still fills the GPU
+  // four times over; small grids keep the 8-lanes-per-cell kernel, which has more parallelism to offer there.
+  static int range_run(const lcx_engine *e)
+  {
+    const int lay = cond_layout();
+    if (lay < 0) return 0;
+    if (lay > 0) return lay;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device);
+    const size_t warps_wanted = size_t(sms) * 32 * 4;
+    size_t run = e->grid.n_cell / warps_wanted;
+    if (run > size_t(RANGE_MAX)) run = RANGE_MAX;
+    if (run < 4) return 0;
+    return int(run);
   }
 
   int cond_solver()
@@ -154,6 +264,14 @@ namespace lcx
     const int mode = cond_solver();
     const int keep_after = step < sstp - 1;
 
+    const int run = e->max_count <= FUSED_MAX ? range_run(e) : 0;
+    if (run > 0)
+    {
+      const unsigned blocks = div_up(div_up(g.n_cell, run), TPB / 32);
+      LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_cond_range<M>), blocks, TPB, 0, g.n_cell, run, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p,
+                                        int(step == 0), keep_after, e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p));
+      return;
+    }
     if (e->max_count <= FUSED_MAX)
     {
       const unsigned blocks = div_up(size_t(g.n_cell) * GROUP, TPB);

@@ -230,6 +230,8 @@ namespace lcx
   // ---- lcx_cond.cu -----------------------------------------------------------------------------------
   int cond_solver();                      // COND_SECANT / COND_TOMS748 / COND_EXACT: lcx_set_cond_solver, else $LCX_COND_SOLVER, else TOMS 748
   void set_cond_solver(int mode);
+  int cond_layout();                      // lcx_set_cond_layout, else $LCX_COND_LAYOUT, else 0 (automatic)
+  void set_cond_layout(int cells_per_warp);
   void cond(lcx_engine *e, real_t dt_sub, real_t RH_max, int step, int sstp);
   void cond_perparticle(lcx_engine *e, real_t dt, real_t RH_max, int sstp, bool mix);
   void cond_perparticle_adaptive(lcx_engine *e, real_t dt, real_t RH_max, int sstp_max, int sstp_act, real_t drw2_eps, real_t drw2_max);

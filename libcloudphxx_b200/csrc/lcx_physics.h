@@ -35,6 +35,22 @@ namespace lcx
   // residual whose root is wanted to 2^-15 only, so a correctly rounded result buys nothing: a translation unit may define
   // LCX_FAST_MATH to get reciprocal-approximation + two Newton steps + one residual correction on the device (error <= 1 ulp,
   // no special-case branch), about 1/3 of the instructions of the IEEE division sequence.  Everywhere else "/" is IEEE.
+  // FP64 instructions cannot carry a full 64-bit immediate: a literal such as 1.71 or 1/5040 is put together by two UMOVs
+  // at every use, which made up 8 % of the executed instructions of the condensation kernel (ncu source view, profiles/).
+  // Operands read from the constant bank cost no instruction, so the literals of the root solve's inner loop live in a table.
+  // Same values, same operations: results are bit-identical to the literal form (the host build keeps the literals).
+#if defined(LCX_FAST_MATH) && defined(__CUDACC__) && !defined(LCX_NO_KC)
+  static __constant__ double lcx_kc[] = {
+    1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0,   // 0..8: Taylor series of exp
+    1e-4, 1. / 3, 1. / 9, 5. / 81,                                                                                                  // 9..12: cbrt(1 + x) series
+    1.71, 1.33                                                                                                                      // 13, 14: transition-regime correction
+  };
+#endif
+#if defined(LCX_FAST_MATH) && defined(__CUDA_ARCH__) && !defined(LCX_NO_KC)
+#  define LCX_KC(i, literal) (::lcx::lcx_kc[i])
+#else
+#  define LCX_KC(i, literal) (literal)
+#endif
 #if defined(LCX_FAST_MATH) && defined(__CUDA_ARCH__)
   __device__ __forceinline__ double lcx_div(double a, double b)
   {
@@ -62,9 +78,10 @@ namespace lcx
   __device__ __forceinline__ double lcx_exp_small(double x)
   {
     if (!(x >= 0 && x < 0.125)) return exp(x);
-    double p = 1.0 / 39916800.0;
-    p = fma(p, x, 1.0 / 3628800.0); p = fma(p, x, 1.0 / 362880.0); p = fma(p, x, 1.0 / 40320.0); p = fma(p, x, 1.0 / 5040.0);
-    p = fma(p, x, 1.0 / 720.0); p = fma(p, x, 1.0 / 120.0); p = fma(p, x, 1.0 / 24.0); p = fma(p, x, 1.0 / 6.0);
+    double p = LCX_KC(0, 1.0 / 39916800.0);
+    p = fma(p, x, LCX_KC(1, 1.0 / 3628800.0)); p = fma(p, x, LCX_KC(2, 1.0 / 362880.0)); p = fma(p, x, LCX_KC(3, 1.0 / 40320.0));
+    p = fma(p, x, LCX_KC(4, 1.0 / 5040.0)); p = fma(p, x, LCX_KC(5, 1.0 / 720.0)); p = fma(p, x, LCX_KC(6, 1.0 / 120.0));
+    p = fma(p, x, LCX_KC(7, 1.0 / 24.0)); p = fma(p, x, LCX_KC(8, 1.0 / 6.0));
     p = fma(p, x, 0.5); p = fma(p, x, 1.0); p = fma(p, x, 1.0);
     return p;
   }
@@ -776,15 +793,16 @@ namespace lcx
       for (int q = 0; q < 2; ++q)
       {
         const real_t x = Re * nu[q];
-        const real_t cb = (fabs(x) < real_t(1e-4))
-          ? real_t(1) + x * (real_t(1. / 3) - x * (real_t(1. / 9) - x * real_t(5. / 81)))
+        const real_t cb = (fabs(x) < real_t(LCX_KC(9, 1e-4)))
+          ? real_t(1) + x * (real_t(LCX_KC(10, 1. / 3)) - x * (real_t(LCX_KC(11, 1. / 9)) - x * real_t(LCX_KC(12, 5. / 81))))
           : real_t(lcx_cbrt_ge1(real_t(1) + x));
         nu[q] = real_t(1) + cb * boost;
       }
       const real_t Sh = nu[0], Nu = nu[1];
       const real_t KnD = k.lam_D * inv_rw, KnK = k.lam_K * inv_rw;
-      const real_t bDn = real_t(1) + KnD, bDd = real_t(1) + KnD * (real_t(1.71) + real_t(1.33) * KnD);
-      const real_t bKn = real_t(1) + KnK, bKd = real_t(1) + KnK * (real_t(1.71) + real_t(1.33) * KnK);
+      const real_t c171 = real_t(LCX_KC(13, 1.71)), c133 = real_t(LCX_KC(14, 1.33));
+      const real_t bDn = real_t(1) + KnD, bDd = real_t(1) + KnD * (c171 + c133 * KnD);
+      const real_t bKn = real_t(1) + KnK, bKd = real_t(1) + KnK * (c171 + c133 * KnK);
       const real_t awn = rw3 - rd3, awd = rw3 - rd3_dry;
       const real_t klv = lcx_exp_small(k.A * inv_rw);
       const real_t tD = bDn * Sh, tK = bKn * Nu;

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LCX_LIB_PATH = os.path.join(_HERE, "lib", "liblcx_b200.so")
+LCX_LIB_PATH = os.path.join(os.environ.get("LCX_B200_LIBDIR") or os.path.join(_HERE, "lib"), "liblcx_b200.so")
 _lib = None
 
 
@@ -47,6 +47,16 @@ def set_cond_solver(name):
 def get_cond_solver():
     mode = lib().lcx_get_cond_solver()
     return [k for k, v in COND_SOLVERS.items() if v == mode][0]
+
+
+def set_cond_layout(cells_per_warp):
+    """work distribution of the fused per-cell condensation kernel, process-wide: 0 automatic (default), -1 eight lanes per
+    cell, k in 1..16 a warp per run of k consecutive cells; see include/lcx_b200.h lcx_set_cond_layout"""
+    lib().lcx_set_cond_layout(int(cells_per_warp))
+
+
+def get_cond_layout():
+    return int(lib().lcx_get_cond_layout())
 
 
 def check(rc):

@@ -334,7 +334,7 @@ for _n in ("dry_rng", "wet_rng", "kappa_rng", "dry_rng_cons", "wet_rng_cons", "k
 
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-B200_LIB_PATH = os.path.join(_HERE, "lib", "liblgrngn_b200.so")
+B200_LIB_PATH = os.path.join(os.environ.get("LCX_B200_LIBDIR") or os.path.join(_HERE, "lib"), "liblgrngn_b200.so")
 _b200 = None
 
 

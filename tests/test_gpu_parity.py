@@ -358,6 +358,55 @@ def test_parcel_perparticle_substepping(ref, b200, sstp_cond, mixing):
     assert a[-1][2].max() > 1e-11, "nothing activated - the test would be vacuous"
 
 
+@pytest.fixture(params=[-1, 1, 3, 16])
+def cond_layout(request):
+    """runs a test under every work distribution of the fused per-cell condensation kernel: eight lanes per cell (-1) and a
+    warp per run of k consecutive cells with balanced lanes (k = 1, 3, 16; the automatic rule picks 16 at cfg4 size)"""
+    from libcloudphxx_b200 import engine
+    engine.set_cond_layout(request.param)
+    yield request.param
+    engine.set_cond_layout(0)
+
+
+@pytest.mark.parametrize("sstp_cond", [1, 3])
+def test_full_step_3d_every_cond_layout(ref, b200, cond_layout, sstp_cond):
+    """test_full_step_3d with the condensation kernel forced into each of its work distributions (ragged runs: 240 cells are
+    not a multiple of 16; sub-stepping exercises the carried-over third moment)"""
+    def check(step, p_r, p_n, f_r, f_n):
+        n_r, n_n = p_r.get_n(), p_n.get_n()
+        assert n_r.size == n_n.size, step
+        assert np.array_equal(n_r, n_n), "multiplicities differ at step %d" % step
+        assert np.array_equal(p_r.get_attr("rd3"), p_n.get_attr("rd3")), step
+        assert S.rel_err(p_r.get_attr("rw2"), p_n.get_attr("rw2")) < (step + 2) * sstp_cond * 2.0 ** -15, step
+        assert S.rel_err(f_r["th"], f_n["th"]) < 1e-9, (step, S.rel_err(f_r["th"], f_n["th"]))
+        assert S.rel_err(f_r["rv"], f_n["rv"]) < 1e-7, (step, S.rel_err(f_r["rv"], f_n["rv"]))
+    S.run_pair(ref, b200, S.box_3d, 5, on_step=check, nx=6, ny=5, nz=8, sd_conc=32, rain_mode=True, sstp_cond=sstp_cond)
+
+
+def test_cond_layouts_agree(b200):
+    """the work distribution changes only the order in which a cell's droplets are summed: after one condensation step from the
+    same state every wet radius is bit-identical across layouts, th and rv agree to summation rounding"""
+    from libcloudphxx_b200 import engine
+    res = []
+    try:
+        for lay in (-1, 1, 5, 16):
+            engine.set_cond_layout(lay)
+            oi, o, f = S.box_3d(b200, nx=7, ny=5, nz=9, sd_conc=40, rain_mode=True, sstp_cond=2)
+            p = b200.factory(L.backend_t.CUDA, oi)
+            p.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
+            p.step_sync(o, f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"])
+            res.append((p.get_attr("rw2"), f["th"].copy(), f["rv"].copy()))
+            p.step_async(o)
+    finally:
+        engine.set_cond_layout(0)
+    rw0, th0, rv0 = res[0]
+    assert not np.array_equal(th0, S.box_3d(b200, nx=7, ny=5, nz=9, sd_conc=40, rain_mode=True)[2]["th"]), "no condensation happened"
+    for rw, th, rv in res[1:]:
+        # sub-step 2 starts from th / rv that may differ in the last bit, so wet radii agree to rounding rather than bit for bit
+        assert S.rel_err(rw0, rw) < 1e-12, S.rel_err(rw0, rw)
+        assert S.rel_err(th0, th) < 1e-14 and S.rel_err(rv0, rv) < 1e-13, (S.rel_err(th0, th), S.rel_err(rv0, rv))
+
+
 @pytest.mark.parametrize("mixing", [1, 0])
 def test_perparticle_substepping_3d_with_transport(ref, b200, mixing):
     """the per-SD records of rv, th, rhod travel with the SDs through advection, coalescence, removal and re-layout"""
