@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 A_FULL_BYTES = 192.0          # algorithmic bytes per SD-update, full step, double
 KERNEL_BYTES = {              # algorithmic bytes per SD per launch of the kernels that sweep all SDs
     "k_cond_cells": 48.0,      # rw2 r+w, rd3, kpa, vt, n (8 B each); the cell fields are 1/40 of that
+    "k_cond_range": 52.0,      # the same + the cell index of every SD (4 B)
     "k_cond": 52.0, "k_coal_small": 76.0, "k_coal_big": 76.0, "k_transport": 80.0, "k_gather": 136.0,
     "(k_cell_reduce_small<Term, IS_MAX>)": 20.0, "k_vterm": 24.0, "k_make_keys": 40.0,
     "k_mv_count": 4.0, "k_mv_list": 4.0, "k_mv_place_stayers": 12.0,
@@ -342,7 +343,7 @@ def run_b200(args):
                         "frac": (achieved / peak) if achieved else None, "traffic": traffic_of(name, n_live),
                         "algorithmic_bytes_per_sd": per_sd, "sd_per_launch": n_live, "mean_launch_ms": t_ms / n_l,
                         "step_frac_of_hbm_roofline": value * A_FULL_BYTES / (world * peak * 1e9),
-                        "note": "k_cond_cells is FP64-pipe/latency bound, not HBM bound (ncu: fp64 pipe ~57 % busy, ~20 of 32 lanes active): profiles/",
+                        "note": "the condensation kernel is FP64-pipe / issue bound, not HBM bound (ncu: fp64 pipe ~57 % busy, ~20 of 32 lanes active, 6 % of DRAM peak): profiles/",
                         "per_kernel": {k: {"GB/s": round(kernel_bytes(k) * n_live / (ms_ / n * 1e-3) / 1e9, 1),
                                            "frac": round(kernel_bytes(k) * n_live / (ms_ / n * 1e-3) / 1e9 / peak, 4)}
                                        for k, (n, ms_) in rep.items() if kernel_bytes(k) and ms_ > 0}}
@@ -382,7 +383,7 @@ def run_b200(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "cfg4 x-slab per GPU: %dx%dx%d cells x %d SD/cell, hall_davis_no_waals, beard77fast, implicit adve, sstp 1/1" % (nx, ny, nz, args.sd_conc),
                        "sd_per_gpu": nx * ny * nz * args.sd_conc, "global_cells": [nx * world, ny, nz], "rng": "philox4x32-10",
-                       "cond_solver": "toms748 (the reference's trial points)",
+                       "cond_solver": "toms748 (the reference's trial points)", "cond_layout": E.get_cond_layout(),
                        "l2": "inputs_exceed_l2 (%.1f GB of SD state per GPU)" % (nx * ny * nz * args.sd_conc * 76 / 1e9),
                        "init_s": round(t_init, 2), "max_sd_per_cell": max_count, "wall_ms_per_step": wall_ms / args.steps},
             "clocks": clocks,

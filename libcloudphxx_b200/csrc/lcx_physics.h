@@ -74,15 +74,21 @@ namespace lcx
     return r;
   }
   __device__ __forceinline__ float lcx_rsqrt(float x) { return rsqrtf(x); }
-  // exp(x) for the Kelvin term, 0 <= x < 1/8 (x = A / rw, A ~ 1e-9 m): Taylor polynomial of degree 11, remainder < 3e-20
+  // exp(x) for the Kelvin term (x = A / rw, A ~ 1e-9 m).  0 <= x < 1/8 (rw > 8 nm): Taylor polynomial of degree 11, remainder
+  // < 3e-20.  1/8 <= x < 1 (the smallest aerosol, a few lanes of a warp at a time: the library routine there was a divergent
+  // 45-instruction detour taking 4 % of the kernel's instructions at 4 of 32 lanes): exp(x) = exp(x/8)^8, three squarings,
+  // <= 7 ulp.  Anything else goes to the library.
   __device__ __forceinline__ double lcx_exp_small(double x)
   {
-    if (!(x >= 0 && x < 0.125)) return exp(x);
+    if (!(x >= 0 && x < 1.0)) return exp(x);
+    const bool scaled = x >= 0.125;
+    const double y = scaled ? x * 0.125 : x;
     double p = LCX_KC(0, 1.0 / 39916800.0);
-    p = fma(p, x, LCX_KC(1, 1.0 / 3628800.0)); p = fma(p, x, LCX_KC(2, 1.0 / 362880.0)); p = fma(p, x, LCX_KC(3, 1.0 / 40320.0));
-    p = fma(p, x, LCX_KC(4, 1.0 / 5040.0)); p = fma(p, x, LCX_KC(5, 1.0 / 720.0)); p = fma(p, x, LCX_KC(6, 1.0 / 120.0));
-    p = fma(p, x, LCX_KC(7, 1.0 / 24.0)); p = fma(p, x, LCX_KC(8, 1.0 / 6.0));
-    p = fma(p, x, 0.5); p = fma(p, x, 1.0); p = fma(p, x, 1.0);
+    p = fma(p, y, LCX_KC(1, 1.0 / 3628800.0)); p = fma(p, y, LCX_KC(2, 1.0 / 362880.0)); p = fma(p, y, LCX_KC(3, 1.0 / 40320.0));
+    p = fma(p, y, LCX_KC(4, 1.0 / 5040.0)); p = fma(p, y, LCX_KC(5, 1.0 / 720.0)); p = fma(p, y, LCX_KC(6, 1.0 / 120.0));
+    p = fma(p, y, LCX_KC(7, 1.0 / 24.0)); p = fma(p, y, LCX_KC(8, 1.0 / 6.0));
+    p = fma(p, y, 0.5); p = fma(p, y, 1.0); p = fma(p, y, 1.0);
+    if (scaled) { p *= p; p *= p; p *= p; }
     return p;
   }
   __device__ __forceinline__ float lcx_exp_small(float x) { return exp(x); }

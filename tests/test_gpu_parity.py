@@ -384,27 +384,34 @@ def test_full_step_3d_every_cond_layout(ref, b200, cond_layout, sstp_cond):
 
 
 def test_cond_layouts_agree(b200):
-    """the work distribution changes only the order in which a cell's droplets are summed: after one condensation step from the
-    same state every wet radius is bit-identical across layouts, th and rv agree to summation rounding"""
+    """the work distribution changes only the order in which a cell's droplets are summed: after one condensation sub-step from
+    the same state every wet radius is bit-identical across layouts and th, rv agree to summation rounding; with a second
+    sub-step (which starts from those th, rv) the wet radii agree far inside the root solve's own 2^-15"""
     from libcloudphxx_b200 import engine
-    res = []
-    try:
-        for lay in (-1, 1, 5, 16):
-            engine.set_cond_layout(lay)
-            oi, o, f = S.box_3d(b200, nx=7, ny=5, nz=9, sd_conc=40, rain_mode=True, sstp_cond=2)
-            p = b200.factory(L.backend_t.CUDA, oi)
-            p.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
-            p.step_sync(o, f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"])
-            res.append((p.get_attr("rw2"), f["th"].copy(), f["rv"].copy()))
-            p.step_async(o)
-    finally:
-        engine.set_cond_layout(0)
-    rw0, th0, rv0 = res[0]
-    assert not np.array_equal(th0, S.box_3d(b200, nx=7, ny=5, nz=9, sd_conc=40, rain_mode=True)[2]["th"]), "no condensation happened"
-    for rw, th, rv in res[1:]:
-        # sub-step 2 starts from th / rv that may differ in the last bit, so wet radii agree to rounding rather than bit for bit
-        assert S.rel_err(rw0, rw) < 1e-12, S.rel_err(rw0, rw)
-        assert S.rel_err(th0, th) < 1e-14 and S.rel_err(rv0, rv) < 1e-13, (S.rel_err(th0, th), S.rel_err(rv0, rv))
+    for sstp_cond in (1, 2):
+        res = []
+        try:
+            for lay in (-1, 1, 5, 16):
+                engine.set_cond_layout(lay)
+                oi, o, f = S.box_3d(b200, nx=7, ny=5, nz=9, sd_conc=40, rain_mode=True, sstp_cond=sstp_cond)
+                th_init = f["th"].copy()
+                p = b200.factory(L.backend_t.CUDA, oi)
+                p.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
+                p.step_sync(o, f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"])
+                res.append((p.get_attr("rw2"), f["th"].copy(), f["rv"].copy()))
+                p.step_async(o)
+        finally:
+            engine.set_cond_layout(0)
+        rw0, th0, rv0 = res[0]
+        assert not np.array_equal(th0, th_init), "no condensation happened"
+        for rw, th, rv in res[1:]:
+            e_rw, e_th, e_rv = S.rel_err(rw0, rw), S.rel_err(th0, th), S.rel_err(rv0, rv)
+            print("sstp_cond %d: layouts differ by rw2 %.3g th %.3g rv %.3g" % (sstp_cond, e_rw, e_th, e_rv))
+            if sstp_cond == 1:
+                assert np.array_equal(rw0, rw)
+                assert e_th < 1e-14 and e_rv < 1e-13, (e_th, e_rv)
+            else:
+                assert e_rw < 1e-8 and e_th < 1e-12 and e_rv < 1e-11, (e_rw, e_th, e_rv)
 
 
 @pytest.mark.parametrize("mixing", [1, 0])
