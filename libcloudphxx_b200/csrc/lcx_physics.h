@@ -103,11 +103,31 @@ namespace lcx
     return c;
   }
   __device__ __forceinline__ float lcx_cbrt_ge1(float y) { return cbrtf(y); }
+  // cbrt(1 + x), 0 <= x <= 1/2 (ventilation factors of cloud and drizzle drops: x = Re Sc <= 0.5 up to r ~ 40 um): the seed is a
+  // degree-5 polynomial in single precision (Chebyshev fit on [0, 1/2], error 1.8e-7 with rounding) instead of cbrtf with its
+  // range reduction, then the same two fixed-slope Newton steps in double (1.8e-7 -> 5e-14 -> 1.8e-16, checked over the whole
+  // interval by tools/check_fastmath.cu).  Half the instructions of lcx_cbrt_ge1, which made up 13 % of the kernel's.
+  __device__ __forceinline__ double lcx_cbrt1p_mid(double x)
+  {
+    const float xf = float(x);
+    float c0 = 0.011139679700136185f;
+    c0 = fmaf(c0, xf, -0.03272373229265213f); c0 = fmaf(c0, xf, 0.059791404753923416f); c0 = fmaf(c0, xf, -0.1108996570110321f);
+    c0 = fmaf(c0, xf, 0.333324670791626f); c0 = fmaf(c0, xf, 1.0f);
+    float sf;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sf) : "f"(3.0f * c0 * c0));
+    const double s = double(sf), y = 1.0 + x;
+    double c = double(c0);
+    c = fma(-fma(c * c, c, -y), s, c);
+    c = fma(-fma(c * c, c, -y), s, c);
+    return c;
+  }
+  __device__ __forceinline__ float lcx_cbrt1p_mid(float x) { return cbrtf(1.0f + x); }
 #else
   template <class T> LCX_HD T lcx_div(T a, T b) { return a / b; }
   template <class T> LCX_HD T lcx_rsqrt(T x) { return T(1) / sqrt(x); }
   template <class T> LCX_HD T lcx_exp_small(T x) { return exp(x); }
   template <class T> LCX_HD T lcx_cbrt_ge1(T y) { return cbrt(y); }
+  template <class T> LCX_HD T lcx_cbrt1p_mid(T x) { return cbrt(T(1) + x); }
 #endif
 
   template <class T> LCX_HD T tmin(T a, T b) { return (b < a) ? b : a; }   // std::min semantics
@@ -801,7 +821,7 @@ namespace lcx
         const real_t x = Re * nu[q];
         const real_t cb = (fabs(x) < real_t(LCX_KC(9, 1e-4)))
           ? real_t(1) + x * (real_t(LCX_KC(10, 1. / 3)) - x * (real_t(LCX_KC(11, 1. / 9)) - x * real_t(LCX_KC(12, 5. / 81))))
-          : real_t(lcx_cbrt_ge1(real_t(1) + x));
+          : (x <= real_t(0.5)) ? real_t(lcx_cbrt1p_mid(x)) : real_t(lcx_cbrt_ge1(real_t(1) + x));
         nu[q] = real_t(1) + cb * boost;
       }
       const real_t Sh = nu[0], Nu = nu[1];
