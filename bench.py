@@ -41,10 +41,18 @@ KERNEL_BYTES = {              # algorithmic bytes per SD per launch of the kerne
 }
 
 
+def base_name(name):
+    """profile names carry template arguments and parentheses (e.g. "(k_cond_range<M>)"): the bare kernel name"""
+    return name.strip("()").split("<")[0]
+
+
 def kernel_bytes(name):
-    """profile names carry template arguments and parentheses (e.g. "(k_cond_cells<false>)"): longest key contained in the name"""
-    hits = [k for k in KERNEL_BYTES if k.strip("()").split("<")[0] in name]
-    return KERNEL_BYTES[max(hits, key=len)] if hits else 0.0
+    for k, v in KERNEL_BYTES.items():
+        if base_name(k) == base_name(name):
+            return v
+    if base_name(name).startswith("k_vterm"):
+        return KERNEL_BYTES["k_vterm"]
+    return 0.0
 
 
 def traffic_of(name, n_sd):
