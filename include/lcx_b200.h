@@ -160,7 +160,7 @@ int  lcx_get_cond_solver(void);
 int  lcx_set_cond_layout(int cells_per_warp);
 int  lcx_get_cond_layout(void);
 /* per-particle condensation sub-stepping, all sub-steps of one time step (particles_step.ipp:199-236,                 */
-/* condensation/perparticle/*.ipp); mix != 0: the vapour / heat exchanged by the SDs of a cell is shared after each sub-step */
+/* condensation/perparticle/ *.ipp); mix != 0: the vapour / heat exchanged by the SDs of a cell is shared after each sub-step */
 int  lcx_cond_perparticle(lcx_engine *e, double dt, double RH_max, int sstp_cond, int mix);
 /* the same with the number of sub-steps chosen per SD (perparticle_nomixing_adaptive_sstp_cond.ipp:8-335); no mixing      */
 int  lcx_cond_perparticle_adaptive(lcx_engine *e, double dt, double RH_max, int sstp_cond_max, int sstp_cond_act,

@@ -38,6 +38,16 @@ def test_host_library_exports_binding_and_extras():
         assert not missing, (header, missing)
 
 
+@pytest.mark.parametrize("header", ["include/lcx_b200.h", "libcloudphxx_b200/bindings/lgrngn_capi.h", "libcloudphxx_b200/host/particles_b200.h"])
+def test_boundary_headers_are_plain_c(header, tmp_path):
+    """the drop-in boundary is a C ABI: every header a foreign-function binding would read compiles as C99 (and as C++) on its own"""
+    import subprocess
+    for lang, std in (("c", "-std=c99"), ("c++", "-std=c++11")):
+        r = subprocess.run(["gcc", std, "-Wall", "-Wextra", "-pedantic", "-Werror", "-x", lang, "-fsyntax-only", "-"],
+                           input='#include "%s"\n' % os.path.join(ROOT, header), capture_output=True, text=True)
+        assert r.returncode == 0, (lang, r.stderr)
+
+
 def gpu_present():
     return E.lib().lcx_device_count() > 0
 
