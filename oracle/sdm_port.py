@@ -428,7 +428,7 @@ def coal_kernel(kind, params, n_a, n_b, rw2_a, rw2_b, vt_a, vt_b):
 # ---- the particle system ----------------------------------------------------------------------------------------------------
 class Particles:
     """0-D / 2-D / 3-D box, sd_conc initialisation, per-cell and per-particle (mixing / no mixing / adaptive, activation
-    sub-stepping with rc2) condensation sub-stepping, SDM coalescence, implicit / Euler advection, sedimentation, periodic side
+    sub-stepping with rc2) condensation sub-stepping, SDM coalescence, implicit / Euler / predictor-corrector advection, sedimentation, periodic side
     walls, open top / bottom, removal or recycling of used-up SDs.  Call order as the reference (src/particles_step.ipp)."""
 
     def __init__(self, nx=0, ny=0, nz=0, dx=1., dy=1., dz=1., dt=1., x0=0., y0=0., z0=0., x1=1., y1=1., z1=1., sd_conc=0, n_sd_max=0,
@@ -874,9 +874,75 @@ class Particles:
         return n_coll
 
     # -- transport: advection/particles_impl_adve.ipp:27-165, sedi.ipp:13-24, bcnd.ipp:99-368 -----------------------------------------
+    def _halo_courant(self, C, ext_x, h):
+        """Courant field with h columns of halo on both x sides, filled the way init_e2l's map does it (init_e2l.ipp:34-114,
+        init_sync.ipp:27-44): the linear element index is wrapped once by the size of the caller's array, so column -1 of the
+        staggered x-field is the caller's LAST face (nx), not face nx - 1"""
+        n = self.nx + ext_x
+        idx = np.arange(-h, n + h)
+        idx = np.where(idx >= n, idx - n, np.where(idx < 0, idx + n, idx))
+        return C[idx]
+
+    def _adve_pred_corr(self):                         # advection/particles_impl_adve.ipp:169-304
+        h = 2                                            # halo_size of pred_corr (particles_impl.ipp ctor)
+        three = self.n_dims == 3
+        Cxh = self._halo_courant(self.Cx, 1, h)
+        Cyh = self._halo_courant(self.Cy, 0, h) if three else None
+        Czh = self._halo_courant(self.Cz, 0, h) if self.n_dims >= 2 else None
+
+        def cell():                                      # hskpng_ijk in the halo's coordinate system
+            i = (self.x / self.dx).astype(np.int64)
+            j = (self.y / self.dy).astype(np.int64) if three else np.zeros(self.n_part, dtype=np.int64)
+            k = (self.z / self.dz).astype(np.int64) if self.n_dims >= 2 else np.zeros(self.n_part, dtype=np.int64)
+            return i, j, k
+
+        def calc(apply):                                 # adve_calc<adve_helper_expl>(apply): all dimensions from the same cell indices
+            i, j, k = cell.ijk
+            g = (lambda a, di, dj, dk: a[i + di, j + dj, k + dk]) if three else \
+                ((lambda a, di, dj, dk: a[i + di, k + dk]) if self.n_dims == 2 else (lambda a, di, dj, dk: a[i + di]))
+            f = 1. if apply else 0.
+            C_l, C_r = g(Cxh, 0, 0, 0), g(Cxh, 1, 0, 0)
+            if self.n_dims == 1:
+                C_r = C_l
+            self.x = f * self.x + (C_r - C_l) * (self.x - self.dx * i) + self.dx * C_l
+            if three:
+                C_l, C_r = g(Cyh, 0, 0, 0), g(Cyh, 0, 1, 0)
+                self.y = f * self.y + (C_r - C_l) * (self.y - self.dy * j) + self.dy * C_l
+            if self.n_dims >= 2:
+                C_l, C_r = g(Czh, 0, 0, 0), g(Czh, 0, 0, 1)
+                self.z = f * self.z + (C_r - C_l) * (self.z - self.dz * k) + self.dz * C_l
+
+        self.x = self.x + float(h) * self.dx             # coordinates that start at the halo's left edge
+        cell.ijk = cell()
+        x_old, y_old, z_old = self.x.copy(), self.y.copy(), self.z.copy()
+        calc(True)                                       # predictor
+        if self.n_dims >= 2:
+            self.z = np.where(self.z >= self.z1, self.z1 - 1e-8 * self.dz, self.z)
+            self.z = np.where(self.z <= self.z0, self.z0 + 1e-8 * self.dz, self.z)
+        if three:
+            L_y = self.y1 - self.y0
+            y_old = np.where(self.y >= self.y1, y_old + L_y, y_old)
+            y_old = np.where(self.y < self.y0, y_old - L_y, y_old)
+            self.y = self.y0 + np.fmod((self.y - self.y0) + 10 * L_y, L_y)
+        cell.ijk = cell()
+        x_old = self.x + x_old
+        if three:
+            y_old = self.y + y_old
+        if self.n_dims >= 2:
+            z_old = self.z + z_old
+        calc(False)                                      # displacement at the midpoint
+        self.x = (self.x + x_old) / 2.
+        if three:
+            self.y = (self.y + y_old) / 2.
+        if self.n_dims >= 2:
+            self.z = (self.z + z_old) / 2.
+        self.x = self.x - float(h) * self.dx
+
     def adve(self):
         if self.n_dims == 0:
             return
+        if self.adve_scheme == "pred_corr":
+            return self._adve_pred_corr()
         i, j, k = self.unravel(self.ijk)
         dims = [("x", i, self.Cx, self.dx, 0)]
         if self.n_dims == 3:

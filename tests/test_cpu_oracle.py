@@ -157,6 +157,40 @@ def test_port_matches_reference_full_step_3d(ref):
         assert np.array_equal(f["th"], fp["th"]) and np.array_equal(f["rv"], fp["rv"]), step
 
 
+@pytest.mark.parametrize("scheme", ["implicit", "euler", "pred_corr"])
+def test_port_advection_schemes_match_reference_3d(ref, scheme):
+    """all three advection schemes on a sheared, non-uniform Courant field (pred_corr reads the 2-column Courant halo, filled
+    the way init_e2l wraps it): positions bit-identical to the reference after every step"""
+    nx, ny, nz, sd_conc = 6, 5, 7, 6
+    eff = np.fromfile(os.path.join(ROOT, "libcloudphxx_b200", "data", "hall_davis_no_waals.f64"))
+    oi, o, f = S.box_3d(ref, nx=nx, ny=ny, nz=nz, sd_conc=sd_conc, adve=getattr(L.as_t, scheme))
+    rng = np.random.default_rng(7)
+    f["Cx"] = 0.3 + 0.4 * rng.random(f["Cx"].shape)
+    f["Cy"] = -0.2 + 0.4 * rng.random(f["Cy"].shape)
+    f["Cz"] = -0.1 + 0.2 * rng.random(f["Cz"].shape)
+    f["Cz"][:, :, 0] = 0.0
+    f["Cz"][:, :, -1] = 0.0
+    o.cond = o.coal = o.sedi = 0
+    p_r = ref.factory(L.backend_t.serial, oi)
+    p_r.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
+    p_p = port.Particles(nx=nx, ny=ny, nz=nz, dx=20., dy=20., dz=20., dt=1., x1=nx * 20., y1=ny * 20., z1=nz * 20., sd_conc=sd_conc,
+                         n_sd_max=int(nx * ny * nz * sd_conc * 1.5), kernel="efficiencies", kernel_params={"eff": eff[1:], "r_max": eff[0]},
+                         dry_distros=[(0.61, lognormal_as_capi(S.AEROSOL_ICICLE))], adve_scheme=scheme)
+    p_p.init(f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"])
+    moved = False
+    x0 = p_p.x.copy()
+    for step in range(8):
+        p_r.step_sync(o, f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"]); p_r.step_async(o)
+        p_p.step_sync(f["th"], f["rv"], f["rhod"], cond=False)
+        p_p.step_async(adve=True, sedi=False, coal=False, cond=False)
+        for k, a in (("x", p_p.x), ("y", p_p.y), ("z", p_p.z)):
+            b = p_r.get_attr(k)
+            assert a.size == b.size, (k, step, a.size, b.size)
+            assert np.array_equal(b, a), (k, step, S.rel_err(b, a))
+        moved |= p_p.x.size != x0.size or not np.array_equal(p_p.x, x0)
+    assert moved
+
+
 def test_port_recycling_matches_reference(ref):
     """opts.rcyc (rcyc.ipp:44-139): who is split, who is re-created, and the storage order afterwards"""
     nx, ny, nz, sd_conc = 4, 3, 6, 16
