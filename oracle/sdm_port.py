@@ -71,6 +71,32 @@ def RH_pv_cc(p, rv, T):                                 # hskpng_Tpr.ipp:71-78, 
     return (p * rv / (rv + eps)) / p_vs_cc(T)
 
 
+def r_vs_cc(T, p):                                      # common/const_cp.hpp:57-63
+    return eps / (p / p_vs_cc(T) - 1)
+
+
+def p_vs_tet(T):                                        # common/tetens.hpp:15-24
+    Tc = T - 273.15
+    return 6.1078e2 * math.exp((17.27 * Tc) / (Tc + 237.3))
+
+
+def r_vs_tet(T, p):                                     # common/tetens.hpp:26-35
+    Tc = T - 273.15
+    return 380. / (p * math.exp(-17.2693882 * Tc / (T - 35.86)) - 610.9)
+
+
+def RH_of(formula, p, rv, T):                           # hskpng_Tpr.ipp:71-103,141-161
+    if formula == "pv_cc":
+        return RH_pv_cc(p, rv, T)
+    if formula == "rv_cc":
+        return rv / r_vs_cc(T, p)
+    if formula == "pv_tet":
+        return (p * rv / (rv + eps)) / p_vs_tet(T)
+    if formula == "rv_tet":
+        return rv / r_vs_tet(T, p)
+    raise ValueError(formula)
+
+
 def visc(T):                                            # common/vterm.hpp:22-31
     q = T / T_tri
     return (1.72 * 1e-5) * (393.0 / (T + 120.0)) * (q * math.sqrt(q))
@@ -437,7 +463,7 @@ class Particles:
                  exact_sstp_cond=False, sstp_cond_mix=True, adaptive_sstp_cond=False, sstp_cond_act=1,
                  sstp_cond_adapt_drw2_eps=1e-4, sstp_cond_adapt_drw2_max=4., rc2_T=10.,
                  sd_const_multi=0, sd_conc_large_tail=False, dry_sizes=(), aerosol_independent_of_rhod=False, aerosol_conc_factor=(),
-                 rd_min=-1., rd_max=-1.):
+                 rd_min=-1., rd_max=-1., RH_formula="pv_cc"):
         self.nx, self.ny, self.nz = nx, ny, nz
         self.dx, self.dy, self.dz, self.dt = dx, dy, dz, dt
         self.x0, self.y0, self.z0, self.x1, self.y1, self.z1 = x0, y0, z0, x1, y1, z1
@@ -453,6 +479,7 @@ class Particles:
         self.vt_kind, self.adve_scheme = vt, adve_scheme
         self.dry_distros = list(dry_distros)          # [(kappa, callable n(ln r))], iterated in ascending kappa like std::map
         self.RH_max_init = RH_max_init
+        self.RH_formula = RH_formula
         self.rng_seed = rng_seed
         self.rng = HostRNG(rng_seed)
         self.puddle = dict(liquid_volume=0., dry_volume=0., liquid_number=0., particle_number=0.)
@@ -472,12 +499,12 @@ class Particles:
         ext = lambda idx, d, a, b: np.minimum((idx + 1) * d, b) - np.maximum(idx * d, a)
         return np.maximum(0., ext(i, self.dx, self.x0, self.x1) * ext(j, self.dy, self.y0, self.y1) * ext(k, self.dz, self.z0, self.z1))
 
-    def hskpng_Tpr(self):                               # hskpng_Tpr.ipp:219-305 (th_dry, variable pressure, pv_cc)
+    def hskpng_Tpr(self):                               # hskpng_Tpr.ipp:219-305 (th_dry, variable pressure, four RH formulae)
         for c in range(self.n_cell):
             T = T_of_th_dry(self.th[c], self.rhod[c])
             p = self.rhod[c] * (R_d + self.rv[c] * R_v) * T
             self.T[c], self.p[c] = T, p
-            self.RH[c] = RH_pv_cc(p, self.rv[c], T)
+            self.RH[c] = RH_of(self.RH_formula, p, self.rv[c], T)
             self.eta[c] = visc(T)
         if self.n_dims == 0:
             self.dv = 1.0 / self.rhod

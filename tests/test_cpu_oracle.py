@@ -191,6 +191,31 @@ def test_port_advection_schemes_match_reference_3d(ref, scheme):
     assert moved
 
 
+@pytest.mark.parametrize("rhf", ["pv_cc", "rv_cc", "pv_tet", "rv_tet"])
+@pytest.mark.parametrize("sstp_cond", [1, 3])
+def test_port_parcel_condensation_matches_reference(ref, rhf, sstp_cond):
+    """0-D parcel, condensation only, each of the four RH formulae (hskpng_Tpr.ipp:71-103), with and without per-cell
+    sub-stepping: wet radii, th and rv bit-identical to the reference after every step"""
+    oi, o, f = S.parcel(ref, n_sd=96, dt=1.0, sstp_cond=sstp_cond, RH_formula=getattr(L.RH_formula_t, rhf))
+    p_r = ref.factory(L.backend_t.serial, oi)
+    p_r.init(f["th"], f["rv"], f["rhod"])
+    fp = {k: v.copy() for k, v in f.items()}
+    p_p = port.Particles(dt=1., sd_conc=96, n_sd_max=96, sstp_cond=sstp_cond, dry_distros=[(0.61, lognormal_as_capi([(0.04e-6, 2.0, 566e6)]))],
+                         sedi_switch=False, coal_switch=False, RH_formula=rhf, vt="undefined")
+    p_p.init(fp["th"], fp["rv"], fp["rhod"])
+    assert np.array_equal(p_r.get_attr("rw2"), p_p.rw2)
+    for step in range(12):
+        f["rhod"] *= 0.999
+        fp["rhod"] *= 0.999
+        p_r.step_sync(o, f["th"], f["rv"], f["rhod"]); p_r.step_async(o)
+        th, rv = p_p.step_sync(fp["th"], fp["rv"], fp["rhod"])
+        fp["th"][:], fp["rv"][:] = th, rv
+        p_p.step_async(adve=False, sedi=False, coal=False, cond=True)
+        assert np.array_equal(p_r.get_attr("rw2"), p_p.rw2), (step, S.rel_err(p_r.get_attr("rw2"), p_p.rw2))
+        assert np.array_equal(f["th"], fp["th"]) and np.array_equal(f["rv"], fp["rv"]), step
+    assert p_p.rw2.max() > 1e-12, "nothing grew"
+
+
 def test_port_recycling_matches_reference(ref):
     """opts.rcyc (rcyc.ipp:44-139): who is split, who is re-created, and the storage order afterwards"""
     nx, ny, nz, sd_conc = 4, 3, 6, 16
