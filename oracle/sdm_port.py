@@ -402,6 +402,64 @@ def vt_beard77_fact(r, p, rhoa, eta):
     return 1.104 * eps_s + ((1.058 * eps_c - 1.104 * eps_s) * (5.52 + math.log(2 * 100 * r)) / 5.01) + 1
 
 
+def vt_beard76(r, T, p, rhoa, eta):                     # common/vterm.hpp:168-221
+    if r <= 9.5e-6:
+        l = 6.62e-8 * (eta / 1.818e-5) * (p_stp / p) * math.sqrt(T / 293.15)
+        C_ac = 1. + 1.255 * l / r
+        return (rho_w - rhoa) * g_acc / (4.5 * eta) * C_ac * r * r
+    if r <= 5.035e-4:
+        b = (-0.318657e1, 0.992696, -0.153193e-2, -0.987059e-3, -0.578878e-3, 0.855176e-4, -0.327815e-5)
+        l = 6.62e-8 * (eta / 1.818e-5) * (p_stp / p) * math.sqrt(T / 293.15)
+        C_ac = 1. + 1.255 * l / r
+        log_N_Da = math.log((32. / 3.) * r * r * r * rhoa * (rho_w - rhoa) * g_acc / eta / eta)
+        Y = 0.
+        for i in range(7):
+            Y = Y + b[i] * math.pow(log_N_Da, float(i))
+        N_Re = C_ac * math.exp(Y)
+        return eta * N_Re / rhoa / 2. / r
+    b = (-0.500015e1, 0.523778e1, -0.204914e1, 0.475294, -0.542819e-1, 0.238449e-2)
+    sg = 0.07275 * (1. - 0.002 * (T - 291.))            # common/kelvin_term.hpp:23-32
+    Bo = (16. / 3.) * r * r * (rho_w - rhoa) * g_acc / sg
+    N_p = sg * sg * sg * rhoa * rhoa / eta / eta / eta / eta / g_acc / (rho_w - rhoa)
+    X = math.log(Bo * math.pow(N_p, 1. / 6.))
+    Y = 0.
+    for i in range(6):
+        Y = Y + b[i] * math.pow(X, float(i))
+    N_Re = math.pow(N_p, 1. / 6.) * math.exp(Y)
+    return eta * N_Re / rhoa / 2. / r
+
+
+def vt_khvorostyanov(r, rhoa, eta, spherical):          # common/vterm.hpp:38-105
+    X = (32. / 3) * (rho_w - rhoa) / rhoa * g_acc * r * r * r / eta / eta * rhoa * rhoa
+    b = (.0902 / 2) * math.sqrt(X) / ((math.sqrt(1. + .0902 * math.sqrt(X)) - 1.) * (math.sqrt(1. + .0902 * math.sqrt(X))))
+    pow_hlpr = math.sqrt(1. + .0902 * math.sqrt(X)) - 1.
+    a = (9.06 * 9.06 / 4) * pow_hlpr * pow_hlpr / math.pow(X, b)
+    if spherical:
+        Av = a * math.pow(eta / rhoa * 1e4, 1. - 2. * b) * math.pow((4. / 3) * rho_w / rhoa * g_acc * 1e2, b)
+    else:
+        lambda_half = 2.35e-3
+        ksi = math.exp(-r / lambda_half) + (1. - math.exp(-r / lambda_half)) / (1. + r / lambda_half)
+        alfa = PI / 6. * rho_w * ksi
+        Av = a * math.pow(eta / rhoa * 1e4, 1. - 2. * b) * math.pow(2.546479 * alfa / rhoa * g_acc * 1e2, b)
+    Bv = 3. * b - 1.
+    return (Av * math.pow((2 * 1e2) * r, Bv)) / 1e2
+
+
+def vt_any(kind, rw2, T, p, rhod, eta, table):          # hskpng_vterm.ipp:38-121
+    if kind == "beard77fast":
+        return vt_beard77fast(rw2, p, rhod, eta, table)
+    r = math.sqrt(rw2)
+    if kind == "beard76":
+        return vt_beard76(r, T, p, rhod, eta)
+    if kind == "beard77":
+        return vt_beard77_fact(r, p, rhod, eta) * vt_beard77_v0(r)
+    if kind == "khvorostyanov_spherical":
+        return vt_khvorostyanov(r, rhod, eta, True)
+    if kind == "khvorostyanov_nonspherical":
+        return vt_khvorostyanov(r, rhod, eta, False)
+    return 0.0                                           # vt_t::undefined
+
+
 def vt_beard77fast(rw2, p, rhod, eta, table):
     dlnr = (VT0_LN_R_MAX - VT0_LN_R_MIN) / VT0_N_BIN
     lnr = .5 * math.log(rw2)
@@ -517,7 +575,7 @@ class Particles:
         for s in range(self.n_part):
             if self.rw2[s] > 0 and (not only_invalid or self.vt[s] == -1.0):
                 c = self.ijk[s]
-                self.vt[s] = vt_beard77fast(self.rw2[s], self.p[c], self.rhod[c], self.eta[c], self.table) if self.vt_kind == "beard77fast" else 0.0
+                self.vt[s] = vt_any(self.vt_kind, self.rw2[s], self.T[c], self.p[c], self.rhod[c], self.eta[c], self.table)
 
     # -- init: src/particles_init.ipp:16-131 and src/impl/initialization/* ----------------------------------------------------
     def init(self, th, rv, rhod, Cx=None, Cy=None, Cz=None):

@@ -216,6 +216,35 @@ def test_port_parcel_condensation_matches_reference(ref, rhf, sstp_cond):
     assert p_p.rw2.max() > 1e-12, "nothing grew"
 
 
+@pytest.mark.parametrize("vt", ["beard76", "beard77", "beard77fast", "khvorostyanov_spherical", "khvorostyanov_nonspherical"])
+def test_port_fall_speed_formulae_match_reference(ref, vt):
+    """sedimentation with each terminal-velocity formula (common/vterm.hpp:38-221), droplets from haze to millimetre drops so
+    that every branch of the piecewise fits is taken: z - dt * vt bit-identical to the reference, step after step"""
+    nx, ny, nz, sd_conc = 3, 2, 8, 12
+    eff = np.fromfile(os.path.join(ROOT, "libcloudphxx_b200", "data", "hall_davis_no_waals.f64"))
+    oi, o, f = S.box_3d(ref, nx=nx, ny=ny, nz=nz, sd_conc=sd_conc, vt=getattr(L.vt_t, vt), cx=0.0, cy=0.0)
+    big = [(30e-6, 1.3, 1e5), (200e-6, 1.25, 1e2)]
+    oi.dry_distros = [L.lognormal(0.61, S.AEROSOL_ICICLE), L.lognormal(1.28, big)]
+    o.cond = o.coal = 0
+    p_r = ref.factory(L.backend_t.serial, oi)
+    p_r.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
+    p_p = port.Particles(nx=nx, ny=ny, nz=nz, dx=20., dy=20., dz=20., dt=1., x1=nx * 20., y1=ny * 20., z1=nz * 20., sd_conc=sd_conc,
+                         n_sd_max=int(nx * ny * nz * sd_conc * 1.5), kernel="efficiencies", kernel_params={"eff": eff[1:], "r_max": eff[0]},
+                         dry_distros=[(0.61, lognormal_as_capi(S.AEROSOL_ICICLE)), (1.28, lognormal_as_capi(big))], vt=vt)
+    p_p.init(f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"])
+    r = np.sqrt(p_p.rw2)
+    assert r.min() < 9.5e-6 and ((r > 20e-6) & (r < 5.035e-4)).any() and r.max() > 5.035e-4, (r.min(), r.max())
+    z0 = p_p.z.copy()
+    for step in range(4):
+        p_r.step_sync(o, f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"]); p_r.step_async(o)
+        p_p.step_sync(f["th"], f["rv"], f["rhod"], cond=False)
+        p_p.step_async(adve=True, sedi=True, coal=False, cond=False)
+        a, b = p_r.get_attr("z"), p_p.z
+        assert a.size == b.size, (step, a.size, b.size)
+        assert np.array_equal(a, b), (step, S.rel_err(a, b))
+    assert p_p.z.size < z0.size, "no drop reached the ground"
+
+
 def test_port_recycling_matches_reference(ref):
     """opts.rcyc (rcyc.ipp:44-139): who is split, who is re-created, and the storage order afterwards"""
     nx, ny, nz, sd_conc = 4, 3, 6, 16
