@@ -506,6 +506,16 @@ def coal_kernel(kind, params, n_a, n_b, rw2_a, rw2_b, vt_a, vt_b):
         return geo * params["mult"] if "mult" in params else geo
     if kind == "efficiencies":
         return interpolated_efficiency(params["eff"], params["r_max"], math.sqrt(rw2_a), math.sqrt(rw2_b)) * geo
+    if kind == "long":                                   # kernels.hpp:144-176
+        res = geo
+        r_L = max(math.sqrt(rw2_a), math.sqrt(rw2_b))
+        if r_L < 50.e-6:
+            r_s = min(math.sqrt(rw2_a), math.sqrt(rw2_b))
+            if r_s <= 3e-6:
+                res = 0.
+            else:
+                res *= 4.5e8 * r_L * r_L * (1. - 3e-6 / r_s)
+        return res
     raise ValueError(kind)
 
 
