@@ -751,6 +751,62 @@ class Particles:
             out = out / self.dv / self.rhod
         return out
 
+    # -- diagnostics: src/particles_diag.ipp:148-656 on top of the selectors / moments of particles_impl_moms.ipp:50-387 ---------
+    # every diag_* below returns what outbuf() would hold afterwards: a dense per-cell array, zero where no selected SD lives
+    def diag_all(self):
+        self.n_filtered = self.n.astype(np.float64)
+
+    def _moms_rng(self, lo, hi, vec, cons):              # moms_rng, range_filter: x >= min && x < max ? y : 0
+        base = self.n_filtered if cons else self.n.astype(np.float64)
+        self.n_filtered = np.where((vec >= lo) & (vec < hi), base, 0.)
+
+    def diag_wet_rng(self, r_min, r_max, cons=False):
+        self._moms_rng(math.pow(r_min, 2), math.pow(r_max, 2), self.rw2, cons)
+
+    def diag_dry_rng(self, r_min, r_max, cons=False):
+        self._moms_rng(math.pow(r_min, 3), math.pow(r_max, 3), self.rd3, cons)
+
+    def diag_kappa_rng(self, k_min, k_max, cons=False):
+        self._moms_rng(k_min, k_max, self.kpa, cons)
+
+    def diag_rw_ge_rc(self):                            # particles_diag.ipp:384-408, moms_cmp
+        rc2 = np.array([math.pow(rw3_cr(self.rd3[s], self.kpa[s], self.T[self.ijk[s]]), 2. / 3) for s in range(self.n_part)])
+        self.n_filtered = np.where(self.rw2 >= rc2, self.n.astype(np.float64), 0.)
+
+    def diag_RH_ge_Sc(self):                            # particles_diag.ipp:353-381, kappa_koehler.hpp:172-190
+        def S_cr(rd3, kpa, T):
+            rw3 = rw3_cr(rd3, kpa, T)
+            return a_w(rw3, rd3, kpa) * math.exp(kelvin_A(T) / math.cbrt(rw3))
+        d = np.array([self.RH[self.ijk[s]] - S_cr(self.rd3[s], self.kpa[s], self.T[self.ijk[s]]) for s in range(self.n_part)])
+        self.n_filtered = np.where(d >= 0., self.n.astype(np.float64), 0.)
+
+    def diag_wet_mom(self, k):
+        return self.moment(self.rw2, k / 2., self.n_filtered)
+
+    def diag_dry_mom(self, k):
+        return self.moment(self.rd3, k / 3., self.n_filtered)
+
+    def diag_kappa_mom(self, k):
+        return self.moment(self.kpa, float(k), self.n_filtered)
+
+    def diag_sd_conc(self):                             # particles_diag.ipp:199-220: number of selected SDs, not divided by anything
+        out = np.zeros(self.n_cell)
+        for pos in range(self.n_part):
+            s = self.sorted_id[pos]
+            out[self.ijk[s]] += 1. if self.n_filtered[s] > 0. else 0.
+        return out
+
+    def diag_precip_rate(self):                         # particles_diag.ipp:561-587: sum of n rw^3 vt, fall speeds refreshed first
+        self.hskpng_vterm(False)
+        flux = np.array([math.pow(self.rw2[s], 3. / 2) * self.vt[s] for s in range(self.n_part)])
+        return self.moment(flux, 1., self.n_filtered, specific=False)
+
+    def diag_max_rw(self):                              # particles_diag.ipp:609-642
+        out = np.zeros(self.n_cell)
+        for s in range(self.n_part):
+            out[self.ijk[s]] = max(out[self.ijk[s]], math.sqrt(self.rw2[s]))
+        return out
+
     # -- condensation: src/particles_step.ipp:161-336, percell/particles_impl_cond.ipp:13-139, update_th_rv.ipp:74-191 ----------
     def step_sync(self, th, rv, rhod=None, RH_max=44., cond=True):
         C = self.n_cell

@@ -278,6 +278,53 @@ def test_port_collision_kernels_match_reference_3d(ref, kernel):
     assert collided > 0, "no collision happened - vacuous"
 
 
+def test_port_diagnostics_match_reference(ref):
+    """selectors, moments, SD concentration, precipitation flux, largest radius (particles_diag.ipp:148-656, moms.ipp:50-387)
+    after a few full steps: the restatement sums in the reference's order, so the per-cell arrays are bit-identical"""
+    nx, ny, nz, sd_conc = 3, 2, 5, 12
+    eff = np.fromfile(os.path.join(ROOT, "libcloudphxx_b200", "data", "hall_davis_no_waals.f64"))
+    oi, o, f = S.box_3d(ref, nx=nx, ny=ny, nz=nz, sd_conc=sd_conc, rain_mode=True)
+    f["rv"][:, :, nz // 2:] = 1.25e-2                    # supersaturated at the temperature of this shallow column: droplets activate
+    p_r = ref.factory(L.backend_t.serial, oi)
+    p_r.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
+    fp = {k: v.copy() for k, v in f.items()}
+    p_p = port_box3d(fp, nx, ny, nz, sd_conc, eff)
+    p_p.init(fp["th"], fp["rv"], fp["rhod"], fp["Cx"], fp["Cy"], fp["Cz"])
+    for step in range(3):
+        p_r.step_sync(o, f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"]); p_r.step_async(o)
+        th, rv = p_p.step_sync(fp["th"], fp["rv"], fp["rhod"])
+        fp["th"][:], fp["rv"][:] = th.reshape(fp["th"].shape), rv.reshape(fp["rv"].shape)
+        p_p.step_async()
+        assert np.array_equal(p_r.get_attr("rw2"), p_p.rw2), step
+
+    def same(name, a):
+        b = p_r.outbuf()
+        assert np.array_equal(a.reshape(-1), b), (name, S.rel_err(b, a.reshape(-1)))
+        return b
+    seen = 0.
+    p_r.diag_all(); p_p.diag_all()
+    for k in range(4):
+        p_r.diag_wet_mom(k); seen += same("wet_mom %d" % k, p_p.diag_wet_mom(k)).sum()
+        p_r.diag_dry_mom(k); same("dry_mom %d" % k, p_p.diag_dry_mom(k))
+    p_r.diag_kappa_mom(1); same("kappa_mom", p_p.diag_kappa_mom(1))
+    p_r.diag_sd_conc(); assert same("sd_conc", p_p.diag_sd_conc()).sum() == p_p.n_part
+    p_r.diag_precip_rate(); assert same("precip_rate", p_p.diag_precip_rate()).sum() > 0
+    p_r.diag_max_rw(); same("max_rw", p_p.diag_max_rw())
+    p_r.diag_wet_rng(1e-6, 25e-6); p_p.diag_wet_rng(1e-6, 25e-6)
+    p_r.diag_wet_mom(3); same("cloud water", p_p.diag_wet_mom(3))
+    p_r.diag_sd_conc(); part = same("sd_conc of a range", p_p.diag_sd_conc()).sum()
+    assert 0 < part < p_p.n_part
+    p_r.diag_dry_rng_cons(0.05e-6, 1.); p_p.diag_dry_rng(0.05e-6, 1., cons=True)
+    p_r.diag_wet_mom(0); assert 0 < same("consecutive selection", p_p.diag_wet_mom(0)).sum()
+    p_r.diag_kappa_rng(1.0, 2.0); p_p.diag_kappa_rng(1.0, 2.0)
+    p_r.diag_dry_mom(3); assert same("second aerosol type", p_p.diag_dry_mom(3)).sum() > 0
+    p_r.diag_rw_ge_rc(); p_p.diag_rw_ge_rc()
+    p_r.diag_wet_mom(0); act = same("activated", p_p.diag_wet_mom(0)).sum()
+    p_r.diag_RH_ge_Sc(); p_p.diag_RH_ge_Sc()
+    p_r.diag_wet_mom(0); same("RH above critical", p_p.diag_wet_mom(0))
+    assert act > 0 and seen > 0
+
+
 def test_port_recycling_matches_reference(ref):
     """opts.rcyc (rcyc.ipp:44-139): who is split, who is re-created, and the storage order afterwards"""
     nx, ny, nz, sd_conc = 4, 3, 6, 16
