@@ -7,14 +7,14 @@ the evaluations of drw2/dt are counted per droplet in the last condensation step
   storage    - cells contiguous, inside a cell the order the re-layout leaves (stayers in old order, then arrivals)
   size class - the same windows of `run` cells, droplets ordered by a coarse size class first (what a warp could do itself)
   ideal      - ordered by the evaluation count itself (lower bound)
-Test infrastructure: uses oracle/, never shipped."""
+Test infrastructure (lives under tests/ because it uses oracle/); never shipped, not collected by pytest."""
 import math
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))      # tests/ is one of the places allowed to use oracle/
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
