@@ -522,7 +522,7 @@ def coal_kernel(kind, params, n_a, n_b, rw2_a, rw2_b, vt_a, vt_b):
 # ---- the particle system ----------------------------------------------------------------------------------------------------
 class Particles:
     """0-D / 2-D / 3-D box, sd_conc initialisation, per-cell and per-particle (mixing / no mixing / adaptive, activation
-    sub-stepping with rc2) condensation sub-stepping, SDM coalescence, implicit / Euler / predictor-corrector advection, sedimentation, periodic side
+    sub-stepping with rc2) condensation sub-stepping, SDM coalescence, implicit / Euler / predictor-corrector advection, sedimentation, subsidence, periodic or open side
     walls, open top / bottom, removal or recycling of used-up SDs.  Call order as the reference (src/particles_step.ipp)."""
 
     def __init__(self, nx=0, ny=0, nz=0, dx=1., dy=1., dz=1., dt=1., x0=0., y0=0., z0=0., x1=1., y1=1., z1=1., sd_conc=0, n_sd_max=0,
@@ -531,7 +531,7 @@ class Particles:
                  exact_sstp_cond=False, sstp_cond_mix=True, adaptive_sstp_cond=False, sstp_cond_act=1,
                  sstp_cond_adapt_drw2_eps=1e-4, sstp_cond_adapt_drw2_max=4., rc2_T=10.,
                  sd_const_multi=0, sd_conc_large_tail=False, dry_sizes=(), aerosol_independent_of_rhod=False, aerosol_conc_factor=(),
-                 rd_min=-1., rd_max=-1., RH_formula="pv_cc"):
+                 rd_min=-1., rd_max=-1., RH_formula="pv_cc", open_side_walls=False, w_LS=None):
         self.nx, self.ny, self.nz = nx, ny, nz
         self.dx, self.dy, self.dz, self.dt = dx, dy, dz, dt
         self.x0, self.y0, self.z0, self.x1, self.y1, self.z1 = x0, y0, z0, x1, y1, z1
@@ -548,6 +548,8 @@ class Particles:
         self.dry_distros = list(dry_distros)          # [(kappa, callable n(ln r))], iterated in ascending kappa like std::map
         self.RH_max_init = RH_max_init
         self.RH_formula = RH_formula
+        self.open_side_walls = open_side_walls
+        self.w_LS = None if w_LS is None else np.array(w_LS, dtype=np.float64)     # large-scale subsidence velocity per level (opts_init.w_LS)
         self.rng_seed = rng_seed
         self.rng = HostRNG(rng_seed)
         self.puddle = dict(liquid_volume=0., dry_volume=0., liquid_number=0., particle_number=0.)
@@ -1076,6 +1078,7 @@ class Particles:
             y_old = np.where(self.y < self.y0, y_old - L_y, y_old)
             self.y = self.y0 + np.fmod((self.y - self.y0) + 10 * L_y, L_y)
         cell.ijk = cell()
+        self._k_midpoint = cell.ijk[2]                   # the level index hskpng_ijk leaves behind (read by subs)
         x_old = self.x + x_old
         if three:
             y_old = self.y + y_old
@@ -1119,9 +1122,15 @@ class Particles:
         if self.n_dims == 0:
             return
         wrap = lambda x, a, b: a + np.fmod((x - a) + 10 * (b - a), b - a)
-        self.x = wrap(self.x, self.x0, self.x1)
+        if not self.open_side_walls:
+            self.x = wrap(self.x, self.x0, self.x1)
+        else:                                            # bcnd.ipp:132-142: SDs that left through a side wall are flagged for removal
+            self.n[(self.x >= self.x1) | (self.x < self.x0)] = 0
         if self.n_dims == 3:
-            self.y = wrap(self.y, self.y0, self.y1)
+            if not self.open_side_walls:
+                self.y = wrap(self.y, self.y0, self.y1)
+            else:
+                self.n[(self.y >= self.y1) | (self.y < self.y0)] = 0
         if self.n_dims > 1:
             self.n[self.z >= self.z1] = 0
             out = self.z < self.z0
@@ -1161,7 +1170,7 @@ class Particles:
         self.n_recycled = n_flagged
         return n_flagged == n_to_rcyc                    # all recycled: nothing left to remove
 
-    def step_async(self, adve=True, sedi=True, coal=True, cond=True, rcyc=False):
+    def step_async(self, adve=True, sedi=True, coal=True, cond=True, rcyc=False, subs=False):
         self.hskpng_Tpr()
         if sedi or coal or cond:
             self.hskpng_vterm(False)
@@ -1176,6 +1185,9 @@ class Particles:
             self.adve()
         if sedi and self.nz:
             self.z = self.z - self.dt * self.vt
+        if subs and self.nz:                             # subsidence/particles_impl_subs.ipp:13-25: w_LS at the level index k the SD had
+            k = self._k_midpoint if (adve and self.adve_scheme == "pred_corr") else self.unravel(self.ijk)[2]     # when ijk was last computed
+            self.z = self.z - self.dt * self.w_LS[k]
         self.bcnd()
         self.n_recycled = 0
         if rcyc:                                         # post_copy.ipp:24-29

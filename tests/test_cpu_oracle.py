@@ -325,6 +325,35 @@ def test_port_diagnostics_match_reference(ref):
     assert act > 0 and seen > 0
 
 
+@pytest.mark.parametrize("scheme", ["implicit", "pred_corr"])
+def test_port_subsidence_and_open_side_walls_match_reference(ref, scheme):
+    """large-scale subsidence (subs.ipp:13-25: w_LS at the level the SD was last indexed in) and open side walls (bcnd.ipp:126-142,
+    202-216: SDs leaving through x or y are removed): surviving SDs and their positions bit-identical to the reference"""
+    nx, ny, nz, sd_conc = 4, 3, 6, 8
+    eff = np.fromfile(os.path.join(ROOT, "libcloudphxx_b200", "data", "hall_davis_no_waals.f64"))
+    oi, o, f = S.box_3d(ref, nx=nx, ny=ny, nz=nz, sd_conc=sd_conc, adve=getattr(L.as_t, scheme), cx=0.4, cy=-0.3)
+    w_LS = 0.5 + 0.3 * np.arange(nz)
+    oi.subs_switch, oi.w_LS, oi.open_side_walls = 1, list(w_LS), 1
+    o.cond = o.coal = 0
+    o.subs = 1
+    p_r = ref.factory(L.backend_t.serial, oi)
+    p_r.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
+    p_p = port.Particles(nx=nx, ny=ny, nz=nz, dx=20., dy=20., dz=20., dt=1., x1=nx * 20., y1=ny * 20., z1=nz * 20., sd_conc=sd_conc,
+                         n_sd_max=int(nx * ny * nz * sd_conc * 1.5), kernel="efficiencies", kernel_params={"eff": eff[1:], "r_max": eff[0]},
+                         dry_distros=[(0.61, lognormal_as_capi(S.AEROSOL_ICICLE))], adve_scheme=scheme, open_side_walls=True, w_LS=w_LS)
+    p_p.init(f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"])
+    n0 = p_p.n_part
+    for step in range(6):
+        p_r.step_sync(o, f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"]); p_r.step_async(o)
+        p_p.step_sync(f["th"], f["rv"], f["rhod"], cond=False)
+        p_p.step_async(adve=True, sedi=True, coal=False, cond=False, subs=True)
+        for k, a in (("x", p_p.x), ("y", p_p.y), ("z", p_p.z)):
+            b = p_r.get_attr(k)
+            assert a.size == b.size, (k, step, a.size, b.size)
+            assert np.array_equal(b, a), (k, step, S.rel_err(b, a))
+    assert 0 < p_p.n_part < n0, "nothing left the domain"
+
+
 def test_port_recycling_matches_reference(ref):
     """opts.rcyc (rcyc.ipp:44-139): who is split, who is re-created, and the storage order afterwards"""
     nx, ny, nz, sd_conc = 4, 3, 6, 16
