@@ -531,7 +531,7 @@ class Particles:
                  exact_sstp_cond=False, sstp_cond_mix=True, adaptive_sstp_cond=False, sstp_cond_act=1,
                  sstp_cond_adapt_drw2_eps=1e-4, sstp_cond_adapt_drw2_max=4., rc2_T=10.,
                  sd_const_multi=0, sd_conc_large_tail=False, dry_sizes=(), aerosol_independent_of_rhod=False, aerosol_conc_factor=(),
-                 rd_min=-1., rd_max=-1., RH_formula="pv_cc", open_side_walls=False, w_LS=None):
+                 rd_min=-1., rd_max=-1., RH_formula="pv_cc", open_side_walls=False, w_LS=None, th_dry=True, const_p=False):
         self.nx, self.ny, self.nz = nx, ny, nz
         self.dx, self.dy, self.dz, self.dt = dx, dy, dz, dt
         self.x0, self.y0, self.z0, self.x1, self.y1, self.z1 = x0, y0, z0, x1, y1, z1
@@ -549,6 +549,9 @@ class Particles:
         self.RH_max_init = RH_max_init
         self.RH_formula = RH_formula
         self.open_side_walls = open_side_walls
+        self.th_dry, self.const_p = th_dry, const_p     # opts_init.th_dry / const_p: what "th" means and whether p is prescribed
+        if const_p and exact_sstp_cond:
+            raise NotImplementedError("the restatement covers const_p with per-cell sub-stepping only")
         self.w_LS = None if w_LS is None else np.array(w_LS, dtype=np.float64)     # large-scale subsidence velocity per level (opts_init.w_LS)
         self.rng_seed = rng_seed
         self.rng = HostRNG(rng_seed)
@@ -571,8 +574,11 @@ class Particles:
 
     def hskpng_Tpr(self):                               # hskpng_Tpr.ipp:219-305 (th_dry, variable pressure, four RH formulae)
         for c in range(self.n_cell):
-            T = T_of_th_dry(self.th[c], self.rhod[c])
-            p = self.rhod[c] * (R_d + self.rv[c] * R_v) * T
+            if self.th_dry:
+                T = T_of_th_dry(self.th[c], self.rhod[c])
+            else:                                        # "standard" potential temperature: T = th * exner(p), common/theta_std.hpp:36-41
+                T = self.th[c] * math.pow(self.p[c] / p_1000, R_d / c_pd)
+            p = self.p[c] if self.const_p else self.rhod[c] * (R_d + self.rv[c] * R_v) * T
             self.T[c], self.p[c] = T, p
             self.RH[c] = RH_of(self.RH_formula, p, self.rv[c], T)
             self.eta[c] = visc(T)
@@ -590,11 +596,13 @@ class Particles:
                 self.vt[s] = vt_any(self.vt_kind, self.rw2[s], self.T[c], self.p[c], self.rhod[c], self.eta[c], self.table)
 
     # -- init: src/particles_init.ipp:16-131 and src/impl/initialization/* ----------------------------------------------------
-    def init(self, th, rv, rhod, Cx=None, Cy=None, Cz=None):
+    def init(self, th, rv, rhod, Cx=None, Cy=None, Cz=None, p=None):
         C = self.n_cell
         self.th, self.rv, self.rhod = (np.array(a, dtype=np.float64).reshape(C).copy() for a in (th, rv, rhod))
         self.Cx, self.Cy, self.Cz = Cx, Cy, Cz
         self.T, self.p, self.RH, self.eta = (np.zeros(C) for _ in range(4))
+        if self.const_p:                                 # particles_init.ipp:39-40: the pressure profile comes from the caller and stays
+            self.p = np.array(p, dtype=np.float64).reshape(C).copy()
         self.dv = self.cell_volumes() if self.n_dims else np.zeros(C)
         self.hskpng_Tpr()
         parts = {k: [] for k in ("n", "rd3", "rw2", "kpa", "x", "y", "z", "ijk")}

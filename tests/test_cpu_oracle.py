@@ -354,6 +354,35 @@ def test_port_subsidence_and_open_side_walls_match_reference(ref, scheme):
     assert 0 < p_p.n_part < n0, "nothing left the domain"
 
 
+@pytest.mark.parametrize("sstp_cond", [1, 4])
+def test_port_const_p_standard_theta_matches_reference(ref, sstp_cond):
+    """opts_init.const_p with the 'standard' potential temperature (hskpng_Tpr.ipp:231-260, theta_std.hpp:36-41): prescribed pressure,
+    T = th * exner(p); parcel condensation bit-identical to the reference"""
+    oi, o, f = S.parcel(ref, n_sd=80, dt=1.0, sstp_cond=sstp_cond)
+    R_d, R_v, c_pd = 8.3144621 / 0.02897, 8.3144621 / 0.018, 1005.0
+    T0 = (f["th"][0] * (f["rhod"][0] * R_d / 1e5) ** (R_d / c_pd)) ** (c_pd / (c_pd - R_d))
+    p_prof = np.array([f["rhod"][0] * (R_d + f["rv"][0] * R_v) * T0])
+    f["th"][0] = S.th_dry2std(f["th"][0], f["rv"][0])
+    oi.const_p, oi.th_dry = 1, 0
+    p_r = ref.factory(L.backend_t.serial, oi)
+    p_r.init(f["th"], f["rv"], f["rhod"], p_prof)
+    fp = {k: v.copy() for k, v in f.items()}
+    p_p = port.Particles(dt=1., sd_conc=80, n_sd_max=80, sstp_cond=sstp_cond, dry_distros=[(0.61, lognormal_as_capi([(0.04e-6, 2.0, 566e6)]))],
+                         sedi_switch=False, coal_switch=False, vt="undefined", th_dry=False, const_p=True)
+    p_p.init(fp["th"], fp["rv"], fp["rhod"], p=p_prof)
+    assert np.array_equal(p_r.get_attr("rw2"), p_p.rw2)
+    for step in range(10):
+        f["th"] -= 0.02                                   # cooling at constant pressure drives the condensation
+        fp["th"] -= 0.02
+        p_r.step_sync(o, f["th"], f["rv"], f["rhod"]); p_r.step_async(o)
+        th, rv = p_p.step_sync(fp["th"], fp["rv"], fp["rhod"])
+        fp["th"][:], fp["rv"][:] = th, rv
+        p_p.step_async(adve=False, sedi=False, coal=False, cond=True)
+        assert np.array_equal(p_r.get_attr("rw2"), p_p.rw2), (step, S.rel_err(p_r.get_attr("rw2"), p_p.rw2))
+        assert np.array_equal(f["th"], fp["th"]) and np.array_equal(f["rv"], fp["rv"]), step
+    assert p_p.rw2.max() > 1e-12, "nothing grew"
+
+
 def test_port_recycling_matches_reference(ref):
     """opts.rcyc (rcyc.ipp:44-139): who is split, who is re-created, and the storage order afterwards"""
     nx, ny, nz, sd_conc = 4, 3, 6, 16
