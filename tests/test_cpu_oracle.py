@@ -383,6 +383,33 @@ def test_port_const_p_standard_theta_matches_reference(ref, sstp_cond):
     assert p_p.rw2.max() > 1e-12, "nothing grew"
 
 
+def test_port_kinematic_2d_matches_reference(ref):
+    """cfg3-shaped case (BASELINE configs[2]): 2-D single-eddy flow with partial boundary cells (x0 = dx/2 ...), geometric kernel
+    with the icicle multiplier 0.5, Khvorostyanov fall speeds, cond + coal sub-stepping: bit-identical to the reference"""
+    nx, nz, sd_conc = 7, 6, 10
+    oi, o, f = S.kinematic_2d(ref, nx=nx, nz=nz, sd_conc=sd_conc, w_max=6.0)
+    f["rv"][:, nz // 2:] = 1.2e-2                        # supersaturated aloft so that droplets activate and collide
+    p_r = ref.factory(L.backend_t.serial, oi)
+    p_r.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], None, f["Cz"])
+    fp = {k: v.copy() for k, v in f.items()}
+    p_p = port.Particles(nx=nx, nz=nz, dx=oi.dx, dz=oi.dz, dt=1., x0=oi.x0, z0=oi.z0, x1=oi.x1, z1=oi.z1, sd_conc=sd_conc,
+                         n_sd_max=nx * nz * sd_conc, sstp_cond=2, sstp_coal=2, kernel="geometric", kernel_params={"mult": 0.5},
+                         vt="khvorostyanov_spherical", dry_distros=[(0.61, lognormal_as_capi(S.AEROSOL_ICICLE))])
+    p_p.init(fp["th"], fp["rv"], fp["rhod"], fp["Cx"], None, fp["Cz"])
+    assert np.array_equal(p_r.get_n(), p_p.n)
+    for k, a in (("rd3", p_p.rd3), ("rw2", p_p.rw2), ("x", p_p.x), ("z", p_p.z)):
+        assert np.array_equal(p_r.get_attr(k), a), k
+    for step in range(4):
+        p_r.step_sync(o, f["th"], f["rv"], f["rhod"], f["Cx"], None, f["Cz"]); p_r.step_async(o)
+        th, rv = p_p.step_sync(fp["th"], fp["rv"], fp["rhod"])
+        fp["th"][:], fp["rv"][:] = th.reshape(fp["th"].shape), rv.reshape(fp["rv"].shape)
+        p_p.step_async()
+        assert np.array_equal(p_r.get_n(), p_p.n), step
+        for k, a in (("rd3", p_p.rd3), ("rw2", p_p.rw2), ("x", p_p.x), ("z", p_p.z)):
+            assert np.array_equal(p_r.get_attr(k), a), (k, step, S.rel_err(p_r.get_attr(k), a))
+        assert np.array_equal(f["th"], fp["th"]) and np.array_equal(f["rv"], fp["rv"]), step
+
+
 def test_port_recycling_matches_reference(ref):
     """opts.rcyc (rcyc.ipp:44-139): who is split, who is re-created, and the storage order afterwards"""
     nx, ny, nz, sd_conc = 4, 3, 6, 16
