@@ -49,6 +49,12 @@ namespace lcx
       real_t *rw2; const real_t *rd3, *kpa, *vt; const n_t *n; const idx_t *ijk;
       const real_t *rhod, *rv_c, *T, *p, *RH, *eta, *lam_D, *lam_K;
     };
+    // gather-on-read (lcx_engine::pending): where the five attributes still sit, and where the copies go
+    struct lazy_args
+    {
+      const uint32_t *perm; const real_t *rw2, *rd3, *kpa, *vt; const n_t *n;
+      real_t *rd3_out, *kpa_out, *vt_out; n_t *n_out;
+    };
 
     __device__ __forceinline__ cond_cell<real_t> load_cell(const cond_args &a, idx_t c)
     {
@@ -135,11 +141,11 @@ namespace lcx
     // Measured alternative: per-lane accumulator columns in shared memory instead of the shuffles - no faster, and its
     // 4 KB per warp limit the run to 8 cells (7.2-7.5 ms against 7.0-7.2 ms per launch for runs of 16).
     constexpr int RANGE_MAX = 16;
-    template <int MODE>
+    template <int MODE, bool LAZY>
     __global__ void __launch_bounds__(TPB, LCX_COND_MINB) k_cond_range(idx_t n_cell, int run, const uint32_t *__restrict__ off, real_t dt, real_t RH_max, cond_args a,
                                                        int n_dims, const real_t *__restrict__ dv, int first_step, int keep_after,
                                                        real_t *__restrict__ rw_mom3, real_t *__restrict__ drw_mom3,
-                                                       real_t *__restrict__ th, real_t *__restrict__ rv)
+                                                       real_t *__restrict__ th, real_t *__restrict__ rv, lazy_args z)
     {
       constexpr int WARPS = TPB / 32;
       __shared__ cond_cell_consts<real_t> s_k[WARPS][RANGE_MAX];
@@ -166,16 +172,22 @@ namespace lcx
         {
           const idx_t cc = a.ijk[i] - c0;
           ci = cc < idx_t(nc) ? int(cc) : nc - 1;
-          const real_t r2 = a.rw2[i];
-          const real_t nn = real_t(a.n[i]);
+          real_t r2, rd3_i, kpa_i, vt_i;
+          n_t n_i;
+          if (LAZY)      // the attributes still lie in the previous layout; their copies into the new one ride along
+          {
+            const uint32_t j = z.perm[i];
+            r2 = z.rw2[j]; rd3_i = z.rd3[j]; kpa_i = z.kpa[j]; vt_i = z.vt[j]; n_i = z.n[j];
+            z.rd3_out[i] = rd3_i; z.kpa_out[i] = kpa_i; z.vt_out[i] = vt_i; z.n_out[i] = n_i;
+          }
+          else { r2 = a.rw2[i]; rd3_i = a.rd3[i]; kpa_i = a.kpa[i]; vt_i = a.vt[i]; n_i = a.n[i]; }
+          const real_t nn = real_t(n_i);
           mb = nn * (r2 * sqrt(r2));
           real_t r2n = r2;
           if (r2 > 0)
-          {
-            r2n = MODE == COND_EXACT ? advance_rw2(r2, a.rd3[i], a.kpa[i], a.vt[i], load_cell(a, c0 + ci), dt, RH_max)
-                                        : advance_rw2_fast<MODE == COND_TOMS748>(r2, a.rd3[i], a.kpa[i], a.vt[i], s_k[w][ci], dt);
-            a.rw2[i] = r2n;
-          }
+            r2n = MODE == COND_EXACT ? advance_rw2(r2, rd3_i, kpa_i, vt_i, load_cell(a, c0 + ci), dt, RH_max)
+                                        : advance_rw2_fast<MODE == COND_TOMS748>(r2, rd3_i, kpa_i, vt_i, s_k[w][ci], dt);
+          if (LAZY || r2 > 0) a.rw2[i] = r2n;
           ma = nn * (r2n * sqrt(r2n));
         }
         // segmented sums over lanes with equal cell index; afterwards the first lane of every segment holds its total
@@ -273,10 +285,21 @@ namespace lcx
     if (run > 0)
     {
       const unsigned blocks = div_up(div_up(g.n_cell, run), TPB / 32);
-      LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_cond_range<M>), blocks, TPB, 0, g.n_cell, run, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p,
-                                        int(step == 0), keep_after, e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p));
+      lazy_args z = {};
+      if (e->pending)      // consume the pending re-layout: read through the permutation from the old buffer set, write everything into the new one
+      {
+        sd_arrays &o = e->A();
+        z = {e->pending_perm.p, o.rw2.p, o.rd3.p, o.kpa.p, o.vt.p, o.n.p, s.rd3.p, s.kpa.p, s.vt.p, s.n.p};
+        e->pending = false;
+        LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_cond_range<M, true>), blocks, TPB, 0, g.n_cell, run, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p,
+                                          int(step == 0), keep_after, e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p, z));
+        return;
+      }
+      LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_cond_range<M, false>), blocks, TPB, 0, g.n_cell, run, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p,
+                                        int(step == 0), keep_after, e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p, z));
       return;
     }
+    finish_pending(e);      // the other condensation kernels work on the current layout only
     if (e->max_count <= FUSED_MAX)
     {
       const unsigned blocks = div_up(size_t(g.n_cell) * GROUP, TPB);

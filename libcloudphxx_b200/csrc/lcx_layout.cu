@@ -408,18 +408,29 @@ namespace lcx
     const size_t n_new = e->h_scalars->n_part;
     e->max_count = e->h_scalars->max_count;
 
+    const bool lazy = e->lazy_gather && !keep_all && n_new > 0;
     if (n_new)
     {
       gather_set G; G.n = 0;
-      add(G, s.n.p, a.n.p, 8); add(G, s.rd3.p, a.rd3.p, 8); add(G, s.rw2.p, a.rw2.p, 8); add(G, s.kpa.p, a.kpa.p, 8);
-      add(G, s.vt.p, a.vt.p, 8); add(G, s.x.p, a.x.p, 8); add(G, s.y.p, a.y.p, 8); add(G, s.z.p, a.z.p, 8);
+      if (!lazy)
+      {
+        add(G, s.n.p, a.n.p, 8); add(G, s.rd3.p, a.rd3.p, 8); add(G, s.rw2.p, a.rw2.p, 8); add(G, s.kpa.p, a.kpa.p, 8);
+        add(G, s.vt.p, a.vt.p, 8);
+      }
+      add(G, s.x.p, a.x.p, 8); add(G, s.y.p, a.y.p, 8); add(G, s.z.p, a.z.p, 8);
       add(G, s.sid.p, a.sid.p, 4);
       add(G, s.pp_rv.p, a.pp_rv.p, 8); add(G, s.pp_th.p, a.pp_th.p, 8); add(G, s.pp_rh.p, a.pp_rh.p, 8); add(G, s.pp_p.p, a.pp_p.p, 8);
       add(G, s.rc2.p, a.rc2.p, 8);
       LCX_CUDA(cudaEventRecord(e->pre_gather, e->stream));      // uploads of the next step's fields may overtake the gather
       LCX_LAUNCH(e, k_gather, div_up(n_new, TPB), TPB, 0, n_new, perm, sorted_keys, g.class_bits, a.ijk.p, G);
       gather_queued = true;
+      if (lazy)      // the permutation lives in sort scratch: keep a copy for whoever consumes the pending attributes
+      {
+        if (e->pending_perm.n < e->cap) e->pending_perm.alloc(e->cap);
+        LCX_CUDA(cudaMemcpyAsync(e->pending_perm.p, perm, n_new * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
+      }
     }
+    e->pending = lazy;
     e->cur ^= 1;
     e->n_part = n_new;
     e->n_grouped = n_new;
@@ -433,6 +444,19 @@ namespace lcx
     }
     if (n_new == 0) { e->sid_hi = 0; e->sid_dense = true; }
     e->tail_is_gather = gather_queued;           // cleared by the next entry point that works on cell fields
+  }
+
+  // n, rd3, rw2, kpa, vt of the live SDs from the old buffer set into the current one (see lcx_engine::pending)
+  void finish_pending(lcx_engine *e)
+  {
+    if (!e->pending) return;
+    e->pending = false;
+    if (e->n_part == 0) return;
+    sd_arrays &dst = e->S(), &src = e->A();
+    gather_set G; G.n = 0;
+    add(G, src.n.p, dst.n.p, 8); add(G, src.rd3.p, dst.rd3.p, 8); add(G, src.rw2.p, dst.rw2.p, 8); add(G, src.kpa.p, dst.kpa.p, 8);
+    add(G, src.vt.p, dst.vt.p, 8);
+    LCX_LAUNCH(e, k_gather, div_up(e->n_part, TPB), TPB, 0, e->n_part, e->pending_perm.p, nullptr, 0, dst.ijk.p, G);
   }
 
   // new sid = rank of the old sid among the survivors (the order a stable compaction of the reference's storage gives)
