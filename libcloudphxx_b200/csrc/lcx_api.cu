@@ -24,10 +24,10 @@ namespace
   // consumer = the call may read or write cell fields on the engine's stream: order it after pending uploads
   // keep_pending = the call works on cell fields only (or is the condensation entry point, which consumes a pending
   // gather-on-read re-layout itself): everything else completes it first
-  void use_device(lcx_engine *e, bool consumer = true, bool keep_pending = false)
+  void use_device(lcx_engine *e, bool consumer = true, unsigned keep_pending = 0u)
   {
     LCX_CUDA(cudaSetDevice(e->device));
-    if (e->pending && !keep_pending) lcx::finish_pending(e);
+    if (e->pending & ~keep_pending) lcx::finish_pending(e, e->pending & ~keep_pending);
     if (!consumer) return;
     if (e->scalars_pending)
     {
@@ -251,7 +251,7 @@ int lcx_destroy(lcx_engine *e) { return guarded([&] { delete e; }); }
 int lcx_sync(lcx_engine *e)
 {
   return guarded([&] {
-    use_device(e, true, true);
+    use_device(e, true, 3u);
     LCX_CUDA(cudaStreamSynchronize(e->stream));
     if (e->upload_batch_open) LCX_CUDA(cudaStreamSynchronize(e->copy_stream));   // the data stay "pending" for the engine's stream
     e->upload_batch_open = false;
@@ -265,7 +265,7 @@ int lcx_field_size(lcx_engine *e, int field, int64_t *count) { return guarded([&
 int lcx_cells_set(lcx_engine *e, int field, const void *src, int64_t count, int src_on_device)
 {
   return guarded([&] {
-    use_device(e, true, true);
+    use_device(e, true, 3u);
     if (field == LCX_F_W_LS && e->w_LS.n != size_t(count)) e->w_LS.alloc(size_t(count));
     const field_ref f = field_of(e, field);
     lcx::wait_courant(e);
@@ -278,7 +278,7 @@ int lcx_cells_set(lcx_engine *e, int field, const void *src, int64_t count, int 
 int lcx_cells_get(lcx_engine *e, int field, void *dst, int64_t count)
 {
   return guarded([&] {
-    use_device(e, true, true);
+    use_device(e, true, 3u);
     const field_ref f = field_of(e, field);
     lcx::wait_courant(e);
     if (size_t(count) > f.n) throw lcx::error("lcx_cells_get: requested more values than the field holds");
@@ -291,7 +291,7 @@ int lcx_cells_set_part(lcx_engine *e, int field, int64_t offset, const void *src
 {
   return guarded([&] {
     const bool after_relayout = e->tail_is_gather;      // nothing but the gather has been queued since the last re-layout
-    use_device(e, /*consumer=*/false, /*keep_pending=*/true);
+    use_device(e, /*consumer=*/false, /*keep_pending=*/3u);
     const field_ref f = field_of(e, field);
     if (offset < 0 || count < 0 || size_t(offset + count) > f.n) throw lcx::error("lcx_cells_set_part: range outside field " + std::to_string(field));
     const bool courant = field == LCX_F_COURANT_X || field == LCX_F_COURANT_Y || field == LCX_F_COURANT_Z;
@@ -314,7 +314,7 @@ int lcx_cells_set_part(lcx_engine *e, int field, int64_t offset, const void *src
 int lcx_cells_get_part(lcx_engine *e, int field, int64_t offset, void *dst, int64_t count)
 {
   return guarded([&] {
-    use_device(e, true, true);
+    use_device(e, true, 3u);
     const field_ref f = field_of(e, field);
     if (offset < 0 || count < 0 || size_t(offset + count) > f.n) throw lcx::error("lcx_cells_get_part: range outside field " + std::to_string(field));
     LCX_CUDA(cudaMemcpyAsync(dst, static_cast<const lcx::real_t *>(f.p) + offset, size_t(count) * sizeof(lcx::real_t), cudaMemcpyDeviceToHost, e->stream));
@@ -408,12 +408,12 @@ int lcx_get_attr_u64(lcx_engine *e, int attr, uint64_t *dst, int64_t cap, int64_
   });
 }
 
-int lcx_hskpng_Tpr(lcx_engine *e) { return guarded([&] { use_device(e, true, true); lcx::hskpng_Tpr(e); }); }
-int lcx_hskpng_mfp(lcx_engine *e) { return guarded([&] { use_device(e, true, true); lcx::hskpng_mfp(e); }); }
-int lcx_hskpng_vterm(lcx_engine *e, int only_invalid) { return guarded([&] { use_device(e); lcx::hskpng_vterm(e, only_invalid != 0); }); }
+int lcx_hskpng_Tpr(lcx_engine *e) { return guarded([&] { use_device(e, true, 3u); lcx::hskpng_Tpr(e); }); }
+int lcx_hskpng_mfp(lcx_engine *e) { return guarded([&] { use_device(e, true, 3u); lcx::hskpng_mfp(e); }); }
+int lcx_hskpng_vterm(lcx_engine *e, int only_invalid) { return guarded([&] { use_device(e, true, lcx_engine::PENDING_XYZ); lcx::hskpng_vterm(e, only_invalid != 0); }); }
 int lcx_sstp_percell_step(lcx_engine *e, int step, int sstp_cond, int var_rho)
-{ return guarded([&] { use_device(e, true, true); lcx::sstp_percell_step(e, step, sstp_cond, var_rho != 0); }); }
-int lcx_sstp_save(lcx_engine *e) { return guarded([&] { use_device(e, true, true); lcx::sstp_save(e); }); }
+{ return guarded([&] { use_device(e, true, 3u); lcx::sstp_percell_step(e, step, sstp_cond, var_rho != 0); }); }
+int lcx_sstp_save(lcx_engine *e) { return guarded([&] { use_device(e, true, 3u); lcx::sstp_save(e); }); }
 
 int lcx_set_cond_solver(int mode) { lcx::set_cond_solver(mode); return 0; }
 int lcx_get_cond_solver(void) { return lcx::cond_solver(); }
@@ -426,17 +426,17 @@ int lcx_cond_perparticle(lcx_engine *e, double dt, double RH_max, int sstp_cond,
 int lcx_cond_perparticle_adaptive(lcx_engine *e, double dt, double RH_max, int sstp_cond_max, int sstp_cond_act, double drw2_eps, double drw2_max)
 { return guarded([&] { use_device(e); lcx::cond_perparticle_adaptive(e, dt, RH_max, sstp_cond_max, sstp_cond_act, drw2_eps, drw2_max); }); }
 
-int lcx_hskpng_rc2(lcx_engine *e) { return guarded([&] { use_device(e); lcx::hskpng_rc2(e); }); }
+int lcx_hskpng_rc2(lcx_engine *e) { return guarded([&] { use_device(e, true, lcx_engine::PENDING_XYZ); lcx::hskpng_rc2(e); }); }
 
 int lcx_cond(lcx_engine *e, double dt_sub, double RH_max, int step, int sstp_cond)
-{ return guarded([&] { use_device(e, true, true); lcx::cond(e, dt_sub, RH_max, step, sstp_cond); }); }
+{ return guarded([&] { use_device(e, true, 3u); lcx::cond(e, dt_sub, RH_max, step, sstp_cond); }); }
 
-int lcx_coal(lcx_engine *e, double dt_sub, const lcx_rng *rng) { return guarded([&] { use_device(e); lcx::coal(e, dt_sub, rng); }); }
+int lcx_coal(lcx_engine *e, double dt_sub, const lcx_rng *rng) { return guarded([&] { use_device(e, true, lcx_engine::PENDING_XYZ); lcx::coal(e, dt_sub, rng); }); }
 
 int lcx_coal_flag(lcx_engine *e, int *increase_sstp_coal)
 {
   return guarded([&] {
-    use_device(e);
+    use_device(e, true, 3u);      // device scalars only
     LCX_CUDA(cudaMemcpyAsync(e->h_scalars, e->scalars.p, sizeof(lcx::dev_scalars), cudaMemcpyDeviceToHost, e->stream));
     LCX_CUDA(cudaStreamSynchronize(e->stream));
     *increase_sstp_coal = int(e->h_scalars->increase_sstp_coal);
@@ -447,7 +447,7 @@ int lcx_coal_flag(lcx_engine *e, int *increase_sstp_coal)
 int lcx_coal_stats(lcx_engine *e, uint64_t *n_collisions, uint64_t *n_pairs_collided)
 {
   return guarded([&] {
-    use_device(e);
+    use_device(e, true, 3u);      // device scalars only
     LCX_CUDA(cudaMemcpyAsync(e->h_scalars, e->scalars.p, sizeof(lcx::dev_scalars), cudaMemcpyDeviceToHost, e->stream));
     LCX_CUDA(cudaStreamSynchronize(e->stream));
     *n_collisions = e->h_scalars->n_collisions;
@@ -455,12 +455,12 @@ int lcx_coal_stats(lcx_engine *e, uint64_t *n_collisions, uint64_t *n_pairs_coll
   });
 }
 
-int lcx_transport(lcx_engine *e, const lcx_transport_opts *o) { return guarded([&] { use_device(e); lcx::transport(e, o); }); }
+int lcx_transport(lcx_engine *e, const lcx_transport_opts *o) { return guarded([&] { use_device(e, true, lcx_engine::PENDING_XYZ); lcx::transport(e, o); }); }
 
 int lcx_puddle(lcx_engine *e, double out[14])
 {
   return guarded([&] {
-    use_device(e);
+    use_device(e, true, 3u);      // device scalars only
     LCX_CUDA(cudaMemcpyAsync(e->h_scalars, e->scalars.p, sizeof(lcx::dev_scalars), cudaMemcpyDeviceToHost, e->stream));
     LCX_CUDA(cudaStreamSynchronize(e->stream));
     for (int i = 0; i < 14; ++i) out[i] = 0;
@@ -545,7 +545,7 @@ int lcx_outbuf(lcx_engine *e, void *dst, int64_t count) { return lcx_cells_get(e
 int lcx_timer_start(lcx_engine *e)
 {
   return guarded([&] {
-    use_device(e, true, true);
+    use_device(e, true, 3u);
     if (!e->timer0) { LCX_CUDA(cudaEventCreate(&e->timer0)); LCX_CUDA(cudaEventCreate(&e->timer1)); }
     LCX_CUDA(cudaEventRecord(e->timer0, e->stream));
   });
@@ -554,7 +554,7 @@ int lcx_timer_start(lcx_engine *e)
 int lcx_timer_stop(lcx_engine *e, float *ms)
 {
   return guarded([&] {
-    use_device(e, true, true);
+    use_device(e, true, 3u);
     if (!e->timer0) throw lcx::error("lcx_timer_stop without lcx_timer_start");
     LCX_CUDA(cudaEventRecord(e->timer1, e->stream));
     LCX_CUDA(cudaEventSynchronize(e->timer1));
@@ -565,7 +565,7 @@ int lcx_timer_stop(lcx_engine *e, float *ms)
 int lcx_profile_enable(lcx_engine *e, int on)
 {
   return guarded([&] {
-    use_device(e, true, true);
+    use_device(e, true, 3u);
     LCX_CUDA(cudaStreamSynchronize(e->stream));
     for (auto &r : e->prof) { cudaEventDestroy(r.t0); cudaEventDestroy(r.t1); }
     e->prof.clear();
@@ -576,7 +576,7 @@ int lcx_profile_enable(lcx_engine *e, int on)
 int lcx_profile_report(lcx_engine *e, char *buf, int64_t size)
 {
   return guarded([&] {
-    use_device(e, true, true);
+    use_device(e, true, 3u);
     LCX_CUDA(cudaStreamSynchronize(e->stream));
     std::map<std::string, std::pair<uint64_t, double>> acc;
     for (auto &r : e->prof)

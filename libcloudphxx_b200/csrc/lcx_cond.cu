@@ -286,11 +286,11 @@ namespace lcx
     {
       const unsigned blocks = div_up(div_up(g.n_cell, run), TPB / 32);
       lazy_args z = {};
-      if (e->pending)      // consume the pending re-layout: read through the permutation from the old buffer set, write everything into the new one
+      if (e->pending & lcx_engine::PENDING_ATTR)      // consume the pending re-layout: read through the permutation from the old buffer set, write everything into the new one
       {
         sd_arrays &o = e->A();
         z = {e->pending_perm.p, o.rw2.p, o.rd3.p, o.kpa.p, o.vt.p, o.n.p, s.rd3.p, s.kpa.p, s.vt.p, s.n.p};
-        e->pending = false;
+        e->pending &= ~unsigned(lcx_engine::PENDING_ATTR);
         LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_cond_range<M, true>), blocks, TPB, 0, g.n_cell, run, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p,
                                           int(step == 0), keep_after, e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p, z));
         return;
@@ -299,7 +299,7 @@ namespace lcx
                                         int(step == 0), keep_after, e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p, z));
       return;
     }
-    finish_pending(e);      // the other condensation kernels work on the current layout only
+    finish_pending(e, lcx_engine::PENDING_ATTR);      // the other condensation kernels work on the current layout only
     if (e->max_count <= FUSED_MAX)
     {
       const unsigned blocks = div_up(size_t(g.n_cell) * GROUP, TPB);

@@ -156,12 +156,15 @@ struct lcx_engine
   lcx::dbuf<lcx::real_t> drw_mom3, rw_mom3, count_mom, mom_partial;
   lcx::dbuf<lcx::real_t> cell_tmp4;        // 4 reals per cell: per-cell parts of the Beard (1977) fall-speed correction
   lcx::dbuf<lcx::real_t> courant_x, courant_y, courant_z, w_LS;
-  // Gather-on-read (opt-in, LCX_LAZY_GATHER=1): after a re-layout only x, y, z, sid and the per-particle records are moved at once.
-  // n, rd3, rw2, kpa, vt of the live SDs stay in the OLD buffer set A() with pending_perm[new position] = old position until the
-  // next consumer: the condensation kernel (FP64-bound, 7 % of the DRAM bandwidth) reads them through the permutation and writes all
-  // five into S() for free; every other consumer first runs finish_pending().
+  // Gather-on-read (opt-in, LCX_LAZY_GATHER=1): after a re-layout only sid and the per-particle records are moved at once.  The
+  // other attributes of the live SDs stay in the OLD buffer set A() with pending_perm[new position] = old position until their
+  // first consumer, which reads them through the permutation and writes them into S():
+  //   PENDING_ATTR  n, rd3, rw2, kpa, vt  - the condensation kernel (FP64-bound, 7 % of the DRAM bandwidth: free of charge);
+  //   PENDING_XYZ   x, y, z               - the transport kernel (nothing reads positions before it).
+  // Every other consumer first runs finish_pending() for what it needs.
+  enum { PENDING_ATTR = 1u, PENDING_XYZ = 2u };
   bool lazy_gather = false;
-  bool pending = false;
+  unsigned pending = 0;
   lcx::dbuf<uint32_t> pending_perm;
   size_t n_grouped = 0;          // SDs [0, n_grouped) still lie in the segments described by cell_off / ijk of the last re-layout
   lcx::dbuf<uint32_t> mv_scan;   // n_cell + 2: movers per old cell, then their exclusive scan (movers-only re-layout)
@@ -213,7 +216,7 @@ namespace lcx
   // ---- lcx_layout.cu ---------------------------------------------------------------------------------
   void compute_cell_offsets(lcx_engine *e, const uint32_t *sorted_keys, size_t n_total);
   void post_copy(lcx_engine *e, bool rcyc, bool keep_all);
-  void finish_pending(lcx_engine *e);      // completes a gather-on-read re-layout (no-op when nothing is pending)
+  void finish_pending(lcx_engine *e, unsigned what = 3u);      // completes (the named parts of) a gather-on-read re-layout
   void scatter_attr_by_sid(lcx_engine *e, int attr, real_t *dst);
   void densify_sid(lcx_engine *e);
 

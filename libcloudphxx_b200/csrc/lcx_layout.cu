@@ -417,7 +417,7 @@ namespace lcx
         add(G, s.n.p, a.n.p, 8); add(G, s.rd3.p, a.rd3.p, 8); add(G, s.rw2.p, a.rw2.p, 8); add(G, s.kpa.p, a.kpa.p, 8);
         add(G, s.vt.p, a.vt.p, 8);
       }
-      add(G, s.x.p, a.x.p, 8); add(G, s.y.p, a.y.p, 8); add(G, s.z.p, a.z.p, 8);
+      if (!lazy) { add(G, s.x.p, a.x.p, 8); add(G, s.y.p, a.y.p, 8); add(G, s.z.p, a.z.p, 8); }
       add(G, s.sid.p, a.sid.p, 4);
       add(G, s.pp_rv.p, a.pp_rv.p, 8); add(G, s.pp_th.p, a.pp_th.p, 8); add(G, s.pp_rh.p, a.pp_rh.p, 8); add(G, s.pp_p.p, a.pp_p.p, 8);
       add(G, s.rc2.p, a.rc2.p, 8);
@@ -430,7 +430,7 @@ namespace lcx
         LCX_CUDA(cudaMemcpyAsync(e->pending_perm.p, perm, n_new * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
       }
     }
-    e->pending = lazy;
+    e->pending = lazy ? (lcx_engine::PENDING_ATTR | (g.n_dims > 0 ? lcx_engine::PENDING_XYZ : 0u)) : 0u;
     e->cur ^= 1;
     e->n_part = n_new;
     e->n_grouped = n_new;
@@ -446,17 +446,22 @@ namespace lcx
     e->tail_is_gather = gather_queued;           // cleared by the next entry point that works on cell fields
   }
 
-  // n, rd3, rw2, kpa, vt of the live SDs from the old buffer set into the current one (see lcx_engine::pending)
-  void finish_pending(lcx_engine *e)
+  // what is still pending of a gather-on-read re-layout: from the old buffer set into the current one (see lcx_engine::pending)
+  void finish_pending(lcx_engine *e, unsigned what)
   {
-    if (!e->pending) return;
-    e->pending = false;
+    what &= e->pending;
+    if (!what) return;
+    e->pending &= ~what;
     if (e->n_part == 0) return;
     sd_arrays &dst = e->S(), &src = e->A();
     gather_set G; G.n = 0;
-    add(G, src.n.p, dst.n.p, 8); add(G, src.rd3.p, dst.rd3.p, 8); add(G, src.rw2.p, dst.rw2.p, 8); add(G, src.kpa.p, dst.kpa.p, 8);
-    add(G, src.vt.p, dst.vt.p, 8);
-    LCX_LAUNCH(e, k_gather, div_up(e->n_part, TPB), TPB, 0, e->n_part, e->pending_perm.p, nullptr, 0, dst.ijk.p, G);
+    if (what & lcx_engine::PENDING_ATTR)
+    {
+      add(G, src.n.p, dst.n.p, 8); add(G, src.rd3.p, dst.rd3.p, 8); add(G, src.rw2.p, dst.rw2.p, 8); add(G, src.kpa.p, dst.kpa.p, 8);
+      add(G, src.vt.p, dst.vt.p, 8);
+    }
+    if (what & lcx_engine::PENDING_XYZ) { add(G, src.x.p, dst.x.p, 8); add(G, src.y.p, dst.y.p, 8); add(G, src.z.p, dst.z.p, 8); }
+    if (G.n) LCX_LAUNCH(e, k_gather, div_up(e->n_part, TPB), TPB, 0, e->n_part, e->pending_perm.p, nullptr, 0, dst.ijk.p, G);
   }
 
   // new sid = rank of the old sid among the survivors (the order a stable compaction of the reference's storage gives)

@@ -107,13 +107,17 @@ namespace lcx
 #ifndef LCX_TR_MINB
 #define LCX_TR_MINB 6      // latency-bound kernel: 40 registers, 48 resident warps; measured best of {3,4,5,6}
 #endif
+    // LAZY: positions still lie in the previous layout (lcx_engine::PENDING_XYZ): read through the permutation, written in place
+    template <bool LAZY>
     __global__ void __launch_bounds__(TPB, LCX_TR_MINB) k_transport(size_t n_part, tr_params P,
                                                       real_t *__restrict__ xs, real_t *__restrict__ ys, real_t *__restrict__ zs,
                                                       const real_t *__restrict__ vt, const idx_t *__restrict__ ijk, n_t *__restrict__ ns,
                                                       const real_t *__restrict__ rw2, const real_t *__restrict__ rd3,
                                                       const real_t *__restrict__ Cx, const real_t *__restrict__ Cy, const real_t *__restrict__ Cz,
                                                       const real_t *__restrict__ w_LS, uint32_t *__restrict__ flag, double *__restrict__ partial,
-                                                      uint32_t *__restrict__ key, uint32_t *__restrict__ val)
+                                                      uint32_t *__restrict__ key, uint32_t *__restrict__ val,
+                                                      const uint32_t *__restrict__ perm, const real_t *__restrict__ xi, const real_t *__restrict__ yi,
+                                                      const real_t *__restrict__ zi)
     {
       __shared__ double red[4][TPB / 32];
       const grid_t &g = P.g;
@@ -130,7 +134,9 @@ namespace lcx
           case 2: i = c / g.nz; k = c % g.nz; break;
           case 3: i = c / (idx_t(g.nz) * g.ny); j = (c / g.nz) % g.ny; k = c % g.nz; break;
         }
-        real_t x = g.nx ? xs[t] : 0, y = g.ny ? ys[t] : 0, z = g.nz ? zs[t] : 0;
+        real_t x, y, z;
+        if (LAZY) { const uint32_t src = perm[t]; x = g.nx ? xi[src] : 0; y = g.ny ? yi[src] : 0; z = g.nz ? zi[src] : 0; }
+        else      { x = g.nx ? xs[t] : 0; y = g.ny ? ys[t] : 0; z = g.nz ? zs[t] : 0; }
         n_t n = ns[t];
 
         if (P.adve && g.n_dims > 0)
@@ -368,8 +374,18 @@ namespace lcx
     static const int ctas_per_sm = [] { const char *v = std::getenv("LCX_TR_CTAS"); return v ? std::atoi(v) : 48; }();
     const unsigned blocks = unsigned(ctas_per_sm > 0 ? std::min<size_t>(div_up(n, TPB), size_t(148) * ctas_per_sm) : div_up(n, TPB));
     if (e->red_partial.n < size_t(blocks) * 4) { LCX_CUDA(cudaStreamSynchronize(e->stream)); e->red_partial.alloc(size_t(blocks) * 4 + 1024); }
-    LCX_LAUNCH(e, k_transport, blocks, TPB, 0, n, P, s.x.p, s.y.p, s.z.p, s.vt.p, s.ijk.p, s.n.p, s.rw2.p, s.rd3.p,
-               e->courant_x.p, e->courant_y.p, e->courant_z.p, e->w_LS.p, e->flag.p, e->red_partial.p, e->key[0].p, e->val[0].p);
+    if (e->pending & lcx_engine::PENDING_XYZ)
+    {
+      sd_arrays &o2 = e->A();
+      e->pending &= ~unsigned(lcx_engine::PENDING_XYZ);
+      LCX_LAUNCH(e, k_transport<true>, blocks, TPB, 0, n, P, s.x.p, s.y.p, s.z.p, s.vt.p, s.ijk.p, s.n.p, s.rw2.p, s.rd3.p,
+                 e->courant_x.p, e->courant_y.p, e->courant_z.p, e->w_LS.p, e->flag.p, e->red_partial.p, e->key[0].p, e->val[0].p,
+                 e->pending_perm.p, o2.x.p, o2.y.p, o2.z.p);
+    }
+    else
+      LCX_LAUNCH(e, k_transport<false>, blocks, TPB, 0, n, P, s.x.p, s.y.p, s.z.p, s.vt.p, s.ijk.p, s.n.p, s.rw2.p, s.rd3.p,
+                 e->courant_x.p, e->courant_y.p, e->courant_z.p, e->w_LS.p, e->flag.p, e->red_partial.p, e->key[0].p, e->val[0].p,
+                 nullptr, nullptr, nullptr, nullptr);
     e->keys_ready = n;      // key[0] / val[0] hold the sort keys of SDs [0, n)
     if (e->grid.n_dims > 1 && !e->cfg.periodic_topbot_walls)
       LCX_LAUNCH(e, k_puddle_final, 1, TPB, 0, blocks, e->red_partial.p, e->scalars.p);

@@ -80,3 +80,24 @@ def test_lazy_against_reference(ref, b200, monkeypatch):
         S.run_pair(ref, b200, S.box_3d, 5, on_step=check, nx=6, ny=5, nz=8, sd_conc=32, rain_mode=True)
     finally:
         E.set_cond_layout(0)
+
+
+def test_lazy_paths_are_taken(b200, monkeypatch):
+    """the per-kernel profile names the variants that ran: with the opt-in both consumers read through the permutation"""
+    from libcloudphxx_b200 import distributed as D
+    monkeypatch.setenv("LCX_LAZY_GATHER", "1")
+    E.set_cond_layout(16)
+    try:
+        oi, o, f = S.box_3d(b200, nx=6, ny=5, nz=8, sd_conc=32, rain_mode=True)
+        p = b200.factory(L.backend_t.CUDA, oi)
+        p.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
+        eng = D.engine_of(b200, p)
+        p.step_sync(o, f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"]); p.step_async(o)
+        eng.profile(True)
+        for _ in range(2):
+            p.step_sync(o, f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"]); p.step_async(o)
+        names = " ".join(eng.profile_report())
+        eng.profile(False)
+        assert "k_transport<true>" in names and "true>)" in names.replace("k_transport<true>", ""), names
+    finally:
+        E.set_cond_layout(0)
