@@ -391,7 +391,7 @@ def run_b200(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "cfg4 x-slab per GPU: %dx%dx%d cells x %d SD/cell, hall_davis_no_waals, beard77fast, implicit adve, sstp 1/1" % (nx, ny, nz, args.sd_conc),
                        "sd_per_gpu": nx * ny * nz * args.sd_conc, "global_cells": [nx * world, ny, nz], "rng": "philox4x32-10",
-                       "cond_solver": "toms748 (the reference's trial points)", "cond_layout": E.get_cond_layout(),
+                       "cond_solver": "toms748 (the reference's trial points)", "cond_layout": E.get_cond_layout(), "lazy_gather": os.environ.get("LCX_LAZY_GATHER", "0") == "1",
                        "l2": "inputs_exceed_l2 (%.1f GB of SD state per GPU)" % (nx * ny * nz * args.sd_conc * 76 / 1e9),
                        "init_s": round(t_init, 2), "max_sd_per_cell": max_count, "wall_ms_per_step": wall_ms / args.steps},
             "clocks": clocks,
