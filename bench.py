@@ -193,7 +193,11 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        os.environ["OMP_NUM_THREADS"] = str(cores)      # torchrun exports OMP_NUM_THREADS=1; only this rank works, it may use every core
+    else:
+        os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = int(os.environ["OMP_NUM_THREADS"])           # the threads the OpenMP back-end will really use
     ref = S.oracle_library()
     nx, ny, nz = args.ref_nx, args.ref_ny, args.ref_nz
     oi, o, f = make_case(ref, nx, ny, nz, args.sd_conc)

@@ -15,7 +15,9 @@
 //                   constants of the run sit in shared memory, the per-cell sums come from a segmented warp reduction
 //                   (the cell index is non-decreasing along the range).  k_cond_cells leaves lanes idle whenever the
 //                   four cells of a warp differ in population (measured: 24.7 of 32 lanes in the kernel body at
-//                   40 +- 6 SDs per cell); here only the last round of a warp is ragged.  Chosen on large grids.
+//                   40 +- 6 SDs per cell); here only the last round of a warp is ragged (31.3 lanes).  Chosen on large
+//                   grids: 7.8 -> 7.0 ms at the bench size - less than the lane count suggests, because the 32
+//                   consecutive SDs of a round need less alike numbers of trial points than the old 4 x 8.
 // Cells too populous for that (0-D boxes: one cell with 1e5..1e6 SDs) use a thread-per-SD kernel between two
 // chunked per-cell moment reductions (lcx_diag.cu).
 // The root solve is FP64-compute bound; three variants are compiled (lcx_set_cond_solver / LCX_COND_SOLVER, lcx_physics.h):

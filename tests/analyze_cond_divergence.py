@@ -7,6 +7,7 @@ the evaluations of drw2/dt are counted per droplet in the last condensation step
   storage    - cells contiguous, inside a cell the order the re-layout leaves (stayers in old order, then arrivals)
   size class - the same windows of `run` cells, droplets ordered by a coarse size class first (what a warp could do itself)
   ideal      - ordered by the evaluation count itself (lower bound)
+  previous   - ordered by the count the droplet needed in the previous step (a 1-byte record a kernel could carry along)
 Test infrastructure (lives under tests/ because it uses oracle/); never shipped, not collected by pytest."""
 import math
 import os
@@ -49,10 +50,10 @@ def main(nx=2, ny=2, nz=128, sd_conc=40, steps=8, run=16):
         return orig(*a)
     port.drw2_dt = counted
 
-    evals = None
+    evals = prev_evals = None
     for step in range(steps):
         last = step == steps - 1
-        if last:
+        if last or step == steps - 2:
             # per-droplet evaluation counts: wrap advance_rw2
             per = np.zeros(p.n_part, dtype=np.int64)
             adv = port.advance_rw2
@@ -70,6 +71,9 @@ def main(nx=2, ny=2, nz=128, sd_conc=40, steps=8, run=16):
             port.advance_rw2 = adv
             evals = per
             break
+        if step == steps - 2:
+            port.advance_rw2 = adv
+            prev_evals = per                             # storage order is stable (no SD is removed in this set-up)
         f["th"][:], f["rv"][:] = th.reshape(f["th"].shape), rv.reshape(f["rv"].shape)
         n_before = p.n_part
         p.step_async()
@@ -128,6 +132,16 @@ def main(nx=2, ny=2, nz=128, sd_conc=40, steps=8, run=16):
         a, b = off[c0], off[min(c0 + run, n_cell)]
         order.append(a + np.argsort(ev[a:b], kind="stable"))
     print("  runs of %d cells ordered by the count itself %.2f" % (run, cost(np.concatenate(order))))
+    if prev_evals is not None:
+        pe = prev_evals[phys]
+        print("  the previous step's count predicts this step's exactly for %.1f %% of the droplets, within one for %.1f %%"
+              % (100. * (pe == ev).mean(), 100. * (np.abs(pe - ev) <= 1).mean()))
+        for r in (run, 8):
+            order = []
+            for c0 in range(0, n_cell, r):
+                a, b = off[c0], off[min(c0 + r, n_cell)]
+                order.append(a + np.argsort(pe[a:b], kind="stable"))
+            print("  runs of %d cells ordered by the PREVIOUS step's count %.2f" % (r, cost(np.concatenate(order))))
 
 
 if __name__ == "__main__":
