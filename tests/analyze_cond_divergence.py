@@ -9,7 +9,6 @@ the evaluations of drw2/dt are counted per droplet in the last condensation step
   ideal      - ordered by the evaluation count itself (lower bound)
   previous   - ordered by the count the droplet needed in the previous step (a 1-byte record a kernel could carry along)
 Test infrastructure (lives under tests/ because it uses oracle/); never shipped, not collected by pytest."""
-import math
 import os
 import sys
 
@@ -36,9 +35,8 @@ def main(nx=2, ny=2, nz=128, sd_conc=40, steps=8, run=16):
     p.init(f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"])
 
     # physical order of the B200 engine: grouped by cell; stayers keep their order, arrivals are appended in old physical order.
-    # SDs are identified by a private tag carried alongside the port's arrays (the port compacts on removal: track through rd3+x)
+    # (no SD is removed in this set-up, so the port's storage index identifies an SD throughout)
     n0 = p.n_part
-    tag = np.arange(n0)
     phys = np.argsort(p.ijk[:n0], kind="stable")       # initial grouping: storage order inside each cell (sorted by dry size)
     cell_of = p.ijk[:n0].copy()
 
@@ -93,7 +91,6 @@ def main(nx=2, ny=2, nz=128, sd_conc=40, steps=8, run=16):
     ev = evals[phys].astype(float)                     # evaluation counts in physical order
     rw2 = p.rw2[:n][phys]
     cells = cell_of[phys]
-    live = ev > 0
     print("droplets %d, evaluations per droplet: mean %.2f, max %d; histogram %s" % (n, ev.mean(), ev.max(), np.bincount(evals)[:16]))
 
     def cost(order):                                   # sum over warp rounds of the max evaluation count, per droplet
