@@ -10,6 +10,15 @@ build (tools/make_golden.py) so the pin also holds where /root/reference is abse
 Python's math module (the same glibc the reference's CPU back-end uses), numpy is used only for + - * / sqrt and for
 integer work, so that agreement can be exact.
 
+Covered (each pinned bit for bit by a test in tests/test_cpu_oracle.py): every initialisation flavour; sort / shuffle / count;
+coalescence with the Golovin, geometric (with and without multiplier), Long and tabulated-efficiency kernels incl. kappa mixing;
+per-cell and per-particle (mixing, no mixing, adaptive, activation sub-stepping) condensation with TOMS 748, the four RH
+formulae, dry theta with diagnosed pressure or standard theta with prescribed pressure; the five fall-speed formulae; implicit,
+Euler and predictor-corrector advection, sedimentation, subsidence; periodic / open walls and the puddle; removal and recycling;
+selectors, moments, SD concentration, precipitation flux, largest radius.  0-D, 2-D and 3-D.
+Not covered: x-slab migration (no reference run of it is possible here: multi_CUDA needs a GPU, MPI is not built), chemistry, ice,
+turbulence, sources / relaxation (outside the hot path).
+
 Every function cites the reference code it restates (paths relative to the reference repository root).
 """
 import math
