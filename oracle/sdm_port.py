@@ -10,6 +10,16 @@ build (tools/make_golden.py) so the pin also holds where /root/reference is abse
 Python's math module (the same glibc the reference's CPU back-end uses), numpy is used only for + - * / sqrt and for
 integer work, so that agreement can be exact.
 
+Covered (each pinned bit for bit by a test in tests/test_cpu_oracle.py): every initialisation flavour; sort / shuffle / count;
+coalescence with the Golovin, geometric (with and without multiplier), Long and tabulated-efficiency kernels incl. kappa mixing;
+per-cell and per-particle (mixing, no mixing, adaptive, activation sub-stepping) condensation with TOMS 748, the four RH
+formulae, dry theta with diagnosed pressure or standard theta with prescribed pressure; the five fall-speed formulae; implicit,
+Euler and predictor-corrector advection, sedimentation, subsidence; periodic / open walls and the puddle; removal and recycling;
+selectors, moments, SD concentration, precipitation flux, largest radius.  0-D, 2-D and 3-D.
+x-slab decomposition and migration (SlabParticles) are restated too but UNPINNED: no reference run of them is possible here (multi_CUDA
+needs a GPU, MPI is not built); the tests check what the reference's own distributed test demands instead.
+Not covered: chemistry, ice, turbulence, sources / relaxation (outside the hot path).
+
 Every function cites the reference code it restates (paths relative to the reference repository root).
 """
 import math
@@ -549,6 +559,7 @@ class Particles:
         self.RH_max_init = RH_max_init
         self.RH_formula = RH_formula
         self.open_side_walls = open_side_walls
+        self.distmem = False                             # set by SlabParticles: x faces shared with neighbouring slabs
         self.th_dry, self.const_p = th_dry, const_p     # opts_init.th_dry / const_p: what "th" means and whether p is prescribed
         if const_p and exact_sstp_cond:
             raise NotImplementedError("the restatement covers const_p with per-cell sub-stepping only")
@@ -1130,7 +1141,10 @@ class Particles:
         if self.n_dims == 0:
             return
         wrap = lambda x, a, b: a + np.fmod((x - a) + 10 * (b - a), b - a)
-        if not self.open_side_walls:
+        if self.distmem:                                 # bcnd.ipp:144-194: ids of the SDs that cross a slab face, in ascending storage order
+            self.lft_id = np.nonzero(self.x < self.x0)[0]
+            self.rgt_id = np.nonzero(self.x >= self.x1)[0]
+        elif not self.open_side_walls:
             self.x = wrap(self.x, self.x0, self.x1)
         else:                                            # bcnd.ipp:132-142: SDs that left through a side wall are flagged for removal
             self.n[(self.x >= self.x1) | (self.x < self.x0)] = 0
@@ -1197,6 +1211,13 @@ class Particles:
             k = self._k_midpoint if (adve and self.adve_scheme == "pred_corr") else self.unravel(self.ijk)[2]     # when ijk was last computed
             self.z = self.z - self.dt * self.w_LS[k]
         self.bcnd()
+        self._n_coll = n_coll
+        if self.distmem:                                 # the slab system exchanges the migrants, then calls post_copy on every slab
+            return n_coll
+        return self.post_copy(rcyc)
+
+    def post_copy(self, rcyc=False):                     # post_copy.ipp:18-35
+        n_coll = self._n_coll
         self.n_recycled = 0
         if rcyc:                                         # post_copy.ipp:24-29
             self.rcyc()
@@ -1214,3 +1235,98 @@ class Particles:
         self.ijk = ((ii * max(1, self.ny) + jj) * max(1, self.nz) + kk) * np.ones(self.n_part, dtype=np.int64)
         self.sort(False)
         return n_coll
+
+
+# ---- x-slab decomposition: src/detail/distmem_opts.hpp:10-52, impl_multi_gpu/particles_multi_gpu_impl.ipp:131-170,
+#      impl_multi_gpu/particles_multi_gpu_impl_step_async_and_copy.ipp:28-206, distributed_memory/particles_impl_{pack,unpack}.ipp ----
+def slab_nx(nx, rank, size):                            # detail::get_dev_nx
+    return int(nx / size + .5) if rank < size - 1 else nx - rank * int(nx / size + .5)
+
+
+class SlabParticles:
+    """The periodic domain cut into `size` x-slabs, each an independent Particles object in its own local coordinates (x0 = 0 for every
+    slab but the first), super-droplets that cross a slab face handed to the neighbour once per step.
+
+    Restated from the reference's multi_CUDA back-end.  NOT PINNED against a run of the reference: multi_CUDA needs GPUs and the MPI
+    variant is not built here.  What tests/test_cpu_oracle.py checks instead are the consequences the reference's own tests demand
+    (tests/mpi/mpi_adve_test.cpp: a pattern advected once around the ring returns unchanged) and agreement with the undivided domain.
+    Order of arrival (the part that must be bit-exact in a re-implementation): every slab first appends what its RIGHT neighbour sent
+    (that neighbour's left-movers, in its ascending storage order), then what its LEFT neighbour sent; the senders' copies get n = 0
+    and disappear in post_copy.  Positions: x' = x1_of_receiver + x - x0_of_sender for left-movers, x' = x0_of_receiver + x - x1_of_sender
+    for right-movers (pack.ipp:15-26), then pulled inside by config.bcond_tolerance = 5e-4 m if still outside (unpack.ipp:14-31,100-101),
+    and - for the batch that came from the right - stepped just below x1 when it landed exactly on it (..._and_copy.ipp:137).
+    Every slab seeds its generator with the same opts_init.rng_seed (particles_multi_gpu_impl.ipp:139: the options are copied)."""
+    BCOND_TOLERANCE = 5e-4                               # src/detail/config.hpp:31
+
+    def __init__(self, size, **kw):
+        assert size > 1 and kw.get("adve_scheme", "implicit") != "pred_corr", "the Courant halo across slabs is not restated"
+        self.size, self.nx, self.dx = size, kw["nx"], kw["dx"]
+        self.slabs, self.n_x_bfr = [], []
+        for rank in range(size):
+            k = dict(kw)
+            bfr = rank * slab_nx(self.nx, 0, size)
+            k["nx"] = slab_nx(self.nx, rank, size)
+            k["x0"] = kw.get("x0", 0.) if rank == 0 else 0.
+            k["x1"] = k["nx"] * self.dx if rank != size - 1 else kw["x1"] - bfr * self.dx
+            k["n_sd_max"] = kw["n_sd_max"] // size + 1
+            p = Particles(**k)
+            p.distmem = True
+            self.slabs.append(p)
+            self.n_x_bfr.append(bfr)
+
+    def _cut(self, a, rank, ext=0):
+        return None if a is None else a[self.n_x_bfr[rank]: self.n_x_bfr[rank] + self.slabs[rank].nx + ext]
+
+    def init(self, th, rv, rhod, Cx=None, Cy=None, Cz=None):
+        for r, p in enumerate(self.slabs):
+            p.init(self._cut(th, r), self._cut(rv, r), self._cut(rhod, r), self._cut(Cx, r, 1), self._cut(Cy, r), self._cut(Cz, r))
+
+    def step_sync(self, th, rv, rhod=None, **kw):
+        out_th, out_rv = np.array(th, dtype=np.float64), np.array(rv, dtype=np.float64)
+        for r, p in enumerate(self.slabs):
+            t, q = p.step_sync(self._cut(th, r), self._cut(rv, r), self._cut(rhod, r) if rhod is not None else None, **kw)
+            a, b = self.n_x_bfr[r], self.n_x_bfr[r] + p.nx
+            out_th[a:b], out_rv[a:b] = t.reshape(out_th[a:b].shape), q.reshape(out_rv[a:b].shape)
+        return out_th, out_rv
+
+    def step_async(self, rcyc=False, **kw):
+        n_coll = sum(p.step_async(**kw) for p in self.slabs)
+        names = ("n", "rd3", "rw2", "kpa", "vt", "x", "y", "z", "rc2")
+        size = self.size
+        # what every slab sends: copies of the attributes of its leavers with x already in the receiver's coordinates
+        out = []
+        for r, p in enumerate(self.slabs):
+            lft, rgt = self.slabs[(r - 1) % size], self.slabs[(r + 1) % size]
+            batch = {}
+            for side, ids, shift in (("lft", p.lft_id, lambda x: lft.x1 + x - p.x0), ("rgt", p.rgt_id, lambda x: rgt.x0 + x - p.x1)):
+                b = {nm: getattr(p, nm)[ids].copy() for nm in names if getattr(p, nm).size}
+                b["x"] = shift(b["x"])
+                if hasattr(p, "pp"):
+                    b["pp"] = {k: v[ids].copy() for k, v in p.pp.items()}
+                batch[side] = b
+            out.append(batch)
+        for r, p in enumerate(self.slabs):
+            tol = self.BCOND_TOLERANCE
+            for src, side in (((r + 1) % size, "lft"), ((r - 1) % size, "rgt")):     # from the right neighbour first, then from the left
+                b = out[src][side]
+                x = b["x"]
+                x = np.where(x >= p.x1, x - tol, np.where(x < p.x0, x + tol, x))     # tolerance_away_from_bcond
+                if side == "lft":
+                    x = np.where(x == p.x1, np.nextafter(x, 0.), x)
+                b = dict(b, x=x)
+                for nm in names:
+                    if getattr(p, nm).size or nm in b:
+                        if nm in b:
+                            setattr(p, nm, np.concatenate([getattr(p, nm), b[nm]]))
+                if hasattr(p, "pp"):
+                    p.pp = {k: np.concatenate([v, b["pp"][k]]) for k, v in p.pp.items()}
+            p.n[p.lft_id] = 0                            # flag_lft / flag_rgt: the senders' copies are removed by post_copy
+            p.n[p.rgt_id] = 0
+            p.n_part = p.n.size
+        for p in self.slabs:
+            p.post_copy(rcyc)
+        return n_coll
+
+    def per_cell(self, fun):
+        """concatenates a per-cell diagnostic of the slabs into the global (nx, ny, nz) order"""
+        return np.concatenate([np.asarray(fun(p)).reshape(p.nx, max(1, p.ny), max(1, p.nz)) for p in self.slabs], axis=0)
