@@ -198,7 +198,16 @@ def run_reference(args):
     else:
         os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     cores = int(os.environ["OMP_NUM_THREADS"])           # the threads the OpenMP back-end will really use
-    ref = S.oracle_library()
+    # timing uses the build with the reference's own release optimisation (-Ofast, oracle/build_ref.py) when it is there and loads;
+    # the IEEE-strict -O2 build that the parity tests use otherwise
+    fast = os.path.join(ROOT, "oracle", "_ref", "liblgrngn_ref_fast.so")
+    ref, flags = None, "-O2"
+    if os.path.exists(fast) and not args.ref_strict:
+        probe = subprocess.run([sys.executable, "-c", "import ctypes; ctypes.CDLL(%r)" % fast], capture_output=True)
+        if probe.returncode == 0:
+            ref, flags = L.Library(fast), "-Ofast"
+    if ref is None:
+        ref = S.oracle_library()
     nx, ny, nz = args.ref_nx, args.ref_ny, args.ref_nz
     oi, o, f = make_case(ref, nx, ny, nz, args.sd_conc)
     p = ref.factory(L.backend_t.OpenMP, oi)
@@ -217,7 +226,7 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "cfg4-shaped 3-D box %dx%dx%d cells x %d SD/cell (bounded sample of the 64x256x128 slab), hall_davis_no_waals, beard77fast, implicit adve" % (nx, ny, nz, args.sd_conc)},
         "cpu_baseline": {"value": v, "unit": "SD-updates/s", "cores": cores, "kind": "reference",
-                         "sample": "%dx%dx%d cells x %d SD/cell = %.3g SDs, %d steps, reference OpenMP back-end (-O2)" % (nx, ny, nz, args.sd_conc, n_sd, args.steps)},
+                         "sample": "%dx%dx%d cells x %d SD/cell = %.3g SDs, %d steps, reference OpenMP back-end (%s)" % (nx, ny, nz, args.sd_conc, n_sd, args.steps, flags)},
         "e2e": {"value": v, "unit": "SD-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -424,6 +433,7 @@ def main():
     ap.add_argument("--ref-nz", type=int, default=64)
     ap.add_argument("--profile-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-strict", action="store_true", help="time the IEEE-strict -O2 build of the reference instead of its -Ofast build")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -56,33 +56,45 @@ def newest_input():
     return t
 
 
-def build(force=False, verbose=True):
+# A second build of the same sources with the optimisation flags of the reference's own portable release configuration
+# (CMakeLists.txt:126, RelWithDebInfoPortable: -Ofast; the default Release adds -march=native, which would tie the library to the
+# CPU of the build container).  TIMING ONLY: bench.py's CPU baseline uses it so that the reference is not handicapped by the
+# IEEE-strict flags the parity oracle needs; no test compares results of this library.
+LIB_FAST = os.path.join(OUT, "liblgrngn_ref_fast.so")
+FAST_FLAGS = ["-Ofast", "-DNDEBUG"]
+
+
+def build(force=False, verbose=True, fast=False):
+    lib = LIB_FAST if fast else LIB
+    out = os.path.join(OUT, "fast") if fast else OUT
+    base = [f for f in BASE if f not in ("-O2", "-DNDEBUG", "-ffp-contract=off")] + FAST_FLAGS if fast else BASE
     if not os.path.isdir(os.path.join(REF, "src")):
-        if os.path.exists(LIB):
-            return LIB
-        raise RuntimeError("reference sources not found at %s and no prebuilt %s" % (REF, LIB))
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest_input():
-        return LIB
-    os.makedirs(OUT, exist_ok=True)
+        if os.path.exists(lib):
+            return lib
+        raise RuntimeError("reference sources not found at %s and no prebuilt %s" % (REF, lib))
+    if not force and os.path.exists(lib) and os.path.getmtime(lib) >= newest_input():
+        return lib
+    os.makedirs(out, exist_ok=True)
 
     def compile_one(unit):
         obj, src, extra = unit
-        objp = os.path.join(OUT, obj)
+        objp = os.path.join(out, obj)
         if not force and os.path.exists(objp) and os.path.getmtime(objp) >= max(os.path.getmtime(src), 0):
             if not src.startswith(REPO) or os.path.getmtime(objp) >= newest_input():
                 return obj, 0.0
         t0 = time.time()
-        subprocess.run(BASE + extra + ["-c", src, "-o", objp], check=True)
+        subprocess.run(base + extra + ["-c", src, "-o", objp], check=True)
         return obj, time.time() - t0
 
     with ThreadPoolExecutor(max_workers=min(7, os.cpu_count() or 1)) as ex:
         for obj, dt in ex.map(compile_one, UNITS):
             if verbose:
-                print("[oracle] %-20s %6.1f s" % (obj, dt), flush=True)
-    subprocess.run([CXX, "-shared", "-fopenmp", "-o", LIB] + [os.path.join(OUT, u[0]) for u in UNITS]
+                print("[oracle%s] %-20s %6.1f s" % (" -Ofast" if fast else "", obj, dt), flush=True)
+    subprocess.run([CXX, "-shared", "-fopenmp", "-o", lib] + [os.path.join(out, u[0]) for u in UNITS]
                    + ["-Wl,-Bsymbolic", "-Wl,--exclude-libs,ALL"], check=True)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv))
+    print(build(force="--force" in sys.argv, fast=True))
