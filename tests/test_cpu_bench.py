@@ -36,3 +36,19 @@ def test_reference_arm_under_torchrun_only_rank0_works():
     assert r.returncode == 0, r.stderr[-2000:]
     d = check_line(r.stdout, 2)
     assert d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)      # torchrun's OMP_NUM_THREADS=1 is overridden for the one working rank
+
+
+def test_roofline_tables_cover_the_kernels_the_profile_names():
+    """the per-kernel roofline of bench.py maps profile names (with template arguments) to algorithmic bytes and to the DRAM traffic of
+    the committed ncu captures"""
+    sys.path.insert(0, ROOT)
+    import bench
+    for name, per_sd in (("(k_cond_range<M, false>)", 52.0), ("(k_cond_range<M, true>)", 52.0), ("(k_cond_cells<M>)", 48.0), ("k_gather", 136.0),
+                         ("k_coal_small", 76.0), ("k_transport<false>", 80.0), ("(k_vterm_beard77<true>)", 24.0), ("k_mv_count", 4.0)):
+        assert bench.kernel_bytes(name) == per_sd, name
+    for name in ("k_mv_counts", "k_scan_tiles", "k_radix_scatter", "k_cells_Tpr"):
+        assert bench.kernel_bytes(name) == 0.0, name          # per-cell / per-mover kernels carry no per-SD figure
+    for name in ("(k_cond_range<M, false>)", "k_gather", "k_transport<false>", "k_coal_small", "(k_vterm_beard77<true>)"):
+        t = bench.traffic_of(name, 1)
+        assert t is not None and 10. < t < 250., (name, t)
+    assert bench.peaks()[0] > 1000.
