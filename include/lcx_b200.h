@@ -93,7 +93,9 @@ typedef struct
   int mode;                   /* lcx_rng_mode_t                                                               */
   const uint32_t *un;         /* INJECT: host array, n_part entries, indexed by storage index (sid)           */
   const void *u01;            /* INJECT: host array of real, n_part entries, indexed by sorted position       */
-  uint64_t seed, call;        /* PHILOX: key and per-call counter                                             */
+  uint64_t seed, call;        /* PHILOX: key (low 32 bits used) and per-call counter                          */
+  uint32_t cell_base;         /* PHILOX: global index of this slab's first cell (streams differ between slabs) */
+  uint32_t stream;            /* PHILOX: second key word, e.g. the slab's rank                                 */
 } lcx_rng;
 
 typedef struct
@@ -135,7 +137,9 @@ int  lcx_n_part(lcx_engine *e, int64_t *n_part);
 int  lcx_set_dense_storage_index(lcx_engine *e, int always);
 /* copy one attribute to the host in reference storage order (sid); n is converted to real           */
 int  lcx_get_attr(lcx_engine *e, int attr, void *dst, int64_t cap, int64_t *n_out);   /* fill_outbuf.ipp:40-79 */
-int  lcx_get_attr_u64(lcx_engine *e, int attr, uint64_t *dst, int64_t cap, int64_t *n_out);
+int  lcx_get_attr_u64(lcx_engine *e, int attr, uint64_t *dst, int64_t cap, int64_t *n_out);   /* exact for n >= 2^53 */
+/* storage index and cell of every SD in PHYSICAL order (introspection for tests: which in-cell slot an SD occupies) */
+int  lcx_get_layout(lcx_engine *e, uint32_t *sid, uint32_t *ijk, int64_t cap, int64_t *n_out);
 
 /* ---- housekeeping passes ------------------------------------------------------------------------------ */
 int  lcx_hskpng_Tpr(lcx_engine *e);                             /* hskpng_Tpr.ipp:219-305                    */
@@ -179,18 +183,27 @@ int  lcx_transport(lcx_engine *e, const lcx_transport_opts *o);           /* adv
 int  lcx_puddle(lcx_engine *e, double out[14]);                           /* accumulated precipitation       */
 
 /* ---- x-slab migration (distributed memory) ------------------------------------------------------------- */
-/* compacts the SDs that left through the left / right face (ascending storage index), shifts x into   */
-/* the neighbour's coordinates and marks the local copies for removal.                                 */
-int  lcx_migr_pack(lcx_engine *e, int64_t *n_lft, int64_t *n_rgt);       /* bcnd.ipp:160-172, pack.ipp:30-121, unpack.ipp:122-145 */
-/* device pointers of the outgoing / incoming buffers: n (uint64[count]) and reals (attribute-major)   */
-int  lcx_migr_buffers(lcx_engine *e, int side, int incoming, void **n_buf, void **real_buf, int64_t *capacity);
-/* copy `count` packed migrants from the outgoing buffer `side` (0: left-movers, 1: right-movers) of `src` into the */
-/* matching incoming buffer of `dst` (device-to-device, peer copy over NVLink when the engines sit on different GPUs) */
-int  lcx_migr_send(lcx_engine *src, int side, lcx_engine *dst, int64_t count);   /* step_async_and_copy.ipp:76-84,110-118 */
+/* Every engine owns one inbox per side (0: left-movers arriving from the RIGHT neighbour, 1: right-movers arriving */
+/* from the LEFT neighbour): a single device allocation [2 headers | n x 2 | reals x 2] - two parities, so a sender may  */
+/* already deliver step s+1 while step s is being unpacked.  Senders write their packed migrants STRAIGHT into the        */
+/* neighbour's inbox (peer memory over NVLink: no staging buffer, no copy engine, no host in the data path) and then      */
+/* publish {count, sequence number} in its header.                                                                        */
+/*   lcx_migr_connect      neighbour engine in the same process (enables peer access when on another device)              */
+/*   lcx_migr_ipc_export / lcx_migr_ipc_connect   neighbour in another process: 64-byte CUDA IPC handle + capacity          */
+/*   lcx_migr_put          sorts the leavers found by lcx_transport by storage index (bcnd.ipp:160-172), packs them with x   */
+/*                         shifted into the neighbour's coordinates (pack.ipp:15-121), zeroes their local multiplicity       */
+/*                         (unpack.ipp:122-145) and publishes the headers; one host read-back (the two counts)               */
+/*   lcx_migr_take         waits for both neighbours' deliveries - same process: their stream event (pass the engines; the   */
+/*                         caller guarantees their lcx_migr_put has RETURNED, e.g. by a thread barrier); other process: pass  */
+/*                         NULL and the sequence number is awaited on the device - then appends the arrivals: right            */
+/*                         neighbour's first, then the left's (unpack.ipp:50-120, step_async_and_copy.ipp:100-190)              */
+enum { LCX_IPC_BLOB_BYTES = 96 };
+int  lcx_migr_connect(lcx_engine *e, int side, lcx_engine *neighbour);
+int  lcx_migr_ipc_export(lcx_engine *e, int side, void *blob);           /* inbox `side` of e                */
+int  lcx_migr_ipc_connect(lcx_engine *e, int side, const void *blob);    /* e's movers of `side` go there    */
+int  lcx_migr_put(lcx_engine *e, int64_t *n_lft, int64_t *n_rgt);
+int  lcx_migr_take(lcx_engine *e, lcx_engine *rgt_neighbour, lcx_engine *lft_neighbour, int64_t *n_from_rgt, int64_t *n_from_lft);
 int  lcx_migr_real_attrs(lcx_engine *e, int *count);                      /* number of real attributes sent  */
-/* append `count` arrivals found in the incoming buffer of `side` (0: sent by the right neighbour,   */
-/* 1: by the left neighbour); call for side 0 first                                                   */
-int  lcx_migr_unpack(lcx_engine *e, int side, int64_t count);            /* unpack.ipp:50-120               */
 
 /* ---- end of step: removal / recycling, cell index, per-cell grouping ------------------------------------ */
 /* keep_all != 0: initial grouping - nothing is removed and the cell indices given to lcx_sd_append are used */

@@ -98,7 +98,13 @@ lcx_engine::~lcx_engine()
   drw_mom3.release(); rw_mom3.release(); count_mom.release(); mom_partial.release();
   courant_x.release(); courant_y.release(); courant_z.release(); w_LS.release(); cell_off.release(); cell_off_new.release(); arr_off.release(); mv_scan.release();
   vt0.release(); eff.release(); hist.release(); scan_tmp.release();
-  for (int s = 0; s < 2; ++s) { for (int d = 0; d < 2; ++d) { mig_n[s][d].release(); mig_real[s][d].release(); } mig_key[s].release(); mig_val[s].release(); }
+  for (int s = 0; s < 2; ++s)
+  {
+    for (int d = 0; d < 2; ++d) { mig_key[s][d].release(); mig_val[s][d].release(); }
+    if (remote[s].ipc && remote[s].base) cudaIpcCloseMemHandle(remote[s].base);
+    inbox[s].release();
+  }
+  if (ev_put) cudaEventDestroy(ev_put);
   scalars.release(); red_partial.release(); cell_tmp4.release();
   for (auto &r : prof) { cudaEventDestroy(r.t0); cudaEventDestroy(r.t1); }
   if (timer0) { cudaEventDestroy(timer0); cudaEventDestroy(timer1); }
@@ -180,7 +186,8 @@ int lcx_create(const lcx_config *cfg, lcx_engine **out)
     g.halo_x = idx_t(g.n_dims == 1 ? g.halo_size : g.n_dims == 2 ? g.halo_size * g.nz : g.halo_size * g.nz * g.ny);
 
     const size_t cap = e->cap = size_t(cfg->n_sd_max);
-    { const char *lz = std::getenv("LCX_LAZY_GATHER"); e->lazy_gather = lz && lz[0] == '1'; }
+    // gather-on-read re-layout (lcx_engine.cuh): on unless LCX_LAZY_GATHER=0 (measured on the cfg4 slab: 16.6 -> 14.6 ms per step)
+    { const char *lz = std::getenv("LCX_LAZY_GATHER"); e->lazy_gather = !(lz && lz[0] == '0'); }
     e->sd[0].alloc(cap, g.nx, g.ny, g.nz);
     e->sd[1].alloc(cap, g.nx, g.ny, g.nz);
     if (cfg->exact_sstp_cond && cfg->allow_sstp_cond)
@@ -224,13 +231,17 @@ int lcx_create(const lcx_config *cfg, lcx_engine **out)
 
     if (cfg->bcond_lft == LCX_BCOND_DISTMEM || cfg->bcond_rgt == LCX_BCOND_DISTMEM)
     {
+      // one x-column's worth of capacity: with |C_x| <= 1 no more than that can cross a face in one step
       e->mig_cap = cap / nx1 + 4096;
       if (e->mig_cap > cap) e->mig_cap = cap;
-      int n_real = 0;
-      lcx_migr_real_attrs(e.get(), &n_real);
+      lcx_migr_real_attrs(e.get(), &e->mig_n_real);
       for (int s = 0; s < 2; ++s)
-        for (int d = 0; d < 2; ++d) { e->mig_n[s][d].alloc(e->mig_cap); e->mig_real[s][d].alloc(e->mig_cap * n_real); }
-      for (int s = 0; s < 2; ++s) { e->mig_key[s].alloc(e->mig_cap); e->mig_val[s].alloc(e->mig_cap); }
+      {
+        for (int d = 0; d < 2; ++d) { e->mig_key[s][d].alloc(e->mig_cap); e->mig_val[s][d].alloc(e->mig_cap); }
+        e->inbox[s].alloc(inbox_bytes(e->mig_cap, e->mig_n_real));
+        LCX_CUDA(cudaMemsetAsync(e->inbox[s].p, 0, MIG_HDR_BYTES, e->stream));
+      }
+      LCX_CUDA(cudaEventCreateWithFlags(&e->ev_put, cudaEventDisableTiming));
     }
 
     e->scalars.alloc(1);
@@ -400,11 +411,37 @@ int lcx_get_attr(lcx_engine *e, int attr, void *dst, int64_t cap, int64_t *n_out
 int lcx_get_attr_u64(lcx_engine *e, int attr, uint64_t *dst, int64_t cap, int64_t *n_out)
 {
   return guarded([&] {
-    std::vector<double> tmp(e->n_part);
-    int64_t n = 0;
-    if (lcx_get_attr(e, attr, tmp.data(), int64_t(tmp.size()), &n) != 0) throw lcx::error(g_last_error);
-    *n_out = n;
-    for (int64_t i = 0; i < n && i < cap; ++i) dst[i] = uint64_t(tmp[size_t(i)]);
+    use_device(e);
+    *n_out = int64_t(e->n_part);
+    if (e->n_part == 0) return;
+    static_assert(sizeof(lcx::real_t) >= 4, "");
+    const size_t cnt = size_t(cap) < e->n_part ? size_t(cap) : e->n_part;
+    if (attr == LCX_A_N && sizeof(lcx::real_t) == sizeof(uint64_t))
+    {
+      // multiplicities travel as 64-bit integers: no round trip through real_t (exact beyond 2^53)
+      lcx::scatter_n_by_sid(e, reinterpret_cast<uint64_t *>(e->tmp_real.p));
+      LCX_CUDA(cudaMemcpyAsync(dst, e->tmp_real.p, cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+      LCX_CUDA(cudaStreamSynchronize(e->stream));
+      return;
+    }
+    std::vector<lcx::real_t> tmp(e->n_part);
+    lcx::scatter_attr_by_sid(e, attr, e->tmp_real.p);
+    LCX_CUDA(cudaMemcpyAsync(tmp.data(), e->tmp_real.p, e->n_part * sizeof(lcx::real_t), cudaMemcpyDeviceToHost, e->stream));
+    LCX_CUDA(cudaStreamSynchronize(e->stream));
+    for (size_t i = 0; i < cnt; ++i) dst[i] = uint64_t(tmp[i]);
+  });
+}
+
+int lcx_get_layout(lcx_engine *e, uint32_t *sid, uint32_t *ijk, int64_t cap, int64_t *n_out)
+{
+  return guarded([&] {
+    use_device(e);
+    *n_out = int64_t(e->n_part);
+    const size_t cnt = size_t(cap) < e->n_part ? size_t(cap) : e->n_part;
+    if (cnt == 0) return;
+    if (sid) LCX_CUDA(cudaMemcpyAsync(sid, e->S().sid.p, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    if (ijk) LCX_CUDA(cudaMemcpyAsync(ijk, e->S().ijk.p, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    LCX_CUDA(cudaStreamSynchronize(e->stream));
   });
 }
 
@@ -471,34 +508,63 @@ int lcx_puddle(lcx_engine *e, double out[14])
   });
 }
 
-int lcx_migr_pack(lcx_engine *e, int64_t *n_lft, int64_t *n_rgt) { return guarded([&] { use_device(e); lcx::migr_pack(e, n_lft, n_rgt); }); }
+namespace
+{
+  struct ipc_blob { cudaIpcMemHandle_t handle; uint64_t cap; int32_t n_real; int32_t real_bytes; char pad[LCX_IPC_BLOB_BYTES - sizeof(cudaIpcMemHandle_t) - 16]; };
+  static_assert(sizeof(ipc_blob) == LCX_IPC_BLOB_BYTES, "IPC blob layout");
+}
 
-int lcx_migr_buffers(lcx_engine *e, int side, int incoming, void **n_buf, void **real_buf, int64_t *capacity)
+int lcx_migr_connect(lcx_engine *e, int side, lcx_engine *nb)
 {
   return guarded([&] {
-    if (side < 0 || side > 1 || incoming < 0 || incoming > 1) throw lcx::error("lcx_migr_buffers: bad side / direction");
-    *n_buf = e->mig_n[side][incoming].p;
-    *real_buf = e->mig_real[side][incoming].p;
-    *capacity = int64_t(e->mig_cap);
+    if (side < 0 || side > 1) throw lcx::error("lcx_migr_connect: bad side");
+    if (!nb || !nb->inbox[side].p) throw lcx::error("lcx_migr_connect: the neighbour has no inbox on that side (not a distributed-memory slab)");
+    if (nb->mig_n_real != e->mig_n_real) throw lcx::error("lcx_migr_connect: neighbours carry different attribute sets");
+    LCX_CUDA(cudaSetDevice(e->device));
+    if (nb->device != e->device)
+    {
+      int can = 0;
+      LCX_CUDA(cudaDeviceCanAccessPeer(&can, e->device, nb->device));
+      if (!can) throw lcx::error("lcx_migr_connect: device " + std::to_string(e->device) + " cannot access device " + std::to_string(nb->device) + " (no peer-to-peer path)");
+      const cudaError_t st = cudaDeviceEnablePeerAccess(nb->device, 0);
+      if (st == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError(); else LCX_CUDA(st);
+    }
+    e->remote[side].base = nb->inbox[side].p; e->remote[side].cap = nb->mig_cap; e->remote[side].ipc = false;
   });
 }
 
-int lcx_migr_send(lcx_engine *src, int side, lcx_engine *dst, int64_t count)
+int lcx_migr_ipc_export(lcx_engine *e, int side, void *blob)
 {
   return guarded([&] {
-    if (count <= 0) return;
-    if (side < 0 || side > 1) throw lcx::error("lcx_migr_send: bad side");
-    if (size_t(count) > dst->mig_cap || size_t(count) > src->mig_cap) throw lcx::error("lcx_migr_send: migration buffer overflow");
-    int n_real = 0;
-    lcx_migr_real_attrs(src, &n_real);
-    use_device(src);
-    // on the sender's stream, after its pack kernel; the receiver waits for it before unpacking
-    LCX_CUDA(cudaMemcpyPeerAsync(dst->mig_n[side][1].p, dst->device, src->mig_n[side][0].p, src->device, size_t(count) * sizeof(lcx::n_t), src->stream));
-    LCX_CUDA(cudaMemcpyPeerAsync(dst->mig_real[side][1].p, dst->device, src->mig_real[side][0].p, src->device,
-                                 size_t(count) * size_t(n_real) * sizeof(lcx::real_t), src->stream));
-    LCX_CUDA(cudaStreamSynchronize(src->stream));
+    if (side < 0 || side > 1 || !e->inbox[side].p) throw lcx::error("lcx_migr_ipc_export: no inbox on that side");
+    LCX_CUDA(cudaSetDevice(e->device));
+    ipc_blob b;
+    std::memset(&b, 0, sizeof(b));
+    LCX_CUDA(cudaIpcGetMemHandle(&b.handle, e->inbox[side].p));
+    b.cap = e->mig_cap; b.n_real = e->mig_n_real; b.real_bytes = int32_t(sizeof(lcx::real_t));
+    std::memcpy(blob, &b, sizeof(b));
   });
 }
+
+int lcx_migr_ipc_connect(lcx_engine *e, int side, const void *blob)
+{
+  return guarded([&] {
+    if (side < 0 || side > 1) throw lcx::error("lcx_migr_ipc_connect: bad side");
+    ipc_blob b;
+    std::memcpy(&b, blob, sizeof(b));
+    if (b.n_real != e->mig_n_real || b.real_bytes != int32_t(sizeof(lcx::real_t))) throw lcx::error("lcx_migr_ipc_connect: neighbours carry different attribute sets");
+    LCX_CUDA(cudaSetDevice(e->device));
+    void *ptr = nullptr;
+    LCX_CUDA(cudaIpcOpenMemHandle(&ptr, b.handle, cudaIpcMemLazyEnablePeerAccess));
+    if (e->remote[side].ipc && e->remote[side].base) cudaIpcCloseMemHandle(e->remote[side].base);
+    e->remote[side].base = static_cast<unsigned char *>(ptr); e->remote[side].cap = size_t(b.cap); e->remote[side].ipc = true;
+  });
+}
+
+int lcx_migr_put(lcx_engine *e, int64_t *n_lft, int64_t *n_rgt) { return guarded([&] { use_device(e); lcx::migr_put(e, n_lft, n_rgt); }); }
+
+int lcx_migr_take(lcx_engine *e, lcx_engine *rgt, lcx_engine *lft, int64_t *n_from_rgt, int64_t *n_from_lft)
+{ return guarded([&] { use_device(e); lcx::migr_take(e, rgt, lft, n_from_rgt, n_from_lft); }); }
 
 int lcx_migr_real_attrs(lcx_engine *e, int *count)
 {
@@ -506,8 +572,6 @@ int lcx_migr_real_attrs(lcx_engine *e, int *count)
   if (e->cfg.exact_sstp_cond && e->cfg.allow_sstp_cond) *count += (e->cfg.const_p ? 4 : 3) + (e->cfg.sstp_cond_act > 1 ? 1 : 0);
   return 0;
 }
-
-int lcx_migr_unpack(lcx_engine *e, int side, int64_t count) { return guarded([&] { use_device(e); lcx::migr_unpack(e, side, count); }); }
 
 int lcx_post_copy(lcx_engine *e, int rcyc, int keep_all) { return guarded([&] { use_device(e); lcx::post_copy(e, rcyc != 0, keep_all != 0); }); }
 

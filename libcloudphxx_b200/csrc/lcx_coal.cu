@@ -50,19 +50,20 @@ namespace lcx
       const uint32_t *un;     // device copy of the injected integer stream (by storage index)
       const real_t *u01;      // device copy of the injected [0,1) stream (by sorted position)
       uint64_t seed, call;
+      uint32_t cell_base, stream;   // global index of the slab's first cell; second key word (slab rank): slabs draw different streams
 
       __device__ __forceinline__ uint32_t get_un(uint32_t sid) const
       {
         if (mode == LCX_RNG_INJECT) return un[sid];
         uint32_t c[4] = {sid, 0u, uint32_t(call), uint32_t(call >> 32)};
-        philox4x32_10(c, philox_key{uint32_t(seed), uint32_t(seed >> 32)});
+        philox4x32_10(c, philox_key{uint32_t(seed), stream});
         return c[0];
       }
       __device__ __forceinline__ real_t get_u01(uint32_t pos) const
       {
         if (mode == LCX_RNG_INJECT) return u01[pos];
         uint32_t c[4] = {pos, 1u, uint32_t(call), uint32_t(call >> 32)};
-        philox4x32_10(c, philox_key{uint32_t(seed), uint32_t(seed >> 32)});
+        philox4x32_10(c, philox_key{uint32_t(seed), stream});
         const uint64_t bits = (uint64_t(c[0]) << 21) ^ (uint64_t(c[1]) >> 11);      // 53-bit mantissa from two words, [0,1)
         return real_t(bits & ((1ull << 53) - 1)) * real_t(1.0 / 9007199254740992.0);
       }
@@ -157,8 +158,8 @@ namespace lcx
 
     __device__ __forceinline__ void philox_cell_block(const rng_src &rng, uint32_t c, uint32_t q, uint32_t (&w)[4])
     {
-      w[0] = c; w[1] = q; w[2] = uint32_t(rng.call); w[3] = uint32_t(rng.call >> 32);
-      philox4x32_10(w, philox_key{uint32_t(rng.seed), uint32_t(rng.seed >> 32)});
+      w[0] = rng.cell_base + c; w[1] = q; w[2] = uint32_t(rng.call); w[3] = uint32_t(rng.call >> 32);
+      philox4x32_10(w, philox_key{uint32_t(rng.seed), rng.stream});
     }
 
     __device__ __forceinline__ real_t u01_from_words(uint32_t w0, uint32_t w1)      // 53-bit mantissa from two words, [0,1)
@@ -304,6 +305,7 @@ namespace lcx
 
     rng_src rng;
     rng.mode = r->mode; rng.un = nullptr; rng.u01 = nullptr; rng.seed = r->seed; rng.call = r->call;
+    rng.cell_base = r->cell_base; rng.stream = r->stream;
     if (r->mode == LCX_RNG_INJECT)
     {
       if (!r->un || !r->u01) throw error("lcx_coal: injected random streams are missing");

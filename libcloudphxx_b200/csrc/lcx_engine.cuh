@@ -101,9 +101,9 @@ namespace lcx
   {
     unsigned int n_part;            // live SDs after the last lcx_post_copy
     unsigned int max_count;         // largest per-cell SD count
-    unsigned int n_lft, n_rgt;      // migrants found by the last lcx_migr_pack
+    unsigned int n_lft, n_rgt;      // SDs that left through the left / right face in the last lcx_transport
     unsigned int increase_sstp_coal;
-    unsigned int pad;
+    unsigned int mig_timeout;       // a neighbour's delivery did not arrive (cross-process wait gave up)
     unsigned long long n_collisions, n_pairs_collided;
     double puddle[8];               // liq_vol, dry_vol, liq_num, prtcl_num (+spare), accumulated
     unsigned long long rcyc_zero, rcyc_one, rcyc_max;   // SDs with n == 0, with n == 1, largest n (recycling)
@@ -156,14 +156,14 @@ struct lcx_engine
   lcx::dbuf<lcx::real_t> drw_mom3, rw_mom3, count_mom, mom_partial;
   lcx::dbuf<lcx::real_t> cell_tmp4;        // 4 reals per cell: per-cell parts of the Beard (1977) fall-speed correction
   lcx::dbuf<lcx::real_t> courant_x, courant_y, courant_z, w_LS;
-  // Gather-on-read (opt-in, LCX_LAZY_GATHER=1): after a re-layout only sid and the per-particle records are moved at once.  The
+  // Gather-on-read (default; LCX_LAZY_GATHER=0 restores the eager gather): after a re-layout only sid and the per-particle records are moved at once.  The
   // other attributes of the live SDs stay in the OLD buffer set A() with pending_perm[new position] = old position until their
   // first consumer, which reads them through the permutation and writes them into S():
   //   PENDING_ATTR  n, rd3, rw2, kpa, vt  - the condensation kernel (FP64-bound, 7 % of the DRAM bandwidth: free of charge);
   //   PENDING_XYZ   x, y, z               - the transport kernel (nothing reads positions before it).
   // Every other consumer first runs finish_pending() for what it needs.
   enum { PENDING_ATTR = 1u, PENDING_XYZ = 2u };
-  bool lazy_gather = false;
+  bool lazy_gather = true;
   unsigned pending = 0;
   lcx::dbuf<uint32_t> pending_perm;
   size_t n_grouped = 0;          // SDs [0, n_grouped) still lie in the segments described by cell_off / ijk of the last re-layout
@@ -177,11 +177,15 @@ struct lcx_engine
   // radix-sort / scan scratch
   lcx::dbuf<uint32_t> hist, scan_tmp;
 
-  // migration buffers: [side][incoming]
-  lcx::dbuf<lcx::n_t> mig_n[2][2];
-  lcx::dbuf<lcx::real_t> mig_real[2][2];
-  lcx::dbuf<uint32_t> mig_key[2], mig_val[2];
+  // x-slab migration (include/lcx_b200.h): lists of leavers per side (storage index, physical index; ping-pong for the sort),
+  // this engine's inboxes and the neighbours' inboxes it delivers into
+  lcx::dbuf<uint32_t> mig_key[2][2], mig_val[2][2];
   size_t mig_cap = 0;
+  int mig_n_real = 0;
+  lcx::dbuf<unsigned char> inbox[2];
+  struct mig_remote { unsigned char *base = nullptr; size_t cap = 0; bool ipc = false; } remote[2];
+  cudaEvent_t ev_put = nullptr;
+  unsigned mig_seq = 0;
   size_t keys_ready = 0;         // key[0] / val[0] already hold the re-layout sort keys of SDs [0, keys_ready) (written by k_transport)
 
   lcx::dbuf<lcx::dev_scalars> scalars;
@@ -218,6 +222,7 @@ namespace lcx
   void post_copy(lcx_engine *e, bool rcyc, bool keep_all);
   void finish_pending(lcx_engine *e, unsigned what = 3u);      // completes (the named parts of) a gather-on-read re-layout
   void scatter_attr_by_sid(lcx_engine *e, int attr, real_t *dst);
+  void scatter_n_by_sid(lcx_engine *e, uint64_t *dst);
   void densify_sid(lcx_engine *e);
 
   // ---- lcx_cells.cu ----------------------------------------------------------------------------------
@@ -257,8 +262,17 @@ namespace lcx
 
   // ---- lcx_transport.cu ------------------------------------------------------------------------------
   void transport(lcx_engine *e, const lcx_transport_opts *o);
-  void migr_pack(lcx_engine *e, int64_t *n_lft, int64_t *n_rgt);
-  void migr_unpack(lcx_engine *e, int side, int64_t count);
+  void migr_put(lcx_engine *e, int64_t *n_lft, int64_t *n_rgt);
+  void migr_take(lcx_engine *e, lcx_engine *rgt, lcx_engine *lft, int64_t *n_from_rgt, int64_t *n_from_lft);
+
+  // layout of an inbox allocation: 256 bytes of headers (one per parity), then n[2][cap], then real[2][n_real][cap]
+  struct mig_hdr { unsigned int count, seq, pad0, pad1; };
+  constexpr size_t MIG_HDR_BYTES = 256;
+  inline size_t inbox_bytes(size_t cap, int n_real) { return MIG_HDR_BYTES + 2 * cap * (sizeof(n_t) + size_t(n_real) * sizeof(real_t)); }
+  inline mig_hdr *box_hdr(unsigned char *b, int parity) { return reinterpret_cast<mig_hdr *>(b) + parity; }
+  inline n_t *box_n(unsigned char *b, size_t cap, int parity) { return reinterpret_cast<n_t *>(b + MIG_HDR_BYTES) + size_t(parity) * cap; }
+  inline real_t *box_real(unsigned char *b, size_t cap, int n_real, int parity)
+  { return reinterpret_cast<real_t *>(b + MIG_HDR_BYTES + 2 * cap * sizeof(n_t)) + size_t(parity) * cap * size_t(n_real); }
 
   real_t *attr_ptr(lcx_engine *e, int attr);
 }

@@ -116,6 +116,17 @@ namespace lcx
       if (t < n) dst[sid[t]] = real_t(src[t]);
     }
 
+    __global__ void __launch_bounds__(TPB) k_scatter_n_by_sid(size_t n, const idx_t *__restrict__ sid, const n_t *__restrict__ src, uint64_t *__restrict__ dst)
+    {
+      const size_t t = size_t(blockIdx.x) * TPB + threadIdx.x;
+      if (t < n) dst[sid[t]] = uint64_t(src[t]);
+    }
+    __global__ void __launch_bounds__(TPB) k_iota(size_t n, uint32_t *__restrict__ val)
+    {
+      const size_t t = size_t(blockIdx.x) * TPB + threadIdx.x;
+      if (t < n) val[t] = uint32_t(t);
+    }
+
     // ---- recycling (rcyc.ipp:44-139) --------------------------------------------------------------------------------
     __global__ void __launch_bounds__(TPB) k_rcyc_stats(size_t n, const n_t *__restrict__ ns, dev_scalars *sc)
     {
@@ -373,6 +384,7 @@ namespace lcx
     sd_arrays &a = e->A();
     const uint32_t *sorted_keys = nullptr;     // full-sort path only: the gather takes the cell index from them
     bool gather_queued = false;
+    size_t keyed_by_transport = 0;             // k_transport writes keys only: the identity permutation is made when the full sort needs it
 
     if (n_old == 0)
     {
@@ -389,6 +401,7 @@ namespace lcx
       const size_t first = e->keys_ready <= n_old ? e->keys_ready : 0;
       if (first < n_old)
         LCX_LAUNCH(e, k_make_keys, div_up(n_old - first, TPB), TPB, 0, first, n_old, g, s.n.p, s.rw2.p, s.x.p, s.y.p, s.z.p, e->key[0].p, e->val[0].p);
+      keyed_by_transport = first;
     }
     e->keys_ready = 0;
 
@@ -397,6 +410,7 @@ namespace lcx
     if (!keep_all && relayout_movers(e, n_old)) perm = e->val[0].p;
     else
     {
+      if (keyed_by_transport) LCX_LAUNCH(e, k_iota, div_up(keyed_by_transport, TPB), TPB, 0, keyed_by_transport, e->val[0].p);
       const int res = radix_sort_pairs(e, n_old, 0, bit_length(g.n_cell) + g.class_bits, 0);
       compute_cell_offsets(e, e->key[res].p, n_old);
       perm = e->val[res].p;
@@ -480,6 +494,14 @@ namespace lcx
     }
     e->sid_hi = n;
     e->sid_dense = true;
+  }
+
+  void scatter_n_by_sid(lcx_engine *e, uint64_t *dst)
+  {
+    const size_t n = e->n_part;
+    if (n == 0) return;
+    densify_sid(e);
+    LCX_LAUNCH(e, k_scatter_n_by_sid, div_up(n, TPB), TPB, 0, n, e->S().sid.p, e->S().n.p, dst);
   }
 
   void scatter_attr_by_sid(lcx_engine *e, int attr, real_t *dst)

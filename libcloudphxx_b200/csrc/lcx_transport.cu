@@ -107,6 +107,10 @@ namespace lcx
 #ifndef LCX_TR_MINB
 #define LCX_TR_MINB 6      // latency-bound kernel: 40 registers, 48 resident warps; measured best of {3,4,5,6}
 #endif
+    // leavers through a slab face are listed on the fly (bcnd.ipp:160-172 does two copy_if sweeps): storage index as the later
+    // sort key, physical index as the value; the lists are unordered (atomic slots) until lcx_migr_put sorts them
+    struct mig_lists { const idx_t *sid; uint32_t *key[2], *val[2]; unsigned int *count[2]; unsigned cap; };
+
     // LAZY: positions still lie in the previous layout (lcx_engine::PENDING_XYZ): read through the permutation, written in place
     template <bool LAZY>
     __global__ void __launch_bounds__(TPB, LCX_TR_MINB) k_transport(size_t n_part, tr_params P,
@@ -114,10 +118,10 @@ namespace lcx
                                                       const real_t *__restrict__ vt, const idx_t *__restrict__ ijk, n_t *__restrict__ ns,
                                                       const real_t *__restrict__ rw2, const real_t *__restrict__ rd3,
                                                       const real_t *__restrict__ Cx, const real_t *__restrict__ Cy, const real_t *__restrict__ Cz,
-                                                      const real_t *__restrict__ w_LS, uint32_t *__restrict__ flag, double *__restrict__ partial,
-                                                      uint32_t *__restrict__ key, uint32_t *__restrict__ val,
+                                                      const real_t *__restrict__ w_LS, double *__restrict__ partial,
+                                                      uint32_t *__restrict__ key,
                                                       const uint32_t *__restrict__ perm, const real_t *__restrict__ xi, const real_t *__restrict__ yi,
-                                                      const real_t *__restrict__ zi)
+                                                      const real_t *__restrict__ zi, mig_lists M)
     {
       __shared__ double red[4][TPB / 32];
       const grid_t &g = P.g;
@@ -241,7 +245,11 @@ namespace lcx
         if (g.ny) ys[t] = y;
         if (g.nz) zs[t] = z;
         ns[t] = n;
-        flag[t] = fl;
+        if (fl)
+        {
+          const unsigned slot = atomicAdd(M.count[fl - 1], 1u);
+          if (slot < M.cap) { M.key[fl - 1][slot] = M.sid[t]; M.val[fl - 1][slot] = uint32_t(t); }     // overflow is reported by lcx_migr_put
+        }
         // sort key of the coming re-layout (hskpng_ijk of post_copy): new cell, or n_cell for SDs that are gone;
         // migrants leave through lcx_migr_pack, which zeroes their multiplicity and re-keys them
         uint32_t kx = relayout_dead_key(g);
@@ -252,8 +260,7 @@ namespace lcx
           if (cell >= g.n_cell) cell = g.n_cell - 1;
           kx = relayout_key(g, cell, g.class_bits ? rw2[t] : real_t(0));
         }
-        key[t] = kx;
-        val[t] = uint32_t(t);
+        key[t] = kx;      // the identity permutation that goes with the keys is only written when the full sort needs it (lcx_layout.cu)
       }
 
       // deterministic block sums of the precipitation terms (second pass: k_puddle_final)
@@ -290,19 +297,10 @@ namespace lcx
     }
 
     // ---- migration ---------------------------------------------------------------------------------------
-    __global__ void __launch_bounds__(TPB) k_mig_collect(size_t n_part, uint32_t which, const uint32_t *__restrict__ flag, const idx_t *__restrict__ sid,
-                                                        uint32_t *__restrict__ key, uint32_t *__restrict__ val, unsigned int *counter, unsigned cap)
-    {
-      const size_t t = size_t(blockIdx.x) * TPB + threadIdx.x;
-      if (t >= n_part || flag[t] != which) return;
-      const unsigned slot = atomicAdd(counter, 1u);
-      if (slot >= cap) return;     // overflow is reported by the host from the counter
-      key[slot] = sid[t];          // order is fixed afterwards by sorting on the storage index
-      val[slot] = uint32_t(t);
-    }
-
     struct mig_attrs { const real_t *src[12]; int n; int x_slot; };
 
+    // Packs the leavers of one side STRAIGHT into the neighbour's inbox (out_n / out_real may be peer memory: plain coalesced
+    // 8-byte stores over NVLink), attribute-major like the reference's buffers (pack.ipp:37-46,77-86).
     __global__ void __launch_bounds__(TPB) k_mig_pack(unsigned count, const uint32_t *__restrict__ val, mig_attrs A, n_t *__restrict__ ns,
                                                      real_t lcl, real_t rmt, n_t *__restrict__ out_n, real_t *__restrict__ out_real)
     {
@@ -317,6 +315,35 @@ namespace lcx
         out_real[size_t(a) * count + jx] = v;
       }
       ns[ph] = 0;                                             // flag_lft / flag_rgt: unpack.ipp:122-145 (its sort key already says "gone")
+    }
+
+    // publishes a delivery: the data written by the kernels before this one on the same stream are made visible system-wide
+    // first, then {count, seq} appear in the receiver's header
+    __global__ void k_mig_signal(mig_hdr *hdr, unsigned count, unsigned seq)
+    {
+      hdr->count = count;
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned int *>(&hdr->seq) = seq;
+      __threadfence_system();
+    }
+
+    // waits (on the device) until the deliveries with sequence number `seq` have been published in this engine's own inbox
+    // headers; only used when the neighbour lives in another process (other GPU: its progress does not depend on this stream).
+    // Gives up after ~20 s instead of hanging the GPU.
+    __global__ void k_mig_wait(const mig_hdr *h0, const mig_hdr *h1, unsigned seq, dev_scalars *sc)
+    {
+      const long long t0 = clock64();
+      for (int q = 0; q < 2; ++q)
+      {
+        const mig_hdr *h = q == 0 ? h0 : h1;
+        if (!h) continue;
+        while (*reinterpret_cast<const volatile unsigned int *>(&h->seq) != seq)
+        {
+          __nanosleep(200);
+          if (clock64() - t0 > 40000000000ll) { sc->mig_timeout = 1u; return; }
+        }
+      }
+      __threadfence_system();
     }
 
     struct mig_dst { real_t *dst[12]; int n; int x_slot; };
@@ -374,70 +401,121 @@ namespace lcx
     static const int ctas_per_sm = [] { const char *v = std::getenv("LCX_TR_CTAS"); return v ? std::atoi(v) : 48; }();
     const unsigned blocks = unsigned(ctas_per_sm > 0 ? std::min<size_t>(div_up(n, TPB), size_t(148) * ctas_per_sm) : div_up(n, TPB));
     if (e->red_partial.n < size_t(blocks) * 4) { LCX_CUDA(cudaStreamSynchronize(e->stream)); e->red_partial.alloc(size_t(blocks) * 4 + 1024); }
+    mig_lists M = {};
+    M.sid = s.sid.p; M.cap = unsigned(e->mig_cap);
+    M.count[0] = &e->scalars.p->n_lft; M.count[1] = &e->scalars.p->n_rgt;
+    for (int sd = 0; sd < 2; ++sd) { M.key[sd] = e->mig_key[sd][0].p; M.val[sd] = e->mig_val[sd][0].p; }
+    if (P.bcond_lft == LCX_BCOND_DISTMEM || P.bcond_rgt == LCX_BCOND_DISTMEM)
+      LCX_CUDA(cudaMemsetAsync(&e->scalars.p->n_lft, 0, 2 * sizeof(unsigned int), e->stream));
     if (e->pending & lcx_engine::PENDING_XYZ)
     {
       sd_arrays &o2 = e->A();
       e->pending &= ~unsigned(lcx_engine::PENDING_XYZ);
       LCX_LAUNCH(e, k_transport<true>, blocks, TPB, 0, n, P, s.x.p, s.y.p, s.z.p, s.vt.p, s.ijk.p, s.n.p, s.rw2.p, s.rd3.p,
-                 e->courant_x.p, e->courant_y.p, e->courant_z.p, e->w_LS.p, e->flag.p, e->red_partial.p, e->key[0].p, e->val[0].p,
-                 e->pending_perm.p, o2.x.p, o2.y.p, o2.z.p);
+                 e->courant_x.p, e->courant_y.p, e->courant_z.p, e->w_LS.p, e->red_partial.p, e->key[0].p,
+                 e->pending_perm.p, o2.x.p, o2.y.p, o2.z.p, M);
     }
     else
       LCX_LAUNCH(e, k_transport<false>, blocks, TPB, 0, n, P, s.x.p, s.y.p, s.z.p, s.vt.p, s.ijk.p, s.n.p, s.rw2.p, s.rd3.p,
-                 e->courant_x.p, e->courant_y.p, e->courant_z.p, e->w_LS.p, e->flag.p, e->red_partial.p, e->key[0].p, e->val[0].p,
-                 nullptr, nullptr, nullptr, nullptr);
+                 e->courant_x.p, e->courant_y.p, e->courant_z.p, e->w_LS.p, e->red_partial.p, e->key[0].p,
+                 nullptr, nullptr, nullptr, nullptr, M);
     e->keys_ready = n;      // key[0] / val[0] hold the sort keys of SDs [0, n)
     if (e->grid.n_dims > 1 && !e->cfg.periodic_topbot_walls)
       LCX_LAUNCH(e, k_puddle_final, 1, TPB, 0, blocks, e->red_partial.p, e->scalars.p);
     e->grouped = false;   // positions changed: cell segments are stale until lcx_post_copy
   }
 
-  void migr_pack(lcx_engine *e, int64_t *n_lft, int64_t *n_rgt)
+  // Sorts each side's leavers by storage index (the reference lists them in ascending SD index: bcnd.ipp:160-172), packs them
+  // into the neighbour's inbox and publishes the delivery.  One host read-back: the two counts.
+  void migr_put(lcx_engine *e, int64_t *n_lft, int64_t *n_rgt)
   {
-    const size_t n = e->n_part;
     sd_arrays &s = e->S();
     *n_lft = *n_rgt = 0;
-    if (n == 0) return;
-    for (int side = 0; side < 2; ++side)
+    const bool dm[2] = {e->cfg.bcond_lft == LCX_BCOND_DISTMEM, e->cfg.bcond_rgt == LCX_BCOND_DISTMEM};
+    if (!dm[0] && !dm[1]) return;
+    const unsigned seq = ++e->mig_seq;
+    const int parity = int(seq & 1u);
+    unsigned count[2] = {0, 0};
+    if (e->n_part)
     {
-      const int bc = side == 0 ? e->cfg.bcond_lft : e->cfg.bcond_rgt;
-      if (bc != LCX_BCOND_DISTMEM) continue;
-      unsigned int *counter = side == 0 ? &e->scalars.p->n_lft : &e->scalars.p->n_rgt;
-      LCX_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), e->stream));
-      uint32_t *mk[2] = {e->mig_key[0].p, e->mig_key[1].p}, *mv[2] = {e->mig_val[0].p, e->mig_val[1].p};
-      LCX_LAUNCH(e, k_mig_collect, div_up(n, TPB), TPB, 0, n, uint32_t(side + 1), e->flag.p, s.sid.p, mk[0], mv[0], counter, unsigned(e->mig_cap));
       LCX_CUDA(cudaMemcpyAsync(e->h_scalars, e->scalars.p, sizeof(dev_scalars), cudaMemcpyDeviceToHost, e->stream));
       LCX_CUDA(cudaStreamSynchronize(e->stream));
-      const unsigned count = side == 0 ? e->h_scalars->n_lft : e->h_scalars->n_rgt;
-      (side == 0 ? *n_lft : *n_rgt) = count;
-      if (count == 0) continue;
-      if (count > e->mig_cap) throw error("migration buffer overflow: " + std::to_string(count) + " super-droplets cross one slab face, capacity " + std::to_string(e->mig_cap));
-      int bits = 0; { uint64_t v = e->sid_hi ? e->sid_hi - 1 : 0; while (v) { ++bits; v >>= 1; } if (bits == 0) bits = 1; }
-      const int res = radix_sort_pairs(e, count, 0, bits, mk, mv, 0);
-      mig_attrs A; real_t *list[12];
-      A.n = fill_attr_list(e, list, &A.x_slot);
-      for (int a = 0; a < A.n; ++a) A.src[a] = list[a];
-      const real_t lcl = side == 0 ? e->grid.x0 : e->grid.x1;
-      const real_t rmt = side == 0 ? real_t(e->cfg.lft_x1) : real_t(e->cfg.rgt_x0);
-      LCX_LAUNCH(e, k_mig_pack, div_up(count, TPB), TPB, 0, count, mv[res], A, s.n.p, lcl, rmt, e->mig_n[side][0].p, e->mig_real[side][0].p);
+      count[0] = e->h_scalars->n_lft; count[1] = e->h_scalars->n_rgt;
     }
+    for (int side = 0; side < 2; ++side)
+    {
+      if (!dm[side]) { count[side] = 0; continue; }
+      lcx_engine::mig_remote &r = e->remote[side];
+      if (!r.base) throw error("lcx_migr_put: no neighbour connected on side " + std::to_string(side) + " (lcx_migr_connect / lcx_migr_ipc_connect)");
+      const unsigned cnt = count[side];
+      if (cnt > e->mig_cap || cnt > r.cap)
+        throw error("migration buffer overflow: " + std::to_string(cnt) + " super-droplets cross one slab face, capacity " + std::to_string(e->mig_cap < r.cap ? e->mig_cap : r.cap));
+      if (cnt)
+      {
+        uint32_t *mk[2] = {e->mig_key[side][0].p, e->mig_key[side][1].p}, *mv[2] = {e->mig_val[side][0].p, e->mig_val[side][1].p};
+        int bits = 0; { uint64_t v = e->sid_hi ? e->sid_hi - 1 : 0; while (v) { ++bits; v >>= 1; } if (bits == 0) bits = 1; }
+        const int res = radix_sort_pairs(e, cnt, 0, bits, mk, mv, 0);
+        mig_attrs A; real_t *list[12];
+        A.n = fill_attr_list(e, list, &A.x_slot);
+        for (int a = 0; a < A.n; ++a) A.src[a] = list[a];
+        const real_t lcl = side == 0 ? e->grid.x0 : e->grid.x1;
+        const real_t rmt = side == 0 ? real_t(e->cfg.lft_x1) : real_t(e->cfg.rgt_x0);
+        LCX_LAUNCH(e, k_mig_pack, div_up(cnt, TPB), TPB, 0, cnt, mv[res], A, s.n.p, lcl, rmt,
+                   box_n(r.base, r.cap, parity), box_real(r.base, r.cap, e->mig_n_real, parity));
+      }
+      LCX_LAUNCH(e, k_mig_signal, 1, 1, 0, box_hdr(r.base, parity), cnt, seq);
+    }
+    LCX_CUDA(cudaEventRecord(e->ev_put, e->stream));
+    *n_lft = count[0]; *n_rgt = count[1];
   }
 
-  void migr_unpack(lcx_engine *e, int side, int64_t count)
+  // Appends the arrivals: first the right neighbour's left-movers, then the left neighbour's right-movers, each in the
+  // sender's storage order (step_async_and_copy.ipp:100-190).  One host read-back: the two counts.
+  void migr_take(lcx_engine *e, lcx_engine *rgt, lcx_engine *lft, int64_t *n_from_rgt, int64_t *n_from_lft)
   {
-    if (count <= 0) return;
-    if (size_t(count) > e->mig_cap) throw error("migration buffer overflow on receive");
-    if (e->n_part + size_t(count) > e->cap)
-      throw error("n_sd_max (" + std::to_string(e->cap) + ") < n_part (" + std::to_string(e->n_part + size_t(count)) + ")");
+    *n_from_rgt = *n_from_lft = 0;
+    // inbox 0 is filled by the right neighbour, inbox 1 by the left one
+    const bool dm[2] = {e->cfg.bcond_rgt == LCX_BCOND_DISTMEM, e->cfg.bcond_lft == LCX_BCOND_DISTMEM};
+    if (!dm[0] && !dm[1]) return;
+    const unsigned seq = e->mig_seq;
+    const int parity = int(seq & 1u);
+    lcx_engine *nb[2] = {rgt, lft};
+    const mig_hdr *wait_for[2] = {nullptr, nullptr};
+    for (int q = 0; q < 2; ++q)
+    {
+      if (!dm[q]) continue;
+      if (nb[q]) { if (nb[q] != e) LCX_CUDA(cudaStreamWaitEvent(e->stream, nb[q]->ev_put, 0)); }
+      else wait_for[q] = box_hdr(e->inbox[q].p, parity);
+    }
+    if (wait_for[0] || wait_for[1])
+      LCX_LAUNCH(e, k_mig_wait, 1, 1, 0, wait_for[0], wait_for[1], seq, e->scalars.p);
+    mig_hdr h[2] = {};
+    for (int q = 0; q < 2; ++q)
+      if (dm[q]) LCX_CUDA(cudaMemcpyAsync(&h[q], box_hdr(e->inbox[q].p, parity), sizeof(mig_hdr), cudaMemcpyDeviceToHost, e->stream));
+    LCX_CUDA(cudaMemcpyAsync(e->h_scalars, e->scalars.p, sizeof(dev_scalars), cudaMemcpyDeviceToHost, e->stream));
+    LCX_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->h_scalars->mig_timeout) throw error("x-slab migration: a neighbour's delivery did not arrive within 20 s");
     sd_arrays &s = e->S();
-    mig_dst A; real_t *list[12];
-    A.n = fill_attr_list(e, list, &A.x_slot);
-    for (int a = 0; a < A.n; ++a) A.dst[a] = list[a];
-    if (e->sid_hi + size_t(count) > e->cap) densify_sid(e);
-    LCX_LAUNCH(e, k_mig_unpack, div_up(size_t(count), TPB), TPB, 0, unsigned(count), e->n_part, e->sid_hi, A, s.n.p, s.sid.p,
-               e->mig_n[side][1].p, e->mig_real[side][1].p, e->grid.x0, e->grid.x1, real_t(5e-4), int(side == 0));
-    e->n_part += size_t(count);
-    e->sid_hi += size_t(count);
-    e->grouped = false;
+    for (int q = 0; q < 2; ++q)
+    {
+      if (!dm[q]) continue;
+      if (h[q].seq != seq) throw error("x-slab migration: sequence mismatch (neighbours out of step: got " + std::to_string(h[q].seq) + ", expected " + std::to_string(seq) + ")");
+      const size_t count = h[q].count;
+      (q == 0 ? *n_from_rgt : *n_from_lft) = int64_t(count);
+      if (count == 0) continue;
+      if (count > e->mig_cap) throw error("migration buffer overflow on receive");
+      if (e->n_part + count > e->cap)
+        throw error("n_sd_max (" + std::to_string(e->cap) + ") < n_part (" + std::to_string(e->n_part + count) + ")");
+      mig_dst A; real_t *list[12];
+      A.n = fill_attr_list(e, list, &A.x_slot);
+      for (int a = 0; a < A.n; ++a) A.dst[a] = list[a];
+      if (e->sid_hi + count > e->cap) densify_sid(e);
+      LCX_LAUNCH(e, k_mig_unpack, div_up(count, TPB), TPB, 0, unsigned(count), e->n_part, e->sid_hi, A, s.n.p, s.sid.p,
+                 box_n(e->inbox[q].p, e->mig_cap, parity), box_real(e->inbox[q].p, e->mig_cap, e->mig_n_real, parity),
+                 e->grid.x0, e->grid.x1, real_t(5e-4), int(q == 0));
+      e->n_part += count;
+      e->sid_hi += count;
+      e->grouped = false;
+    }
   }
 }

@@ -1,6 +1,5 @@
-"""ctypes view of the parts of the engine C ABI (include/lcx_b200.h) that Python-side plumbing needs:
-device timers, the per-kernel profile, launch counters and the x-slab migration hooks used when one process
-drives one GPU (torchrun) and torch.distributed moves the migrant buffers over NCCL/NVLink.
+"""ctypes view of the parts of the engine C ABI (include/lcx_b200.h) that Python-side plumbing (bench.py, tests) needs:
+device timers, the per-kernel profile, launch counters, cell statistics.
 """
 import ctypes as C
 import os
@@ -26,10 +25,8 @@ def lib():
         l.lcx_n_part.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         l.lcx_sync.argtypes = [C.c_void_p]
         l.lcx_cell_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
-        l.lcx_migr_pack.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
-        l.lcx_migr_buffers.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
         l.lcx_migr_real_attrs.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
-        l.lcx_migr_unpack.argtypes = [C.c_void_p, C.c_int, C.c_int64]
+        l.lcx_puddle.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         l.lcx_coal_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         _lib = l
     return _lib
@@ -116,21 +113,12 @@ class Engine:
             out[name] = (int(launches), float(ms))
         return out
 
-    # ---- migration -------------------------------------------------------------------------------------------
-    def migr_pack(self):
-        a, b = C.c_int64(), C.c_int64()
-        check(self.l.lcx_migr_pack(self.h, C.byref(a), C.byref(b)))
-        return a.value, b.value
-
-    def migr_buffers(self, side, incoming):
-        n_buf, r_buf, cap = C.c_void_p(), C.c_void_p(), C.c_int64()
-        check(self.l.lcx_migr_buffers(self.h, side, int(incoming), C.byref(n_buf), C.byref(r_buf), C.byref(cap)))
-        return n_buf.value, r_buf.value, cap.value
-
     def migr_real_attrs(self):
         v = C.c_int()
         check(self.l.lcx_migr_real_attrs(self.h, C.byref(v)))
         return v.value
 
-    def migr_unpack(self, side, count):
-        check(self.l.lcx_migr_unpack(self.h, side, count))
+    def puddle(self):
+        out = (C.c_double * 14)()
+        check(self.l.lcx_puddle(self.h, out))
+        return list(out)

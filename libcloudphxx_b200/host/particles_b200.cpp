@@ -22,9 +22,15 @@
 
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <dlfcn.h>
+#include <exception>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <fstream>
 #include <iostream>
 #include <limits>
@@ -47,6 +53,7 @@ namespace libcloudphxx
           return LGRNGN_B200_RNG_PHILOX;
         }
         int g_rng_mode = initial_rng_mode();
+        int g_dense_sid = -1;          // -1: dense storage indices exactly when the random stream is injected; 0 / 1: forced
         lgrngn_b200_distmem g_distmem = {0, 1, -1., -1., 0};
 
         void chk(int rc) { if (rc != 0) throw std::runtime_error(std::string("libcloudph++ (B200 engine): ") + lcx_last_error()); }
@@ -103,6 +110,86 @@ namespace libcloudphxx
         return n_x_bfr;
       }
 
+      // One host thread per slab, kept for the life time of the particle system.  The reference's multi_CUDA spawns a
+      // std::thread per device in every API call (particles_multi_gpu_impl.ipp:208-227); here the threads persist and each
+      // call hands them one job.  Every slab's blocking points (read-backs of counts, field copies) then only stall its own
+      // thread, so the GPUs run concurrently.
+      class slab_workers
+      {
+        struct worker
+        {
+          std::thread th;
+          std::mutex m;
+          std::condition_variable cv;
+          std::function<void()> job;
+          bool has_job = false, quit = false, done = true;
+          std::exception_ptr err;
+        };
+        std::vector<std::unique_ptr<worker>> w;
+
+        static void loop(worker *k)
+        {
+          for (;;)
+          {
+            std::function<void()> job;
+            {
+              std::unique_lock<std::mutex> lk(k->m);
+              k->cv.wait(lk, [&] { return k->has_job || k->quit; });
+              if (k->quit) return;
+              job.swap(k->job);
+              k->has_job = false;
+            }
+            std::exception_ptr err;
+            try { job(); } catch (...) { err = std::current_exception(); }
+            {
+              std::lock_guard<std::mutex> lk(k->m);
+              k->err = err;
+              k->done = true;
+            }
+            k->cv.notify_all();
+          }
+        }
+
+        public:
+        explicit slab_workers(int n)
+        {
+          for (int i = 0; i < n; ++i)
+          {
+            w.emplace_back(new worker);
+            w.back()->th = std::thread(loop, w.back().get());
+          }
+        }
+        ~slab_workers()
+        {
+          for (auto &k : w)
+          {
+            { std::lock_guard<std::mutex> lk(k->m); k->quit = true; }
+            k->cv.notify_all();
+            k->th.join();
+          }
+        }
+        // runs f(d) for every slab d on that slab's thread; returns when all are done (= a barrier between phases);
+        // the first exception is re-thrown in the caller
+        template <class F>
+        void run(F f)
+        {
+          for (size_t d = 0; d < w.size(); ++d)
+          {
+            worker *k = w[d].get();
+            { std::lock_guard<std::mutex> lk(k->m); k->job = [f, d] { f(int(d)); }; k->has_job = true; k->done = false; k->err = nullptr; }
+            k->cv.notify_all();
+          }
+          std::exception_ptr first;
+          for (auto &k : w)
+          {
+            std::unique_lock<std::mutex> lk(k->m);
+            k->cv.wait(lk, [&] { return k->done; });
+            if (k->err && !first) first = k->err;
+          }
+          if (first) std::rethrow_exception(first);
+        }
+      };
+
       // ======================================================================================================
       // one x-slab on one device: the reference's particles_t<real_t, CUDA>
       // ======================================================================================================
@@ -131,8 +218,13 @@ namespace libcloudphxx
         int rng_mode;
         std::mt19937 engine;               // one generator per object, as src/detail/urand.hpp:24,57
         uint64_t philox_call = 0;
+        int slab_rank = 0;                 // position of this slab in the decomposition: second Philox key word
+        size_t philox_cell_base = 0;       // process-distributed runs: cells of the ranks before this one (n_cell_bfr stays 0 there)
         std::vector<uint32_t> un_host;
         std::vector<real_t> u01_host;
+        // caller-supplied streams for the next coalescence sub-steps (lgrngn_b200_inject_rng), consumed before anything is drawn
+        std::deque<std::pair<std::vector<uint32_t>, std::vector<real_t>>> injected;
+        bool dense_sid;
 
         // l2e[q] = element of the caller's array that feeds cell q; runs = the same map as maximal contiguous pieces.
         // Few runs (contiguous arrays: 1 for scalars, 3 for a Courant field with its periodic halo) are copied straight
@@ -176,6 +268,7 @@ namespace libcloudphxx
           allow_sstp_cond = oi.sstp_cond > 1 || oi.sstp_cond_act > 1;
           pure_const_multi = (oi.sd_conc == 0) && (oi.sd_const_multi > 0 || oi.dry_sizes.size() > 0);
           rng_mode = g_rng_mode;
+          dense_sid = g_dense_sid < 0 ? rng_mode == LGRNGN_B200_RNG_MT19937 : g_dense_sid != 0;
           engine.seed(oi.rng_seed);
           unsupported_options();
         }
@@ -386,7 +479,7 @@ namespace libcloudphxx
           std::vector<real_t> eff;
           if (oi.coal_switch) eff = init_kernel(c);
           chk(lcx_create(&c, &e));
-          chk(lcx_set_dense_storage_index(e, rng_mode == LGRNGN_B200_RNG_MT19937));
+          chk(lcx_set_dense_storage_index(e, dense_sid));
           if (!eff.empty()) chk(lcx_set_efficiencies(e, eff.data(), int64_t(eff.size())));
         }
 
@@ -845,14 +938,14 @@ namespace libcloudphxx
         }
 
         // device-resident variant of sync_in + step_cond: the fields of the previous step stay where they are
-        void step_resident(const opts_t<real_t> &opts)
+        void step_resident_cond(const opts_t<real_t> &opts)
         {
           if (!init_called) throw std::runtime_error("libcloudph++: please call init() before calling step_sync()");
+          if (should_now_run_async) throw std::runtime_error("libcloudph++: please call step_async() before calling step_sync() again");
           arrinfo_t<real_t> none_th, none_rv;
           var_rho = false;
           should_now_run_cond = true;
           step_cond(opts, none_th, none_rv);
-          step_async(opts);
         }
 
         void step_cond(const opts_t<real_t> &opts, arrinfo_t<real_t> &th, arrinfo_t<real_t> &rv)
@@ -913,7 +1006,19 @@ namespace libcloudphxx
             {
               lcx_rng r;
               std::memset(&r, 0, sizeof(r));
-              if (rng_mode == LGRNGN_B200_RNG_MT19937)
+              if (!injected.empty())
+              {
+                int64_t n_part = 0;
+                chk(lcx_n_part(e, &n_part));
+                un_host.swap(injected.front().first); u01_host.swap(injected.front().second);
+                injected.pop_front();
+                if (un_host.size() < size_t(n_part) || u01_host.size() < size_t(n_part))
+                  throw std::runtime_error("libcloudph++ (B200 engine): injected random stream shorter than the number of super-droplets");
+                if (!dense_sid) throw std::runtime_error("libcloudph++ (B200 engine): injected random streams need dense storage indices (lgrngn_b200_set_dense_sid)");
+                r.mode = LCX_RNG_INJECT; r.un = un_host.data(); r.u01 = u01_host.data();
+                ++philox_call;                 // a caller replaying the Philox stream on the host stays in step with the call counter
+              }
+              else if (rng_mode == LGRNGN_B200_RNG_MT19937)
               {
                 // same draw order as the reference: un[n_part] for the shuffle, then u01[n_part] (hskpng_sort.ipp:33, coal.ipp:373)
                 int64_t n_part = 0;
@@ -924,7 +1029,12 @@ namespace libcloudphxx
                 for (auto &v : u01_host) v = draw_u01();
                 r.mode = LCX_RNG_INJECT; r.un = un_host.data(); r.u01 = u01_host.data();
               }
-              else { r.mode = LCX_RNG_PHILOX; r.seed = uint64_t(uint32_t(oi.rng_seed)); r.call = philox_call++; }
+              else
+              {
+                // counter-based stream: key = (rng_seed, slab rank), counter = (global cell or storage index, block, call)
+                r.mode = LCX_RNG_PHILOX; r.seed = uint64_t(uint32_t(oi.rng_seed)); r.call = philox_call++;
+                r.cell_base = uint32_t(n_cell_bfr + philox_cell_base); r.stream = uint32_t(slab_rank);
+              }
               chk(lcx_coal(e, dt / sstp_coal, &r));
               if (step + 1 != sstp_coal) chk(lcx_hskpng_vterm(e, 1));
             }
@@ -948,10 +1058,25 @@ namespace libcloudphxx
 
         void post_copy(const opts_t<real_t> &opts) { chk(lcx_post_copy(e, opts.rcyc, 0)); }
 
+        // x-slab migration through the neighbours' inboxes (include/lcx_b200.h); rgt / lft = neighbour engines of this process,
+        // nullptr when the neighbours live in other processes
+        int64_t n_sent[2] = {0, 0}, n_received[2] = {0, 0};
+        void migr_put() { chk(lcx_migr_put(e, &n_sent[0], &n_sent[1])); }
+        void migr_take(lcx_engine *rgt, lcx_engine *lft) { chk(lcx_migr_take(e, rgt, lft, &n_received[0], &n_received[1])); }
+
+        bool process_distributed = false;      // one slab of a run spread over several processes (particles_b200.h)
+
         void step_async(const opts_t<real_t> &opts)
         {
           step_async_local(opts);
-          if (!spawned) post_copy(opts);
+          if (process_distributed)
+          {
+            if (opts.rcyc) throw std::runtime_error("libcloudph++: Particle recycling can't be used in distributed-memory runs");
+            // like the reference's MPI build, the exchange is part of step_async (particles_step.ipp:484-490 -> mpi_exchange)
+            if (opts.adve) { migr_put(); migr_take(nullptr, nullptr); }
+            post_copy(opts);
+          }
+          else if (!spawned) post_copy(opts);
         }
 
         // ---- diagnostics -----------------------------------------------------------------------------------------
@@ -1003,15 +1128,25 @@ namespace libcloudphxx
         typedef typename parent_t::chem_cmap_t chem_cmap_t;
 
         std::vector<std::unique_ptr<slab<real_t>>> slabs;
+        std::unique_ptr<slab_workers> workers;     // multi_CUDA with more than one slab: one host thread per slab
         opts_init_t<real_t> glob;
         bool multi;
+        bool connected = false;
         std::vector<real_t> gathered;
+
+        template <class F>
+        void for_slabs(F f)
+        {
+          if (workers) workers->run([&](int d) { f(*slabs[size_t(d)]); });
+          else for (auto &s : slabs) f(*s);
+        }
 
         // single device (optionally one rank of a process-distributed run, see particles_b200.h)
         explicit particles_impl(const opts_init_t<real_t> &o) : glob(o), multi(false)
         {
           std::pair<int, int> bc;
           const lgrngn_b200_distmem dm = g_distmem;
+          g_distmem = lgrngn_b200_distmem{0, 1, -1., -1., 0};      // consumed: later particle systems of this process are ordinary ones
           if (dm.size > 1)
           {
             if (o.nx == 0) throw std::runtime_error("libcloudph++: distributed memory doesn't work for 0D setup.");
@@ -1022,9 +1157,18 @@ namespace libcloudphxx
           slabs.emplace_back(new slab<real_t>(o, bc, o.nx));   // Eulerian arrays are rank-local
           if (dm.size > 1)
           {
-            slabs[0]->spawned = true;
-            slabs[0]->lft_x1 = real_t(dm.lft_x1);
-            slabs[0]->rgt_x0 = real_t(dm.rgt_x0);
+            slab<real_t> &s0 = *slabs[0];
+            s0.spawned = true;
+            s0.process_distributed = true;
+            s0.lft_x1 = real_t(dm.lft_x1);
+            s0.rgt_x0 = real_t(dm.rgt_x0);
+            s0.slab_rank = dm.rank;
+            // the Eulerian arrays are rank-local; the global cell offset only decorrelates the slabs' random streams
+            s0.philox_cell_base = size_t(dm.rank) * s0.n_cell;
+            if (o.adve_scheme == as_t::pred_corr)
+              throw std::runtime_error("libcloudph++ (B200 engine): predictor-corrector advection in a process-distributed run needs the neighbours' Courant "
+                                       "halo columns (particles_impl_xchng_courants.ipp), which this back-end does not exchange between processes; "
+                                       "use adve_scheme implicit / euler, or the multi_CUDA backend (whose Eulerian arrays are global)");
           }
           this->opts_init = &slabs[0]->oi;
         }
@@ -1072,8 +1216,10 @@ namespace libcloudphxx
             s.n_x_bfr = n_x_bfr;
             s.n_cell_bfr = size_t(n_x_bfr) * m1(o_d.ny) * m1(o_d.nz);
             s.spawned = dev_count > 1;
+            s.slab_rank = d;
             s.oi.dev_count = dev_count;
           }
+          if (dev_count > 1) workers.reset(new slab_workers(dev_count));
           for (int d = 0; d < dev_count && dev_count > 1; ++d)
           {
             const int lft = d > 0 ? d - 1 : dev_count - 1, rgt = d < dev_count - 1 ? d + 1 : 0;
@@ -1085,73 +1231,82 @@ namespace libcloudphxx
 
         slab<real_t> &one() { return *slabs[0]; }
 
+        ~particles_impl() { workers.reset(); }
+
         // ---- API ---------------------------------------------------------------------------------------------------
         void init(const arrinfo_t<real_t> th, const arrinfo_t<real_t> rv, const arrinfo_t<real_t> rhod, const arrinfo_t<real_t> p,
                   const arrinfo_t<real_t> cx, const arrinfo_t<real_t> cy, const arrinfo_t<real_t> cz, const chem_cmap_t ambient_chem) override
         {
-          for (auto &s : slabs) s->init(th, rv, rhod, p, cx, cy, cz, ambient_chem.size());
+          const size_t n_chem = ambient_chem.size();
+          for_slabs([&](slab<real_t> &s) { s.init(th, rv, rhod, p, cx, cy, cz, n_chem); });
+          // every slab delivers its leavers straight into its neighbours' inboxes: particles_multi_gpu_impl.ipp:92-116 (peer access)
+          const int G = int(slabs.size());
+          if (multi && G > 1)
+          {
+            for (int d = 0; d < G; ++d)
+            {
+              const int lft = d > 0 ? d - 1 : G - 1, rgt = d < G - 1 ? d + 1 : 0;
+              if (slabs[size_t(d)]->bcond.first == distmem) chk(lcx_migr_connect(slabs[size_t(d)]->e, 0, slabs[size_t(lft)]->e));
+              if (slabs[size_t(d)]->bcond.second == distmem) chk(lcx_migr_connect(slabs[size_t(d)]->e, 1, slabs[size_t(rgt)]->e));
+            }
+            connected = true;
+          }
         }
 
         void step_sync(const opts_t<real_t> &opts, arrinfo_t<real_t> th, arrinfo_t<real_t> rv, const arrinfo_t<real_t> rhod,
                        const arrinfo_t<real_t> cx, const arrinfo_t<real_t> cy, const arrinfo_t<real_t> cz,
                        const arrinfo_t<real_t> diss_rate, chem_map_t ambient_chem) override
         {
-          for (auto &s : slabs) s->sync_in(th, rv, rhod, cx, cy, cz, diss_rate, ambient_chem.size(), /*defer_wait=*/true);
-          step_cond(opts, th, rv, ambient_chem);
+          const size_t n_chem = ambient_chem.size();
+          for_slabs([&](slab<real_t> &s) {
+            s.sync_in(th, rv, rhod, cx, cy, cz, diss_rate, n_chem, /*defer_wait=*/true);
+            arrinfo_t<real_t> th_ = th, rv_ = rv;
+            s.step_cond(opts, th_, rv_);
+          });
         }
 
         void sync_in(arrinfo_t<real_t> th, arrinfo_t<real_t> rv, const arrinfo_t<real_t> rhod, const arrinfo_t<real_t> cx,
                      const arrinfo_t<real_t> cy, const arrinfo_t<real_t> cz, const arrinfo_t<real_t> diss_rate, chem_map_t ambient_chem) override
         {
-          for (auto &s : slabs) s->sync_in(th, rv, rhod, cx, cy, cz, diss_rate, ambient_chem.size());
+          const size_t n_chem = ambient_chem.size();
+          for_slabs([&](slab<real_t> &s) { arrinfo_t<real_t> th_ = th, rv_ = rv; s.sync_in(th_, rv_, rhod, cx, cy, cz, diss_rate, n_chem); });
         }
 
         void step_cond(const opts_t<real_t> &opts, arrinfo_t<real_t> th, arrinfo_t<real_t> rv, chem_map_t) override
         {
-          for (auto &s : slabs) s->step_cond(opts, th, rv);
+          for_slabs([&](slab<real_t> &s) { arrinfo_t<real_t> th_ = th, rv_ = rv; s.step_cond(opts, th_, rv_); });
         }
 
         void step_async(const opts_t<real_t> &opts) override
         {
           if (multi && opts.rcyc)
             throw std::runtime_error("libcloudph++: Particle recycling can't be used in the multi_CUDA backend (it would consume whole memory quickly");
-          for (auto &s : slabs) s->step_async_local(opts);
           const int G = int(slabs.size());
           if (multi && G > 1)
           {
-            if (opts.adve)
-            {
-              // neighbour exchange in the reference's order: every slab first receives its right neighbour's left-movers,
-              // then its left neighbour's right-movers (step_async_and_copy.ipp:76-190)
-              std::vector<int64_t> n_lft(size_t(G), 0), n_rgt(size_t(G), 0);
-              for (int d = 0; d < G; ++d) chk(lcx_migr_pack(slabs[size_t(d)]->e, &n_lft[size_t(d)], &n_rgt[size_t(d)]));
-              for (int d = 0; d < G; ++d)
+            // phase 1: everything local, then each slab packs its leavers straight into its neighbours' inboxes (peer memory);
+            // phase 2 (after all deliveries have been queued - run() returning is the barrier): each slab's stream waits for its
+            // neighbours' delivery events, appends the arrivals (right neighbour's first) and re-groups.  The reference needs five
+            // barriers and four peer copies per step for this (step_async_and_copy.ipp:28-206).
+            for_slabs([&](slab<real_t> &s) { s.step_async_local(opts); if (opts.adve) s.migr_put(); });
+            for_slabs([&](slab<real_t> &s) {
+              if (opts.adve)
               {
-                const int rgt = d < G - 1 ? d + 1 : 0;
-                if (slabs[size_t(d)]->bcond.second == distmem && n_lft[size_t(rgt)] > 0)
-                  chk(lcx_migr_send(slabs[size_t(rgt)]->e, 0, slabs[size_t(d)]->e, n_lft[size_t(rgt)]));
+                const int d = s.slab_rank, lft = d > 0 ? d - 1 : G - 1, rgt = d < G - 1 ? d + 1 : 0;
+                s.migr_take(s.bcond.second == distmem ? slabs[size_t(rgt)]->e : nullptr, s.bcond.first == distmem ? slabs[size_t(lft)]->e : nullptr);
               }
-              for (int d = 0; d < G; ++d)
-              {
-                const int rgt = d < G - 1 ? d + 1 : 0;
-                if (slabs[size_t(d)]->bcond.second == distmem) chk(lcx_migr_unpack(slabs[size_t(d)]->e, 0, n_lft[size_t(rgt)]));
-              }
-              for (int d = 0; d < G; ++d)
-              {
-                const int lft = d > 0 ? d - 1 : G - 1;
-                if (slabs[size_t(d)]->bcond.first == distmem && n_rgt[size_t(lft)] > 0)
-                  chk(lcx_migr_send(slabs[size_t(lft)]->e, 1, slabs[size_t(d)]->e, n_rgt[size_t(lft)]));
-              }
-              for (int d = 0; d < G; ++d)
-              {
-                const int lft = d > 0 ? d - 1 : G - 1;
-                if (slabs[size_t(d)]->bcond.first == distmem) chk(lcx_migr_unpack(slabs[size_t(d)]->e, 1, n_rgt[size_t(lft)]));
-              }
-            }
-            for (auto &s : slabs) s->post_copy(opts);
+              s.post_copy(opts);
+            });
           }
           else
-            for (auto &s : slabs) if (!s->spawned) s->post_copy(opts);   // a spawned single slab is finished by its driver (particles_b200.h)
+            for (auto &s : slabs) s->step_async(opts);
+        }
+
+        // one model step on the fields already resident in device memory (particles_b200.h)
+        void step_resident(const opts_t<real_t> &opts)
+        {
+          for_slabs([&](slab<real_t> &s) { s.step_resident_cond(opts); });
+          step_async(opts);
         }
 
         // selectors
@@ -1451,40 +1606,109 @@ namespace libcloudphxx
 // ---- C entry points for process-distributed runs and test control (particles_b200.h) ---------------------------------
 namespace lg = libcloudphxx::lgrngn;
 
+template <class F>
+static int guarded_c(F f)
+{
+  try { f(); return 0; }
+  catch (const std::exception &ex) { std::cerr << ex.what() << std::endl; return 1; }
+}
+
 extern "C" {
 
 void lgrngn_b200_set_rng_mode(int mode) { lg::b200::g_rng_mode = mode; }
 int lgrngn_b200_get_rng_mode(void) { return lg::b200::g_rng_mode; }
 void lgrngn_b200_set_distmem(const lgrngn_b200_distmem *d) { lg::b200::g_distmem = *d; }
 
-static lg::b200::slab<double> &slab_of(void *proto)
+void lgrngn_b200_set_dense_sid(int mode) { lg::b200::g_dense_sid = mode; }
+
+static lg::b200::particles_impl<double> &impl_of(void *proto)
 {
   auto *p = dynamic_cast<lg::b200::particles_impl<double> *>(static_cast<lg::particles_proto_t<double> *>(proto));
   if (!p) throw std::runtime_error("not a B200 particle system");
-  return p->one();
+  return *p;
 }
+static lg::b200::slab<double> &slab_of(void *proto) { return impl_of(proto).one(); }
 
 void *lgrngn_b200_engine(void *proto)
 {
   try { return slab_of(proto).e; } catch (...) { return nullptr; }
 }
 
+int lgrngn_b200_n_slabs(void *proto)
+{
+  try { return int(impl_of(proto).slabs.size()); } catch (...) { return 0; }
+}
+
+void *lgrngn_b200_engine_of_slab(void *proto, int d)
+{
+  try { auto &p = impl_of(proto); return (d >= 0 && size_t(d) < p.slabs.size()) ? p.slabs[size_t(d)]->e : nullptr; } catch (...) { return nullptr; }
+}
+
 int lgrngn_b200_step_resident(void *proto, int flags)
 {
-  try
-  {
+  return guarded_c([&] {
     lg::opts_t<double> o;
     o.adve = flags & 1; o.sedi = flags & 2; o.cond = flags & 4; o.coal = flags & 8;
-    slab_of(proto).step_resident(o);
-    return 0;
-  }
-  catch (const std::exception &ex) { std::cerr << ex.what() << std::endl; return 1; }
+    impl_of(proto).step_resident(o);
+  });
 }
 
 int lgrngn_b200_post_copy(void *proto, int rcyc)
 {
-  try { lg::opts_t<double> o; o.rcyc = rcyc != 0; slab_of(proto).post_copy(o); return 0; }
-  catch (const std::exception &ex) { std::cerr << ex.what() << std::endl; return 1; }
+  return guarded_c([&] { lg::opts_t<double> o; o.rcyc = rcyc != 0; slab_of(proto).post_copy(o); });
+}
+
+int lgrngn_b200_distmem_export(void *proto, void *blobs)
+{
+  return guarded_c([&] {
+    auto &s = slab_of(proto);
+    if (!s.e) throw std::runtime_error("libcloudph++ (B200 engine): call init() before exporting the migration inboxes");
+    std::memset(blobs, 0, 2 * LCX_IPC_BLOB_BYTES);
+    // inbox 0 receives the RIGHT neighbour's left-movers, inbox 1 the LEFT neighbour's right-movers
+    if (s.bcond.second == lg::b200::distmem) lg::b200::chk(lcx_migr_ipc_export(s.e, 0, blobs));
+    if (s.bcond.first == lg::b200::distmem) lg::b200::chk(lcx_migr_ipc_export(s.e, 1, static_cast<char *>(blobs) + LCX_IPC_BLOB_BYTES));
+  });
+}
+
+int lgrngn_b200_distmem_connect(void *proto, const void *lft_blobs, const void *rgt_blobs)
+{
+  return guarded_c([&] {
+    auto &s = slab_of(proto);
+    if (!s.e) throw std::runtime_error("libcloudph++ (B200 engine): call init() before connecting the neighbours");
+    if (s.bcond.first == lg::b200::distmem) lg::b200::chk(lcx_migr_ipc_connect(s.e, 0, lft_blobs));
+    if (s.bcond.second == lg::b200::distmem) lg::b200::chk(lcx_migr_ipc_connect(s.e, 1, static_cast<const char *>(rgt_blobs) + LCX_IPC_BLOB_BYTES));
+  });
+}
+
+int lgrngn_b200_migr_stats(void *proto, long long *out)
+{
+  return guarded_c([&] {
+    auto &p = impl_of(proto);
+    for (int q = 0; q < 4; ++q) out[q] = 0;
+    for (auto &s : p.slabs) { out[0] += s->n_sent[0]; out[1] += s->n_sent[1]; out[2] += s->n_received[0]; out[3] += s->n_received[1]; }
+  });
+}
+
+int lgrngn_b200_inject_rng(void *proto, const unsigned int *un, const double *u01, long long n)
+{
+  return guarded_c([&] {
+    auto &s = slab_of(proto);
+    s.injected.emplace_back(std::vector<uint32_t>(un, un + n), std::vector<double>(u01, u01 + n));
+  });
+}
+
+long long lgrngn_b200_philox_call(void *proto)
+{
+  try { return (long long)slab_of(proto).philox_call; } catch (...) { return -1; }
+}
+
+int lgrngn_b200_get_layout(void *proto, unsigned int *sid, unsigned int *ijk, long long cap, long long *n_out)
+{
+  return guarded_c([&] {
+    int64_t n = 0;
+    lg::b200::chk(lcx_get_layout(slab_of(proto).e, sid, ijk, cap, &n));
+    *n_out = n;
+  });
 }
 
 

@@ -24,8 +24,26 @@ typedef struct
 void  lgrngn_b200_set_rng_mode(int mode);       /* applies to particle systems created afterwards (default: $LCX_RNG or Philox) */
 int   lgrngn_b200_get_rng_mode(void);
 void  lgrngn_b200_set_distmem(const lgrngn_b200_distmem *d);
-void *lgrngn_b200_engine(void *particles_proto); /* lcx_engine* of a single-slab particle system */
+void *lgrngn_b200_engine(void *particles_proto); /* lcx_engine* of the first (or only) slab */
+int   lgrngn_b200_n_slabs(void *particles_proto);
+void *lgrngn_b200_engine_of_slab(void *particles_proto, int slab);
 int   lgrngn_b200_post_copy(void *particles_proto, int rcyc);
+/* Process-distributed runs: after init() every rank exports two 96-byte blobs (CUDA IPC handles of its two migration     */
+/* inboxes: [0] filled by its RIGHT neighbour, [1] by its LEFT neighbour), the caller moves them to the neighbours with    */
+/* whatever transport it has (MPI, torch.distributed, a file), and each rank connects with the blob pairs of its left and   */
+/* right neighbours.  From then on step_async() itself migrates the super-droplets: packed straight into the neighbour's    */
+/* inbox over NVLink, ordered by sequence numbers in device memory; no host communication in the step.                      */
+int   lgrngn_b200_distmem_export(void *particles_proto, void *blobs /* 2 x 96 bytes */);
+int   lgrngn_b200_distmem_connect(void *particles_proto, const void *lft_neighbour_blobs, const void *rgt_neighbour_blobs);
+/* migrants of the last step, summed over the slabs: sent left, sent right, received from the right, received from the left */
+int   lgrngn_b200_migr_stats(void *particles_proto, long long *out4);
+/* test hooks: storage indices kept dense (1) / re-numbered lazily (0) / chosen by the random-stream mode (-1, default);     */
+/* random streams for the next coalescence sub-step (un by storage index, u01 by sorted position; one call per sub-step);   */
+/* number of Philox calls made so far; storage index and cell of every super-droplet in physical order                       */
+void  lgrngn_b200_set_dense_sid(int mode);
+int   lgrngn_b200_inject_rng(void *particles_proto, const unsigned int *un, const double *u01, long long n);
+long long lgrngn_b200_philox_call(void *particles_proto);
+int   lgrngn_b200_get_layout(void *particles_proto, unsigned int *sid, unsigned int *ijk, long long cap, long long *n_out);
 /* one full model step (condensation + th/rv feedback, then coalescence / transport / housekeeping) on the Eulerian  */
 /* fields ALREADY RESIDENT in device memory: no host<->device field traffic.  flags: bit0 adve, bit1 sedi, bit2 cond, */
 /* bit3 coal.  Used by bench.py for the device-resident throughput figure.                                            */

@@ -360,3 +360,100 @@ def mass_density_spectrum(p, scale=6.0):
 def rmsd(a1, a2):
     m = (a1 > 0) | (a2 > 0)
     return float(np.sqrt(((a1[m] - a2[m]) ** 2).sum() / m.sum()))
+
+
+# ---- the benchmarked random stream (Philox4x32-10 in the kernels) restated on the host -------------------------------------
+import contextlib
+
+
+@contextlib.contextmanager
+def rng_mode(lib, mode, dense_sid=-1):
+    """particle systems created inside use the given random stream: 0 = Philox in the kernels (what bench.py times and what
+    users get by default), 1 = replay of the reference's mt19937 draw order; dense_sid as lgrngn_b200_set_dense_sid"""
+    lib.lib.lgrngn_b200_set_rng_mode.argtypes = [C.c_int]
+    lib.lib.lgrngn_b200_set_dense_sid.argtypes = [C.c_int]
+    lib.lib.lgrngn_b200_set_rng_mode(mode)
+    lib.lib.lgrngn_b200_set_dense_sid(dense_sid)
+    try:
+        yield
+    finally:
+        lib.lib.lgrngn_b200_set_rng_mode(1)
+        lib.lib.lgrngn_b200_set_dense_sid(-1)
+
+
+def proto(lib, p):
+    lib.lib.lgc_proto.restype = C.c_void_p
+    lib.lib.lgc_proto.argtypes = [C.c_void_p]
+    return C.c_void_p(lib.lib.lgc_proto(p._h))
+
+
+def step_resident(lib, p, flags=0b1111):
+    lib.lib.lgrngn_b200_step_resident.argtypes = [C.c_void_p, C.c_int]
+    assert lib.lib.lgrngn_b200_step_resident(proto(lib, p), flags) == 0
+
+
+def philox_call(lib, p):
+    lib.lib.lgrngn_b200_philox_call.restype = C.c_longlong
+    lib.lib.lgrngn_b200_philox_call.argtypes = [C.c_void_p]
+    return int(lib.lib.lgrngn_b200_philox_call(proto(lib, p)))
+
+
+def physical_layout(lib, p, cap):
+    """(sid, ijk) of every super-droplet in the order it lies in device memory"""
+    sid, ijk, n = np.empty(cap, np.uint32), np.empty(cap, np.uint32), C.c_longlong()
+    lib.lib.lgrngn_b200_get_layout.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.POINTER(C.c_longlong)]
+    assert lib.lib.lgrngn_b200_get_layout(proto(lib, p), sid.ctypes.data, ijk.ctypes.data, cap, C.byref(n)) == 0
+    return sid[:n.value].copy(), ijk[:n.value].copy()
+
+
+def inject_rng(lib, p, un, u01):
+    un = np.ascontiguousarray(un, np.uint32)
+    u01 = np.ascontiguousarray(u01, np.float64)
+    lib.lib.lgrngn_b200_inject_rng.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong]
+    assert lib.lib.lgrngn_b200_inject_rng(proto(lib, p), un.ctypes.data, u01.ctypes.data, un.size) == 0
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 (Salmon et al., SC'11) on numpy arrays of counters; returns the four output words"""
+    M0, M1, W0, W1, mask = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85, 0xFFFFFFFF
+    c = [np.asarray(v, np.uint64) & mask for v in np.broadcast_arrays(c0, c1, c2, c3)]
+    k0, k1 = int(k0) & mask, int(k1) & mask
+    for _ in range(10):
+        p0, p1 = c[0] * np.uint64(M0), c[2] * np.uint64(M1)
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & np.uint64(mask), p1 >> np.uint64(32), p1 & np.uint64(mask)
+        c = [hi1 ^ c[1] ^ np.uint64(k0), lo1, hi0 ^ c[3] ^ np.uint64(k1), lo0]
+        k0, k1 = (k0 + W0) & mask, (k1 + W1) & mask
+    return [v.astype(np.uint32) for v in c]
+
+
+def philox_u01(w0, w1):
+    bits = ((w0.astype(np.uint64) << np.uint64(21)) ^ (w1.astype(np.uint64) >> np.uint64(11))) & np.uint64((1 << 53) - 1)
+    return bits.astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def philox_streams_for_layout(sid, ijk, seed, call, small, cell_base=0, stream=0):
+    """(un by storage index, u01 by sorted position) that the coalescence kernels draw for this physical layout:
+    small cells (csrc/lcx_coal.cu k_coal_small): block q of cell c gives the sort keys of in-cell slots 4q..4q+3, block q | 2^31
+    the u01 of pairs 2q, 2q+1, consumed at the position of the pair's first super-droplet;
+    big cells (k_coal_big): un from counter (sid, 0), u01 from counter (sorted position, 1)"""
+    n = sid.size
+    lo, hi = call & 0xFFFFFFFF, call >> 32
+    un, u01 = np.zeros(n, np.uint32), np.zeros(n, np.float64)
+    if not small:
+        un[sid] = philox4x32_10(sid, 0, lo, hi, seed, stream)[0]
+        w = philox4x32_10(np.arange(n), 1, lo, hi, seed, stream)
+        return un, philox_u01(w[0], w[1])
+    first = np.r_[0, np.flatnonzero(np.diff(ijk)) + 1]                   # start of every non-empty cell's segment
+    start = np.repeat(first, np.diff(np.r_[first, n]))
+    slot = np.arange(n) - start                                          # in-cell position e
+    w = philox4x32_10(cell_base + ijk.astype(np.uint64), slot // 4, lo, hi, seed, stream)
+    keys = np.choose(slot % 4, w)
+    un[sid] = keys
+    # u01 of pair k sits at physical position b + 2k: words (2k) % 4 and (2k) % 4 + 1 of block (2k) // 4 | 2^31
+    even = slot % 2 == 0
+    q = (slot // 4) | 0x80000000
+    w = philox4x32_10(cell_base + ijk.astype(np.uint64), q, lo, hi, seed, stream)
+    first_word = np.where(slot % 4 == 0, w[0], w[2])
+    second_word = np.where(slot % 4 == 0, w[1], w[3])
+    u01[even] = philox_u01(first_word, second_word)[even]
+    return un, u01

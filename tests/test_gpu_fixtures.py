@@ -46,13 +46,17 @@ def test_cond_adaptive_substepping_fixture(b200, row):
 @pytest.mark.parametrize("vt", [L.vt_t.beard76, L.vt_t.beard77, L.vt_t.beard77fast])
 def test_hall_davis_coalescence_vs_bott(b200, vt):
     """tests/python/physics/coalescence_hall_davis_no_waals.py:82-105: mass-density spectrum after 1800 s vs Bott's bin model"""
+    assert bott_rmsd(b200, vt) < 6e-2
+
+
+def bott_rmsd(b200, vt):
     bott = np.load(os.path.join(ROOT, "tests", "golden", "bott1800.npy"))
     oi, o, f = S.hall_davis_box(b200, vt)
     p = b200.factory(L.backend_t.CUDA, oi)
     p.init(f["th"], f["rv"], f["rhod"])
     p.step_sync(o, f["th"], f["rv"], f["rhod"])
     p.step_async(o)
-    assert S.rmsd(S.mass_density_spectrum(p) * 1000, bott) < 6e-2
+    return S.rmsd(S.mass_density_spectrum(p) * 1000, bott)
 
 
 def test_golden_golovin_box(b200):
@@ -87,6 +91,10 @@ def test_golden_box3d(b200):
 
 def test_golovin_analytic(b200):
     """tests/python/physics/coalescence_golovin.py:112-155 (sd_conc branch): RMSD of the mass density vs Golovin's solution < 1.2e-5"""
+    assert golovin_analytic_rmsd(b200) < 1.2e-5
+
+
+def golovin_analytic_rmsd(b200):
     from scipy import special
     n_zero, r_zero, b, t_sim = 2.0 ** 23, 30.084e-6, 1500., 800
     oi, o, f = S.box_golovin(b200, n_sd=2 ** 14, dt=float(t_sim), sstp_coal=t_sim)
@@ -108,4 +116,4 @@ def test_golovin_analytic(b200):
         bessel = special.iv(1, 2 * x * np.sqrt(tau))
         val = 0. if np.isinf(bessel) else n0 / v0 * bessel * (1 - tau) * np.exp(-x * (tau + 1)) / x / np.sqrt(tau)
         gol[i] = (0. if np.isnan(val) else val) * v * v * 3000.
-    assert S.rmsd(res, gol) < 1.2e-5
+    return S.rmsd(res, gol)

@@ -123,11 +123,11 @@ def test_multi_cuda_devices_match_fold(b200, monkeypatch):
         assert np.array_equal(a, b)
 
 
-@pytest.mark.skipif("n_devices() < 2")
 def test_torchrun_ranks_roundtrip():
-    """one process per GPU, migrants exchanged over NCCL on the engine's own device buffers"""
-    n = min(n_devices(), 4)
+    """one process per slab (one per GPU where there are enough; on a single-GPU box the ranks share the device and only the
+    transport differs: CUDA IPC inside one device instead of NVLink), migrants packed straight into the neighbours' inboxes"""
+    n = min(max(n_devices(), 2), 4)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
            "--master-port", "29517", os.path.join(ROOT, "tests", "dist_worker.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0 and "DIST_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
