@@ -358,7 +358,7 @@ def run_b200(args):
 
     def resident_step():
         if lib.lib.lgrngn_b200_step_resident(proto, 0b1111) != 0:
-            raise RuntimeError("resident step failed")
+            raise RuntimeError("resident step failed on rank %d (live SDs %s)" % (rank, [e_.n_part() for e_ in engines]))
 
     def host_step():
         api_step(p, o, f)
@@ -387,13 +387,15 @@ def run_b200(args):
         return max(e_.timer_stop() for e_ in engines)
 
     def dry_volume():
-        """4/3 pi sum(n rd^3) of the live super-droplets of this process + what rained into the puddle; the invariant of
-        coalescence, transport and migration together"""
+        """4/3 pi sum(n rd^3) of the live super-droplets of this process + what left through the bottom (puddle) and the lid; the
+        invariant of coalescence, transport and migration together"""
         p.diag_all()
         p.diag_dry_mom(3)
         cells = p.outbuf().reshape(f["rhod"].shape)
         live = float((cells * f["rhod"]).sum() * 20.0 ** 3 * 4.0 / 3.0 * np.pi)
-        return live, float(p.diag_puddle()["dry_volume"])
+        # freshly collided super-droplets carry the "invalid" fall speed -1 through the sedimentation step (reference quirk, kept):
+        # the ones next to the lid leave through it, unaccounted for by the reference's puddle; the engine tallies them
+        return live, float(p.diag_puddle()["dry_volume"]) + sum(e_.top_loss()[0] for e_ in engines)
 
     # the first API step uploads the fields; afterwards they are resident
     live0, pud0 = dry_volume()
@@ -477,7 +479,7 @@ def run_b200(args):
     # ---- conservation over everything that ran so far (every rank, every N): dry volume live + rained out ------------------------
     live1, pud1 = dry_volume()
     vol1 = reduce(live1 + pud1, "SUM")
-    conservation = {"dry_volume_rel_err": abs(vol1 - vol0) / vol0, "dry_volume_rained_out_frac": reduce(pud1, "SUM") / vol0,
+    conservation = {"dry_volume_rel_err": abs(vol1 - vol0) / vol0, "dry_volume_left_domain_frac": reduce(pud1, "SUM") / vol0,
                     "sd_live_start": nx_glob * ny * nz * args.sd_conc, "sd_live_end": int(reduce(float(n_live()), "SUM")),
                     "migrants_per_step": (reduce(float(np.mean(migrants)), "SUM") if migrants else 0.0),
                     "migrant_frac_per_slab_step": (reduce(float(np.mean(migrants)), "SUM") / max(live_end, 1.0) if migrants else 0.0)}

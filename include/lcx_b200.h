@@ -163,6 +163,10 @@ int  lcx_get_cond_solver(void);
 /* run of k consecutive cells with its lanes balanced over the run's super-droplets                                       */
 int  lcx_set_cond_layout(int cells_per_warp);
 int  lcx_get_cond_layout(void);
+/* the run-per-warp kernel in its phase-grouped form (default 1): droplets that need a 4th / 5th growth-law evaluation are parked   */
+/* in shared memory and processed a full warp at a time; results are bit-identical to the plain form (0), which stays for A/B runs */
+int  lcx_set_cond_staged(int on);
+int  lcx_get_cond_staged(void);
 /* per-particle condensation sub-stepping, all sub-steps of one time step (particles_step.ipp:199-236,                 */
 /* condensation/perparticle/ *.ipp); mix != 0: the vapour / heat exchanged by the SDs of a cell is shared after each sub-step */
 int  lcx_cond_perparticle(lcx_engine *e, double dt, double RH_max, int sstp_cond, int mix);
@@ -181,6 +185,9 @@ int  lcx_coal_stats(lcx_engine *e, uint64_t *n_collisions, uint64_t *n_pairs_col
 /* ---- transport: advection + sedimentation + subsidence + boundary conditions ---------------------------- */
 int  lcx_transport(lcx_engine *e, const lcx_transport_opts *o);           /* adve.ipp:98-304, sedi.ipp:13-24, subs.ipp:13-25, bcnd.ipp:114-368 */
 int  lcx_puddle(lcx_engine *e, double out[14]);                           /* accumulated precipitation       */
+/* what left through the LID (z >= z1), which the reference removes without accounting (bcnd.ipp:330-336): accumulated dry   */
+/* volume (same convention as the puddle) and number of super-droplets; lets callers close the dry-volume budget            */
+int  lcx_top_loss(lcx_engine *e, double out[2]);
 
 /* ---- x-slab migration (distributed memory) ------------------------------------------------------------- */
 /* Every engine owns one inbox per side (0: left-movers arriving from the RIGHT neighbour, 1: right-movers arriving */

@@ -456,6 +456,8 @@ int lcx_set_cond_solver(int mode) { lcx::set_cond_solver(mode); return 0; }
 int lcx_get_cond_solver(void) { return lcx::cond_solver(); }
 int lcx_set_cond_layout(int cells_per_warp) { lcx::set_cond_layout(cells_per_warp); return 0; }
 int lcx_get_cond_layout(void) { return lcx::cond_layout(); }
+int lcx_set_cond_staged(int on) { lcx::set_cond_staged(on); return 0; }
+int lcx_get_cond_staged(void) { return lcx::cond_staged(); }
 
 int lcx_cond_perparticle(lcx_engine *e, double dt, double RH_max, int sstp_cond, int mix)
 { return guarded([&] { use_device(e); lcx::cond_perparticle(e, dt, RH_max, sstp_cond, mix != 0); }); }
@@ -512,6 +514,16 @@ namespace
 {
   struct ipc_blob { cudaIpcMemHandle_t handle; uint64_t cap; int32_t n_real; int32_t real_bytes; char pad[LCX_IPC_BLOB_BYTES - sizeof(cudaIpcMemHandle_t) - 16]; };
   static_assert(sizeof(ipc_blob) == LCX_IPC_BLOB_BYTES, "IPC blob layout");
+}
+
+int lcx_top_loss(lcx_engine *e, double out[2])
+{
+  return guarded([&] {
+    use_device(e, true, 3u);      // device scalars only
+    LCX_CUDA(cudaMemcpyAsync(e->h_scalars, e->scalars.p, sizeof(lcx::dev_scalars), cudaMemcpyDeviceToHost, e->stream));
+    LCX_CUDA(cudaStreamSynchronize(e->stream));
+    out[0] = e->h_scalars->puddle[4]; out[1] = e->h_scalars->puddle[5];
+  });
 }
 
 int lcx_migr_connect(lcx_engine *e, int side, lcx_engine *nb)

@@ -24,6 +24,7 @@ namespace lcx
     constexpr int CELL_LANES = 16;           // lanes that share one cell in k_coal_small (two cells per warp)
     constexpr int GROUPS = TPB / CELL_LANES;
     constexpr unsigned SMALL_MAX = 256;      // largest cell population handled by k_coal_small
+    constexpr int KAPPA_ITER_MAX = 1024;     // collisions of one pair up to which kappa is mixed event by event like the reference
 
     // ---- Philox4x32-10 (Salmon, Moraes, Dror & Shaw, SC'11) --------------------------------------------
     struct philox_key { uint32_t k0, k1; };
@@ -93,15 +94,21 @@ namespace lcx
       if (cx.rc2) cx.rc2[lo] = real_t(-1);
       if (cx.multi_kappa)
       {
-        // rd3-weighted mean of kappa, applied once per collision: weighted_summator, coal.ipp:59-96
+        // rd3-weighted mean of kappa, applied once per collision: weighted_summator, coal.ipp:59-96.  The reference iterates
+        // col_no times (with an int counter); a rain drop sweeping up thousands of droplets would keep one lane - hence its whole
+        // CTA - busy for that long, so beyond KAPPA_ITER_MAX collisions the recurrence's closed form is used: the same weighted
+        // mean, summed in one step (differs from the iterated value by rounding only, <= col_no * 2^-53 relative)
         const real_t kpa_hi = cx.kpa[hi];
         real_t kpa_lo = cx.kpa[lo];
         real_t rd3_old = rd3_new - col_no * rd3_hi;
-        for (int ci = 0; ci < real_t(col_no); ++ci)
-        {
-          kpa_lo = (kpa_hi * rd3_hi + kpa_lo * rd3_old) / (rd3_hi + rd3_old);
-          rd3_old += rd3_hi;
-        }
+        if (col_no <= n_t(KAPPA_ITER_MAX))
+          for (int ci = 0; ci < int(col_no); ++ci)
+          {
+            kpa_lo = (kpa_hi * rd3_hi + kpa_lo * rd3_old) / (rd3_hi + rd3_old);
+            rd3_old += rd3_hi;
+          }
+        else
+          kpa_lo = (real_t(col_no) * (kpa_hi * rd3_hi) + kpa_lo * rd3_old) / (real_t(col_no) * rd3_hi + rd3_old);
         cx.kpa[lo] = kpa_lo;
       }
     }

@@ -221,6 +221,223 @@ namespace lcx
       }
     }
 
+    // ---- staged variant of k_cond_range (TOMS 748 only) --------------------------------------------------------------------------------
+    // A round of k_cond_range costs as many growth-law evaluations as its slowest droplet needs (5.1 on the bench workload) while the
+    // droplets need 3.65 on average (2: 8 %, 3: 33 %, 4: 45 %, 5: 13 %): a third of the FP64 issue slots belong to lanes that are
+    // already done.  Letting a lane start its next droplet at once was measured and rejected: the lanes then sit
+    // in different phases of TOMS 748 and the division-heavy interpolation code of each phase runs serially.  The number of
+    // evaluations done IS the phase, though, so droplets are re-grouped by it: the same warp-per-run-of-cells decomposition, but
+    //   stage 0  takes 32 new droplets through the three evaluations everybody needs (old point, far bracket end, secant point);
+    //            whoever is not finished parks its solver state in a per-warp queue in shared memory (ballot-compacted);
+    //   stage 1  runs the 4th evaluation on 32 parked droplets at a time - all in the same phase, all lanes busy;
+    //            the few still unfinished park again;
+    //   stage 2  runs those 32 at a time to completion (5th evaluation for nearly all of them).
+    // A stage runs as soon as its queue holds a full warp (later stages first, so no queue exceeds 63 entries); the partial rest is
+    // drained at the end of the run.  Same trial points, same arithmetic per droplet: rw2 is bit-identical to k_cond_range.  The
+    // per-cell sums of n r^3 are taken in a final sweep over the run in exactly the order k_cond_range uses, so th and rv are
+    // bit-identical as well.  Queue entry: 13 doubles + 2 words; 13 KB of shared memory per warp -> 2 warps per CTA, 7 CTAs per SM.
+    constexpr int ST_TPB = 64, ST_WARPS = ST_TPB / 32, QCAP = 64, QF0 = 11, QF1 = 13;
+#ifndef LCX_COND_ST_MINB
+#define LCX_COND_ST_MINB 7
+#endif
+    template <int NF>
+    struct cond_queue
+    {
+      real_t f[NF][QCAP];      // a b fa fb d fd e fe c rw2_old rd2 [a0 b0]
+      uint32_t idx[QCAP], meta[QCAP];
+    };
+    struct staged_smem
+    {
+      cond_cell_consts<real_t> k[ST_WARPS][RANGE_MAX];
+      real_t m[ST_WARPS][RANGE_MAX][2];
+      cond_queue<QF0> q0[ST_WARPS];
+      cond_queue<QF1> q1[ST_WARPS];
+    };
+
+    __device__ __forceinline__ unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
+    template <int NF>
+    __device__ __forceinline__ void queue_push(cond_queue<NF> &q, int &count, bool busy, const euler_rw2_solver<real_t> &sv, uint32_t i, int ci)
+    {
+      const unsigned m = __ballot_sync(0xffffffffu, busy);
+      if (busy)
+      {
+        const int pos = count + __popc(m & lanemask_lt());
+        q.f[0][pos] = sv.s.a; q.f[1][pos] = sv.s.b; q.f[2][pos] = sv.s.fa; q.f[3][pos] = sv.s.fb; q.f[4][pos] = sv.s.d; q.f[5][pos] = sv.s.fd;
+        q.f[6][pos] = sv.s.e; q.f[7][pos] = sv.s.fe; q.f[8][pos] = sv.c; q.f[9][pos] = sv.rw2_old; q.f[10][pos] = sv.rd2;
+        if (NF > 11) { q.f[11][pos] = sv.a0; q.f[12][pos] = sv.b0; }
+        q.idx[pos] = i;
+        q.meta[pos] = uint32_t(ci) | (uint32_t(sv.phase) << 8) | (uint32_t(sv.bracketing) << 12) | (sv.left << 16);
+      }
+      count += __popc(m);
+      __syncwarp();
+    }
+    template <int NF>
+    __device__ __forceinline__ bool queue_pop(cond_queue<NF> &q, int &count, int lane, euler_rw2_solver<real_t> &sv, uint32_t &i, int &ci)
+    {
+      const int take = count < 32 ? count : 32;
+      const bool busy = lane < take;
+      if (busy)
+      {
+        const int pos = count - take + lane;
+        sv.s.a = q.f[0][pos]; sv.s.b = q.f[1][pos]; sv.s.fa = q.f[2][pos]; sv.s.fb = q.f[3][pos]; sv.s.d = q.f[4][pos]; sv.s.fd = q.f[5][pos];
+        sv.s.e = q.f[6][pos]; sv.s.fe = q.f[7][pos]; sv.c = q.f[8][pos]; sv.rw2_old = q.f[9][pos]; sv.rd2 = q.f[10][pos];
+        if (NF > 11) { sv.a0 = q.f[11][pos]; sv.b0 = q.f[12][pos]; }
+        i = q.idx[pos];
+        const uint32_t mt = q.meta[pos];
+        ci = int(mt & 0xffu); sv.phase = int((mt >> 8) & 0xfu); sv.bracketing = ((mt >> 12) & 1u) != 0u; sv.left = mt >> 16;
+      }
+      count -= take;
+      __syncwarp();
+      return busy;
+    }
+
+    template <bool LAZY>
+    __global__ void __launch_bounds__(ST_TPB, LCX_COND_ST_MINB) k_cond_staged(idx_t n_cell, int run, const uint32_t *__restrict__ off, real_t dt, real_t RH_max, cond_args a,
+                                                       int n_dims, const real_t *__restrict__ dv, int first_step, int keep_after,
+                                                       real_t *__restrict__ rw_mom3, real_t *__restrict__ drw_mom3,
+                                                       real_t *__restrict__ th, real_t *__restrict__ rv, lazy_args z)
+    {
+      __shared__ staged_smem sm;
+      const int w = threadIdx.x / 32, l = threadIdx.x % 32;
+      const size_t c0_ = (size_t(blockIdx.x) * ST_WARPS + w) * size_t(run);
+      if (c0_ >= n_cell) return;                      // whole warps leave; nothing below synchronises across warps
+      const idx_t c0 = idx_t(c0_);
+      const int nc = int(n_cell - c0 < idx_t(run) ? n_cell - c0 : idx_t(run));
+      if (l < nc)
+      {
+        sm.k[w][l] = make_cond_consts(load_cell(a, c0 + l), RH_max);
+        sm.m[w][l][0] = 0; sm.m[w][l][1] = 0;
+      }
+      __syncwarp();
+      const uint32_t b = off[c0], en = off[c0 + nc];
+      cond_queue<QF0> &q0 = sm.q0[w];
+      cond_queue<QF1> &q1 = sm.q1[w];
+      int n0 = 0, n1 = 0;                              // queue fills (warp-uniform)
+      uint32_t next = b;                               // first droplet not yet started
+
+      for (;;)
+      {
+        // pick the work of this round (warp-uniform): the latest stage that can fill the warp, else new droplets, else leftovers
+        int src;
+        if (n1 >= 32) src = 2; else if (n0 >= 32) src = 1; else if (next < en) src = 0; else if (n1 > 0) src = 2; else if (n0 > 0) src = 1; else break;
+
+        euler_rw2_solver<real_t> sv;
+        uint32_t i = 0;
+        int ci = 0;
+        bool busy = false;
+        real_t rd3_i = 0, rd3_dry = 0, vt_cRe = 0;
+        if (src == 0)
+        {
+          i = next + l;
+          const bool act = i < en;
+          ci = RANGE_MAX;                               // idle lanes sit behind the last SD: keys stay non-decreasing
+          real_t mb = 0;
+          sv.start(real_t(0), dt);
+          if (act)
+          {
+            const idx_t cc = a.ijk[i] - c0;
+            ci = cc < idx_t(nc) ? int(cc) : nc - 1;
+            real_t r2, kpa_i, vt_i;
+            n_t n_i;
+            if (LAZY)      // the attributes still lie in the previous layout; their copies into the new one ride along
+            {
+              const uint32_t j = z.perm[i];
+              r2 = z.rw2[j]; rd3_i = z.rd3[j]; kpa_i = z.kpa[j]; vt_i = z.vt[j]; n_i = z.n[j];
+              z.rd3_out[i] = rd3_i; z.kpa_out[i] = kpa_i; z.vt_out[i] = vt_i; z.n_out[i] = n_i;
+              if (!(r2 > 0)) a.rw2[i] = r2;
+            }
+            else { r2 = a.rw2[i]; rd3_i = a.rd3[i]; kpa_i = a.kpa[i]; vt_i = a.vt[i]; n_i = a.n[i]; }
+            mb = real_t(n_i) * (r2 * sqrt(r2));
+            if (r2 > 0)
+            {
+              busy = true;
+              sv.start(r2, dt);
+              rd3_dry = rd3_i * (real_t(1) - kpa_i); vt_cRe = vt_i * sm.k[w][ci].c_Re;
+            }
+          }
+          // the "before" sums, segment by segment exactly as k_cond_range takes them
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1)
+          {
+            const int ko = __shfl_down_sync(0xffffffffu, ci, o);
+            const real_t vb = __shfl_down_sync(0xffffffffu, mb, o);
+            if (l + o < 32 && ko == ci) mb += vb;
+          }
+          const int prev = __shfl_up_sync(0xffffffffu, ci, 1);
+          if (act && (l == 0 || prev != ci)) sm.m[w][ci][0] += mb;
+          __syncwarp();
+          next += 32;
+        }
+        else
+        {
+          busy = src == 1 ? queue_pop(q0, n0, l, sv, i, ci) : queue_pop(q1, n1, l, sv, i, ci);
+          sv.dt = dt;
+          if (busy)
+          {
+            rd3_i = a.rd3[i];                           // written in place (or, gather-on-read, by stage 0 of this warp)
+            rd3_dry = rd3_i * (real_t(1) - a.kpa[i]); vt_cRe = a.vt[i] * sm.k[w][ci].c_Re;
+          }
+        }
+
+        // ONE site for the growth law and the solver step, whatever the stage: 3 evaluations for new droplets, 1 for stage 1,
+        // to completion for stage 2
+        const int limit = src == 0 ? 3 : src == 1 ? 1 : 1000;
+        for (int it = 0; it < limit && __any_sync(0xffffffffu, busy); ++it)
+        {
+          if (busy)
+          {
+            real_t result;
+            const real_t g = drw2_dt_fast(sv.point(), rd3_i, rd3_dry, vt_cRe, sm.k[w][ci < RANGE_MAX ? ci : 0]);
+            if (sv.feed(g, rd3_i, result)) { a.rw2[i] = result; busy = false; }
+          }
+        }
+        if (src == 0) queue_push(q0, n0, busy, sv, i, ci);
+        else if (src == 1) queue_push(q1, n1, busy, sv, i, ci);
+      }
+      __syncwarp();
+
+      // the "after" sums from the radii just written, in the order of k_cond_range: round by round, segment by segment
+      for (uint32_t base = b; base < en; base += 32)
+      {
+        const uint32_t i = base + l;
+        const bool act = i < en;
+        int ci = RANGE_MAX;
+        real_t ma = 0;
+        if (act)
+        {
+          const idx_t cc = a.ijk[i] - c0;
+          ci = cc < idx_t(nc) ? int(cc) : nc - 1;
+          const real_t r2n = a.rw2[i];
+          ma = real_t(a.n[i]) * (r2n * sqrt(r2n));
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+          const int ko = __shfl_down_sync(0xffffffffu, ci, o);
+          const real_t va = __shfl_down_sync(0xffffffffu, ma, o);
+          if (l + o < 32 && ko == ci) ma += va;
+        }
+        const int prev = __shfl_up_sync(0xffffffffu, ci, 1);
+        if (act && (l == 0 || prev != ci)) sm.m[w][ci][1] += ma;
+        __syncwarp();
+      }
+      if (l < nc)
+      {
+        const idx_t c = c0 + l;
+        const cond_cell<real_t> cl = load_cell(a, c);
+        real_t m3_before = sm.m[w][l][0], m3_after = sm.m[w][l][1];
+        if (n_dims > 0) { m3_before = m3_before / dv[c] / cl.rhod; m3_after = m3_after / dv[c] / cl.rhod; }
+        if (!first_step) m3_before = rw_mom3[c];
+        if (keep_after) rw_mom3[c] = m3_after;
+        const real_t drv = (-m3_before + m3_after) * (cst<real_t>::rho_w() * real_t(4. / 3) * cst<real_t>::pi());
+        drw_mom3[c] = drv;
+        rv[c] = cl.rv - drv;
+        const real_t th_c = th[c];
+        th[c] = th_c - drv * d_th_d_rv(cl.T, th_c);
+      }
+    }
+
     // out[c] = -before[c] + after[c]
     __global__ void k_mom_diff(idx_t n_cell, const real_t *__restrict__ after, const real_t *__restrict__ before, real_t *__restrict__ out)
     {
@@ -229,6 +446,7 @@ namespace lcx
     }
 
     int g_solver = -1;
+    int g_staged = -1;         // -1: not read yet ($LCX_COND_STAGED, default on); 0 / 1
     int g_layout = -2;         // -2: not read yet; -1: 8 lanes per cell; 0: automatic; 1..RANGE_MAX: cells per warp of k_cond_range
   }
 
@@ -261,6 +479,13 @@ namespace lcx
     return int(run);
   }
 
+  int cond_staged()
+  {
+    if (g_staged < 0) { const char *v = std::getenv("LCX_COND_STAGED"); g_staged = (v && v[0] == '0') ? 0 : 1; }
+    return g_staged;
+  }
+  void set_cond_staged(int on) { g_staged = on ? 1 : 0; }
+
   int cond_solver()
   {
     if (g_solver < 0)
@@ -284,6 +509,23 @@ namespace lcx
     const int keep_after = step < sstp - 1;
 
     const int run = e->max_count <= FUSED_MAX ? range_run(e) : 0;
+    if (run > 0 && mode == COND_TOMS748 && cond_staged())
+    {
+      const unsigned blocks = div_up(div_up(g.n_cell, run), ST_WARPS);
+      lazy_args z = {};
+      if (e->pending & lcx_engine::PENDING_ATTR)
+      {
+        sd_arrays &o = e->A();
+        z = {e->pending_perm.p, o.rw2.p, o.rd3.p, o.kpa.p, o.vt.p, o.n.p, s.rd3.p, s.kpa.p, s.vt.p, s.n.p};
+        e->pending &= ~unsigned(lcx_engine::PENDING_ATTR);
+        LCX_LAUNCH(e, k_cond_staged<true>, blocks, ST_TPB, 0, g.n_cell, run, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p,
+                   int(step == 0), keep_after, e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p, z);
+        return;
+      }
+      LCX_LAUNCH(e, k_cond_staged<false>, blocks, ST_TPB, 0, g.n_cell, run, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p,
+                 int(step == 0), keep_after, e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p, z);
+      return;
+    }
     if (run > 0)
     {
       const unsigned blocks = div_up(div_up(g.n_cell, run), TPB / 32);

@@ -7,6 +7,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -105,7 +106,7 @@ namespace lcx
     unsigned int increase_sstp_coal;
     unsigned int mig_timeout;       // a neighbour's delivery did not arrive (cross-process wait gave up)
     unsigned long long n_collisions, n_pairs_collided;
-    double puddle[8];               // liq_vol, dry_vol, liq_num, prtcl_num (+spare), accumulated
+    double puddle[8];               // liq_vol, dry_vol, liq_num, prtcl_num, accumulated; [4], [5]: dry volume / SDs lost through the lid
     unsigned long long rcyc_zero, rcyc_one, rcyc_max;   // SDs with n == 0, with n == 1, largest n (recycling)
   };
 }
@@ -206,6 +207,9 @@ struct lcx_engine
 
 namespace lcx
 {
+  // LCX_TRACE=1: every launch is announced on stderr and waited for (finds the kernel that hangs or faults)
+  inline bool trace_launches() { static const bool on = [] { const char *v = std::getenv("LCX_TRACE"); return v && v[0] == '1'; }(); return on; }
+
   inline unsigned div_up(size_t a, size_t b) { return unsigned((a + b - 1) / b); }
 
   // ---- lcx_sort.cu -----------------------------------------------------------------------------------
@@ -248,6 +252,8 @@ namespace lcx
   void set_cond_solver(int mode);
   int cond_layout();                      // lcx_set_cond_layout, else $LCX_COND_LAYOUT, else 0 (automatic)
   void set_cond_layout(int cells_per_warp);
+  int cond_staged();                      // lcx_set_cond_staged, else $LCX_COND_STAGED, else on: the phase-grouped variant of the range kernel
+  void set_cond_staged(int on);
   void cond(lcx_engine *e, real_t dt_sub, real_t RH_max, int step, int sstp);
   void cond_perparticle(lcx_engine *e, real_t dt, real_t RH_max, int sstp, bool mix);
   void cond_perparticle_adaptive(lcx_engine *e, real_t dt, real_t RH_max, int sstp_max, int sstp_act, real_t drw2_eps, real_t drw2_max);
@@ -294,8 +300,10 @@ namespace lcx
       LCX_CUDA(cudaEventCreate(&lcx_pr_.t1));                                  \
       LCX_CUDA(cudaEventRecord(lcx_pr_.t0, (e)->stream));                      \
     }                                                                          \
+    if (::lcx::trace_launches()) std::fprintf(stderr, "[lcx dev %d] %s grid %u\n", (e)->device, #kernel, dim3(grid).x); \
     kernel<<<(grid), (block), (smem), (e)->stream>>>(__VA_ARGS__);             \
     LCX_CUDA(cudaGetLastError());                                              \
+    if (::lcx::trace_launches()) LCX_CUDA(cudaStreamSynchronize((e)->stream)); \
     if ((e)->profiling) {                                                      \
       LCX_CUDA(cudaEventRecord(lcx_pr_.t1, (e)->stream));                      \
       (e)->prof.push_back(lcx_pr_);                                            \

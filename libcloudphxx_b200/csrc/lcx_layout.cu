@@ -235,7 +235,8 @@ namespace lcx
     }
     // stayers move to the front of their cell's new segment in their old order
     __global__ void __launch_bounds__(TPB) k_mv_place_stayers(uint32_t n_cell, int class_bits, const uint32_t *__restrict__ off, const uint32_t *__restrict__ key,
-                                                             const uint32_t *__restrict__ new_off, uint32_t *__restrict__ perm, idx_t *__restrict__ ijk_new)
+                                                             const uint32_t *__restrict__ new_off, uint32_t *__restrict__ perm, idx_t *__restrict__ ijk_new,
+                                                             const idx_t *__restrict__ sid_old, idx_t *__restrict__ sid_new)
     {
       const uint32_t c = (blockIdx.x * TPB + threadIdx.x) / MVG;
       const int l = threadIdx.x % MVG;
@@ -248,7 +249,12 @@ namespace lcx
         const uint32_t t = b + r * MVG + l;
         const bool stays = t < en && (key[t] >> class_bits) == c;
         const unsigned m = group_ballot(stays);
-        if (stays) { const uint32_t d = base + __popc(m & ((1u << l) - 1u)); perm[d] = t; ijk_new[d] = c; }
+        if (stays)
+        {
+          const uint32_t d = base + __popc(m & ((1u << l) - 1u));
+          perm[d] = t; ijk_new[d] = c;
+          if (sid_new) sid_new[d] = sid_old[t];      // gather-on-read: the storage index moves right here, no gather kernel needed
+        }
         base += __popc(m);
       }
     }
@@ -264,7 +270,8 @@ namespace lcx
     }
     __global__ void __launch_bounds__(TPB) k_mv_place_arrivals(uint32_t n_m, uint32_t n_cell, const uint32_t *__restrict__ mkey, const uint32_t *__restrict__ mval,
                                                               const uint32_t *__restrict__ new_off, const uint32_t *__restrict__ arr_off,
-                                                              uint32_t *__restrict__ perm, idx_t *__restrict__ ijk_new)
+                                                              uint32_t *__restrict__ perm, idx_t *__restrict__ ijk_new,
+                                                              const idx_t *__restrict__ sid_old, idx_t *__restrict__ sid_new)
     {
       const uint32_t j = blockIdx.x * TPB + threadIdx.x;
       if (j >= n_m) return;
@@ -275,6 +282,7 @@ namespace lcx
       const uint32_t d = new_off[c] + stay + (j - a0);
       perm[d] = mval[j];
       ijk_new[d] = c;
+      if (sid_new) sid_new[d] = sid_old[mval[j]];
     }
 
     int bit_length(uint64_t v) { int b = 0; while (v) { ++b; v >>= 1; } return b; }
@@ -334,7 +342,9 @@ namespace lcx
   // Re-layout that sorts only the SDs which changed cell.  Returns false (nothing done) when too many SDs moved for it to pay
   // off or when there is no previous grouping to start from; the caller then takes the full radix sort.
   // Result: perm in val[0], new cell indices in A().ijk, segment starts in cell_off, n_part / max_count in the device scalars.
-  static bool relayout_movers(lcx_engine *e, size_t n_old)
+  // perm_out: where the permutation goes (the sort scratch, or - gather-on-read - straight into pending_perm, in which case the
+  // storage indices are moved on the fly as well)
+  static bool relayout_movers(lcx_engine *e, size_t n_old, uint32_t *perm_out, bool move_sid)
   {
     static const bool enabled = [] { const char *v = std::getenv("LCX_RELAYOUT"); return !(v && std::string(v) == "sort"); }();
     const grid_t &g = e->grid;
@@ -364,11 +374,13 @@ namespace lcx
     LCX_LAUNCH(e, k_cell_offsets, div_up(size_t(n_m) + 1, TPB), TPB, 0, size_t(n_m), g.n_cell, 0, mk[res], e->arr_off.p);
     LCX_LAUNCH(e, k_mv_counts, div_up(g.n_cell + 2, TPB), TPB, 0, g.n_cell, e->cell_off.p, mvoff, e->arr_off.p, e->cell_off_new.p);
     exclusive_scan_u32(e, e->cell_off_new.p, size_t(g.n_cell) + 2);
+    const idx_t *sid_old = move_sid ? e->S().sid.p : nullptr;
+    idx_t *sid_new = move_sid ? e->A().sid.p : nullptr;
     LCX_LAUNCH(e, k_mv_place_stayers, cell_blocks, TPB, 0, g.n_cell, g.class_bits, e->cell_off.p, e->key[0].p, e->cell_off_new.p,
-               e->val[0].p, e->A().ijk.p);
+               perm_out, e->A().ijk.p, sid_old, sid_new);
     if (n_m)
       LCX_LAUNCH(e, k_mv_place_arrivals, div_up(n_m, TPB), TPB, 0, n_m, g.n_cell, mk[res], mv[res], e->cell_off_new.p, e->arr_off.p,
-                 e->val[0].p, e->A().ijk.p);
+                 perm_out, e->A().ijk.p, sid_old, sid_new);
     LCX_CUDA(cudaMemcpyAsync(e->cell_off.p, e->cell_off_new.p, (size_t(g.n_cell) + 2) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
     LCX_CUDA(cudaMemsetAsync(&e->scalars.p->max_count, 0, sizeof(unsigned int), e->stream));
     LCX_LAUNCH(e, k_max_count, div_up(g.n_cell, TPB), TPB, 0, g.n_cell, e->cell_off.p, e->scalars.p);
@@ -407,7 +419,14 @@ namespace lcx
 
     // where every survivor goes: perm[new position] = old position, segment starts in cell_off, new cell index in a.ijk
     const uint32_t *perm = nullptr;
-    if (!keep_all && relayout_movers(e, n_old)) perm = e->val[0].p;
+    const bool lazy_wanted = e->lazy_gather && !keep_all;
+    if (lazy_wanted && e->pending_perm.n < e->cap) e->pending_perm.alloc(e->cap);
+    bool sid_moved = false;
+    if (!keep_all && relayout_movers(e, n_old, lazy_wanted ? e->pending_perm.p : e->val[0].p, lazy_wanted))
+    {
+      perm = lazy_wanted ? e->pending_perm.p : e->val[0].p;
+      sid_moved = lazy_wanted;
+    }
     else
     {
       if (keyed_by_transport) LCX_LAUNCH(e, k_iota, div_up(keyed_by_transport, TPB), TPB, 0, keyed_by_transport, e->val[0].p);
@@ -432,17 +451,17 @@ namespace lcx
         add(G, s.vt.p, a.vt.p, 8);
       }
       if (!lazy) { add(G, s.x.p, a.x.p, 8); add(G, s.y.p, a.y.p, 8); add(G, s.z.p, a.z.p, 8); }
-      add(G, s.sid.p, a.sid.p, 4);
+      if (!sid_moved) add(G, s.sid.p, a.sid.p, 4);
       add(G, s.pp_rv.p, a.pp_rv.p, 8); add(G, s.pp_th.p, a.pp_th.p, 8); add(G, s.pp_rh.p, a.pp_rh.p, 8); add(G, s.pp_p.p, a.pp_p.p, 8);
       add(G, s.rc2.p, a.rc2.p, 8);
       LCX_CUDA(cudaEventRecord(e->pre_gather, e->stream));      // uploads of the next step's fields may overtake the gather
-      LCX_LAUNCH(e, k_gather, div_up(n_new, TPB), TPB, 0, n_new, perm, sorted_keys, g.class_bits, a.ijk.p, G);
-      gather_queued = true;
-      if (lazy)      // the permutation lives in sort scratch: keep a copy for whoever consumes the pending attributes
+      if (G.n || sorted_keys)
       {
-        if (e->pending_perm.n < e->cap) e->pending_perm.alloc(e->cap);
-        LCX_CUDA(cudaMemcpyAsync(e->pending_perm.p, perm, n_new * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
+        LCX_LAUNCH(e, k_gather, div_up(n_new, TPB), TPB, 0, n_new, perm, sorted_keys, g.class_bits, a.ijk.p, G);
+        gather_queued = true;
       }
+      if (lazy && perm != e->pending_perm.p)      // full-sort path: the permutation lives in sort scratch, keep a copy for whoever consumes the pending attributes
+        LCX_CUDA(cudaMemcpyAsync(e->pending_perm.p, perm, n_new * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
     }
     e->pending = lazy ? (lcx_engine::PENDING_ATTR | (g.n_dims > 0 ? lcx_engine::PENDING_XYZ : 0u)) : 0u;
     e->cur ^= 1;

@@ -800,42 +800,46 @@ namespace lcx
     return real_t(1) + cb * boost;
   }
 
+  // drw2/dt in the single-quotient form; k may live in shared memory (the staged condensation kernel reads it from there)
+  template <class real_t>
+  LCX_HD real_t drw2_dt_fast(real_t rw2, real_t rd3, real_t rd3_dry, real_t vt_cRe, const cond_cell_consts<real_t> &k)
+  {
+    const real_t inv_rw = lcx_rsqrt(rw2);
+    const real_t rw = rw2 * inv_rw;
+    const real_t rw3 = rw2 * rw;
+    const real_t Re = vt_cRe * rw;
+    // Sh = Nu(Sc, Re), Nu = Nu(Pr, Re): the Re^0.077 factor is shared, the two cube roots go through one code site
+    const real_t boost = (Re > real_t(1)) ? tmax(real_t(1), real_t(pow(Re, real_t(.077)))) : real_t(1);
+    real_t nu[2] = {k.Sc, k.Pr};
+    // (both rounds unrolled on purpose: the two cube-root chains are independent and interleave; measured 5 % on the kernel)
+    for (int q = 0; q < 2; ++q)
+    {
+      const real_t x = Re * nu[q];
+      const real_t cb = (fabs(x) < real_t(LCX_KC(9, 1e-4)))
+        ? real_t(1) + x * (real_t(LCX_KC(10, 1. / 3)) - x * (real_t(LCX_KC(11, 1. / 9)) - x * real_t(LCX_KC(12, 5. / 81))))
+        : (x <= real_t(0.5)) ? real_t(lcx_cbrt1p_mid(x)) : real_t(lcx_cbrt_ge1(real_t(1) + x));
+      nu[q] = real_t(1) + cb * boost;
+    }
+    const real_t Sh = nu[0], Nu = nu[1];
+    const real_t KnD = k.lam_D * inv_rw, KnK = k.lam_K * inv_rw;
+    const real_t c171 = real_t(LCX_KC(13, 1.71)), c133 = real_t(LCX_KC(14, 1.33));
+    const real_t bDn = real_t(1) + KnD, bDd = real_t(1) + KnD * (c171 + c133 * KnD);
+    const real_t bKn = real_t(1) + KnK, bKd = real_t(1) + KnK * (c171 + c133 * KnK);
+    const real_t awn = rw3 - rd3, awd = rw3 - rd3_dry;
+    const real_t klv = lcx_exp_small(k.A * inv_rw);
+    const real_t tD = bDn * Sh, tK = bKn * Nu;
+    const real_t num = (awd - awn * klv * k.inv_RH) * (tD * tK);
+    const real_t den = awd * (k.X * bDd * tK + k.Y * bKd * tD);
+    return lcx_div(num, cst<real_t>::rho_w() * den);
+  }
+
   template <class real_t>
   struct growth_fast
   {
     real_t rw2_old, dt, rd3, rd3_dry, vt_cRe;   // rd3_dry = rd3 (1 - kappa), vt_cRe = vt * c_Re
     cond_cell_consts<real_t> k;
 
-    LCX_HD real_t drw2_dt(real_t rw2) const
-    {
-      const real_t inv_rw = lcx_rsqrt(rw2);
-      const real_t rw = rw2 * inv_rw;
-      const real_t rw3 = rw2 * rw;
-      const real_t Re = vt_cRe * rw;
-      // Sh = Nu(Sc, Re), Nu = Nu(Pr, Re): the Re^0.077 factor is shared, the two cube roots go through one code site
-      const real_t boost = (Re > real_t(1)) ? tmax(real_t(1), real_t(pow(Re, real_t(.077)))) : real_t(1);
-      real_t nu[2] = {k.Sc, k.Pr};
-      // (both rounds unrolled on purpose: the two cube-root chains are independent and interleave; measured 5 % on the kernel)
-      for (int q = 0; q < 2; ++q)
-      {
-        const real_t x = Re * nu[q];
-        const real_t cb = (fabs(x) < real_t(LCX_KC(9, 1e-4)))
-          ? real_t(1) + x * (real_t(LCX_KC(10, 1. / 3)) - x * (real_t(LCX_KC(11, 1. / 9)) - x * real_t(LCX_KC(12, 5. / 81))))
-          : (x <= real_t(0.5)) ? real_t(lcx_cbrt1p_mid(x)) : real_t(lcx_cbrt_ge1(real_t(1) + x));
-        nu[q] = real_t(1) + cb * boost;
-      }
-      const real_t Sh = nu[0], Nu = nu[1];
-      const real_t KnD = k.lam_D * inv_rw, KnK = k.lam_K * inv_rw;
-      const real_t c171 = real_t(LCX_KC(13, 1.71)), c133 = real_t(LCX_KC(14, 1.33));
-      const real_t bDn = real_t(1) + KnD, bDd = real_t(1) + KnD * (c171 + c133 * KnD);
-      const real_t bKn = real_t(1) + KnK, bKd = real_t(1) + KnK * (c171 + c133 * KnK);
-      const real_t awn = rw3 - rd3, awd = rw3 - rd3_dry;
-      const real_t klv = lcx_exp_small(k.A * inv_rw);
-      const real_t tD = bDn * Sh, tK = bKn * Nu;
-      const real_t num = (awd - awn * klv * k.inv_RH) * (tD * tK);
-      const real_t den = awd * (k.X * bDd * tK + k.Y * bKd * tD);
-      return lcx_div(num, cst<real_t>::rho_w() * den);
-    }
+    LCX_HD real_t drw2_dt(real_t rw2) const { return drw2_dt_fast(rw2, rd3, rd3_dry, vt_cRe, k); }
     LCX_HD real_t operator()(const real_t &x) const { return (rw2_old + dt * drw2_dt(x) - x); }
   };
 

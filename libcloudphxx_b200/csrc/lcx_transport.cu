@@ -109,7 +109,7 @@ namespace lcx
 #endif
     // leavers through a slab face are listed on the fly (bcnd.ipp:160-172 does two copy_if sweeps): storage index as the later
     // sort key, physical index as the value; the lists are unordered (atomic slots) until lcx_migr_put sorts them
-    struct mig_lists { const idx_t *sid; uint32_t *key[2], *val[2]; unsigned int *count[2]; unsigned cap; };
+    struct mig_lists { const idx_t *sid; uint32_t *key[2], *val[2]; unsigned int *count[2]; unsigned cap; double *top_loss; };
 
     // LAZY: positions still lie in the previous layout (lcx_engine::PENDING_XYZ): read through the permutation, written in place
     template <bool LAZY>
@@ -142,6 +142,7 @@ namespace lcx
         if (LAZY) { const uint32_t src = perm[t]; x = g.nx ? xi[src] : 0; y = g.ny ? yi[src] : 0; z = g.nz ? zi[src] : 0; }
         else      { x = g.nx ? xs[t] : 0; y = g.ny ? ys[t] : 0; z = g.nz ? zs[t] : 0; }
         n_t n = ns[t];
+        const n_t n_in = n;
 
         if (P.adve && g.n_dims > 0)
         {
@@ -225,7 +226,14 @@ namespace lcx
           {
             if (!P.periodic_topbot)
             {
-              if (z >= g.z1) n = 0;
+              if (z >= g.z1)
+              {
+                // leaves through the lid without any accounting in the reference (bcnd.ipp:330-336); freshly collided SDs do so
+                // regularly: their fall speed is the "invalid" marker -1, i.e. they rise by dt metres.  Rare, so the tally for
+                // conservation checks (lcx_top_loss) is a plain atomic - it feeds no result.
+                if (n != 0) { atomicAdd(M.top_loss, double(count_vol(real_t(n), rd3[t], real_t(1.)))); atomicAdd(M.top_loss + 1, 1.0); }
+                n = 0;
+              }
               if (z < g.z0)
               {
                 const real_t nf = real_t(n);
@@ -244,7 +252,7 @@ namespace lcx
         if (g.nx) xs[t] = x;
         if (g.ny) ys[t] = y;
         if (g.nz) zs[t] = z;
-        ns[t] = n;
+        if (n != n_in) ns[t] = n;      // only SDs that left the domain change their multiplicity here
         if (fl)
         {
           const unsigned slot = atomicAdd(M.count[fl - 1], 1u);
@@ -330,7 +338,7 @@ namespace lcx
     // waits (on the device) until the deliveries with sequence number `seq` have been published in this engine's own inbox
     // headers; only used when the neighbour lives in another process (other GPU: its progress does not depend on this stream).
     // Gives up after ~20 s instead of hanging the GPU.
-    __global__ void k_mig_wait(const mig_hdr *h0, const mig_hdr *h1, unsigned seq, dev_scalars *sc)
+    __global__ void k_mig_wait(const mig_hdr *h0, const mig_hdr *h1, unsigned seq, dev_scalars *sc, long long max_cycles)
     {
       const long long t0 = clock64();
       for (int q = 0; q < 2; ++q)
@@ -340,7 +348,7 @@ namespace lcx
         while (*reinterpret_cast<const volatile unsigned int *>(&h->seq) != seq)
         {
           __nanosleep(200);
-          if (clock64() - t0 > 40000000000ll) { sc->mig_timeout = 1u; return; }
+          if (clock64() - t0 > max_cycles) { sc->mig_timeout = 1u; return; }
         }
       }
       __threadfence_system();
@@ -403,7 +411,7 @@ namespace lcx
     if (e->red_partial.n < size_t(blocks) * 4) { LCX_CUDA(cudaStreamSynchronize(e->stream)); e->red_partial.alloc(size_t(blocks) * 4 + 1024); }
     mig_lists M = {};
     M.sid = s.sid.p; M.cap = unsigned(e->mig_cap);
-    M.count[0] = &e->scalars.p->n_lft; M.count[1] = &e->scalars.p->n_rgt;
+    M.count[0] = &e->scalars.p->n_lft; M.count[1] = &e->scalars.p->n_rgt; M.top_loss = &e->scalars.p->puddle[4];
     for (int sd = 0; sd < 2; ++sd) { M.key[sd] = e->mig_key[sd][0].p; M.val[sd] = e->mig_val[sd][0].p; }
     if (P.bcond_lft == LCX_BCOND_DISTMEM || P.bcond_rgt == LCX_BCOND_DISTMEM)
       LCX_CUDA(cudaMemsetAsync(&e->scalars.p->n_lft, 0, 2 * sizeof(unsigned int), e->stream));
@@ -427,6 +435,8 @@ namespace lcx
 
   // Sorts each side's leavers by storage index (the reference lists them in ascending SD index: bcnd.ipp:160-172), packs them
   // into the neighbour's inbox and publishes the delivery.  One host read-back: the two counts.
+  static bool mig_debug() { static const bool on = [] { const char *v = std::getenv("LCX_MIG_DEBUG"); return v && v[0] == '1'; }(); return on; }
+
   void migr_put(lcx_engine *e, int64_t *n_lft, int64_t *n_rgt)
   {
     sd_arrays &s = e->S();
@@ -467,6 +477,7 @@ namespace lcx
     }
     LCX_CUDA(cudaEventRecord(e->ev_put, e->stream));
     *n_lft = count[0]; *n_rgt = count[1];
+    if (mig_debug()) std::fprintf(stderr, "[mig dev %d] put seq %u: %u left, %u right (n_part %zu)\n", e->device, seq, count[0], count[1], e->n_part);
   }
 
   // Appends the arrivals: first the right neighbour's left-movers, then the left neighbour's right-movers, each in the
@@ -487,14 +498,19 @@ namespace lcx
       if (nb[q]) { if (nb[q] != e) LCX_CUDA(cudaStreamWaitEvent(e->stream, nb[q]->ev_put, 0)); }
       else wait_for[q] = box_hdr(e->inbox[q].p, parity);
     }
+    static const long long max_cycles = [] { const char *v = std::getenv("LCX_MIG_TIMEOUT_S"); return (long long)((v ? std::atof(v) : 20.) * 2e9); }();
     if (wait_for[0] || wait_for[1])
-      LCX_LAUNCH(e, k_mig_wait, 1, 1, 0, wait_for[0], wait_for[1], seq, e->scalars.p);
+      LCX_LAUNCH(e, k_mig_wait, 1, 1, 0, wait_for[0], wait_for[1], seq, e->scalars.p, max_cycles);
     mig_hdr h[2] = {};
     for (int q = 0; q < 2; ++q)
       if (dm[q]) LCX_CUDA(cudaMemcpyAsync(&h[q], box_hdr(e->inbox[q].p, parity), sizeof(mig_hdr), cudaMemcpyDeviceToHost, e->stream));
     LCX_CUDA(cudaMemcpyAsync(e->h_scalars, e->scalars.p, sizeof(dev_scalars), cudaMemcpyDeviceToHost, e->stream));
     LCX_CUDA(cudaStreamSynchronize(e->stream));
-    if (e->h_scalars->mig_timeout) throw error("x-slab migration: a neighbour's delivery did not arrive within 20 s");
+    if (mig_debug()) std::fprintf(stderr, "[mig dev %d] take seq %u: headers (%u, %u) (%u, %u) timeout %u\n", e->device, seq, h[0].seq, h[0].count, h[1].seq, h[1].count, e->h_scalars->mig_timeout);
+    if (e->h_scalars->mig_timeout)
+      throw error("x-slab migration: a neighbour's delivery did not arrive in time (waiting for sequence number " + std::to_string(seq) + "; inbox from the right holds " +
+                  std::to_string(h[0].seq) + " with " + std::to_string(h[0].count) + " super-droplets, inbox from the left " + std::to_string(h[1].seq) + " with " +
+                  std::to_string(h[1].count) + "; $LCX_MIG_TIMEOUT_S)");
     sd_arrays &s = e->S();
     for (int q = 0; q < 2; ++q)
     {

@@ -27,6 +27,7 @@ def lib():
         l.lcx_cell_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         l.lcx_migr_real_attrs.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         l.lcx_puddle.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        l.lcx_top_loss.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         l.lcx_coal_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         _lib = l
     return _lib
@@ -54,6 +55,15 @@ def set_cond_layout(cells_per_warp):
 
 def get_cond_layout():
     return int(lib().lcx_get_cond_layout())
+
+
+def set_cond_staged(on):
+    """phase-grouped form of the run-per-warp condensation kernel (default on; bit-identical results either way)"""
+    lib().lcx_set_cond_staged(int(bool(on)))
+
+
+def get_cond_staged():
+    return bool(lib().lcx_get_cond_staged())
 
 
 def check(rc):
@@ -122,3 +132,9 @@ class Engine:
         out = (C.c_double * 14)()
         check(self.l.lcx_puddle(self.h, out))
         return list(out)
+
+    def top_loss(self):
+        """(dry volume, number of super-droplets) that left through the lid since creation"""
+        out = (C.c_double * 2)()
+        check(self.l.lcx_top_loss(self.h, out))
+        return out[0], out[1]

@@ -214,6 +214,14 @@ namespace libcloudphxx
 
       virtual void step_async(const opts_t<real_t> &) { unsupported("step_async"); }
 
+      // The ORDER of the virtual methods is the reference's (lgrngn/particles.hpp:20-125) - it fixes the v-table slots, so a host
+      // model compiled against the reference's headers calls the right methods when linked to this library; checked by
+      // tests/test_cpu_abi.py with lgrngn_abi_probe.hpp (and at run time through lgrngn_b200_abi_layout()).
+      // per-cell fields (result is fetched with outbuf())
+      virtual void diag_sd_conc()                                    { unsupported("diag_sd_conc"); }
+      virtual void diag_pressure()                                   { unsupported("diag_pressure"); }
+      virtual void diag_temperature()                                { unsupported("diag_temperature"); }
+      virtual void diag_RH()                                         { unsupported("diag_RH"); }
       // selectors (fill the per-SD mask used by the following *_mom / sd_conc call)
       virtual void diag_all()                                        { unsupported("diag_all"); }
       virtual void diag_rw_ge_rc()                                   { unsupported("diag_rw_ge_rc"); }
@@ -233,11 +241,7 @@ namespace libcloudphxx
       virtual void diag_kappa_rng_cons(const real_t&, const real_t&) { unsupported("diag_kappa_rng_cons"); }
       virtual void diag_ice_cons()                                   { unsupported("diag_ice_cons"); }
       virtual void diag_water_cons()                                 { unsupported("diag_water_cons"); }
-      // per-cell fields / moments (result is fetched with outbuf())
-      virtual void diag_sd_conc()                                    { unsupported("diag_sd_conc"); }
-      virtual void diag_pressure()                                   { unsupported("diag_pressure"); }
-      virtual void diag_temperature()                                { unsupported("diag_temperature"); }
-      virtual void diag_RH()                                         { unsupported("diag_RH"); }
+      // moments (result is fetched with outbuf())
       virtual void diag_dry_mom(const int&)                          { unsupported("diag_dry_mom"); }
       virtual void diag_wet_mom(const int&)                          { unsupported("diag_wet_mom"); }
       virtual void diag_ice_a_mom(const int&)                        { unsupported("diag_ice_a_mom"); }

@@ -19,6 +19,7 @@
 #include "lcx_b200.h"
 #include "lcx_physics.h"
 #include "particles_b200.h"
+#include <lgrngn_abi_probe.hpp>
 
 #include <algorithm>
 #include <cmath>
@@ -1309,8 +1310,15 @@ namespace libcloudphxx
           step_async(opts);
         }
 
+        // diagnostics need the engines, which init() creates (the reference asserts here; a release build of it would crash)
+        void ready() const
+        {
+          for (const auto &s : slabs)
+            if (!s->e) throw std::runtime_error("libcloudph++: please call init() before asking for diagnostics");
+        }
+
         // selectors
-        void sel(int kind, int attr, real_t lo, real_t hi, bool cons) { for (auto &s : slabs) chk(lcx_moms_select(s->e, kind, attr, lo, hi, cons)); }
+        void sel(int kind, int attr, real_t lo, real_t hi, bool cons) { ready(); for (auto &s : slabs) chk(lcx_moms_select(s->e, kind, attr, lo, hi, cons)); }
         void diag_all() override { sel(LCX_SEL_ALL, 0, 0, 0, false); }
         void diag_rw_ge_rc() override { sel(LCX_SEL_RW_GE_RC, 0, 0, 0, false); }
         void diag_RH_ge_Sc() override { sel(LCX_SEL_RH_GE_SC, 0, 0, 0, false); }
@@ -1337,21 +1345,22 @@ namespace libcloudphxx
         { throw std::runtime_error("libcloudph++: chemistry is switched off in opts_init, but diag_chem was called"); }
 
         // moments and fields
-        void mom(int attr, real_t power) { for (auto &s : slabs) chk(lcx_moms_calc(s->e, attr, power, 1)); }
+        void mom(int attr, real_t power) { ready(); for (auto &s : slabs) chk(lcx_moms_calc(s->e, attr, power, 1)); }
         void diag_dry_mom(const int &k) override { mom(LCX_A_RD3, k / 3.); }
         void diag_wet_mom(const int &k) override { mom(LCX_A_RW2, k / 2.); }
         void diag_kappa_mom(const int &k) override { mom(LCX_A_KPA, k); }
-        void diag_sd_conc() override { for (auto &s : slabs) chk(lcx_diag_sd_conc(s->e)); }
-        void diag_pressure() override { for (auto &s : slabs) s->diag_field(LCX_F_P); }
-        void diag_temperature() override { for (auto &s : slabs) s->diag_field(LCX_F_T); }
-        void diag_RH() override { for (auto &s : slabs) s->diag_field(LCX_F_RH); }
-        void diag_precip_rate() override { for (auto &s : slabs) chk(lcx_diag_precip_rate(s->e)); }
-        void diag_max_rw() override { for (auto &s : slabs) chk(lcx_diag_max_rw(s->e)); }
-        void diag_wet_mass_dens(const real_t &rad, const real_t &sig0) override { for (auto &s : slabs) chk(lcx_diag_mass_dens(s->e, LCX_A_RW2, rad, sig0, 1. / 2.)); }
-        void diag_vel_div() override { for (auto &s : slabs) chk(lcx_diag_vel_div(s->e, s->oi.dt)); }
+        void diag_sd_conc() override { ready(); for (auto &s : slabs) chk(lcx_diag_sd_conc(s->e)); }
+        void diag_pressure() override { ready(); for (auto &s : slabs) s->diag_field(LCX_F_P); }
+        void diag_temperature() override { ready(); for (auto &s : slabs) s->diag_field(LCX_F_T); }
+        void diag_RH() override { ready(); for (auto &s : slabs) s->diag_field(LCX_F_RH); }
+        void diag_precip_rate() override { ready(); for (auto &s : slabs) chk(lcx_diag_precip_rate(s->e)); }
+        void diag_max_rw() override { ready(); for (auto &s : slabs) chk(lcx_diag_max_rw(s->e)); }
+        void diag_wet_mass_dens(const real_t &rad, const real_t &sig0) override { ready(); for (auto &s : slabs) chk(lcx_diag_mass_dens(s->e, LCX_A_RW2, rad, sig0, 1. / 2.)); }
+        void diag_vel_div() override { ready(); for (auto &s : slabs) chk(lcx_diag_vel_div(s->e, s->oi.dt)); }
 
         real_t *outbuf() override
         {
+          ready();
           if (!multi) return one().outbuf();
           gathered.resize(size_t(m1(glob.nx)) * m1(glob.ny) * m1(glob.nz));
           for (auto &s : slabs)
@@ -1365,11 +1374,13 @@ namespace libcloudphxx
         std::vector<real_t> get_attr(const std::string &name) override
         {
           if (multi) throw std::runtime_error("get_attr doesnt work in multi_CUDA backend.");
+          ready();
           return one().get_attr(name);
         }
 
         std::map<common::output_t, real_t> diag_puddle() override
         {
+          ready();
           std::map<common::output_t, real_t> res;
           for (int q = 0; q < 14; ++q) res[static_cast<common::output_t>(q)] = 0;
           for (auto &s : slabs) for (const auto &kv : s->diag_puddle()) res[kv.first] += kv.second;
@@ -1711,6 +1722,13 @@ int lgrngn_b200_get_layout(void *proto, unsigned int *sid, unsigned int *ijk, lo
   });
 }
 
+
+long lgrngn_b200_abi_layout(char *buf, long size)
+{
+  const std::string s = lgrngn_abi_probe::describe_all();
+  if (buf && size > 0) { std::strncpy(buf, s.c_str(), size_t(size) - 1); buf[size - 1] = 0; }
+  return long(s.size());
+}
 
 double lgrngn_b200_common(const char *name, double a, double b, double c, double d, double e)
 {

@@ -48,6 +48,10 @@ int   lgrngn_b200_get_layout(void *particles_proto, unsigned int *sid, unsigned 
 /* fields ALREADY RESIDENT in device memory: no host<->device field traffic.  flags: bit0 adve, bit1 sedi, bit2 cond, */
 /* bit3 coal.  Used by bench.py for the device-resident throughput figure.                                            */
 int   lgrngn_b200_step_resident(void *particles_proto, int flags);
+/* Binary-compatibility guard: the layout of opts_init_t / opts_t / arrinfo_t and the v-table slots of particles_proto_t as THIS  */
+/* library was compiled (text, see host/include/lgrngn_abi_probe.hpp); returns the length.  A host model built with other headers */
+/* (the reference's) compiles the same probe against them and compares the two strings before calling factory().                */
+long  lgrngn_b200_abi_layout(char *buf, long size);
 /* scalar thermodynamic helpers and constants of libcloudphxx::common as the reference's Python module exposes them  */
 /* (bindings/python/common.hpp:20-170, lib.cpp:40-120); unknown names give NaN                                       */
 double lgrngn_b200_common(const char *name, double a, double b, double c, double d, double e);

@@ -1,6 +1,7 @@
 """torchrun worker of tests/test_gpu_multi.py: one rank per GPU, each owning an x-slab; checks the invariants the
 reference's own distributed test asserts (tests/mpi/mpi_adve_test.cpp:143-256): after advecting once round the periodic
 domain with C = +1 every per-cell statistic is back where it started, and nothing is lost or duplicated on the way."""
+import ctypes as C
 import os
 import sys
 
@@ -15,6 +16,57 @@ from libcloudphxx_b200 import distributed as D, lgrngn as L   # noqa: E402
 from tests import support as S                                # noqa: E402
 
 
+def full_microphysics(lib, rank, world, local):
+    """cfg5-shaped: Cx = 0.5 (half a column of super-droplets crosses every slab face each step, most SDs change cell, so the
+    re-layout takes its full-sort path), a rain mode that falls out, condensation + coalescence under the Philox stream:
+    the dry volume of all ranks + what left the domain is conserved, every rank keeps its SDs in step"""
+    from libcloudphxx_b200 import engine as E
+    nx, ny, nz, steps = [int(v) for v in os.environ.get("LCX_DIST_FULL_SHAPE", "6,8,10,24").split(",")]
+    lib.lib.lgrngn_b200_set_rng_mode.argtypes = [C.c_int]
+    lib.lib.lgrngn_b200_set_rng_mode(0)
+    D.configure(lib, rank, world, lft_x1=nx * 20.0, rgt_x0=0.0, n_x_tot=nx * world)
+    oi, o, f = S.box_3d(lib, nx=nx, ny=ny, nz=nz, sd_conc=40, rain_mode=True, cx=0.5, n_sd_max=int(nx * ny * nz * 40 * 1.25))
+    oi.rng_seed = 44 + rank
+    oi.dev_id = local
+    p = lib.factory(L.backend_t.CUDA, oi)
+    p.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
+    D.connect(lib, p, rank, world)
+    eng = D.engine_of(lib, p)
+
+    def volume():
+        p.diag_all(); p.diag_dry_mom(3)
+        live = float((p.outbuf().reshape(nx, ny, nz) * f["rhod"]).sum() * 20.0 ** 3 * 4.0 / 3.0 * np.pi)
+        tot = [None] * world
+        dist.all_gather_object(tot, (live, p.diag_puddle()["dry_volume"], eng.top_loss()[0], eng.n_part()))
+        return tot
+    v0 = volume()
+    total0 = sum(t[0] + t[1] + t[2] for t in v0)
+    sent = []
+    import time
+    for step in range(steps):
+        try:
+            p.step_sync(o, f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"])
+            p.step_async(o)
+        except Exception as ex:
+            print("rank %d failed at step %d: %s" % (rank, step, ex), file=sys.stderr, flush=True)
+            time.sleep(8)            # lets the other ranks report their own view before the launcher tears everything down
+            raise
+        sent.append(D.migr_stats(lib, p))
+    v1 = volume()
+    total1 = sum(t[0] + t[1] + t[2] for t in v1)
+    assert abs(total1 - total0) <= 1e-10 * total0, (total0, total1)
+    assert sum(t[1] for t in v1) > 0, "nothing rained out"
+    moved = [None] * world
+    dist.all_gather_object(moved, sent)
+    for step in range(steps):      # what every rank sent right is what its right neighbour received from the left, and vice versa
+        for r in range(world):
+            assert moved[r][step][1] == moved[(r + 1) % world][step][3], (step, r)
+            assert moved[r][step][0] == moved[(r - 1) % world][step][2], (step, r)
+    assert sum(m[1] for m in sent) > steps * 0.3 * ny * nz * 40, "hardly anything migrated"
+    if rank == 0:
+        print("DIST_FULL_OK world=%d sd=%s" % (world, [t[3] for t in v1]))
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     n_dev = torch.cuda.device_count()
@@ -25,6 +77,11 @@ def main():
     else:
         dist.init_process_group("gloo")
     lib = L.b200()
+    if "--full" in sys.argv:
+        full_microphysics(lib, rank, world, local)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     nx_of = lambda r: r + 2                     # unequal slabs, like mpi_adve_test.cpp:88
     nx, ny, nz = nx_of(rank), 3, 4
     n_x_tot = sum(nx_of(r) for r in range(world))

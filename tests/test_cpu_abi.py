@@ -129,3 +129,85 @@ def test_efficiency_tables_are_shipped():
         t = np.fromfile(os.path.join(ROOT, "libcloudphxx_b200", "data", name + ".f64"))
         assert t.size == 1 + 201 * 202 // 2 and t[0] == 1100.0
         assert 0.0 <= t[1:].min() and t[1:].max() < 1e2
+
+
+# ---- binary compatibility with callers compiled against the reference's own headers -------------------------------------------
+REF_ROOT = "/root/reference"
+GOLDEN_LAYOUT = os.path.join(ROOT, "tests", "golden", "abi_layout_reference.txt")
+OWN_INC = os.path.join(ROOT, "libcloudphxx_b200", "host", "include")
+
+
+def build_probe(tmp_path, include_dirs, name):
+    import subprocess
+    exe = str(tmp_path / name)
+    cmd = ["g++", "-std=c++17", "-w"] + [a for d in include_dirs for a in ("-I", d)] + ["-I", OWN_INC, os.path.join(ROOT, "tests", "cpp", "abi_probe_main.cpp"), "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+
+
+def test_api_layout_equals_the_reference_layout(tmp_path):
+    """sizes, member offsets, enum values and v-table slots seen through THIS library's headers == those recorded from the
+    reference's headers (tests/golden/abi_layout_reference.txt): a model compiled against either can link to liblgrngn_b200.so"""
+    own = build_probe(tmp_path, [], "probe_own")
+    assert own == open(GOLDEN_LAYOUT).read()
+    assert "diag_sd_conc=5" in own and "outbuf=" in own
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF_ROOT, "include")), reason="reference headers only exist in the development container")
+def test_recorded_reference_layout_is_current(tmp_path):
+    ref = build_probe(tmp_path, [os.path.join(ROOT, "oracle", "boost_shim"), os.path.join(REF_ROOT, "include"), "/usr/local/cuda/include"], "probe_ref")
+    assert ref == open(GOLDEN_LAYOUT).read()
+
+
+def test_library_reports_the_layout_it_was_built_with():
+    lib = L.b200().lib
+    lib.lgrngn_b200_abi_layout.restype = C.c_long
+    lib.lgrngn_b200_abi_layout.argtypes = [C.c_char_p, C.c_long]
+    n = lib.lgrngn_b200_abi_layout(None, 0)
+    buf = C.create_string_buffer(n + 1)
+    lib.lgrngn_b200_abi_layout(buf, n + 1)
+    assert buf.value.decode() == open(GOLDEN_LAYOUT).read()
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF_ROOT, "include")), reason="reference headers only exist in the development container")
+def test_caller_built_with_reference_headers_links_and_calls(tmp_path):
+    """a translation unit that only ever saw the REFERENCE's headers, linked to liblgrngn_b200.so: factory() (options passed by
+    value across the boundary) answers with the reference's error for a back-end that is not compiled in, and - where no GPU
+    exists - refuses the CUDA back-end instead of computing on the host"""
+    import subprocess
+    src = tmp_path / "caller.cpp"
+    src.write_text(r'''
+#include <libcloudph++/lgrngn/factory.hpp>
+#include <iostream>
+using namespace libcloudphxx::lgrngn;
+int main()
+{
+  opts_init_t<double> oi;
+  oi.dt = 1; oi.sd_conc = 8; oi.n_sd_max = 8; oi.kernel = kernel_t::golovin; oi.kernel_parameters = {1500.};
+  oi.terminal_velocity = vt_t::beard77fast;
+  int ok = 0;
+  try { factory<double>(serial, oi); } catch (const std::runtime_error &e) { std::cout << "serial: " << e.what() << "\n"; ++ok; }
+  try
+  {
+    particles_proto_t<double> *p = factory<double>(CUDA, oi);
+    std::cout << "cuda: created n_sd_max=" << p->opts_init->n_sd_max << " kernel=" << int(p->opts_init->kernel) << "\n";
+    try { p->diag_sd_conc(); } catch (const std::exception &e) { std::cout << "diag: " << e.what() << "\n"; }
+    delete p;
+    ++ok;
+  }
+  catch (const std::runtime_error &e) { std::cout << "cuda: " << e.what() << "\n"; ++ok; }
+  return ok == 2 ? 0 : 1;
+}
+''')
+    exe = str(tmp_path / "caller")
+    libdir = os.path.join(ROOT, "libcloudphxx_b200", "lib")
+    cmd = ["g++", "-std=c++17", "-w", "-I", os.path.join(ROOT, "oracle", "boost_shim"), "-I", os.path.join(REF_ROOT, "include"),
+           "-I", "/usr/local/cuda/include", str(src), "-o", exe, "-L", libdir, "-llgrngn_b200", "-llcx_b200", "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "serial: libcloudph++: serial backend was not compiled" in out.stdout
+    assert "cuda: created n_sd_max=8 kernel=2" in out.stdout, out.stdout                    # options survived the trip by value
+    assert "diag: libcloudph++: please call init() before asking for diagnostics" in out.stdout, out.stdout      # v-table slot 5 is diag_sd_conc
