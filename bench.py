@@ -45,6 +45,7 @@ KERNEL_BYTES_EXACT = {        # gather-on-read variants (the default): the re-la
     # kernel (permutation 4 + five attributes read 40 + cell index 4 + five attributes written 40), that of x, y, z in the
     # transport kernel (+ permutation 4), and k_gather is left with the storage index (permutation 4 + read 4 + write 4)
     "(k_cond_range<M, true>)": 88.0, "k_transport<true>": 76.0,
+    "k_cond_staged<true>": 88.0, "k_cond_staged<false>": 52.0,      # the phase-grouped form of the range kernel: same traffic
 }
 LAZY = os.environ.get("LCX_LAZY_GATHER", "1") != "0"
 

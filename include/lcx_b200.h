@@ -163,7 +163,7 @@ int  lcx_get_cond_solver(void);
 /* run of k consecutive cells with its lanes balanced over the run's super-droplets                                       */
 int  lcx_set_cond_layout(int cells_per_warp);
 int  lcx_get_cond_layout(void);
-/* the run-per-warp kernel in its phase-grouped form (default 1): droplets that need a 4th / 5th growth-law evaluation are parked   */
+/* the run-per-warp kernel in its phase-grouped form (opt-in, default 0; measured slower on B200: DESIGN.md section 8): droplets that need a 4th / 5th growth-law evaluation are parked   */
 /* in shared memory and processed a full warp at a time; results are bit-identical to the plain form (0), which stays for A/B runs */
 int  lcx_set_cond_staged(int on);
 int  lcx_get_cond_staged(void);

@@ -236,6 +236,7 @@ namespace lcx
     // drained at the end of the run.  Same trial points, same arithmetic per droplet: rw2 is bit-identical to k_cond_range.  The
     // per-cell sums of n r^3 are taken in a final sweep over the run in exactly the order k_cond_range uses, so th and rv are
     // bit-identical as well.  Queue entry: 13 doubles + 2 words; 13 KB of shared memory per warp -> 2 warps per CTA, 7 CTAs per SM.
+    // MEASURED (B200, cfg4 slab): slower than k_cond_range despite the better lane use - see cond_staged() below; kept as an opt-in.
     constexpr int ST_TPB = 64, ST_WARPS = ST_TPB / 32, QCAP = 64, QF0 = 11, QF1 = 13;
 #ifndef LCX_COND_ST_MINB
 #define LCX_COND_ST_MINB 7
@@ -481,7 +482,10 @@ namespace lcx
 
   int cond_staged()
   {
-    if (g_staged < 0) { const char *v = std::getenv("LCX_COND_STAGED"); g_staged = (v && v[0] == '0') ? 0 : 1; }
+    // off by default: measured on the cfg4 slab it raises the active lanes from 20.3 to 25.8 of 32 and executes 12 % fewer warp
+    // instructions, but its 29 KB of queues per CTA leave 14 warps per SM instead of 29 and the issue rate drops from 66 % to 42 %:
+    // 9.75 ms against 7.12 ms under ncu (profiles/r02_cond_staged_vs_range_ncu.md)
+    if (g_staged < 0) { const char *v = std::getenv("LCX_COND_STAGED"); g_staged = (v && v[0] == '1') ? 1 : 0; }
     return g_staged;
   }
   void set_cond_staged(int on) { g_staged = on ? 1 : 0; }

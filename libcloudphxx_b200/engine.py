@@ -58,7 +58,7 @@ def get_cond_layout():
 
 
 def set_cond_staged(on):
-    """phase-grouped form of the run-per-warp condensation kernel (default on; bit-identical results either way)"""
+    """phase-grouped form of the run-per-warp condensation kernel (opt-in, default off; bit-identical results either way)"""
     lib().lcx_set_cond_staged(int(bool(on)))
 
 

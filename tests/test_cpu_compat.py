@@ -14,6 +14,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 COMPAT = os.path.join(ROOT, "libcloudphxx_b200", "compat")
 REF_TESTS = "/root/reference/tests/python"
+FIXTURES = os.path.join(ROOT, "tests", "golden", "ref_scripts")      # verbatim copies, so the scripts also run where the reference is absent
 
 SCRIPTS = ["unit/uniform_init.py", "unit/lgrngn_adve.py", "unit/terminal_velocities.py", "unit/multiple_kappas.py",
            "unit/adve_scheme.py", "unit/lgrngn_subsidence.py", "physics/test_coal.py", "physics/lgrngn_cond.py", "physics/puddle.py"]
@@ -30,8 +31,13 @@ def env(impl):
 
 @pytest.mark.skipif(not os.path.isdir(REF_TESTS), reason="reference test scripts are not mounted here")
 @pytest.mark.parametrize("script", SCRIPTS)
+def test_fixture_copy_is_the_reference_script(script):
+    assert open(os.path.join(FIXTURES, script), "rb").read() == open(os.path.join(REF_TESTS, script), "rb").read()
+
+
+@pytest.mark.parametrize("script", SCRIPTS)
 def test_reference_script_runs_unchanged_on_the_compat_package(script):
-    path = os.path.join(REF_TESTS, script)
+    path = os.path.join(FIXTURES, script)
     r = subprocess.run([sys.executable, os.path.basename(path)], cwd=os.path.dirname(path), env=env("reference"),
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-2000:]

@@ -210,3 +210,25 @@ def test_step_order_errors_have_the_reference_texts(pkg):
     p.step_sync(o, th, rv, rhod)
     with pytest.raises(RuntimeError, match="please call step_async\\(\\) before calling step_sync\\(\\) again"):
         p.step_sync(o, th, rv, rhod)
+
+
+# ---- the reference's own test scripts, unchanged, on the CUDA back-end ----------------------------------------------------------
+REF_SCRIPTS = ["unit/uniform_init.py", "unit/lgrngn_adve.py", "unit/terminal_velocities.py", "unit/multiple_kappas.py",
+               "unit/adve_scheme.py", "unit/lgrngn_subsidence.py", "physics/test_coal.py", "physics/lgrngn_cond.py", "physics/puddle.py"]
+
+
+@pytest.mark.parametrize("rng", ["mt19937", "philox"])
+@pytest.mark.parametrize("script", REF_SCRIPTS)
+def test_reference_script_runs_unchanged_on_the_cuda_backend(script, rng):
+    """tests/golden/ref_scripts/ holds verbatim copies of the reference's tests/python/{unit,physics} scripts; each runs in its own
+    interpreter against liblgrngn_b200.so, the serial / OpenMP back-ends they ask for redirected to CUDA (puddle.py asks for
+    multi_CUDA itself), under the replayed mt19937 stream and under the default in-kernel Philox stream"""
+    import subprocess
+    path = os.path.join(ROOT, "tests", "golden", "ref_scripts", script)
+    env = dict(os.environ)
+    env.pop("LIBCLOUDPHXX_COMPAT_LIBRARY", None)
+    env["PYTHONPATH"] = ROOT + os.pathsep + os.path.join(ROOT, "libcloudphxx_b200", "compat") + os.pathsep + env.get("PYTHONPATH", "")
+    env["LIBCLOUDPHXX_COMPAT_REDIRECT"] = "1"
+    env["LCX_RNG"] = rng
+    r = subprocess.run([sys.executable, os.path.basename(path)], cwd=os.path.dirname(path), env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-2500:]

@@ -30,7 +30,7 @@ def run(b200, staged, layout, monkeypatch, lazy="1", steps=6, **box):
         return out
     finally:
         E.set_cond_layout(0)
-        E.set_cond_staged(True)
+        E.set_cond_staged(False)
 
 
 def same(a, b):
@@ -59,6 +59,7 @@ def test_staged_kernel_is_the_one_that_runs(b200, monkeypatch):
     from libcloudphxx_b200 import distributed as D
     monkeypatch.setenv("LCX_LAZY_GATHER", "1")
     E.set_cond_layout(16)
+    E.set_cond_staged(True)
     try:
         oi, o, f = S.box_3d(b200, nx=4, ny=4, nz=6, sd_conc=24)
         p = b200.factory(L.backend_t.CUDA, oi)
@@ -73,3 +74,4 @@ def test_staged_kernel_is_the_one_that_runs(b200, monkeypatch):
         assert any("k_cond_staged" in k for k in rep), sorted(rep)
     finally:
         E.set_cond_layout(0)
+        E.set_cond_staged(False)

@@ -169,3 +169,55 @@ def test_multi_cuda_cfg5_shaped_conserves(b200, monkeypatch, slabs):
         assert s[0] + s[1] == s[2] + s[3] and s[1] > 0
     assert abs(total() - v0) <= 1e-10 * v0
     assert p.diag_puddle()["dry_volume"] > 0
+
+
+@pytest.mark.parametrize("slabs", [2, 3])
+def test_multi_cuda_pred_corr_matches_the_single_slab(b200, monkeypatch, slabs):
+    """predictor-corrector advection reads Courant numbers two columns beyond an SD's cell (adve.ipp:183-303): across a slab face
+    these must be the NEIGHBOUR's columns (particles_impl_xchng_courants.ipp:15-153 in the reference's MPI build; here every slab of
+    multi_CUDA maps its halo from the caller's global array).  Sheared, x-dependent Cx: the slabs together must reproduce the
+    single-device run - per-cell SD counts exactly, moments to rounding (positions are slab-local, so the last bit may differ)"""
+    if n_devices() < slabs:
+        monkeypatch.setenv("LCX_SLABS_ON_ONE_DEVICE", "1")
+    nx, ny, nz = 4 * slabs + 1, 3, 6
+
+    def run(backend):
+        oi, o, f = S.box_3d(b200, nx=nx, ny=ny, nz=nz, sd_conc=24, adve=L.as_t.pred_corr)
+        oi.dev_count = slabs if backend == L.backend_t.multi_CUDA else 0
+        oi.n_sd_max = int(oi.n_sd_max * 2)
+        xs = np.arange(nx + 1)[:, None, None]
+        zs = np.arange(nz)[None, None, :]
+        f["Cx"][:] = 0.55 + 0.35 * np.sin(2 * np.pi * xs / nx) + 0.05 * zs / nz          # sheared and varying along x
+        f["Cy"][:] = 0.1
+        o.cond = o.coal = o.sedi = 0
+        p = b200.factory(backend, oi)
+        p.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
+        out = []
+        for _ in range(6):
+            p.step_sync(o, f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"])
+            p.step_async(o)
+            out.append(per_cell(p, (nx, ny, nz)))
+        return out
+    one, many = run(L.backend_t.CUDA), run(L.backend_t.multi_CUDA)
+    for step, (a, b) in enumerate(zip(one, many)):
+        assert np.array_equal(a[0], b[0]), "SD counts per cell differ at step %d" % step
+        for x, y in zip(a[1:], b[1:]):
+            assert np.allclose(x, y, rtol=1e-12, atol=0), step
+    assert not np.array_equal(one[0][0], one[-1][0]), "nothing moved"
+
+
+def test_process_distributed_pred_corr_is_refused(b200):
+    """a rank-local Courant array cannot supply the neighbour's halo columns, and this back-end does not exchange them between
+    processes: construction must fail loudly instead of advecting with the rank's own far edge"""
+    from libcloudphxx_b200 import distributed as D
+    D.configure(b200, 0, 2, lft_x1=80.0, rgt_x0=0.0, n_x_tot=8)
+    oi, o, f = S.box_3d(b200, nx=4, ny=3, nz=4, sd_conc=8, adve=L.as_t.pred_corr)
+    with pytest.raises(RuntimeError, match="Courant"):
+        b200.factory(L.backend_t.CUDA, oi)
+    # the setting was consumed by the failed constructor: the next particle system is an ordinary single-device one
+    oi2, o2, f2 = S.box_3d(b200, nx=4, ny=3, nz=4, sd_conc=8)
+    p = b200.factory(L.backend_t.CUDA, oi2)
+    p.init(f2["th"], f2["rv"], f2["rhod"], None, f2["Cx"], f2["Cy"], f2["Cz"])
+    p.step_sync(o2, f2["th"], f2["rv"], f2["rhod"], f2["Cx"], f2["Cy"], f2["Cz"])
+    p.step_async(o2)
+    assert p.get_n().size > 0
