@@ -333,7 +333,7 @@ def run_b200(args):
     ny, nz = args.ny, args.nz
     # weak scaling: args.nx columns per GPU; strong scaling: args.nx columns in total, split like distmem_opts.hpp:10-18
     if args.scaling == "strong":
-        share = int(args.nx / n_slabs + .5)
+        share = args.nx // n_slabs             # int / int in the reference: the .5 never rounds up
         nx_of = lambda r: share if r < n_slabs - 1 else args.nx - r * share
     else:
         nx_of = lambda r: args.nx

@@ -122,6 +122,10 @@ int  lcx_cells_get(lcx_engine *e, int field, void *dst, int64_t count);         
 /* host memory may be pageable or pinned - pinned memory (lcx_host_alloc or the caller's own) moves at full PCIe rate      */
 int  lcx_cells_set_part(lcx_engine *e, int field, int64_t offset, const void *src, int64_t count);
 int  lcx_cells_get_part(lcx_engine *e, int field, int64_t offset, void *dst, int64_t count);
+/* Both take HOST or DEVICE memory on the caller's side (unified addressing tells them apart): a host model whose Eulerian   */
+/* fields already live on the GPU passes device pointers through arrinfo_t and no PCIe traffic happens.                       */
+int  lcx_pointer_on_device(const void *p, int *on_device);      /* 1: device (or managed) memory, 0: host memory           */
+int  lcx_copy_to_host(void *dst_host, const void *src_any, size_t bytes);   /* blocking; used by init() for device-resident fields */
 int  lcx_host_alloc(size_t bytes, void **out);                  /* page-locked staging memory for the host layer          */
 int  lcx_host_free(void *p);
 int  lcx_set_vt0_table(lcx_engine *e, const void *table, int n);            /* init_vterm.ipp:36-59          */

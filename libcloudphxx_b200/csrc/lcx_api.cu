@@ -316,7 +316,7 @@ int lcx_cells_set_part(lcx_engine *e, int field, int64_t offset, const void *src
       }
       e->upload_batch_open = true;
     }
-    LCX_CUDA(cudaMemcpyAsync(static_cast<lcx::real_t *>(f.p) + offset, src, size_t(count) * sizeof(lcx::real_t), cudaMemcpyHostToDevice, e->copy_stream));
+    LCX_CUDA(cudaMemcpyAsync(static_cast<lcx::real_t *>(f.p) + offset, src, size_t(count) * sizeof(lcx::real_t), cudaMemcpyDefault, e->copy_stream));
     if (courant) { LCX_CUDA(cudaEventRecord(e->courant_ready, e->copy_stream)); e->courant_pending = true; }
     else         { LCX_CUDA(cudaEventRecord(e->scalars_ready, e->copy_stream)); e->scalars_pending = true; }
   });
@@ -328,9 +328,24 @@ int lcx_cells_get_part(lcx_engine *e, int field, int64_t offset, void *dst, int6
     use_device(e, true, 3u);
     const field_ref f = field_of(e, field);
     if (offset < 0 || count < 0 || size_t(offset + count) > f.n) throw lcx::error("lcx_cells_get_part: range outside field " + std::to_string(field));
-    LCX_CUDA(cudaMemcpyAsync(dst, static_cast<const lcx::real_t *>(f.p) + offset, size_t(count) * sizeof(lcx::real_t), cudaMemcpyDeviceToHost, e->stream));
+    LCX_CUDA(cudaMemcpyAsync(dst, static_cast<const lcx::real_t *>(f.p) + offset, size_t(count) * sizeof(lcx::real_t), cudaMemcpyDefault, e->stream));
   });
 }
+
+int lcx_pointer_on_device(const void *p, int *on_device)
+{
+  *on_device = 0;
+  return guarded([&] {
+    if (!p) return;
+    cudaPointerAttributes at;
+    const cudaError_t st = cudaPointerGetAttributes(&at, p);
+    if (st != cudaSuccess) { cudaGetLastError(); return; }      // plain pageable host memory on older drivers
+    *on_device = (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) ? 1 : 0;
+  });
+}
+
+int lcx_copy_to_host(void *dst_host, const void *src_any, size_t bytes)
+{ return guarded([&] { if (bytes) LCX_CUDA(cudaMemcpy(dst_host, src_any, bytes, cudaMemcpyDefault)); }); }
 
 int lcx_host_alloc(size_t bytes, void **out)
 {

@@ -23,8 +23,9 @@ namespace lcx
     constexpr int TPB = 256;
     constexpr int CELL_LANES = 16;           // lanes that share one cell in k_coal_small (two cells per warp)
     constexpr int GROUPS = TPB / CELL_LANES;
-    constexpr unsigned SMALL_MAX = 256;      // largest cell population handled by k_coal_small
-    constexpr int KAPPA_ITER_MAX = 1024;     // collisions of one pair up to which kappa is mixed event by event like the reference
+    constexpr unsigned SMALL_MAX = 256;      // largest cell population handled by k_coal_small in its usual configuration
+    constexpr unsigned MEDIUM_MAX = 1024;    // ... and in the big-shared-memory configuration (rain piling up in a few cells)
+    constexpr int KAPPA_ITER_MAX = 64;       // collisions of one pair up to which kappa is mixed event by event like the reference
 
     // ---- Philox4x32-10 (Salmon, Moraes, Dror & Shaw, SC'11) --------------------------------------------
     struct philox_key { uint32_t k0, k1; };
@@ -178,11 +179,19 @@ namespace lcx
 #ifndef LCX_COAL_MINB
 #define LCX_COAL_MINB 4      // 64 registers, 4 CTAs per SM: measured best of {1,3,4,5}
 #endif
-    __global__ void __launch_bounds__(TPB, LCX_COAL_MINB) k_coal_small(idx_t n_cell, const uint32_t *__restrict__ off, const idx_t *__restrict__ sid,
+    // CAP = largest cell population: 256 (static shared memory, 4 CTAs per SM: the usual case) or MEDIUM_MAX (dynamic shared
+    // memory, 2 CTAs per SM) for grids where sedimenting drops pile up in a few cells - far cheaper than the global-sort path
+    template <int CAP>
+    __global__ void __launch_bounds__(TPB, CAP == int(SMALL_MAX) ? LCX_COAL_MINB : 2) k_coal_small(idx_t n_cell, const uint32_t *__restrict__ off, const idx_t *__restrict__ sid,
                                                        rng_src rng, coal_ctx cx)
     {
-      __shared__ __align__(16) uint32_t skey[GROUPS][SMALL_MAX + KEY_PAD];
-      __shared__ unsigned short sperm[GROUPS][SMALL_MAX];
+      extern __shared__ __align__(16) unsigned char coal_dyn_smem[];
+      __shared__ __align__(16) uint32_t skey_static[CAP == int(SMALL_MAX) ? GROUPS : 1][CAP == int(SMALL_MAX) ? CAP + KEY_PAD : 1];
+      __shared__ unsigned short sperm_static[CAP == int(SMALL_MAX) ? GROUPS : 1][CAP == int(SMALL_MAX) ? CAP : 1];
+      uint32_t (*skey)[CAP + KEY_PAD] = CAP == int(SMALL_MAX) ? reinterpret_cast<uint32_t (*)[CAP + KEY_PAD]>(&skey_static[0][0])
+                                                               : reinterpret_cast<uint32_t (*)[CAP + KEY_PAD]>(coal_dyn_smem);
+      unsigned short (*sperm)[CAP] = CAP == int(SMALL_MAX) ? reinterpret_cast<unsigned short (*)[CAP]>(&sperm_static[0][0])
+                                                            : reinterpret_cast<unsigned short (*)[CAP]>(coal_dyn_smem + sizeof(uint32_t) * GROUPS * (CAP + KEY_PAD));
       const int grp = threadIdx.x / CELL_LANES, l = threadIdx.x % CELL_LANES;
       const idx_t c = blockIdx.x * GROUPS + grp;
       uint32_t b = 0, m = 0;
@@ -337,7 +346,14 @@ namespace lcx
 
     if (e->max_count <= SMALL_MAX)
     {
-      LCX_LAUNCH(e, k_coal_small, div_up(g.n_cell, GROUPS), TPB, 0, g.n_cell, e->cell_off.p, s.sid.p, rng, cx);
+      LCX_LAUNCH(e, k_coal_small<int(SMALL_MAX)>, div_up(g.n_cell, GROUPS), TPB, 0, g.n_cell, e->cell_off.p, s.sid.p, rng, cx);
+      return;
+    }
+    if (e->max_count <= MEDIUM_MAX && g.n_cell > 1)
+    {
+      constexpr size_t smem = sizeof(uint32_t) * GROUPS * (MEDIUM_MAX + KEY_PAD) + sizeof(unsigned short) * GROUPS * MEDIUM_MAX;
+      LCX_CUDA(cudaFuncSetAttribute(k_coal_small<int(MEDIUM_MAX)>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));      // per device; a cheap host call
+      LCX_LAUNCH(e, k_coal_small<int(MEDIUM_MAX)>, div_up(g.n_cell, GROUPS), TPB, smem, g.n_cell, e->cell_off.p, s.sid.p, rng, cx);
       return;
     }
 

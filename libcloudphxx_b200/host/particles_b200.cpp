@@ -412,11 +412,32 @@ namespace libcloudphxx
           }
         }
 
+        // device-pointer fast path of arrinfo_t: a model that keeps its fields on the GPU hands device pointers; copies then stay on the device
+        static bool on_device(const void *p) { int d = 0; chk(lcx_pointer_on_device(p, &d)); return d != 0; }
+
+        // host copy of a caller's array that may live in device memory (initialisation and the Courant-range check read fields on the host)
+        struct host_view
+        {
+          std::vector<real_t> buf;
+          const real_t *data;
+          host_view(const arrinfo_t<real_t> &a, const map_t &m) : data(a.data)
+          {
+            if (a.is_null() || !on_device(a.data)) return;
+            long hi = 0;
+            for (const run_t &r : m.runs) hi = std::max(hi, r.src + r.len);
+            buf.resize(size_t(hi));
+            chk(lcx_copy_to_host(buf.data(), a.data, buf.size() * sizeof(real_t)));
+            data = buf.data();
+          }
+        };
+
         // both directions only queue the copies; the caller ends the batch with finish_transfers()
         void sync_in_field(const arrinfo_t<real_t> &from, const map_t &m, int field)   // impl_sync.ipp:15-40
         {
           if (from.is_null()) return;
           const real_t *src = from.data;
+          if (!m.direct() && on_device(src))
+            throw std::runtime_error("libcloudph++ (B200 engine): Eulerian arrays in device memory must be (nearly) contiguous: z fastest, no padding between rows");
           if (m.direct())
           {
             for (const run_t &r : m.runs) chk(lcx_cells_set_part(e, field, r.dst, src + r.src, r.len));
@@ -430,6 +451,8 @@ namespace libcloudphxx
         void sync_out_field(int field, const map_t &m, arrinfo_t<real_t> &to)           // impl_sync.ipp:42-68
         {
           if (to.is_null()) return;
+          if (!m.direct() && on_device(to.data))
+            throw std::runtime_error("libcloudph++ (B200 engine): Eulerian arrays in device memory must be (nearly) contiguous: z fastest, no padding between rows");
           if (m.direct())
           {
             for (const run_t &r : m.runs) chk(lcx_cells_get_part(e, field, r.dst, to.data + r.src, r.len));
@@ -585,13 +608,14 @@ namespace libcloudphxx
         {
           cell_state cs;
           cs.rhod.resize(n_cell); cs.T.resize(n_cell); cs.RH.resize(n_cell); cs.dv.resize(n_cell);
+          const host_view h_th(th, m_th), h_rv(rv, m_rv), h_rhod(rhod, m_rhod), h_p(p, m_p);
           for (size_t c = 0; c < n_cell; ++c)
           {
-            const real_t th_c = th.data[m_th.l2e[c]], rv_c = rv.data[m_rv.l2e[c]], rhod_c = rhod.data[m_rhod.l2e[c]];
+            const real_t th_c = h_th.data[m_th.l2e[c]], rv_c = h_rv.data[m_rv.l2e[c]], rhod_c = h_rhod.data[m_rhod.l2e[c]];
             real_t T_c, p_c;
             if (oi.th_dry) T_c = lcx::T_of_th_dry(th_c, rhod_c);
-            else           T_c = th_c * lcx::exner(p.data[m_p.l2e[c]]);
-            p_c = oi.const_p ? p.data[m_p.l2e[c]] : lcx::p_of_rhod_rv_T(rhod_c, rv_c, T_c);
+            else           T_c = th_c * lcx::exner(h_p.data[m_p.l2e[c]]);
+            p_c = oi.const_p ? h_p.data[m_p.l2e[c]] : lcx::p_of_rhod_rv_T(rhod_c, rv_c, T_c);
             cs.rhod[c] = rhod_c; cs.T[c] = T_c;
             cs.RH[c] = lcx::RH_of(int(oi.RH_formula), p_c, rv_c, T_c);
             if (n_dims == 0) cs.dv[c] = real_t(1) / rhod_c;
@@ -932,7 +956,8 @@ namespace libcloudphxx
           if (oi.adve_scheme == as_t::pred_corr && !cx.is_null())
           {
             real_t cmin = std::numeric_limits<real_t>::max(), cmax = -cmin;
-            for (const long l : m_cx.l2e) { cmin = std::min(cmin, cx.data[l]); cmax = std::max(cmax, cx.data[l]); }
+            const host_view h_cx(cx, m_cx);
+            for (const long l : m_cx.l2e) { cmin = std::min(cmin, h_cx.data[l]); cmax = std::max(cmax, h_cx.data[l]); }
             if (!(cmin >= real_t(-2.)) || !(cmax <= real_t(2.))) adve_scheme = as_t::euler;
           }
           should_now_run_cond = true;

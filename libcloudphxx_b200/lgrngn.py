@@ -237,6 +237,22 @@ def _arr(a):
     """numpy array (float64, any strides that are multiples of 8 B) -> lgc_arr; None -> NULL"""
     if a is None:
         return None
+    cai = getattr(a, "__cuda_array_interface__", None)
+    if cai is not None and not isinstance(a, np.ndarray):
+        # device-resident field (e.g. a torch CUDA tensor): the raw device pointer goes through arrinfo_t, copies stay on the GPU
+        assert cai["typestr"] in ("<f8", "=f8", "|f8"), "Eulerian fields must be float64"
+        c = _Arr()
+        c.data = C.cast(C.c_void_p(int(cai["data"][0])), C.POINTER(C.c_double))
+        shape = tuple(cai["shape"])
+        if cai.get("strides"):
+            st = [s // 8 for s in cai["strides"]]
+        else:
+            st = [int(np.prod(shape[i + 1:], dtype=np.int64)) for i in range(len(shape))]
+        while len(st) < 3:
+            st.append(1)
+        for i in range(3):
+            c.strides[i] = st[i]
+        return C.byref(c)
     assert a.dtype == np.float64, "Eulerian fields must be float64"
     c = _Arr()
     c.data = a.ctypes.data_as(C.POINTER(C.c_double))

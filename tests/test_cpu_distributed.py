@@ -48,11 +48,13 @@ def test_inbox_handles_reach_the_ring_neighbours_gloo(size):
 
 
 def test_slab_split_matches_reference_rule():
-    """x-columns per device: int(nx/G + .5) for all but the last, remainder to the last (src/detail/distmem_opts.hpp:10-18)"""
+    """x-columns per device: int(nx / G + .5) for all but the last, remainder to the last (src/detail/distmem_opts.hpp:10-18);
+    nx and G are ints there, so nx / G is an INTEGER division and the .5 never rounds up"""
     def dev_nx(nx, rank, size):
-        return int(nx / size + .5) if rank < size - 1 else nx - rank * int(nx / size + .5)
+        return int(nx // size + .5) if rank < size - 1 else nx - rank * int(nx // size + .5)
     for nx, size in ((512, 8), (5, 2), (7, 3), (10, 4)):
         parts = [dev_nx(nx, r, size) for r in range(size)]
         assert sum(parts) == nx and all(p > 0 for p in parts), (nx, size, parts)
-    assert [dev_nx(5, r, 2) for r in range(2)] == [3, 2]
+    assert [dev_nx(5, r, 2) for r in range(2)] == [2, 3]
     assert [dev_nx(7, r, 3) for r in range(3)] == [2, 2, 3]
+    assert [dev_nx(9, r, 2) for r in range(2)] == [4, 5]

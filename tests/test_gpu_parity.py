@@ -496,3 +496,24 @@ def test_float_api_is_served_by_the_double_engine(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
     print(r.stdout)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_coalescence_with_populous_cells_exact(ref, b200):
+    """cells holding 256 < n <= 1024 super-droplets take the per-cell kernel in its big-shared-memory configuration
+    (k_coal_small<1024>) instead of the global sort: collision outcomes still exact under the replayed stream"""
+    seen = {}
+
+    def setup(lib):
+        oi, o, f = S.box_3d(lib, nx=2, ny=2, nz=3, sd_conc=600, rain_mode=True, dt=2.0, sstp_coal=2)
+        o.cond = 0
+        return oi, o, f
+
+    def check(step, p_r, p_n, f_r, f_n):
+        n_r, n_n = p_r.get_n(), p_n.get_n()
+        assert n_r.size == n_n.size and np.array_equal(n_r, n_n), step
+        assert np.array_equal(p_r.get_attr("rd3"), p_n.get_attr("rd3")), step
+        assert S.rel_err(p_r.get_attr("rw2"), p_n.get_attr("rw2")) < 1e-14, step
+        seen.setdefault("n0", int(n_r.sum()))
+        seen["n1"] = int(n_r.sum())
+    S.run_pair(ref, b200, setup, 4, on_step=check)
+    assert seen["n1"] < seen["n0"]
