@@ -105,7 +105,7 @@ lcx_engine::~lcx_engine()
     inbox[s].release();
   }
   if (ev_put) cudaEventDestroy(ev_put);
-  scalars.release(); red_partial.release(); cell_tmp4.release();
+  scalars.release(); red_partial.release(); cell_tmp4.release(); big_cells.release();
   for (auto &r : prof) { cudaEventDestroy(r.t0); cudaEventDestroy(r.t1); }
   if (timer0) { cudaEventDestroy(timer0); cudaEventDestroy(timer1); }
   if (h_scalars) cudaFreeHost(h_scalars);
@@ -204,6 +204,7 @@ int lcx_create(const lcx_config *cfg, lcx_engine **out)
     e->drw_mom3.alloc(n_cell); e->rw_mom3.alloc(n_cell); e->count_mom.alloc(n_cell);
     if (cfg->terminal_velocity == lcx::VT_BEARD77 || cfg->terminal_velocity == lcx::VT_BEARD77FAST) e->cell_tmp4.alloc(size_t(n_cell) * 4);
     if (cfg->allow_sstp_cond) { e->sstp_tmp_rv.alloc(n_cell); e->sstp_tmp_th.alloc(n_cell); e->sstp_tmp_rh.alloc(n_cell); }
+    e->big_cells.alloc(n_cell);
     e->cell_off.alloc(n_cell + 2); e->cell_off_new.alloc(n_cell + 2); e->arr_off.alloc(n_cell + 2); e->mv_scan.alloc(n_cell + 2);
     const size_t h = size_t(g.halo_size);
     switch (g.n_dims)   // staggered Courant fields with x-halo: init_sync.ipp:29-44

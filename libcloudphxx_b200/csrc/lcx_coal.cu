@@ -23,7 +23,7 @@ namespace lcx
     constexpr int TPB = 256;
     constexpr int CELL_LANES = 16;           // lanes that share one cell in k_coal_small (two cells per warp)
     constexpr int GROUPS = TPB / CELL_LANES;
-    constexpr unsigned SMALL_MAX = 256;      // largest cell population handled by k_coal_small in its usual configuration
+    constexpr unsigned SMALL_MAX = BIG_CELL; // largest cell population handled by k_coal_small in its usual configuration
     constexpr unsigned MEDIUM_MAX = 1024;    // ... and in the big-shared-memory configuration (rain piling up in a few cells)
     constexpr int KAPPA_ITER_MAX = 64;       // collisions of one pair up to which kappa is mixed event by event like the reference
 
@@ -183,7 +183,7 @@ namespace lcx
     // memory, 2 CTAs per SM) for grids where sedimenting drops pile up in a few cells - far cheaper than the global-sort path
     template <int CAP>
     __global__ void __launch_bounds__(TPB, CAP == int(SMALL_MAX) ? LCX_COAL_MINB : 2) k_coal_small(idx_t n_cell, const uint32_t *__restrict__ off, const idx_t *__restrict__ sid,
-                                                       rng_src rng, coal_ctx cx)
+                                                       rng_src rng, coal_ctx cx, const uint32_t *__restrict__ cell_list, uint32_t n_list)
     {
       extern __shared__ __align__(16) unsigned char coal_dyn_smem[];
       __shared__ __align__(16) uint32_t skey_static[CAP == int(SMALL_MAX) ? GROUPS : 1][CAP == int(SMALL_MAX) ? CAP + KEY_PAD : 1];
@@ -193,10 +193,12 @@ namespace lcx
       unsigned short (*sperm)[CAP] = CAP == int(SMALL_MAX) ? reinterpret_cast<unsigned short (*)[CAP]>(&sperm_static[0][0])
                                                             : reinterpret_cast<unsigned short (*)[CAP]>(coal_dyn_smem + sizeof(uint32_t) * GROUPS * (CAP + KEY_PAD));
       const int grp = threadIdx.x / CELL_LANES, l = threadIdx.x % CELL_LANES;
-      const idx_t c = blockIdx.x * GROUPS + grp;
+      // all cells of the grid, or (cell_list) only the listed ones - the populous cells the usual configuration leaves out
+      const uint32_t slot = blockIdx.x * GROUPS + grp;
+      const idx_t c = cell_list ? (slot < n_list ? cell_list[slot] : n_cell) : slot;
       uint32_t b = 0, m = 0;
       if (c < n_cell) { b = off[c]; m = off[c + 1] - b; }
-      if (m < 2) m = 0;                                    // nothing to pair; keep the lanes for the warp-wide syncs
+      if (m < 2 || m > uint32_t(CAP)) m = 0;               // nothing to pair (or not this launch's cell); keep the lanes for the warp-wide syncs
       const uint32_t m4 = (m + 3u) & ~3u;
       uint32_t *const key = skey[grp];
       unsigned short *const perm = sperm[grp];
@@ -346,14 +348,18 @@ namespace lcx
 
     if (e->max_count <= SMALL_MAX)
     {
-      LCX_LAUNCH(e, k_coal_small<int(SMALL_MAX)>, div_up(g.n_cell, GROUPS), TPB, 0, g.n_cell, e->cell_off.p, s.sid.p, rng, cx);
+      LCX_LAUNCH(e, k_coal_small<int(SMALL_MAX)>, div_up(g.n_cell, GROUPS), TPB, 0, g.n_cell, e->cell_off.p, s.sid.p, rng, cx, (const uint32_t *)nullptr, 0u);
       return;
     }
     if (e->max_count <= MEDIUM_MAX && g.n_cell > 1)
     {
       constexpr size_t smem = sizeof(uint32_t) * GROUPS * (MEDIUM_MAX + KEY_PAD) + sizeof(unsigned short) * GROUPS * MEDIUM_MAX;
       LCX_CUDA(cudaFuncSetAttribute(k_coal_small<int(MEDIUM_MAX)>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));      // per device; a cheap host call
-      LCX_LAUNCH(e, k_coal_small<int(MEDIUM_MAX)>, div_up(g.n_cell, GROUPS), TPB, smem, g.n_cell, e->cell_off.p, s.sid.p, rng, cx);
+      // the grid as usual (cells above SMALL_MAX skip themselves), then the few populous cells from the list post_copy made
+      LCX_LAUNCH(e, k_coal_small<int(SMALL_MAX)>, div_up(g.n_cell, GROUPS), TPB, 0, g.n_cell, e->cell_off.p, s.sid.p, rng, cx, (const uint32_t *)nullptr, 0u);
+      if (e->n_big)
+        LCX_LAUNCH(e, k_coal_small<int(MEDIUM_MAX)>, div_up(e->n_big, GROUPS), TPB, smem, g.n_cell, e->cell_off.p, s.sid.p, rng, cx,
+                   (const uint32_t *)e->big_cells.p, uint32_t(e->n_big));
       return;
     }
 

@@ -108,7 +108,9 @@ namespace lcx
     unsigned long long n_collisions, n_pairs_collided;
     double puddle[8];               // liq_vol, dry_vol, liq_num, prtcl_num, accumulated; [4], [5]: dry volume / SDs lost through the lid
     unsigned long long rcyc_zero, rcyc_one, rcyc_max;   // SDs with n == 0, with n == 1, largest n (recycling)
+    unsigned int n_big, pad2;       // cells holding more than BIG_CELL super-droplets (listed in lcx_engine::big_cells)
   };
+  constexpr unsigned BIG_CELL = 256;  // largest cell population the per-cell coalescence kernel takes in its usual configuration
 }
 
 struct lcx_engine
@@ -133,6 +135,8 @@ struct lcx_engine
   size_t n_part = 0;             // live SDs (host copy)
   size_t n_tail = 0;             // SDs appended (migration) since the last post_copy, already counted in n_part
   unsigned max_count = 0;        // host copy of the largest cell population
+  unsigned n_big = 0;            // host copy: number of cells with more than BIG_CELL super-droplets
+  lcx::dbuf<uint32_t> big_cells; // their indices (any order)
   bool grouped = false;          // SD arrays physically grouped by cell, cell_off valid
   // storage indices: every sid is < sid_hi; dense means {sid} = [0, n_part).  With injected random streams (and for
   // get_attr) they must be dense, so removals are followed by a re-numbering; with Philox any unique, order-preserving

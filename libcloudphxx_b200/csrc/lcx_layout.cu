@@ -63,10 +63,11 @@ namespace lcx
       if (t == n) off[n_cell + 1] = uint32_t(n);
     }
 
-    __global__ void __launch_bounds__(TPB) k_max_count(uint32_t n_cell, const uint32_t *__restrict__ off, dev_scalars *sc)
+    __global__ void __launch_bounds__(TPB) k_max_count(uint32_t n_cell, const uint32_t *__restrict__ off, dev_scalars *sc, uint32_t *__restrict__ big_cells)
     {
       const uint32_t c = blockIdx.x * TPB + threadIdx.x;
       uint32_t m = (c < n_cell) ? off[c + 1] - off[c] : 0u;
+      if (m > BIG_CELL) big_cells[atomicAdd(&sc->n_big, 1u)] = c;      // rare: sedimenting drops piling up; coalescence treats these cells apart
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
       if ((threadIdx.x & 31) == 0 && m) atomicMax(&sc->max_count, m);
@@ -298,8 +299,9 @@ namespace lcx
   {
     const grid_t &g = e->grid;
     LCX_CUDA(cudaMemsetAsync(&e->scalars.p->max_count, 0, sizeof(unsigned int), e->stream));
+    LCX_CUDA(cudaMemsetAsync(&e->scalars.p->n_big, 0, sizeof(unsigned int), e->stream));
     LCX_LAUNCH(e, k_cell_offsets, div_up(n_total + 1, TPB), TPB, 0, n_total, g.n_cell, g.class_bits, sorted_keys, e->cell_off.p);
-    LCX_LAUNCH(e, k_max_count, div_up(g.n_cell, TPB), TPB, 0, g.n_cell, e->cell_off.p, e->scalars.p);
+    LCX_LAUNCH(e, k_max_count, div_up(g.n_cell, TPB), TPB, 0, g.n_cell, e->cell_off.p, e->scalars.p, e->big_cells.p);
   }
 
   // rcyc.ipp:44-139.  The reference sorts (stably) the whole storage by multiplicity; ties therefore resolve by storage
@@ -383,7 +385,8 @@ namespace lcx
                  perm_out, e->A().ijk.p, sid_old, sid_new);
     LCX_CUDA(cudaMemcpyAsync(e->cell_off.p, e->cell_off_new.p, (size_t(g.n_cell) + 2) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, e->stream));
     LCX_CUDA(cudaMemsetAsync(&e->scalars.p->max_count, 0, sizeof(unsigned int), e->stream));
-    LCX_LAUNCH(e, k_max_count, div_up(g.n_cell, TPB), TPB, 0, g.n_cell, e->cell_off.p, e->scalars.p);
+    LCX_CUDA(cudaMemsetAsync(&e->scalars.p->n_big, 0, sizeof(unsigned int), e->stream));
+    LCX_LAUNCH(e, k_max_count, div_up(g.n_cell, TPB), TPB, 0, g.n_cell, e->cell_off.p, e->scalars.p, e->big_cells.p);
     return true;
   }
 
@@ -401,7 +404,7 @@ namespace lcx
     if (n_old == 0)
     {
       LCX_CUDA(cudaMemsetAsync(e->cell_off.p, 0, e->cell_off.bytes(), e->stream));
-      e->max_count = 0; e->grouped = true; e->n_grouped = 0;
+      e->max_count = 0; e->n_big = 0; e->grouped = true; e->n_grouped = 0;
       return;
     }
 
@@ -440,6 +443,7 @@ namespace lcx
     LCX_CUDA(cudaStreamSynchronize(e->stream));
     const size_t n_new = e->h_scalars->n_part;
     e->max_count = e->h_scalars->max_count;
+    e->n_big = e->h_scalars->n_big;
 
     const bool lazy = e->lazy_gather && !keep_all && n_new > 0;
     if (n_new)

@@ -8,6 +8,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# verbatim copies of the reference's own test scripts live under tests/golden/ref_scripts (one is called test_coal.py): they are run
+# as subprocesses by tests/test_*_compat.py, never collected as test modules of this suite
+collect_ignore_glob = ["golden/*"]
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `pytest -m gpu`)")
 

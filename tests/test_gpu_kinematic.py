@@ -25,7 +25,7 @@ def run(b200, steps=120, **kw):
 
 def test_eddy_forms_a_cloud_and_closes_the_water_budget(b200):
     m, d0, d1 = run(b200)
-    assert d0["cloudy_cells"] == 0 and d0["RH_max"] < 1.0
+    assert d0["cloudy_cells"] == 0 and d0["RH_max"] > 1.05       # icicle's profile starts supersaturated aloft (kin_cloud_2d_lgrngn.hpp:127: "deals with initial supersaturation")
     assert d1["cloudy_cells"] > 30 and d1["rc_max"] > 1e-4, d1            # the updraft branch condenses > 0.1 g/kg
     assert d1["RH_max"] < 1.03, d1                                          # supersaturation stays bounded: condensation keeps up
     assert d1["sd_min"] > 0 and abs(d1["sd_mean"] - d0["sd_mean"]) < 0.05 * d0["sd_mean"], d1     # the non-divergent flow keeps cells populated
