@@ -22,6 +22,12 @@
 #include <stddef.h>
 #include <stdint.h>
 
+/* The single-precision engine is the same source compiled with LCX_F32: real = float, every symbol below carries the suffix  */
+/* _f32 (lcx_create_f32, ...), `void *` array arguments then point to floats; scalars stay double in the signatures.           */
+#ifdef LCX_F32
+#include "lcx_b200_f32_names.h"
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif

@@ -18,7 +18,11 @@
 
 namespace lcx
 {
-  typedef double real_t;          // v1 instantiates the double-precision engine only
+#ifdef LCX_F32
+  typedef float real_t;           // the single-precision engine: same sources, liblcx_b200_f32.so (build.py)
+#else
+  typedef double real_t;
+#endif
   typedef uint32_t idx_t;         // SD indices / cell indices / storage indices (n_sd_max < 2^32 per slab)
 
   struct error : std::runtime_error { explicit error(const std::string &s) : std::runtime_error(s) {} };

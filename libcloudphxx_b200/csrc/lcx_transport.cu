@@ -55,9 +55,10 @@ namespace lcx
     __device__ __forceinline__ real_t step_expl(real_t x, idx_t i, real_t C_l, real_t C_r, real_t dx, bool apply)   // adve.ipp:62-93
     { return apply * x + (C_r - C_l) * (x - dx * i) + dx * C_l; }
 
-    // staggered-field indices of the two faces of (halo-extended) cell cp in each direction: init_grid.ipp:93-155
+    // staggered-field indices of the two faces of (halo-extended) cell cp = (i * ny + j) * nz + k in each direction:
+    // init_grid.ipp:93-155.  i and j come from the caller (it has them anyway): no integer division here.
     struct faces { idx_t xl, xr, yl, yr, zl, zr; };
-    __device__ __forceinline__ faces faces_of(const grid_t &g, idx_t cp)
+    __device__ __forceinline__ faces faces_of(const grid_t &g, idx_t cp, idx_t i, idx_t j)
     {
       faces f;
       f.xl = cp;
@@ -65,15 +66,14 @@ namespace lcx
       f.yl = f.yr = f.zl = f.zr = 0;
       if (g.n_dims == 3)
       {
-        const idx_t col = idx_t(g.nz) * g.ny;
-        f.yl = cp + (cp / col) * g.nz;
+        f.yl = cp + i * g.nz;                  // cp / (ny nz) = i
         f.yr = f.yl + g.nz;
-        f.zl = cp + g.ny * (cp / col) + (cp - (cp / col) * col) / g.nz;
+        f.zl = cp + g.ny * i + j;              // (cp - i ny nz) / nz = j
         f.zr = f.zl + 1;
       }
       else if (g.n_dims == 2)
       {
-        f.zl = cp + cp / g.nz;
+        f.zl = cp + i;                         // cp / nz = i
         f.zr = f.zl + 1;
       }
       return f;
@@ -132,11 +132,11 @@ namespace lcx
       {
         const idx_t c = ijk[t];
         idx_t i = 0, j = 0, k = 0;
-        switch (g.n_dims)
+        switch (g.n_dims)      // two integer divisions at most: q = c / nz, then i = q / ny
         {
           case 1: i = c; break;
-          case 2: i = c / g.nz; k = c % g.nz; break;
-          case 3: i = c / (idx_t(g.nz) * g.ny); j = (c / g.nz) % g.ny; k = c % g.nz; break;
+          case 2: i = c / g.nz; k = c - i * g.nz; break;
+          case 3: { const idx_t q = c / g.nz; k = c - q * g.nz; i = q / g.ny; j = q - i * g.ny; } break;
         }
         real_t x, y, z;
         if (LAZY) { const uint32_t src = perm[t]; x = g.nx ? xi[src] : 0; y = g.ny ? yi[src] : 0; z = g.nz ? zi[src] : 0; }
@@ -148,7 +148,7 @@ namespace lcx
         {
           if (P.scheme == AS_IMPLICIT || P.scheme == AS_EULER)
           {
-            const faces f = faces_of(g, c + g.halo_x);
+            const faces f = faces_of(g, c + g.halo_x, i + idx_t(g.halo_size), j);
             if (P.scheme == AS_IMPLICIT)
             {
               x = step_impl(x, i, Cx[f.xl], Cx[f.xr], g.dx);
@@ -168,7 +168,7 @@ namespace lcx
             idx_t ih, jh, kh;
             idx_t ch = cell_of(g, x, y, z, ih, jh, kh);
             real_t x_old = x, y_old = y, z_old = z;
-            faces f = faces_of(g, ch);
+            faces f = faces_of(g, ch, ih, jh);
             x = step_expl(x, ih, Cx[f.xl], Cx[f.xr], g.dx, true);
             if (g.n_dims > 2) y = step_expl(y, jh, Cy[f.yl], Cy[f.yr], g.dy, true);
             if (g.n_dims > 1) z = step_expl(z, kh, Cz[f.zl], Cz[f.zr], g.dz, true);
@@ -187,7 +187,7 @@ namespace lcx
             x_old = x + x_old;
             if (g.n_dims > 2) y_old = y + y_old;
             if (g.n_dims > 1) z_old = z + z_old;
-            f = faces_of(g, ch);
+            f = faces_of(g, ch, ih, jh);
             x = step_expl(x, ih, Cx[f.xl], Cx[f.xr], g.dx, false);
             if (g.n_dims > 2) y = step_expl(y, jh, Cy[f.yl], Cy[f.yr], g.dy, false);
             if (g.n_dims > 1) z = step_expl(z, kh, Cz[f.zl], Cz[f.zr], g.dz, false);
