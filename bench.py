@@ -48,6 +48,13 @@ KERNEL_BYTES_EXACT = {        # gather-on-read variants (the default): the re-la
     "k_cond_staged<true>": 88.0, "k_cond_staged<false>": 52.0,      # the phase-grouped form of the range kernel: same traffic
 }
 LAZY = os.environ.get("LCX_LAZY_GATHER", "1") != "0"
+# --real f32 (the single-precision engine, a SECOND mode - never the headline): the same tables with 4-byte reals.
+# (fixed bytes, number of real words) per SD of the kernels that dominate; the multiplicity stays 8 bytes, indices and keys 4
+REAL_BYTES = 8
+A_FULL_BYTES_F32 = 136.0      # 36 read + 36 write state (n 8 + 7 x 4), 52 sort, 12 random inputs
+KERNEL_WORDS = {"(k_cond_range<M, true>)": (24, 8), "k_cond_range": (20, 4), "k_cond_cells": (16, 4), "k_cond": (20, 4),
+                "k_transport<true>": (20, 7), "k_transport": (16, 7), "k_coal_small": (12, 8), "k_coal_big": (12, 8),
+                "k_vterm": (0, 3), "k_mv_count": (4, 0), "k_mv_list": (4, 0), "k_mv_place_stayers": (12, 0)}
 
 
 def base_name(name):
@@ -56,6 +63,10 @@ def base_name(name):
 
 
 def kernel_bytes(name):
+    if REAL_BYTES == 4:
+        key = name if name in KERNEL_WORDS else ("k_vterm" if base_name(name).startswith("k_vterm") else base_name(name))
+        fixed, words = KERNEL_WORDS.get(key, (0, 0))
+        return float(fixed + 4 * words)
     if name in KERNEL_BYTES_EXACT:
         return KERNEL_BYTES_EXACT[name]
     if LAZY and base_name(name) == "k_gather":
@@ -72,7 +83,7 @@ def traffic_of(name, n_sd):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture (profiles/):
     recorded per SD there because the capture ran on a smaller box; scaled to this launch's SD count"""
     p = os.path.join(ROOT, "profiles", "traffic.json")
-    if not os.path.exists(p):
+    if not os.path.exists(p) or REAL_BYTES == 4:      # the capture is of the double-precision engine
         return None
     table = json.load(open(p))["dram_bytes_per_sd"]
     hits = [k for k in table if k in name]
@@ -159,9 +170,9 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples), "source": self.source}
 
 
-def pinned(shape):
+def pinned(shape, dtype=np.float64):
     import torch
-    return torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
+    return torch.empty(shape, dtype=torch.float64 if dtype == np.float64 else torch.float32, pin_memory=True).numpy()
 
 
 def make_case(lib, nx, ny, nz, sd_conc, n_sd_max_factor=1.25, pin=False, rank=0, size=1, config="cfg4"):
@@ -170,7 +181,8 @@ def make_case(lib, nx, ny, nz, sd_conc, n_sd_max_factor=1.25, pin=False, rank=0,
     a face every step); SURVEY.md section 8d"""
     from libcloudphxx_b200 import lgrngn as L
     from tests import support as S
-    alloc = pinned if pin else (lambda s: np.empty(s, dtype=np.float64))
+    dtype = getattr(lib, "dtype", np.float64)
+    alloc = (lambda s: pinned(s, dtype)) if pin else (lambda s: np.empty(s, dtype=dtype))
     oi = lib.opts_init_t()
     oi.nx, oi.ny, oi.nz = nx, ny, nz
     oi.dx = oi.dy = oi.dz = 20.0
@@ -322,7 +334,12 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    lib = L.b200()
+    global REAL_BYTES
+    f32 = args.real == "f32"
+    if f32:
+        assert world == 1 and args.gpus == 1, "--real f32 is a single-GPU informative mode"
+        REAL_BYTES = 4
+    lib = L.b200(args.real)
     if world > 1:       # torchrun exports OMP_NUM_THREADS=1; the host-side initialisation wants its share of the cores
         try:
             C.CDLL("libgomp.so.1").omp_set_num_threads(max(1, (cores or os.cpu_count() or 1) // (1 if cores else world)))
@@ -354,11 +371,12 @@ def run_b200(args):
     t_init = time.time() - t0
     engines = [D.engine_of(lib, p, d) for d in range(D.n_slabs(lib, p))]
     eng = engines[0]
-    lib.lib.lgrngn_b200_step_resident.argtypes = [C.c_void_p, C.c_int]
+    step_resident_fn = lib.lib.lgrngn_b200_step_resident_f32 if f32 else lib.lib.lgrngn_b200_step_resident
+    step_resident_fn.argtypes = [C.c_void_p, C.c_int]
     proto = D.proto_of(lib, p)
 
     def resident_step():
-        if lib.lib.lgrngn_b200_step_resident(proto, 0b1111) != 0:
+        if step_resident_fn(proto, 0b1111) != 0:
             raise RuntimeError("resident step failed on rank %d (live SDs %s)" % (rank, [e_.n_part() for e_ in engines]))
 
     def host_step():
@@ -456,9 +474,9 @@ def run_b200(args):
         roofline = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "peak_source": src, "unit": "GB/s",
                     "frac": (achieved / peak) if achieved else None, "traffic": traffic_of(name, n_prof),
                     "algorithmic_bytes_per_sd": per_sd, "sd_per_launch": n_prof, "mean_launch_ms": t_ms / n_l,
-                    "step_frac_of_hbm_roofline": value * A_FULL_BYTES / (n_slabs * peak * 1e9),
+                    "step_frac_of_hbm_roofline": value * (A_FULL_BYTES_F32 if f32 else A_FULL_BYTES) / (n_slabs * peak * 1e9),
                     "step_dram_bytes_per_sd": round(traffic_step / n_prof, 1) if traffic_step else None,
-                    "note": "the condensation kernel is FP64-pipe / issue bound, not HBM bound (ncu: profiles/)",
+                    "note": "the condensation kernel is %s-pipe / issue bound, not HBM bound (ncu: profiles/)" % ("FP32" if f32 else "FP64"),
                     "per_kernel": {k: {"GB/s": round(kernel_bytes(k) * n_prof / (ms_ / n * 1e-3) / 1e9, 1),
                                        "frac": round(kernel_bytes(k) * n_prof / (ms_ / n * 1e-3) / 1e9 / peak, 4)}
                                    for k, (n, ms_) in rep.items() if kernel_bytes(k) and ms_ > 0}}
@@ -484,11 +502,11 @@ def run_b200(args):
                     "sd_live_start": nx_glob * ny * nz * args.sd_conc, "sd_live_end": int(reduce(float(n_live()), "SUM")),
                     "migrants_per_step": (reduce(float(np.mean(migrants)), "SUM") if migrants else 0.0),
                     "migrant_frac_per_slab_step": (reduce(float(np.mean(migrants)), "SUM") / max(live_end, 1.0) if migrants else 0.0)}
-    assert conservation["dry_volume_rel_err"] < 1e-10, "dry volume not conserved: %r" % (conservation,)
+    assert conservation["dry_volume_rel_err"] < (1e-4 if f32 else 1e-10), "dry volume not conserved: %r" % (conservation,)
 
     # ---- the opt-in fast root search, for information (not the headline: see include/lcx_b200.h lcx_set_cond_solver) ----
     alt = None
-    if n_slabs == 1 and not args.no_alt:
+    if n_slabs == 1 and not args.no_alt and not f32:
         E.set_cond_solver("secant")
         for _ in range(2):
             resident_step()
@@ -505,7 +523,7 @@ def run_b200(args):
 
     # ---- CPU baseline beside it (rank 0, N = 1) -----------------------------------------------------------------------
     cpu = None
-    if rank == 0 and n_slabs == 1 and not args.no_cpu_baseline:
+    if rank == 0 and n_slabs == 1 and not args.no_cpu_baseline and not f32:
         try:
             out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1"],
                                  capture_output=True, text=True, timeout=900)
@@ -519,15 +537,15 @@ def run_b200(args):
         line = {
             "metric": "super-droplet updates/s (cond+coal+sedi+adve step)", "value": value, "unit": "SD-updates/s",
             "n_gpus": n_slabs, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%s x-slab%s: %dx%dx%d cells x %d SD/cell, hall_davis_no_waals, beard77fast, implicit adve, sstp 1/1, Cx=%s%s"
-                                   % (args.config, " per GPU" if args.scaling == "weak" else "s of a fixed domain", nx_of(0), ny, nz, args.sd_conc,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": args.real, "data": "synthetic",
+            "config": {"workload": "%s%s x-slab%s: %dx%dx%d cells x %d SD/cell, hall_davis_no_waals, beard77fast, implicit adve, sstp 1/1, Cx=%s%s"
+                                   % ("SINGLE-PRECISION ENGINE (factory<float>, second mode, not the headline) " if f32 else "", args.config, " per GPU" if args.scaling == "weak" else "s of a fixed domain", nx_of(0), ny, nz, args.sd_conc,
                                       "0.5" if args.config == "cfg5" else "0.1", ", rain mode (live-SD-weighted throughput)" if args.config == "cfg5" else ""),
                        "sd_per_gpu": sd_total // n_slabs, "global_cells": [nx_glob, ny, nz], "rng": "philox4x32-10",
                        "multi_gpu": ("multi_CUDA: one process, one host thread per GPU" if in_process else
                                      "one process per GPU, migrants packed into the neighbours' inboxes over CUDA-IPC peer memory" if world > 1 else "single GPU"),
                        "cond_solver": "toms748 (the reference's trial points)", "cond_layout": E.get_cond_layout(), "lazy_gather": os.environ.get("LCX_LAZY_GATHER", "1") != "0",
-                       "l2": "inputs_exceed_l2 (%.1f GB of SD state per GPU)" % (sd_total / n_slabs * 76 / 1e9),
+                       "l2": "inputs_exceed_l2 (%.1f GB of SD state per GPU)" % (sd_total / n_slabs * (44 if f32 else 76) / 1e9),
                        "init_s": round(t_init, 2), "max_sd_per_cell": max_count, "wall_ms_per_step": wall_ms / args.steps},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "SD-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps},
@@ -549,6 +567,7 @@ def main():
     ap.add_argument("--config", default="cfg4", choices=["cfg4", "cfg5"], help="BASELINE.json configs[3] / configs[4]")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="weak: --nx columns per GPU; strong: --nx columns in total")
     ap.add_argument("--no-alt", action="store_true", help="skip the informative opt-in secant pass")
+    ap.add_argument("--real", default="f64", choices=["f64", "f32"], help="f32: the single-precision engine (factory<float>), single GPU, informative")
     ap.add_argument("--nx", type=int, default=64)
     ap.add_argument("--ny", type=int, default=256)
     ap.add_argument("--nz", type=int, default=128)

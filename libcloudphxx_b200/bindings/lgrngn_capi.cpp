@@ -14,14 +14,20 @@
 namespace lg = libcloudphxx::lgrngn;
 namespace lc = libcloudphxx::common;
 
+typedef lgc_real real;
+
 #if defined(LGC_REFERENCE_BUILD)
 // implemented in oracle/ref_internals.cpp (reads the reference's private state)
 extern "C" long lgc_ref_internal_get_n(void *proto, int backend, unsigned long long *dst, long cap);
+extern "C" long lgc_ref_internal_get_n_f32(void *proto, int backend, unsigned long long *dst, long cap);
+#else
+// extension of the B200 back-end (host/particles_b200.h): multiplicities as 64-bit integers, either precision
+extern "C" int lgrngn_b200_get_n(void *proto, int real_bytes, unsigned long long *dst, long long cap, long long *n_out);
 #endif
 
 struct lgc_handle
 {
-  std::unique_ptr<lg::particles_proto_t<double>> p;
+  std::unique_ptr<lg::particles_proto_t<real>> p;
   int backend;
   long n_cell;
 };
@@ -31,49 +37,50 @@ namespace
   thread_local std::string last_error;
 
   // sum of lognormal modes in ln r
-  struct lognormal_sum : lc::unary_function<double>
+  struct lognormal_sum : lc::unary_function<real>
   {
     std::vector<double> mean_r, stdev, n_tot;
-    double funval(const double lnr) const
+    real funval(const real lnr_) const
     {
+      const double lnr = lnr_;
       double res = 0;
       for (std::size_t m = 0; m < mean_r.size(); ++m)
       {
         const double lns = std::log(stdev[m]), d = lnr - std::log(mean_r[m]);
         res += n_tot[m] * std::exp(-(d * d) / 2. / (lns * lns)) / lns / std::sqrt(2 * M_PI);
       }
-      return res;
+      return real(res);
     }
   };
 
   // exponential distribution in droplet volume written in ln r (Shima et al. 2009, Golovin test)
-  struct expvolume : lc::unary_function<double>
+  struct expvolume : lc::unary_function<real>
   {
     double r0, n0;
-    double funval(const double lnr) const
+    real funval(const real lnr) const
     {
-      const double r = std::exp(lnr), q = r / r0, q3 = q * q * q;
-      return n0 * 3. * q3 * std::exp(-q3);
+      const double r = std::exp(double(lnr)), q = r / r0, q3 = q * q * q;
+      return real(n0 * 3. * q3 * std::exp(-q3));
     }
   };
 
   // the caller's own n(ln r)
-  struct callback_distro : lc::unary_function<double>
+  struct callback_distro : lc::unary_function<real>
   {
     double (*fn)(double, void *);
     void *ctx;
-    double funval(const double lnr) const { return fn(lnr, ctx); }
+    real funval(const real lnr) const { return real(fn(double(lnr), ctx)); }
   };
 
-  lg::arrinfo_t<double> mk(const lgc_arr *a)
+  lg::arrinfo_t<real> mk(const lgc_arr *a)
   {
-    if (a == nullptr || a->data == nullptr) return lg::arrinfo_t<double>();
-    return lg::arrinfo_t<double>(a->data, std::vector<ptrdiff_t>{a->strides[0], a->strides[1], a->strides[2]});
+    if (a == nullptr || a->data == nullptr) return lg::arrinfo_t<real>();
+    return lg::arrinfo_t<real>(a->data, std::vector<ptrdiff_t>{a->strides[0], a->strides[1], a->strides[2]});
   }
 
-  lg::opts_t<double> mk(const lgc_opts *o)
+  lg::opts_t<real> mk(const lgc_opts *o)
   {
-    lg::opts_t<double> r;
+    lg::opts_t<real> r;
     r.adve = o->adve; r.sedi = o->sedi; r.subs = o->subs; r.cond = o->cond; r.coal = o->coal; r.rcyc = o->rcyc;
     r.RH_max = o->RH_max; r.dt = o->dt;
     return r;
@@ -104,7 +111,7 @@ const char *lgc_impl_name(void)
 void lgc_opts_init_defaults(lgc_opts_init *o)
 {
   std::memset(o, 0, sizeof(*o));
-  const lg::opts_init_t<double> d;
+  const lg::opts_init_t<real> d;
   o->backend = lg::CUDA;
   o->nx = d.nx; o->ny = d.ny; o->nz = d.nz;
   o->dx = d.dx; o->dy = d.dy; o->dz = d.dz; o->dt = d.dt;
@@ -130,7 +137,7 @@ void lgc_opts_init_defaults(lgc_opts_init *o)
 
 void lgc_opts_defaults(lgc_opts *o)
 {
-  const lg::opts_t<double> d;
+  const lg::opts_t<real> d;
   o->adve = d.adve; o->sedi = d.sedi; o->subs = d.subs; o->cond = d.cond; o->coal = d.coal; o->rcyc = d.rcyc;
   o->RH_max = d.RH_max; o->dt = d.dt;
 }
@@ -139,7 +146,7 @@ int lgc_create(const lgc_opts_init *c, lgc_handle **out)
 {
   *out = nullptr;
   return guarded([&] {
-    lg::opts_init_t<double> o;
+    lg::opts_init_t<real> o;
     o.nx = c->nx; o.ny = c->ny; o.nz = c->nz;
     o.dx = c->dx; o.dy = c->dy; o.dz = c->dz; o.dt = c->dt;
     o.sstp_cond = c->sstp_cond; o.sstp_coal = c->sstp_coal;
@@ -168,12 +175,12 @@ int lgc_create(const lgc_opts_init *c, lgc_handle **out)
     for (int i = 0; i < c->n_dry_sizes; ++i)
     {
       const lgc_dry_size &d = c->dry_sizes[i];
-      o.dry_sizes[lg::kappa_rd_insol_t<double>(d.kappa, d.rd_insol)][d.radius] = std::make_pair(d.conc, d.count);
+      o.dry_sizes[lg::kappa_rd_insol_t<real>(real(d.kappa), real(d.rd_insol))][real(d.radius)] = std::make_pair(real(d.conc), d.count);
     }
     for (int i = 0; i < c->n_distros; ++i)
     {
       const lgc_distro &d = c->distros[i];
-      std::shared_ptr<lc::unary_function<double>> f;
+      std::shared_ptr<lc::unary_function<real>> f;
       if (d.kind == 0)
       {
         auto s = std::make_shared<lognormal_sum>();
@@ -196,12 +203,12 @@ int lgc_create(const lgc_opts_init *c, lgc_handle **out)
         f = s;
       }
       else throw std::runtime_error("lgc_create: unknown distro kind");
-      o.dry_distros.emplace(lg::kappa_rd_insol_t<double>(d.kappa, d.rd_insol), f);
+      o.dry_distros.emplace(lg::kappa_rd_insol_t<real>(real(d.kappa), real(d.rd_insol)), f);
     }
     std::unique_ptr<lgc_handle> h(new lgc_handle);
     h->backend = c->backend;
-    h->p.reset(lg::factory<double>(lg::backend_t(c->backend), o));
-    const lg::opts_init_t<double> &oi = *h->p->opts_init;
+    h->p.reset(lg::factory<real>(lg::backend_t(c->backend), o));
+    const lg::opts_init_t<real> &oi = *h->p->opts_init;
     h->n_cell = long(oi.nx ? oi.nx : 1) * (oi.ny ? oi.ny : 1) * (oi.nz ? oi.nz : 1);
     if (c->backend == lg::multi_CUDA) h->n_cell = long(c->nx ? c->nx : 1) * (c->ny ? c->ny : 1) * (c->nz ? c->nz : 1);
     *out = h.release();
@@ -241,7 +248,7 @@ int lgc_step_async(lgc_handle *h, const lgc_opts *o)
 int lgc_diag(lgc_handle *h, int what, double a, double b)
 {
   return guarded([&] {
-    lg::particles_proto_t<double> &p = *h->p;
+    lg::particles_proto_t<real> &p = *h->p;
     switch (what)
     {
       case LGC_DIAG_ALL:            p.diag_all(); break;
@@ -273,20 +280,20 @@ int lgc_diag(lgc_handle *h, int what, double a, double b)
 
 long lgc_n_cell(lgc_handle *h) { return h->n_cell; }
 
-int lgc_outbuf(lgc_handle *h, double *dst, long n)
+int lgc_outbuf(lgc_handle *h, real *dst, long n)
 {
   return guarded([&] {
-    const double *src = h->p->outbuf();
-    std::memcpy(dst, src, sizeof(double) * std::size_t(n < h->n_cell ? n : h->n_cell));
+    const real *src = h->p->outbuf();
+    std::memcpy(dst, src, sizeof(real) * std::size_t(n < h->n_cell ? n : h->n_cell));
   });
 }
 
-int lgc_get_attr(lgc_handle *h, const char *name, double *dst, long cap, long *n_out)
+int lgc_get_attr(lgc_handle *h, const char *name, real *dst, long cap, long *n_out)
 {
   return guarded([&] {
-    const std::vector<double> v = h->p->get_attr(name);
+    const std::vector<real> v = h->p->get_attr(name);
     *n_out = long(v.size());
-    std::memcpy(dst, v.data(), sizeof(double) * std::size_t(*n_out < cap ? *n_out : cap));
+    std::memcpy(dst, v.data(), sizeof(real) * std::size_t(*n_out < cap ? *n_out : cap));
   });
 }
 
@@ -294,14 +301,13 @@ int lgc_get_n(lgc_handle *h, unsigned long long *dst, long cap, long *n_out)
 {
   return guarded([&] {
 #if defined(LGC_REFERENCE_BUILD)
-    *n_out = lgc_ref_internal_get_n(h->p.get(), h->backend, dst, cap);
+    *n_out = sizeof(real) == 4 ? lgc_ref_internal_get_n_f32(h->p.get(), h->backend, dst, cap) : lgc_ref_internal_get_n(h->p.get(), h->backend, dst, cap);
     if (*n_out < 0) throw std::runtime_error("lgc_get_n: only the serial and OpenMP oracle back-ends expose n");
 #else
-    // extension of this back-end: multiplicities are readable like any other attribute
-    // (exact while n < 2^53, which init guarantees: reference init_n.ipp:136)
-    const std::vector<double> v = h->p->get_attr("n");
-    *n_out = long(v.size());
-    for (long i = 0; i < *n_out && i < cap; ++i) dst[i] = (unsigned long long)(v[std::size_t(i)]);
+    // extension of this back-end: multiplicities are readable as 64-bit integers (get_attr("n") would round them to real)
+    long long got = 0;
+    if (lgrngn_b200_get_n(h->p.get(), int(sizeof(real)), dst, cap, &got) != 0) throw std::runtime_error("lgc_get_n failed");
+    *n_out = long(got);
 #endif
   });
 }

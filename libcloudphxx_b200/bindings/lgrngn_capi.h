@@ -1,4 +1,6 @@
-/* Flat C view of libcloudphxx::lgrngn::particles_proto_t<double>.
+/* Flat C view of libcloudphxx::lgrngn::particles_proto_t<real>, real = double (symbols lgc_*) or, compiled with
+ * -DLGC_FLOAT, float (symbols lgcf_*; the reference instantiates both: src/lib.cpp:43-44).  Arrays are `lgc_real`,
+ * scalar options stay double in the structs and are converted on the way in.
  *
  * Role: what the reference's Boost.Python module (reference bindings/python/lgrngn.hpp:41-149,
  * bindings/python/lib.cpp:217-434) does for Python callers, done here as a plain C surface that
@@ -11,6 +13,30 @@
 #define LGRNGN_CAPI_H
 #ifdef __cplusplus
 extern "C" {
+#endif
+
+#ifdef LGC_FLOAT
+typedef float lgc_real;
+#define lgc_create lgcf_create
+#define lgc_destroy lgcf_destroy
+#define lgc_diag lgcf_diag
+#define lgc_get_attr lgcf_get_attr
+#define lgc_get_n lgcf_get_n
+#define lgc_impl_name lgcf_impl_name
+#define lgc_init lgcf_init
+#define lgc_last_error lgcf_last_error
+#define lgc_n_cell lgcf_n_cell
+#define lgc_opts_defaults lgcf_opts_defaults
+#define lgc_opts_init_defaults lgcf_opts_init_defaults
+#define lgc_outbuf lgcf_outbuf
+#define lgc_proto lgcf_proto
+#define lgc_puddle lgcf_puddle
+#define lgc_step_async lgcf_step_async
+#define lgc_step_cond lgcf_step_cond
+#define lgc_step_sync lgcf_step_sync
+#define lgc_sync_in lgcf_sync_in
+#else
+typedef double lgc_real;
 #endif
 
 typedef struct lgc_handle lgc_handle;
@@ -72,7 +98,7 @@ typedef struct
 } lgc_opts;
 
 /* data == NULL means "not supplied" (null arrinfo_t); strides are in elements */
-typedef struct { double *data; long strides[3]; } lgc_arr;
+typedef struct { lgc_real *data; long strides[3]; } lgc_arr;
 
 enum lgc_diag_t
 {
@@ -102,12 +128,12 @@ int  lgc_step_cond(lgc_handle *, const lgc_opts *, const lgc_arr *th, const lgc_
 int  lgc_step_async(lgc_handle *, const lgc_opts *);
 int  lgc_diag(lgc_handle *, int what, double a, double b);
 long lgc_n_cell(lgc_handle *);
-int  lgc_outbuf(lgc_handle *, double *dst, long n);
+int  lgc_outbuf(lgc_handle *, lgc_real *dst, long n);
 /* copies a per-SD attribute (storage order); *n_out = number of SDs, even if cap is too small */
-int  lgc_get_attr(lgc_handle *, const char *name, double *dst, long cap, long *n_out);
+int  lgc_get_attr(lgc_handle *, const char *name, lgc_real *dst, long cap, long *n_out);
 int  lgc_get_n(lgc_handle *, unsigned long long *dst, long cap, long *n_out);
 int  lgc_puddle(lgc_handle *, double *out14);
-void *lgc_proto(lgc_handle *);            /* the underlying particles_proto_t<double>* (for back-end specific extras) */
+void *lgc_proto(lgc_handle *);            /* the underlying particles_proto_t<real>* (for back-end specific extras) */
 
 #ifdef __cplusplus
 }

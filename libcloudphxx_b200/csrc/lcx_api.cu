@@ -144,7 +144,7 @@ int lcx_create(const lcx_config *cfg, lcx_engine **out)
   *out = nullptr;
   return guarded([&] {
     using namespace lcx;
-    if (cfg->real_bytes != 8) throw error("lcx_create: only real_bytes = 8 (double) is available in this build");
+    if (cfg->real_bytes != int(sizeof(real_t))) throw error("lcx_create: this engine computes in " + std::string(sizeof(real_t) == 8 ? "double" : "single") + " precision; real_bytes does not match");
     if (lcx_device_count() == 0) throw error("lcx_create: no CUDA device is available - the B200 back-end has no CPU fallback");
     if (cfg->n_sd_max == 0) throw error("lcx_create: n_sd_max must be positive");
     if (cfg->n_sd_max >= 0xfffffff0ull) throw error("lcx_create: n_sd_max per slab must be below 2^32");
@@ -438,6 +438,18 @@ int lcx_get_attr_u64(lcx_engine *e, int attr, uint64_t *dst, int64_t cap, int64_
       lcx::scatter_n_by_sid(e, reinterpret_cast<uint64_t *>(e->tmp_real.p));
       LCX_CUDA(cudaMemcpyAsync(dst, e->tmp_real.p, cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
       LCX_CUDA(cudaStreamSynchronize(e->stream));
+      return;
+    }
+    if (attr == LCX_A_N)
+    {
+      // single-precision engine: the real-sized scratch array is too small for 64-bit integers; a diagnostics path, so a
+      // temporary allocation will do
+      uint64_t *scratch = nullptr;
+      LCX_CUDA(cudaMalloc(&scratch, e->n_part * sizeof(uint64_t)));
+      lcx::scatter_n_by_sid(e, scratch);
+      LCX_CUDA(cudaMemcpyAsync(dst, scratch, cnt * sizeof(uint64_t), cudaMemcpyDeviceToHost, e->stream));
+      LCX_CUDA(cudaStreamSynchronize(e->stream));
+      LCX_CUDA(cudaFree(scratch));
       return;
     }
     std::vector<lcx::real_t> tmp(e->n_part);

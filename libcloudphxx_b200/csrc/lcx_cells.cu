@@ -67,8 +67,11 @@ namespace lcx
 
     template <bool FAST>
     __global__ void __launch_bounds__(TPB) k_vterm_beard77(size_t n_part, int only_invalid, const real_t *__restrict__ rw2, const idx_t *__restrict__ ijk,
-                                                          const beard77_cell<real_t> *__restrict__ cells, const real_t *__restrict__ vt0, real_t *__restrict__ vt)
+                                                          const beard77_cell<real_t> *__restrict__ cells, const real_t *__restrict__ vt0, real_t *__restrict__ vt,
+                                                          const vt0_bins<real_t> bins)
     {
+      // `bins` comes from the host (the same object the host layer built the table with): constructed here it cost two log()
+      // per droplet, a fifth of the kernel's instructions
       const size_t i = size_t(blockIdx.x) * TPB + threadIdx.x;
       if (i >= n_part) return;
       const real_t r2 = rw2[i];
@@ -76,7 +79,6 @@ namespace lcx
       if (only_invalid && !(vt[i] == real_t(-1))) return;
       const beard77_cell<real_t> k = cells[ijk[i]];
       const real_t r = sqrt(r2);
-      const vt0_bins<real_t> bins;
       vt[i] = vt_beard77_fact(r, k) * (FAST ? vt0[bins.bin_of(r2)] : vt_beard77_v0(r));
     }
 
@@ -131,10 +133,11 @@ namespace lcx
       const grid_t &g = e->grid;
       beard77_cell<real_t> *cells = reinterpret_cast<beard77_cell<real_t> *>(e->cell_tmp4.p);
       LCX_LAUNCH(e, k_beard77_cells, div_up(g.n_cell, TPB), TPB, 0, g.n_cell, e->p.p, e->rhod.p, e->eta.p, cells);
+      const vt0_bins<real_t> bins;
       if (formula == VT_BEARD77FAST)
-        LCX_LAUNCH(e, (k_vterm_beard77<true>), div_up(e->n_part, TPB), TPB, 0, e->n_part, int(only_invalid), s.rw2.p, s.ijk.p, cells, e->vt0.p, s.vt.p);
+        LCX_LAUNCH(e, (k_vterm_beard77<true>), div_up(e->n_part, TPB), TPB, 0, e->n_part, int(only_invalid), s.rw2.p, s.ijk.p, cells, e->vt0.p, s.vt.p, bins);
       else
-        LCX_LAUNCH(e, (k_vterm_beard77<false>), div_up(e->n_part, TPB), TPB, 0, e->n_part, int(only_invalid), s.rw2.p, s.ijk.p, cells, e->vt0.p, s.vt.p);
+        LCX_LAUNCH(e, (k_vterm_beard77<false>), div_up(e->n_part, TPB), TPB, 0, e->n_part, int(only_invalid), s.rw2.p, s.ijk.p, cells, e->vt0.p, s.vt.p, bins);
       return;
     }
     LCX_LAUNCH(e, k_vterm, div_up(e->n_part, TPB), TPB, 0, e->n_part, e->cfg.terminal_velocity, int(only_invalid),

@@ -115,13 +115,14 @@ namespace lcx
     }
 
     // one candidate pair: a = physical index of the SD at even in-cell position, b = the next one: coal.ipp:181-268
-    __device__ __forceinline__ void try_pair(const coal_ctx &cx, uint32_t a, uint32_t b, real_t u01, real_t scl, real_t dv_c,
+    // pref = dt / dv * scale factor of the cell (the first two operations of the reference's product, the same for all its pairs)
+    __device__ __forceinline__ void try_pair(const coal_ctx &cx, uint32_t a, uint32_t b, real_t u01, real_t pref,
                                             unsigned long long &n_coll, unsigned long long &n_pairs)
     {
       const n_t n_a = cx.n[a], n_b = cx.n[b];
       const real_t rw2_a = cx.rw2[a], rw2_b = cx.rw2[b];
       const real_t vt_a = cx.vt[a], vt_b = cx.vt[b];
-      const real_t prob = cx.dt / dv_c * scl * coal_kernel(cx.kp, n_a, n_b, rw2_a, rw2_b, vt_a, vt_b);
+      const real_t prob = pref * coal_kernel(cx.kp, n_a, n_b, rw2_a, rw2_b, vt_a, vt_b);
       n_t col_no = n_t(prob);
       if (cx.pure_const_multi && col_no >= 1) cx.sc->increase_sstp_coal = 1u;
       if (u01 < prob - col_no) ++col_no;
@@ -176,6 +177,24 @@ namespace lcx
       return real_t(bits & ((1ull << 53) - 1)) * real_t(1.0 / 9007199254740992.0);
     }
 
+    // ranks of the lane's SDs e0, e0 + 16, ... (N of them) among the m keys of the cell; returns the sum of the ranks it wrote
+    template <int N>
+    __device__ __forceinline__ uint32_t rank_sweep(const uint32_t *key, unsigned short *perm, uint32_t e0, uint32_t m, uint32_t m4)
+    {
+      uint32_t mine[N], r[N], sum = 0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) { const uint32_t e = e0 + i * CELL_LANES; mine[i] = e < m ? key[e] : 0u; r[i] = 0; }
+      for (uint32_t j = 0; j < m4; j += 4)
+      {
+        const uint4 k = *reinterpret_cast<const uint4 *>(key + j);
+#pragma unroll
+        for (int i = 0; i < N; ++i) r[i] += (k.x < mine[i]) + (k.y < mine[i]) + (k.z < mine[i]) + (k.w < mine[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < N; ++i) { const uint32_t e = e0 + i * CELL_LANES; if (e < m) { perm[r[i]] = (unsigned short)e; sum += r[i]; } }
+      return sum;
+    }
+
 #ifndef LCX_COAL_MINB
 #define LCX_COAL_MINB 4      // 64 registers, 4 CTAs per SM: measured best of {1,3,4,5}
 #endif
@@ -216,29 +235,27 @@ namespace lcx
         }
       else
         for (uint32_t e = l; e < m4; e += CELL_LANES) key[e] = e < m ? rng.un[sid[b + e]] : 0xffffffffu;
-      for (uint32_t e = l; e < m; e += CELL_LANES) perm[e] = 0xffffu;
       __syncwarp();
 
-      // rank = number of smaller keys; a lane ranks up to four of its SDs per sweep over the keys
-      for (uint32_t e0 = l; e0 < m; e0 += 4 * CELL_LANES)
+      // rank = number of smaller keys; a lane ranks up to four of its SDs per sweep over the keys - as many as the more populous
+      // of the warp's two cells needs (three at 40 SDs per cell: a fourth would be a quarter more comparisons for nothing).
+      // Equal keys inside the cell share a rank, which shows in the sum of the ranks: m (m - 1) / 2 exactly when all differ.
+      const uint32_t m_warp = max(m, __shfl_xor_sync(0xffffffffu, m, 16));
+      uint32_t rank_sum = 0;
+      for (uint32_t e0 = l; e0 - l < m_warp; e0 += 4 * CELL_LANES)
       {
-        uint32_t mine[4], r[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { const uint32_t e = e0 + i * CELL_LANES; mine[i] = e < m ? key[e] : 0u; }
-        for (uint32_t j = 0; j < m4; j += 4)
-        {
-          const uint4 k = *reinterpret_cast<const uint4 *>(key + j);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) r[i] += (k.x < mine[i]) + (k.y < mine[i]) + (k.z < mine[i]) + (k.w < mine[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { const uint32_t e = e0 + i * CELL_LANES; if (e < m) perm[r[i]] = (unsigned short)e; }
+        const uint32_t left = m_warp - (e0 - l);           // warp-uniform
+        if (left > 3 * CELL_LANES)      rank_sum += rank_sweep<4>(key, perm, e0, m, m4);
+        else if (left > 2 * CELL_LANES) rank_sum += rank_sweep<3>(key, perm, e0, m, m4);
+        else if (left > CELL_LANES)     rank_sum += rank_sweep<2>(key, perm, e0, m, m4);
+        else                            rank_sum += rank_sweep<1>(key, perm, e0, m, m4);
       }
+#pragma unroll
+      for (int o = CELL_LANES / 2; o > 0; o >>= 1) rank_sum += __shfl_xor_sync(0xffffffffu, rank_sum, o);
       __syncwarp();
 
-      // equal keys inside the cell collide on one slot and leave another empty
-      bool hole = false;
-      for (uint32_t e = l; e < m; e += CELL_LANES) hole |= perm[e] == 0xffffu;
+      // equal keys inside the cell: re-rank with the storage index as tie-break
+      const bool hole = rank_sum != m * (m - 1) / 2 && m != 0;
       const unsigned group_lanes = 0xffffu << (threadIdx.x & 16);
       if (__ballot_sync(0xffffffffu, hole) & group_lanes)
       {
@@ -265,12 +282,11 @@ namespace lcx
       unsigned long long n_coll = 0, n_pairs = 0;
       if (m)
       {
-        const real_t scl = coal_scale_factor<real_t>(n_t(m));
-        const real_t dv_c = cx.dv[c];
+        const real_t pref = cx.dt / cx.dv[c] * coal_scale_factor<real_t>(n_t(m));
         for (uint32_t k = l; 2 * k + 1 < m; k += CELL_LANES)
         {
           const real_t u01 = philox ? u01_from_words(key[2 * k], key[2 * k + 1]) : rng.u01[b + 2 * k];
-          try_pair(cx, b + perm[2 * k], b + perm[2 * k + 1], u01, scl, dv_c, n_coll, n_pairs);
+          try_pair(cx, b + perm[2 * k], b + perm[2 * k + 1], u01, pref, n_coll, n_pairs);
         }
       }
       flush_stats(cx, n_coll, n_pairs);
@@ -302,7 +318,7 @@ namespace lcx
       if (((pos - b) & 1u) != 0u) return;     // only every second SD of a cell starts a pair
       if (pos + 1 >= en) return;              // the last SD of an odd-sized cell stays unpaired
       unsigned long long n_coll = 0, n_pairs = 0;
-      try_pair(cx, perm[pos], perm[pos + 1], rng.get_u01(uint32_t(pos)), coal_scale_factor<real_t>(n_t(en - b)), cx.dv[c], n_coll, n_pairs);
+      try_pair(cx, perm[pos], perm[pos + 1], rng.get_u01(uint32_t(pos)), cx.dt / cx.dv[c] * coal_scale_factor<real_t>(n_t(en - b)), n_coll, n_pairs);
       if (n_pairs)
       {
         atomicAdd(&cx.sc->n_collisions, n_coll);

@@ -82,6 +82,8 @@ namespace lcx
     // group of 8 lanes per cell: growth + 3rd-moment change + th/rv update
     // Not fused here although it looks tempting: the hskpng_Tpr + hskpng_vterm_all that open step_async.  Measured as an
     // epilogue of the last sub-step it cost 0.86 ms against 0.27 ms for the separate full-occupancy k_vterm (16 M SDs).
+    // Measured and rejected as well (round 2): the straight-line TOMS 748 with the growth law as a __noinline__ function
+    // reached from its eight call sites (no phase bookkeeping, 60 KB of SASS): 7.13 ms against 6.70 ms for the machine.
     // Lanes of a group stay in lock-step droplet by droplet on purpose: all root solves of a warp are then in the same
     // phase of TOMS 748 and share its (division-heavy) interpolation code; letting early finishers start their next
     // droplet at once (persistent-lane variant, measured) desynchronises the phases and is 35 % slower.

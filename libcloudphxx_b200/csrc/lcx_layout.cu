@@ -245,6 +245,7 @@ namespace lcx
       const uint32_t b = live ? off[c] : 0u, en = live ? off[c + 1] : 0u;
       uint32_t base = live ? new_off[c] : 0u;
       const uint32_t rounds = __reduce_max_sync(0xffffffffu, (en - b + MVG - 1) / MVG);
+      // (measured and dropped: issuing four rounds' loads before the first ballot - 0.725 ms against 0.694 ms)
       for (uint32_t r = 0; r < rounds; ++r)
       {
         const uint32_t t = b + r * MVG + l;
@@ -451,13 +452,13 @@ namespace lcx
       gather_set G; G.n = 0;
       if (!lazy)
       {
-        add(G, s.n.p, a.n.p, 8); add(G, s.rd3.p, a.rd3.p, 8); add(G, s.rw2.p, a.rw2.p, 8); add(G, s.kpa.p, a.kpa.p, 8);
-        add(G, s.vt.p, a.vt.p, 8);
+        add(G, s.n.p, a.n.p, 8); add(G, s.rd3.p, a.rd3.p, int(sizeof(real_t))); add(G, s.rw2.p, a.rw2.p, int(sizeof(real_t))); add(G, s.kpa.p, a.kpa.p, int(sizeof(real_t)));
+        add(G, s.vt.p, a.vt.p, int(sizeof(real_t)));
       }
-      if (!lazy) { add(G, s.x.p, a.x.p, 8); add(G, s.y.p, a.y.p, 8); add(G, s.z.p, a.z.p, 8); }
+      if (!lazy) { add(G, s.x.p, a.x.p, int(sizeof(real_t))); add(G, s.y.p, a.y.p, int(sizeof(real_t))); add(G, s.z.p, a.z.p, int(sizeof(real_t))); }
       if (!sid_moved) add(G, s.sid.p, a.sid.p, 4);
-      add(G, s.pp_rv.p, a.pp_rv.p, 8); add(G, s.pp_th.p, a.pp_th.p, 8); add(G, s.pp_rh.p, a.pp_rh.p, 8); add(G, s.pp_p.p, a.pp_p.p, 8);
-      add(G, s.rc2.p, a.rc2.p, 8);
+      add(G, s.pp_rv.p, a.pp_rv.p, int(sizeof(real_t))); add(G, s.pp_th.p, a.pp_th.p, int(sizeof(real_t))); add(G, s.pp_rh.p, a.pp_rh.p, int(sizeof(real_t))); add(G, s.pp_p.p, a.pp_p.p, int(sizeof(real_t)));
+      add(G, s.rc2.p, a.rc2.p, int(sizeof(real_t)));
       LCX_CUDA(cudaEventRecord(e->pre_gather, e->stream));      // uploads of the next step's fields may overtake the gather
       if (G.n || sorted_keys)
       {
@@ -494,10 +495,10 @@ namespace lcx
     gather_set G; G.n = 0;
     if (what & lcx_engine::PENDING_ATTR)
     {
-      add(G, src.n.p, dst.n.p, 8); add(G, src.rd3.p, dst.rd3.p, 8); add(G, src.rw2.p, dst.rw2.p, 8); add(G, src.kpa.p, dst.kpa.p, 8);
-      add(G, src.vt.p, dst.vt.p, 8);
+      add(G, src.n.p, dst.n.p, 8); add(G, src.rd3.p, dst.rd3.p, int(sizeof(real_t))); add(G, src.rw2.p, dst.rw2.p, int(sizeof(real_t))); add(G, src.kpa.p, dst.kpa.p, int(sizeof(real_t)));
+      add(G, src.vt.p, dst.vt.p, int(sizeof(real_t)));
     }
-    if (what & lcx_engine::PENDING_XYZ) { add(G, src.x.p, dst.x.p, 8); add(G, src.y.p, dst.y.p, 8); add(G, src.z.p, dst.z.p, 8); }
+    if (what & lcx_engine::PENDING_XYZ) { add(G, src.x.p, dst.x.p, int(sizeof(real_t))); add(G, src.y.p, dst.y.p, int(sizeof(real_t))); add(G, src.z.p, dst.z.p, int(sizeof(real_t))); }
     if (G.n) LCX_LAUNCH(e, k_gather, div_up(e->n_part, TPB), TPB, 0, e->n_part, e->pending_perm.p, nullptr, 0, dst.ijk.p, G);
   }
 

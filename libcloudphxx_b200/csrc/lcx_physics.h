@@ -332,15 +332,16 @@ namespace lcx
     template <class T>
     LCX_HD T cubic(const T &a, const T &b, const T &d, const T &e, const T &fa, const T &fb, const T &fd, const T &fe)
     {
-      const T q11 = (d - e) * fd / (fe - fd);
-      const T q21 = (b - d) * fb / (fd - fb);
-      const T q31 = (a - b) * fa / (fb - fa);
-      const T d21 = (b - d) * fd / (fd - fb);
-      const T d31 = (a - b) * fb / (fb - fa);
-      const T q22 = (d21 - q11) * fb / (fe - fb);
-      const T q32 = (d31 - q21) * fa / (fd - fa);
-      const T d32 = (d31 - q21) * fd / (fd - fa);
-      const T q33 = (d32 - q22) * fa / (fe - fa);
+      // lcx_div is the plain quotient except inside the condensation kernels' fast-math root solve
+      const T q11 = lcx_div((d - e) * fd, fe - fd);
+      const T q21 = lcx_div((b - d) * fb, fd - fb);
+      const T q31 = lcx_div((a - b) * fa, fb - fa);
+      const T d21 = lcx_div((b - d) * fd, fd - fb);
+      const T d31 = lcx_div((a - b) * fb, fb - fa);
+      const T q22 = lcx_div((d21 - q11) * fb, fe - fb);
+      const T q32 = lcx_div((d31 - q21) * fa, fd - fa);
+      const T d32 = lcx_div((d31 - q21) * fd, fd - fa);
+      const T q33 = lcx_div((d32 - q22) * fa, fe - fa);
       T c = q31 + q32 + q33 + a;
       if ((c <= a) || (c >= b)) c = quadratic(a, b, d, fa, fb, fd, 3);
       return c;
@@ -349,9 +350,12 @@ namespace lcx
     template <class T>
     LCX_HD bool values_coincide(const state<T> &s)
     {
+      // "any of the six differences below the threshold" as one comparison of their minimum: no chain of six branches
+      // (fmin drops NaNs like the comparisons do; all six NaN -> NaN < m -> false)
       const T m = fpl<T>::tiny() * 32;
-      return (fabs(s.fa - s.fb) < m) || (fabs(s.fa - s.fd) < m) || (fabs(s.fa - s.fe) < m) ||
-             (fabs(s.fb - s.fd) < m) || (fabs(s.fb - s.fe) < m) || (fabs(s.fd - s.fe) < m);
+      const T d1 = fmin(fabs(s.fa - s.fb), fabs(s.fa - s.fd)), d2 = fmin(fabs(s.fa - s.fe), fabs(s.fb - s.fd)),
+              d3 = fmin(fabs(s.fb - s.fe), fabs(s.fd - s.fe));
+      return fmin(fmin(d1, d2), d3) < m;
     }
   }
 
@@ -405,7 +409,7 @@ namespace lcx
       // double-length secant step from the end with the smaller residual
       T u, fu;
       if (fabs(s.fa) < fabs(s.fb)) { u = s.a; fu = s.fa; } else { u = s.b; fu = s.fb; }
-      c = u - 2 * (fu / (s.fb - s.fa)) * (s.b - s.a);
+      c = u - 2 * lcx_div(fu, s.fb - s.fa) * (s.b - s.a);
       if (fabs(c - u) > (s.b - s.a) / 2) c = s.a + (s.b - s.a) / 2;
       s.e = s.d; s.fe = s.fd;
       rebracket(f, s, c);
@@ -1027,15 +1031,20 @@ namespace lcx
     const real_t *eff;        // packed lower-triangular efficiency table
   };
 
-  LCX_HD int kernel_index(n_t R)   // kernel_utils.hpp:12-19 (argument arrives as an integer, compared in double)
+  // kernel_utils.hpp:12-19.  The reference takes the integer radius, compares and divides it in double and truncates:
+  // int(100 + (R - 100.) / 10.).  For an integer R > 100 the rounded quotient never reaches the next integer (its fractional
+  // part is a multiple of 1/10), so integer arithmetic gives the same index without the 64-bit int -> double conversions.
+  LCX_HD int kernel_index(n_t R)
   {
-    if (R <= 100.) return int(R);
-    return int(100 + (R - 100.) / 10.);
+    const uint32_t r = uint32_t(R);            // radii in micrometres, below the table's r_max
+    if (r <= 100u) return int(r);
+    return int(100u + (r - 100u) / 10u);
   }
-  LCX_HD size_t kernel_vector_index(int i, int j)   // kernel_utils.hpp:21-28 (n_user_params = 0 for tables)
+  // kernel_utils.hpp:21-28 (n_user_params = 0 for tables): size_t(0.5 * i * (i + 1) + j), exact in double, hence in integers
+  LCX_HD size_t kernel_vector_index(int i, int j)
   {
-    if (i >= j) return size_t(0.5 * i * (i + 1) + j);
-    return size_t(0.5 * j * (j + 1) + i);
+    const uint32_t a = uint32_t(i >= j ? i : j), b = uint32_t(i >= j ? j : i);
+    return size_t(a * (a + 1u) / 2u + b);
   }
 
   template <class real_t>
@@ -1058,7 +1067,11 @@ namespace lcx
     w[1] = x[1] - r1;
     w[2] = r2 - x[2];
     w[3] = x[3] - r2;
-    return (kp.eff[iv0] * w[1] * w[3] + kp.eff[iv1] * w[0] * w[3] + kp.eff[iv2] * w[1] * w[2] + kp.eff[iv3] * w[0] * w[2]) / dx / dy;
+    // ... / dx / dy with dx, dy = 1 below 100 um: dividing by one changes nothing, so those two divisions are skipped
+    real_t res = kp.eff[iv0] * w[1] * w[3] + kp.eff[iv1] * w[0] * w[3] + kp.eff[iv2] * w[1] * w[2] + kp.eff[iv3] * w[0] * w[2];
+    if (dx != 1) res = res / dx;
+    if (dy != 1) res = res / dy;
+    return res;
   }
 
   template <class real_t>

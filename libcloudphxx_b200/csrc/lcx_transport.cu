@@ -27,25 +27,43 @@ namespace lcx
       int adve, sedi, subs, scheme;
       real_t dt;
       int open_side_walls, periodic_topbot, bcond_lft, bcond_rgt;
+      // per-launch constants the host works out once instead of every thread: 1/dx.. (correctly rounded, as the kernel's own
+      // real_t(1) / dx was), 1/(x1 - x0).. for the periodic wrap, and the magic numbers of the divisions by nz and ny
+      real_t inv_dx, inv_dy, inv_dz, inv_Lx, inv_Ly, inv_Lz;
+      uint32_t nz_m, nz_s1, nz_s2, ny_m, ny_s1, ny_s2;
     };
+
+    // n / d for any 32-bit n by multiplication (Granlund & Montgomery 1994, fig. 4.1): m, s1, s2 from fastdiv_setup(d)
+    __device__ __forceinline__ uint32_t fastdiv(uint32_t n, uint32_t m, uint32_t s1, uint32_t s2)
+    {
+      const uint32_t t = __umulhi(m, n);
+      return (t + ((n - t) >> s1)) >> s2;
+    }
+    void fastdiv_setup(uint32_t d, uint32_t &m, uint32_t &s1, uint32_t &s2)
+    {
+      uint32_t l = 0;
+      while ((uint64_t(1) << l) < d) ++l;                       // ceil(log2 d)
+      m = uint32_t(((uint64_t(1) << 32) * ((uint64_t(1) << l) - d)) / d + 1);
+      s1 = l < 1 ? l : 1; s2 = l < 1 ? 0 : l - 1;
+    }
 
     // fmod(t, L) for t >= 0, L > 0 and a small quotient, without the library's iterative reduction.  fmod is exact in IEEE
     // arithmetic (the remainder is always representable), and t - q L evaluated by ONE fma is exact whenever it is
     // representable, i.e. as soon as q is the true integer quotient; a quotient off by one (rounding of t / L) is
     // detected by the sign / size of the remainder and the fma is redone.  Bit-identical to fmod().
-    __device__ __forceinline__ real_t fmod_small_quotient(real_t t, real_t L)
+    __device__ __forceinline__ real_t fmod_small_quotient(real_t t, real_t L, real_t inv_L)
     {
-      real_t q = floor(t / L);
+      real_t q = floor(t * inv_L);       // a quotient that may be off by one costs no more than the rounded t / L was: see above
       real_t r = fma(-q, L, t);
       if (r < 0)       { q -= 1; r = fma(-q, L, t); }
       else if (r >= L) { q += 1; r = fma(-q, L, t); }
       return r;
     }
-    __device__ __forceinline__ real_t periodic_wrap(real_t x, real_t a, real_t b)   // bcnd.ipp:99-110
+    __device__ __forceinline__ real_t periodic_wrap(real_t x, real_t a, real_t b, real_t inv_L)   // bcnd.ipp:99-110
     {
       const real_t L = b - a, t = (x - a) + 10 * L;
       // the reference assumes |displacement| < 10 domain lengths; outside that (or for NaN) fall back to the library
-      const real_t r = (t >= 0 && t < 64 * L) ? fmod_small_quotient(t, L) : fmod(t, L);
+      const real_t r = (t >= 0 && t < 64 * L) ? fmod_small_quotient(t, L, inv_L) : fmod(t, L);
       return a + r;
     }
 
@@ -85,16 +103,18 @@ namespace lcx
     __device__ __forceinline__ idx_t index_of(real_t x, real_t dx, real_t inv_dx)
     {
       const double q = double(x) * double(inv_dx);
-      const double fl = floor(q), fr = q - fl;
-      if (fr > 1e-9 && fr < 1 - 1e-9 && q < 1048576.) return idx_t(size_t(fl));
+      const int qi = __double2int_rd(q);                        // floor and conversion in one instruction (q < 2^20 below)
+      const double fr = q - double(qi);
+      if (fr > 1e-9 && fr < 1 - 1e-9 && q < 1048576.) return idx_t(qi);
       return idx_t(size_t(double(x) / double(dx)));
     }
 
-    __device__ __forceinline__ idx_t cell_of(const grid_t &g, real_t x, real_t y, real_t z, idx_t &i, idx_t &j, idx_t &k)   // hskpng_ijk.ipp:159-200
+    __device__ __forceinline__ idx_t cell_of(const tr_params &P, real_t x, real_t y, real_t z, idx_t &i, idx_t &j, idx_t &k)   // hskpng_ijk.ipp:159-200
     {
-      i = g.nx ? index_of(x, g.dx, real_t(1) / g.dx) : 0;
-      j = g.ny ? index_of(y, g.dy, real_t(1) / g.dy) : 0;
-      k = g.nz ? index_of(z, g.dz, real_t(1) / g.dz) : 0;
+      const grid_t &g = P.g;
+      i = g.nx ? index_of(x, g.dx, P.inv_dx) : 0;
+      j = g.ny ? index_of(y, g.dy, P.inv_dy) : 0;
+      k = g.nz ? index_of(z, g.dz, P.inv_dz) : 0;
       switch (g.n_dims)
       {
         case 1: return i;
@@ -135,8 +155,8 @@ namespace lcx
         switch (g.n_dims)      // two integer divisions at most: q = c / nz, then i = q / ny
         {
           case 1: i = c; break;
-          case 2: i = c / g.nz; k = c - i * g.nz; break;
-          case 3: { const idx_t q = c / g.nz; k = c - q * g.nz; i = q / g.ny; j = q - i * g.ny; } break;
+          case 2: i = fastdiv(c, P.nz_m, P.nz_s1, P.nz_s2); k = c - i * g.nz; break;
+          case 3: { const idx_t q = fastdiv(c, P.nz_m, P.nz_s1, P.nz_s2); k = c - q * g.nz; i = fastdiv(q, P.ny_m, P.ny_s1, P.ny_s2); j = q - i * g.ny; } break;
         }
         real_t x, y, z;
         if (LAZY) { const uint32_t src = perm[t]; x = g.nx ? xi[src] : 0; y = g.ny ? yi[src] : 0; z = g.nz ? zi[src] : 0; }
@@ -166,7 +186,7 @@ namespace lcx
           {
             x = x + real_t(g.halo_size) * g.dx;
             idx_t ih, jh, kh;
-            idx_t ch = cell_of(g, x, y, z, ih, jh, kh);
+            idx_t ch = cell_of(P, x, y, z, ih, jh, kh);
             real_t x_old = x, y_old = y, z_old = z;
             faces f = faces_of(g, ch, ih, jh);
             x = step_expl(x, ih, Cx[f.xl], Cx[f.xr], g.dx, true);
@@ -181,9 +201,9 @@ namespace lcx
             {
               if (y >= g.y1) y_old = y_old + (g.y1 - g.y0);
               if (y < g.y0)  y_old = y_old - (g.y1 - g.y0);
-              y = periodic_wrap(y, g.y0, g.y1);
+              y = periodic_wrap(y, g.y0, g.y1, P.inv_Ly);
             }
-            ch = cell_of(g, x, y, z, ih, jh, kh);
+            ch = cell_of(P, x, y, z, ih, jh, kh);
             x_old = x + x_old;
             if (g.n_dims > 2) y_old = y + y_old;
             if (g.n_dims > 1) z_old = z + z_old;
@@ -207,7 +227,7 @@ namespace lcx
           // x walls: bcnd.ipp:124-195
           if (P.bcond_lft == LCX_BCOND_SHAREDMEM && P.bcond_rgt == LCX_BCOND_SHAREDMEM)
           {
-            if (!P.open_side_walls) x = periodic_wrap(x, g.x0, g.x1);
+            if (!P.open_side_walls) x = periodic_wrap(x, g.x0, g.x1, P.inv_Lx);
             else if (x >= g.x1 || x < g.x0) n = 0;
           }
           else
@@ -218,7 +238,7 @@ namespace lcx
           // y walls: bcnd.ipp:197-219
           if (g.n_dims == 3)
           {
-            if (!P.open_side_walls) y = periodic_wrap(y, g.y0, g.y1);
+            if (!P.open_side_walls) y = periodic_wrap(y, g.y0, g.y1, P.inv_Ly);
             else if (y >= g.y1 || y < g.y0) n = 0;
           }
           // z walls: bcnd.ipp:221-364
@@ -245,7 +265,7 @@ namespace lcx
                 n = 0;
               }
             }
-            else z = periodic_wrap(z, g.z0, g.z1);
+            else z = periodic_wrap(z, g.z0, g.z1, P.inv_Lz);
           }
         }
 
@@ -264,7 +284,7 @@ namespace lcx
         if (n != 0 && fl == 0)
         {
           idx_t i2, j2, k2;
-          idx_t cell = cell_of(g, x, y, z, i2, j2, k2);
+          idx_t cell = cell_of(P, x, y, z, i2, j2, k2);
           if (cell >= g.n_cell) cell = g.n_cell - 1;
           kx = relayout_key(g, cell, g.class_bits ? rw2[t] : real_t(0));
         }
@@ -404,6 +424,13 @@ namespace lcx
     P.dt = real_t(o->dt);
     P.open_side_walls = e->cfg.open_side_walls; P.periodic_topbot = e->cfg.periodic_topbot_walls;
     P.bcond_lft = e->cfg.bcond_lft; P.bcond_rgt = e->cfg.bcond_rgt;
+    {
+      const grid_t &g = e->grid;
+      P.inv_dx = g.nx ? real_t(1) / g.dx : real_t(0); P.inv_dy = g.ny ? real_t(1) / g.dy : real_t(0); P.inv_dz = g.nz ? real_t(1) / g.dz : real_t(0);
+      P.inv_Lx = g.nx ? real_t(1) / (g.x1 - g.x0) : real_t(0); P.inv_Ly = g.ny ? real_t(1) / (g.y1 - g.y0) : real_t(0); P.inv_Lz = g.nz ? real_t(1) / (g.z1 - g.z0) : real_t(0);
+      fastdiv_setup(uint32_t(g.nz > 0 ? g.nz : 1), P.nz_m, P.nz_s1, P.nz_s2);
+      fastdiv_setup(uint32_t(g.ny > 0 ? g.ny : 1), P.ny_m, P.ny_s1, P.ny_s2);
+    }
     if (P.subs && e->w_LS.n < size_t(e->grid.nz)) throw error("subsidence requested but no w_LS profile was set");
     if (P.scheme == AS_PRED_CORR && e->grid.halo_size != 2) throw error("predictor-corrector advection needs a 2-cell Courant halo");
     static const int ctas_per_sm = [] { const char *v = std::getenv("LCX_TR_CTAS"); return v ? std::atoi(v) : 48; }();

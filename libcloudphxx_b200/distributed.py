@@ -35,15 +35,21 @@ def proto_of(lib, prt):
     return C.c_void_p(lib.lib.lgc_proto(prt._h))
 
 
+def _sfx(lib):
+    return "_f32" if getattr(lib, "real", "f64") == "f32" else ""
+
+
 def engine_of(lib, prt, slab=0):
-    lib.lib.lgrngn_b200_engine_of_slab.restype = C.c_void_p
-    lib.lib.lgrngn_b200_engine_of_slab.argtypes = [C.c_void_p, C.c_int]
-    return E.Engine(lib.lib.lgrngn_b200_engine_of_slab(proto_of(lib, prt), slab))
+    f = getattr(lib.lib, "lgrngn_b200_engine_of_slab" + _sfx(lib))
+    f.restype = C.c_void_p
+    f.argtypes = [C.c_void_p, C.c_int]
+    return E.Engine(f(proto_of(lib, prt), slab), getattr(lib, "real", "f64"))
 
 
 def n_slabs(lib, prt):
-    lib.lib.lgrngn_b200_n_slabs.argtypes = [C.c_void_p]
-    return int(lib.lib.lgrngn_b200_n_slabs(proto_of(lib, prt)))
+    f = getattr(lib.lib, "lgrngn_b200_n_slabs" + _sfx(lib))
+    f.argtypes = [C.c_void_p]
+    return int(f(proto_of(lib, prt)))
 
 
 def migr_stats(lib, prt):

@@ -5,16 +5,40 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LCX_LIB_PATH = os.path.join(os.environ.get("LCX_B200_LIBDIR") or os.path.join(_HERE, "lib"), "liblcx_b200.so")
+_LIBDIR = os.environ.get("LCX_B200_LIBDIR") or os.path.join(_HERE, "lib")
+LCX_LIB_PATH = os.path.join(_LIBDIR, "liblcx_b200.so")
+LCX_F32_LIB_PATH = os.path.join(_LIBDIR, "liblcx_b200_f32.so")
 _lib = None
+_lib_f32 = None
 
 
-def lib():
-    global _lib
+class _Suffixed:
+    """the single-precision engine exports the same entry points with the suffix _f32 (include/lcx_b200_f32_names.h)"""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+
+    def __getattr__(self, name):
+        return getattr(self._cdll, name + "_f32")
+
+
+def lib(real="f64"):
+    global _lib, _lib_f32
+    if real == "f32":
+        if _lib_f32 is None:
+            if not os.path.exists(LCX_F32_LIB_PATH):
+                raise OSError("single-precision CUDA engine not built: %s is missing (there is no CPU fallback)" % LCX_F32_LIB_PATH)
+            _lib_f32 = _bind(_Suffixed(C.CDLL(LCX_F32_LIB_PATH, mode=C.RTLD_GLOBAL)))
+        return _lib_f32
     if _lib is None:
         if not os.path.exists(LCX_LIB_PATH):
             raise OSError("CUDA engine not built: %s is missing (there is no CPU fallback)" % LCX_LIB_PATH)
-        l = C.CDLL(LCX_LIB_PATH, mode=C.RTLD_GLOBAL)
+        _lib = _bind(C.CDLL(LCX_LIB_PATH, mode=C.RTLD_GLOBAL))
+    return _lib
+
+
+def _bind(l):
+    if True:
         l.lcx_last_error.restype = C.c_char_p
         l.lcx_version.restype = C.c_char_p
         l.lcx_timer_start.argtypes = [C.c_void_p]
@@ -29,8 +53,7 @@ def lib():
         l.lcx_puddle.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         l.lcx_top_loss.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         l.lcx_coal_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
-        _lib = l
-    return _lib
+    return l
 
 
 COND_SOLVERS = {"secant": 0, "toms748": 1, "exact": 2}
@@ -66,57 +89,58 @@ def get_cond_staged():
     return bool(lib().lcx_get_cond_staged())
 
 
-def check(rc):
+def check(rc, real="f64"):
     if rc != 0:
-        raise RuntimeError(lib().lcx_last_error().decode())
+        raise RuntimeError(lib(real).lcx_last_error().decode())
 
 
 class Engine:
-    """non-owning handle of the lcx_engine behind a single-slab particle system"""
+    """non-owning handle of the lcx_engine behind a single-slab particle system (real = "f32": an engine of liblcx_b200_f32.so)"""
 
-    def __init__(self, handle):
+    def __init__(self, handle, real="f64"):
         if not handle:
             raise RuntimeError("no engine behind this particle system")
         self.h = C.c_void_p(handle)
-        self.l = lib()
+        self.real = real
+        self.l = lib(real)
 
     def sync(self):
-        check(self.l.lcx_sync(self.h))
+        check(self.l.lcx_sync(self.h), self.real)
 
     def timer_start(self):
-        check(self.l.lcx_timer_start(self.h))
+        check(self.l.lcx_timer_start(self.h), self.real)
 
     def timer_stop(self):
         ms = C.c_float()
-        check(self.l.lcx_timer_stop(self.h, C.byref(ms)))
+        check(self.l.lcx_timer_stop(self.h, C.byref(ms)), self.real)
         return ms.value
 
     def launches(self):
         v = C.c_uint64()
-        check(self.l.lcx_launch_count(self.h, C.byref(v)))
+        check(self.l.lcx_launch_count(self.h, C.byref(v)), self.real)
         return v.value
 
     def n_part(self):
         v = C.c_int64()
-        check(self.l.lcx_n_part(self.h, C.byref(v)))
+        check(self.l.lcx_n_part(self.h, C.byref(v)), self.real)
         return v.value
 
     def cell_stats(self):
         a, b = C.c_int64(), C.c_int64()
-        check(self.l.lcx_cell_stats(self.h, C.byref(a), C.byref(b)))
+        check(self.l.lcx_cell_stats(self.h, C.byref(a), C.byref(b)), self.real)
         return a.value, b.value
 
     def coal_stats(self):
         a, b = C.c_uint64(), C.c_uint64()
-        check(self.l.lcx_coal_stats(self.h, C.byref(a), C.byref(b)))
+        check(self.l.lcx_coal_stats(self.h, C.byref(a), C.byref(b)), self.real)
         return a.value, b.value
 
     def profile(self, on):
-        check(self.l.lcx_profile_enable(self.h, int(on)))
+        check(self.l.lcx_profile_enable(self.h, int(on)), self.real)
 
     def profile_report(self):
         buf = C.create_string_buffer(1 << 16)
-        check(self.l.lcx_profile_report(self.h, buf, len(buf)))
+        check(self.l.lcx_profile_report(self.h, buf, len(buf)), self.real)
         out = {}
         for line in buf.value.decode().splitlines():
             name, launches, ms = line.rsplit(" ", 2)
@@ -125,16 +149,16 @@ class Engine:
 
     def migr_real_attrs(self):
         v = C.c_int()
-        check(self.l.lcx_migr_real_attrs(self.h, C.byref(v)))
+        check(self.l.lcx_migr_real_attrs(self.h, C.byref(v)), self.real)
         return v.value
 
     def puddle(self):
         out = (C.c_double * 14)()
-        check(self.l.lcx_puddle(self.h, out))
+        check(self.l.lcx_puddle(self.h, out), self.real)
         return list(out)
 
     def top_loss(self):
         """(dry volume, number of super-droplets) that left through the lid since creation"""
         out = (C.c_double * 2)()
-        check(self.l.lcx_top_loss(self.h, out))
+        check(self.l.lcx_top_loss(self.h, out), self.real)
         return out[0], out[1]

@@ -17,6 +17,7 @@
 #include <libcloudph++/lgrngn/factory.hpp>
 
 #include "lcx_b200.h"
+#include "lcx_api_select.hpp"
 #include "lcx_physics.h"
 #include "particles_b200.h"
 #include <lgrngn_abi_probe.hpp>
@@ -198,9 +199,11 @@ namespace libcloudphxx
       struct slab
       {
         typedef unsigned long long n_t;
+        typedef lcx_api<real_t> L;         // the engine of this precision: liblcx_b200.so (double) or liblcx_b200_f32.so (float)
+        static void chk(int rc) { if (rc != 0) throw std::runtime_error(std::string("libcloudph++ (B200 engine): ") + L::last_error()); }
 
         opts_init_t<real_t> oi;            // this slab's options
-        lcx_engine *e = nullptr;
+        typename L::engine *e = nullptr;
         int n_dims;
         size_t n_cell;
         int n_x_bfr = 0, n_x_tot = 0;
@@ -246,7 +249,7 @@ namespace libcloudphxx
               else runs.push_back(run_t{long(q), l2e[q], 1});
             }
           }
-          ~map_t() { if (pinned) lcx_host_free(pinned); }
+          ~map_t() { if (pinned) L::host_free(pinned); }
         };
         map_t m_th, m_rv, m_rhod, m_p, m_cx, m_cy, m_cz;
         std::vector<real_t> outbuf_host;
@@ -274,7 +277,7 @@ namespace libcloudphxx
           unsupported_options();
         }
 
-        ~slab() { if (e) lcx_destroy(e); }
+        ~slab() { if (e) L::destroy(e); }
 
         void unsupported_options() const
         {
@@ -369,7 +372,7 @@ namespace libcloudphxx
         void init_e2l(const arrinfo_t<real_t> &arr, map_t &m, int field, int ext_x = 0, int ext_y = 0, int ext_z = 0, long offset = 0)
         {
           int64_t count = 0;
-          chk(lcx_field_size(e, field, &count));
+          chk(L::field_size(e, field, &count));
           m.l2e.resize(size_t(count));
           const long shift = long(n_cell_bfr) + offset;
           long max_stride = 0, max_stride_n_cell = 0;
@@ -407,13 +410,13 @@ namespace libcloudphxx
           if (!m.direct() && !m.pinned)
           {
             void *ptr = nullptr;
-            chk(lcx_host_alloc(m.l2e.size() * sizeof(real_t), &ptr));
+            chk(L::host_alloc(m.l2e.size() * sizeof(real_t), &ptr));
             m.pinned = static_cast<real_t *>(ptr);
           }
         }
 
         // device-pointer fast path of arrinfo_t: a model that keeps its fields on the GPU hands device pointers; copies then stay on the device
-        static bool on_device(const void *p) { int d = 0; chk(lcx_pointer_on_device(p, &d)); return d != 0; }
+        static bool on_device(const void *p) { int d = 0; chk(L::pointer_on_device(p, &d)); return d != 0; }
 
         // host copy of a caller's array that may live in device memory (initialisation and the Courant-range check read fields on the host)
         struct host_view
@@ -426,7 +429,7 @@ namespace libcloudphxx
             long hi = 0;
             for (const run_t &r : m.runs) hi = std::max(hi, r.src + r.len);
             buf.resize(size_t(hi));
-            chk(lcx_copy_to_host(buf.data(), a.data, buf.size() * sizeof(real_t)));
+            chk(L::copy_to_host(buf.data(), a.data, buf.size() * sizeof(real_t)));
             data = buf.data();
           }
         };
@@ -440,13 +443,13 @@ namespace libcloudphxx
             throw std::runtime_error("libcloudph++ (B200 engine): Eulerian arrays in device memory must be (nearly) contiguous: z fastest, no padding between rows");
           if (m.direct())
           {
-            for (const run_t &r : m.runs) chk(lcx_cells_set_part(e, field, r.dst, src + r.src, r.len));
+            for (const run_t &r : m.runs) chk(L::cells_set_part(e, field, r.dst, src + r.src, r.len));
             return;
           }
           const long n = long(m.l2e.size());
 #pragma omp parallel for schedule(static)
           for (long q = 0; q < n; ++q) m.pinned[q] = src[m.l2e[size_t(q)]];
-          chk(lcx_cells_set_part(e, field, 0, m.pinned, n));
+          chk(L::cells_set_part(e, field, 0, m.pinned, n));
         }
         void sync_out_field(int field, const map_t &m, arrinfo_t<real_t> &to)           // impl_sync.ipp:42-68
         {
@@ -455,15 +458,15 @@ namespace libcloudphxx
             throw std::runtime_error("libcloudph++ (B200 engine): Eulerian arrays in device memory must be (nearly) contiguous: z fastest, no padding between rows");
           if (m.direct())
           {
-            for (const run_t &r : m.runs) chk(lcx_cells_get_part(e, field, r.dst, to.data + r.src, r.len));
+            for (const run_t &r : m.runs) chk(L::cells_get_part(e, field, r.dst, to.data + r.src, r.len));
             return;
           }
-          chk(lcx_cells_get_part(e, field, 0, m.pinned, int64_t(m.l2e.size())));
+          chk(L::cells_get_part(e, field, 0, m.pinned, int64_t(m.l2e.size())));
           pending_out.push_back(std::make_pair(&m, to.data));
         }
         void finish_transfers()
         {
-          chk(lcx_sync(e));
+          chk(L::sync(e));
           for (const auto &po : pending_out)
           {
             const map_t &m = *po.first;
@@ -502,9 +505,9 @@ namespace libcloudphxx
           c.rc2_T = oi.rc2_T;
           std::vector<real_t> eff;
           if (oi.coal_switch) eff = init_kernel(c);
-          chk(lcx_create(&c, &e));
-          chk(lcx_set_dense_storage_index(e, dense_sid));
-          if (!eff.empty()) chk(lcx_set_efficiencies(e, eff.data(), int64_t(eff.size())));
+          chk(L::create(&c, &e));
+          chk(L::set_dense_storage_index(e, dense_sid));
+          if (!eff.empty()) chk(L::set_efficiencies(e, eff.data(), int64_t(eff.size())));
         }
 
         // kernel parameter checks and efficiency tables: init_kernel.ipp:6-235
@@ -567,9 +570,9 @@ namespace libcloudphxx
           sync_in_field(cy, m_cy, LCX_F_COURANT_Y);
           sync_in_field(cz, m_cz, LCX_F_COURANT_Z);
           finish_transfers();
-          if (oi.subs_switch) chk(lcx_cells_set(e, LCX_F_W_LS, oi.w_LS.data(), int64_t(oi.w_LS.size()), 0));
+          if (oi.subs_switch) chk(L::cells_set(e, LCX_F_W_LS, oi.w_LS.data(), int64_t(oi.w_LS.size()), 0));
 
-          chk(lcx_hskpng_Tpr(e));
+          chk(L::hskpng_Tpr(e));
 
           if (!oi.no_ccn_at_init)
           {
@@ -584,12 +587,12 @@ namespace libcloudphxx
             const lcx::vt0_bins<real_t> bins;
             std::vector<real_t> vt0(lcx::VT0_N_BIN);
             for (int it = 0; it < lcx::VT0_N_BIN; ++it) vt0[size_t(it)] = lcx::vt_beard77_v0(bins.mid(it));
-            chk(lcx_set_vt0_table(e, vt0.data(), int(vt0.size())));
+            chk(L::set_vt0_table(e, vt0.data(), int(vt0.size())));
           }
-          chk(lcx_hskpng_vterm(e, 1));
-          chk(lcx_hskpng_rc2(e));                        // critical radii for activation sub-stepping (particles_init.ipp:116-117)
-          chk(lcx_sstp_save(e));
-          chk(lcx_post_copy(e, 0, /*keep_all=*/1));      // hskpng_count(): group by the cells assigned at creation
+          chk(L::hskpng_vterm(e, 1));
+          chk(L::hskpng_rc2(e));                        // critical radii for activation sub-stepping (particles_init.ipp:116-117)
+          chk(L::sstp_save(e));
+          chk(L::post_copy(e, 0, /*keep_all=*/1));      // hskpng_count(): group by the cells assigned at creation
           engine.seed(oi.rng_seed);
           philox_call = 0;
         }
@@ -801,7 +804,7 @@ namespace libcloudphxx
               (*v[ix])[s] = u01[s] * std::min(b[ix], (ii + 1) * d[ix]) + (1. - u01[s]) * std::max(a[ix], ii * d[ix]);
             }
           }
-          chk(lcx_sd_append(e, int64_t(n_new), reinterpret_cast<const uint64_t *>(n.data()), rd3.data(), rw2.data(), kpa.data(),
+          chk(L::sd_append(e, int64_t(n_new), reinterpret_cast<const uint64_t *>(n.data()), rd3.data(), rw2.data(), kpa.data(),
                             xs.empty() ? nullptr : xs.data(), ys.empty() ? nullptr : ys.data(), zs.empty() ? nullptr : zs.data(), ijk.data()));
         }
 
@@ -982,22 +985,22 @@ namespace libcloudphxx
           adjust_timesteps(opts.dt);
           if (opts.cond)
           {
-            chk(lcx_hskpng_mfp(e));          // from the T, p left by the previous Tpr, as the reference does (particles_step.ipp:189-194)
+            chk(L::hskpng_mfp(e));          // from the T, p left by the previous Tpr, as the reference does (particles_step.ipp:189-194)
             if (oi.exact_sstp_cond && (sstp_cond > 1 || sstp_cond_act > 1))     // per-particle sub-stepping: particles_step.ipp:199-236
             {
               if (oi.adaptive_sstp_cond)
-                chk(lcx_cond_perparticle_adaptive(e, dt, opts.RH_max, sstp_cond, sstp_cond_act, oi.sstp_cond_adapt_drw2_eps, oi.sstp_cond_adapt_drw2_max));
+                chk(L::cond_perparticle_adaptive(e, dt, opts.RH_max, sstp_cond, sstp_cond_act, oi.sstp_cond_adapt_drw2_eps, oi.sstp_cond_adapt_drw2_max));
               else
-                chk(lcx_cond_perparticle(e, dt, opts.RH_max, sstp_cond, oi.sstp_cond_mix));
+                chk(L::cond_perparticle(e, dt, opts.RH_max, sstp_cond, oi.sstp_cond_mix));
             }
             else
               for (int step = 0; step < sstp_cond; ++step)
               {
-                chk(lcx_sstp_percell_step(e, step, sstp_cond, var_rho));
-                chk(lcx_hskpng_Tpr(e));
-                chk(lcx_cond(e, dt / sstp_cond, opts.RH_max, step, sstp_cond));      // includes update_th_rv
+                chk(L::sstp_percell_step(e, step, sstp_cond, var_rho));
+                chk(L::hskpng_Tpr(e));
+                chk(L::cond(e, dt / sstp_cond, opts.RH_max, step, sstp_cond));      // includes update_th_rv
               }
-            chk(lcx_sstp_save(e));
+            chk(L::sstp_save(e));
             sync_out_field(LCX_F_TH, m_th, th);
             sync_out_field(LCX_F_RV, m_rv, rv);
             finish_transfers();
@@ -1023,8 +1026,8 @@ namespace libcloudphxx
           if (opts.rlx) throw std::runtime_error("libcloudph++: aerosol relaxation was switched off in opts_init");
           adjust_timesteps(opts.dt);
 
-          chk(lcx_hskpng_Tpr(e));
-          if (opts.sedi || opts.coal || opts.cond) chk(lcx_hskpng_vterm(e, 0));
+          chk(L::hskpng_Tpr(e));
+          if (opts.sedi || opts.coal || opts.cond) chk(L::hskpng_vterm(e, 0));
 
           if (opts.coal)
           {
@@ -1035,7 +1038,7 @@ namespace libcloudphxx
               if (!injected.empty())
               {
                 int64_t n_part = 0;
-                chk(lcx_n_part(e, &n_part));
+                chk(L::n_part(e, &n_part));
                 un_host.swap(injected.front().first); u01_host.swap(injected.front().second);
                 injected.pop_front();
                 if (un_host.size() < size_t(n_part) || u01_host.size() < size_t(n_part))
@@ -1048,7 +1051,7 @@ namespace libcloudphxx
               {
                 // same draw order as the reference: un[n_part] for the shuffle, then u01[n_part] (hskpng_sort.ipp:33, coal.ipp:373)
                 int64_t n_part = 0;
-                chk(lcx_n_part(e, &n_part));
+                chk(L::n_part(e, &n_part));
                 un_host.resize(size_t(n_part)); u01_host.resize(size_t(n_part));
                 std::uniform_int_distribution<unsigned int> dist_un(0, std::numeric_limits<unsigned int>::max());
                 for (auto &v : un_host) v = uint32_t(real_t(dist_un(engine)));
@@ -1061,34 +1064,34 @@ namespace libcloudphxx
                 r.mode = LCX_RNG_PHILOX; r.seed = uint64_t(uint32_t(oi.rng_seed)); r.call = philox_call++;
                 r.cell_base = uint32_t(n_cell_bfr + philox_cell_base); r.stream = uint32_t(slab_rank);
               }
-              chk(lcx_coal(e, dt / sstp_coal, &r));
-              if (step + 1 != sstp_coal) chk(lcx_hskpng_vterm(e, 1));
+              chk(L::coal(e, dt / sstp_coal, &r));
+              if (step + 1 != sstp_coal) chk(L::hskpng_vterm(e, 1));
             }
             if (pure_const_multi)
             {
               int flag = 0;
-              chk(lcx_coal_flag(e, &flag));
+              chk(L::coal_flag(e, &flag));
               if (flag) ++sstp_coal;
             }
-            chk(lcx_hskpng_rc2(e));                       // collisions changed rd3 / kappa (particles_step.ipp:402-403)
+            chk(L::hskpng_rc2(e));                       // collisions changed rd3 / kappa (particles_step.ipp:402-403)
           }
 
           if (n_dims > 0)
           {
             lcx_transport_opts t;
             t.adve = opts.adve; t.sedi = opts.sedi; t.subs = opts.subs; t.adve_scheme = int(adve_scheme); t.dt = dt;
-            chk(lcx_transport(e, &t));
+            chk(L::transport(e, &t));
           }
           adve_scheme = oi.adve_scheme;
         }
 
-        void post_copy(const opts_t<real_t> &opts) { chk(lcx_post_copy(e, opts.rcyc, 0)); }
+        void post_copy(const opts_t<real_t> &opts) { chk(L::post_copy(e, opts.rcyc, 0)); }
 
         // x-slab migration through the neighbours' inboxes (include/lcx_b200.h); rgt / lft = neighbour engines of this process,
         // nullptr when the neighbours live in other processes
         int64_t n_sent[2] = {0, 0}, n_received[2] = {0, 0};
-        void migr_put() { chk(lcx_migr_put(e, &n_sent[0], &n_sent[1])); }
-        void migr_take(lcx_engine *rgt, lcx_engine *lft) { chk(lcx_migr_take(e, rgt, lft, &n_received[0], &n_received[1])); }
+        void migr_put() { chk(L::migr_put(e, &n_sent[0], &n_sent[1])); }
+        void migr_take(typename L::engine *rgt, typename L::engine *lft) { chk(L::migr_take(e, rgt, lft, &n_received[0], &n_received[1])); }
 
         bool process_distributed = false;      // one slab of a run spread over several processes (particles_b200.h)
 
@@ -1106,12 +1109,12 @@ namespace libcloudphxx
         }
 
         // ---- diagnostics -----------------------------------------------------------------------------------------
-        void diag_field(int field) { chk(lcx_hskpng_Tpr(e)); chk(lcx_diag_cell_field(e, field)); }
+        void diag_field(int field) { chk(L::hskpng_Tpr(e)); chk(L::diag_cell_field(e, field)); }
 
         real_t *outbuf()
         {
           outbuf_host.resize(n_cell);
-          chk(lcx_outbuf(e, outbuf_host.data(), int64_t(n_cell)));
+          chk(L::outbuf(e, outbuf_host.data(), int64_t(n_cell)));
           return outbuf_host.data();
         }
 
@@ -1126,17 +1129,17 @@ namespace libcloudphxx
           else throw std::runtime_error("Unknown attribute name passed to get_attr.");
           if ((a == LCX_A_X && !oi.nx) || (a == LCX_A_Y && !oi.ny) || (a == LCX_A_Z && !oi.nz)) return std::vector<real_t>();
           int64_t n_part = 0;
-          chk(lcx_n_part(e, &n_part));
+          chk(L::n_part(e, &n_part));
           std::vector<real_t> out(size_t(n_part), real_t(0));
           int64_t got = 0;
-          chk(lcx_get_attr(e, a, out.data(), n_part, &got));
+          chk(L::get_attr(e, a, out.data(), n_part, &got));
           return out;
         }
 
         std::map<common::output_t, real_t> diag_puddle()
         {
           double raw[14];
-          chk(lcx_puddle(e, raw));
+          chk(L::puddle(e, raw));
           std::map<common::output_t, real_t> res;
           for (int q = 0; q < 14; ++q) res[static_cast<common::output_t>(q)] = real_t(raw[q]);
           return res;
@@ -1152,6 +1155,8 @@ namespace libcloudphxx
         typedef particles_proto_t<real_t> parent_t;
         typedef typename parent_t::chem_map_t chem_map_t;
         typedef typename parent_t::chem_cmap_t chem_cmap_t;
+        typedef lcx_api<real_t> L;
+        static void chk(int rc) { slab<real_t>::chk(rc); }
 
         std::vector<std::unique_ptr<slab<real_t>>> slabs;
         std::unique_ptr<slab_workers> workers;     // multi_CUDA with more than one slab: one host thread per slab
@@ -1207,7 +1212,7 @@ namespace libcloudphxx
           // LCX_SLABS_ON_ONE_DEVICE=1 places every slab on device 0: lets the decomposition be tested on a single GPU
           const char *fold = std::getenv("LCX_SLABS_ON_ONE_DEVICE");
           const bool one_device = fold && std::string(fold) == "1";
-          int dev_count = lcx_device_count();
+          int dev_count = L::device_count();
           if (glob.dev_count > 0)
           {
             if (dev_count < glob.dev_count && !(one_device && dev_count > 0))
@@ -1272,8 +1277,8 @@ namespace libcloudphxx
             for (int d = 0; d < G; ++d)
             {
               const int lft = d > 0 ? d - 1 : G - 1, rgt = d < G - 1 ? d + 1 : 0;
-              if (slabs[size_t(d)]->bcond.first == distmem) chk(lcx_migr_connect(slabs[size_t(d)]->e, 0, slabs[size_t(lft)]->e));
-              if (slabs[size_t(d)]->bcond.second == distmem) chk(lcx_migr_connect(slabs[size_t(d)]->e, 1, slabs[size_t(rgt)]->e));
+              if (slabs[size_t(d)]->bcond.first == distmem) chk(L::migr_connect(slabs[size_t(d)]->e, 0, slabs[size_t(lft)]->e));
+              if (slabs[size_t(d)]->bcond.second == distmem) chk(L::migr_connect(slabs[size_t(d)]->e, 1, slabs[size_t(rgt)]->e));
             }
             connected = true;
           }
@@ -1343,7 +1348,7 @@ namespace libcloudphxx
         }
 
         // selectors
-        void sel(int kind, int attr, real_t lo, real_t hi, bool cons) { ready(); for (auto &s : slabs) chk(lcx_moms_select(s->e, kind, attr, lo, hi, cons)); }
+        void sel(int kind, int attr, real_t lo, real_t hi, bool cons) { ready(); for (auto &s : slabs) chk(L::moms_select(s->e, kind, attr, lo, hi, cons)); }
         void diag_all() override { sel(LCX_SEL_ALL, 0, 0, 0, false); }
         void diag_rw_ge_rc() override { sel(LCX_SEL_RW_GE_RC, 0, 0, 0, false); }
         void diag_RH_ge_Sc() override { sel(LCX_SEL_RH_GE_SC, 0, 0, 0, false); }
@@ -1370,18 +1375,18 @@ namespace libcloudphxx
         { throw std::runtime_error("libcloudph++: chemistry is switched off in opts_init, but diag_chem was called"); }
 
         // moments and fields
-        void mom(int attr, real_t power) { ready(); for (auto &s : slabs) chk(lcx_moms_calc(s->e, attr, power, 1)); }
+        void mom(int attr, real_t power) { ready(); for (auto &s : slabs) chk(L::moms_calc(s->e, attr, power, 1)); }
         void diag_dry_mom(const int &k) override { mom(LCX_A_RD3, k / 3.); }
         void diag_wet_mom(const int &k) override { mom(LCX_A_RW2, k / 2.); }
         void diag_kappa_mom(const int &k) override { mom(LCX_A_KPA, k); }
-        void diag_sd_conc() override { ready(); for (auto &s : slabs) chk(lcx_diag_sd_conc(s->e)); }
+        void diag_sd_conc() override { ready(); for (auto &s : slabs) chk(L::diag_sd_conc(s->e)); }
         void diag_pressure() override { ready(); for (auto &s : slabs) s->diag_field(LCX_F_P); }
         void diag_temperature() override { ready(); for (auto &s : slabs) s->diag_field(LCX_F_T); }
         void diag_RH() override { ready(); for (auto &s : slabs) s->diag_field(LCX_F_RH); }
-        void diag_precip_rate() override { ready(); for (auto &s : slabs) chk(lcx_diag_precip_rate(s->e)); }
-        void diag_max_rw() override { ready(); for (auto &s : slabs) chk(lcx_diag_max_rw(s->e)); }
-        void diag_wet_mass_dens(const real_t &rad, const real_t &sig0) override { ready(); for (auto &s : slabs) chk(lcx_diag_mass_dens(s->e, LCX_A_RW2, rad, sig0, 1. / 2.)); }
-        void diag_vel_div() override { ready(); for (auto &s : slabs) chk(lcx_diag_vel_div(s->e, s->oi.dt)); }
+        void diag_precip_rate() override { ready(); for (auto &s : slabs) chk(L::diag_precip_rate(s->e)); }
+        void diag_max_rw() override { ready(); for (auto &s : slabs) chk(L::diag_max_rw(s->e)); }
+        void diag_wet_mass_dens(const real_t &rad, const real_t &sig0) override { ready(); for (auto &s : slabs) chk(L::diag_mass_dens(s->e, LCX_A_RW2, rad, sig0, 1. / 2.)); }
+        void diag_vel_div() override { ready(); for (auto &s : slabs) chk(L::diag_vel_div(s->e, s->oi.dt)); }
 
         real_t *outbuf() override
         {
@@ -1621,13 +1626,15 @@ namespace libcloudphxx
       {
         case multi_CUDA:
         case CUDA:
-          if constexpr (std::is_same<real_t, double>::value)
+          // factory<float> (src/lib.cpp:43): the single-precision engine, like the reference's float instantiation.
+          // LCX_FLOAT_VIA_DOUBLE=1 serves float callers from the double-precision engine instead (widening adapter).
+          if constexpr (std::is_same<real_t, float>::value)
           {
-            if (backend == multi_CUDA) return new b200::particles_impl<double>(opts_init, 0);
-            return new b200::particles_impl<double>(opts_init);
+            const char *v = std::getenv("LCX_FLOAT_VIA_DOUBLE");
+            if (v && v[0] == '1') return new b200::particles_float(backend, opts_init);
           }
-          else
-            return new b200::particles_float(backend, opts_init);
+          if (backend == multi_CUDA) return new b200::particles_impl<real_t>(opts_init, 0);
+          return new b200::particles_impl<real_t>(opts_init);
         case OpenMP:     throw std::runtime_error("libcloudph++: OpenMP backend was not compiled");
         case serial:     throw std::runtime_error("libcloudph++: serial backend was not compiled");
         default:         throw std::runtime_error("libcloudph++: unknown backend");
@@ -1649,6 +1656,14 @@ static int guarded_c(F f)
   catch (const std::exception &ex) { std::cerr << ex.what() << std::endl; return 1; }
 }
 
+template <class real_t>
+static lg::b200::particles_impl<real_t> &impl_of_t(void *proto)
+{
+  auto *p = dynamic_cast<lg::b200::particles_impl<real_t> *>(static_cast<lg::particles_proto_t<real_t> *>(proto));
+  if (!p) throw std::runtime_error("not a B200 particle system of this precision");
+  return *p;
+}
+
 extern "C" {
 
 void lgrngn_b200_set_rng_mode(int mode) { lg::b200::g_rng_mode = mode; }
@@ -1657,13 +1672,41 @@ void lgrngn_b200_set_distmem(const lgrngn_b200_distmem *d) { lg::b200::g_distmem
 
 void lgrngn_b200_set_dense_sid(int mode) { lg::b200::g_dense_sid = mode; }
 
-static lg::b200::particles_impl<double> &impl_of(void *proto)
-{
-  auto *p = dynamic_cast<lg::b200::particles_impl<double> *>(static_cast<lg::particles_proto_t<double> *>(proto));
-  if (!p) throw std::runtime_error("not a B200 particle system");
-  return *p;
-}
+static lg::b200::particles_impl<double> &impl_of(void *proto) { return impl_of_t<double>(proto); }
 static lg::b200::slab<double> &slab_of(void *proto) { return impl_of(proto).one(); }
+
+// ---- the same handles for a single-precision particle system (particles_proto_t<float>*) ----
+int lgrngn_b200_n_slabs_f32(void *proto)
+{
+  try { return int(impl_of_t<float>(proto).slabs.size()); } catch (...) { return 0; }
+}
+void *lgrngn_b200_engine_of_slab_f32(void *proto, int d)      // an lcx_engine of liblcx_b200_f32.so: use the _f32 entry points on it
+{
+  try { auto &p = impl_of_t<float>(proto); return (d >= 0 && size_t(d) < p.slabs.size()) ? p.slabs[size_t(d)]->e : nullptr; } catch (...) { return nullptr; }
+}
+int lgrngn_b200_step_resident_f32(void *proto, int flags)
+{
+  return guarded_c([&] {
+    lg::opts_t<float> o;
+    o.adve = flags & 1; o.sedi = flags & 2; o.cond = flags & 4; o.coal = flags & 8;
+    impl_of_t<float>(proto).step_resident(o);
+  });
+}
+// multiplicities as 64-bit integers in storage order (get_attr("n") rounds them to real_t); real_bytes = sizeof the caller's real_t
+int lgrngn_b200_get_n(void *proto, int real_bytes, unsigned long long *dst, long long cap, long long *n_out)
+{
+  return guarded_c([&] {
+    int64_t got = 0;
+    if (real_bytes == 4)
+    {
+      auto &s = impl_of_t<float>(proto).one();
+      lg::b200::slab<float>::chk(lcx_get_attr_u64_f32(s.e, LCX_A_N, reinterpret_cast<uint64_t *>(dst), cap, &got));
+    }
+    else
+      lg::b200::chk(lcx_get_attr_u64(slab_of(proto).e, LCX_A_N, reinterpret_cast<uint64_t *>(dst), cap, &got));
+    *n_out = got;
+  });
+}
 
 void *lgrngn_b200_engine(void *proto)
 {

@@ -48,6 +48,12 @@ int   lgrngn_b200_get_layout(void *particles_proto, unsigned int *sid, unsigned 
 /* fields ALREADY RESIDENT in device memory: no host<->device field traffic.  flags: bit0 adve, bit1 sedi, bit2 cond, */
 /* bit3 coal.  Used by bench.py for the device-resident throughput figure.                                            */
 int   lgrngn_b200_step_resident(void *particles_proto, int flags);
+/* Single-precision particle systems (factory<float>: the engine liblcx_b200_f32.so, entry points lcx_*_f32): the same handles */
+int   lgrngn_b200_n_slabs_f32(void *particles_proto_float);
+void *lgrngn_b200_engine_of_slab_f32(void *particles_proto_float, int slab);
+int   lgrngn_b200_step_resident_f32(void *particles_proto_float, int flags);
+/* multiplicities as 64-bit integers in storage order, either precision (real_bytes = 8 or 4 says which proto it is)          */
+int   lgrngn_b200_get_n(void *particles_proto, int real_bytes, unsigned long long *dst, long long cap, long long *n_out);
 /* Binary-compatibility guard: the layout of opts_init_t / opts_t / arrinfo_t and the v-table slots of particles_proto_t as THIS  */
 /* library was compiled (text, see host/include/lgrngn_abi_probe.hpp); returns the length.  A host model built with other headers */
 /* (the reference's) compiles the same probe against them and compares the two strings before calling factory().                */

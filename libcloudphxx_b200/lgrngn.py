@@ -82,7 +82,20 @@ class _Opts(C.Structure):
 
 
 class _Arr(C.Structure):
-    _fields_ = [("data", C.POINTER(C.c_double)), ("strides", C.c_long * 3)]
+    _fields_ = [("data", C.c_void_p), ("strides", C.c_long * 3)]      # data: lgc_real * (double, or float for the lgcf_* binding)
+
+
+class _Prefixed:
+    """the flat binding of one precision: `lgc_xyz` resolves to `lgc_xyz` (double) or `lgcf_xyz` (float) of the shared library;
+    every other name (back-end specific extras) passes through"""
+
+    def __init__(self, cdll, prefix):
+        self._cdll, self._prefix = cdll, prefix
+
+    def __getattr__(self, name):
+        if name.startswith("lgc_"):
+            return getattr(self._cdll, self._prefix + name[4:])
+        return getattr(self._cdll, name)
 
 
 DIAG = {name: i for i, name in enumerate([
@@ -112,11 +125,17 @@ def expvolume(kappa, r0, n0, rd_insol=0.0):
 class Library:
     """One loaded implementation of the flat binding (the B200 back-end or, in tests, the reference)."""
 
-    def __init__(self, path):
+    def __init__(self, path, real="f64"):
+        """real: "f64" drives factory<double> (lgc_*), "f32" factory<float> (lgcf_*; the reference instantiates both)"""
         if not os.path.exists(path):
             raise OSError("shared library not found: %s (run `python -c 'import __graft_entry__ as g; g.build()'`)" % path)
+        assert real in ("f64", "f32")
         self.path = path
-        self.lib = lib = C.CDLL(path, mode=C.RTLD_LOCAL)
+        self.real = real
+        self.dtype = np.float64 if real == "f64" else np.float32
+        self.creal = C.c_double if real == "f64" else C.c_float
+        self.cdll = C.CDLL(path, mode=C.RTLD_LOCAL)
+        self.lib = lib = _Prefixed(self.cdll, "lgc_" if real == "f64" else "lgcf_")
         P = C.POINTER
         lib.lgc_last_error.restype = C.c_char_p
         lib.lgc_impl_name.restype = C.c_char_p
@@ -132,8 +151,8 @@ class Library:
         lib.lgc_diag.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
         lib.lgc_n_cell.argtypes = [C.c_void_p]
         lib.lgc_n_cell.restype = C.c_long
-        lib.lgc_outbuf.argtypes = [C.c_void_p, P(C.c_double), C.c_long]
-        lib.lgc_get_attr.argtypes = [C.c_void_p, C.c_char_p, P(C.c_double), C.c_long, P(C.c_long)]
+        lib.lgc_outbuf.argtypes = [C.c_void_p, P(self.creal), C.c_long]
+        lib.lgc_get_attr.argtypes = [C.c_void_p, C.c_char_p, P(self.creal), C.c_long, P(C.c_long)]
         lib.lgc_get_n.argtypes = [C.c_void_p, P(C.c_ulonglong), C.c_long, P(C.c_long)]
         lib.lgc_puddle.argtypes = [C.c_void_p, P(C.c_double)]
         self.name = lib.lgc_impl_name().decode()
@@ -233,19 +252,20 @@ class Opts:
         return c
 
 
-def _arr(a):
-    """numpy array (float64, any strides that are multiples of 8 B) -> lgc_arr; None -> NULL"""
+def _arr(a, dtype=np.float64):
+    """numpy array (of the library's real type, any strides that are multiples of the item size) -> lgc_arr; None -> NULL"""
     if a is None:
         return None
+    item = np.dtype(dtype).itemsize
     cai = getattr(a, "__cuda_array_interface__", None)
     if cai is not None and not isinstance(a, np.ndarray):
         # device-resident field (e.g. a torch CUDA tensor): the raw device pointer goes through arrinfo_t, copies stay on the GPU
-        assert cai["typestr"] in ("<f8", "=f8", "|f8"), "Eulerian fields must be float64"
+        assert cai["typestr"][1:] == "f%d" % item, "Eulerian fields must be %s" % np.dtype(dtype).name
         c = _Arr()
-        c.data = C.cast(C.c_void_p(int(cai["data"][0])), C.POINTER(C.c_double))
+        c.data = int(cai["data"][0])
         shape = tuple(cai["shape"])
         if cai.get("strides"):
-            st = [s // 8 for s in cai["strides"]]
+            st = [s // item for s in cai["strides"]]
         else:
             st = [int(np.prod(shape[i + 1:], dtype=np.int64)) for i in range(len(shape))]
         while len(st) < 3:
@@ -253,9 +273,9 @@ def _arr(a):
         for i in range(3):
             c.strides[i] = st[i]
         return C.byref(c)
-    assert a.dtype == np.float64, "Eulerian fields must be float64"
+    assert a.dtype == dtype, "Eulerian fields must be %s" % np.dtype(dtype).name
     c = _Arr()
-    c.data = a.ctypes.data_as(C.POINTER(C.c_double))
+    c.data = a.ctypes.data
     st = [s // a.itemsize for s in a.strides] if a.ndim else []
     while len(st) < 3:
         st.append(1)
@@ -282,19 +302,22 @@ class Particles:
             self._lib.lgc_destroy(h)
             self._h = None
 
+    def _a(self, *arrays):
+        return [_arr(a, self._L.dtype) for a in arrays]
+
     def init(self, th, rv, rhod, p=None, Cx=None, Cy=None, Cz=None):
-        self._L.check(self._lib.lgc_init(self._h, _arr(th), _arr(rv), _arr(rhod), _arr(p), _arr(Cx), _arr(Cy), _arr(Cz)))
+        self._L.check(self._lib.lgc_init(self._h, *self._a(th, rv, rhod, p, Cx, Cy, Cz)))
 
     def step_sync(self, opts, th, rv, rhod=None, Cx=None, Cy=None, Cz=None):
         o = opts._pack()
-        self._L.check(self._lib.lgc_step_sync(self._h, C.byref(o), _arr(th), _arr(rv), _arr(rhod), _arr(Cx), _arr(Cy), _arr(Cz)))
+        self._L.check(self._lib.lgc_step_sync(self._h, C.byref(o), *self._a(th, rv, rhod, Cx, Cy, Cz)))
 
     def sync_in(self, th, rv, rhod=None, Cx=None, Cy=None, Cz=None):
-        self._L.check(self._lib.lgc_sync_in(self._h, _arr(th), _arr(rv), _arr(rhod), _arr(Cx), _arr(Cy), _arr(Cz)))
+        self._L.check(self._lib.lgc_sync_in(self._h, *self._a(th, rv, rhod, Cx, Cy, Cz)))
 
     def step_cond(self, opts, th, rv):
         o = opts._pack()
-        self._L.check(self._lib.lgc_step_cond(self._h, C.byref(o), _arr(th), _arr(rv)))
+        self._L.check(self._lib.lgc_step_cond(self._h, C.byref(o), *self._a(th, rv)))
 
     def step_async(self, opts):
         o = opts._pack()
@@ -304,14 +327,14 @@ class Particles:
         self._L.check(self._lib.lgc_diag(self._h, DIAG[what], float(a), float(b)))
 
     def outbuf(self):
-        out = np.empty(self.n_cell, dtype=np.float64)
-        self._L.check(self._lib.lgc_outbuf(self._h, out.ctypes.data_as(C.POINTER(C.c_double)), out.size))
+        out = np.empty(self.n_cell, dtype=self._L.dtype)
+        self._L.check(self._lib.lgc_outbuf(self._h, out.ctypes.data_as(C.POINTER(self._L.creal)), out.size))
         return out
 
     def get_attr(self, name):
-        buf = np.empty(self._cap, dtype=np.float64)
+        buf = np.empty(self._cap, dtype=self._L.dtype)
         n = C.c_long()
-        self._L.check(self._lib.lgc_get_attr(self._h, name.encode(), buf.ctypes.data_as(C.POINTER(C.c_double)), buf.size, C.byref(n)))
+        self._L.check(self._lib.lgc_get_attr(self._h, name.encode(), buf.ctypes.data_as(C.POINTER(self._L.creal)), buf.size, C.byref(n)))
         return buf[:n.value].copy()
 
     def get_n(self):
@@ -351,12 +374,12 @@ for _n in ("dry_rng", "wet_rng", "kappa_rng", "dry_rng_cons", "wet_rng_cons", "k
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 B200_LIB_PATH = os.path.join(os.environ.get("LCX_B200_LIBDIR") or os.path.join(_HERE, "lib"), "liblgrngn_b200.so")
-_b200 = None
+_b200 = {}
 
 
-def b200():
-    """the B200-native back-end (hand-written CUDA behind the lgrngn API); fails loudly if it is not built"""
-    global _b200
-    if _b200 is None:
-        _b200 = Library(B200_LIB_PATH)
-    return _b200
+def b200(real="f64"):
+    """the B200-native back-end (hand-written CUDA behind the lgrngn API); fails loudly if it is not built.
+    real = "f32": factory<float>, served by the single-precision engine"""
+    if real not in _b200:
+        _b200[real] = Library(B200_LIB_PATH, real)
+    return _b200[real]

@@ -7,7 +7,8 @@ floating point is plain IEEE and comparable with `nvcc -fmad=false`):
   * /root/reference/src/lib_omp.cpp   - the reference's OpenMP back-end (-fopenmp)
   * /root/reference/src/lib.cpp       - the reference's factory
   * libcloudphxx_b200/bindings/lgrngn_capi.cpp, with -DLGC_REFERENCE_BUILD and the reference's
-    headers: the same flat C binding the product ships, so Python drives both identically
+    headers: the same flat C binding the product ships, so Python drives both identically; twice, for the
+    reference's double and float instantiations (lgc_* / lgcf_*)
   * oracle/ref_internals.cpp (x2) + ref_internals_glue.cpp - read-only access to private state
 The reference needs Boost (absent from this image); oracle/boost_shim/ supplies the few names it uses.
 Thrust comes from the CUDA toolkit (host back-ends only: no GPU code in the oracle).
@@ -39,7 +40,11 @@ UNITS = [  # (object name, source, extra flags)
     ("lib.o", os.path.join(REF, "src", "lib.cpp"), ["-fopenmp"]),
     ("capi.o", os.path.join(REPO, "libcloudphxx_b200", "bindings", "lgrngn_capi.cpp"),
      ["-DLGC_REFERENCE_BUILD", "-I", os.path.join(REPO, "libcloudphxx_b200", "bindings")]),
+    ("capi_f32.o", os.path.join(REPO, "libcloudphxx_b200", "bindings", "lgrngn_capi.cpp"),
+     ["-DLGC_REFERENCE_BUILD", "-DLGC_FLOAT", "-I", os.path.join(REPO, "libcloudphxx_b200", "bindings")]),
     ("internals_serial.o", os.path.join(HERE, "ref_internals.cpp"), []),
+    ("internals_serial_f32.o", os.path.join(HERE, "ref_internals.cpp"), ["-DLGC_INTERNALS_F32"]),
+    ("internals_omp_f32.o", os.path.join(HERE, "ref_internals.cpp"), ["-fopenmp", "-DLGC_INTERNALS_OMP", "-DLGC_INTERNALS_F32"]),
     ("internals_omp.o", os.path.join(HERE, "ref_internals.cpp"), ["-fopenmp", "-DLGC_INTERNALS_OMP"]),
     ("internals_glue.o", os.path.join(HERE, "ref_internals_glue.cpp"), []),
 ]
@@ -86,7 +91,7 @@ def build(force=False, verbose=True, fast=False):
         subprocess.run(base + extra + ["-c", src, "-o", objp], check=True)
         return obj, time.time() - t0
 
-    with ThreadPoolExecutor(max_workers=min(7, os.cpu_count() or 1)) as ex:
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         for obj, dt in ex.map(compile_one, UNITS):
             if verbose:
                 print("[oracle%s] %-20s %6.1f s" % (" -Ofast" if fast else "", obj, dt), flush=True)

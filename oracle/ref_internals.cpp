@@ -10,17 +10,25 @@
 // Test infrastructure: never linked into the product.
 #include "lib.hpp"
 
+// -DLGC_INTERNALS_F32: the same readers for the reference's single-precision instantiation (src/lib.cpp:43)
+#if defined(LGC_INTERNALS_F32)
+   typedef float lgc_ref_real;
+#  define LGC_SFX(name, be) name##_##be##_f32
+#else
+   typedef double lgc_ref_real;
+#  define LGC_SFX(name, be) name##_##be
+#endif
 #if defined(LGC_INTERNALS_OMP)
 #  include <thrust/system/omp/execution_policy.h>
 #  include <thrust/system/omp/vector.h>
    namespace thrust_device = ::thrust::omp;
 #  define LGC_BACKEND OpenMP
-#  define LGC_FN(name) name##_omp
+#  define LGC_FN(name) LGC_SFX(name, omp)
 #else
 #  include <thrust/system/cpp/vector.h>
    namespace thrust_device = ::thrust::cpp;
 #  define LGC_BACKEND serial
-#  define LGC_FN(name) name##_serial
+#  define LGC_FN(name) LGC_SFX(name, serial)
 #endif
 
 #include "particles.tpp"
@@ -31,7 +39,7 @@
 namespace
 {
   using namespace libcloudphxx::lgrngn;
-  typedef particles_t<double, LGC_BACKEND> prt_t;
+  typedef particles_t<lgc_ref_real, LGC_BACKEND> prt_t;
 
   template <class vec_t, class out_t>
   long copy_out(const vec_t &v, std::size_t n, out_t *dst, long cap)
@@ -44,7 +52,7 @@ namespace
 // returns the number of elements of the named array (copies at most cap of them), -1 if unknown
 extern "C" long LGC_FN(lgc_ref_dump_u64)(void *proto, const char *name, unsigned long long *dst, long cap)
 {
-  prt_t *p = static_cast<prt_t *>(static_cast<particles_proto_t<double> *>(proto));
+  prt_t *p = static_cast<prt_t *>(static_cast<particles_proto_t<lgc_ref_real> *>(proto));
   auto &s = *p->pimpl;
   const std::string nm(name);
   if (nm == "n")          return copy_out(s.n, s.n_part, dst, cap);
@@ -61,7 +69,7 @@ extern "C" long LGC_FN(lgc_ref_dump_u64)(void *proto, const char *name, unsigned
 
 extern "C" long LGC_FN(lgc_ref_dump_f64)(void *proto, const char *name, double *dst, long cap)
 {
-  prt_t *p = static_cast<prt_t *>(static_cast<particles_proto_t<double> *>(proto));
+  prt_t *p = static_cast<prt_t *>(static_cast<particles_proto_t<lgc_ref_real> *>(proto));
   auto &s = *p->pimpl;
   const std::string nm(name);
   if (nm == "vt")   return copy_out(s.vt, s.n_part, dst, cap);

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <memory>
+#include <string>
 #include <vector>
 
 using namespace libcloudphxx::lgrngn;
@@ -60,8 +61,11 @@ result<real_t> run()
   return r;
 }
 
-int main()
+int main(int argc, char **argv)
 {
+  // argv[1] = "native": the single-precision engine - roots of the growth equation are then bracketed to 2^-7 (sizeof(float) * 8 / 4
+  // bits, src/detail/config.hpp:39) like in the reference's float build, so fields agree with the double run to ~1e-3 only
+  const bool native = argc > 1 && std::string(argv[1]) == "native";
   const auto d = run<double>();
   const auto f = run<float>();
   double e_th = 0, e_rv = 0;
@@ -73,6 +77,7 @@ int main()
   const double e_m3 = std::fabs(f.m3_sum - d.m3_sum) / d.m3_sum;
   std::printf("float vs double: th %.3g rv %.3g m3 %.3g, SDs %zu / %zu, sd_conc sums %.0f / %.0f\n", e_th, e_rv, e_m3, f.n_sd, d.n_sd, f.sd_conc_sum, d.sd_conc_sum);
   // inputs / outputs pass through single precision once per step; the spectrum is evaluated in float
-  const bool ok = e_th < 5e-6 && e_rv < 5e-4 && e_m3 < 5e-3 && f.n_sd > 0 && std::fabs(double(f.n_sd) - double(d.n_sd)) < 0.02 * d.n_sd && f.sd_conc_sum == double(f.n_sd);
+  const double b_th = native ? 5e-3 : 5e-6, b_rv = native ? 5e-2 : 5e-4, b_m3 = native ? 1e-2 : 5e-3;
+  const bool ok = e_th < b_th && e_rv < b_rv && e_m3 < b_m3 && f.n_sd > 0 && std::fabs(double(f.n_sd) - double(d.n_sd)) < 0.02 * d.n_sd && f.sd_conc_sum == double(f.n_sd);
   return ok ? 0 : 1;
 }

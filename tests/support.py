@@ -15,7 +15,14 @@ ORACLE_LIB = os.path.join(ROOT, "oracle", "_ref", "liblgrngn_ref.so")
 _cache = {}
 
 
-def oracle_library():
+def oracle_library(real="f64"):
+    """the reference built from its own sources; real = "f32": its single-precision instantiation (lgcf_* binding)"""
+    if real == "f32":
+        if "ref32" not in _cache:
+            oracle_library()
+            _cache["ref32"] = L.Library(ORACLE_LIB, "f32")
+            assert _cache["ref32"].name == "reference"
+        return _cache["ref32"]
     if "ref" not in _cache:
         if not os.path.exists(ORACLE_LIB):
             import importlib.util
@@ -33,7 +40,12 @@ def oracle_library():
     return _cache["ref"]
 
 
-def b200_library():
+def b200_library(real="f64"):
+    if real == "f32":
+        if "b20032" not in _cache:
+            b200_library()                           # sets the (process-wide) replay mode
+            _cache["b20032"] = L.b200("f32")
+        return _cache["b20032"]
     if "b200" not in _cache:
         lib = L.b200()
         assert lib.name == "b200"
@@ -194,6 +206,8 @@ def run_pair(ref, b200, setup, n_steps, backend_ref=L.backend_t.serial, on_step=
     """runs the same case on the oracle and on the B200 back-end, step by step; on_step(step, p_ref, p_new, f_ref, f_new)"""
     oi_r, o_r, f_r = setup(ref, **kw)
     oi_n, o_n, f_n = setup(b200, **kw)
+    f_r = {k: np.ascontiguousarray(v, dtype=ref.dtype) for k, v in f_r.items()}        # single-precision libraries take float32 fields
+    f_n = {k: np.ascontiguousarray(v, dtype=b200.dtype) for k, v in f_n.items()}
     p_r = ref.factory(backend_ref, oi_r)
     p_n = b200.factory(L.backend_t.CUDA, oi_n)
     init_args = lambda f: (f["th"], f["rv"], f["rhod"], None, f.get("Cx"), f.get("Cy"), f.get("Cz"))

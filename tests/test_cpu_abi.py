@@ -29,6 +29,29 @@ def test_engine_abi_exports_every_declared_symbol():
     assert b"sm_100a" in lib.lcx_version()
 
 
+def test_single_precision_engine_exports_the_same_abi_with_suffix():
+    """liblcx_b200_f32.so: every entry point of include/lcx_b200.h under its _f32 name (include/lcx_b200_f32_names.h), and the
+    generated name list is in step with the header"""
+    names = declared_functions(os.path.join(ROOT, "include", "lcx_b200.h"))
+    cdll = C.CDLL(E.LCX_F32_LIB_PATH)
+    missing = [n for n in names if not hasattr(cdll, n + "_f32")]
+    assert not missing, missing
+    listed = re.findall(r"#define (lcx_[A-Za-z0-9_]+) \1_f32", open(os.path.join(ROOT, "include", "lcx_b200_f32_names.h")).read())
+    assert sorted(set(listed) - {"lcx_engine"}) == sorted(set(re.findall(r"\b(lcx_[A-Za-z0-9_]+)\s*\(", re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "lcx_b200.h")).read(), flags=re.S))))
+    assert b"sm_100a" in E.lib("f32").lcx_version()
+    # the two engines must not share C++ symbols (each binds its own: -Bsymbolic + namespaces lcx / lcx_f32)
+    assert not hasattr(cdll, "lcx_create")
+
+
+def test_float_binding_is_exported():
+    """factory<float> through the flat binding: the lgcf_* twins of every lgc_* entry point"""
+    lib = L.b200("f32")
+    names = [n for n in declared_functions(os.path.join(ROOT, "libcloudphxx_b200", "bindings", "lgrngn_capi.h")) if n.startswith("lgc_")]
+    missing = [n for n in names if not hasattr(lib.cdll, "lgcf_" + n[4:])]
+    assert names and not missing, missing
+    assert lib.lib.lgc_impl_name() == b"b200" and lib.dtype == np.float32
+
+
 def test_host_library_exports_binding_and_extras():
     lib = L.b200().lib
     for header in ("libcloudphxx_b200/bindings/lgrngn_capi.h", "libcloudphxx_b200/host/particles_b200.h"):

@@ -589,3 +589,24 @@ def test_port_slabs_full_microphysics_conserves_dry_volume():
         p.step_async()
     fallen = sum(q.puddle["dry_volume"] for q in p.slabs) / (4. / 3. * np.pi)
     assert abs(vol() + fallen - v0) <= 1e-12 * v0
+
+
+def test_reference_float_instantiation_tracks_its_double_one():
+    """the oracle's single-precision arm (factory<float> of the reference build, lgcf_* binding): same case, same seed; the float
+    run's root search stops on a 2^-7 bracket (8 bits), so wet radii agree with the double run to a few per cent, fields to 1e-3"""
+    out = {}
+    for real in ("f64", "f32"):
+        ref = S.oracle_library(real)
+        oi, o, f = S.parcel(ref, n_sd=500)
+        f = {k: np.ascontiguousarray(v, dtype=ref.dtype) for k, v in f.items()}
+        p = ref.factory(L.backend_t.serial, oi)
+        p.init(f["th"], f["rv"], f["rhod"])
+        for _ in range(5):
+            p.step_sync(o, f["th"], f["rv"], f["rhod"])
+            p.step_async(o)
+        out[real] = (p.get_n(), p.get_attr("rw2"), float(f["th"][0]), float(f["rv"][0]))
+        assert out[real][1].dtype == ref.dtype
+    assert out["f32"][0].size == out["f64"][0].size == 500
+    r64, r32 = np.sort(out["f64"][1]), np.sort(out["f32"][1].astype(np.float64))
+    assert np.median(np.abs(r32 - r64) / r64) < 2e-2
+    assert abs(out["f32"][2] - out["f64"][2]) < 1e-3 * out["f64"][2] and abs(out["f32"][3] - out["f64"][3]) < 1e-2 * out["f64"][3]

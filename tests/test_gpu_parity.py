@@ -482,18 +482,21 @@ def test_adaptive_substepping_3d_with_coalescence(ref, b200):
     S.run_pair(ref, b200, setup, 5, on_step=check)
 
 
-def test_float_api_is_served_by_the_double_engine(tmp_path):
+@pytest.mark.parametrize("via_double", [False, True])
+def test_float_api_against_double(tmp_path, via_double):
     """factory<float> (src/lib.cpp:43): a C++ caller in single precision gets the same physics as one in double, to
-    single-precision accuracy of the fields it exchanges (tests/cpp/float_api.cpp, public C++ API only)"""
+    single-precision accuracy of the fields it exchanges (tests/cpp/float_api.cpp, public C++ API only).  Served by the
+    single-precision engine (default) or, with LCX_FLOAT_VIA_DOUBLE=1, by the double-precision engine behind a widening adapter"""
     import os
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = str(tmp_path / "float_api")
     lib = os.path.join(root, "libcloudphxx_b200", "lib")
     subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-I", os.path.join(root, "libcloudphxx_b200", "host", "include"),
-                    os.path.join(root, "tests", "cpp", "float_api.cpp"), "-L", lib, "-llgrngn_b200", "-llcx_b200",
+                    os.path.join(root, "tests", "cpp", "float_api.cpp"), "-L", lib, "-llgrngn_b200", "-llcx_b200", "-llcx_b200_f32",
                     "-Wl,-rpath," + lib, "-o", exe], check=True)
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, LCX_FLOAT_VIA_DOUBLE="1" if via_double else "0")
+    r = subprocess.run([exe] + ([] if via_double else ["native"]), capture_output=True, text=True, timeout=600, env=env)
     print(r.stdout)
     assert r.returncode == 0, r.stdout + r.stderr
 
