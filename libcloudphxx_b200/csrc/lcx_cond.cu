@@ -487,6 +487,9 @@ namespace lcx
     // off by default: measured on the cfg4 slab it raises the active lanes from 20.3 to 25.8 of 32 and executes 12 % fewer warp
     // instructions, but its 29 KB of queues per CTA leave 14 warps per SM instead of 29 and the issue rate drops from 66 % to 42 %:
     // 9.75 ms against 7.12 ms under ncu (profiles/r02_cond_staged_vs_range_ncu.md)
+    // Round 2 also measured a lighter form that parks only the stragglers (droplets needing a fifth evaluation, 13.6 %: 11 doubles
+    // each, one queue, 24-28 warps per SM): 7.3-8.0 ms against 6.7 ms - the generic loop around the one evaluation site costs more
+    // issue slots than the nearly empty fifth pass it removes.  Not kept.
     if (g_staged < 0) { const char *v = std::getenv("LCX_COND_STAGED"); g_staged = (v && v[0] == '1') ? 1 : 0; }
     return g_staged;
   }
@@ -515,7 +518,7 @@ namespace lcx
     const int keep_after = step < sstp - 1;
 
     const int run = e->max_count <= FUSED_MAX ? range_run(e) : 0;
-    if (run > 0 && mode == COND_TOMS748 && cond_staged())
+    if (run > 0 && mode == COND_TOMS748 && cond_staged() == 1)
     {
       const unsigned blocks = div_up(div_up(g.n_cell, run), ST_WARPS);
       lazy_args z = {};

@@ -184,7 +184,8 @@ namespace lcx
     // exclusive scan mv[t] = number of movers before t.
     // Everything below walks the OLD cell segments with 8 lanes per cell (four cells per warp): a lane knows its SD's old cell
     // from the segment it is in, movers are ranked inside the cell with a ballot, and only per-cell counts are scanned.
-    constexpr int MVG = 8;
+    constexpr int MVG = 8;                // lanes per cell of the counting / listing kernels
+    constexpr int MVG_PLACE = 16;         // ... and of k_mv_place_stayers (measured: 16 lanes 0.57 ms, 8 lanes 0.69 ms; the other two lose with 16)
     __device__ __forceinline__ unsigned group_ballot(bool pred)
     { return (__ballot_sync(0xffffffffu, pred) >> ((threadIdx.x & 31) / MVG * MVG)) & ((1u << MVG) - 1u); }
 
@@ -239,18 +240,18 @@ namespace lcx
                                                              const uint32_t *__restrict__ new_off, uint32_t *__restrict__ perm, idx_t *__restrict__ ijk_new,
                                                              const idx_t *__restrict__ sid_old, idx_t *__restrict__ sid_new)
     {
-      const uint32_t c = (blockIdx.x * TPB + threadIdx.x) / MVG;
-      const int l = threadIdx.x % MVG;
+      const uint32_t c = (blockIdx.x * TPB + threadIdx.x) / MVG_PLACE;
+      const int l = threadIdx.x % MVG_PLACE;
       const bool live = c < n_cell;
       const uint32_t b = live ? off[c] : 0u, en = live ? off[c + 1] : 0u;
       uint32_t base = live ? new_off[c] : 0u;
-      const uint32_t rounds = __reduce_max_sync(0xffffffffu, (en - b + MVG - 1) / MVG);
+      const uint32_t rounds = __reduce_max_sync(0xffffffffu, (en - b + MVG_PLACE - 1) / MVG_PLACE);
       // (measured and dropped: issuing four rounds' loads before the first ballot - 0.725 ms against 0.694 ms)
       for (uint32_t r = 0; r < rounds; ++r)
       {
-        const uint32_t t = b + r * MVG + l;
+        const uint32_t t = b + r * MVG_PLACE + l;
         const bool stays = t < en && (key[t] >> class_bits) == c;
-        const unsigned m = group_ballot(stays);
+        const unsigned m = (__ballot_sync(0xffffffffu, stays) >> ((threadIdx.x & 31) / MVG_PLACE * MVG_PLACE)) & ((1u << MVG_PLACE) - 1u);
         if (stays)
         {
           const uint32_t d = base + __popc(m & ((1u << l) - 1u));
@@ -379,7 +380,7 @@ namespace lcx
     exclusive_scan_u32(e, e->cell_off_new.p, size_t(g.n_cell) + 2);
     const idx_t *sid_old = move_sid ? e->S().sid.p : nullptr;
     idx_t *sid_new = move_sid ? e->A().sid.p : nullptr;
-    LCX_LAUNCH(e, k_mv_place_stayers, cell_blocks, TPB, 0, g.n_cell, g.class_bits, e->cell_off.p, e->key[0].p, e->cell_off_new.p,
+    LCX_LAUNCH(e, k_mv_place_stayers, div_up((size_t(g.n_cell) + 1) * MVG_PLACE, TPB), TPB, 0, g.n_cell, g.class_bits, e->cell_off.p, e->key[0].p, e->cell_off_new.p,
                perm_out, e->A().ijk.p, sid_old, sid_new);
     if (n_m)
       LCX_LAUNCH(e, k_mv_place_arrivals, div_up(n_m, TPB), TPB, 0, n_m, g.n_cell, mk[res], mv[res], e->cell_off_new.p, e->arr_off.p,

@@ -38,7 +38,7 @@ def lib(real="f64"):
 
 
 def _bind(l):
-    if True:
+    if l is not None:
         l.lcx_last_error.restype = C.c_char_p
         l.lcx_version.restype = C.c_char_p
         l.lcx_timer_start.argtypes = [C.c_void_p]

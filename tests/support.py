@@ -318,12 +318,16 @@ def cond_substepping_scenario(lib, backend, RH_formula, sstp_cond, constp, step_
     return res
 
 
-COND_SUBSTEPPING_TOL = {     # tests/python/physics/lgrngn_cond_substepping_test.py:79-91; th_diff (a ~5e-3 K "leak" built from
-    # differences of 300 K numbers) is widened from 1e-5 to 2e-5: the fixture came from an -Ofast build of the reference, the
-    # oracle is built with IEEE -O2, and the sstp_cond = 32 row differs by 1.3e-5 between the two builds of the SAME code
-    "ss": ("rtol", 1.5e-2), "th_diff": ("atol", 2e-5), "rv_diff": ("atol", 1e-6), "act": ("rtol", 1.5e-2), "mr": ("rtol", 1.5e-2),
+COND_SUBSTEPPING_TOL = {     # tests/python/physics/lgrngn_cond_substepping_test.py:79-91, the reference's own tolerances
+    "ss": ("rtol", 1.5e-2), "th_diff": ("atol", 1e-5), "rv_diff": ("atol", 1e-6), "act": ("rtol", 1.5e-2), "mr": ("rtol", 1.5e-2),
     "sr": ("rtol", 1.5e-2), "tr": ("rtol", 1.5e-2), "act_post_evap": ("rtol", 1.5e-2), "gccn_post_evap": ("rtol", 1.5e-2),
     "th_post_cond": ("rtol", 1e-4), "rv_post_cond": ("rtol", 1e-3)}
+# One exception, measured rather than assumed (tests/test_cpu_oracle.py::test_th_diff_of_the_sstp32_rows_depends_on_the_build_flags):
+# th_diff is a ~5e-3 K "leak" built from differences of 300 K numbers, and the fixture was made with the reference's -Ofast release
+# flags.  The -Ofast build of oracle/_ref reproduces every row's th_diff to 3e-7; the IEEE-strict -O2 build (what parity is checked
+# against) differs from the fixture by 1.0e-5 .. 1.3e-5 on the rows with sstp_cond = 32 without const_p, by < 2.6e-6 on all others
+# (all 280 rows measured).  Those rows - and only those - get 2e-5.
+TH_DIFF_ATOL_SSTP32 = 2e-5
 
 
 def load_cond_substepping_rows(which="percell"):
@@ -336,6 +340,8 @@ def load_cond_substepping_rows(which="percell"):
 def check_cond_substepping(res, row):
     bad = []
     for key, (kind, tol) in COND_SUBSTEPPING_TOL.items():
+        if key == "th_diff" and int(row["sstp_cond"]) == 32 and row["constp"] == "False":
+            tol = TH_DIFF_ATOL_SSTP32
         ref, got = float(row[key]), res[key]
         ok = abs(got - ref) <= (tol if kind == "atol" else tol * abs(ref))
         if not ok:

@@ -56,6 +56,26 @@ def test_reference_build_reproduces_cond_fixture_const_p(ref):
     assert not S.check_cond_substepping(res, rows[0]), S.check_cond_substepping(res, rows[0])
 
 
+def test_th_diff_of_the_sstp32_rows_depends_on_the_build_flags(ref):
+    """why tests/support.py allows 2e-5 on th_diff for the sstp_cond = 32 rows: the reference's fixture was produced with its -Ofast
+    release flags; the same sources built that way (oracle/_ref/liblgrngn_ref_fast.so) reproduce the row to 1e-6, the IEEE-strict
+    -O2 build used for parity lands 1.0e-5 .. 1.5e-5 away - a property of the build flags, not of the restated algorithm"""
+    fast_path = os.path.join(ROOT, "oracle", "_ref", "liblgrngn_ref_fast.so")
+    if not os.path.exists(fast_path):
+        pytest.skip("the -Ofast build of the reference is not present")
+    fast = L.Library(fast_path)
+    row = [r for r in S.load_cond_substepping_rows() if r["constp"] == "False" and r["RH_formula"] == "pv_cc" and int(r["sstp_cond"]) == 32][0]
+    want = float(row["th_diff"])
+    got_fast = S.cond_substepping_scenario(fast, L.backend_t.OpenMP, L.RH_formula_t.pv_cc, 32, False)["th_diff"]
+    got_strict = S.cond_substepping_scenario(ref, L.backend_t.OpenMP, L.RH_formula_t.pv_cc, 32, False)["th_diff"]
+    assert abs(got_fast - want) < 1e-6, (got_fast, want)
+    assert 5e-6 < abs(got_strict - want) < S.TH_DIFF_ATOL_SSTP32, (got_strict, want)
+    # and a row with fewer sub-steps holds the reference's own 1e-5 on the strict build with room to spare
+    row8 = [r for r in S.load_cond_substepping_rows() if r["constp"] == "False" and r["RH_formula"] == "pv_cc" and int(r["sstp_cond"]) == 8][0]
+    got8 = S.cond_substepping_scenario(ref, L.backend_t.OpenMP, L.RH_formula_t.pv_cc, 8, False)["th_diff"]
+    assert abs(got8 - float(row8["th_diff"])) < 5e-6
+
+
 def test_reference_build_reproduces_bott_spectrum(ref):
     bott = np.load(os.path.join(ROOT, "tests", "golden", "bott1800.npy"))
     oi, o, f = S.hall_davis_box(ref, L.vt_t.beard77fast)

@@ -102,3 +102,34 @@ def test_f32_diagnostics(ref32, b200_32):
             getattr(p, mom[0])(*mom[1:])
             out.append(p.outbuf().astype(np.float64).sum())
         assert abs(out[0] - out[1]) <= bar * abs(out[0]), (sel, mom, out)
+
+
+def test_f32_multi_cuda_roundtrip_on_one_device(b200_32, monkeypatch):
+    """the single-precision engine behind factory<float>(multi_CUDA): three unequal x-slabs (folded onto one GPU), migration through
+    the float inboxes; advecting once round the periodic domain rolls every per-cell statistic exactly and returns it unchanged"""
+    monkeypatch.setenv("LCX_SLABS_ON_ONE_DEVICE", "1")
+    nx = 7
+    oi, o, f = S.box_3d(b200_32, nx=nx, ny=3, nz=4, sd_conc=16, rain_mode=True)
+    oi.dev_count = 3
+    oi.n_sd_max = int(oi.n_sd_max * 2)
+    f = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in f.items()}
+    f["Cx"][:] = 1.0
+    f["Cy"][:] = 0.0
+    o.cond = o.coal = o.sedi = 0
+    p = b200_32.factory(L.backend_t.multi_CUDA, oi)
+    p.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
+
+    def per_cell():
+        out = []
+        for mom in (p.diag_sd_conc, lambda: p.diag_dry_mom(1), lambda: p.diag_kappa_mom(1)):
+            p.diag_all(); mom(); out.append(p.outbuf().reshape(nx, 3, 4).copy())
+        return out
+    before = per_cell()
+    assert before[0].sum() == nx * 3 * 4 * 16
+    for step in range(nx):
+        p.step_sync(o, f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"])
+        p.step_async(o)
+        for a, b in zip(before, per_cell()):
+            assert np.array_equal(np.roll(a, step + 1, axis=0), b), step
+    for a, b in zip(before, per_cell()):
+        assert np.array_equal(a, b)

@@ -18,7 +18,7 @@ run() {  # name, extra args...
   echo "$name n=$N rc=$? $(tail -c 300 $OUT/r02_scale_${name}_n$N.err | tr '\n' ' ' | cut -c1-200)"
 }
 run cfg4_weak
-if [ "$N" != "1" ]; then
+if [ "$N" != "1" ] && [ -z "$SKIP_MULTICUDA" ]; then
   python bench.py --gpus $N --steps $STEPS --warmup $WARM --no-cpu-baseline --no-alt > $OUT/r02_scale_cfg4_weak_multicuda_n$N.json 2> $OUT/r02_scale_cfg4_weak_multicuda_n$N.err
   echo "cfg4_weak_multicuda n=$N rc=$?"
 fi
