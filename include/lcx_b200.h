@@ -130,6 +130,13 @@ int  lcx_cells_set_part(lcx_engine *e, int field, int64_t offset, const void *sr
 int  lcx_cells_get_part(lcx_engine *e, int field, int64_t offset, void *dst, int64_t count);
 /* Both take HOST or DEVICE memory on the caller's side (unified addressing tells them apart): a host model whose Eulerian   */
 /* fields already live on the GPU passes device pointers through arrinfo_t and no PCIe traffic happens.                       */
+/* Chunked step_sync: while a cell window [c_begin, c_end) is set, lcx_hskpng_Tpr and lcx_cond (run-per-warp kernel only) work on */
+/* those cells alone, and lcx_cells_get_part read-backs do not hold up the next chunk's kernels.  The host layer uploads chunk    */
+/* k + 1 and reads chunk k back while chunk k + 1 computes: the copies of step_sync hide behind the condensation kernel.          */
+/* Windows must start at multiples of lcx_cond_granule() cells (0: the kernel in use cannot be windowed), arrive in order, cover   */
+/* the grid, and be cleared with (0, 0).  Results are bit-identical to the un-chunked step.                                       */
+int  lcx_set_cell_window(lcx_engine *e, int64_t c_begin, int64_t c_end);
+int  lcx_cond_granule(lcx_engine *e, int64_t *cells);
 int  lcx_pointer_on_device(const void *p, int *on_device);      /* 1: device (or managed) memory, 0: host memory           */
 int  lcx_copy_to_host(void *dst_host, const void *src_any, size_t bytes);   /* blocking; used by init() for device-resident fields */
 int  lcx_host_alloc(size_t bytes, void **out);                  /* page-locked staging memory for the host layer          */

@@ -34,6 +34,14 @@ namespace
       LCX_CUDA(cudaStreamWaitEvent(e->stream, e->scalars_ready, 0));
       e->scalars_pending = false;
     }
+    // read-backs queued on the third stream: whatever comes next may overwrite what they read - except inside a chunked step,
+    // where the next chunk's kernels touch other cells only (the batch ends with lcx_sync)
+    if (e->d2h_open && e->win_end == 0)
+    {
+      LCX_CUDA(cudaEventRecord(e->d2h_mark, e->d2h_stream));
+      LCX_CUDA(cudaStreamWaitEvent(e->stream, e->d2h_mark, 0));
+      e->d2h_open = false;
+    }
     e->tail_is_gather = false;
   }
 
@@ -114,6 +122,10 @@ lcx_engine::~lcx_engine()
   if (courant_ready) cudaEventDestroy(courant_ready);
   if (main_mark) cudaEventDestroy(main_mark);
   if (copy_stream) cudaStreamDestroy(copy_stream);
+  if (d2h_stream) cudaStreamDestroy(d2h_stream);
+  if (win_stream) { if (stream == win_stream) stream = win_home; cudaStreamDestroy(win_stream); }
+  if (win_join) cudaEventDestroy(win_join);
+  if (d2h_mark) cudaEventDestroy(d2h_mark);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -156,6 +168,10 @@ int lcx_create(const lcx_config *cfg, lcx_engine **out)
     LCX_CUDA(cudaSetDevice(dev));
     LCX_CUDA(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     LCX_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    LCX_CUDA(cudaStreamCreateWithFlags(&e->d2h_stream, cudaStreamNonBlocking));
+    LCX_CUDA(cudaStreamCreateWithFlags(&e->win_stream, cudaStreamNonBlocking));
+    LCX_CUDA(cudaEventCreateWithFlags(&e->win_join, cudaEventDisableTiming));
+    LCX_CUDA(cudaEventCreateWithFlags(&e->d2h_mark, cudaEventDisableTiming));
     LCX_CUDA(cudaEventCreateWithFlags(&e->courant_ready, cudaEventDisableTiming));
     LCX_CUDA(cudaEventCreateWithFlags(&e->main_mark, cudaEventDisableTiming));
     LCX_CUDA(cudaEventCreateWithFlags(&e->scalars_ready, cudaEventDisableTiming));
@@ -267,8 +283,51 @@ int lcx_sync(lcx_engine *e)
     LCX_CUDA(cudaStreamSynchronize(e->stream));
     if (e->upload_batch_open) LCX_CUDA(cudaStreamSynchronize(e->copy_stream));   // the data stay "pending" for the engine's stream
     e->upload_batch_open = false;
+    if (e->d2h_open) LCX_CUDA(cudaStreamSynchronize(e->d2h_stream));
+    e->d2h_open = false;
   });
 }
+
+int lcx_set_cell_window(lcx_engine *e, int64_t c_begin, int64_t c_end)
+{
+  return guarded([&] {
+    LCX_CUDA(cudaSetDevice(e->device));
+    if (c_begin == 0 && c_end == 0)
+    {
+      if (e->win_end == 0) return;
+      // back to the engine's own stream, behind the chunks that ran on the second one
+      if (e->stream == e->win_stream)
+      {
+        LCX_CUDA(cudaEventRecord(e->win_join, e->win_stream));
+        e->stream = e->win_home;
+        LCX_CUDA(cudaStreamWaitEvent(e->stream, e->win_join, 0));
+      }
+      else if (e->win_count > 1)
+      {
+        LCX_CUDA(cudaEventRecord(e->win_join, e->win_stream));
+        LCX_CUDA(cudaStreamWaitEvent(e->stream, e->win_join, 0));
+      }
+      e->win_begin = e->win_end = 0;
+      e->win_count = 0;
+      return;
+    }
+    if (c_begin < 0 || c_end <= c_begin || c_end > int64_t(e->grid.n_cell)) throw lcx::error("lcx_set_cell_window: bad range");
+    // Consecutive chunks alternate between two streams: they work on disjoint cells and SDs, so chunk k + 1 (as soon as its
+    // fields have arrived) fills the SMs that chunk k's last wave of CTAs leaves idle instead of waiting for the kernel to end
+    if (e->win_end == 0)
+    {
+      e->win_home = e->stream;
+      LCX_CUDA(cudaEventRecord(e->win_join, e->stream));           // fork: the second stream starts behind what is queued so far
+      LCX_CUDA(cudaStreamWaitEvent(e->win_stream, e->win_join, 0));
+      e->win_count = 0;
+    }
+    e->stream = (e->win_count & 1) ? e->win_stream : e->win_home;
+    ++e->win_count;
+    e->win_begin = lcx::idx_t(c_begin); e->win_end = lcx::idx_t(c_end);
+  });
+}
+
+int lcx_cond_granule(lcx_engine *e, int64_t *cells) { return guarded([&] { *cells = lcx::cond_granule(e); }); }
 
 void *lcx_stream(lcx_engine *e) { return e->stream; }
 
@@ -329,7 +388,12 @@ int lcx_cells_get_part(lcx_engine *e, int field, int64_t offset, void *dst, int6
     use_device(e, true, 3u);
     const field_ref f = field_of(e, field);
     if (offset < 0 || count < 0 || size_t(offset + count) > f.n) throw lcx::error("lcx_cells_get_part: range outside field " + std::to_string(field));
-    LCX_CUDA(cudaMemcpyAsync(dst, static_cast<const lcx::real_t *>(f.p) + offset, size_t(count) * sizeof(lcx::real_t), cudaMemcpyDefault, e->stream));
+    // on a third stream, behind what is queued on the engine's stream so far: in a chunked step the next chunk's kernels need not
+    // wait for this chunk's read-back (lcx_sync ends the batch)
+    LCX_CUDA(cudaEventRecord(e->main_mark, e->stream));
+    LCX_CUDA(cudaStreamWaitEvent(e->d2h_stream, e->main_mark, 0));
+    LCX_CUDA(cudaMemcpyAsync(dst, static_cast<const lcx::real_t *>(f.p) + offset, size_t(count) * sizeof(lcx::real_t), cudaMemcpyDefault, e->d2h_stream));
+    e->d2h_open = true;
   });
 }
 

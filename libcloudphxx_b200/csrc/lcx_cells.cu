@@ -10,13 +10,13 @@ namespace lcx
     constexpr int TPB = 256;
 
     // T, p, RH, eta (and dv = 1/rhod for a parcel): hskpng_Tpr.ipp:219-305
-    __global__ void __launch_bounds__(TPB) k_cells_Tpr(idx_t n_cell, int n_dims, int th_dry, int const_p, int RH_formula,
+    __global__ void __launch_bounds__(TPB) k_cells_Tpr(idx_t c_begin, idx_t n_cell, int n_dims, int th_dry, int const_p, int RH_formula,
                                                       const real_t *__restrict__ th, const real_t *__restrict__ rv,
                                                       const real_t *__restrict__ rhod, real_t *__restrict__ p,
                                                       real_t *__restrict__ T, real_t *__restrict__ RH, real_t *__restrict__ eta,
                                                       real_t *__restrict__ dv)
     {
-      const idx_t c = blockIdx.x * TPB + threadIdx.x;
+      const idx_t c = c_begin + blockIdx.x * TPB + threadIdx.x;      // cells [c_begin, n_cell): the whole grid or one chunk of it
       if (c >= n_cell) return;
       const real_t th_c = th[c], rv_c = rv[c], rhod_c = rhod[c];
       real_t T_c, p_c;
@@ -113,7 +113,8 @@ namespace lcx
   void hskpng_Tpr(lcx_engine *e)
   {
     const grid_t &g = e->grid;
-    LCX_LAUNCH(e, k_cells_Tpr, div_up(g.n_cell, TPB), TPB, 0, g.n_cell, g.n_dims, e->cfg.th_dry, e->cfg.const_p, e->cfg.RH_formula,
+    const idx_t c_begin = e->win_end ? e->win_begin : 0, c_end = e->win_end ? e->win_end : g.n_cell;
+    LCX_LAUNCH(e, k_cells_Tpr, div_up(c_end - c_begin, TPB), TPB, 0, c_begin, c_end, g.n_dims, e->cfg.th_dry, e->cfg.const_p, e->cfg.RH_formula,
                e->th.p, e->rv.p, e->rhod.p, e->p.p, e->T.p, e->RH.p, e->eta.p, e->dv.p);
   }
 

@@ -146,7 +146,7 @@ namespace lcx
     // 4 KB per warp limit the run to 8 cells (7.2-7.5 ms against 7.0-7.2 ms per launch for runs of 16).
     constexpr int RANGE_MAX = 16;
     template <int MODE, bool LAZY>
-    __global__ void __launch_bounds__(TPB, LCX_COND_MINB) k_cond_range(idx_t n_cell, int run, const uint32_t *__restrict__ off, real_t dt, real_t RH_max, cond_args a,
+    __global__ void __launch_bounds__(TPB, LCX_COND_MINB) k_cond_range(idx_t c_begin, idx_t n_cell, int run, const uint32_t *__restrict__ off, real_t dt, real_t RH_max, cond_args a,
                                                        int n_dims, const real_t *__restrict__ dv, int first_step, int keep_after,
                                                        real_t *__restrict__ rw_mom3, real_t *__restrict__ drw_mom3,
                                                        real_t *__restrict__ th, real_t *__restrict__ rv, lazy_args z)
@@ -155,7 +155,8 @@ namespace lcx
       __shared__ cond_cell_consts<real_t> s_k[WARPS][RANGE_MAX];
       __shared__ real_t s_m[WARPS][RANGE_MAX][2];
       const int w = threadIdx.x / 32, l = threadIdx.x % 32;
-      const size_t c0_ = (size_t(blockIdx.x) * WARPS + w) * size_t(run);
+      // cells [c_begin, n_cell): the whole grid, or one chunk of it whose first cell is a multiple of `run` (same runs either way)
+      const size_t c0_ = size_t(c_begin) + (size_t(blockIdx.x) * WARPS + w) * size_t(run);
       if (c0_ >= n_cell) return;                      // whole warps leave; nothing below synchronises across warps
       const idx_t c0 = idx_t(c0_);
       const int nc = int(n_cell - c0 < idx_t(run) ? n_cell - c0 : idx_t(run));
@@ -482,6 +483,15 @@ namespace lcx
     return int(run);
   }
 
+  // cells per CTA of the run-per-warp kernel if the next lcx_cond would take it (and not its staged form), else 0: chunks of a
+  // windowed step must start at multiples of it
+  int cond_granule(lcx_engine *e)
+  {
+    if (cond_staged() && cond_solver() == COND_TOMS748) return 0;
+    const int run = e->max_count <= FUSED_MAX ? range_run(e) : 0;
+    return run > 0 ? run * (TPB / 32) : 0;
+  }
+
   int cond_staged()
   {
     // off by default: measured on the cfg4 slab it raises the active lanes from 20.3 to 25.8 of 32 and executes 12 % fewer warp
@@ -518,7 +528,7 @@ namespace lcx
     const int keep_after = step < sstp - 1;
 
     const int run = e->max_count <= FUSED_MAX ? range_run(e) : 0;
-    if (run > 0 && mode == COND_TOMS748 && cond_staged() == 1)
+    if (run > 0 && mode == COND_TOMS748 && cond_staged() == 1 && e->win_end == 0)
     {
       const unsigned blocks = div_up(div_up(g.n_cell, run), ST_WARPS);
       lazy_args z = {};
@@ -535,23 +545,29 @@ namespace lcx
                  int(step == 0), keep_after, e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p, z);
       return;
     }
+    const bool windowed = e->win_end != 0;
     if (run > 0)
     {
-      const unsigned blocks = div_up(div_up(g.n_cell, run), TPB / 32);
+      // chunked step_sync: only the window's cells; the chunks arrive in order and the last one (ending at n_cell) closes a
+      // pending gather-on-read re-layout
+      const idx_t c_begin = windowed ? e->win_begin : 0, c_end = windowed ? e->win_end : g.n_cell;
+      if (windowed && (c_begin % idx_t(run) != 0 || c_end <= c_begin || c_end > g.n_cell)) throw error("lcx_cond: cell window not aligned to the kernel's runs");
+      const unsigned blocks = div_up(div_up(c_end - c_begin, run), TPB / 32);
       lazy_args z = {};
       if (e->pending & lcx_engine::PENDING_ATTR)      // consume the pending re-layout: read through the permutation from the old buffer set, write everything into the new one
       {
         sd_arrays &o = e->A();
         z = {e->pending_perm.p, o.rw2.p, o.rd3.p, o.kpa.p, o.vt.p, o.n.p, s.rd3.p, s.kpa.p, s.vt.p, s.n.p};
-        e->pending &= ~unsigned(lcx_engine::PENDING_ATTR);
-        LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_cond_range<M, true>), blocks, TPB, 0, g.n_cell, run, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p,
+        if (c_end == g.n_cell) e->pending &= ~unsigned(lcx_engine::PENDING_ATTR);
+        LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_cond_range<M, true>), blocks, TPB, 0, c_begin, c_end, run, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p,
                                           int(step == 0), keep_after, e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p, z));
         return;
       }
-      LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_cond_range<M, false>), blocks, TPB, 0, g.n_cell, run, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p,
+      LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_cond_range<M, false>), blocks, TPB, 0, c_begin, c_end, run, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p,
                                         int(step == 0), keep_after, e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p, z));
       return;
     }
+    if (windowed) throw error("lcx_cond: a cell window needs the run-per-warp kernel (lcx_cond_granule says when)");
     finish_pending(e, lcx_engine::PENDING_ATTR);      // the other condensation kernels work on the current layout only
     if (e->max_count <= FUSED_MAX)
     {

@@ -133,6 +133,16 @@ struct lcx_engine
   // copy stream has to wait for); every entry point that consumes cell fields first orders itself after scalars_ready
   cudaEvent_t scalars_ready = nullptr, pre_gather = nullptr;
   bool scalars_pending = false, upload_batch_open = false, tail_is_gather = false;
+  // Chunked step_sync (lcx_set_cell_window): the host layer uploads th / rv / rhod of one x-chunk, runs hskpng_Tpr and the
+  // condensation kernel on that chunk's cells only, and reads th / rv of the chunk back on a third stream while the next chunk
+  // computes - the host<->device copies of step_sync then hide behind the condensation kernel instead of bracketing it
+  lcx::idx_t win_begin = 0, win_end = 0;          // [begin, end) in cells; 0, 0 = the whole grid
+  cudaStream_t d2h_stream = nullptr;
+  cudaStream_t win_stream = nullptr, win_home = nullptr;   // odd chunks run on win_stream (`stream` points at it meanwhile), win_home keeps the engine's own
+  cudaEvent_t win_join = nullptr;
+  int win_count = 0;
+  cudaEvent_t d2h_mark = nullptr;
+  bool d2h_open = false;
   uint64_t launches = 0;
 
   size_t cap = 0;                // n_sd_max
@@ -263,6 +273,7 @@ namespace lcx
   int cond_staged();                      // lcx_set_cond_staged, else $LCX_COND_STAGED, else on: the phase-grouped variant of the range kernel
   void set_cond_staged(int on);
   void cond(lcx_engine *e, real_t dt_sub, real_t RH_max, int step, int sstp);
+  int cond_granule(lcx_engine *e);       // cells per CTA of the run-per-warp condensation kernel, 0 if it would not be chosen
   void cond_perparticle(lcx_engine *e, real_t dt, real_t RH_max, int sstp, bool mix);
   void cond_perparticle_adaptive(lcx_engine *e, real_t dt, real_t RH_max, int sstp_max, int sstp_act, real_t drw2_eps, real_t drw2_max);
   void hskpng_rc2(lcx_engine *e);

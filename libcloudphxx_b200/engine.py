@@ -70,10 +70,11 @@ def get_cond_solver():
     return [k for k, v in COND_SOLVERS.items() if v == mode][0]
 
 
-def set_cond_layout(cells_per_warp):
-    """work distribution of the fused per-cell condensation kernel, process-wide: 0 automatic (default), -1 eight lanes per
-    cell, k in 1..16 a warp per run of k consecutive cells; see include/lcx_b200.h lcx_set_cond_layout"""
-    lib().lcx_set_cond_layout(int(cells_per_warp))
+def set_cond_layout(cells_per_warp, real="f64"):
+    """work distribution of the fused per-cell condensation kernel, process-wide (per engine library: real = "f32" addresses the
+    single-precision one): 0 automatic (default), -1 eight lanes per cell, k in 1..16 a warp per run of k consecutive cells;
+    see include/lcx_b200.h lcx_set_cond_layout"""
+    lib(real).lcx_set_cond_layout(int(cells_per_warp))
 
 
 def get_cond_layout():

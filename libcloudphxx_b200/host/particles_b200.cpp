@@ -934,9 +934,9 @@ namespace libcloudphxx
 
         // defer_wait: the caller (step_sync) runs step_cond right away and waits for the uploads at its end, so the Courant
         // fields - needed only by step_async - travel while the condensation kernel runs
-        void sync_in(arrinfo_t<real_t> &th, arrinfo_t<real_t> &rv, const arrinfo_t<real_t> &rhod, const arrinfo_t<real_t> &cx,
-                     const arrinfo_t<real_t> &cy, const arrinfo_t<real_t> &cz, const arrinfo_t<real_t> &diss_rate, size_t n_ambient_chem,
-                     bool defer_wait = false)
+        // argument and call-order checks of sync_in (particles_step.ipp:32-110), the Courant maps, the Euler fall-back of pred_corr
+        bool sync_in_checks(arrinfo_t<real_t> &th, arrinfo_t<real_t> &rv, const arrinfo_t<real_t> &rhod, const arrinfo_t<real_t> &cx,
+                            const arrinfo_t<real_t> &cy, const arrinfo_t<real_t> &cz, const arrinfo_t<real_t> &diss_rate, size_t n_ambient_chem)
         {
           if (!init_called) throw std::runtime_error("libcloudph++: please call init() before calling step_sync()");
           if (should_now_run_async) throw std::runtime_error("libcloudph++: please call step_async() before calling step_sync() again");
@@ -946,6 +946,24 @@ namespace libcloudphxx
           if (!diss_rate.is_null())
             throw std::runtime_error("libcloudph++: turbulent advection, coalescence and condesation are switched off and diss_rate is not empty");
           if (m_cx.l2e.empty()) init_courant_maps(cx, cy, cz);
+          // |C_x| > 2 would leave the 2-cell halo of the predictor-corrector scheme: fall back to Euler for this step
+          if (oi.adve_scheme == as_t::pred_corr && !cx.is_null())
+          {
+            real_t cmin = std::numeric_limits<real_t>::max(), cmax = -cmin;
+            const host_view h_cx(cx, m_cx);
+            for (const long l : m_cx.l2e) { cmin = std::min(cmin, h_cx.data[l]); cmax = std::max(cmax, h_cx.data[l]); }
+            if (!(cmin >= real_t(-2.)) || !(cmax <= real_t(2.))) adve_scheme = as_t::euler;
+          }
+          return true;
+        }
+
+        // defer_wait: the caller (step_sync) runs step_cond right away and waits for the uploads at its end, so the Courant
+        // fields - needed only by step_async - travel while the condensation kernel runs
+        void sync_in(arrinfo_t<real_t> &th, arrinfo_t<real_t> &rv, const arrinfo_t<real_t> &rhod, const arrinfo_t<real_t> &cx,
+                     const arrinfo_t<real_t> &cy, const arrinfo_t<real_t> &cz, const arrinfo_t<real_t> &diss_rate, size_t n_ambient_chem,
+                     bool defer_wait = false, bool checked = false)
+        {
+          if (!checked) sync_in_checks(th, rv, rhod, cx, cy, cz, diss_rate, n_ambient_chem);
           var_rho = !rhod.is_null();
           sync_in_field(th, m_th, LCX_F_TH);
           sync_in_field(rv, m_rv, LCX_F_RV);
@@ -955,15 +973,77 @@ namespace libcloudphxx
           sync_in_field(cz, m_cz, LCX_F_COURANT_Z);
           transfers_open = defer_wait;
           if (!defer_wait) finish_transfers();          // the caller may overwrite its arrays as soon as this returns
-          // |C_x| > 2 would leave the 2-cell halo of the predictor-corrector scheme: fall back to Euler for this step
-          if (oi.adve_scheme == as_t::pred_corr && !cx.is_null())
-          {
-            real_t cmin = std::numeric_limits<real_t>::max(), cmax = -cmin;
-            const host_view h_cx(cx, m_cx);
-            for (const long l : m_cx.l2e) { cmin = std::min(cmin, h_cx.data[l]); cmax = std::max(cmax, h_cx.data[l]); }
-            if (!(cmin >= real_t(-2.)) || !(cmax <= real_t(2.))) adve_scheme = as_t::euler;
-          }
           should_now_run_cond = true;
+        }
+
+        // ---- chunked step_sync ------------------------------------------------------------------------------------------
+        // Condensation is cell-local, so step_sync need not be upload -> compute -> read back: the grid is cut into chunks of
+        // whole kernel runs, chunk k + 1 travels to the device and chunk k's th / rv travel back while a chunk computes
+        // (lcx_set_cell_window).  Same kernels on the same cells in the same order inside each run: bit-identical results.
+        // Chosen by step_sync when the per-cell path with one sub-step runs on contiguous host arrays.
+        // read at every call (two getenv per step) so that tests can switch it inside one process
+        static long env_long(const char *name, long dflt) { const char *s = std::getenv(name); return s && *s ? std::atol(s) : dflt; }
+        // piece [c0, c1) of a field's runs
+        template <class F> static void for_run_pieces(const map_t &m, long c0, long c1, F f)
+        {
+          for (const run_t &r : m.runs)
+          {
+            const long lo = std::max(c0, r.dst), hi = std::min(c1, r.dst + r.len);
+            if (lo < hi) f(lo, r.src + (lo - r.dst), hi - lo);
+          }
+        }
+        bool step_sync_chunked(const opts_t<real_t> &opts, arrinfo_t<real_t> &th, arrinfo_t<real_t> &rv, const arrinfo_t<real_t> &rhod,
+                               const arrinfo_t<real_t> &cx, const arrinfo_t<real_t> &cy, const arrinfo_t<real_t> &cz)
+        {
+          const long K = env_long("LCX_SYNC_CHUNKS", 8);
+          if (K < 2 || !opts.cond || opts.turb_cond || oi.exact_sstp_cond || allow_sstp_cond || oi.const_p) return false;
+          if (opts.chem_dsl || opts.chem_dsc || opts.chem_rct || long(n_cell) < env_long("LCX_SYNC_CHUNK_MIN_CELLS", 1l << 16)) return false;
+          if (opts.dt > 0 || th.is_null() || rv.is_null() || !m_th.direct() || !m_rv.direct() || (!rhod.is_null() && !m_rhod.direct())) return false;
+          if (on_device(th.data) || on_device(rv.data)) return false;      // device-resident fields: nothing to hide
+          int64_t granule = 0;
+          chk(L::cond_granule(e, &granule));
+          if (granule <= 0) return false;
+          long chunk = long((n_cell + size_t(K) - 1) / size_t(K));
+          chunk = (chunk + granule - 1) / granule * granule;
+          if (size_t(chunk) >= n_cell) return false;
+
+          // what sync_in does, except that th / rv / rhod go chunk by chunk and the Courant fields last
+          var_rho = !rhod.is_null();
+          should_now_run_cond = false;
+          adjust_timesteps(opts.dt);
+          auto upload = [&](long c0, long c1) {
+            for_run_pieces(m_th, c0, c1, [&](long dst, long src, long len) { chk(L::cells_set_part(e, LCX_F_TH, dst, th.data + src, len)); });
+            for_run_pieces(m_rv, c0, c1, [&](long dst, long src, long len) { chk(L::cells_set_part(e, LCX_F_RV, dst, rv.data + src, len)); });
+            if (var_rho) for_run_pieces(m_rhod, c0, c1, [&](long dst, long src, long len) { chk(L::cells_set_part(e, LCX_F_RHOD, dst, rhod.data + src, len)); });
+          };
+          const long n = long(n_cell);
+          upload(0, std::min(chunk, n));     // before anything is queued on the engine's stream: this one overlaps the previous step's re-layout
+          chk(L::hskpng_mfp(e));             // from the T, p left by the previous Tpr (particles_step.ipp:189-194)
+          try
+          {
+            for (long c0 = 0; c0 < n; c0 += chunk)
+            {
+              const long c1 = std::min(c0 + chunk, n);
+              chk(L::set_cell_window(e, c0, c1));
+              chk(L::hskpng_Tpr(e));
+              chk(L::cond(e, dt, opts.RH_max, 0, 1));
+              if (c1 < n) upload(c1, std::min(c1 + chunk, n));
+              else
+              {
+                sync_in_field(cx, m_cx, LCX_F_COURANT_X);
+                sync_in_field(cy, m_cy, LCX_F_COURANT_Y);
+                sync_in_field(cz, m_cz, LCX_F_COURANT_Z);
+              }
+              for_run_pieces(m_th, c0, c1, [&](long cell, long host, long len) { chk(L::cells_get_part(e, LCX_F_TH, cell, th.data + host, len)); });
+              for_run_pieces(m_rv, c0, c1, [&](long cell, long host, long len) { chk(L::cells_get_part(e, LCX_F_RV, cell, rv.data + host, len)); });
+            }
+          }
+          catch (...) { L::set_cell_window(e, 0, 0); throw; }
+          chk(L::set_cell_window(e, 0, 0));
+          finish_transfers();
+          transfers_open = false;
+          should_now_run_async = true;
+          return true;
         }
 
         // device-resident variant of sync_in + step_cond: the fields of the previous step stay where they are
@@ -1290,8 +1370,9 @@ namespace libcloudphxx
         {
           const size_t n_chem = ambient_chem.size();
           for_slabs([&](slab<real_t> &s) {
-            s.sync_in(th, rv, rhod, cx, cy, cz, diss_rate, n_chem, /*defer_wait=*/true);
             arrinfo_t<real_t> th_ = th, rv_ = rv;
+            if (s.sync_in_checks(th_, rv_, rhod, cx, cy, cz, diss_rate, n_chem) && s.step_sync_chunked(opts, th_, rv_, rhod, cx, cy, cz)) return;
+            s.sync_in(th_, rv_, rhod, cx, cy, cz, diss_rate, n_chem, /*defer_wait=*/true, /*checked=*/true);
             s.step_cond(opts, th_, rv_);
           });
         }
