@@ -228,6 +228,13 @@ int  lcx_migr_ipc_connect(lcx_engine *e, int side, const void *blob);    /* e's 
 int  lcx_migr_put(lcx_engine *e, int64_t *n_lft, int64_t *n_rgt);
 int  lcx_migr_take(lcx_engine *e, lcx_engine *rgt_neighbour, lcx_engine *lft_neighbour, int64_t *n_from_rgt, int64_t *n_from_lft);
 int  lcx_migr_real_attrs(lcx_engine *e, int *count);                      /* number of real attributes sent  */
+/* Courant halo of predictor-corrector advection between process-distributed slabs (replaces xchng_courants,                   */
+/* src/impl/distributed_memory/particles_impl_xchng_courants.ipp:15-153: MPI_Isend / MPI_Recv of halo_size x-planes of Cx, Cy, */
+/* Cz per side): lcx_halo_put copies this slab's outermost interior planes straight into the neighbours' inboxes (peer memory)  */
+/* and publishes them; lcx_halo_take waits on the device for both neighbours' planes and copies them into this slab's halo.     */
+/* Call both, in this order, on every rank, after the Courant fields of the step were set and before lcx_transport.            */
+int  lcx_halo_put(lcx_engine *e);
+int  lcx_halo_take(lcx_engine *e);
 
 /* ---- end of step: removal / recycling, cell index, per-cell grouping ------------------------------------ */
 /* keep_all != 0: initial grouping - nothing is removed and the cell indices given to lcx_sd_append are used */

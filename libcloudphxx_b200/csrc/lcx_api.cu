@@ -255,7 +255,7 @@ int lcx_create(const lcx_config *cfg, lcx_engine **out)
       for (int s = 0; s < 2; ++s)
       {
         for (int d = 0; d < 2; ++d) { e->mig_key[s][d].alloc(e->mig_cap); e->mig_val[s][d].alloc(e->mig_cap); }
-        e->inbox[s].alloc(inbox_bytes(e->mig_cap, e->mig_n_real));
+        e->inbox[s].alloc(inbox_bytes(e->mig_cap, e->mig_n_real, lcx::halo_values(g)));
         LCX_CUDA(cudaMemsetAsync(e->inbox[s].p, 0, MIG_HDR_BYTES, e->stream));
       }
       LCX_CUDA(cudaEventCreateWithFlags(&e->ev_put, cudaEventDisableTiming));
@@ -669,6 +669,10 @@ int lcx_migr_put(lcx_engine *e, int64_t *n_lft, int64_t *n_rgt) { return guarded
 
 int lcx_migr_take(lcx_engine *e, lcx_engine *rgt, lcx_engine *lft, int64_t *n_from_rgt, int64_t *n_from_lft)
 { return guarded([&] { use_device(e); lcx::migr_take(e, rgt, lft, n_from_rgt, n_from_lft); }); }
+
+int lcx_halo_put(lcx_engine *e) { return guarded([&] { use_device(e, true, 3u); lcx::halo_put(e); }); }
+
+int lcx_halo_take(lcx_engine *e) { return guarded([&] { use_device(e, true, 3u); lcx::halo_take(e); }); }
 
 int lcx_migr_real_attrs(lcx_engine *e, int *count)
 {

@@ -204,7 +204,7 @@ struct lcx_engine
   lcx::dbuf<unsigned char> inbox[2];
   struct mig_remote { unsigned char *base = nullptr; size_t cap = 0; bool ipc = false; } remote[2];
   cudaEvent_t ev_put = nullptr;
-  unsigned mig_seq = 0;
+  unsigned mig_seq = 0, halo_seq = 0;   // halo_seq: deliveries of Courant halo planes (lcx_halo_put / lcx_halo_take)
   size_t keys_ready = 0;         // key[0] / val[0] already hold the re-layout sort keys of SDs [0, keys_ready) (written by k_transport)
 
   lcx::dbuf<lcx::dev_scalars> scalars;
@@ -289,11 +289,18 @@ namespace lcx
   void transport(lcx_engine *e, const lcx_transport_opts *o);
   void migr_put(lcx_engine *e, int64_t *n_lft, int64_t *n_rgt);
   void migr_take(lcx_engine *e, lcx_engine *rgt, lcx_engine *lft, int64_t *n_from_rgt, int64_t *n_from_lft);
+  size_t halo_values(const grid_t &g);      // Courant values one neighbour delivers per step: halo_x + halo_y + halo_z
+  void halo_put(lcx_engine *e);
+  void halo_take(lcx_engine *e);
 
-  // layout of an inbox allocation: 256 bytes of headers (one per parity), then n[2][cap], then real[2][n_real][cap]
-  struct mig_hdr { unsigned int count, seq, pad0, pad1; };
+  // layout of an inbox allocation: 256 bytes of headers (one per parity), then n[2][cap], then real[2][n_real][cap], then the
+  // Courant halo planes of the neighbour halo[2][halo_n] (predictor-corrector advection only, else halo_n = 0)
+  struct mig_hdr { unsigned int count, seq, halo_seq, pad1; };
   constexpr size_t MIG_HDR_BYTES = 256;
-  inline size_t inbox_bytes(size_t cap, int n_real) { return MIG_HDR_BYTES + 2 * cap * (sizeof(n_t) + size_t(n_real) * sizeof(real_t)); }
+  inline size_t inbox_sd_bytes(size_t cap, int n_real) { return MIG_HDR_BYTES + 2 * cap * (sizeof(n_t) + size_t(n_real) * sizeof(real_t)); }
+  inline size_t inbox_bytes(size_t cap, int n_real, size_t halo_n) { return inbox_sd_bytes(cap, n_real) + 2 * halo_n * sizeof(real_t); }
+  inline real_t *box_halo(unsigned char *b, size_t cap, int n_real, size_t halo_n, int parity)
+  { return reinterpret_cast<real_t *>(b + inbox_sd_bytes(cap, n_real)) + size_t(parity) * halo_n; }
   inline mig_hdr *box_hdr(unsigned char *b, int parity) { return reinterpret_cast<mig_hdr *>(b) + parity; }
   inline n_t *box_n(unsigned char *b, size_t cap, int parity) { return reinterpret_cast<n_t *>(b + MIG_HDR_BYTES) + size_t(parity) * cap; }
   inline real_t *box_real(unsigned char *b, size_t cap, int n_real, int parity)

@@ -374,6 +374,41 @@ namespace lcx
       __threadfence_system();
     }
 
+    // ---- Courant halo planes between process-distributed slabs: particles_impl_xchng_courants.ipp:15-153 -----------------
+    // up to three contiguous pieces (Cx, Cy, Cz planes) copied between this engine's Courant arrays and a packed buffer that
+    // may be peer memory (the neighbour's inbox): plain coalesced stores over NVLink
+    struct halo_pieces { const real_t *src[3]; real_t *dst[3]; unsigned n[3]; };
+    __global__ void __launch_bounds__(TPB) k_halo_copy(halo_pieces P)
+    {
+      unsigned t = blockIdx.x * TPB + threadIdx.x;
+      for (int q = 0; q < 3; ++q)
+      {
+        if (t < P.n[q]) { P.dst[q][t] = P.src[q][t]; return; }
+        t -= P.n[q];
+      }
+    }
+    __global__ void k_halo_signal(mig_hdr *hdr, unsigned seq)
+    {
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned int *>(&hdr->halo_seq) = seq;
+      __threadfence_system();
+    }
+    __global__ void k_halo_wait(const mig_hdr *h0, const mig_hdr *h1, unsigned seq, dev_scalars *sc, long long max_cycles)
+    {
+      const long long t0 = clock64();
+      for (int q = 0; q < 2; ++q)
+      {
+        const mig_hdr *h = q == 0 ? h0 : h1;
+        if (!h) continue;
+        while (*reinterpret_cast<const volatile unsigned int *>(&h->halo_seq) != seq)
+        {
+          __nanosleep(200);
+          if (clock64() - t0 > max_cycles) { sc->mig_timeout = 2u; return; }
+        }
+      }
+      __threadfence_system();
+    }
+
     struct mig_dst { real_t *dst[12]; int n; int x_slot; };
 
     __global__ void __launch_bounds__(TPB) k_mig_unpack(unsigned count, size_t n_part_old, size_t sid_first, mig_dst A, n_t *__restrict__ ns, idx_t *__restrict__ sid,
@@ -460,6 +495,85 @@ namespace lcx
     e->grouped = false;   // positions changed: cell segments are stale until lcx_post_copy
   }
 
+  // Courant values of the planes one neighbour needs: halo_size x-planes of each staggered field
+  static void halo_counts(const grid_t &g, unsigned n[3])
+  {
+    const unsigned h = unsigned(g.halo_size);
+    n[0] = n[1] = n[2] = 0;
+    if (h == 0 || g.n_dims == 0) return;
+    n[0] = g.n_dims == 1 ? h : g.n_dims == 2 ? h * g.nz : h * g.nz * g.ny;                       // halo_x
+    if (g.n_dims == 3) n[1] = h * (g.ny + 1) * g.nz;                                            // halo_y
+    if (g.n_dims >= 2) n[2] = g.n_dims == 2 ? h * (g.nz + 1) : h * (g.nz + 1) * g.ny;           // halo_z
+  }
+  size_t halo_values(const grid_t &g) { unsigned n[3]; halo_counts(g, n); return size_t(n[0]) + n[1] + n[2]; }
+
+  static long long wait_cycles()
+  {
+    static const long long c = [] { const char *v = std::getenv("LCX_MIG_TIMEOUT_S"); return (long long)((v ? std::atof(v) : 20.) * 2e9); }();
+    return c;
+  }
+
+  // Each distributed side: this slab's outermost interior planes go STRAIGHT into the neighbour's inbox (its halo section), then
+  // the delivery is published.  What goes where is the reference's rule (xchng_courants.ipp:26-52): to the left neighbour the
+  // planes right of face 0 (Cx: faces 1..h, Cy / Cz: columns 0..h-1) - its right halo; to the right neighbour the last h planes
+  // (Cx: faces nx-h..nx-1, Cy / Cz: columns nx-h..nx-1) - its left halo.
+  void halo_put(lcx_engine *e)
+  {
+    const grid_t &g = e->grid;
+    unsigned n[3];
+    halo_counts(g, n);
+    const size_t total = size_t(n[0]) + n[1] + n[2];
+    const bool dm[2] = {e->cfg.bcond_lft == LCX_BCOND_DISTMEM, e->cfg.bcond_rgt == LCX_BCOND_DISTMEM};
+    if (total == 0 || (!dm[0] && !dm[1])) return;
+    wait_courant(e);
+    const unsigned seq = ++e->halo_seq;
+    const int parity = int(seq & 1u);
+    const size_t h = size_t(g.halo_size);
+    const size_t col_x = n[0] / h, col_y = n[1] / h, col_z = n[2] / h;      // values per x-plane
+    for (int side = 0; side < 2; ++side)
+    {
+      if (!dm[side]) continue;
+      lcx_engine::mig_remote &r = e->remote[side];
+      if (!r.base) throw error("lcx_halo_put: no neighbour connected on side " + std::to_string(side));
+      real_t *out = box_halo(r.base, r.cap, e->mig_n_real, total, parity);
+      halo_pieces P;
+      // first plane sent, in planes of the halo-extended arrays (interior face / column f sits at plane h + f)
+      const size_t px = side == 0 ? h + 1 : size_t(g.nx), pyz = side == 0 ? h : size_t(g.nx);
+      P.src[0] = e->courant_x.p + px * col_x;                           P.dst[0] = out;               P.n[0] = n[0];
+      P.src[1] = n[1] ? e->courant_y.p + pyz * col_y : nullptr;         P.dst[1] = out + n[0];        P.n[1] = n[1];
+      P.src[2] = n[2] ? e->courant_z.p + pyz * col_z : nullptr;         P.dst[2] = out + n[0] + n[1]; P.n[2] = n[2];
+      LCX_LAUNCH(e, k_halo_copy, div_up(total, TPB), TPB, 0, P);
+      LCX_LAUNCH(e, k_halo_signal, 1, 1, 0, box_hdr(r.base, parity), seq);
+    }
+  }
+
+  // Waits (on the device) for both neighbours' planes and copies them into this slab's halo: the right neighbour's into the last
+  // h planes of each array, the left neighbour's into the first h
+  void halo_take(lcx_engine *e)
+  {
+    const grid_t &g = e->grid;
+    unsigned n[3];
+    halo_counts(g, n);
+    const size_t total = size_t(n[0]) + n[1] + n[2];
+    // inbox 0 is filled by the right neighbour, inbox 1 by the left one
+    const bool dm[2] = {e->cfg.bcond_rgt == LCX_BCOND_DISTMEM, e->cfg.bcond_lft == LCX_BCOND_DISTMEM};
+    if (total == 0 || (!dm[0] && !dm[1])) return;
+    const unsigned seq = e->halo_seq;
+    const int parity = int(seq & 1u);
+    LCX_LAUNCH(e, k_halo_wait, 1, 1, 0, dm[0] ? box_hdr(e->inbox[0].p, parity) : nullptr, dm[1] ? box_hdr(e->inbox[1].p, parity) : nullptr,
+               seq, e->scalars.p, wait_cycles());
+    for (int q = 0; q < 2; ++q)
+    {
+      if (!dm[q]) continue;
+      const real_t *in = box_halo(e->inbox[q].p, e->mig_cap, e->mig_n_real, total, parity);
+      halo_pieces P;
+      P.src[0] = in;               P.dst[0] = q == 0 ? e->courant_x.p + e->courant_x.n - n[0] : e->courant_x.p;                 P.n[0] = n[0];
+      P.src[1] = in + n[0];        P.dst[1] = n[1] ? (q == 0 ? e->courant_y.p + e->courant_y.n - n[1] : e->courant_y.p) : nullptr; P.n[1] = n[1];
+      P.src[2] = in + n[0] + n[1]; P.dst[2] = n[2] ? (q == 0 ? e->courant_z.p + e->courant_z.n - n[2] : e->courant_z.p) : nullptr; P.n[2] = n[2];
+      LCX_LAUNCH(e, k_halo_copy, div_up(total, TPB), TPB, 0, P);
+    }
+  }
+
   // Sorts each side's leavers by storage index (the reference lists them in ascending SD index: bcnd.ipp:160-172), packs them
   // into the neighbour's inbox and publishes the delivery.  One host read-back: the two counts.
   static bool mig_debug() { static const bool on = [] { const char *v = std::getenv("LCX_MIG_DEBUG"); return v && v[0] == '1'; }(); return on; }
@@ -525,7 +639,7 @@ namespace lcx
       if (nb[q]) { if (nb[q] != e) LCX_CUDA(cudaStreamWaitEvent(e->stream, nb[q]->ev_put, 0)); }
       else wait_for[q] = box_hdr(e->inbox[q].p, parity);
     }
-    static const long long max_cycles = [] { const char *v = std::getenv("LCX_MIG_TIMEOUT_S"); return (long long)((v ? std::atof(v) : 20.) * 2e9); }();
+    const long long max_cycles = wait_cycles();
     if (wait_for[0] || wait_for[1])
       LCX_LAUNCH(e, k_mig_wait, 1, 1, 0, wait_for[0], wait_for[1], seq, e->scalars.p, max_cycles);
     mig_hdr h[2] = {};
@@ -534,6 +648,8 @@ namespace lcx
     LCX_CUDA(cudaMemcpyAsync(e->h_scalars, e->scalars.p, sizeof(dev_scalars), cudaMemcpyDeviceToHost, e->stream));
     LCX_CUDA(cudaStreamSynchronize(e->stream));
     if (mig_debug()) std::fprintf(stderr, "[mig dev %d] take seq %u: headers (%u, %u) (%u, %u) timeout %u\n", e->device, seq, h[0].seq, h[0].count, h[1].seq, h[1].count, e->h_scalars->mig_timeout);
+    if (e->h_scalars->mig_timeout == 2u)
+      throw error("Courant halo exchange: a neighbour's planes did not arrive in time (predictor-corrector advection between process-distributed slabs; $LCX_MIG_TIMEOUT_S)");
     if (e->h_scalars->mig_timeout)
       throw error("x-slab migration: a neighbour's delivery did not arrive in time (waiting for sequence number " + std::to_string(seq) + "; inbox from the right holds " +
                   std::to_string(h[0].seq) + " with " + std::to_string(h[0].count) + " super-droplets, inbox from the left " + std::to_string(h[1].seq) + " with " +

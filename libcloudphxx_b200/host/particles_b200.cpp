@@ -1158,6 +1158,9 @@ namespace libcloudphxx
 
           if (n_dims > 0)
           {
+            // rank-local Courant arrays cannot hold the neighbours' columns of the predictor-corrector halo: exchanged between the
+            // slabs' engines every step (particles_step.ipp:111-112 -> xchng_courants.ipp:15-153; here over peer memory, no MPI)
+            if (process_distributed && halo_size > 0 && opts.adve) { chk(L::halo_put(e)); chk(L::halo_take(e)); }
             lcx_transport_opts t;
             t.adve = opts.adve; t.sedi = opts.sedi; t.subs = opts.subs; t.adve_scheme = int(adve_scheme); t.dt = dt;
             chk(L::transport(e, &t));
@@ -1276,10 +1279,6 @@ namespace libcloudphxx
             s0.slab_rank = dm.rank;
             // the Eulerian arrays are rank-local; the global cell offset only decorrelates the slabs' random streams
             s0.philox_cell_base = size_t(dm.rank) * s0.n_cell;
-            if (o.adve_scheme == as_t::pred_corr)
-              throw std::runtime_error("libcloudph++ (B200 engine): predictor-corrector advection in a process-distributed run needs the neighbours' Courant "
-                                       "halo columns (particles_impl_xchng_courants.ipp), which this back-end does not exchange between processes; "
-                                       "use adve_scheme implicit / euler, or the multi_CUDA backend (whose Eulerian arrays are global)");
           }
           this->opts_init = &slabs[0]->oi;
         }

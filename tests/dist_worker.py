@@ -67,6 +67,58 @@ def full_microphysics(lib, rank, world, local):
         print("DIST_FULL_OK world=%d sd=%s" % (world, [t[3] for t in v1]))
 
 
+def pred_corr_halo(lib, rank, world, local):
+    """predictor-corrector advection between process-distributed slabs: every rank passes its OWN piece of the Courant fields, the
+    two halo planes per side must arrive from the neighbours (the reference's MPI build: particles_impl_xchng_courants.ipp:26-140 -
+    to the left neighbour go Cx faces 1, 2 and Cy / Cz columns 0, 1, to the right neighbour the last two faces / columns).  Checked on
+    the device arrays themselves against a numpy statement of that rule on a global field whose every value is unique."""
+    from libcloudphxx_b200 import engine as E
+    halo, ny, nz, dx = 2, 3, 5, 20.0
+    nxs = [4 + r for r in range(world)]                       # unequal slabs
+    nx, x_bfr, n_x_tot = nxs[rank], sum(nxs[:rank]), sum(nxs)
+    D.configure(lib, rank, world, lft_x1=nxs[(rank - 1) % world] * dx, rgt_x0=0.0, n_x_tot=n_x_tot)
+    oi, o, f = S.box_3d(lib, nx=nx, ny=ny, nz=nz, sd_conc=16, adve=L.as_t.pred_corr)
+    oi.n_sd_max = int(oi.n_sd_max * 2)
+    oi.rng_seed = 99 + rank
+    oi.dev_id = local
+    shapes = {"Cx": (n_x_tot + 1, ny, nz), "Cy": (n_x_tot, ny + 1, nz), "Cz": (n_x_tot, ny, nz + 1)}
+    G = {k: (1e-3 + np.arange(int(np.prod(sh))).reshape(sh) * 1e-4) * {"Cx": 1.0, "Cy": 0.5, "Cz": 0.1}[k] for k, sh in shapes.items()}
+    for k in G:
+        f[k] = np.ascontiguousarray(G[k][x_bfr:x_bfr + nx + (1 if k == "Cx" else 0)])
+    o.cond = o.coal = o.sedi = 0
+    p = lib.factory(L.backend_t.CUDA, oi)
+    p.init(f["th"], f["rv"], f["rhod"], None, f["Cx"], f["Cy"], f["Cz"])
+    D.connect(lib, p, rank, world)
+    eng = D.engine_of(lib, p)
+    n0 = [None] * world
+    dist.all_gather_object(n0, eng.n_part())
+    lcx = E.lib()
+    lcx.lcx_cells_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]
+    lcx.lcx_field_size.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
+    for step in range(4):
+        f["Cx"] *= 1.0 + 0.01 * step                          # the fields change every step: a stale halo would show
+        G["Cx"] = G["Cx"] * (1.0 + 0.01 * step)
+        p.step_sync(o, f["th"], f["rv"], f["rhod"], f["Cx"], f["Cy"], f["Cz"])
+        p.step_async(o)
+        for field, name in ((4, "Cx"), (5, "Cy"), (6, "Cz")):
+            cnt = C.c_int64()
+            E.check(lcx.lcx_field_size(eng.h, field, C.byref(cnt)))
+            got = np.empty(cnt.value)
+            E.check(lcx.lcx_cells_get(eng.h, field, got.ctypes.data, cnt.value))
+            own = nx + (1 if name == "Cx" else 0)
+            first_rgt = 1 if name == "Cx" else 0               # the right neighbour's faces 1, 2 / columns 0, 1
+            cols = np.concatenate([(x_bfr - halo + np.arange(halo)) % n_x_tot, x_bfr + np.arange(own),
+                                   (x_bfr + nx + first_rgt + np.arange(halo)) % n_x_tot])
+            want = G[name][cols]
+            assert got.size == want.size, (name, got.size, want.shape)
+            assert np.array_equal(got.reshape(want.shape), want), "rank %d step %d: %s halo differs" % (rank, step, name)
+    n1 = [None] * world
+    dist.all_gather_object(n1, eng.n_part())
+    assert 0.98 * sum(n0) <= sum(n1) <= sum(n0), (n0, n1)      # the field has a small upward component: a few SDs may leave through the lid
+    if rank == 0:
+        print("DIST_HALO_OK world=%d sd=%s" % (world, n1))
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     n_dev = torch.cuda.device_count()
@@ -77,6 +129,11 @@ def main():
     else:
         dist.init_process_group("gloo")
     lib = L.b200()
+    if "--halo" in sys.argv:
+        pred_corr_halo(lib, rank, world, local)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     if "--full" in sys.argv:
         full_microphysics(lib, rank, world, local)
         dist.barrier()
