@@ -148,6 +148,15 @@ int  lcx_set_efficiencies(lcx_engine *e, const void *table, int64_t n);     /* i
 /* append `count` SDs (host arrays; absent dimensions may be NULL); vt := invalid; sid continues      */
 int  lcx_sd_append(lcx_engine *e, int64_t count, const uint64_t *n, const void *rd3, const void *rw2,
                    const void *kpa, const void *x, const void *y, const void *z, const uint32_t *ijk);
+/* Device-side creation of the `sd_conc` flavour (per_cell super-droplets in every cell; reference: init_dry_sd_conc.ipp:25-66,    */
+/* init_wet.ipp:18-74, init_xyz.ipp:16-73, init_ijk.ipp:36-52) from the counter-based random stream (key = seed, stream; counter  */
+/* = SD index, call): dry radii stratified in ln(rd) over [log_rd_min, log_rd_max], equilibrium wet radii at min(RH, RH_max) of    */
+/* the cell (lcx_hskpng_Tpr must have run), positions uniform in the cell.  Multiplicities are left 0: the dry radii cubed come    */
+/* back in rd3_host (n_cell * per_cell reals, host memory), the caller evaluates its spectrum and sends n with lcx_sd_set_n       */
+/* (physical order == order of creation until the first lcx_post_copy).                                                          */
+int  lcx_sd_append_sd_conc(lcx_engine *e, int64_t per_cell, double log_rd_min, double log_rd_max, double kappa, double RH_max,
+                           uint64_t seed, uint32_t stream, uint64_t call, void *rd3_host);
+int  lcx_sd_set_n(lcx_engine *e, int64_t first, int64_t count, const uint64_t *n);
 int  lcx_n_part(lcx_engine *e, int64_t *n_part);
 /* always != 0 (default): storage indices are re-numbered after every removal, as injected random streams and          */
 /* lcx_get_attr need; 0: the re-numbering is postponed until something needs it (enough for the Philox stream)         */

@@ -35,7 +35,7 @@ CXX_FLAGS = ["-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-fopenmp", "-Wa
              "-I", "/usr/local/cuda/include"]
 
 CU_SOURCES = ["lcx_api.cu", "lcx_sort.cu", "lcx_cells.cu", "lcx_diag.cu", "lcx_cond.cu", "lcx_cond_pp.cu", "lcx_coal.cu",
-              "lcx_transport.cu", "lcx_layout.cu"]
+              "lcx_transport.cu", "lcx_layout.cu", "lcx_init.cu"]
 CU_HEADERS = ["lcx_engine.cuh", "lcx_physics.h", os.path.join(REPO, "include", "lcx_b200_f32_names.h")]
 # translation units whose results are tolerance-class anyway (condensation root solve): FMA contraction allowed
 FMAD_OK = {"lcx_cond.cu"}

@@ -470,6 +470,28 @@ int lcx_sd_append(lcx_engine *e, int64_t count, const uint64_t *n, const void *r
   });
 }
 
+int lcx_sd_append_sd_conc(lcx_engine *e, int64_t per_cell, double log_rd_min, double log_rd_max, double kappa, double RH_max,
+                          uint64_t seed, uint32_t stream, uint64_t call, void *rd3_host)
+{
+  return guarded([&] {
+    use_device(e);
+    if (per_cell <= 0) return;
+    lcx::sd_append_sd_conc(e, size_t(per_cell), lcx::real_t(log_rd_min), lcx::real_t(log_rd_max), lcx::real_t(kappa), lcx::real_t(RH_max),
+                           seed, stream, call, static_cast<lcx::real_t *>(rd3_host));
+  });
+}
+
+int lcx_sd_set_n(lcx_engine *e, int64_t first, int64_t count, const uint64_t *n)
+{
+  return guarded([&] {
+    use_device(e);
+    if (first < 0 || count < 0 || size_t(first + count) > e->n_part) throw lcx::error("lcx_sd_set_n: range outside the super-droplets");
+    if (e->grouped) throw lcx::error("lcx_sd_set_n: call it right after lcx_sd_append_sd_conc (the re-layout has already moved the super-droplets)");
+    LCX_CUDA(cudaMemcpyAsync(e->S().n.p + first, n, size_t(count) * sizeof(lcx::n_t), cudaMemcpyHostToDevice, e->stream));
+    LCX_CUDA(cudaStreamSynchronize(e->stream));
+  });
+}
+
 int lcx_set_dense_storage_index(lcx_engine *e, int always)
 { return guarded([&] { use_device(e); e->dense_always = always != 0; if (e->dense_always) lcx::densify_sid(e); }); }
 

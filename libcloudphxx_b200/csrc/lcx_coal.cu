@@ -27,25 +27,6 @@ namespace lcx
     constexpr unsigned MEDIUM_MAX = 1024;    // ... and in the big-shared-memory configuration (rain piling up in a few cells)
     constexpr int KAPPA_ITER_MAX = 64;       // collisions of one pair up to which kappa is mixed event by event like the reference
 
-    // ---- Philox4x32-10 (Salmon, Moraes, Dror & Shaw, SC'11) --------------------------------------------
-    struct philox_key { uint32_t k0, k1; };
-    __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1)
-    {
-      const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-      const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-      c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-    }
-    __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], philox_key k)
-    {
-#pragma unroll
-      for (int r = 0; r < 10; ++r)
-      {
-        philox_round(c, k.k0, k.k1);
-        k.k0 += 0x9E3779B9u; k.k1 += 0xBB67AE85u;
-      }
-    }
-
     struct rng_src
     {
       int mode;

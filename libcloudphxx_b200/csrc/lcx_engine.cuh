@@ -307,6 +307,35 @@ namespace lcx
   { return reinterpret_cast<real_t *>(b + MIG_HDR_BYTES + 2 * cap * sizeof(n_t)) + size_t(parity) * cap * size_t(n_real); }
 
   real_t *attr_ptr(lcx_engine *e, int attr);
+
+  // ---- lcx_init.cu -----------------------------------------------------------------------------------
+  void sd_append_sd_conc(lcx_engine *e, size_t per_cell, real_t log_rd_min, real_t log_rd_max, real_t kappa, real_t RH_max,
+                         uint64_t seed, uint32_t stream, uint64_t call, real_t *rd3_host);
+
+  // ---- Philox4x32-10 (Salmon, Moraes, Dror & Shaw, SC'11) --------------------------------------------
+  struct philox_key { uint32_t k0, k1; };
+  __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1)
+  {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  }
+  __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], philox_key k)
+  {
+#pragma unroll
+    for (int r = 0; r < 10; ++r)
+    {
+      philox_round(c, k.k0, k.k1);
+      k.k0 += 0x9E3779B9u; k.k1 += 0xBB67AE85u;
+    }
+  }
+  // 53-bit mantissa from two Philox words: uniform in [0, 1)
+  __device__ __forceinline__ double philox_u01(uint32_t w0, uint32_t w1)
+  {
+    const uint64_t bits = (uint64_t(w0) << 21) ^ (uint64_t(w1) >> 11);
+    return double(bits & ((1ull << 53) - 1)) * (1.0 / 9007199254740992.0);
+  }
 }
 
 // runs CALL once with the compile-time constant M set to the run-time solver mode

@@ -23,6 +23,7 @@
 #include <lgrngn_abi_probe.hpp>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdlib>
@@ -552,15 +553,18 @@ namespace libcloudphxx
         void init(const arrinfo_t<real_t> &th, const arrinfo_t<real_t> &rv, const arrinfo_t<real_t> &rhod, const arrinfo_t<real_t> &p,
                   const arrinfo_t<real_t> &cx, const arrinfo_t<real_t> &cy, const arrinfo_t<real_t> &cz, size_t n_ambient_chem)
         {
+          stopwatch sw;
           init_sanity_check(th, rv, rhod, p, cx, cy, cz, n_ambient_chem);
           if (oi.rng_seed_init_switch) engine.seed(oi.rng_seed_init);
           create_engine();
+          sw.lap("create_engine");
 
           init_e2l(th, m_th, LCX_F_TH);
           init_e2l(rv, m_rv, LCX_F_RV);
           init_e2l(rhod, m_rhod, LCX_F_RHOD);
           if (oi.const_p) init_e2l(p, m_p, LCX_F_P);
           init_courant_maps(cx, cy, cz);
+          sw.lap("index maps");
 
           sync_in_field(th, m_th, LCX_F_TH);
           sync_in_field(rv, m_rv, LCX_F_RV);
@@ -573,12 +577,15 @@ namespace libcloudphxx
           if (oi.subs_switch) chk(L::cells_set(e, LCX_F_W_LS, oi.w_LS.data(), int64_t(oi.w_LS.size()), 0));
 
           chk(L::hskpng_Tpr(e));
+          sw.lap("field uploads");
 
           if (!oi.no_ccn_at_init)
           {
             const cell_state cs = host_cells(th, rv, rhod, p);
+            sw.lap("host cell state");
             if (oi.dry_distros.size() > 0) init_SD_with_distros(cs);
             if (oi.dry_sizes.size() > 0) init_SD_with_sizes(cs);
+            sw.lap("super-droplets (total)");
           }
 
           if (oi.terminal_velocity == vt_t::beard77fast)
@@ -593,6 +600,8 @@ namespace libcloudphxx
           chk(L::hskpng_rc2(e));                        // critical radii for activation sub-stepping (particles_init.ipp:116-117)
           chk(L::sstp_save(e));
           chk(L::post_copy(e, 0, /*keep_all=*/1));      // hskpng_count(): group by the cells assigned at creation
+          chk(L::sync(e));
+          sw.lap("vterm, rc2, grouping");
           engine.seed(oi.rng_seed);
           philox_call = 0;
         }
@@ -612,8 +621,10 @@ namespace libcloudphxx
           cell_state cs;
           cs.rhod.resize(n_cell); cs.T.resize(n_cell); cs.RH.resize(n_cell); cs.dv.resize(n_cell);
           const host_view h_th(th, m_th), h_rv(rv, m_rv), h_rhod(rhod, m_rhod), h_p(p, m_p);
-          for (size_t c = 0; c < n_cell; ++c)
+#pragma omp parallel for schedule(static)
+          for (long cl = 0; cl < long(n_cell); ++cl)
           {
+            const size_t c = size_t(cl);
             const real_t th_c = h_th.data[m_th.l2e[c]], rv_c = h_rv.data[m_rv.l2e[c]], rhod_c = h_rhod.data[m_rhod.l2e[c]];
             real_t T_c, p_c;
             if (oi.th_dry) T_c = lcx::T_of_th_dry(th_c, rhod_c);
@@ -671,6 +682,32 @@ namespace libcloudphxx
         }
 
         real_t draw_u01() { return std::uniform_real_distribution<real_t>(0, 1)(engine); }
+
+        // Super-droplets of the sd_conc flavour are created on the device when the random stream is the counter-based one
+        // (the initial state is then another sample of the same distributions than the reference's mt19937 gives - like every
+        // later draw in that mode); LCX_DEVICE_INIT=0 keeps the host path, which the replayed mt19937 stream always takes.
+        uint64_t init_call = 0;
+        bool device_init() const
+        {
+          if (rng_mode == LGRNGN_B200_RNG_MT19937) return false;
+          const char *v = std::getenv("LCX_DEVICE_INIT");
+          return !(v && v[0] == '0');
+        }
+
+        // LCX_INIT_TIMING=1: phases of init() on stderr (where the seconds of a large initialisation go)
+        struct stopwatch
+        {
+          bool on;
+          std::chrono::steady_clock::time_point t;
+          stopwatch() : on(std::getenv("LCX_INIT_TIMING") && std::getenv("LCX_INIT_TIMING")[0] == '1'), t(std::chrono::steady_clock::now()) {}
+          void lap(const char *what)
+          {
+            if (!on) return;
+            const auto now = std::chrono::steady_clock::now();
+            std::fprintf(stderr, "[lcx init] %-28s %8.3f s\n", what, std::chrono::duration<double>(now - t).count());
+            t = now;
+          }
+        };
 
         // Brent's minimiser (Brent 1973, ch. 5) with the stopping rule and step choices of the Boost.Math routine the
         // reference calls in init_dist_analysis.ipp:95 (brent_find_minima with bits capped at half the mantissa)
@@ -777,6 +814,7 @@ namespace libcloudphxx
         {
           const size_t n_new = ijk.size();
           if (n_new == 0) return;
+          stopwatch sw;
           std::vector<real_t> rw2(n_new), kpa(n_new, kappa), xs, ys, zs, u01(n_new);
 #pragma omp parallel for schedule(static)
           for (long sl = 0; sl < long(n_new); ++sl)
@@ -785,6 +823,7 @@ namespace libcloudphxx
             const real_t RH = std::min(cs.RH[ijk[s]], oi.RH_max);
             rw2[s] = std::pow(lcx::rw3_eq(rd3[s], kpa[s], RH, cs.T[ijk[s]]), real_t(2. / 3));
           }
+          sw.lap("  equilibrium wet radii");
           const int nn[3] = {oi.nx, oi.ny, oi.nz};
           const real_t a[3] = {oi.x0, oi.y0, oi.z0}, b[3] = {oi.x1, oi.y1, oi.z1}, d[3] = {oi.dx, oi.dy, oi.dz};
           std::vector<real_t> *v[3] = {&xs, &ys, &zs};
@@ -792,20 +831,26 @@ namespace libcloudphxx
           {
             if (nn[ix] == 0) continue;
             v[ix]->resize(n_new);
-            for (size_t s = 0; s < n_new; ++s) u01[s] = draw_u01();
+            for (size_t s = 0; s < n_new; ++s) u01[s] = draw_u01();      // the one sequential part: std::mt19937 in the reference's order
+            sw.lap("  mt19937 draws (positions)");
             const size_t nz1 = size_t(m1(oi.nz)), ny1 = size_t(m1(oi.ny));
-            for (size_t s = 0; s < n_new; ++s)
+            real_t *out = v[ix]->data();
+#pragma omp parallel for schedule(static)
+            for (long sl = 0; sl < long(n_new); ++sl)
             {
+              const size_t s = size_t(sl);
               const size_t c = ijk[s];
               size_t ii;
               if (n_dims == 1) ii = c;
               else if (n_dims == 2) ii = ix == 0 ? c / nz1 : c % nz1;
               else ii = ix == 0 ? c / (nz1 * ny1) : ix == 1 ? (c / nz1) % ny1 : c % nz1;
-              (*v[ix])[s] = u01[s] * std::min(b[ix], (ii + 1) * d[ix]) + (1. - u01[s]) * std::max(a[ix], ii * d[ix]);
+              out[s] = u01[s] * std::min(b[ix], (ii + 1) * d[ix]) + (1. - u01[s]) * std::max(a[ix], ii * d[ix]);
             }
+            sw.lap("  positions");
           }
           chk(L::sd_append(e, int64_t(n_new), reinterpret_cast<const uint64_t *>(n.data()), rd3.data(), rw2.data(), kpa.data(),
                             xs.empty() ? nullptr : xs.data(), ys.empty() ? nullptr : ys.data(), zs.empty() ? nullptr : zs.data(), ijk.data()));
+          sw.lap("  upload (sd_append)");
         }
 
         // sd_conc SDs per cell, stratified in ln(rd): init_SD_with_distros_sd_conc.ipp:16-52, init_dry_sd_conc.ipp:25-66, init_n.ipp:48-137
@@ -825,9 +870,38 @@ namespace libcloudphxx
           const std::vector<uint32_t> ijk = cells_of_new(std::vector<size_t>(n_cell, per_cell));
           const size_t n_new = ijk.size();
 
+          stopwatch sw;
+          // multiplicity of one SD from the caller's spectrum: init_n.ipp:48-137 (evaluated on the host, like the reference)
+          auto multiplicity = [&](size_t s, real_t rd3_s) {
+            const real_t lnrd2 = std::log(rd3_s) / 3.;
+            real_t v = multiplier * fun(lnrd2);
+            if (!oi.aerosol_independent_of_rhod) v = v * cs.rhod[ijk[s]] / rho_stp;
+            if (!oi.aerosol_conc_factor.empty()) v = v * oi.aerosol_conc_factor[ijk[s] % size_t(oi.nz)];
+            if (n_dims > 0) v = v * cs.dv[ijk[s]] / real_t(oi.dx * oi.dy * oi.dz);
+            return n_t(v + real_t(0.5));
+          };
+          if (device_init())
+          {
+            // counter-based random stream: dry radii, equilibrium wet radii and positions are made on the device (lcx_init.cu);
+            // only the spectrum - an arbitrary functor of the caller's - is evaluated here
+            std::vector<real_t> rd3(n_new);
+            std::vector<n_t> n(n_new);
+            int64_t first = 0;
+            chk(L::n_part(e, &first));
+            chk(L::sd_append_sd_conc(e, int64_t(per_cell), log_rd_min, log_rd_max, kr.kappa, oi.RH_max, uint64_t(uint32_t(oi.rng_seed)),
+                                     uint32_t(slab_rank), ~uint64_t(0) - init_call++, rd3.data()));
+            sw.lap("  device: rd3, rw2, xyz");
+#pragma omp parallel for schedule(static)
+            for (long sl = 0; sl < long(n_new); ++sl) n[size_t(sl)] = multiplicity(size_t(sl), rd3[size_t(sl)]);
+            sw.lap("  multiplicities (host)");
+            chk(L::sd_set_n(e, first, int64_t(n_new), reinterpret_cast<const uint64_t *>(n.data())));
+            sw.lap("  upload of n");
+            return;
+          }
           std::vector<n_t> n(n_new);
           std::vector<real_t> rd3(n_new), u01(n_new);
           for (size_t s = 0; s < n_new; ++s) u01[s] = draw_u01();
+          sw.lap("  mt19937 draws (dry radii)");
 #pragma omp parallel for schedule(static)
           for (long sl = 0; sl < long(n_new); ++sl)
           {
@@ -835,13 +909,9 @@ namespace libcloudphxx
             const size_t ptr = size_t(ijk[s]) * per_cell;
             const real_t lnrd = log_rd_min + real_t(s - ptr + u01[s]) * (log_rd_max - log_rd_min) / real_t(per_cell);
             rd3[s] = std::exp(3 * lnrd);
-            const real_t lnrd2 = std::log(rd3[s]) / 3.;
-            real_t v = multiplier * fun(lnrd2);
-            if (!oi.aerosol_independent_of_rhod) v = v * cs.rhod[ijk[s]] / rho_stp;
-            if (!oi.aerosol_conc_factor.empty()) v = v * oi.aerosol_conc_factor[ijk[s] % size_t(oi.nz)];
-            if (n_dims > 0) v = v * cs.dv[ijk[s]] / real_t(oi.dx * oi.dy * oi.dz);
-            n[s] = n_t(v + real_t(0.5));
+            n[s] = multiplicity(s, rd3[s]);
           }
+          sw.lap("  dry radii, multiplicities");
           finalize_new(cs, ijk, n, rd3, kr.kappa);
         }
 
