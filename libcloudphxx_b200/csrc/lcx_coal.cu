@@ -22,7 +22,11 @@ namespace lcx
   {
     constexpr int TPB = 256;
     constexpr int CELL_LANES = 16;           // lanes that share one cell in k_coal_small (two cells per warp)
-    constexpr int GROUPS = TPB / CELL_LANES;
+#ifndef LCX_COAL_TPB
+#define LCX_COAL_TPB 256                     // threads per CTA of k_coal_small
+#endif
+    constexpr int CTPB = LCX_COAL_TPB;
+    constexpr int GROUPS = CTPB / CELL_LANES;
     constexpr unsigned SMALL_MAX = BIG_CELL; // largest cell population handled by k_coal_small in its usual configuration
     constexpr unsigned MEDIUM_MAX = 1024;    // ... and in the big-shared-memory configuration (rain piling up in a few cells)
     constexpr int KAPPA_ITER_MAX = 64;       // collisions of one pair up to which kappa is mixed event by event like the reference
@@ -182,7 +186,7 @@ namespace lcx
     // CAP = largest cell population: 256 (static shared memory, 4 CTAs per SM: the usual case) or MEDIUM_MAX (dynamic shared
     // memory, 2 CTAs per SM) for grids where sedimenting drops pile up in a few cells - far cheaper than the global-sort path
     template <int CAP>
-    __global__ void __launch_bounds__(TPB, CAP == int(SMALL_MAX) ? LCX_COAL_MINB : 2) k_coal_small(idx_t n_cell, const uint32_t *__restrict__ off, const idx_t *__restrict__ sid,
+    __global__ void __launch_bounds__(CTPB, (CAP == int(SMALL_MAX) ? LCX_COAL_MINB : 2) * 256 / CTPB) k_coal_small(idx_t n_cell, const uint32_t *__restrict__ off, const idx_t *__restrict__ sid,
                                                        rng_src rng, coal_ctx cx, const uint32_t *__restrict__ cell_list, uint32_t n_list)
     {
       extern __shared__ __align__(16) unsigned char coal_dyn_smem[];
@@ -345,7 +349,7 @@ namespace lcx
 
     if (e->max_count <= SMALL_MAX)
     {
-      LCX_LAUNCH(e, k_coal_small<int(SMALL_MAX)>, div_up(g.n_cell, GROUPS), TPB, 0, g.n_cell, e->cell_off.p, s.sid.p, rng, cx, (const uint32_t *)nullptr, 0u);
+      LCX_LAUNCH(e, k_coal_small<int(SMALL_MAX)>, div_up(g.n_cell, GROUPS), CTPB, 0, g.n_cell, e->cell_off.p, s.sid.p, rng, cx, (const uint32_t *)nullptr, 0u);
       return;
     }
     if (e->max_count <= MEDIUM_MAX && g.n_cell > 1)
@@ -353,9 +357,9 @@ namespace lcx
       constexpr size_t smem = sizeof(uint32_t) * GROUPS * (MEDIUM_MAX + KEY_PAD) + sizeof(unsigned short) * GROUPS * MEDIUM_MAX;
       LCX_CUDA(cudaFuncSetAttribute(k_coal_small<int(MEDIUM_MAX)>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));      // per device; a cheap host call
       // the grid as usual (cells above SMALL_MAX skip themselves), then the few populous cells from the list post_copy made
-      LCX_LAUNCH(e, k_coal_small<int(SMALL_MAX)>, div_up(g.n_cell, GROUPS), TPB, 0, g.n_cell, e->cell_off.p, s.sid.p, rng, cx, (const uint32_t *)nullptr, 0u);
+      LCX_LAUNCH(e, k_coal_small<int(SMALL_MAX)>, div_up(g.n_cell, GROUPS), CTPB, 0, g.n_cell, e->cell_off.p, s.sid.p, rng, cx, (const uint32_t *)nullptr, 0u);
       if (e->n_big)
-        LCX_LAUNCH(e, k_coal_small<int(MEDIUM_MAX)>, div_up(e->n_big, GROUPS), TPB, smem, g.n_cell, e->cell_off.p, s.sid.p, rng, cx,
+        LCX_LAUNCH(e, k_coal_small<int(MEDIUM_MAX)>, div_up(e->n_big, GROUPS), CTPB, smem, g.n_cell, e->cell_off.p, s.sid.p, rng, cx,
                    (const uint32_t *)e->big_cells.p, uint32_t(e->n_big));
       return;
     }

@@ -37,6 +37,13 @@ namespace lcx
   namespace
   {
     constexpr int TPB = 128;
+#ifndef LCX_COND_RANGE_TPB
+#define LCX_COND_RANGE_TPB 32               // ONE warp per CTA of the run-per-warp kernel (32 CTAs per SM at 64 registers): warps of a CTA finish at different times and a 4-warp CTA holds its slot until the last one has (measured 7.02 -> 6.75 ms; 64 and 256 threads: 7.05, 7.07)
+#endif
+#ifndef LCX_COND_RANGE_MINB
+#define LCX_COND_RANGE_MINB (LCX_COND_MINB * 128 / LCX_COND_RANGE_TPB)
+#endif
+    constexpr int RTPB = LCX_COND_RANGE_TPB;
 #ifndef LCX_COND_MINB
 #define LCX_COND_MINB 8                      // 8 CTAs of 4 warps per SM (64 registers): measured best of {4,5,6,8}
 #endif
@@ -146,12 +153,12 @@ namespace lcx
     // 4 KB per warp limit the run to 8 cells (7.2-7.5 ms against 7.0-7.2 ms per launch for runs of 16).
     constexpr int RANGE_MAX = 16;
     template <int MODE, bool LAZY>
-    __global__ void __launch_bounds__(TPB, LCX_COND_MINB) k_cond_range(idx_t c_begin, idx_t n_cell, int run, const uint32_t *__restrict__ off, real_t dt, real_t RH_max, cond_args a,
+    __global__ void __launch_bounds__(RTPB, LCX_COND_RANGE_MINB) k_cond_range(idx_t c_begin, idx_t n_cell, int run, const uint32_t *__restrict__ off, real_t dt, real_t RH_max, cond_args a,
                                                        int n_dims, const real_t *__restrict__ dv, int first_step, int keep_after,
                                                        real_t *__restrict__ rw_mom3, real_t *__restrict__ drw_mom3,
                                                        real_t *__restrict__ th, real_t *__restrict__ rv, lazy_args z)
     {
-      constexpr int WARPS = TPB / 32;
+      constexpr int WARPS = RTPB / 32;
       __shared__ cond_cell_consts<real_t> s_k[WARPS][RANGE_MAX];
       __shared__ real_t s_m[WARPS][RANGE_MAX][2];
       const int w = threadIdx.x / 32, l = threadIdx.x % 32;
@@ -489,7 +496,7 @@ namespace lcx
   {
     if (cond_staged() && cond_solver() == COND_TOMS748) return 0;
     const int run = e->max_count <= FUSED_MAX ? range_run(e) : 0;
-    return run > 0 ? run * (TPB / 32) : 0;
+    return run > 0 ? run * (RTPB / 32) : 0;
   }
 
   int cond_staged()
@@ -552,18 +559,18 @@ namespace lcx
       // pending gather-on-read re-layout
       const idx_t c_begin = windowed ? e->win_begin : 0, c_end = windowed ? e->win_end : g.n_cell;
       if (windowed && (c_begin % idx_t(run) != 0 || c_end <= c_begin || c_end > g.n_cell)) throw error("lcx_cond: cell window not aligned to the kernel's runs");
-      const unsigned blocks = div_up(div_up(c_end - c_begin, run), TPB / 32);
+      const unsigned blocks = div_up(div_up(c_end - c_begin, run), RTPB / 32);
       lazy_args z = {};
       if (e->pending & lcx_engine::PENDING_ATTR)      // consume the pending re-layout: read through the permutation from the old buffer set, write everything into the new one
       {
         sd_arrays &o = e->A();
         z = {e->pending_perm.p, o.rw2.p, o.rd3.p, o.kpa.p, o.vt.p, o.n.p, s.rd3.p, s.kpa.p, s.vt.p, s.n.p};
         if (c_end == g.n_cell) e->pending &= ~unsigned(lcx_engine::PENDING_ATTR);
-        LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_cond_range<M, true>), blocks, TPB, 0, c_begin, c_end, run, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p,
+        LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_cond_range<M, true>), blocks, RTPB, 0, c_begin, c_end, run, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p,
                                           int(step == 0), keep_after, e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p, z));
         return;
       }
-      LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_cond_range<M, false>), blocks, TPB, 0, c_begin, c_end, run, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p,
+      LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_cond_range<M, false>), blocks, RTPB, 0, c_begin, c_end, run, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p,
                                         int(step == 0), keep_after, e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p, z));
       return;
     }
