@@ -151,7 +151,10 @@ namespace lcx
     // shared memory (one writer per cell and round: the order of summation is fixed by the layout alone, hence reproducible).
     // Measured alternative: per-lane accumulator columns in shared memory instead of the shuffles - no faster, and its
     // 4 KB per warp limit the run to 8 cells (7.2-7.5 ms against 7.0-7.2 ms per launch for runs of 16).
-    constexpr int RANGE_MAX = 16;
+#ifndef LCX_COND_RANGE_MAX
+#define LCX_COND_RANGE_MAX 16
+#endif
+    constexpr int RANGE_MAX = LCX_COND_RANGE_MAX;
     template <int MODE, bool LAZY>
     __global__ void __launch_bounds__(RTPB, LCX_COND_RANGE_MINB) k_cond_range(idx_t c_begin, idx_t n_cell, int run, const uint32_t *__restrict__ off, real_t dt, real_t RH_max, cond_args a,
                                                        int n_dims, const real_t *__restrict__ dv, int first_step, int keep_after,

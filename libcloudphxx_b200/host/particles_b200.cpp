@@ -1073,9 +1073,23 @@ namespace libcloudphxx
           int64_t granule = 0;
           chk(L::cond_granule(e, &granule));
           if (granule <= 0) return false;
-          long chunk = long((n_cell + size_t(K) - 1) / size_t(K));
+          // chunk boundaries, multiples of the granule: K equal chunks, except that the first and the last one are cut in four and two
+          // (1/4, 1/2 of a chunk ... 1/2, 1/4): the upload of the first chunk and the read-back of the last are the part of the
+          // traffic that no kernel hides
+          const long n = long(n_cell);
+          long chunk = (n + K - 1) / K;
           chunk = (chunk + granule - 1) / granule * granule;
-          if (size_t(chunk) >= n_cell) return false;
+          if (chunk >= n) return false;
+          std::vector<long> edge(1, 0);
+          auto cut = [&](long at) { at = std::min(n, (at + granule - 1) / granule * granule); if (at > edge.back()) edge.push_back(at); };
+          const bool graded = env_long("LCX_SYNC_GRADED", 1) != 0 && chunk >= 8 * granule;
+          for (long c0 = 0; c0 < n; c0 += chunk)
+          {
+            const long c1 = std::min(c0 + chunk, n);
+            if (graded && c0 == 0) { cut(chunk / 4); cut(chunk / 4 + chunk / 2); }
+            if (graded && c1 == n) { cut(c1 - (c1 - c0) / 4 - (c1 - c0) / 2); cut(c1 - (c1 - c0) / 4); }
+            cut(c1);
+          }
 
           // what sync_in does, except that th / rv / rhod go chunk by chunk and the Courant fields last
           var_rho = !rhod.is_null();
@@ -1086,18 +1100,17 @@ namespace libcloudphxx
             for_run_pieces(m_rv, c0, c1, [&](long dst, long src, long len) { chk(L::cells_set_part(e, LCX_F_RV, dst, rv.data + src, len)); });
             if (var_rho) for_run_pieces(m_rhod, c0, c1, [&](long dst, long src, long len) { chk(L::cells_set_part(e, LCX_F_RHOD, dst, rhod.data + src, len)); });
           };
-          const long n = long(n_cell);
-          upload(0, std::min(chunk, n));     // before anything is queued on the engine's stream: this one overlaps the previous step's re-layout
+          upload(edge[0], edge[1]);          // before anything is queued on the engine's stream
           chk(L::hskpng_mfp(e));             // from the T, p left by the previous Tpr (particles_step.ipp:189-194)
           try
           {
-            for (long c0 = 0; c0 < n; c0 += chunk)
+            for (size_t k = 0; k + 1 < edge.size(); ++k)
             {
-              const long c1 = std::min(c0 + chunk, n);
+              const long c0 = edge[k], c1 = edge[k + 1];
               chk(L::set_cell_window(e, c0, c1));
               chk(L::hskpng_Tpr(e));
               chk(L::cond(e, dt, opts.RH_max, 0, 1));
-              if (c1 < n) upload(c1, std::min(c1 + chunk, n));
+              if (k + 2 < edge.size()) upload(c1, edge[k + 2]);
               else
               {
                 sync_in_field(cx, m_cx, LCX_F_COURANT_X);
