@@ -45,6 +45,7 @@ KERNEL_BYTES_EXACT = {        # gather-on-read variants (the default): the re-la
     # kernel (permutation 4 + five attributes read 40 + cell index 4 + five attributes written 40), that of x, y, z in the
     # transport kernel (+ permutation 4), and k_gather is left with the storage index (permutation 4 + read 4 + write 4)
     "(k_cond_range<M, true>)": 88.0, "k_transport<true>": 76.0,
+    "(k_cond_classed<M, true>)": 96.0, "(k_cond_classed<M, false>)": 60.0,      # class-ordered walk: + one more read of rw2 for the classification sweep
     "k_cond_staged<true>": 88.0, "k_cond_staged<false>": 52.0,      # the phase-grouped form of the range kernel: same traffic
 }
 LAZY = os.environ.get("LCX_LAZY_GATHER", "1") != "0"
@@ -52,7 +53,7 @@ LAZY = os.environ.get("LCX_LAZY_GATHER", "1") != "0"
 # (fixed bytes, number of real words) per SD of the kernels that dominate; the multiplicity stays 8 bytes, indices and keys 4
 REAL_BYTES = 8
 A_FULL_BYTES_F32 = 136.0      # 36 read + 36 write state (n 8 + 7 x 4), 52 sort, 12 random inputs
-KERNEL_WORDS = {"(k_cond_range<M, true>)": (24, 8), "k_cond_range": (20, 4), "k_cond_cells": (16, 4), "k_cond": (20, 4),
+KERNEL_WORDS = {"(k_cond_range<M, true>)": (24, 8), "k_cond_range": (20, 4), "(k_cond_classed<M, true>)": (24, 9), "k_cond_classed": (20, 5), "k_cond_cells": (16, 4), "k_cond": (20, 4),
                 "k_transport<true>": (20, 7), "k_transport": (16, 7), "k_coal_small": (12, 8), "k_coal_big": (12, 8),
                 "k_vterm": (0, 3), "k_mv_count": (4, 0), "k_mv_list": (4, 0), "k_mv_place_stayers": (12, 0)}
 

@@ -191,6 +191,11 @@ int  lcx_set_cond_layout(int cells_per_warp);
 int  lcx_get_cond_layout(void);
 /* the run-per-warp kernel in its phase-grouped form (opt-in, default 0; measured slower on B200: DESIGN.md section 8): droplets that need a 4th / 5th growth-law evaluation are parked   */
 /* in shared memory and processed a full warp at a time; results are bit-identical to the plain form (0), which stays for A/B runs */
+/* Order in which the run-per-warp kernel walks a run's droplets: -1 automatic (default; $LCX_COND_CLASSED): class by class -    */
+/* drizzle / rain drops (rw > 40 um) apart from the rest - once the previous step counted more than one large drop in 64, else  */
+/* in storage order; 0 never; 1 always.  Wet radii are bit-identical either way, a cell's sums are taken in another order.      */
+int  lcx_set_cond_classed(int mode);
+int  lcx_get_cond_classed(void);
 int  lcx_set_cond_staged(int on);
 int  lcx_get_cond_staged(void);
 /* per-particle condensation sub-stepping, all sub-steps of one time step (particles_step.ipp:199-236,                 */

@@ -570,6 +570,8 @@ int lcx_set_cond_solver(int mode) { lcx::set_cond_solver(mode); return 0; }
 int lcx_get_cond_solver(void) { return lcx::cond_solver(); }
 int lcx_set_cond_layout(int cells_per_warp) { lcx::set_cond_layout(cells_per_warp); return 0; }
 int lcx_get_cond_layout(void) { return lcx::cond_layout(); }
+int lcx_set_cond_classed(int mode) { lcx::set_cond_classed(mode); return 0; }
+int lcx_get_cond_classed(void) { return lcx::cond_classed(); }
 int lcx_set_cond_staged(int on) { lcx::set_cond_staged(on); return 0; }
 int lcx_get_cond_staged(void) { return lcx::cond_staged(); }
 

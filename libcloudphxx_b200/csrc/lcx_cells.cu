@@ -41,15 +41,28 @@ namespace lcx
     }
 
     // terminal velocity of liquid SDs; `only_invalid` refreshes entries flagged -1: hskpng_vterm.ipp:185-342
+    // drops with rw > 40 um seen by a full fall-speed pass - in one CTA of 64, a fixed sample: what the next step's condensation
+    // picks its walk order by (lcx_cond.cu, k_cond_classed).  n_large == nullptr: not a full pass.  (Every warp adding to the one
+    // counter cost 1.4 ms on a rain-laden slab.)
+    constexpr unsigned LARGE_SAMPLE = 64;
+    __device__ __forceinline__ void count_large(real_t r2, unsigned int *n_large)
+    {
+      if (!n_large || (blockIdx.x % LARGE_SAMPLE) != 0) return;
+      const unsigned active = __activemask();
+      const unsigned m = __ballot_sync(active, r2 > real_t(1.6e-9));
+      if (m && (threadIdx.x % 32) == unsigned(__ffs(active) - 1)) atomicAdd(n_large, unsigned(__popc(m)));
+    }
+
     __global__ void __launch_bounds__(TPB) k_vterm(size_t n_part, int formula, int only_invalid,
                                                   const real_t *__restrict__ rw2, const idx_t *__restrict__ ijk,
                                                   const real_t *__restrict__ T, const real_t *__restrict__ p,
                                                   const real_t *__restrict__ rhod, const real_t *__restrict__ eta,
-                                                  const real_t *__restrict__ vt0, real_t *__restrict__ vt)
+                                                  const real_t *__restrict__ vt0, real_t *__restrict__ vt, unsigned int *__restrict__ n_large)
     {
       const size_t i = size_t(blockIdx.x) * TPB + threadIdx.x;
       if (i >= n_part) return;
       const real_t r2 = rw2[i];
+      count_large(r2, n_large);
       if (!(r2 > real_t(0))) return;
       if (only_invalid && !(vt[i] == real_t(-1))) return;
       const idx_t c = ijk[i];
@@ -68,13 +81,14 @@ namespace lcx
     template <bool FAST>
     __global__ void __launch_bounds__(TPB) k_vterm_beard77(size_t n_part, int only_invalid, const real_t *__restrict__ rw2, const idx_t *__restrict__ ijk,
                                                           const beard77_cell<real_t> *__restrict__ cells, const real_t *__restrict__ vt0, real_t *__restrict__ vt,
-                                                          const vt0_bins<real_t> bins)
+                                                          const vt0_bins<real_t> bins, unsigned int *__restrict__ n_large)
     {
       // `bins` comes from the host (the same object the host layer built the table with): constructed here it cost two log()
       // per droplet, a fifth of the kernel's instructions
       const size_t i = size_t(blockIdx.x) * TPB + threadIdx.x;
       if (i >= n_part) return;
       const real_t r2 = rw2[i];
+      count_large(r2, n_large);
       if (!(r2 > real_t(0))) return;
       if (only_invalid && !(vt[i] == real_t(-1))) return;
       const beard77_cell<real_t> k = cells[ijk[i]];
@@ -128,6 +142,7 @@ namespace lcx
   {
     if (e->n_part == 0) return;
     sd_arrays &s = e->S();
+    unsigned int *n_large = only_invalid ? nullptr : &e->scalars.p->n_large;       // a full pass also counts the large drops
     const int formula = e->cfg.terminal_velocity;
     if (formula == VT_BEARD77 || formula == VT_BEARD77FAST)
     {
@@ -136,13 +151,13 @@ namespace lcx
       LCX_LAUNCH(e, k_beard77_cells, div_up(g.n_cell, TPB), TPB, 0, g.n_cell, e->p.p, e->rhod.p, e->eta.p, cells);
       const vt0_bins<real_t> bins;
       if (formula == VT_BEARD77FAST)
-        LCX_LAUNCH(e, (k_vterm_beard77<true>), div_up(e->n_part, TPB), TPB, 0, e->n_part, int(only_invalid), s.rw2.p, s.ijk.p, cells, e->vt0.p, s.vt.p, bins);
+        LCX_LAUNCH(e, (k_vterm_beard77<true>), div_up(e->n_part, TPB), TPB, 0, e->n_part, int(only_invalid), s.rw2.p, s.ijk.p, cells, e->vt0.p, s.vt.p, bins, n_large);
       else
-        LCX_LAUNCH(e, (k_vterm_beard77<false>), div_up(e->n_part, TPB), TPB, 0, e->n_part, int(only_invalid), s.rw2.p, s.ijk.p, cells, e->vt0.p, s.vt.p, bins);
+        LCX_LAUNCH(e, (k_vterm_beard77<false>), div_up(e->n_part, TPB), TPB, 0, e->n_part, int(only_invalid), s.rw2.p, s.ijk.p, cells, e->vt0.p, s.vt.p, bins, n_large);
       return;
     }
     LCX_LAUNCH(e, k_vterm, div_up(e->n_part, TPB), TPB, 0, e->n_part, e->cfg.terminal_velocity, int(only_invalid),
-               s.rw2.p, s.ijk.p, e->T.p, e->p.p, e->rhod.p, e->eta.p, e->vt0.p, s.vt.p);
+               s.rw2.p, s.ijk.p, e->T.p, e->p.p, e->rhod.p, e->eta.p, e->vt0.p, s.vt.p, n_large);
   }
 
   void sstp_percell_step(lcx_engine *e, int step, int sstp, bool var_rho)

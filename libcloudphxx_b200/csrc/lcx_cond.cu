@@ -155,15 +155,28 @@ namespace lcx
 #define LCX_COND_RANGE_MAX 16
 #endif
     constexpr int RANGE_MAX = LCX_COND_RANGE_MAX;
-    template <int MODE, bool LAZY>
-    __global__ void __launch_bounds__(RTPB, LCX_COND_RANGE_MINB) k_cond_range(idx_t c_begin, idx_t n_cell, int run, const uint32_t *__restrict__ off, real_t dt, real_t RH_max, cond_args a,
-                                                       int n_dims, const real_t *__restrict__ dv, int first_step, int keep_after,
-                                                       real_t *__restrict__ rw_mom3, real_t *__restrict__ drw_mom3,
-                                                       real_t *__restrict__ th, real_t *__restrict__ rv, lazy_args z)
+    // CLASSED (k_cond_classed): the droplets of a run are first split into two classes by size - drizzle / rain drops (rw > 40 um:
+    // Re > 1, the branch of the ventilation factors with a log / exp pair and full cube roots) and everything else - and each class
+    // is walked in rounds of its own (a 2-byte order list per run in shared memory, filled from both ends by ballot compaction,
+    // ascending inside each class so that the cell index stays non-decreasing along a round).  In the plain order a round of 32
+    // holds a few large drops among aerosol and cloud droplets: the expensive branches then run at 5-6 of 32 lanes and everybody
+    // waits (ncu on the rain-laden cfg5 slab: 13.6 of 32 lanes per instruction, a quarter of the instructions in Re^0.077).  Same
+    // arithmetic per droplet: wet radii are bit-identical to the plain order; a cell's droplets are summed in another order (th, rv
+    // agree to rounding, like between the other work distributions).  The host picks the variant from the number of large drops
+    // the fall-speed pass of the previous step counted (dev_scalars::n_large), so a given run always takes the same sequence of variants.
+    constexpr int ORD_CAP = 1024;                       // longest run (SDs) the order list holds; longer runs keep the plain order
+#define LCX_LARGE_RW2 real_t(1.6e-9)                 // (40 um)^2
+
+    template <int MODE, bool LAZY, bool CLASSED>
+    __device__ __forceinline__ void cond_range_body(idx_t c_begin, idx_t n_cell, int run, const uint32_t *__restrict__ off, real_t dt, real_t RH_max, const cond_args &a,
+                                                    int n_dims, const real_t *__restrict__ dv, int first_step, int keep_after,
+                                                    real_t *__restrict__ rw_mom3, real_t *__restrict__ drw_mom3,
+                                                    real_t *__restrict__ th, real_t *__restrict__ rv, const lazy_args &z)
     {
       constexpr int WARPS = RTPB / 32;
       __shared__ cond_cell_consts<real_t> s_k[WARPS][RANGE_MAX];
       __shared__ real_t s_m[WARPS][RANGE_MAX][2];
+      __shared__ unsigned short s_ord[WARPS][CLASSED ? ORD_CAP : 1];
       const int w = threadIdx.x / 32, l = threadIdx.x % 32;
       // cells [c_begin, n_cell): the whole grid, or one chunk of it whose first cell is a multiple of `run` (same runs either way)
       const size_t c0_ = size_t(c_begin) + (size_t(blockIdx.x) * WARPS + w) * size_t(run);
@@ -177,10 +190,49 @@ namespace lcx
       }
       __syncwarp();
       const uint32_t b = off[c0], en = off[c0 + nc];
-      for (uint32_t base = b; base < en; base += 32)
+      // the two classes: [0, n0) of the order list ascending, the large drops from its far end downwards
+      uint32_t n0 = 0, n1 = 0, rounds0 = 0, rounds = 0;
+      bool ordered = false;
+      if (CLASSED)
       {
-        const uint32_t i = base + l;
-        const bool act = i < en;
+        const uint32_t len = en - b;
+        const unsigned lt = (1u << l) - 1u;
+        ordered = len <= uint32_t(ORD_CAP);
+        n0 = len;
+        if (ordered)
+        {
+          n0 = 0;
+          for (uint32_t base = 0; base < len; base += 32)
+          {
+            const uint32_t q = base + l;
+            bool big = false, small = false;
+            if (q < len)
+            {
+              const real_t r2 = LAZY ? z.rw2[z.perm[b + q]] : a.rw2[b + q];
+              big = r2 > LCX_LARGE_RW2;
+              small = !big;
+            }
+            const unsigned m_big = __ballot_sync(0xffffffffu, big), m_small = __ballot_sync(0xffffffffu, small);
+            if (big) s_ord[w][len - 1 - (n1 + __popc(m_big & lt))] = (unsigned short)q;
+            if (small) s_ord[w][n0 + __popc(m_small & lt)] = (unsigned short)q;
+            n0 += __popc(m_small); n1 += __popc(m_big);
+          }
+          __syncwarp();
+        }
+        rounds0 = (n0 + 31) / 32; rounds = rounds0 + (n1 + 31) / 32;
+      }
+      // storage order: rounds of 32 consecutive SDs; class order: the rounds of the first class, then those of the large drops
+      for (uint32_t r = 0, base = b; CLASSED ? r < rounds : base < en; ++r, base += 32)
+      {
+        uint32_t i = base + l;
+        bool act = i < en;
+        if (CLASSED)
+        {
+          const bool second = r >= rounds0;
+          const uint32_t q = (second ? r - rounds0 : r) * 32 + l;
+          act = q < (second ? n1 : n0);
+          i = b + (ordered ? (act ? uint32_t(s_ord[w][second ? (en - b) - 1 - q : q]) : 0u) : q);
+        }
         int ci = RANGE_MAX;                           // idle lanes sit behind the last SD: keys stay non-decreasing
         real_t mb = 0, ma = 0;
         if (act)
@@ -233,6 +285,20 @@ namespace lcx
         th[c] = th_c - drv * d_th_d_rv(cl.T, th_c);
       }
     }
+
+    template <int MODE, bool LAZY>
+    __global__ void __launch_bounds__(RTPB, LCX_COND_RANGE_MINB) k_cond_range(idx_t c_begin, idx_t n_cell, int run, const uint32_t *__restrict__ off, real_t dt, real_t RH_max, cond_args a,
+                                                       int n_dims, const real_t *__restrict__ dv, int first_step, int keep_after,
+                                                       real_t *__restrict__ rw_mom3, real_t *__restrict__ drw_mom3,
+                                                       real_t *__restrict__ th, real_t *__restrict__ rv, lazy_args z)
+    { cond_range_body<MODE, LAZY, false>(c_begin, n_cell, run, off, dt, RH_max, a, n_dims, dv, first_step, keep_after, rw_mom3, drw_mom3, th, rv, z); }
+
+    template <int MODE, bool LAZY>
+    __global__ void __launch_bounds__(RTPB, LCX_COND_RANGE_MINB) k_cond_classed(idx_t c_begin, idx_t n_cell, int run, const uint32_t *__restrict__ off, real_t dt, real_t RH_max, cond_args a,
+                                                       int n_dims, const real_t *__restrict__ dv, int first_step, int keep_after,
+                                                       real_t *__restrict__ rw_mom3, real_t *__restrict__ drw_mom3,
+                                                       real_t *__restrict__ th, real_t *__restrict__ rv, lazy_args z)
+    { cond_range_body<MODE, LAZY, true>(c_begin, n_cell, run, off, dt, RH_max, a, n_dims, dv, first_step, keep_after, rw_mom3, drw_mom3, th, rv, z); }
 
     // ---- staged variant of k_cond_range (TOMS 748 only) --------------------------------------------------------------------------------
     // A round of k_cond_range costs as many growth-law evaluations as its slowest droplet needs (5.1 on the bench workload) while the
@@ -460,6 +526,7 @@ namespace lcx
     }
 
     int g_solver = -1;
+    int g_classed = -2;        // -2: not read yet; -1 automatic, 0 never, 1 always
     int g_staged = -1;         // -1: not read yet ($LCX_COND_STAGED, default on); 0 / 1
     int g_layout = -2;         // -2: not read yet; -1: 8 lanes per cell; 0: automatic; 1..RANGE_MAX: cells per warp of k_cond_range
   }
@@ -501,6 +568,13 @@ namespace lcx
     const int run = e->max_count <= FUSED_MAX ? range_run(e) : 0;
     return run > 0 ? run * (RTPB / 32) : 0;
   }
+
+  int cond_classed()
+  {
+    if (g_classed == -2) { const char *v = std::getenv("LCX_COND_CLASSED"); g_classed = !v || !v[0] ? -1 : v[0] == '1' ? 1 : v[0] == '0' ? 0 : -1; }
+    return g_classed;
+  }
+  void set_cond_classed(int mode) { g_classed = mode > 0 ? 1 : mode == 0 ? 0 : -1; }
 
   int cond_staged()
   {
@@ -563,18 +637,29 @@ namespace lcx
       const idx_t c_begin = windowed ? e->win_begin : 0, c_end = windowed ? e->win_end : g.n_cell;
       if (windowed && (c_begin % idx_t(run) != 0 || c_end <= c_begin || c_end > g.n_cell)) throw error("lcx_cond: cell window not aligned to the kernel's runs");
       const unsigned blocks = div_up(div_up(c_end - c_begin, run), RTPB / 32);
+      // droplets walked class by class when the previous call counted enough large drops (more than one in 64; cond_classed())
+      const int cls = cond_classed();
+      const bool classed = cls == 1 || (cls < 0 && e->n_large * 64 * 64 > e->n_part);      // n_large: counted in one CTA of 64 (lcx_cells.cu)
       lazy_args z = {};
       if (e->pending & lcx_engine::PENDING_ATTR)      // consume the pending re-layout: read through the permutation from the old buffer set, write everything into the new one
       {
         sd_arrays &o = e->A();
         z = {e->pending_perm.p, o.rw2.p, o.rd3.p, o.kpa.p, o.vt.p, o.n.p, s.rd3.p, s.kpa.p, s.vt.p, s.n.p};
         if (c_end == g.n_cell) e->pending &= ~unsigned(lcx_engine::PENDING_ATTR);
-        LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_cond_range<M, true>), blocks, RTPB, 0, c_begin, c_end, run, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p,
-                                          int(step == 0), keep_after, e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p, z));
+        if (classed)
+          LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_cond_classed<M, true>), blocks, RTPB, 0, c_begin, c_end, run, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p,
+                                            int(step == 0), keep_after, e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p, z))
+        else
+          LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_cond_range<M, true>), blocks, RTPB, 0, c_begin, c_end, run, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p,
+                                            int(step == 0), keep_after, e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p, z))
         return;
       }
-      LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_cond_range<M, false>), blocks, RTPB, 0, c_begin, c_end, run, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p,
-                                        int(step == 0), keep_after, e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p, z));
+      if (classed)
+        LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_cond_classed<M, false>), blocks, RTPB, 0, c_begin, c_end, run, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p,
+                                          int(step == 0), keep_after, e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p, z))
+      else
+        LCX_BY_COND_MODE(mode, LCX_LAUNCH(e, (k_cond_range<M, false>), blocks, RTPB, 0, c_begin, c_end, run, e->cell_off.p, dt_sub, RH_max, a, g.n_dims, e->dv.p,
+                                          int(step == 0), keep_after, e->rw_mom3.p, e->drw_mom3.p, e->th.p, e->rv.p, z))
       return;
     }
     if (windowed) throw error("lcx_cond: a cell window needs the run-per-warp kernel (lcx_cond_granule says when)");

@@ -112,7 +112,8 @@ namespace lcx
     unsigned long long n_collisions, n_pairs_collided;
     double puddle[8];               // liq_vol, dry_vol, liq_num, prtcl_num, accumulated; [4], [5]: dry volume / SDs lost through the lid
     unsigned long long rcyc_zero, rcyc_one, rcyc_max;   // SDs with n == 0, with n == 1, largest n (recycling)
-    unsigned int n_big, pad2;       // cells holding more than BIG_CELL super-droplets (listed in lcx_engine::big_cells)
+    unsigned int n_big;             // cells holding more than BIG_CELL super-droplets (listed in lcx_engine::big_cells)
+    unsigned int n_large;           // drops with rw > 40 um counted by the condensation kernels since the last lcx_post_copy
   };
   constexpr unsigned BIG_CELL = 256;  // largest cell population the per-cell coalescence kernel takes in its usual configuration
 }
@@ -205,6 +206,7 @@ struct lcx_engine
   struct mig_remote { unsigned char *base = nullptr; size_t cap = 0; bool ipc = false; } remote[2];
   cudaEvent_t ev_put = nullptr;
   unsigned mig_seq = 0, halo_seq = 0;   // halo_seq: deliveries of Courant halo planes (lcx_halo_put / lcx_halo_take)
+  size_t n_large = 0;            // dev_scalars::n_large as of the last lcx_post_copy
   size_t keys_ready = 0;         // key[0] / val[0] already hold the re-layout sort keys of SDs [0, keys_ready) (written by k_transport)
 
   lcx::dbuf<lcx::dev_scalars> scalars;
@@ -270,6 +272,8 @@ namespace lcx
   void set_cond_solver(int mode);
   int cond_layout();                      // lcx_set_cond_layout, else $LCX_COND_LAYOUT, else 0 (automatic)
   void set_cond_layout(int cells_per_warp);
+  int cond_classed();                     // lcx_set_cond_classed, else $LCX_COND_CLASSED, else -1 (automatic): droplets walked class by class
+  void set_cond_classed(int mode);
   int cond_staged();                      // lcx_set_cond_staged, else $LCX_COND_STAGED, else on: the phase-grouped variant of the range kernel
   void set_cond_staged(int on);
   void cond(lcx_engine *e, real_t dt_sub, real_t RH_max, int step, int sstp);

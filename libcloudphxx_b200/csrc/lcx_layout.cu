@@ -446,6 +446,8 @@ namespace lcx
     const size_t n_new = e->h_scalars->n_part;
     e->max_count = e->h_scalars->max_count;
     e->n_big = e->h_scalars->n_big;
+    e->n_large = e->h_scalars->n_large;          // counted by this step's condensation; the next step's choice of kernel variant
+    LCX_CUDA(cudaMemsetAsync(&e->scalars.p->n_large, 0, sizeof(unsigned int), e->stream));
 
     const bool lazy = e->lazy_gather && !keep_all && n_new > 0;
     if (n_new)

@@ -81,6 +81,16 @@ def get_cond_layout():
     return int(lib().lcx_get_cond_layout())
 
 
+def set_cond_classed(mode, real="f64"):
+    """order in which the run-per-warp condensation kernel walks a run's droplets: -1 automatic (drizzle / rain drops apart from the
+    rest once the previous step counted enough of them), 0 storage order always, 1 class by class always; include/lcx_b200.h"""
+    lib(real).lcx_set_cond_classed(int(mode))
+
+
+def get_cond_classed(real="f64"):
+    return int(lib(real).lcx_get_cond_classed())
+
+
 def set_cond_staged(on):
     """phase-grouped form of the run-per-warp condensation kernel (opt-in, default off; bit-identical results either way)"""
     lib().lcx_set_cond_staged(int(bool(on)))

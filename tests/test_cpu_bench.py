@@ -46,7 +46,8 @@ def test_roofline_tables_cover_the_kernels_the_profile_names():
     bench.LAZY = False
     for name, per_sd in (("(k_cond_range<M, false>)", 52.0), ("(k_cond_range<M, true>)", 88.0), ("(k_cond_cells<M>)", 48.0), ("k_gather", 136.0),
                          ("k_coal_small", 76.0), ("k_transport<false>", 72.0), ("k_transport<true>", 76.0), ("(k_vterm_beard77<true>)", 24.0),
-                         ("k_mv_count", 4.0), ("k_cond_staged<true>", 88.0), ("k_cond_staged<false>", 52.0)):
+                         ("k_mv_count", 4.0), ("k_cond_staged<true>", 88.0), ("k_cond_staged<false>", 52.0),
+                         ("(k_cond_classed<M, true>)", 96.0), ("(k_cond_classed<M, false>)", 60.0)):
         assert bench.kernel_bytes(name) == per_sd, name
     bench.LAZY = True
     assert bench.kernel_bytes("k_gather") == 12.0        # gather-on-read: only the storage index is left to the gather kernel

@@ -16,6 +16,7 @@ def run(b200, staged, layout, monkeypatch, lazy="1", steps=6, **box):
     monkeypatch.setenv("LCX_LAZY_GATHER", lazy)
     E.set_cond_layout(layout)
     E.set_cond_staged(staged)
+    E.set_cond_classed(0)          # the staged kernel sums a cell's droplets in storage order: compare with the plain kernel doing the same
     try:
         kw = dict(nx=6, ny=5, nz=8, sd_conc=40, rain_mode=True)
         kw.update(box)
@@ -31,6 +32,7 @@ def run(b200, staged, layout, monkeypatch, lazy="1", steps=6, **box):
     finally:
         E.set_cond_layout(0)
         E.set_cond_staged(False)
+        E.set_cond_classed(-1)
 
 
 def same(a, b):
