@@ -10,7 +10,8 @@ def main(path, skip=0):
     rows = rows[skip:]
     agg = OrderedDict()
     for r in rows:
-        name = r[4].split("(")[0].replace("<unnamed>::", "").replace("lcx::", "").replace("void ", "")
+        name = r[4].split("(")[0].replace("void ", "")
+        name = name[name.rindex("::") + 2:] if "::" in name else name          # lcx::<unnamed>::k_name<...>
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1
         a[1] += float(r[14])
