@@ -1243,6 +1243,34 @@ def slab_nx(nx, rank, size):                            # detail::get_dev_nx
     return int(nx / size + .5) if rank < size - 1 else nx - rank * int(nx / size + .5)
 
 
+def xchng_courants_rule(n_dims, nx, ny, nz, halo=2):
+    """Which values of a slab's halo-extended Courant arrays travel to which neighbour, as flat offsets and counts: the index
+    arithmetic of src/impl/distributed_memory/particles_impl_xchng_courants.ipp:26-52 (arrays laid out as init_sync.ipp:29-44:
+    Cx (nx + 2 h + 1) x-planes, Cy / Cz (nx + 2 h) x-planes, z fastest).  Returns {name: (plane_size, send_to_lft, send_to_rgt,
+    recv_from_lft, recv_from_rgt, count)}: `count` values starting at send_to_lft go to the left neighbour, which stores them at
+    ITS recv_from_rgt (and the other way round).  Test infrastructure (tests/test_cpu_distributed.py), restated from the reference;
+    the product's engine does the same between GPUs (csrc/lcx_transport.cu halo_put / halo_take)."""
+    ny1, nz1 = max(ny, 1), max(nz, 1)
+    n_cell = nx * ny1 * nz1
+    out = {}
+    if n_dims >= 1:
+        plane = 1 if n_dims == 1 else nz if n_dims == 2 else nz * ny
+        halo_x = halo * plane
+        size = (nx + 2 * halo + 1) * plane
+        out["Cx"] = (plane, (halo + 1) * plane, n_cell, 0, size - halo_x, halo_x)                    # :26-31, :45-46, halo_x values
+    if n_dims >= 2:
+        plane = (nz + 1) if n_dims == 2 else (nz + 1) * ny
+        halo_z = halo * plane
+        size = (nx + 2 * halo) * plane
+        out["Cz"] = (plane, halo_z, nx * plane, 0, size - halo_z, halo_z)                             # :33-37, :47-48
+    if n_dims == 3:
+        plane = (ny + 1) * nz
+        halo_y = halo * plane
+        size = (nx + 2 * halo) * plane
+        out["Cy"] = (plane, halo_y, nx * plane, 0, size - halo_y, halo_y)                             # :39-42, :49-50
+    return out
+
+
 class SlabParticles:
     """The periodic domain cut into `size` x-slabs, each an independent Particles object in its own local coordinates (x0 = 0 for every
     slab but the first), super-droplets that cross a slab face handed to the neighbour once per step.
