@@ -134,7 +134,9 @@ int  lcx_cells_get_part(lcx_engine *e, int field, int64_t offset, void *dst, int
 /* those cells alone, and lcx_cells_get_part read-backs do not hold up the next chunk's kernels.  The host layer uploads chunk    */
 /* k + 1 and reads chunk k back while chunk k + 1 computes: the copies of step_sync hide behind the condensation kernel.          */
 /* Windows must start at multiples of lcx_cond_granule() cells (0: the kernel in use cannot be windowed), arrive in order, cover   */
-/* the grid, and be cleared with (0, 0).  Results are bit-identical to the un-chunked step.                                       */
+/* the grid, and be cleared with (0, 0).  Results are bit-identical to the un-chunked step.  Consecutive windows run on two         */
+/* alternating streams (they touch disjoint cells and SDs); clearing the window joins them.  No reference counterpart: the        */
+/* reference's step_sync is upload -> step_cond -> read-back in sequence (src/particles_step.ipp:32-336).                          */
 int  lcx_set_cell_window(lcx_engine *e, int64_t c_begin, int64_t c_end);
 int  lcx_cond_granule(lcx_engine *e, int64_t *cells);
 int  lcx_pointer_on_device(const void *p, int *on_device);      /* 1: device (or managed) memory, 0: host memory           */
